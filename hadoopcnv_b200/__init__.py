@@ -1,0 +1,12 @@
+"""hadoopcnv_b200 -- B200-native (sm_100a CUDA) implementation of HadoopCNV's data-parallel hot path:
+read binning (depth caller + binner) and per-chromosome HMM segmentation, behind the C ABI in include/hcnv.h.
+
+Importing the package does not load CUDA; creating a `Context` does and fails loudly without a GPU or
+without the built libhcnv.so.  There is no CPU fallback.
+"""
+from ._lib import HcnvError, LIB_PATH, build  # noqa: F401
+from .api import (BinsResult, Contig, Context, config_load, format_double, format_float, pack_blocks,  # noqa: F401
+                  pack_long_blocks, write_bins_text, write_results_text)
+
+__all__ = ["Context", "Contig", "BinsResult", "HcnvError", "pack_blocks", "pack_long_blocks", "config_load",
+           "format_float", "format_double", "write_bins_text", "write_results_text", "build", "LIB_PATH"]

@@ -1,0 +1,113 @@
+"""ctypes binding of libhcnv.so (include/hcnv.h).  Fails loudly when the CUDA library is missing:
+there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhcnv.so")
+
+HCNV_OK = 0
+HCNV_VITERBI_SKIPPED = 1
+HCNV_E_INVALID, HCNV_E_CUDA, HCNV_E_NOMEM, HCNV_E_RANGE, HCNV_E_UNSORTED = -1, -2, -3, -4, -5
+HCNV_E_INCONSISTENT, HCNV_E_NO_MINIMUM, HCNV_E_IO, HCNV_E_PARSE, HCNV_E_CAPACITY, HCNV_E_INTERNAL = -6, -7, -8, -9, -10, -11
+HCNV_SHORT_MAX = 4095
+HCNV_SEG_SEQUENTIAL = 1
+
+
+class HcnvError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__("libhcnv status %d: %s" % (status, message))
+        self.status = status
+
+
+class BinParams(C.Structure):
+    _fields_ = [("bin_width", C.c_int32), ("max_block_len", C.c_int32), ("mapping_quality_threshold", C.c_double),
+                ("tile_bins", C.c_int32), ("flags", C.c_int32)]
+
+
+class ContigInput(C.Structure):
+    _fields_ = [("length", C.c_int32),
+                ("blocks", C.c_void_p), ("n_blocks", C.c_int64),
+                ("long_blocks", C.c_void_p), ("n_long", C.c_int64),
+                ("snp_pos1", C.c_void_p), ("snp_zyg", C.c_void_p), ("n_snp", C.c_int64),
+                ("obs", C.c_void_p), ("n_obs", C.c_int64)]
+
+
+class Bins(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("bin", C.c_void_p), ("start", C.c_void_p), ("end", C.c_void_p),
+                ("median", C.c_void_p), ("mse", C.c_void_p), ("total", C.c_void_p), ("n", C.c_void_p),
+                ("contig_offset", C.c_void_p)]
+
+
+class SegmentProblem(C.Structure):
+    _fields_ = [("n_markers", C.c_int64), ("median", C.c_void_p), ("mse", C.c_void_p), ("total", C.c_void_p),
+                ("n", C.c_void_p), ("lambda1", C.c_float), ("lambda2", C.c_float),
+                ("scaled", C.c_void_p), ("state", C.c_void_p), ("cn", C.c_void_p),
+                ("mean_coverage", C.c_float), ("sd", C.c_float), ("lambda1_used", C.c_float),
+                ("lambda2_used", C.c_float), ("final_loss", C.c_float), ("last_row", C.c_float * 6),
+                ("status", C.c_int32), ("want_sd", C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [("bam_file", C.c_char * 1024), ("vcf_file", C.c_char * 1024),
+                ("run_depth_caller", C.c_int32), ("run_global_sort", C.c_int32), ("init_vcf_lookup", C.c_int32),
+                ("run_binner", C.c_int32), ("run_cnv_caller", C.c_int32), ("run_sr_pe_extracter", C.c_int32),
+                ("bam_file_reducers", C.c_int32), ("text_file_reducers", C.c_int32), ("reducer_tasks", C.c_int32),
+                ("abberation_penalty", C.c_float), ("transition_penalty", C.c_float)]
+
+
+# every symbol include/hcnv.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "hcnv_abi_sizes", "hcnv_ctx_create", "hcnv_ctx_destroy", "hcnv_last_error", "hcnv_strerror", "hcnv_version", "hcnv_ctx_stream",
+    "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_bin_params_default", "hcnv_bin_contigs",
+    "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
+    "hcnv_write_bins_text", "hcnv_write_results_text",
+]
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libhcnv.so in-tree with nvcc for sm_100a (see csrc/Makefile)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc")]
+    if not verbose:
+        cmd.append("-s")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libhcnv.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C hadoopcnv_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.hcnv_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.hcnv_ctx_destroy.argtypes = [C.c_void_p]
+    L.hcnv_ctx_destroy.restype = None
+    L.hcnv_last_error.argtypes = [C.c_void_p]
+    L.hcnv_last_error.restype = C.c_char_p
+    L.hcnv_strerror.argtypes = [C.c_int]
+    L.hcnv_strerror.restype = C.c_char_p
+    L.hcnv_ctx_stream.argtypes = [C.c_void_p]
+    L.hcnv_ctx_stream.restype = C.c_void_p
+    L.hcnv_ctx_kernel_launches.argtypes = [C.c_void_p]
+    L.hcnv_ctx_kernel_launches.restype = C.c_int64
+    L.hcnv_ctx_synchronize.argtypes = [C.c_void_p]
+    L.hcnv_bin_params_default.argtypes = [C.POINTER(BinParams)]
+    L.hcnv_bin_params_default.restype = None
+    L.hcnv_bin_contigs.argtypes = [C.c_void_p, C.POINTER(BinParams), C.c_int32, C.POINTER(ContigInput), C.POINTER(Bins)]
+    L.hcnv_bins_to_hmm_input.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hcnv_segment_batch.argtypes = [C.c_void_p, C.c_float, C.c_int32, C.POINTER(SegmentProblem), C.c_int32]
+    L.hcnv_config_load.argtypes = [C.c_char_p, C.POINTER(Config)]
+    L.hcnv_format_float.argtypes = [C.c_float, C.c_char_p]
+    L.hcnv_format_double.argtypes = [C.c_double, C.c_char_p]
+    L.hcnv_write_bins_text.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64] + [C.c_void_p] * 7
+    L.hcnv_write_results_text.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64] + [C.c_void_p] * 6
+    _lib = L
+    return L

@@ -1,0 +1,288 @@
+"""Array-level Python host API over the C ABI (include/hcnv.h).
+
+Inputs/outputs are either numpy arrays (host buffers: the library copies them to and from the GPU) or
+torch CUDA tensors (resident in HBM: the kernels read and write them in place).  torch is used only for
+device memory and streams; all compute happens in libhcnv.so's hand-written sm_100a kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+BLOCK_DTYPE = np.dtype([("start0", "<i4"), ("len_mapq", "<u4")])
+LONG_BLOCK_DTYPE = np.dtype([("start0", "<i4"), ("len", "<i4"), ("mapq", "<i4"), ("reserved", "<i4")])
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x) -> Optional[int]:
+    if x is None:
+        return None
+    if _is_torch(x):
+        assert x.is_contiguous()
+        return x.data_ptr()
+    assert x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data
+
+
+def _len(x) -> int:
+    if x is None:
+        return 0
+    return int(x.shape[0])
+
+
+def pack_blocks(start0, length, mapq=None) -> np.ndarray:
+    """Host helper: numpy arrays -> hcnv_block records (len | mapq << 24)."""
+    start0 = np.asarray(start0)
+    length = np.asarray(length).astype(np.uint32)
+    if (length > L.HCNV_SHORT_MAX).any():
+        raise ValueError("short blocks must be <= HCNV_SHORT_MAX bases; route longer ones to long_blocks")
+    b = np.empty(len(start0), dtype=BLOCK_DTYPE)
+    b["start0"] = start0
+    mq = np.zeros(len(start0), np.uint32) if mapq is None else np.asarray(mapq).astype(np.uint32)
+    b["len_mapq"] = length | (mq << np.uint32(24))
+    return b
+
+
+def pack_long_blocks(start0, length, mapq=None) -> np.ndarray:
+    b = np.zeros(len(start0), dtype=LONG_BLOCK_DTYPE)
+    b["start0"] = start0
+    b["len"] = length
+    if mapq is not None:
+        b["mapq"] = mapq
+    return b
+
+
+@dataclass
+class Contig:
+    """One reference sequence's inputs (hcnv_contig_input)."""
+    length: int
+    blocks: object = None          # hcnv_block records, sorted by start0 (numpy structured / torch int32 [n,2] or int64 [n])
+    long_blocks: object = None     # hcnv_long_block records
+    snp_pos1: object = None        # int32, ascending unique
+    snp_zyg: object = None         # int8 in {0,-1,-2}
+    obs: object = None             # uint32 (torch: int32) snp_index << 4 | base4
+
+
+@dataclass
+class BinsResult:
+    bin: object
+    start: object
+    end: object
+    median: object
+    mse: object        # [n, 6] float64
+    total: object
+    n: object
+    contig_offset: np.ndarray   # int64 [n_contigs + 1]
+
+    def contig(self, c: int) -> "BinsResult":
+        a, b = int(self.contig_offset[c]), int(self.contig_offset[c + 1])
+        return BinsResult(self.bin[a:b], self.start[a:b], self.end[a:b], self.median[a:b], self.mse[a:b],
+                          self.total[a:b], self.n[a:b], np.array([0, b - a], np.int64))
+
+    def __len__(self):
+        return int(self.contig_offset[-1])
+
+
+class Context:
+    """hcnv_ctx: one GPU, one stream, grow-only scratch.  Single-threaded like a Hadoop task instance."""
+
+    def __init__(self, device: int = 0):
+        self._lib = L.lib()
+        h = C.c_void_p()
+        st = self._lib.hcnv_ctx_create(device, C.byref(h))
+        if st != 0:
+            raise L.HcnvError(st, "hcnv_ctx_create(device=%d): %s (a CUDA device is required; there is no CPU fallback)"
+                              % (device, self._lib.hcnv_strerror(st).decode()))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hcnv_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st < 0:
+            raise L.HcnvError(st, self._lib.hcnv_last_error(self._h).decode() or self._lib.hcnv_strerror(st).decode())
+        return st
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.hcnv_ctx_stream(self._h) or 0)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.hcnv_ctx_kernel_launches(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.hcnv_ctx_synchronize(self._h))
+
+    # ------------------------------------------------------------------ B1
+    def bin_contigs(self, contigs: Sequence[Contig], bin_width: int = 100, max_block_len: int = 0,
+                    mapping_quality_threshold: float = 0.0, tile_bins: int = 0, out: Optional[BinsResult] = None,
+                    capacity: Optional[int] = None) -> BinsResult:
+        """hcnv_bin_contigs.  With numpy inputs returns numpy outputs; with torch CUDA inputs returns torch CUDA
+        outputs (allocate once and pass them back in as `out` to keep the timed region allocation-free)."""
+        n = len(contigs)
+        arr = (L.ContigInput * n)()
+        on_device = False
+        for i, c in enumerate(contigs):
+            arr[i].length = int(c.length)
+            arr[i].blocks, arr[i].n_blocks = _ptr(c.blocks), _len(c.blocks)
+            arr[i].long_blocks, arr[i].n_long = _ptr(c.long_blocks), _len(c.long_blocks)
+            arr[i].snp_pos1, arr[i].snp_zyg, arr[i].n_snp = _ptr(c.snp_pos1), _ptr(c.snp_zyg), _len(c.snp_pos1)
+            arr[i].obs, arr[i].n_obs = _ptr(c.obs), _len(c.obs)
+            for x in (c.blocks, c.long_blocks, c.snp_pos1, c.obs):
+                if x is not None and _is_torch(x):
+                    on_device = True
+        cap = capacity if capacity is not None else sum(int(c.length) // bin_width + 1 for c in contigs)
+        if out is None:
+            out = self.alloc_bins(cap, on_device, n)
+        b = L.Bins()
+        b.capacity = cap
+        b.bin, b.start, b.end, b.median = _ptr(out.bin), _ptr(out.start), _ptr(out.end), _ptr(out.median)
+        b.mse, b.total, b.n = _ptr(out.mse), _ptr(out.total), _ptr(out.n)
+        off = np.zeros(n + 1, np.int64)
+        b.contig_offset = off.ctypes.data
+        p = L.BinParams()
+        self._lib.hcnv_bin_params_default(C.byref(p))
+        p.bin_width, p.max_block_len, p.mapping_quality_threshold, p.tile_bins = bin_width, max_block_len, mapping_quality_threshold, tile_bins
+        self._check(self._lib.hcnv_bin_contigs(self._h, C.byref(p), n, arr, C.byref(b)))
+        nb = int(off[-1])
+        return BinsResult(out.bin[:nb], out.start[:nb], out.end[:nb], out.median[:nb], out.mse[:nb], out.total[:nb],
+                          out.n[:nb], off)
+
+    def alloc_bins(self, cap: int, on_device: bool, n_contigs: int = 1) -> BinsResult:
+        if on_device:
+            import torch
+            dev = torch.device("cuda", self.device)
+            return BinsResult(torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev),
+                              torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.float32, device=dev),
+                              torch.empty((cap, 6), dtype=torch.float64, device=dev), torch.empty(cap, dtype=torch.float64, device=dev),
+                              torch.empty(cap, dtype=torch.int32, device=dev), np.zeros(n_contigs + 1, np.int64))
+        return BinsResult(np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float32),
+                          np.empty((cap, 6), np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32),
+                          np.zeros(n_contigs + 1, np.int64))
+
+    # ------------------------------------------------------------------ between B1 and B2
+    def bins_to_hmm_input(self, mse, total=None):
+        """Double.toString -> Float.valueOf round trip of BinReducer's mse/total columns (hcnv_bins_to_hmm_input)."""
+        n = _len(mse)
+        if _is_torch(mse):
+            import torch
+            m32 = torch.empty((n, 6), dtype=torch.float32, device=mse.device)
+            t32 = torch.empty(n, dtype=torch.float32, device=mse.device) if total is not None else None
+        else:
+            mse = np.ascontiguousarray(mse, dtype=np.float64)
+            total = None if total is None else np.ascontiguousarray(total, dtype=np.float64)
+            m32 = np.empty((n, 6), np.float32)
+            t32 = np.empty(n, np.float32) if total is not None else None
+        self._check(self._lib.hcnv_bins_to_hmm_input(self._h, n, _ptr(mse), _ptr(total), _ptr(m32), _ptr(t32)))
+        return m32, t32
+
+    # ------------------------------------------------------------------ B2
+    def segment_batch(self, problems: List[dict], alpha: float = 0.5, flags: int = 0, raise_on_exit: bool = True) -> List[dict]:
+        """hcnv_segment_batch.  Each problem: dict(median, mse, total, n, lambda1, lambda2[, want_sd][, scaled/state/cn
+        preallocated outputs]).  Returns one dict per problem with scaled/state/cn and the scalar outputs."""
+        k = len(problems)
+        arr = (L.SegmentProblem * k)()
+        keep = []
+        for i, q in enumerate(problems):
+            med = q["median"]
+            M = _len(med)
+            if _is_torch(med):
+                import torch
+                scaled = q.get("scaled", None)
+                state = q.get("state", None)
+                cn = q.get("cn", None)
+                if scaled is None:
+                    scaled = torch.empty(M, dtype=torch.float32, device=med.device)
+                if state is None:
+                    state = torch.empty(M, dtype=torch.int32, device=med.device)
+                if cn is None:
+                    cn = torch.empty(M, dtype=torch.int32, device=med.device)
+                mse, total, n = q["mse"], q["total"], q["n"]
+            else:
+                med = np.ascontiguousarray(med, dtype=np.float32)
+                mse = np.ascontiguousarray(q["mse"], dtype=np.float32).reshape(M, 6)
+                total = np.ascontiguousarray(q["total"], dtype=np.float32)
+                n = np.ascontiguousarray(q["n"], dtype=np.int32)
+                scaled, state, cn = np.empty(M, np.float32), np.empty(M, np.int32), np.empty(M, np.int32)
+            keep.append((med, mse, total, n, scaled, state, cn))
+            a = arr[i]
+            a.n_markers = M
+            a.median, a.mse, a.total, a.n = _ptr(med), _ptr(mse), _ptr(total), _ptr(n)
+            a.lambda1, a.lambda2 = float(q["lambda1"]), float(q["lambda2"])
+            a.scaled, a.state, a.cn = _ptr(scaled), _ptr(state), _ptr(cn)
+            a.want_sd = int(q.get("want_sd", 0))
+        st = self._lib.hcnv_segment_batch(self._h, float(alpha), k, arr, flags)
+        if st < 0 and (raise_on_exit or st != L.HCNV_E_NO_MINIMUM):
+            self._check(st)
+        res = []
+        for i in range(k):
+            a = arr[i]
+            res.append(dict(scaled=keep[i][4], state=keep[i][5], cn=keep[i][6], mean_coverage=np.float32(a.mean_coverage),
+                            sd=np.float32(a.sd), lambda1=np.float32(a.lambda1_used), lambda2=np.float32(a.lambda2_used),
+                            final_loss=np.float32(a.final_loss), last_row=np.array(list(a.last_row), np.float32),
+                            status=int(a.status)))
+        return res
+
+
+# ---------------------------------------------------------------------- B3 (host only, no GPU needed)
+def format_float(v) -> str:
+    buf = C.create_string_buffer(64)
+    L.lib().hcnv_format_float(float(np.float32(v)), buf)
+    return buf.value.decode()
+
+
+def format_double(v) -> str:
+    buf = C.create_string_buffer(64)
+    L.lib().hcnv_format_double(float(v), buf)
+    return buf.value.decode()
+
+
+def config_load(path: str) -> dict:
+    """UserConfig.init + getters (UserConfig.java:25-141)."""
+    c = L.Config()
+    st = L.lib().hcnv_config_load(path.encode(), C.byref(c))
+    if st != 0:
+        raise L.HcnvError(st, "hcnv_config_load(%s): %s" % (path, L.lib().hcnv_strerror(st).decode()))
+    return dict(BAM_FILE=c.bam_file.decode(), VCF_FILE=c.vcf_file.decode(),
+                RUN_DEPTH_CALLER=bool(c.run_depth_caller), RUN_GLOBAL_SORT=bool(c.run_global_sort),
+                INIT_VCF_LOOKUP=bool(c.init_vcf_lookup), RUN_BINNER=bool(c.run_binner), RUN_CNV_CALLER=bool(c.run_cnv_caller),
+                RUN_SR_PE_EXTRACTER=bool(c.run_sr_pe_extracter), BAM_FILE_REDUCERS=c.bam_file_reducers,
+                TEXT_FILE_REDUCERS=c.text_file_reducers, REDUCER_TASKS=c.reducer_tasks,
+                ABBERATION_PENALTY=np.float32(c.abberation_penalty), TRANSITION_PENALTY=np.float32(c.transition_penalty))
+
+
+def write_bins_text(path: str, chrom: str, bins: BinsResult, append: bool = False):
+    st = L.lib().hcnv_write_bins_text(path.encode(), int(append), chrom.encode(), len(bins.bin),
+                                      _ptr(np.ascontiguousarray(bins.bin)), _ptr(np.ascontiguousarray(bins.start)),
+                                      _ptr(np.ascontiguousarray(bins.end)), _ptr(np.ascontiguousarray(bins.median)),
+                                      _ptr(np.ascontiguousarray(bins.mse)), _ptr(np.ascontiguousarray(bins.total)),
+                                      _ptr(np.ascontiguousarray(bins.n)))
+    if st != 0:
+        raise L.HcnvError(st, "hcnv_write_bins_text")
+
+
+def write_results_text(path: str, chrom: str, start, end, scaled, state, cn, mse32, append: bool = False):
+    args = [np.ascontiguousarray(start, dtype=np.int32), np.ascontiguousarray(end, dtype=np.int32),
+            np.ascontiguousarray(scaled, dtype=np.float32), np.ascontiguousarray(state, dtype=np.int32),
+            np.ascontiguousarray(cn, dtype=np.int32), np.ascontiguousarray(mse32, dtype=np.float32)]
+    st = L.lib().hcnv_write_results_text(path.encode(), int(append), chrom.encode(), len(args[0]), *[_ptr(a) for a in args])
+    if st != 0:
+        raise L.HcnvError(st, "hcnv_write_results_text")

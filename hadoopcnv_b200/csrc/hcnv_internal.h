@@ -1,0 +1,91 @@
+// hcnv_internal.h -- context, scratch memory and launch helpers shared by the libhcnv translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/hcnv.h"
+
+// A grow-only device buffer owned by the context.
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + 256);
+        if (e == cudaSuccess) cap = bytes + 256;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum { HCNV_NBUF = 24 };
+
+struct hcnv_ctx {
+    int          device = 0;
+    int          sm_count = 0;
+    size_t       smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int64_t      launches = 0;
+    std::string  err;
+    DevBuf       buf[HCNV_NBUF];      // named scratch slots, see the .cu files
+    PinBuf       pin[4];
+};
+
+#define HCNV_CUDA(ctx, call)                                                                   \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            char m__[512];                                                                     \
+            snprintf(m__, sizeof m__, "%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+                     cudaGetErrorString(e__));                                                 \
+            (ctx)->err = m__;                                                                  \
+            return e__ == cudaErrorMemoryAllocation ? HCNV_E_NOMEM : HCNV_E_CUDA;              \
+        }                                                                                      \
+    } while (0)
+
+static inline int hcnv_fail(hcnv_ctx* ctx, int code, const char* msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+// pointer kind: 0 = host pageable, 1 = host pinned, 2 = device (or managed)
+static inline int hcnv_ptr_kind(const void* p) {
+    if (!p) return -1;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 2;
+    if (a.type == cudaMemoryTypeHost) return 1;
+    return 0;
+}
+
+// implemented in bin_kernels.cu / hmm_kernels.cu
+int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t n_contigs,
+                          const hcnv_contig_input* contigs, hcnv_bins* out);
+int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
+                                float* mse_f32, float* total_f32);
+int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems,
+                            int32_t flags);

@@ -1,0 +1,465 @@
+// hmm_kernels.cu -- B2: per-chromosome HMM segmentation, sm_100a.
+//
+// Replaces CnvReducer.reduce (Reducers.java:225-243) and Hmm.java:
+//   init            Hmm.java:341-391   sequential-f32 mean coverage
+//   scale_depth     Hmm.java:121-135
+//   get_sd          Hmm.java:103-119   (only when asked for, or when a penalty is negative)
+//   compute_emission Hmm.java:147-170  (fused into the Viterbi step)
+//   search/run      Hmm.java:311-332   (the "mid < .01" rule)
+//   do_viterbi      Hmm.java:176-238   (exact float32 evaluation order, strict '<', first index wins;
+//                                       the reference's non-chained traceback through the final arg-min state)
+// plus the Double.toString -> Float.valueOf round trip that sits between BinReducer's output and Hmm.init.
+//
+// Compiled with --fmad=false: Java never contracts a*b+c.
+#include "hcnv_internal.h"
+#include <cfloat>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// f64 -> shortest decimal -> f32, exactly, without printing.
+// (float)d with round-to-nearest-even is the answer unless d sits exactly half way between two adjacent
+// floats; then the parse of the PRINTED value decides, i.e. the sign of (shortest decimal - d).
+// ------------------------------------------------------------------------------------------------
+struct Big { uint32_t w[16]; };
+
+__device__ void big_zero(Big& a) { for (int i = 0; i < 16; ++i) a.w[i] = 0; }
+__device__ void big_mul_small(Big& a, uint32_t m) {
+    unsigned long long carry = 0;
+    for (int i = 0; i < 16; ++i) { unsigned long long t = (unsigned long long)a.w[i] * m + carry; a.w[i] = (uint32_t)t; carry = t >> 32; }
+}
+__device__ uint32_t big_div_small(Big& a, uint32_t dv) {   // a /= dv, returns remainder
+    unsigned long long rem = 0;
+    for (int i = 15; i >= 0; --i) { unsigned long long t = (rem << 32) | a.w[i]; a.w[i] = (uint32_t)(t / dv); rem = t % dv; }
+    return (uint32_t)rem;
+}
+__device__ void big_shl(Big& a, int s) {
+    int ws = s >> 5, bs = s & 31;
+    for (int i = 15; i >= 0; --i) {
+        unsigned long long v = 0;
+        if (i - ws >= 0) v = (unsigned long long)a.w[i - ws] << bs;
+        if (bs && i - ws - 1 >= 0) v |= (unsigned long long)a.w[i - ws - 1] >> (32 - bs);
+        a.w[i] = (uint32_t)v;
+    }
+}
+__device__ int big_cmp(const Big& a, const Big& b) {
+    for (int i = 15; i >= 0; --i) { if (a.w[i] != b.w[i]) return a.w[i] < b.w[i] ? -1 : 1; }
+    return 0;
+}
+__device__ void big_sub(Big& a, const Big& b) {       // a -= b (a >= b)
+    long long borrow = 0;
+    for (int i = 0; i < 16; ++i) { long long t = (long long)a.w[i] - b.w[i] - borrow; borrow = t < 0; a.w[i] = (uint32_t)t; }
+}
+__device__ void big_sub_mul(Big& a, const Big& b, uint32_t m) {   // a -= b * m
+    Big t = b; big_mul_small(t, m); big_sub(a, t);
+}
+__device__ bool big_is_zero(const Big& a) { uint32_t o = 0; for (int i = 0; i < 16; ++i) o |= a.w[i]; return o == 0; }
+
+// sign of (shortest round-trip decimal of d) - d, for a positive normal double whose significand has <= 26 bits
+__device__ __noinline__ int shortest_decimal_direction(double d) {
+    unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+    int E = (int)((bits >> 52) & 0x7ff) - 1023;
+    unsigned long long m = (bits & ((1ull << 52) - 1)) | (1ull << 52);
+    int q = E - 52;
+    int tz = __ffsll((long long)m) - 1;
+    m >>= tz; q += tz;                                  // d = m * 2^q, m odd
+    int L = 64 - __clzll((long long)m);
+    Big N; big_zero(N); N.w[0] = (uint32_t)m; N.w[1] = (uint32_t)(m >> 32);
+    Big rhs; big_zero(rhs); rhs.w[0] = 1;
+    int a = 0;
+    if (q < 0) {
+        int k = -q;
+        for (int i = 0; i < k; ++i) { big_mul_small(N, 5); big_mul_small(rhs, 5); }
+        a = 54 - L;
+    } else {
+        big_shl(N, q);
+        int e2 = q + L - 54;
+        if (e2 >= 0) big_shl(rhs, e2); else a = -e2;
+    }
+    // decimal digits of N, most significant first
+    unsigned char dig[160];
+    int D = 0;
+    { Big t = N; while (!big_is_zero(t)) { dig[D++] = (unsigned char)big_div_small(t, 10); } }
+    for (int i = 0; i < D / 2; ++i) { unsigned char t = dig[i]; dig[i] = dig[D - 1 - i]; dig[D - 1 - i] = t; }
+    // P = 10^(D-1)
+    Big P; big_zero(P); P.w[0] = 1;
+    for (int i = 0; i < D - 1; ++i) big_mul_small(P, 10);
+    Big r = N;
+    for (int n = 1; n <= 17; ++n) {
+        if (n >= D) return 0;                          // the full expansion fits: printed value == d
+        big_sub_mul(r, P, dig[n - 1]);                 // r = N mod 10^(D-n), P = 10^(D-n)
+        Big twice = r; big_shl(twice, 1);
+        int c = big_cmp(twice, P);
+        bool up = c > 0 || (c == 0 && (dig[n - 1] & 1));
+        Big err;
+        if (up) { err = P; big_sub(err, r); } else err = r;
+        if (big_is_zero(err)) return 0;
+        Big lhs = err; big_shl(lhs, a);
+        if (big_cmp(lhs, rhs) <= 0) return up ? 1 : -1;
+        big_div_small(P, 10);
+    }
+    return 0;   // 17 digits always round-trip; not reached
+}
+
+__device__ __forceinline__ float f64_text_f32(double d) {
+    float f = __double2float_rn(d);
+    if (!(fabs(d) < 3.0e38) || d == 0.0 || (double)f == d) return f;     // NaN/Inf/huge/zero/exact
+    double ad = fabs(d);
+    float af = fabsf(f);
+    float lo = ((double)af > ad) ? __uint_as_float(__float_as_uint(af) - 1u) : af;
+    float hi = __uint_as_float(__float_as_uint(lo) + 1u);
+    double mid = 0.5 * ((double)lo + (double)hi);        // exact
+    if (ad != mid) return f;
+    int dir = shortest_decimal_direction(ad);
+    float r = dir > 0 ? hi : (dir < 0 ? lo : af /* tie: parse rounds to even like the cast */);
+    return d < 0 ? -r : r;
+}
+
+__global__ void k_text_roundtrip(const double* __restrict__ mse, const double* __restrict__ total, long long n,
+                                 float* __restrict__ mse32, float* __restrict__ total32) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = i; j < n * 6; j += stride) mse32[j] = f64_text_f32(mse[j]);
+    if (total) for (long long j = i; j < n; j += stride) total32[j] = f64_text_f32(total[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SegDev {
+    const float*   median; const float* mse; const float* total; const int32_t* n;
+    float*         scaled; int32_t* state; int32_t* cn;
+    uint32_t*      codes;          // per marker: traceback[m][c] for c = 0..5, 3 bits each
+    long long      M;
+    float          lambda1, lambda2;
+    int            want_sd;
+    // results
+    float          mean, sd, l1u, l2u, final_loss, last_row[6];
+    int            status, sstar, skip, pad;
+};
+
+__constant__ float c_mu[6] = {-1.0f, -0.5f, 0.f, 0.f, 0.5f, 1.0f};   // Hmm.java:34
+__constant__ int   c_cn[6] = {0, 1, 2, 2, 3, 4};                     // Hmm.java:35
+
+// One warp per chromosome: mean coverage = sequential float sum of totals / int sum of sites (Hmm.java:369-373)
+__global__ void k_mean_coverage(SegDev* probs, int n_probs) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_probs) return;
+    SegDev& P = probs[w];
+    const long long M = P.M;
+    float s = 0.f;
+    int sites = 0;
+    float vnext = (lane < M) ? __ldg(&P.total[lane]) : 0.f;
+    int nnext = (lane < M) ? __ldg(&P.n[lane]) : 0;
+    for (long long m0 = 0; m0 < M; m0 += 32) {
+        float v = vnext; int nn = nnext;
+        long long mn = m0 + 32 + lane;
+        vnext = (mn < M) ? __ldg(&P.total[mn]) : 0.f;
+        nnext = (mn < M) ? __ldg(&P.n[mn]) : 0;
+        int cnt = (int)min((long long)32, M - m0);
+        sites += nn;
+        if (cnt == 32) {
+            #pragma unroll
+            for (int j = 0; j < 32; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
+        } else {
+            for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sites += __shfl_xor_sync(0xffffffffu, sites, o);   // int sum wraps like Java's
+    if (lane == 0) P.mean = __fdiv_rn(s, (float)sites);
+}
+
+// scale_depth, Hmm.java:121-135 (element-wise; all problems in one launch via a block->problem map)
+__global__ void k_scale_depth(SegDev* probs, const int* __restrict__ blk_prob, const long long* __restrict__ blk_first) {
+    SegDev& P = probs[blk_prob[blockIdx.x]];
+    long long i = blk_first[blockIdx.x] + threadIdx.x;
+    if (i >= P.M) return;
+    float mean = P.mean;
+    float s = __fdiv_rn(__fsub_rn(__ldg(&P.median[i]), mean), mean);
+    if (s < -2.0f) s = -2.0f;
+    if (s > 2.0f) s = 2.0f;
+    P.scaled[i] = s;
+}
+
+// get_sd, Hmm.java:103-119: two sequential float passes; one warp per chromosome
+__global__ void k_sd(SegDev* probs, int n_probs) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_probs) return;
+    SegDev& P = probs[w];
+    const long long M = P.M;
+    bool need = P.want_sd || P.lambda1 < 0 || P.lambda2 < 0;
+    float sd = 0.f;
+    if (need && M >= 2) {
+        float mean = 0.f;
+        for (long long m0 = 0; m0 < M; m0 += 32) {
+            long long m = m0 + lane;
+            float v = (m < M) ? P.scaled[m] : 0.f;
+            int cnt = (int)min((long long)32, M - m0);
+            for (int j = 0; j < cnt; ++j) mean = __fadd_rn(mean, __shfl_sync(0xffffffffu, v, j));
+        }
+        mean = __fdiv_rn(mean, (float)(int)M);
+        float acc = 0.f;
+        for (long long m0 = 0; m0 < M; m0 += 32) {
+            long long m = m0 + lane;
+            float v = (m < M) ? P.scaled[m] : 0.f;
+            float dev = __fsub_rn(v, mean);
+            float d2 = __fmul_rn(dev, dev);
+            int cnt = (int)min((long long)32, M - m0);
+            for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, d2, j));
+        }
+        sd = (float)sqrt((double)__fdiv_rn(acc, (float)((int)M - 1)));
+    }
+    if (lane == 0) {
+        P.sd = sd;
+        float l1 = P.lambda1, l2 = P.lambda2;
+        if (l1 < 0) l1 = __fmul_rn(2.f, sd);          // Hmm.java:93-99
+        if (l2 < 0) l2 = __fmul_rn(5.f, sd);
+        // search(0, lambda2 * 2), Hmm.java:311-318
+        float lmax = __fmul_rn(l2, 2.f);
+        float mid = __fdiv_rn(__fsub_rn(lmax, 0.f), 2.f);
+        l2 = __fadd_rn(0.f, mid);
+        P.skip = ((double)mid < .01) ? 1 : 0;
+        P.l1u = l1; P.l2u = l2;
+        P.status = P.skip ? HCNV_VITERBI_SKIPPED : HCNV_OK;
+        P.final_loss = 0.f; P.sstar = 0;
+        for (int s = 0; s < 6; ++s) P.last_row[s] = 0.f;
+    }
+}
+
+// Exact sequential Viterbi, one warp per chromosome; lanes 0..5 own the current state c.
+// Per marker: ((((L[m-1][p] + (1-alpha)*lrr) + alpha*baf) + lambda1*|mu_c|) + lambda2*|mu_c - mu_p|), Hmm.java:195-198,
+// strict '<' over ascending p starting from Float.MAX_VALUE (Hmm.java:184,199-203); a state no candidate
+// improves keeps loss 0 and traceback 0 (Java array defaults).
+#define VIT_CHUNK 32
+__global__ void __launch_bounds__(32) k_viterbi_seq(SegDev* probs, float alpha) {
+    __shared__ float s_sd[2][VIT_CHUNK];
+    __shared__ float s_mse[2][VIT_CHUNK * 6];
+    SegDev& P = probs[blockIdx.x];
+    const int lane = threadIdx.x;
+    const long long M = P.M;
+    if (P.skip) return;
+    const int c = lane < 6 ? lane : 0;
+    const float oma = __fsub_rn(1.f, alpha);
+    const float l1 = P.l1u, l2 = P.l2u;
+    const float muc = c_mu[c];
+    const float c3 = __fmul_rn(l1, fabsf(muc));
+    float c4[6];
+    #pragma unroll
+    for (int p = 0; p < 6; ++p) c4[p] = __fmul_rn(l2, fabsf(__fsub_rn(muc, c_mu[p])));
+    const float* __restrict__ sdp = P.scaled;
+    const float* __restrict__ msep = P.mse;
+
+    // marker 0 (Hmm.java:179-181); emissions are all zero when markers < 2 (Hmm.java:148-150)
+    float L;
+    {
+        float lrr = 0.f, baf = 0.f;
+        if (M >= 2) { float dev = __fsub_rn(sdp[0], muc); lrr = __fmul_rn(dev, dev); baf = msep[c]; }
+        L = __fadd_rn(__fadd_rn(__fmul_rn(oma, lrr), __fmul_rn(alpha, baf)), c3);
+    }
+    int bad = 0;
+    uint32_t mycode = 0;
+    // chunked staging of emissions through shared memory, next chunk prefetched into registers
+    float r_sd = 0.f, r_m[6];
+    auto fetch = [&](long long m0) {
+        long long m = m0 + lane;
+        r_sd = (m < M) ? __ldg(&sdp[m]) : 0.f;
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) { long long e = m0 * 6 + i * 32 + lane; r_m[i] = (e < M * 6) ? __ldg(&msep[e]) : 0.f; }
+    };
+    auto stash = [&](int buf) {
+        s_sd[buf][lane] = r_sd;
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) s_mse[buf][i * 32 + lane] = r_m[i];
+    };
+    fetch(0); stash(0); __syncwarp();
+    int buf = 0;
+    for (long long m0 = 0; m0 < M; m0 += VIT_CHUNK) {
+        if (m0 + VIT_CHUNK < M) fetch(m0 + VIT_CHUNK);
+        int cnt = (int)min((long long)VIT_CHUNK, M - m0);
+        for (int j = (m0 == 0 ? 1 : 0); j < cnt; ++j) {
+            float dev = __fsub_rn(s_sd[buf][j], muc);
+            float A = __fmul_rn(oma, __fmul_rn(dev, dev));
+            float B = __fmul_rn(alpha, s_mse[buf][j * 6 + c]);
+            float mn = FLT_MAX, Ln = 0.f; int arg = 0;
+            #pragma unroll
+            for (int p = 0; p < 6; ++p) {
+                float Lp = __shfl_sync(0xffffffffu, L, p);
+                float loss = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(Lp, A), B), c3), c4[p]);
+                if (loss < mn) { mn = loss; Ln = mn; arg = p; }
+            }
+            if ((double)mn == 1e10) bad = 1;                                   // Hmm.java:205-215
+            L = Ln;
+            uint32_t code = __reduce_or_sync(0xffffffffu, lane < 6 ? ((uint32_t)arg << (3 * lane)) : 0u);
+            if (lane == j) mycode = code;
+        }
+        if (lane < cnt) P.codes[m0 + lane] = mycode;
+        if (m0 + VIT_CHUNK < M) { buf ^= 1; stash(buf); }
+        __syncwarp();
+    }
+    // final arg-min over the last row (Hmm.java:220-232)
+    int min_index = 1; float mn = FLT_MAX;
+    float row[6];
+    #pragma unroll
+    for (int s = 0; s < 6; ++s) { row[s] = __shfl_sync(0xffffffffu, L, s); if (row[s] < mn) { mn = row[s]; min_index = s; } }
+    bad = __any_sync(0xffffffffu, bad && lane < 6);
+    if (lane == 0) {
+        for (int s = 0; s < 6; ++s) P.last_row[s] = row[s];
+        P.sstar = min_index;
+        P.final_loss = mn;
+        if (bad || mn == FLT_MAX) { P.status = HCNV_E_NO_MINIMUM; P.skip = 2; }
+    }
+}
+
+// best_state / cn columns (Hmm.java:234-237, 483-484)
+__global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_prob, const long long* __restrict__ blk_first) {
+    SegDev& P = probs[blk_prob[blockIdx.x]];
+    long long i = blk_first[blockIdx.x] + threadIdx.x;
+    const long long M = P.M;
+    if (i >= M) return;
+    int st = 0;
+    if (!P.skip) {
+        int s = P.sstar;
+        if (i == M - 1) st = c_cn[s];                                         // (sic) Hmm.java:234
+        else st = (int)((P.codes[i + 1] >> (3 * s)) & 7u);                    // traceback[m+1][s*], Hmm.java:236
+    }
+    if (P.state) P.state[i] = st;
+    if (P.cn) P.cn[i] = c_cn[st];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+namespace {
+enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT };
+}
+
+int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
+                                float* mse_f32, float* total_f32)
+{
+    if (!ctx || n < 0 || (n > 0 && (!mse || !mse_f32))) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    if ((total == nullptr) != (total_f32 == nullptr)) return hcnv_fail(ctx, HCNV_E_INVALID, "total and total_f32 must both be given or both be null");
+    if (n == 0) return HCNV_OK;
+    const bool dev = hcnv_ptr_kind(mse) == 2;
+    if ((hcnv_ptr_kind(mse_f32) == 2) != dev || (total && ((hcnv_ptr_kind(total) == 2) != dev || (hcnv_ptr_kind(total_f32) == 2) != dev)))
+        return hcnv_fail(ctx, HCNV_E_INVALID, "mixed host/device pointers");
+    const double *d_mse = mse, *d_tot = total; float *d_m32 = mse_f32, *d_t32 = total_f32;
+    if (!dev) {
+        HCNV_CUDA(ctx, ctx->buf[H_RT_IN].reserve(8 * 7 * (size_t)n));
+        HCNV_CUDA(ctx, ctx->buf[H_RT_OUT].reserve(4 * 7 * (size_t)n));
+        double* di = ctx->buf[H_RT_IN].as<double>(); float* fo = ctx->buf[H_RT_OUT].as<float>();
+        HCNV_CUDA(ctx, cudaMemcpyAsync(di, mse, 48 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        if (total) HCNV_CUDA(ctx, cudaMemcpyAsync(di + 6 * n, total, 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        d_mse = di; d_tot = total ? di + 6 * n : nullptr; d_m32 = fo; d_t32 = total ? fo + 6 * n : nullptr;
+    }
+    int grid = (int)std::min<long long>((n * 6 + 255) / 256, (long long)ctx->sm_count * 32);
+    k_text_roundtrip<<<grid, 256, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32);
+    ctx->launches++;
+    HCNV_CUDA(ctx, cudaGetLastError());
+    if (!dev) {
+        HCNV_CUDA(ctx, cudaMemcpyAsync(mse_f32, d_m32, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (total) HCNV_CUDA(ctx, cudaMemcpyAsync(total_f32, d_t32, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HCNV_OK;
+}
+
+int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* probs, int32_t flags)
+{
+    (void)flags;
+    if (!ctx || n_problems <= 0 || !probs) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    long long totM = 0;
+    int kind = -1;
+    for (int i = 0; i < n_problems; ++i) {
+        hcnv_segment_problem& q = probs[i];
+        if (q.n_markers < 1) return hcnv_fail(ctx, HCNV_E_INVALID, "a chromosome needs at least one marker (CnvReducer only builds an Hmm when it has values)");
+        if (q.n_markers >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers");
+        if (!q.median || !q.mse || !q.total || !q.n) return hcnv_fail(ctx, HCNV_E_INVALID, "null input array");
+        const void* ptrs[7] = { q.median, q.mse, q.total, q.n, q.scaled, q.state, q.cn };
+        for (int j = 0; j < 7; ++j) {
+            if (!ptrs[j]) continue;
+            int kd = hcnv_ptr_kind(ptrs[j]) == 2 ? 2 : 0;
+            if (kind < 0) kind = kd; else if (kind != kd) return hcnv_fail(ctx, HCNV_E_INVALID, "mixed host/device pointers");
+        }
+        totM += q.n_markers;
+    }
+    const bool dev = kind == 2;
+    std::vector<SegDev> h(n_problems);
+    HCNV_CUDA(ctx, ctx->buf[H_CODES].reserve(4 * (size_t)totM));
+    HCNV_CUDA(ctx, ctx->buf[H_SCALED].reserve(4 * (size_t)totM));
+    if (!dev) {
+        HCNV_CUDA(ctx, ctx->buf[H_IN_F32].reserve(4 * 8 * (size_t)totM));     // median, mse*6, total
+        HCNV_CUDA(ctx, ctx->buf[H_IN_I32].reserve(4 * (size_t)totM));
+        HCNV_CUDA(ctx, ctx->buf[H_OUT_I32].reserve(4 * 2 * (size_t)totM));
+    }
+    long long off = 0;
+    std::vector<int> blk_prob; std::vector<long long> blk_first;
+    for (int i = 0; i < n_problems; ++i) {
+        hcnv_segment_problem& q = probs[i];
+        SegDev& d = h[i];
+        memset(&d, 0, sizeof d);
+        const long long M = q.n_markers;
+        d.M = M; d.lambda1 = q.lambda1; d.lambda2 = q.lambda2; d.want_sd = q.want_sd;
+        d.codes = ctx->buf[H_CODES].as<uint32_t>() + off;
+        if (dev) {
+            d.median = q.median; d.mse = q.mse; d.total = q.total; d.n = q.n;
+            d.scaled = q.scaled ? q.scaled : ctx->buf[H_SCALED].as<float>() + off;
+            d.state = q.state; d.cn = q.cn;
+        } else {
+            float* f = ctx->buf[H_IN_F32].as<float>();
+            float* dm = f + off; float* dmse = f + totM + 6 * off; float* dt = f + 7 * totM + off;
+            int32_t* dn = ctx->buf[H_IN_I32].as<int32_t>() + off;
+            HCNV_CUDA(ctx, cudaMemcpyAsync(dm, q.median, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyAsync(dmse, q.mse, 24 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyAsync(dt, q.total, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyAsync(dn, q.n, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+            d.median = dm; d.mse = dmse; d.total = dt; d.n = dn;
+            d.scaled = ctx->buf[H_SCALED].as<float>() + off;
+            d.state = ctx->buf[H_OUT_I32].as<int32_t>() + off;
+            d.cn = ctx->buf[H_OUT_I32].as<int32_t>() + totM + off;
+        }
+        for (long long b = 0; b < M; b += 256) { blk_prob.push_back(i); blk_first.push_back(b); }
+        off += M;
+    }
+    const size_t nblk = blk_prob.size();
+    HCNV_CUDA(ctx, ctx->buf[H_PROBS].reserve(sizeof(SegDev) * (size_t)n_problems));
+    HCNV_CUDA(ctx, ctx->buf[H_BLKMAP].reserve(12 * nblk + 64));
+    SegDev* dprobs = ctx->buf[H_PROBS].as<SegDev>();
+    long long* d_first = ctx->buf[H_BLKMAP].as<long long>();
+    int* d_prob = (int*)(d_first + nblk);
+    HCNV_CUDA(ctx, cudaMemcpyAsync(dprobs, h.data(), sizeof(SegDev) * (size_t)n_problems, cudaMemcpyHostToDevice, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemcpyAsync(d_first, blk_first.data(), 8 * nblk, cudaMemcpyHostToDevice, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemcpyAsync(d_prob, blk_prob.data(), 4 * nblk, cudaMemcpyHostToDevice, ctx->stream));
+
+    const int wpb = 4;   // warps per block for the one-warp-per-chromosome kernels
+    k_mean_coverage<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
+    k_scale_depth<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_prob, d_first);
+    k_sd<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
+    k_viterbi_seq<<<n_problems, 32, 0, ctx->stream>>>(dprobs, alpha);
+    k_traceback<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_prob, d_first);
+    ctx->launches += 5;
+    HCNV_CUDA(ctx, cudaGetLastError());
+    HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), dprobs, sizeof(SegDev) * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dev) {
+        off = 0;
+        for (int i = 0; i < n_problems; ++i) {
+            hcnv_segment_problem& q = probs[i];
+            const size_t M = (size_t)q.n_markers;
+            if (q.scaled) HCNV_CUDA(ctx, cudaMemcpyAsync(q.scaled, h[i].scaled, 4 * M, cudaMemcpyDeviceToHost, ctx->stream));
+            if (q.state) HCNV_CUDA(ctx, cudaMemcpyAsync(q.state, h[i].state, 4 * M, cudaMemcpyDeviceToHost, ctx->stream));
+            if (q.cn) HCNV_CUDA(ctx, cudaMemcpyAsync(q.cn, h[i].cn, 4 * M, cudaMemcpyDeviceToHost, ctx->stream));
+            off += (long long)M;
+        }
+    }
+    HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int worst = HCNV_OK;
+    for (int i = 0; i < n_problems; ++i) {
+        hcnv_segment_problem& q = probs[i];
+        q.mean_coverage = h[i].mean; q.sd = h[i].sd; q.lambda1_used = h[i].l1u; q.lambda2_used = h[i].l2u;
+        q.final_loss = h[i].final_loss; q.status = h[i].status;
+        for (int s = 0; s < 6; ++s) q.last_row[s] = h[i].last_row[s];
+        if (q.status < 0) worst = q.status;
+    }
+    if (worst < 0) return hcnv_fail(ctx, worst, "Hmm: failed to find minimum (the reference exits here, Hmm.java:205-215,229-232)");
+    return HCNV_OK;
+}

@@ -1,0 +1,243 @@
+// textio.cpp -- B3: config.txt and the text layouts between the reference's jobs (host code, no CUDA).
+//
+//   UserConfig.init / getters   UserConfig.java:25-141  (java.util.Properties syntax)
+//   bins part files             Reducers.java:191-203   chr \t bin \t start \t end \t median \t mse0..5 \t total \t n
+//   results.txt                 Hmm.java:479-490 + Reducers.java:238-241
+//   Float.toString / Double.toString number formatting (shortest digits that round-trip, Java notation)
+#include "../../include/hcnv.h"
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+
+namespace {
+
+// ---- shortest round-trip digits ---------------------------------------------------------------
+// Returns digits (no leading/trailing zeros unless the value needs them) and the decimal exponent of the
+// first digit.  Tries increasing precision; at each precision also the neighbours of the nearest decimal,
+// because the rounding interval is asymmetric at powers of two.
+template <class T> T parse_as(const char* s);
+template <> float parse_as<float>(const char* s) { return strtof(s, nullptr); }
+template <> double parse_as<double>(const char* s) { return strtod(s, nullptr); }
+
+template <class T>
+void shortest_digits(T v, char* digits, int* nd_out, int* e10_out) {
+    const int maxp = sizeof(T) == 4 ? 9 : 17;
+    char tmp[48];
+    for (int p = 1; p <= maxp; ++p) {
+        snprintf(tmp, sizeof tmp, "%.*e", p - 1, (double)v);
+        unsigned long long n = 0; int nd = 0; const char* c = tmp;
+        for (; *c && *c != 'e'; ++c) if (*c != '.') { n = n * 10 + (unsigned)(*c - '0'); ++nd; }
+        int e10 = atoi(c + 1);
+        unsigned long long lim = 1; for (int i = 0; i < nd; ++i) lim *= 10;
+        const long long deltas[3] = {0, -1, 1};
+        for (int di = 0; di < 3; ++di) {
+            unsigned long long m = n; int e = e10;
+            if (deltas[di] < 0) { if (m == lim / 10) continue; m -= 1; }
+            else if (deltas[di] > 0) { m += 1; if (m >= lim) { m /= 10; e += 1; } }
+            char cand[48], dg[24];
+            snprintf(dg, sizeof dg, "%0*llu", nd, m);
+            snprintf(cand, sizeof cand, "%c.%se%d", dg[0], dg[1] ? dg + 1 : "0", e);
+            if (parse_as<T>(cand) == v) {
+                int k = nd;
+                while (k > 1 && dg[k - 1] == '0') --k;
+                memcpy(digits, dg, (size_t)k); digits[k] = 0;
+                *nd_out = k; *e10_out = e;
+                return;
+            }
+        }
+    }
+    digits[0] = '0'; digits[1] = 0; *nd_out = 1; *e10_out = 0;   // not reached for finite v
+}
+
+template <class T>
+int java_to_string(T v, char* buf) {
+    if (std::isnan(v)) { strcpy(buf, "NaN"); return 3; }
+    if (std::isinf(v)) { strcpy(buf, v < 0 ? "-Infinity" : "Infinity"); return (int)strlen(buf); }
+    if (v == 0) { strcpy(buf, std::signbit(v) ? "-0.0" : "0.0"); return (int)strlen(buf); }
+    char dg[24]; int nd, e10;
+    T av = v < 0 ? -v : v;
+    shortest_digits<T>(av, dg, &nd, &e10);
+    char* o = buf;
+    if (v < 0) *o++ = '-';
+    if ((double)av >= 1e-3 && (double)av < 1e7) {
+        if (e10 >= 0) {
+            for (int i = 0; i <= e10; ++i) *o++ = i < nd ? dg[i] : '0';
+            *o++ = '.';
+            if (nd > e10 + 1) { for (int i = e10 + 1; i < nd; ++i) *o++ = dg[i]; } else *o++ = '0';
+        } else {
+            *o++ = '0'; *o++ = '.';
+            for (int i = 0; i < -e10 - 1; ++i) *o++ = '0';
+            for (int i = 0; i < nd; ++i) *o++ = dg[i];
+        }
+    } else {
+        *o++ = dg[0]; *o++ = '.';
+        if (nd > 1) { for (int i = 1; i < nd; ++i) *o++ = dg[i]; } else *o++ = '0';
+        *o++ = 'E';
+        o += sprintf(o, "%d", e10);
+    }
+    *o = 0;
+    return (int)(o - buf);
+}
+
+// ---- java.util.Properties.load (the subset config.txt uses: comments, '=' ':' or blank separators,
+// backslash escapes and line continuations) ------------------------------------------------------
+bool load_properties(const char* path, std::map<std::string, std::string>& kv) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    std::string text; char b[4096]; size_t n;
+    while ((n = fread(b, 1, sizeof b, f)) > 0) text.append(b, n);
+    fclose(f);
+    size_t i = 0, N = text.size();
+    auto is_ws = [](char c) { return c == ' ' || c == '\t' || c == '\f'; };
+    while (i < N) {
+        // logical line
+        std::string line;
+        bool first_phys = true;
+        while (i < N) {
+            size_t e = i;
+            while (e < N && text[e] != '\n' && text[e] != '\r') ++e;
+            std::string phys = text.substr(i, e - i);
+            i = e;
+            if (i < N) { if (text[i] == '\r' && i + 1 < N && text[i + 1] == '\n') i += 2; else ++i; }
+            size_t s = 0;
+            while (s < phys.size() && is_ws(phys[s])) ++s;
+            phys = phys.substr(s);
+            if (first_phys && (phys.empty() || phys[0] == '#' || phys[0] == '!')) { line.clear(); break; }
+            first_phys = false;
+            size_t bs = 0;
+            for (size_t k = phys.size(); k > 0 && phys[k - 1] == '\\'; --k) ++bs;
+            if (bs % 2 == 1) { line += phys.substr(0, phys.size() - 1); continue; }
+            line += phys;
+            break;
+        }
+        if (line.empty()) continue;
+        std::string key, val;
+        size_t p = 0;
+        auto unescape = [&](std::string& dst, bool is_key) {
+            while (p < line.size()) {
+                char c = line[p];
+                if (is_key && (c == '=' || c == ':' || is_ws(c))) break;
+                if (c == '\\' && p + 1 < line.size()) {
+                    char d = line[++p];
+                    if (d == 't') dst += '\t'; else if (d == 'n') dst += '\n'; else if (d == 'r') dst += '\r'; else if (d == 'f') dst += '\f';
+                    else dst += d;
+                    ++p;
+                } else { dst += c; ++p; }
+            }
+        };
+        unescape(key, true);
+        while (p < line.size() && is_ws(line[p])) ++p;
+        if (p < line.size() && (line[p] == '=' || line[p] == ':')) { ++p; while (p < line.size() && is_ws(line[p])) ++p; }
+        unescape(val, false);
+        kv[key] = val;
+    }
+    return true;
+}
+
+std::string jtrim(const std::string& s) {   // String.trim(): strips chars <= ' '
+    size_t a = 0, b = s.size();
+    while (a < b && (unsigned char)s[a] <= ' ') ++a;
+    while (b > a && (unsigned char)s[b - 1] <= ' ') --b;
+    return s.substr(a, b - a);
+}
+bool parse_bool(const std::map<std::string, std::string>& kv, const char* k) {   // Boolean.parseBoolean (no trim)
+    auto it = kv.find(k);
+    if (it == kv.end()) return false;
+    const std::string& s = it->second;
+    return s.size() == 4 && tolower(s[0]) == 't' && tolower(s[1]) == 'r' && tolower(s[2]) == 'u' && tolower(s[3]) == 'e';
+}
+bool parse_int(const std::string& s, int32_t* out) {   // Integer.parseInt
+    if (s.empty()) return false;
+    size_t p = 0; if (s[0] == '-' || s[0] == '+') p = 1;
+    if (p == s.size()) return false;
+    long long v = 0;
+    for (; p < s.size(); ++p) { if (!isdigit((unsigned char)s[p])) return false; v = v * 10 + (s[p] - '0'); if (v > 2147483648LL) return false; }
+    if (s[0] == '-') v = -v;
+    if (v > 2147483647LL || v < -2147483648LL) return false;
+    *out = (int32_t)v; return true;
+}
+bool parse_float(const std::string& s0, float* out) {   // Float.parseFloat(trimmed): optional f/F/d/D suffix
+    std::string s = jtrim(s0);
+    if (s.empty()) return false;
+    char last = s[s.size() - 1];
+    if (last == 'f' || last == 'F' || last == 'd' || last == 'D') s.erase(s.size() - 1);
+    if (s.empty()) return false;
+    if (s == "NaN" || s == "+NaN" || s == "-NaN") { *out = NAN; return true; }
+    if (s == "Infinity" || s == "+Infinity") { *out = INFINITY; return true; }
+    if (s == "-Infinity") { *out = -INFINITY; return true; }
+    for (char c : s) if (!(isdigit((unsigned char)c) || c == '.' || c == 'e' || c == 'E' || c == '+' || c == '-')) return false;
+    char* end = nullptr;
+    float v = strtof(s.c_str(), &end);
+    if (!end || *end) return false;
+    *out = v; return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hcnv_format_float(float v, char* buf) { return buf ? java_to_string<float>(v, buf) : HCNV_E_INVALID; }
+int hcnv_format_double(double v, char* buf) { return buf ? java_to_string<double>(v, buf) : HCNV_E_INVALID; }
+
+int hcnv_config_load(const char* path, hcnv_config* out) {
+    if (!path || !out) return HCNV_E_INVALID;
+    std::map<std::string, std::string> kv;
+    if (!load_properties(path, kv)) return HCNV_E_IO;
+    memset(out, 0, sizeof *out);
+    auto get = [&](const char* k) -> const std::string* { auto it = kv.find(k); return it == kv.end() ? nullptr : &it->second; };
+    if (const std::string* s = get("BAM_FILE")) snprintf(out->bam_file, sizeof out->bam_file, "%s", s->c_str());
+    if (const std::string* s = get("VCF_FILE")) snprintf(out->vcf_file, sizeof out->vcf_file, "%s", s->c_str());
+    out->run_depth_caller = parse_bool(kv, "RUN_DEPTH_CALLER");
+    out->run_global_sort = parse_bool(kv, "RUN_GLOBAL_SORT");
+    out->init_vcf_lookup = parse_bool(kv, "INIT_VCF_LOOKUP");
+    out->run_binner = parse_bool(kv, "RUN_BINNER");
+    out->run_cnv_caller = parse_bool(kv, "RUN_CNV_CALLER");
+    out->run_sr_pe_extracter = parse_bool(kv, "RUN_SR_PE_EXTRACTER");
+    // PennCnvSeq.run reads all of these unconditionally (PennCnvSeq.java:106-118): a missing or malformed one throws
+    const std::string* s;
+    if (!(s = get("ABBERATION_PENALTY")) || !parse_float(*s, &out->abberation_penalty)) return HCNV_E_PARSE;
+    if (!(s = get("TRANSITION_PENALTY")) || !parse_float(*s, &out->transition_penalty)) return HCNV_E_PARSE;
+    if (!(s = get("BAM_FILE_REDUCERS")) || !parse_int(*s, &out->bam_file_reducers)) return HCNV_E_PARSE;     // no trim (UserConfig.java:92)
+    if (!(s = get("TEXT_FILE_REDUCERS")) || !parse_int(*s, &out->text_file_reducers)) return HCNV_E_PARSE;
+    if (!(s = get("REDUCER_TASKS")) || !parse_int(jtrim(*s), &out->reducer_tasks)) return HCNV_E_PARSE;      // trimmed (UserConfig.java:127)
+    return HCNV_OK;
+}
+
+int hcnv_write_bins_text(const char* path, int append, const char* chr, int64_t n,
+                         const int32_t* bin, const int32_t* start, const int32_t* end, const float* median,
+                         const double* mse, const double* total, const int32_t* cnt) {
+    if (!path || !chr || n < 0) return HCNV_E_INVALID;
+    FILE* f = fopen(path, append ? "ab" : "wb");
+    if (!f) return HCNV_E_IO;
+    char b[64];
+    for (int64_t i = 0; i < n; ++i) {
+        fprintf(f, "%s\t%d\t%d\t%d\t", chr, bin[i], start[i], end[i]);
+        java_to_string<double>((double)median[i], b); fputs(b, f);         // Double.toString(medianDepth), Reducers.java:202
+        for (int s = 0; s < 6; ++s) { java_to_string<double>(mse[i * 6 + s], b); fputc('\t', f); fputs(b, f); }
+        java_to_string<double>(total[i], b);
+        fprintf(f, "\t%s\t%d\n", b, cnt[i]);
+    }
+    return fclose(f) == 0 ? HCNV_OK : HCNV_E_IO;
+}
+
+int hcnv_write_results_text(const char* path, int append, const char* chr, int64_t n,
+                            const int32_t* start, const int32_t* end, const float* scaled,
+                            const int32_t* state, const int32_t* cn, const float* mse) {
+    if (!path || !chr || n < 0) return HCNV_E_INVALID;
+    FILE* f = fopen(path, append ? "ab" : "wb");
+    if (!f) return HCNV_E_IO;
+    char b[64];
+    for (int64_t i = 0; i < n; ++i) {
+        java_to_string<float>(scaled[i], b);
+        fprintf(f, "%s\t%d\t%d\t%s\t%d\t%d", chr, start[i], end[i], b, state[i], cn[i]);
+        for (int s = 0; s < 6; ++s) { java_to_string<float>(mse[i * 6 + s], b); fputc('\t', f); fputs(b, f); }
+        fputc('\n', f);
+    }
+    return fclose(f) == 0 ? HCNV_OK : HCNV_E_IO;
+}
+
+}  // extern "C"

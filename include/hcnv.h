@@ -1,0 +1,178 @@
+/*
+ * hcnv.h -- C ABI of libhcnv: HadoopCNV's data-parallel hot path on B200 (sm_100a).
+ *
+ * The reference (WGLab/HadoopCNV, Java on Hadoop) has no FFI; its operator boundaries are the
+ * Hadoop Mapper/Reducer call-backs and the tab-separated text files between jobs.  This library sits
+ * behind the same three seams.  File:line citations are under the reference's
+ * src/main/java/edu/usc/.  INTEGRATION.md shows the JNI / Panama binding a maintainer would add.
+ *
+ *   B1  binning       replaces SAMRecordWindowMapper.map      (Mappers.java:167-272)
+ *                              AlleleDepthWindowReducer.reduce (Reducers.java:341-425)
+ *                              BinMapper.map                   (Mappers.java:43-62)
+ *                              BinReducer.reduce               (Reducers.java:55-204)
+ *   B2  segmentation  replaces CnvReducer.reduce               (Reducers.java:225-243)
+ *                              Hmm.init/run/getResults         (Hmm.java:341-391,329-332,296-298)
+ *   B3  files/config  replaces UserConfig.init                 (UserConfig.java:25-29) and the
+ *                              workdir/{bins,cnv} text layouts (Reducers.java:191-203, Hmm.java:479-490)
+ *
+ * Conventions: every call returns an int status (0 ok, >0 informational, <0 error); nothing exits or
+ * throws (contrast Hmm.java:214,231, Utils.java:80).  The caller owns every buffer it passes; the
+ * library never frees caller memory.  A buffer may be a host pointer (pageable or pinned) or a device
+ * pointer of the context's GPU; the kind is discovered with cudaPointerGetAttributes, all buffers of one
+ * call must be of one kind.  A context is single-threaded like a Hadoop task instance; independent
+ * contexts may run concurrently.  There is no CPU fallback: without a CUDA device every compute
+ * call fails with HCNV_E_CUDA.
+ */
+#ifndef HCNV_H
+#define HCNV_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCNV_OK                 0
+#define HCNV_VITERBI_SKIPPED    1   /* Hmm.search's "Too small a range, aborting" (Hmm.java:315-318): all calls are state 0 */
+#define HCNV_E_INVALID         -1   /* bad argument */
+#define HCNV_E_CUDA            -2   /* CUDA error (no device, launch failure, ...) */
+#define HCNV_E_NOMEM           -3
+#define HCNV_E_RANGE           -4   /* a record lies outside [1, contig length] or is longer than max_block_len */
+#define HCNV_E_UNSORTED        -5   /* blocks / SNP table not sorted by position */
+#define HCNV_E_INCONSISTENT    -6   /* allele observations at a SNP site do not add up to its coverage */
+#define HCNV_E_NO_MINIMUM      -7   /* the reference would System.exit here (Hmm.java:205-215,229-232) */
+#define HCNV_E_IO              -8
+#define HCNV_E_PARSE           -9
+#define HCNV_E_CAPACITY       -10   /* an output buffer is too small */
+#define HCNV_E_INTERNAL       -11
+
+#define HCNV_STATES 6               /* Hmm.java:24 */
+#define HCNV_SHORT_MAX 4095         /* longest block allowed in the sorted short-block stream */
+
+typedef struct hcnv_ctx hcnv_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int         hcnv_ctx_create(int device, hcnv_ctx** out);
+void        hcnv_ctx_destroy(hcnv_ctx* ctx);
+const char* hcnv_last_error(const hcnv_ctx* ctx);
+const char* hcnv_strerror(int status);
+int         hcnv_version(void);
+/* sizeof of hcnv_block, hcnv_long_block, hcnv_bin_params, hcnv_contig_input, hcnv_bins, hcnv_segment_problem, hcnv_config
+ * (so that a binding can verify its struct layouts) */
+void        hcnv_abi_sizes(int32_t out[7]);
+/* cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the caller) */
+void*       hcnv_ctx_stream(hcnv_ctx* ctx);
+/* number of kernels this context has launched so far */
+int64_t     hcnv_ctx_kernel_launches(const hcnv_ctx* ctx);
+int         hcnv_ctx_synchronize(hcnv_ctx* ctx);
+
+/* ---- B1: binning ------------------------------------------------------------------------------ */
+
+/* One alignment block (a run of M/=/X CIGAR operations; htsjdk AlignmentBlock, Mappers.java:201-212)
+ * of at most HCNV_SHORT_MAX bases.  start0 = 0-based reference start (refstart-1, Mappers.java:218-219);
+ * len_mapq = length | mapq << 24 (mapq as in Mappers.java:192).  Sorted by start0 within a contig. */
+typedef struct { int32_t start0; uint32_t len_mapq; } hcnv_block;
+
+/* A block of any length (e.g. the baseline BAM's artificial whole-interval reads, example/preprocessBAM.py).
+ * Not required to be sorted.  Splitting a block is results-neutral: only per-position counts matter. */
+typedef struct { int32_t start0; int32_t len; int32_t mapq; int32_t reserved; } hcnv_long_block;
+
+typedef struct {
+    int32_t bin_width;                  /* Constants.bin_width (Constants.java:33), default 100 */
+    int32_t max_block_len;              /* upper bound of len over the short blocks (<= HCNV_SHORT_MAX); 0 = HCNV_SHORT_MAX */
+    double  mapping_quality_threshold;  /* Constants.mapping_quality_threshold (Constants.java:21), default 0 */
+    int32_t tile_bins;                  /* tuning: bins per CTA tile, 0 = default */
+    int32_t flags;                      /* reserved, 0 */
+} hcnv_bin_params;
+void hcnv_bin_params_default(hcnv_bin_params* p);
+
+/* Inputs of one contig (= one reference sequence; the reducer key's refname, Keys.java:226-238).
+ * snp_pos1/snp_zyg: the VCF side input of VcfLookup.parseVcf2Text (VcfLookup.java:135-196) as a table of
+ * unique ascending 1-based positions with zygosity in {0,-1,-2} (Utils.java:15-84).
+ * obs: one entry per (alignment block, SNP site it covers): snp index << 4 | BAM 4-bit base code
+ * ("=ACMGRSVTWYHKDBN"; the base SAMRecordWindowMapper stores, 'A' = 1 for SEQ=*, Mappers.java:248-256). */
+typedef struct {
+    int32_t                length;      /* contig length in bp; positions are 1..length */
+    const hcnv_block*      blocks;      int64_t n_blocks;
+    const hcnv_long_block* long_blocks; int64_t n_long;
+    const int32_t*         snp_pos1;    const int8_t* snp_zyg; int64_t n_snp;
+    const uint32_t*        obs;         int64_t n_obs;
+} hcnv_contig_input;
+
+/* Outputs: one record per non-empty bin, all contigs concatenated in input order, bins ascending within a
+ * contig (the (chr,bin) secondary sort, PennCnvSeq.java:382-414).  Field meaning = the columns BinReducer
+ * writes (Reducers.java:191-203): bin id, startbp, endbp, medianDepth, mse_states[0..5], total_depth, n.
+ * capacity >= sum over contigs of (length / bin_width + 1) always suffices. */
+typedef struct {
+    int64_t  capacity;
+    int32_t* bin; int32_t* start; int32_t* end;
+    float*   median;
+    double*  mse;            /* capacity * 6 */
+    double*  total;
+    int32_t* n;
+    int64_t* contig_offset;  /* n_contigs + 1 entries (host memory, always): contig c owns [offset[c], offset[c+1]) */
+} hcnv_bins;
+
+int hcnv_bin_contigs(hcnv_ctx* ctx, const hcnv_bin_params* params,
+                     int32_t n_contigs, const hcnv_contig_input* contigs, hcnv_bins* out);
+
+/* ---- between B1 and B2: what Hmm.init's text parsing does to a bins record ---------------------- */
+/* Double.toString -> Float.valueOf round trip of mse (Reducers.java:191-192 -> Hmm.java:364) and of total
+ * (Reducers.java:202 -> Hmm.java:369); n values.  Bit-identical to printing and re-parsing the text. */
+int hcnv_bins_to_hmm_input(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
+                           float* mse_f32, float* total_f32);
+
+/* ---- B2: segmentation ------------------------------------------------------------------------- */
+/* One chromosome (one CnvReducer.reduce call).  Inputs are what Hmm holds after Hmm.init parsed the
+ * reducer values (Hmm.java:353-389).  lambda1/lambda2 = ABBERATION_PENALTY / TRANSITION_PENALTY
+ * (PennCnvSeq.java:319-320); negative means "estimate from sd" (Hmm.java:93-99). */
+typedef struct {
+    int64_t        n_markers;
+    const float*   median;          /* depth.get(i)            */
+    const float*   mse;             /* n_markers * 6           */
+    const float*   total;           /* per-bin total depth     */
+    const int32_t* n;               /* per-bin site count      */
+    float          lambda1, lambda2;
+    /* outputs (may be NULL to skip) */
+    float*         scaled;          /* scaled_depth, results.txt column 4 (Hmm.java:481) */
+    int32_t*       state;           /* best_state,   results.txt column 5 (Hmm.java:483) */
+    int32_t*       cn;              /* cn_arr[best_state], column 6 (Hmm.java:484)       */
+    /* scalar outputs */
+    float          mean_coverage;   /* Hmm.java:373 */
+    float          sd;              /* Hmm.java:91 (computed only if want_sd or a penalty is negative) */
+    float          lambda1_used, lambda2_used;
+    float          final_loss;      /* min over the last row of loss_mat (Hmm.java:221-227) */
+    float          last_row[HCNV_STATES];
+    int32_t        status;          /* HCNV_OK, HCNV_VITERBI_SKIPPED or HCNV_E_NO_MINIMUM */
+    int32_t        want_sd;
+} hcnv_segment_problem;
+
+#define HCNV_SEG_SEQUENTIAL 1       /* flags: force the one-warp-per-chromosome exact kernel */
+int hcnv_segment_batch(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems, int32_t flags);
+
+/* ---- B3: config and text layouts -------------------------------------------------------------- */
+typedef struct {
+    char    bam_file[1024];
+    char    vcf_file[1024];
+    int32_t run_depth_caller, run_global_sort, init_vcf_lookup, run_binner, run_cnv_caller, run_sr_pe_extracter;
+    int32_t bam_file_reducers, text_file_reducers, reducer_tasks;
+    float   abberation_penalty, transition_penalty;
+} hcnv_config;
+/* java.util.Properties syntax, the keys of UserConfig.java:35-137, Float.parseFloat's trailing 'f' */
+int hcnv_config_load(const char* path, hcnv_config* out);
+
+/* Float.toString / Double.toString; return the length written (buf >= 32 bytes) */
+int hcnv_format_float(float v, char* buf);
+int hcnv_format_double(double v, char* buf);
+
+/* bins part-file lines "chr\tbin\tstart\tend\tmedian\tmse0..5\ttotal\tn" (Reducers.java:191-203); host arrays */
+int hcnv_write_bins_text(const char* path, int append, const char* chr, int64_t n,
+                         const int32_t* bin, const int32_t* start, const int32_t* end, const float* median,
+                         const double* mse, const double* total, const int32_t* cnt);
+/* results.txt lines "chr\tstart\tend\tscaled\tstate\tcn\tmse0..5" (Hmm.java:479-490, Reducers.java:238-241) */
+int hcnv_write_results_text(const char* path, int append, const char* chr, int64_t n,
+                            const int32_t* start, const int32_t* end, const float* scaled,
+                            const int32_t* state, const int32_t* cn, const float* mse);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,193 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs.  Integers, bytes and indices must be bit-exact; the float columns are bit-exact too
+(the kernels reproduce the reference's float32/float64 evaluation order), which is stricter than the 1e-5
+relative tolerance BASELINE.json asks for."""
+import numpy as np
+import pytest
+
+import hadoopcnv_b200 as H
+from hadoopcnv_b200 import _lib as L
+from hadoopcnv_b200 import synth
+from oracle import oracle as O
+from tests import helpers as Hp
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def oracle_bins(c, W, mapq_threshold=0.0):
+    """CPU oracle over one synthetic contig (short + long blocks)."""
+    blocks = c.blocks.cpu().numpy()
+    ob = np.empty(len(blocks), O.BLOCK_DTYPE)
+    ob["start0"] = blocks[:, 0]; ob["len_mapq"] = blocks[:, 1].view(np.uint32)
+    depth, tally = O.depth_from_blocks(ob, c.length, c.obs.cpu().numpy().view(np.uint32) if c.snp_pos1.shape[0] else None,
+                                       c.snp_pos1.shape[0], mapq_threshold)
+    lb = c.long_blocks.cpu().numpy()
+    for s, l, mq, _ in lb:
+        if (1.0 - 10 ** (-mq * 0.1)) >= mapq_threshold:
+            depth[s + 1: s + 1 + l] += 1
+    sp = c.snp_pos1.cpu().numpy() if c.snp_pos1.shape[0] else None
+    sz = c.snp_zyg.cpu().numpy() if c.snp_pos1.shape[0] else None
+    return O.bin_reduce(depth, c.length, W, sp, sz, tally)
+
+
+def assert_bins_equal(got, want):
+    assert len(got.bin) == len(want["bin"])
+    for k in ("bin", "start", "end", "n"):
+        np.testing.assert_array_equal(np.asarray(getattr(got, k)), want[k], err_msg=k)
+    np.testing.assert_array_equal(np.asarray(got.median), want["median"])
+    np.testing.assert_array_equal(np.asarray(got.total), want["total"])
+    np.testing.assert_array_equal(np.asarray(got.mse).view(np.uint64), want["mse"].view(np.uint64))   # bit-exact f64
+
+
+@pytest.mark.parametrize("W,cov,tile_bins", [(100, 30, 0), (100, 30, 32), (100, 30, 256), (50, 100, 0), (100, 3, 64), (7, 30, 0), (1000, 30, 0)])
+def test_binning_matches_oracle_host_buffers(ctx, W, cov, tile_bins):
+    g = synth.make_genome(coverage=cov, scale=0.0015, device="cpu", contigs=["chr10", "chr11", "chr21", "chrY"], seed=1234 + W)
+    api_contigs = synth.to_api_contigs(g, host=True)
+    res = ctx.bin_contigs(api_contigs, bin_width=W, max_block_len=synth.READ_LEN, tile_bins=tile_bins)
+    assert res.contig_offset[0] == 0 and len(res.contig_offset) == len(g) + 1
+    for i, c in enumerate(g):
+        assert_bins_equal(res.contig(i), oracle_bins(c, W))
+
+
+def test_binning_device_buffers_and_default_lookback(ctx):
+    import torch
+    g = synth.make_genome(coverage=30, scale=0.003, device="cuda", contigs=["chr1", "chr2", "chrX"], seed=99)
+    res = ctx.bin_contigs(synth.to_api_contigs(g), bin_width=100)          # max_block_len left at HCNV_SHORT_MAX
+    torch.cuda.synchronize()
+    for i, c in enumerate(g):
+        r = res.contig(i)
+        got = H.BinsResult(*[x.cpu().numpy() for x in (r.bin, r.start, r.end, r.median, r.mse, r.total, r.n)], r.contig_offset)
+        assert_bins_equal(got, oracle_bins(c, 100))
+
+
+def test_binning_edge_cases(ctx):
+    # empty contig, contig shorter than a bin, block ending exactly at the contig end, VCF-only bins, deep pile-up
+    # (depth range > 64 inside one bin exercises the wide distinct-set path), SNP at position 0 is never produced
+    W = 100
+    starts = [0] * 300 + [5] * 40 + list(range(10, 90)) + [950]
+    lens = [50] * 300 + [90] * 40 + [30] * 80 + [50]
+    order = np.argsort(starts, kind="stable")
+    blocks = H.pack_blocks(np.array(starts)[order], np.array(lens)[order])
+    snp = np.array([20, 45, 520, 777, 1000], np.int32); zyg = np.array([-1, -2, 0, -1, -2], np.int8)
+    obs = []
+    depth, _ = O.depth_from_blocks(blocks.view(O.BLOCK_DTYPE), 1000)
+    rng = np.random.default_rng(5)
+    for si, p in enumerate(snp):
+        for _ in range(int(depth[p])):
+            obs.append((si << 4) | int(rng.choice([1, 2, 4, 8, 15])))
+    obs = np.array(obs, np.uint32)
+    contigs = [H.Contig(1000, blocks, None, snp, zyg, obs), H.Contig(5000), H.Contig(37, H.pack_blocks([0, 30], [37, 7])),
+               H.Contig(100, H.pack_blocks([99], [1]))]
+    res = ctx.bin_contigs(contigs, bin_width=W)
+    want0 = O.bin_contig(blocks.view(O.BLOCK_DTYPE), 1000, W, snp, zyg, obs)
+    assert_bins_equal(res.contig(0), want0)
+    assert len(res.contig(1).bin) == 0
+    assert_bins_equal(res.contig(2), O.bin_contig(O.pack_blocks([0, 30], [37, 7]), 37, W))
+    w3 = O.bin_contig(O.pack_blocks([99], [1]), 100, W)
+    assert_bins_equal(res.contig(3), w3)
+    assert list(w3["bin"]) == [100] and list(w3["start"]) == [100]
+
+
+def test_binning_mapq_threshold(ctx):
+    g = synth.make_genome(coverage=20, scale=0.001, device="cpu", contigs=["chr21"], seed=5, het_per_bp=0, hom_per_bp=0)
+    thr = 0.9                                      # 1 - 10^(-q/10) >= 0.9  <=>  q >= 10
+    res = ctx.bin_contigs(synth.to_api_contigs(g, host=True), mapping_quality_threshold=thr, max_block_len=150)
+    assert_bins_equal(res.contig(0), oracle_bins(g[0], 100, thr))
+
+
+def test_binning_rejects_bad_input(ctx):
+    b = H.pack_blocks([10, 5], [20, 20])
+    with pytest.raises(H.HcnvError) as e:
+        ctx.bin_contigs([H.Contig(1000, b)])
+    assert e.value.status == L.HCNV_E_UNSORTED
+    with pytest.raises(H.HcnvError) as e:
+        ctx.bin_contigs([H.Contig(100, H.pack_blocks([90], [20]))])
+    assert e.value.status == L.HCNV_E_RANGE
+    with pytest.raises(H.HcnvError) as e:
+        ctx.bin_contigs([H.Contig(1000, H.pack_blocks([90], [200]))], max_block_len=150)
+    assert e.value.status == L.HCNV_E_RANGE
+    snp = np.array([100], np.int32); zyg = np.array([-1], np.int8)
+    with pytest.raises(H.HcnvError) as e:      # two blocks cover the site but only one observation
+        ctx.bin_contigs([H.Contig(1000, H.pack_blocks([90, 95], [20, 20]), None, snp, zyg, np.array([1], np.uint32))])
+    assert e.value.status == L.HCNV_E_INCONSISTENT
+
+
+def test_text_roundtrip_conversion(ctx):
+    rng = np.random.default_rng(17)
+    n = 6000
+    mse = rng.random((n, 6)) ** 3
+    # exact float midpoints (the printed decimal decides) and sums of float-exact squares
+    fl = rng.random(n).astype(np.float32)
+    mid = (fl.astype(np.float64) + np.nextafter(fl, f32(2)).astype(np.float64)) / 2
+    mse[:, 0] = mid
+    a = (rng.random(n).astype(np.float32) ** 2).astype(np.float64); b = (rng.random(n).astype(np.float32) ** 2).astype(np.float64)
+    mse[:, 1] = (a + b) / 2
+    mse[:, 2] = np.ldexp(1.0, -rng.integers(1, 60, n)) * (1 + np.ldexp(1.0, -24))     # midpoints across binades
+    mse[:5, 3] = [0.0, 1.0, 0.25, 2.0 ** -44, 1e-300]
+    total = np.concatenate([rng.integers(0, 5000, n - 3).astype(np.float64), [2.0 ** 24 + 1, 2.0 ** 25 + 2, 123456789.0]])
+    m32, t32 = ctx.bins_to_hmm_input(mse, total)
+    np.testing.assert_array_equal(m32.view(np.uint32), O.f64_text_f32(mse).view(np.uint32))
+    np.testing.assert_array_equal(t32.view(np.uint32), O.f64_text_f32(total).view(np.uint32))
+    assert (m32[:, 0] != mid.astype(np.float32)).any()       # the midpoint cases really differ from a plain cast
+
+
+@pytest.mark.parametrize("seed,M,l1,l2", [(1, 5000, 0.01, 1.6), (2, 3333, 0.3, 0.4), (3, 700, -1.0, -1.0), (4, 2, 0.01, 1.6),
+                                          (5, 1, 0.01, 1.6), (6, 120, 0.01, 0.01), (7, 33, 0.05, 3.2), (8, 64, 0.1, 0.8)])
+def test_hmm_matches_oracle(ctx, seed, M, l1, l2):
+    rng = np.random.default_rng(seed)
+    b = Hp.random_bins(rng, M)
+    mse32 = O.f64_text_f32(b["mse"]); tot32 = O.f64_text_f32(b["total"])
+    want = O.hmm(b["median"], mse32, tot32, b["n"], l1, l2)
+    got = ctx.segment_batch([dict(median=b["median"], mse=mse32, total=tot32, n=b["n"], lambda1=l1, lambda2=l2, want_sd=1)])[0]
+    assert got["status"] == want["rc"]
+    np.testing.assert_array_equal(got["state"], want["state"])
+    np.testing.assert_array_equal(got["cn"], want["cn"])
+    np.testing.assert_array_equal(got["scaled"].view(np.uint32), want["scaled"].view(np.uint32))
+    for k in ("mean_coverage", "sd", "lambda1", "lambda2", "final_loss"):
+        assert f32(got[k]).view(np.uint32) == f32(want[k]).view(np.uint32), k
+    if want["rc"] == 0:
+        np.testing.assert_array_equal(got["last_row"].view(np.uint32), want["last_row"].view(np.uint32))
+
+
+def test_hmm_batch_of_chromosomes_long(ctx):
+    """Several chromosomes in one call, long enough that the float order matters."""
+    rng = np.random.default_rng(21)
+    probs, wants = [], []
+    for M, l1, l2 in [(200000, 0.01, 1.6), (150001, 0.3, 0.4), (40000, 0.05, 0.8)]:
+        b = Hp.random_bins(rng, M)
+        mse32 = b["mse"].astype(np.float32); tot32 = b["total"].astype(np.float32)
+        probs.append(dict(median=b["median"], mse=mse32, total=tot32, n=b["n"], lambda1=l1, lambda2=l2))
+        wants.append(O.hmm(b["median"], mse32, tot32, b["n"], l1, l2, fast=True))
+    gots = ctx.segment_batch(probs)
+    for got, want in zip(gots, wants):
+        np.testing.assert_array_equal(got["state"], want["state"])
+        assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+        assert f32(got["mean_coverage"]).view(np.uint32) == f32(want["mean_coverage"]).view(np.uint32)
+
+
+def test_hmm_nan_and_degenerate_inputs(ctx):
+    M = 50
+    med = np.full(M, 20, np.float32); mse = np.zeros((M, 6), np.float32); tot = np.full(M, 2000, np.float32); n = np.full(M, 100, np.int32)
+    mse[10, 2] = np.nan; mse[20, :] = np.inf
+    want = O.hmm(med, mse, tot, n, 0.01, 1.6)
+    got = ctx.segment_batch([dict(median=med, mse=mse, total=tot, n=n, lambda1=0.01, lambda2=1.6)], raise_on_exit=False)[0]
+    assert got["status"] == (L.HCNV_E_NO_MINIMUM if want["rc"] < 0 else want["rc"])
+    if want["rc"] >= 0:
+        np.testing.assert_array_equal(got["state"], want["state"])
+
+
+def test_end_to_end_bins_to_calls(ctx):
+    """reads -> bins -> text-equivalent float conversion -> calls, chromosome by chromosome, equals the oracle chain."""
+    g = synth.make_genome(coverage=30, scale=0.004, device="cpu", contigs=["chr15", "chr16"], seed=77)
+    res = ctx.bin_contigs(synth.to_api_contigs(g, host=True), max_block_len=150)
+    for i, c in enumerate(g):
+        r = res.contig(i)
+        want_b = oracle_bins(c, 100)
+        assert_bins_equal(r, want_b)
+        m32, t32 = ctx.bins_to_hmm_input(r.mse, r.total)
+        want = O.hmm(want_b["median"], O.f64_text_f32(want_b["mse"]), O.f64_text_f32(want_b["total"]), want_b["n"], 0.01, 1.6)
+        got = ctx.segment_batch([dict(median=r.median, mse=m32, total=t32, n=r.n, lambda1=0.01, lambda2=1.6)])[0]
+        np.testing.assert_array_equal(got["state"], want["state"])
+        np.testing.assert_array_equal(got["scaled"].view(np.uint32), want["scaled"].view(np.uint32))
+        assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
