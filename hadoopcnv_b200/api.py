@@ -128,6 +128,15 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._lib.hcnv_ctx_kernel_launches(self._h))
 
+    def kernel_ms(self) -> dict:
+        """Device time (ms, CUDA events on the context's stream) of the most recent launch of each kernel."""
+        out = {}
+        for name, k in L.KERNELS.items():
+            v = float(self._lib.hcnv_ctx_kernel_ms(self._h, k))
+            if v >= 0:
+                out[name] = v
+        return out
+
     def synchronize(self):
         self._check(self._lib.hcnv_ctx_synchronize(self._h))
 

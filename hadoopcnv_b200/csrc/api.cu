@@ -46,6 +46,9 @@ int hcnv_ctx_create(int device, hcnv_ctx** out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return HCNV_E_CUDA; }
+    for (int i = 0; i < HCNV_K_COUNT; ++i) {
+        if (cudaEventCreate(&c->kt_a[i]) != cudaSuccess || cudaEventCreate(&c->kt_b[i]) != cudaSuccess) { delete c; return HCNV_E_CUDA; }
+    }
     *out = c;
     return HCNV_OK;
 }
@@ -56,6 +59,7 @@ void hcnv_ctx_destroy(hcnv_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& b : c->buf) b.release();
     for (auto& b : c->pin) b.release();
+    for (int i = 0; i < HCNV_K_COUNT; ++i) { if (c->kt_a[i]) cudaEventDestroy(c->kt_a[i]); if (c->kt_b[i]) cudaEventDestroy(c->kt_b[i]); }
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -68,6 +72,14 @@ int hcnv_ctx_synchronize(hcnv_ctx* c) {
     if (!c) return HCNV_E_INVALID;
     HCNV_CUDA(c, cudaStreamSynchronize(c->stream));
     return HCNV_OK;
+}
+
+float hcnv_ctx_kernel_ms(hcnv_ctx* c, int which) {
+    if (!c || which < 0 || which >= HCNV_K_COUNT || !c->kt_valid[which]) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(c->kt_b[which]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, c->kt_a[which], c->kt_b[which]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    return ms;
 }
 
 int hcnv_bin_contigs(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t n_contigs,

@@ -581,8 +581,11 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     HCNV_CUDA(ctx, cudaMemsetAsync(k.status, 0, 8 * (size_t)n_tiles, ctx->stream));
     if (tot_snp) HCNV_CUDA(ctx, cudaMemsetAsync(k.tally, 0, 64 * (size_t)tot_snp, ctx->stream));
 
+    KT_BEGIN(ctx, HCNV_K_TILE_INDEX);
     k_tile_index<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(k);
+    KT_END(ctx, HCNV_K_TILE_INDEX);
     ctx->launches++;
+    KT_BEGIN(ctx, HCNV_K_TALLY);
     for (int c = 0; c < n_contigs; ++c) {
         if (hc[c].n_obs == 0) continue;
         long long nb = (hc[c].n_obs + 255) / 256;
@@ -590,6 +593,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         k_tally<<<grid, 256, 0, ctx->stream>>>(hc[c].obs, hc[c].n_obs, hc[c].n_snp, k.tally + 16 * (size_t)hc[c].snp_base, k.err);
         ctx->launches++;
     }
+    KT_END(ctx, HCNV_K_TALLY);
+    KT_BEGIN(ctx, HCNV_K_BIN_TILES);
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
@@ -599,6 +604,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     if (W % 4 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<4>));
     else if (W % 2 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<2>));
     else HCNV_CUDA(ctx, launch(k_bin_tiles<1>));
+    KT_END(ctx, HCNV_K_BIN_TILES);
     ctx->launches++;
 
     // results: error flags + contig offsets always come back to the host

@@ -52,7 +52,12 @@ struct hcnv_ctx {
     std::string  err;
     DevBuf       buf[HCNV_NBUF];      // named scratch slots, see the .cu files
     PinBuf       pin[4];
+    cudaEvent_t  kt_a[HCNV_K_COUNT] = {};  // per-kernel start/stop events on `stream`
+    cudaEvent_t  kt_b[HCNV_K_COUNT] = {};
+    bool         kt_valid[HCNV_K_COUNT] = {};
 };
+#define KT_BEGIN(ctx, slot) cudaEventRecord((ctx)->kt_a[slot], (ctx)->stream)
+#define KT_END(ctx, slot)   do { cudaEventRecord((ctx)->kt_b[slot], (ctx)->stream); (ctx)->kt_valid[slot] = true; } while (0)
 
 #define HCNV_CUDA(ctx, call)                                                                   \
     do {                                                                                       \

@@ -353,7 +353,9 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
         d_mse = di; d_tot = total ? di + 6 * n : nullptr; d_m32 = fo; d_t32 = total ? fo + 6 * n : nullptr;
     }
     int grid = (int)std::min<long long>((n * 6 + 255) / 256, (long long)ctx->sm_count * 32);
+    KT_BEGIN(ctx, HCNV_K_TEXT_ROUNDTRIP);
     k_text_roundtrip<<<grid, 256, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32);
+    KT_END(ctx, HCNV_K_TEXT_ROUNDTRIP);
     ctx->launches++;
     HCNV_CUDA(ctx, cudaGetLastError());
     if (!dev) {
@@ -432,11 +434,21 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
     HCNV_CUDA(ctx, cudaMemcpyAsync(d_prob, blk_prob.data(), 4 * nblk, cudaMemcpyHostToDevice, ctx->stream));
 
     const int wpb = 4;   // warps per block for the one-warp-per-chromosome kernels
+    KT_BEGIN(ctx, HCNV_K_MEAN_COVERAGE);
     k_mean_coverage<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
+    KT_END(ctx, HCNV_K_MEAN_COVERAGE);
+    KT_BEGIN(ctx, HCNV_K_SCALE_DEPTH);
     k_scale_depth<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_prob, d_first);
+    KT_END(ctx, HCNV_K_SCALE_DEPTH);
+    KT_BEGIN(ctx, HCNV_K_SD);
     k_sd<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
+    KT_END(ctx, HCNV_K_SD);
+    KT_BEGIN(ctx, HCNV_K_VITERBI);
     k_viterbi_seq<<<n_problems, 32, 0, ctx->stream>>>(dprobs, alpha);
+    KT_END(ctx, HCNV_K_VITERBI);
+    KT_BEGIN(ctx, HCNV_K_TRACEBACK);
     k_traceback<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_prob, d_first);
+    KT_END(ctx, HCNV_K_TRACEBACK);
     ctx->launches += 5;
     HCNV_CUDA(ctx, cudaGetLastError());
     HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), dprobs, sizeof(SegDev) * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));

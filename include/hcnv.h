@@ -63,6 +63,18 @@ void*       hcnv_ctx_stream(hcnv_ctx* ctx);
 /* number of kernels this context has launched so far */
 int64_t     hcnv_ctx_kernel_launches(const hcnv_ctx* ctx);
 int         hcnv_ctx_synchronize(hcnv_ctx* ctx);
+/* device time in ms (CUDA events on the context's stream) of the most recent launch of one kernel; -1 if never launched */
+#define HCNV_K_TILE_INDEX      0
+#define HCNV_K_TALLY           1
+#define HCNV_K_BIN_TILES       2
+#define HCNV_K_TEXT_ROUNDTRIP  3
+#define HCNV_K_MEAN_COVERAGE   4
+#define HCNV_K_SCALE_DEPTH     5
+#define HCNV_K_SD              6
+#define HCNV_K_VITERBI         7
+#define HCNV_K_TRACEBACK       8
+#define HCNV_K_COUNT          16
+float       hcnv_ctx_kernel_ms(hcnv_ctx* ctx, int which);
 
 /* ---- B1: binning ------------------------------------------------------------------------------ */
 
