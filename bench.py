@@ -400,7 +400,7 @@ def run_b200(args):
             "reads_per_s_binned": g_reads / (sum(kavg.get(k_, 0) for k_ in ("tile_index", "tally", "bin_tiles")) / 1e3) if kavg.get("bin_tiles") else None,
             "kernel_ms": kavg, "gpu_launches": g_launches, "clocks": clock_info,
             "roofline": roofline, "roofline_binning": roofline_binning, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "checks": {"final_loss_sum_rank0": float(np.sum(final_losses)), "input_generation_s": t_gen},
+            "checks": {"final_loss_sum_rank0": float(np.sum(final_losses)), "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
         }
         print(json.dumps(line))
     sys.stdout.flush()

@@ -15,7 +15,8 @@ HCNV_E_INVALID, HCNV_E_CUDA, HCNV_E_NOMEM, HCNV_E_RANGE, HCNV_E_UNSORTED = -1, -
 HCNV_E_INCONSISTENT, HCNV_E_NO_MINIMUM, HCNV_E_IO, HCNV_E_PARSE, HCNV_E_CAPACITY, HCNV_E_INTERNAL = -6, -7, -8, -9, -10, -11
 HCNV_SHORT_MAX = 4095
 HCNV_SEG_SEQUENTIAL = 1
-KERNELS = dict(tile_index=0, tally=1, bin_tiles=2, text_roundtrip=3, mean_coverage=4, scale_depth=5, sd=6, viterbi=7, traceback=8)
+KERNELS = dict(tile_index=0, tally=1, bin_tiles=2, text_roundtrip=3, mean_coverage=4, scale_depth=5, sd=6, viterbi=7, traceback=8,
+               vit_p0=9, vit_p0c=10, vit_p1=11, vit_p2=12, vit_p3=13)
 
 
 class HcnvError(RuntimeError):
@@ -63,7 +64,7 @@ class Config(C.Structure):
 # every symbol include/hcnv.h declares (tests check the library exports all of them)
 EXPORTS = [
     "hcnv_abi_sizes", "hcnv_ctx_create", "hcnv_ctx_destroy", "hcnv_last_error", "hcnv_strerror", "hcnv_version", "hcnv_ctx_stream",
-    "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_bin_params_default", "hcnv_bin_contigs",
+    "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_ctx_stat", "hcnv_bin_params_default", "hcnv_bin_contigs",
     "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
     "hcnv_write_bins_text", "hcnv_write_results_text",
 ]
@@ -102,6 +103,8 @@ def lib():
     L.hcnv_ctx_synchronize.argtypes = [C.c_void_p]
     L.hcnv_ctx_kernel_ms.argtypes = [C.c_void_p, C.c_int]
     L.hcnv_ctx_kernel_ms.restype = C.c_float
+    L.hcnv_ctx_stat.argtypes = [C.c_void_p, C.c_int]
+    L.hcnv_ctx_stat.restype = C.c_int64
     L.hcnv_bin_params_default.argtypes = [C.POINTER(BinParams)]
     L.hcnv_bin_params_default.restype = None
     L.hcnv_bin_contigs.argtypes = [C.c_void_p, C.POINTER(BinParams), C.c_int32, C.POINTER(ContigInput), C.POINTER(Bins)]

@@ -137,6 +137,14 @@ class Context:
                 out[name] = v
         return out
 
+    def stats(self) -> dict:
+        """Counters of the last segment_batch call (hcnv_ctx_stat)."""
+        f = self._lib.hcnv_ctx_stat
+        return dict(viterbi_segments=int(f(self._h, 0)), viterbi_segments_replayed=int(f(self._h, 1)),
+                    viterbi_repairs=int(f(self._h, 2)),
+                    diag=dict(zip(("p1_segments", "p1_overflow", "p1_inf", "p1_with_ties", "p2_no_binade", "p2_flagged",
+                                   "p2_exponent_mismatch", "p2_leaves_binade"), [int(f(self._h, 16 + i)) for i in range(8)])))
+
     def synchronize(self):
         self._check(self._lib.hcnv_ctx_synchronize(self._h))
 

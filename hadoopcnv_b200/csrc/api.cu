@@ -74,6 +74,12 @@ int hcnv_ctx_synchronize(hcnv_ctx* c) {
     return HCNV_OK;
 }
 
+int64_t hcnv_ctx_stat(const hcnv_ctx* c, int which) {
+    if (!c) return -1;
+    if (which >= 16 && which < 32) return c->vdbg[which - 16];
+    switch (which) { case 0: return c->vit_segments; case 1: return c->vit_replayed; case 2: return c->vit_repairs; default: return -1; }
+}
+
 float hcnv_ctx_kernel_ms(hcnv_ctx* c, int which) {
     if (!c || which < 0 || which >= HCNV_K_COUNT || !c->kt_valid[which]) return -1.f;
     float ms = -1.f;

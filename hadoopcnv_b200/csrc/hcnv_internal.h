@@ -49,6 +49,8 @@ struct hcnv_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int64_t      launches = 0;
+    int64_t      vit_segments = 0, vit_replayed = 0, vit_repairs = 0;
+    int          vdbg[16] = {};
     std::string  err;
     DevBuf       buf[HCNV_NBUF];      // named scratch slots, see the .cu files
     PinBuf       pin[4];

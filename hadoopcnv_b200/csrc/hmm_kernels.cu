@@ -135,7 +135,10 @@ struct SegDev {
     int            want_sd;
     // results
     float          mean, sd, l1u, l2u, final_loss, last_row[6];
-    int            status, sstar, skip, pad;
+    int            status, sstar, skip;
+    int            par;            // 1: exact segment-parallel path (viterbi_par.cuh), 0: one-warp sequential kernel
+    int            irregular;      // NaN / negative / infinite inputs or penalties: only the literal sequential kernel is exact
+    int            n_seg, first_bad, pad;
 };
 
 __constant__ float c_mu[6] = {-1.0f, -0.5f, 0.f, 0.f, 0.5f, 1.0f};   // Hmm.java:34
@@ -146,6 +149,7 @@ __global__ void k_mean_coverage(SegDev* probs, int n_probs) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_probs) return;
     SegDev& P = probs[w];
+    if (!P.pad) return;                              // k_mean_coverage_par already did it exactly
     const long long M = P.M;
     float s = 0.f;
     int sites = 0;
@@ -170,6 +174,121 @@ __global__ void k_mean_coverage(SegDev* probs, int n_probs) {
     if (lane == 0) P.mean = __fdiv_rn(s, (float)sites);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same sequential float sum, evaluated exactly in parallel (one CTA per chromosome).
+// Per-bin totals are non-negative integers.  Below 2^24 every partial sum is exact.  Inside a binade
+// [2^e, 2^(e+1)), e >= 24, the sum is a multiple of u = 2^(e-23); with S = s*u and t = q*u + r:
+//   fl(S + t) = (s + q + c) * u,  c = 0 if r < u/2, 1 if r > u/2, and for r == u/2 (a tie) c = (s + q) & 1.
+// So each element is a map  s -> s + a[s & 1]  and maps compose associatively: a block scan over a window of
+// elements gives the exact running sum.  When the sum leaves the binade, the crossing element is added with one
+// real float add and the next binade starts behind it.  Totals that are not non-negative integers fall back to the
+// sequential warp kernel above.
+struct PMap { long long a0, a1; };
+__device__ __forceinline__ PMap pm_compose(const PMap& f, const PMap& g) {     // f first, then g
+    PMap r;
+    r.a0 = f.a0 + ((f.a0 & 1) ? g.a1 : g.a0);
+    r.a1 = f.a1 + (((f.a1 + 1) & 1) ? g.a1 : g.a0);
+    return r;
+}
+__device__ __forceinline__ PMap pm_shfl_up(const PMap& m, int o) {
+    PMap r; r.a0 = __shfl_up_sync(0xffffffffu, m.a0, o); r.a1 = __shfl_up_sync(0xffffffffu, m.a1, o); return r;
+}
+#define MC_T 512
+#define MC_K 16
+__global__ void __launch_bounds__(MC_T) k_mean_coverage_par(SegDev* probs) {
+    __shared__ float s_el[MC_T * (MC_K + 1)];
+    __shared__ PMap s_w[MC_T / 32];
+    __shared__ long long s_sbefore;
+    __shared__ int s_cross, s_int[2];
+    SegDev& P = probs[blockIdx.x];
+    const long long M = P.M;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* __restrict__ tot = P.total;
+    // pass 0: int sum of sites (wraps like Java's int) and the "non-negative integers" test
+    int sites = 0, okint = 1;
+    for (long long i = tid; i < M; i += MC_T) {
+        float t = __ldg(&tot[i]);
+        sites += __ldg(&P.n[i]);
+        okint &= (t >= 0.f && t < 9.0e18f && t == truncf(t)) ? 1 : 0;
+    }
+    if (tid == 0) { s_int[0] = 0; s_int[1] = 1; }
+    __syncthreads();
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sites += __shfl_xor_sync(0xffffffffu, sites, o); okint &= __shfl_xor_sync(0xffffffffu, okint, o); }
+    if (lane == 0) { atomicAdd(&s_int[0], sites); atomicAnd(&s_int[1], okint); }
+    __syncthreads();
+    sites = s_int[0];
+    if (!s_int[1]) { if (tid == 0) P.mean = __int_as_float(0x7fc00001); P.pad = 1; return; }   // marker: sequential kernel takes over
+    float S = 0.f;
+    long long pos = 0;
+    while (pos < M) {
+        const int e = (S >= 16777216.f) ? (int)((__float_as_uint(S) >> 23) & 0xffu) - 127 : 23;
+        const int sh = e - 23;
+        const long long msk = (1ll << sh) - 1, half = sh > 0 ? (1ll << (sh - 1)) : -1;
+        const long long thr = 1ll << 24;
+        const long long s_start = (long long)S >> sh;
+        const int wlen = (int)min((long long)MC_T * MC_K, M - pos);
+        __syncthreads();
+        for (int g = tid; g < wlen; g += MC_T) s_el[(g / MC_K) * (MC_K + 1) + (g % MC_K)] = __ldg(&tot[pos + g]);
+        if (tid == 0) s_cross = 0x7fffffff;
+        __syncthreads();
+        const int first = tid * MC_K, cnt = max(0, min(MC_K, wlen - first));
+        PMap f; f.a0 = 0; f.a1 = 0;
+        for (int k2 = 0; k2 < cnt; ++k2) {
+            long long ti = (long long)s_el[tid * (MC_K + 1) + k2];
+            long long q = ti >> sh, r = ti & msk;
+            long long up = r > half && sh > 0 ? 1 : 0;
+            bool tie = r == half;
+            f.a0 += q + (tie ? ((f.a0 + q) & 1) : up);
+            f.a1 += q + (tie ? ((1 + f.a1 + q) & 1) : up);
+        }
+        // ordered block scan of the maps
+        PMap inc = f;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { PMap u = pm_shfl_up(inc, o); if (lane >= o) inc = pm_compose(u, inc); }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            PMap w; w.a0 = 0; w.a1 = 0;
+            if (lane < MC_T / 32) w = s_w[lane];
+            PMap wi = w;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { PMap u = pm_shfl_up(wi, o); if (lane >= o) wi = pm_compose(u, wi); }
+            if (lane < MC_T / 32) s_w[lane] = wi;                      // inclusive over warps
+        }
+        __syncthreads();
+        const PMap wtot = s_w[MC_T / 32 - 1];
+        const long long s_end = s_start + ((s_start & 1) ? wtot.a1 : wtot.a0);
+        if (s_end < thr) { S = (float)(s_end << sh); pos += wlen; continue; }
+        // the sum leaves the binade inside this window: find the first element whose result reaches 2^(e+1)
+        PMap ex; ex.a0 = 0; ex.a1 = 0;                                  // exclusive prefix of this thread
+        {
+            PMap prevw; prevw.a0 = 0; prevw.a1 = 0;
+            if (wid > 0) prevw = s_w[wid - 1];
+            PMap lanex = pm_shfl_up(inc, 1);
+            if (lane == 0) { lanex.a0 = 0; lanex.a1 = 0; }
+            ex = pm_compose(prevw, lanex);
+        }
+        long long sv = s_start + ((s_start & 1) ? ex.a1 : ex.a0);
+        int mycross = 0x7fffffff; long long mybefore = 0;
+        for (int k2 = 0; k2 < cnt; ++k2) {
+            long long ti = (long long)s_el[tid * (MC_K + 1) + k2];
+            long long q = ti >> sh, r = ti & msk;
+            long long nx = sv + q + ((r == half) ? ((sv + q) & 1) : ((r > half && sh > 0) ? 1 : 0));
+            if (nx >= thr && mycross == 0x7fffffff) { mycross = first + k2; mybefore = sv; }
+            sv = nx;
+        }
+        if (mycross != 0x7fffffff) atomicMin(&s_cross, mycross);
+        __syncthreads();
+        const int ic = s_cross;
+        if (mycross == ic) s_sbefore = mybefore;
+        __syncthreads();
+        S = __fadd_rn((float)(s_sbefore << sh), s_el[(ic / MC_K) * (MC_K + 1) + (ic % MC_K)]);   // the one real float add
+        pos += ic + 1;
+    }
+    if (tid == 0) P.mean = __fdiv_rn(S, (float)sites);
+}
+
 // scale_depth, Hmm.java:121-135 (element-wise; all problems in one launch via a block->problem map)
 __global__ void k_scale_depth(SegDev* probs, const int* __restrict__ blk_prob, const long long* __restrict__ blk_first) {
     SegDev& P = probs[blk_prob[blockIdx.x]];
@@ -183,7 +302,7 @@ __global__ void k_scale_depth(SegDev* probs, const int* __restrict__ blk_prob, c
 }
 
 // get_sd, Hmm.java:103-119: two sequential float passes; one warp per chromosome
-__global__ void k_sd(SegDev* probs, int n_probs) {
+__global__ void k_sd(SegDev* probs, int n_probs, float alpha) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_probs) return;
     SegDev& P = probs[w];
@@ -224,6 +343,9 @@ __global__ void k_sd(SegDev* probs, int n_probs) {
         P.status = P.skip ? HCNV_VITERBI_SKIPPED : HCNV_OK;
         P.final_loss = 0.f; P.sstar = 0;
         for (int s = 0; s < 6; ++s) P.last_row[s] = 0.f;
+        // the parallel path assumes finite, non-negative addends (sign bit clear), i.e. 0 <= alpha <= 1 and penalties >= +0
+        bool okp = __float_as_uint(l1) < 0x7f800000u && __float_as_uint(l2) < 0x7f800000u && alpha >= 0.f && alpha <= 1.f;
+        if (!okp) P.irregular = 1;
     }
 }
 
@@ -239,6 +361,7 @@ __global__ void __launch_bounds__(32) k_viterbi_seq(SegDev* probs, float alpha) 
     const int lane = threadIdx.x;
     const long long M = P.M;
     if (P.skip) return;
+    if (P.par && !P.irregular) return;               // done by the segment-parallel path
     const int c = lane < 6 ? lane : 0;
     const float oma = __fsub_rn(1.f, alpha);
     const float l1 = P.l1u, l2 = P.l2u;
@@ -317,6 +440,7 @@ __global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_prob, con
     long long i = blk_first[blockIdx.x] + threadIdx.x;
     const long long M = P.M;
     if (i >= M) return;
+    if (P.par && !P.irregular && !P.skip) return;    // k_vit_p3 already wrote the calls
     int st = 0;
     if (!P.skip) {
         int s = P.sstar;
@@ -327,11 +451,13 @@ __global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_prob, con
     if (P.cn) P.cn[i] = c_cn[st];
 }
 
+#include "viterbi_par.cuh"
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
 namespace {
-enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT };
+enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR };
 }
 
 int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
@@ -396,6 +522,8 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
     }
     long long off = 0;
     std::vector<int> blk_prob; std::vector<long long> blk_first;
+    const int VSEG = VSEG_DEFAULT;
+    std::vector<int> seg_base(n_problems + 1, 0);
     for (int i = 0; i < n_problems; ++i) {
         hcnv_segment_problem& q = probs[i];
         SegDev& d = h[i];
@@ -422,7 +550,12 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         }
         for (long long b = 0; b < M; b += 256) { blk_prob.push_back(i); blk_first.push_back(b); }
         off += M;
+        d.par = (!(flags & HCNV_SEG_SEQUENTIAL) && M >= V_PAR_MIN_MARKERS) ? 1 : 0;
+        d.n_seg = d.par ? (int)((M - 1 + VSEG - 1) / VSEG) : 0;
+        d.first_bad = 0x7fffffff;
+        seg_base[i + 1] = seg_base[i] + d.n_seg;
     }
+    const int total_segs = seg_base[n_problems];
     const size_t nblk = blk_prob.size();
     HCNV_CUDA(ctx, ctx->buf[H_PROBS].reserve(sizeof(SegDev) * (size_t)n_problems));
     HCNV_CUDA(ctx, ctx->buf[H_BLKMAP].reserve(12 * nblk + 64));
@@ -435,21 +568,75 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
 
     const int wpb = 4;   // warps per block for the one-warp-per-chromosome kernels
     KT_BEGIN(ctx, HCNV_K_MEAN_COVERAGE);
+    k_mean_coverage_par<<<n_problems, MC_T, 0, ctx->stream>>>(dprobs);
     k_mean_coverage<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
     KT_END(ctx, HCNV_K_MEAN_COVERAGE);
     KT_BEGIN(ctx, HCNV_K_SCALE_DEPTH);
     k_scale_depth<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_prob, d_first);
     KT_END(ctx, HCNV_K_SCALE_DEPTH);
     KT_BEGIN(ctx, HCNV_K_SD);
-    k_sd<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
+    k_sd<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems, alpha);
     KT_END(ctx, HCNV_K_SD);
+    ctx->launches += 4;
+
+    // ---- exact segment-parallel Viterbi for the long chromosomes (viterbi_par.cuh)
+    if (total_segs > 0) {
+        const size_t S = (size_t)total_segs;
+        size_t o_seg = 0, o_epred = o_seg + 4 * (size_t)(n_problems + 1), o_flags = o_epred + 4 * S, o_force = o_flags + 4 * S;
+        size_t o_repl = o_force + 4 * S, o_tf = (o_repl + 4 * (size_t)n_problems + 255) / 256 * 256, o_ti = o_tf + 144 * S;
+        size_t o_ls = o_ti + 288 * S, bytes = o_ls + 24 * (S + (size_t)n_problems);
+        HCNV_CUDA(ctx, ctx->buf[H_VPAR].reserve(bytes));
+        char* vb = ctx->buf[H_VPAR].as<char>();
+        int* d_segbase = (int*)(vb + o_seg); int* d_epred = (int*)(vb + o_epred); int* d_flags = (int*)(vb + o_flags);
+        int* d_force = (int*)(vb + o_force); int* d_repl = (int*)(vb + o_repl);
+        float* d_tf = (float*)(vb + o_tf); int* d_ti = (int*)(vb + o_ti); float* d_ls = (float*)(vb + o_ls);
+        HCNV_CUDA(ctx, cudaMemcpyAsync(d_segbase, seg_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream));
+        HCNV_CUDA(ctx, cudaMemsetAsync(d_force, 0, 4 * S, ctx->stream));
+        { int z[16] = {0}; HCNV_CUDA(ctx, cudaMemcpyToSymbolAsync(g_vdbg, z, sizeof z, 0, cudaMemcpyHostToDevice, ctx->stream)); }
+        const unsigned gs = (unsigned)((S + 127) / 128);
+        KT_BEGIN(ctx, HCNV_K_VIT_P0);
+        k_vit_p0<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_tf);
+        KT_END(ctx, HCNV_K_VIT_P0);
+        KT_BEGIN(ctx, HCNV_K_VIT_P0C);
+        k_vit_p0c<<<n_problems, 32, 0, ctx->stream>>>(dprobs, d_segbase, alpha, d_tf, d_epred);
+        KT_END(ctx, HCNV_K_VIT_P0C);
+        KT_BEGIN(ctx, HCNV_K_VIT_P1);
+        k_vit_p1<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_epred, d_ti, d_flags);
+        KT_END(ctx, HCNV_K_VIT_P1);
+        ctx->launches += 3;
+        for (int iter = 0; ; ++iter) {
+            KT_BEGIN(ctx, HCNV_K_VIT_P2);
+            k_vit_p2<<<n_problems, 32, 0, ctx->stream>>>(dprobs, d_segbase, VSEG, alpha, d_epred, d_ti, d_flags, d_force, d_ls, d_repl);
+            KT_END(ctx, HCNV_K_VIT_P2);
+            KT_BEGIN(ctx, HCNV_K_VIT_P3);
+            k_vit_p3<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_ls, d_force);
+            KT_END(ctx, HCNV_K_VIT_P3);
+            ctx->launches += 2;
+            HCNV_CUDA(ctx, cudaGetLastError());
+            HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), dprobs, sizeof(SegDev) * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
+            HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            bool again = false;
+            for (int i = 0; i < n_problems; ++i)
+                if (h[i].par && !h[i].irregular && !h[i].skip && h[i].first_bad != 0x7fffffff) again = true;
+            if (!again) break;
+            ctx->vit_repairs++;
+            if (iter >= 16) return hcnv_fail(ctx, HCNV_E_INTERNAL, "segment-parallel Viterbi did not converge");
+        }
+        std::vector<int> repl(n_problems, 0);
+        HCNV_CUDA(ctx, cudaMemcpyAsync(repl.data(), d_repl, 4 * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaMemcpyFromSymbolAsync(ctx->vdbg, g_vdbg, sizeof ctx->vdbg, 0, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->vit_segments = total_segs; ctx->vit_replayed = 0;
+        for (int i = 0; i < n_problems; ++i) if (h[i].par && !h[i].irregular && !h[i].skip) ctx->vit_replayed += repl[i];
+    } else { ctx->vit_segments = 0; ctx->vit_replayed = 0; }
+    // ---- everything else (short chromosomes, irregular inputs): the literal one-warp kernel
     KT_BEGIN(ctx, HCNV_K_VITERBI);
     k_viterbi_seq<<<n_problems, 32, 0, ctx->stream>>>(dprobs, alpha);
     KT_END(ctx, HCNV_K_VITERBI);
     KT_BEGIN(ctx, HCNV_K_TRACEBACK);
     k_traceback<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_prob, d_first);
     KT_END(ctx, HCNV_K_TRACEBACK);
-    ctx->launches += 5;
+    ctx->launches += 2;
     HCNV_CUDA(ctx, cudaGetLastError());
     HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), dprobs, sizeof(SegDev) * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
     if (!dev) {

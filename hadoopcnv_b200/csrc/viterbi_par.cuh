@@ -1,0 +1,513 @@
+// viterbi_par.cuh -- exact segment-parallel evaluation of Hmm.do_viterbi (Hmm.java:176-238).
+// Included by hmm_kernels.cu after SegDev / c_mu / c_cn are defined.
+//
+// The reference's recurrence is a float32 chain whose rounding order decides per-bin calls,
+// so a plain associative scan is not allowed.  What IS exact: while all six losses and the winning candidates of
+// a stretch of markers stay inside one float binade [2^e, 2^(e+1)), every add is  fl(L + y) = L + rnd_u(y)  with
+// u = 2^(e-23) (unless y/u has fractional part exactly 1/2: a tie whose direction depends on L's parity).  In units
+// of u the chain is therefore an INTEGER min-plus recurrence, which is associative:
+//
+//   P0  (thread / segment)  approximate float 6x6 min-plus transfer matrix of each segment of VSEG markers
+//   P0c (warp / chromosome) chain them in f64 -> predicted binade of every segment
+//   P1  (thread / segment)  exact integer transfer matrix for that binade; flags ties / overflow
+//   P2  (warp / chromosome) walk the segments with the EXACT start vector: apply the matrix when the segment is
+//                           flag-free and really inside its predicted binade, otherwise replay its markers with the
+//                           exact float step; stores the exact start vector of every segment, final arg-min state
+//   P3  (thread / segment)  replays every segment from its exact start vector with the reference's float
+//                           arithmetic, writes best_state / cn, and VERIFIES that it reproduces the next
+//                           segment's start vector bit for bit.  A mismatch (never seen; would mean a matrix was
+//                           applied outside its validity) marks the segment for forced replay and P2/P3 rerun.
+//
+// The result is therefore exact by verification, not by trust in the binade model.
+#pragma once
+#include <cuda_pipeline.h>
+
+#define VSEG_DEFAULT 128
+#define V_EMIN 6                   // binades below 2^6: u so small that per-segment sums could overflow int32 -> replay
+#define V_INF_I (1 << 29)
+#define V_INF_F 1.0e30f
+#define V_PAR_MIN_MARKERS 4096     // shorter chromosomes go to the one-warp kernel
+
+__device__ int g_vdbg[16];   // diagnostic counters (hcnv_ctx_stat 16..31)
+
+struct VitConsts {
+    float oma, alpha;
+    float c3[6];      // lambda1 * |mu_c|
+    float dq[5];      // lambda2 * {0, .5, 1, 1.5, 2}
+};
+
+__device__ __forceinline__ VitConsts make_consts(float alpha, float l1, float l2) {
+    VitConsts k;
+    k.oma = __fsub_rn(1.f, alpha); k.alpha = alpha;
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) k.c3[c] = __fmul_rn(l1, fabsf(c_mu[c]));
+    k.dq[0] = __fmul_rn(l2, 0.f); k.dq[1] = __fmul_rn(l2, 0.5f); k.dq[2] = __fmul_rn(l2, 1.0f);
+    k.dq[3] = __fmul_rn(l2, 1.5f); k.dq[4] = __fmul_rn(l2, 2.0f);
+    return k;
+}
+
+// point on the mu line of each state: mu = {-1,-.5,0,0,.5,1} -> {0,1,2,2,3,4}; |mu_c - mu_p| = 0.5 * |pt_c - pt_p|
+__device__ __forceinline__ int vpt(int c) { return c < 3 ? c : c - 1; }
+
+__device__ __forceinline__ int find_prob(const int* __restrict__ seg_base, int n_probs, int g) {
+    int lo = 0, hi = n_probs - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (__ldg(&seg_base[mid]) <= g) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+// emission terms of one marker for all six states: A = (1-alpha)*lrr, B = alpha*baf  (Hmm.java:157-159,196-197)
+__device__ __forceinline__ void emis(const VitConsts& k, float sd, const float* mse, float* A, float* B) {
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        float dev = __fsub_rn(sd, c_mu[c]);
+        A[c] = __fmul_rn(k.oma, __fmul_rn(dev, dev));
+        B[c] = __fmul_rn(k.alpha, mse[c]);
+    }
+}
+
+__device__ __forceinline__ void load_marker(const float* __restrict__ sdp, const float* __restrict__ msep, long long m, float& sd, float* mse) {
+    sd = __ldg(&sdp[m]);
+    if ((reinterpret_cast<unsigned long long>(msep) & 7ull) == 0) {          // uniform per chromosome
+        const float2* q = reinterpret_cast<const float2*>(msep + m * 6);
+        float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        mse[0] = a.x; mse[1] = a.y; mse[2] = b.x; mse[3] = b.y; mse[4] = c.x; mse[5] = c.y;
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) mse[i] = __ldg(&msep[m * 6 + i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- P0
+__global__ void __launch_bounds__(128) k_vit_p0(SegDev* probs, const int* __restrict__ seg_base, int n_probs, int total_segs,
+                                                int VSEG, float alpha, float* __restrict__ Tf) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_segs) return;
+    int pi = find_prob(seg_base, n_probs, g);
+    SegDev& P = probs[pi];
+    if (P.skip || !P.par) return;
+    const int s = g - seg_base[pi];
+    const long long M = P.M;
+    const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+    const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
+    float v[6][6];
+    #pragma unroll
+    for (int i = 0; i < 6; ++i)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) v[i][c] = (i == c) ? 0.f : V_INF_F;
+    bool bad = false;
+    float sd, mse[6];
+    if (s == 0) {                                     // marker 0 belongs to no segment: check it here
+        load_marker(P.scaled, P.mse, 0, sd, mse);
+        bad |= !(fabsf(sd) <= 2.0f);
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) bad |= __float_as_uint(mse[c]) >= 0x7f800000u;
+    }
+    for (long long m = a; m < b; ++m) {
+        load_marker(P.scaled, P.mse, m, sd, mse);
+        bad |= !(fabsf(sd) <= 2.0f);                  // NaN scaled depth (mean coverage 0/NaN) is not regular
+        float A[6], B[6], e[6];
+        emis(k, sd, mse, A, B);
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            bad |= __float_as_uint(mse[c]) >= 0x7f800000u;     // negative, NaN or Inf
+            e[c] = A[c] + B[c] + k.c3[c];
+        }
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            float w[5] = {v[i][0], v[i][1], fminf(v[i][2], v[i][3]), v[i][4], v[i][5]};
+            float nk[5];
+            #pragma unroll
+            for (int kk = 0; kk < 5; ++kk) {
+                float best = w[kk];
+                #pragma unroll
+                for (int j = 0; j < 5; ++j) if (j != kk) best = fminf(best, w[j] + k.dq[j > kk ? j - kk : kk - j]);
+                nk[kk] = best;
+            }
+            #pragma unroll
+            for (int c = 0; c < 6; ++c) v[i][c] = fminf(nk[vpt(c)] + e[c], V_INF_F);
+        }
+    }
+    if (bad) atomicOr(&P.irregular, 1);
+    float* out = Tf + (size_t)g * 36;
+    #pragma unroll
+    for (int i = 0; i < 6; ++i)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) out[i * 6 + c] = v[i][c];
+}
+
+// ---------------------------------------------------------------------------------------------- P0c
+// exact loss vector after marker 0 (Hmm.java:179-181) for lane c
+__device__ __forceinline__ float loss0(const SegDev& P, const VitConsts& k, int c) {
+    float lrr = 0.f, baf = 0.f;
+    if (P.M >= 2) { float dev = __fsub_rn(P.scaled[0], c_mu[c]); lrr = __fmul_rn(dev, dev); baf = P.mse[c]; }
+    return __fadd_rn(__fadd_rn(__fmul_rn(k.oma, lrr), __fmul_rn(k.alpha, baf)), k.c3[c]);
+}
+
+__device__ __forceinline__ int fexp(float x) { return (int)((__float_as_uint(x) >> 23) & 0xffu) - 127; }
+
+#define VB 32      // segments per staged batch in the chaining kernels
+
+// stage `cnt` matrices of `words` 32-bit words each (16-byte aligned) into shared memory with cp.async
+__device__ __forceinline__ void stage_mats(void* sdst, const void* gsrc, int cnt, int lane, int words = 36) {
+    const int4* src = reinterpret_cast<const int4*>(gsrc);
+    int4* dst = reinterpret_cast<int4*>(sdst);
+    for (int w = lane; w < cnt * (words / 4); w += 32) __pipeline_memcpy_async(dst + w, src + w, 16);
+    __pipeline_commit();
+}
+
+__global__ void __launch_bounds__(32) k_vit_p0c(SegDev* probs, const int* __restrict__ seg_base, float alpha,
+                                                const float* __restrict__ Tf, int* __restrict__ epred) {
+    __shared__ __align__(16) float sT[2][VB * 36];
+    __shared__ int sE[VB];
+    SegDev& P = probs[blockIdx.x];
+    if (P.skip || !P.par) return;
+    const int lane = threadIdx.x, j = lane < 6 ? lane : 0;
+    const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
+    const int nseg = P.n_seg, base = seg_base[blockIdx.x];
+    double L = (double)loss0(P, k, j);
+    if (nseg > 0) stage_mats(sT[0], Tf + (size_t)base * 36, min(VB, nseg), lane);
+    int buf = 0;
+    for (int s0 = 0; s0 < nseg; s0 += VB, buf ^= 1) {
+        const bool more = s0 + VB < nseg;
+        if (more) stage_mats(sT[buf ^ 1], Tf + (size_t)(base + s0 + VB) * 36, min(VB, nseg - s0 - VB), lane);
+        if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+        __syncwarp();
+        const int cnt = min(VB, nseg - s0);
+        for (int ss = 0; ss < cnt; ++ss) {
+            const float* t = &sT[buf][ss * 36 + j];
+            double lo = L, best = 1e300;
+            #pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double Li = __shfl_sync(0xffffffffu, L, i);
+                lo = fmin(lo, Li);
+                best = fmin(best, Li + (double)t[i * 6]);
+            }
+            double hi = best;
+            #pragma unroll
+            for (int o = 1; o < 8; o <<= 1) hi = fmax(hi, __shfl_xor_sync(0xffffffffu, lane < 6 ? hi : 0.0, o));
+            L = best;
+            if (lane == 0) {
+                int e_lo = fexp((float)lo), e_hi = fexp((float)hi);
+                sE[ss] = (e_lo == e_hi && e_lo >= V_EMIN && e_lo <= 30 && lo > 0.0) ? e_lo : -1;
+            }
+        }
+        __syncwarp();
+        if (lane < cnt) epred[base + s0 + lane] = sE[lane];
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- P1
+// Quantise a non-negative float addend to units of u = 2^(e-23).  Not a tie: round to nearest.  Tie (fractional
+// part exactly 1/2): fl(X*u + y) rounds to the EVEN neighbour, i.e. adds floor(y/u) + ((X + floor(y/u)) & 1): the
+// increment depends only on the parity of the running sum X, and the result is even.
+__device__ __forceinline__ int vquant(float y, float scale, bool& ovf, bool& tie) {
+    float x = __fmul_rn(y, scale);                  // exact: scale is a power of two
+    if (!(x < 67108864.f)) { ovf = true; tie = false; return 0; }   // 2^26: keeps every sum below 2^31
+    float tr = truncf(x);
+    tie = __fsub_rn(x, tr) == 0.5f;
+    return tie ? (int)tr : __float2int_rn(x);
+}
+// one add of the 4-add chain on (increment so far, parity of the running sum)
+__device__ __forceinline__ void vadd(int q, bool tie, int& inc, int& par) {
+    if (tie) { inc += q + ((par + q) & 1); par = 0; }
+    else { inc += q; par = (par + q) & 1; }
+}
+
+// Transfer "matrix" of a segment: 12 rows (start state i, parity of its start value) x 6 end states.  Row (i, pi)
+// holds min path costs relative to the start value; the absolute parity of an entry w is (pi + w) & 1, which is
+// all a later tie needs.  Without ties the two parity variants are identical.
+#define VT_WORDS 72
+__global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __restrict__ seg_base, int n_probs, int total_segs,
+                                                int VSEG, float alpha, const int* __restrict__ epred,
+                                                int* __restrict__ Ti, int* __restrict__ flags) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_segs) return;
+    int pi = find_prob(seg_base, n_probs, g);
+    SegDev& P = probs[pi];
+    if (P.skip || !P.par) return;
+    const int e = epred[g];
+    if (e < 0 || P.irregular) { flags[g] = 0; return; }
+    const int s = g - seg_base[pi];
+    const long long M = P.M;
+    const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+    const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
+    const float scale = __int_as_float((127 + 23 - e) << 23);
+    bool ovf = false, const_tie = false;
+    int qc3[6], qd[5]; bool tc3[6], td[5];
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) { qc3[c] = vquant(k.c3[c], scale, ovf, tc3[c]); const_tie |= tc3[c]; }
+    #pragma unroll
+    for (int d = 0; d < 5; ++d) { qd[d] = vquant(k.dq[d], scale, ovf, td[d]); const_tie |= td[d]; }
+    int v0[6][6], v1[6][6];
+    #pragma unroll
+    for (int i = 0; i < 6; ++i)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) { v0[i][c] = (i == c) ? 0 : V_INF_I; v1[i][c] = v0[i][c]; }
+    bool split = false;                             // v1 differs from v0 only after the first tie
+    for (long long m = a; m < b; ++m) {
+        float sd, mse[6], A[6], B[6];
+        load_marker(P.scaled, P.mse, m, sd, mse);
+        emis(k, sd, mse, A, B);
+        int qa[6], qb[6]; bool ta[6], tb[6], mt = const_tie;
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) { qa[c] = vquant(A[c], scale, ovf, ta[c]); qb[c] = vquant(B[c], scale, ovf, tb[c]); mt |= ta[c] | tb[c]; }
+        if (!mt) {
+            int E[6];
+            #pragma unroll
+            for (int c = 0; c < 6; ++c) E[c] = qa[c] + qb[c] + qc3[c];
+            auto plain = [&](int (&v)[6][6]) {
+                #pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    int w[5] = {v[i][0], v[i][1], min(v[i][2], v[i][3]), v[i][4], v[i][5]};
+                    int nk[5];
+                    #pragma unroll
+                    for (int kk = 0; kk < 5; ++kk) {
+                        int best = w[kk] + qd[0];
+                        #pragma unroll
+                        for (int j = 0; j < 5; ++j) if (j != kk) best = min(best, w[j] + qd[j > kk ? j - kk : kk - j]);
+                        nk[kk] = best;
+                    }
+                    #pragma unroll
+                    for (int c = 0; c < 6; ++c) v[i][c] = min(nk[vpt(c)] + E[c], V_INF_I);
+                }
+            };
+            plain(v0);
+            if (split) plain(v1);
+        } else {
+            if (!split) {
+                split = true;
+                #pragma unroll
+                for (int i = 0; i < 6; ++i)
+                    #pragma unroll
+                    for (int c = 0; c < 6; ++c) v1[i][c] = v0[i][c];
+            }
+            // increment of the whole 4-add chain into state c over distance d, for a source of even / odd absolute value
+            int inc0[30], inc1[30];
+            #pragma unroll
+            for (int c = 0; c < 6; ++c)
+                #pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    int i0 = 0, p0 = 0, i1 = 0, p1 = 1;
+                    vadd(qa[c], ta[c], i0, p0); vadd(qb[c], tb[c], i0, p0); vadd(qc3[c], tc3[c], i0, p0); vadd(qd[d], td[d], i0, p0);
+                    vadd(qa[c], ta[c], i1, p1); vadd(qb[c], tb[c], i1, p1); vadd(qc3[c], tc3[c], i1, p1); vadd(qd[d], td[d], i1, p1);
+                    inc0[c * 5 + d] = i0; inc1[c * 5 + d] = i1;
+                }
+            auto tied = [&](int (&v)[6][6], int ps) {
+                #pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    int w[5] = {v[i][0], v[i][1], min(v[i][2], v[i][3]), v[i][4], v[i][5]};
+                    int nv[6];
+                    #pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        int best = V_INF_I;
+                        #pragma unroll
+                        for (int j = 0; j < 5; ++j) {
+                            const int d = j > vpt(c) ? j - vpt(c) : vpt(c) - j;
+                            best = min(best, w[j] + (((ps + w[j]) & 1) ? inc1[c * 5 + d] : inc0[c * 5 + d]));
+                        }
+                        nv[c] = best;
+                    }
+                    #pragma unroll
+                    for (int c = 0; c < 6; ++c) v[i][c] = min(nv[c], V_INF_I);
+                }
+            };
+            tied(v0, 0);
+            tied(v1, 1);
+        }
+    }
+    int* out = Ti + (size_t)g * VT_WORDS;
+    bool bad = ovf;
+    #pragma unroll
+    for (int i = 0; i < 6; ++i)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int w1 = split ? v1[i][c] : v0[i][c];
+            out[i * 6 + c] = v0[i][c]; out[36 + i * 6 + c] = w1;
+            bad |= v0[i][c] >= (V_INF_I >> 1) || w1 >= (V_INF_I >> 1);
+        }
+    flags[g] = bad ? 0 : 1;
+    atomicAdd(&g_vdbg[0], 1); if (ovf) atomicAdd(&g_vdbg[1], 1); if (bad && !ovf) atomicAdd(&g_vdbg[2], 1); if (split) atomicAdd(&g_vdbg[3], 1);
+}
+
+// ---------------------------------------------------------------------------------------------- exact float step
+// lanes 0..5 hold L[c]; regular inputs (finite, non-negative): the min over ascending p with strict '<' from
+// Float.MAX_VALUE equals the plain minimum when it is below Float.MAX_VALUE, else "no candidate" -> 0 (Java default)
+__device__ __forceinline__ float lanes_step(float L, float A, float B, float c3, const float* c4) {
+    float best = 3.402823466e+38f;
+    #pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        float Lp = __shfl_sync(0xffffffffu, L, p);
+        best = fminf(best, __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(Lp, A), B), c3), c4[p]));
+    }
+    return best < 3.402823466e+38f ? best : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------- P2
+__global__ void __launch_bounds__(32) k_vit_p2(SegDev* probs, const int* __restrict__ seg_base, int VSEG, float alpha,
+                                               const int* __restrict__ epred, const int* __restrict__ Ti,
+                                               const int* __restrict__ flags, const int* __restrict__ force,
+                                               float* __restrict__ Lstart, int* __restrict__ replayed) {
+    SegDev& P = probs[blockIdx.x];
+    if (P.skip || !P.par || P.irregular) return;
+    const int lane = threadIdx.x, c = lane < 6 ? lane : 0;
+    const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
+    const float c3 = k.c3[c];
+    float c4[6];
+    #pragma unroll
+    for (int p = 0; p < 6; ++p) { int d = vpt(c) - vpt(p); c4[p] = k.dq[d < 0 ? -d : d]; }
+    const int nseg = P.n_seg, base = seg_base[blockIdx.x];
+    const long long M = P.M;
+    float* ls = Lstart + ((size_t)base + blockIdx.x) * 6;     // n_seg + 1 vectors per chromosome
+    float L = loss0(P, k, c);
+    if (lane < 6) ls[lane] = L;
+    int bad1e10 = 0, n_replayed = 0;
+    __shared__ __align__(16) int sT[2][VB * 72];
+    if (nseg > 0) stage_mats(sT[0], Ti + (size_t)base * 72, min(VB, nseg), lane, 72);
+    int buf = 0;
+    // per-batch control words: lane l holds (usable, binade) of segment s0 + l
+    int f_nx = 0, e_nx = -1;
+    if (lane < nseg) { f_nx = __ldg(&flags[base + lane]) && !__ldg(&force[base + lane]); e_nx = __ldg(&epred[base + lane]); }
+    for (int s0 = 0; s0 < nseg; s0 += VB, buf ^= 1) {
+      const bool more = s0 + VB < nseg;
+      const int f_cur = f_nx, e_cur = e_nx;
+      if (more) {
+          stage_mats(sT[buf ^ 1], Ti + (size_t)(base + s0 + VB) * 72, min(VB, nseg - s0 - VB), lane, 72);
+          int sn = s0 + VB + lane;
+          f_nx = 0; e_nx = -1;
+          if (sn < nseg) { f_nx = __ldg(&flags[base + sn]) && !__ldg(&force[base + sn]); e_nx = __ldg(&epred[base + sn]); }
+          __pipeline_wait_prior(1);
+      } else __pipeline_wait_prior(0);
+      __syncwarp();
+      const int cnt = min(VB, nseg - s0);
+      for (int ss = 0; ss < cnt; ++ss) {
+        const int s = s0 + ss;
+        int ok = __shfl_sync(0xffffffffu, f_cur, ss), e = __shfl_sync(0xffffffffu, e_cur, ss);
+        if (lane == 0 && !ok) atomicAdd(&g_vdbg[e < 0 ? 4 : 5], 1);
+        { int ok0 = ok; ok = ok && __all_sync(0xffffffffu, lane >= 6 || (L > 0.f && fexp(L) == e)); if (lane == 0 && ok0 && !ok) atomicAdd(&g_vdbg[6], 1); }
+        float Lnew = L;
+        if (ok) {
+            const float scale = __int_as_float((127 + 23 - e) << 23), inv = __int_as_float((127 - 23 + e) << 23);
+            int Li = __float2int_rn(__fmul_rn(L, scale));            // exact: L is a multiple of u
+            int best = 0x7fffffff;
+            #pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                int Lsrc = __shfl_sync(0xffffffffu, Li, i);                  // row (i, parity of the start value)
+                best = min(best, Lsrc + sT[buf][ss * 72 + ((Lsrc & 1) * 6 + i) * 6 + c]);
+            }
+            ok = __all_sync(0xffffffffu, lane >= 6 || best < (1 << 24));
+            if (lane == 0 && !ok) atomicAdd(&g_vdbg[7], 1);
+            Lnew = __fmul_rn((float)best, inv);
+        }
+        if (!ok) {                                                    // exact replay of this segment
+            ++n_replayed;
+            const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+            Lnew = L;
+            for (long long m0 = a; m0 < b; m0 += 32) {
+                long long m = m0 + lane;
+                float sdv = (m < b) ? __ldg(&P.scaled[m]) : 0.f;
+                float mv[6];
+                #pragma unroll
+                for (int i = 0; i < 6; ++i) { long long idx = m0 * 6 + i * 32 + lane; mv[i] = (idx < b * 6) ? __ldg(&P.mse[idx]) : 0.f; }
+                int cnt = (int)min((long long)32, b - m0);
+                for (int jj = 0; jj < cnt; ++jj) {
+                    float sdj = __shfl_sync(0xffffffffu, sdv, jj);
+                    int el = jj * 6 + c;                              // element of the 192-float chunk
+                    float msel = 0.f;
+                    #pragma unroll
+                    for (int i = 0; i < 6; ++i) { float x = __shfl_sync(0xffffffffu, mv[i], el & 31); if ((el >> 5) == i) msel = x; }
+                    float dev = __fsub_rn(sdj, c_mu[c]);
+                    float A = __fmul_rn(k.oma, __fmul_rn(dev, dev)), B = __fmul_rn(k.alpha, msel);
+                    Lnew = lanes_step(Lnew, A, B, c3, c4);
+                    if ((double)Lnew == 1e10) bad1e10 = 1;
+                }
+            }
+        }
+        L = Lnew;
+        if (lane < 6) ls[(size_t)(s + 1) * 6 + lane] = L;
+      }
+      __syncwarp();
+    }
+    int min_index = 1; float mn = 3.402823466e+38f, row[6];
+    #pragma unroll
+    for (int s6 = 0; s6 < 6; ++s6) { row[s6] = __shfl_sync(0xffffffffu, L, s6); if (row[s6] < mn) { mn = row[s6]; min_index = s6; } }
+    bad1e10 = __any_sync(0xffffffffu, bad1e10 && lane < 6);
+    if (lane == 0) {
+        for (int s6 = 0; s6 < 6; ++s6) P.last_row[s6] = row[s6];
+        P.sstar = min_index; P.final_loss = mn;
+        P.status = HCNV_OK;
+        if (bad1e10 || mn == 3.402823466e+38f) { P.status = HCNV_E_NO_MINIMUM; P.skip = 2; }
+        P.first_bad = 0x7fffffff;
+        replayed[blockIdx.x] = n_replayed;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- P3
+__global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __restrict__ seg_base, int n_probs, int total_segs,
+                                                int VSEG, float alpha, const float* __restrict__ Lstart, int* __restrict__ force) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_segs) return;
+    int pi = find_prob(seg_base, n_probs, g);
+    SegDev& P = probs[pi];
+    if (P.skip || !P.par || P.irregular) return;
+    const int s = g - seg_base[pi];
+    const long long M = P.M;
+    const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+    const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
+    const float* ls = Lstart + ((size_t)seg_base[pi] + pi) * 6 + (size_t)s * 6;
+    const int sstar = P.sstar;
+    float L[6];
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) L[c] = __ldg(&ls[c]);
+    float c4s[6];                                     // transition penalties into s*
+    #pragma unroll
+    for (int p = 0; p < 6; ++p) { int d = vpt(sstar) - vpt(p); c4s[p] = k.dq[d < 0 ? -d : d]; }
+    const float c3s = k.c3[sstar];
+    int bad = 0;
+    float sd, mse[6];
+    load_marker(P.scaled, P.mse, a, sd, mse);
+    for (long long m = a; m < b; ++m) {
+        float sdn = 0.f, msen[6] = {0, 0, 0, 0, 0, 0};
+        if (m + 1 < b) load_marker(P.scaled, P.mse, m + 1, sdn, msen);
+        float A[6], B[6], Ln[6];
+        emis(k, sd, mse, A, B);
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            float best = 3.402823466e+38f;
+            #pragma unroll
+            for (int p = 0; p < 6; ++p) {
+                int d = vpt(c) - vpt(p);
+                best = fminf(best, __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(L[p], A[c]), B[c]), k.c3[c]), k.dq[d < 0 ? -d : d]));
+            }
+            Ln[c] = best < 3.402823466e+38f ? best : 0.f;
+            if ((double)Ln[c] == 1e10) bad = 1;
+        }
+        // traceback[m][s*]: first p (ascending) whose candidate equals the minimum (strict '<' keeps the first)
+        float As = A[0], Bs = B[0], Ls = Ln[0];
+        #pragma unroll
+        for (int c = 1; c < 6; ++c) if (c == sstar) { As = A[c]; Bs = B[c]; Ls = Ln[c]; }
+        int arg = 0;
+        #pragma unroll
+        for (int p = 5; p >= 0; --p) {
+            float cand = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(L[p], As), Bs), c3s), c4s[p]);
+            if (cand == Ls && cand < 3.402823466e+38f) arg = p;
+        }
+        if (P.state) P.state[m - 1] = arg;                           // best_state[m-1] = traceback[m][s*] (Hmm.java:236)
+        if (P.cn) P.cn[m - 1] = c_cn[arg];
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) { L[c] = Ln[c]; mse[c] = msen[c]; }
+        sd = sdn;
+    }
+    // verify against the start vector of the next segment (bit for bit)
+    const float* nx = ls + 6;
+    bool same = true;
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) same &= __float_as_uint(L[c]) == __float_as_uint(__ldg(&nx[c]));
+    if (!same) { atomicMin(&P.first_bad, s); force[g] = 1; }
+    if (bad) P.status = HCNV_E_NO_MINIMUM;                          // Hmm.java:205-215 would exit
+    if (b == M) {                                                    // last marker (Hmm.java:234, sic)
+        int st = c_cn[sstar];
+        if (P.state) P.state[M - 1] = st;
+        if (P.cn) P.cn[M - 1] = c_cn[st];
+    }
+}

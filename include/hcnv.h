@@ -73,8 +73,16 @@ int         hcnv_ctx_synchronize(hcnv_ctx* ctx);
 #define HCNV_K_SD              6
 #define HCNV_K_VITERBI         7
 #define HCNV_K_TRACEBACK       8
+#define HCNV_K_VIT_P0          9    /* segment-parallel Viterbi: approximate transfer matrices   */
+#define HCNV_K_VIT_P0C        10    /*   binade prediction                                       */
+#define HCNV_K_VIT_P1         11    /*   exact integer transfer matrices                         */
+#define HCNV_K_VIT_P2         12    /*   exact chaining (+ replay of flagged segments)           */
+#define HCNV_K_VIT_P3         13    /*   exact float replay per segment: calls + verification    */
 #define HCNV_K_COUNT          16
 float       hcnv_ctx_kernel_ms(hcnv_ctx* ctx, int which);
+/* counters of the last hcnv_segment_batch call: 0 = segments of the segment-parallel Viterbi, 1 = segments that were
+ * replayed with the sequential exact step (binade crossings, rounding ties), 2 = verification failures repaired (cumulative) */
+int64_t     hcnv_ctx_stat(const hcnv_ctx* ctx, int which);
 
 /* ---- B1: binning ------------------------------------------------------------------------------ */
 

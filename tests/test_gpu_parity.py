@@ -166,6 +166,94 @@ def test_hmm_batch_of_chromosomes_long(ctx):
         assert f32(got["mean_coverage"]).view(np.uint32) == f32(want["mean_coverage"]).view(np.uint32)
 
 
+def _check_calls(got, want):
+    assert got["status"] == want["rc"]
+    np.testing.assert_array_equal(got["state"], want["state"])
+    np.testing.assert_array_equal(got["cn"], want["cn"])
+    assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+    np.testing.assert_array_equal(got["last_row"].view(np.uint32), want["last_row"].view(np.uint32))
+
+
+@pytest.mark.parametrize("seed,M,l1,l2,depth", [(31, 300000, 0.01, 1.6, 30), (32, 250000, 0.3, 0.4, 30), (33, 120001, 0.05, 3.2, 8),
+                                                (34, 90000, 0.5, 1.0, 100), (35, 4096, 0.01, 1.6, 30), (36, 70000, -1.0, -1.0, 30)])
+def test_segment_parallel_viterbi_is_exact(ctx, seed, M, l1, l2, depth):
+    """Long chromosomes take the segment-parallel path (integer transfer matrices inside a float binade + verified
+    float replay); it must reproduce the sequential float chain bit for bit, through binade crossings and rounding
+    ties, and agree with the forced one-warp sequential kernel."""
+    rng = np.random.default_rng(seed)
+    b = Hp.random_bins(rng, M, mean_depth=depth)
+    mse32 = O.f64_text_f32(b["mse"]); tot32 = b["total"].astype(np.float32)
+    prob = dict(median=b["median"], mse=mse32, total=tot32, n=b["n"], lambda1=l1, lambda2=l2)
+    want = O.hmm(b["median"], mse32, tot32, b["n"], l1, l2, fast=True)
+    want_full = O.hmm(b["median"], mse32, tot32, b["n"], l1, l2) if M <= 130000 else None
+    got = ctx.segment_batch([dict(prob)])[0]
+    st = ctx.stats()
+    assert st["viterbi_segments"] == (M - 1 + 127) // 128 and st["viterbi_repairs"] == 0
+    assert st["viterbi_segments_replayed"] < st["viterbi_segments"]           # the matrices really carry most segments
+    seq = ctx.segment_batch([dict(prob)], flags=L.HCNV_SEG_SEQUENTIAL)[0]
+    assert ctx.stats()["viterbi_segments"] == 0
+    for r in (got, seq):
+        np.testing.assert_array_equal(r["state"], want["state"])
+        np.testing.assert_array_equal(r["cn"], want["cn"])
+        assert f32(r["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+    if want_full is not None:
+        _check_calls(got, want_full)
+
+
+def test_segment_parallel_viterbi_forced_ties(ctx):
+    """Emissions chosen on a coarse dyadic grid so that many addends are exact half-ulp ties in the running binade:
+    those segments must be flagged and replayed, the result stays exact."""
+    rng = np.random.default_rng(41)
+    M = 60000
+    b = Hp.random_bins(rng, M)
+    mse32 = (rng.integers(0, 64, (M, 6)) / 4096.0).astype(np.float32) * (rng.random((M, 1)) < 0.3)
+    med = (rng.integers(20, 40, M)).astype(np.float32)
+    tot32 = np.full(M, 3000, np.float32); n = np.full(M, 100, np.int32)
+    want = O.hmm(med, mse32.astype(np.float32), tot32, n, 0.25, 0.5, fast=True)
+    got = ctx.segment_batch([dict(median=med, mse=mse32.astype(np.float32), total=tot32, n=n, lambda1=0.25, lambda2=0.5)])[0]
+    np.testing.assert_array_equal(got["state"], want["state"])
+    assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+    assert ctx.stats()["viterbi_repairs"] == 0
+
+
+def test_segment_parallel_mixed_batch(ctx):
+    """Long regular, long irregular (NaN -> literal sequential kernel), skipped and short chromosomes in one call."""
+    rng = np.random.default_rng(51)
+    probs, wants = [], []
+    for M, l1, l2, nan in [(50000, 0.01, 1.6, False), (30000, 0.01, 1.6, True), (20000, 0.01, 0.004, False), (500, 0.3, 0.4, False),
+                           (9000, 0.1, 0.8, False)]:
+        b = Hp.random_bins(rng, M)
+        mse32 = b["mse"].astype(np.float32); tot32 = b["total"].astype(np.float32)
+        if nan:
+            mse32[12345, 3] = np.nan
+        probs.append(dict(median=b["median"], mse=mse32, total=tot32, n=b["n"], lambda1=l1, lambda2=l2))
+        wants.append(O.hmm(b["median"], mse32, tot32, b["n"], l1, l2, fast=True))
+    gots = ctx.segment_batch(probs, raise_on_exit=False)
+    for got, want in zip(gots, wants):
+        assert got["status"] == (L.HCNV_E_NO_MINIMUM if want["rc"] < 0 else want["rc"])
+        if want["rc"] >= 0:
+            np.testing.assert_array_equal(got["state"], want["state"])
+            assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+
+
+@pytest.mark.parametrize("seed,M,hi,frac", [(61, 1000000, 6000, False), (62, 300000, 1 << 26, False), (63, 50000, 40, False),
+                                            (64, 200000, 6000, True), (65, 7, 1 << 27, False), (66, 700001, 3, False)])
+def test_mean_coverage_is_the_sequential_float_sum(ctx, seed, M, hi, frac):
+    """Hmm.java:369-373: mean_coverage is a sequential float32 running sum; above 2^24 every add rounds (ties to even),
+    so it must be reproduced in order.  The CUDA path does it with an exact parity-tracking scan per binade."""
+    rng = np.random.default_rng(seed)
+    tot = rng.integers(0, hi, M).astype(np.float32)
+    if frac:
+        tot = tot + np.float32(0.5)                      # not integers: the sequential fallback kernel
+    n = rng.integers(1, 101, M).astype(np.int32)
+    want_sum = np.add.accumulate(tot, dtype=np.float32)[-1]
+    want = f32(want_sum / f32(int(n.sum())))
+    med = np.full(M, 20, np.float32); mse = np.zeros((M, 6), np.float32)
+    got = ctx.segment_batch([dict(median=med, mse=mse, total=tot, n=n, lambda1=0.01, lambda2=0.004)])[0]   # viterbi skipped
+    assert got["status"] == L.HCNV_VITERBI_SKIPPED
+    assert f32(got["mean_coverage"]).view(np.uint32) == want.view(np.uint32)
+
+
 def test_hmm_nan_and_degenerate_inputs(ctx):
     M = 50
     med = np.full(M, 20, np.float32); mse = np.zeros((M, 6), np.float32); tot = np.full(M, 2000, np.float32); n = np.full(M, 100, np.int32)
