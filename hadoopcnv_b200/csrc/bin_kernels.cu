@@ -200,236 +200,7 @@ __device__ __noinline__ void distinct_wide(const int32_t* dp, int W, int& n_dist
     n_distinct_pos = count;
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256) k_bin_tiles(BinK p) {
-    extern __shared__ __align__(16) int32_t smem[];
-    __shared__ int s_tile;
-    __shared__ int s_warp[32];
-    __shared__ long long s_prefix;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_tile = (int)atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const int t = s_tile;
-    if (t >= p.n_tiles) return;
-    const ContigDev c = p.contigs[p.tile_contig[t]];
-    const int k = t - c.tile_base;
-    const int W = p.W, TB = p.TB;
-    const int TP = TB * W;
-    const long long T0 = (long long)k * TP, T1 = T0 + TP;
-    int32_t* diff = smem;                       // TP + 4 entries; entry TP is the sink for ends at the tile edge
-
-    // ---- phase 1: clear
-    for (int i = tid * 4; i < TP + 4; i += nthr * 4) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
-    __syncthreads();
-
-    // ---- phase 2: blocks of any length (few)
-    for (long long i = tid; i < c.n_long; i += nthr) {
-        hcnv_long_block r = c.longs[i];
-        long long s1 = (long long)r.start0 + 1, e1 = s1 + r.len;
-        if (r.len < 0 || r.start0 < 0 || e1 - 1 > c.length) { atomicOr(&p.err[ERR_RANGE], 1); continue; }
-        uint32_t mq = (uint32_t)r.mapq & 255u;
-        if (!((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u)) continue;
-        long long s = max(s1, T0), e = min(e1, T1);
-        if (e > s) { atomicAdd(&diff[(int)(s - T0)], 1); atomicAdd(&diff[(int)(e - T0)], -1); }
-    }
-
-    // ---- phase 3: the sorted short-block stream: own range [lo, hi) plus the look-back [lb, lo)
-    {
-        const uint32_t lb = p.rec_lb[t], lo = p.rec_lo[t], hi = p.rec_hi[t];
-        if (hi < lo || lo < lb) atomicOr(&p.err[ERR_UNSORTED], 1);
-        const hcnv_block* __restrict__ blocks = c.blocks;
-        for (uint32_t i0 = lb; i0 < hi; i0 += nthr) {
-            uint32_t i = i0 + tid;
-            bool live = i < hi;
-            int2 raw = live ? __ldg(reinterpret_cast<const int2*>(blocks) + i) : make_int2(0, 0);
-            int start0 = raw.x;
-            uint32_t lm = (uint32_t)raw.y;
-            // sortedness of every adjacent pair this tile touches
-            int prev = __shfl_up_sync(0xffffffffu, start0, 1);
-            if (lane == 0) prev = (live && i > 0) ? __ldg(&blocks[i - 1].start0) : start0;
-            if (live) {
-                if (i > 0 && prev > start0) atomicOr(&p.err[ERR_UNSORTED], 1);
-                int len = (int)(lm & 0xFFFFFFu);
-                uint32_t mq = lm >> 24;
-                long long s1 = (long long)start0 + 1, e1 = s1 + len;
-                if (len > p.maxlen || start0 < 0 || e1 - 1 > c.length) atomicOr(&p.err[ERR_RANGE], 1);
-                else if ((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u) {
-                    long long s = max(s1, T0), e = min(e1, T1);
-                    if (e > s) { atomicAdd(&diff[(int)(s - T0)], 1); atomicAdd(&diff[(int)(e - T0)], -1); }
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 4a: per-bin sum of the difference array -> exclusive scan -> depth carried into each bin
-    const int b = tid;                                  // one thread per bin (blockDim.x == TB)
-    const int nb_tile = min(TB, c.n_bins_max - k * TB); // bins of this tile that exist
-    int32_t* dp = diff + b * W;
-    int bsum = 0;
-    if (b < nb_tile) {
-        if (VEC == 4) { const int4* q = reinterpret_cast<const int4*>(dp); for (int i = 0; i < W / 4; ++i) { int4 v = q[i]; bsum += (v.x + v.y) + (v.z + v.w); } }
-        else if (VEC == 2) { const int2* q = reinterpret_cast<const int2*>(dp); for (int i = 0; i < W / 2; ++i) { int2 v = q[i]; bsum += v.x + v.y; } }
-        else { for (int i = 0; i < W; ++i) bsum += dp[i]; }
-    }
-    int incl = bsum;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        int v = (lane < (nthr >> 5)) ? s_warp[lane] : 0;
-        int w = v;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
-        s_warp[lane] = w - v;                           // exclusive
-    }
-    __syncthreads();
-    const int carry = incl - bsum + s_warp[wid];
-
-    // ---- phase 4b..6: walk, SNP sites, BinReducer record
-    int   o_n = 0, o_start = 0, o_end = 0;
-    float o_median = 0.f;
-    double mse[6] = {0, 0, 0, 0, 0, 0};
-    double o_total = 0;
-    if (b < nb_tile) {
-        WalkOut w;
-        walk_bin<VEC>(dp, W, carry, w);
-        const long long bin_lo = T0 + (long long)b * W;             // 1-based position of dp[0]
-        int n = w.n, first = w.first, last = w.last;
-        bool has_zero = false;                                       // a VCF-only position puts depth 0 into depthSet
-        int nbaf = 0;
-        // SNP sites of this bin, ascending (VcfLookup side input; Reducers.java:76-82,120-129)
-        const uint32_t slo = p.snp_lo[t], shi = p.snp_hi[t];
-        if (shi > slo) {
-            uint32_t s = slo + lower_bound_i32(c.snp_pos + slo, (long long)(shi - slo), (int32_t)bin_lo);
-            for (; s < shi; ++s) {
-                int pos = __ldg(&c.snp_pos[s]);
-                if (pos >= bin_lo + W) break;
-                if (s > 0 && __ldg(&c.snp_pos[s - 1]) >= pos) atomicOr(&p.err[ERR_UNSORTED], 1);
-                if (pos < 0 || pos > c.length) { atomicOr(&p.err[ERR_RANGE], 1); continue; }
-                int off = (int)(pos - bin_lo);
-                int d = dp[off];
-                const uint4* tr = reinterpret_cast<const uint4*>(p.tally + ((size_t)(c.snp_base + s)) * 16);
-                uint32_t tot = 0, mx = 0;
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 v = __ldg(tr + j);
-                    tot += v.x + v.y + v.z + v.w;
-                    mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w));
-                }
-                if (tot != (uint32_t)d) atomicOr(&p.err[ERR_INCONSISTENT], 1);
-                int zyg = c.snp_zyg[s];
-                if (d == 0) {                                        // position exists only because of the VCF record
-                    ++n; first = min(first, off); last = max(last, off); has_zero = true;
-                } else if (zyg <= 0) {
-                    float ptd = (float)d, mxd = (float)mx;
-                    float baf = __fdiv_rn(__fsub_rn(ptd, mxd), ptd);             // Reducers.java:126
-                    float baf2 = __fmul_rn(baf, baf);                             // :163
-                    double bb = (double)baf, b2 = (double)baf2;
-                    double a = (0.5 - bb) * (0.5 - bb), q = (0.25 - bb) * (0.25 - bb);
-                    mse[0] += fmin(b2, fmin(a, q));                               // :164
-                    mse[1] += b2;
-                    if (zyg == -1) {
-                        mse[2] += b2; mse[3] += a;
-                        mse[4] += (0.33 - bb) * (0.33 - bb);
-                        mse[5] += fmin(q, a);
-                    } else { mse[2] += b2; mse[3] += b2; mse[4] += b2; mse[5] += b2; }
-                    ++nbaf;
-                }
-            }
-        }
-        if (nbaf > 1) { double dn = (double)nbaf; for (int j = 0; j < 6; ++j) mse[j] = mse[j] / dn; }   // :186-190 (dummy BAF 0 -> 0/1)
-        // distinct-depth "median": element size/2 - 1 of the ascending distinct set, 0 if size < 2 (Reducers.java:142-147)
-        if (n > 0) {
-            int size, want, val = 0;
-            if (w.oob < 64u) {
-                size = __popc(w.m0) + __popc(w.m1) + (has_zero ? 1 : 0);
-                want = size / 2 - 1;
-                if (size >= 2) {
-                    int kk = want - (has_zero ? 1 : 0);
-                    val = (kk < 0) ? 0 : w.base + kth_set_bit(w.m0, w.m1, kk);
-                }
-            } else {
-                int npos = 0, dummy = 0;
-                distinct_wide(dp, W, npos, -1, dummy);
-                size = npos + (has_zero ? 1 : 0);
-                want = size / 2 - 1;
-                if (size >= 2) {
-                    int kk = want - (has_zero ? 1 : 0);
-                    if (kk >= 0) distinct_wide(dp, W, npos, kk, val);
-                }
-            }
-            o_median = (float)val;
-            o_n = n; o_start = (int)(bin_lo + first); o_end = (int)(bin_lo + last);
-            o_total = (double)w.sum;
-        }
-    }
-
-    // ---- compaction: rank of this bin among the tile's non-empty bins, then the tile's global offset
-    const unsigned ball = __ballot_sync(0xffffffffu, o_n > 0);
-    const int wcount = __popc(ball);
-    const int wrank = __popc(ball & ((1u << lane) - 1u));
-    __syncthreads();                                   // s_warp reuse
-    if (lane == 0) s_warp[wid] = wcount;
-    __syncthreads();
-    int tile_count = 0, warp_off = 0;
-    for (int i = 0; i < (nthr >> 5); ++i) { int v = s_warp[i]; if (i < wid) warp_off += v; tile_count += v; }
-
-    // decoupled look-back: status word = flag << 62 | value; flag 1 = tile aggregate, 2 = inclusive prefix
-    if (wid == 0) {
-        const unsigned long long FLAG_AGG = 1ull << 62, FLAG_PRE = 2ull << 62, VAL = (1ull << 62) - 1;
-        volatile unsigned long long* st = p.status;
-        long long excl = 0;
-        if (t == 0) {
-            if (lane == 0) { st[0] = FLAG_PRE | (unsigned long long)tile_count; }
-        } else {
-            if (lane == 0) { st[t] = FLAG_AGG | (unsigned long long)tile_count; }
-            __threadfence();
-            int j = t - 1;                              // look back 32 tiles at a time
-            bool done = false;
-            long long spins = 0;
-            while (!done) {
-                int idx = j - lane;
-                unsigned long long v = (idx >= 0) ? st[idx] : FLAG_PRE;
-                unsigned flagged = __ballot_sync(0xffffffffu, (v >> 62) != 0);
-                unsigned pre = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                // usable lanes: consecutive from lane 0 while flagged, up to and including the first prefix
-                unsigned not_flagged = ~flagged;
-                int first_gap = not_flagged ? (__ffs(not_flagged) - 1) : 32;
-                int first_pre = pre ? (__ffs(pre) - 1) : 32;
-                int take = (first_pre < first_gap) ? first_pre + 1 : first_gap;   // lanes [0, take)
-                long long contrib = (lane < take) ? (long long)(v & VAL) : 0;
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                excl += contrib;
-                j -= take;
-                if (first_pre < first_gap) done = true;
-                else if (take == 0) {
-                    if (++spins > (1ll << 24)) { if (lane == 0) atomicOr(&p.err[ERR_INTERNAL], 1); done = true; }
-                    __nanosleep(64);
-                }
-            }
-            if (lane == 0) { __threadfence(); st[t] = FLAG_PRE | (unsigned long long)(excl + tile_count); }
-        }
-        if (lane == 0) {
-            s_prefix = excl;
-            if (k == 0) p.contig_offset[p.tile_contig[t]] = excl;
-            if (t == p.n_tiles - 1) p.contig_offset[p.n_contigs] = excl + tile_count;
-        }
-    }
-    __syncthreads();
-    if (o_n > 0) {
-        long long r = s_prefix + warp_off + wrank;
-        if (r >= p.capacity) { atomicOr(&p.err[ERR_CAPACITY], 1); return; }
-        p.o_bin[r] = (int)(T0 + (long long)b * W);
-        p.o_start[r] = o_start; p.o_end[r] = o_end; p.o_median[r] = o_median;
-        double2* m = reinterpret_cast<double2*>(p.o_mse + r * 6);
-        m[0] = make_double2(mse[0], mse[1]); m[1] = make_double2(mse[2], mse[3]); m[2] = make_double2(mse[4], mse[5]);
-        p.o_total[r] = o_total; p.o_n[r] = o_n;
-    }
-}
+#include "bin_tile_kernel.cuh"
 
 }  // namespace
 
@@ -466,13 +237,14 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     if (!out->bin || !out->start || !out->end || !out->median || !out->mse || !out->total || !out->n || !out->contig_offset)
         return hcnv_fail(ctx, HCNV_E_INVALID, "null output array");
 
-    // tile geometry: TB bins per CTA, TB*W*4 bytes of shared memory
+    // tile geometry: TB bins (= threads) per CTA; shared memory = difference array + one staged chunk of records
     int TB = P.tile_bins > 0 ? P.tile_bins : 128;
     TB = (TB + 31) / 32 * 32;
-    if (TB > 256) TB = 256;
-    while (TB > 32 && (size_t)TB * W * 4 + 64 > ctx->smem_optin) TB -= 32;
-    if ((size_t)TB * W * 4 + 64 > ctx->smem_optin) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory");
-    const size_t smem_bytes = ((size_t)TB * W + 4) * 4;
+    if (TB > 128) TB = 128;
+    auto smem_need = [&](int tb) { return (((size_t)tb * W + 4) * 4 + 15) / 16 * 16 + (size_t)(RCAP + 4) * 8; };
+    while (TB > 32 && smem_need(TB) > ctx->smem_optin) TB -= 32;
+    if (smem_need(TB) > ctx->smem_optin) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1600)");
+    const size_t smem_bytes = smem_need(TB);
 
     // pointer kinds
     int in_kind = -1;
@@ -480,7 +252,9 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     for (int c = 0; c < n_contigs; ++c) {
         const hcnv_contig_input& ci = contigs[c];
         if (ci.length < 0 || ci.n_blocks < 0 || ci.n_long < 0 || ci.n_snp < 0 || ci.n_obs < 0) return hcnv_fail(ctx, HCNV_E_INVALID, "negative count");
-        if (ci.n_blocks >= (1ll << 32) - 1 || ci.n_snp >= (1ll << 28)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many records in one contig");
+        if (ci.n_blocks >= (1ll << 31) || ci.n_snp >= (1ll << 28)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many records in one contig");
+        if (ci.length > 0x7fffffff - 2 * HCNV_SHORT_MAX - 4096 * 128) return hcnv_fail(ctx, HCNV_E_INVALID, "contig too long");
+        if (ci.n_blocks && (reinterpret_cast<uintptr_t>(ci.blocks) & 7)) return hcnv_fail(ctx, HCNV_E_INVALID, "blocks must be 8-byte aligned");
         const void* ptrs[5] = { ci.n_blocks ? (const void*)ci.blocks : nullptr, ci.n_long ? (const void*)ci.long_blocks : nullptr,
                                 ci.n_snp ? (const void*)ci.snp_pos1 : nullptr, ci.n_snp ? (const void*)ci.snp_zyg : nullptr,
                                 ci.n_obs ? (const void*)ci.obs : nullptr };
@@ -598,7 +372,12 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        kern<<<n_tiles, TB, smem_bytes, ctx->stream>>>(k);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem_bytes);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const int grid = std::min(n_tiles, ctx->sm_count * per_sm);       // persistent CTAs, tiles by ticket
+        kern<<<grid, TB, smem_bytes, ctx->stream>>>(k);
         return cudaGetLastError();
     };
     if (W % 4 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<4>));
