@@ -452,6 +452,7 @@ __global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_prob, con
 }
 
 #include "viterbi_par.cuh"
+#include "viterbi_chain.cuh"
 
 }  // namespace
 
@@ -584,9 +585,16 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         const size_t S = (size_t)total_segs;
         size_t o_seg = 0, o_epred = o_seg + 4 * (size_t)(n_problems + 1), o_flags = o_epred + 4 * S, o_force = o_flags + 4 * S;
         size_t o_repl = o_force + 4 * S, o_tf = (o_repl + 4 * (size_t)n_problems + 255) / 256 * 256, o_ti = o_tf + 144 * S;
-        size_t o_ls = o_ti + 288 * S, bytes = o_ls + 24 * (S + (size_t)n_problems);
+        // chunks of VCH segments (viterbi_chain.cuh)
+        std::vector<int> chunk_base(n_problems + 1, 0);
+        for (int i = 0; i < n_problems; ++i) chunk_base[i + 1] = chunk_base[i] + (h[i].n_seg + VCH - 1) / VCH;
+        const size_t NC = (size_t)chunk_base[n_problems];
+        size_t o_ls = o_ti + 288 * S, o_tc = (o_ls + 24 * (S + (size_t)n_problems) + 255) / 256 * 256;
+        size_t o_cinfo = o_tc + 288 * NC, o_cbase = o_cinfo + 4 * NC, bytes = o_cbase + 4 * (size_t)(n_problems + 1);
         HCNV_CUDA(ctx, ctx->buf[H_VPAR].reserve(bytes));
         char* vb = ctx->buf[H_VPAR].as<char>();
+        int* d_tc = (int*)(vb + o_tc); int* d_cinfo = (int*)(vb + o_cinfo); int* d_cbase = (int*)(vb + o_cbase);
+        HCNV_CUDA(ctx, cudaMemcpyAsync(d_cbase, chunk_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream));
         int* d_segbase = (int*)(vb + o_seg); int* d_epred = (int*)(vb + o_epred); int* d_flags = (int*)(vb + o_flags);
         int* d_force = (int*)(vb + o_force); int* d_repl = (int*)(vb + o_repl);
         float* d_tf = (float*)(vb + o_tf); int* d_ti = (int*)(vb + o_ti); float* d_ls = (float*)(vb + o_ls);
@@ -598,16 +606,28 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         k_vit_p0<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_tf);
         KT_END(ctx, HCNV_K_VIT_P0);
         KT_BEGIN(ctx, HCNV_K_VIT_P0C);
-        k_vit_p0c<<<n_problems, 32, 0, ctx->stream>>>(dprobs, d_segbase, alpha, d_tf, d_epred);
+        {
+            const int sm = 2 * P0C_T * 36 * 4;
+            HCNV_CUDA(ctx, cudaFuncSetAttribute(k_vit_p0c_par, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+            k_vit_p0c_par<<<n_problems, P0C_T, sm, ctx->stream>>>(dprobs, d_segbase, alpha, d_tf, d_epred);
+        }
         KT_END(ctx, HCNV_K_VIT_P0C);
         KT_BEGIN(ctx, HCNV_K_VIT_P1);
         k_vit_p1<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_epred, d_ti, d_flags);
         KT_END(ctx, HCNV_K_VIT_P1);
         ctx->launches += 3;
         for (int iter = 0; ; ++iter) {
+            const unsigned gc = (unsigned)((NC + 63) / 64);
+            KT_BEGIN(ctx, HCNV_K_VIT_P1B);
+            k_vit_p1b<<<gc, 64, 0, ctx->stream>>>(dprobs, d_segbase, d_cbase, n_problems, (int)NC, d_epred, d_ti, d_flags, d_force, d_tc, d_cinfo);
+            KT_END(ctx, HCNV_K_VIT_P1B);
             KT_BEGIN(ctx, HCNV_K_VIT_P2);
-            k_vit_p2<<<n_problems, 32, 0, ctx->stream>>>(dprobs, d_segbase, VSEG, alpha, d_epred, d_ti, d_flags, d_force, d_ls, d_repl);
+            k_vit_p2c<<<n_problems, 32, 0, ctx->stream>>>(dprobs, d_segbase, d_cbase, VSEG, alpha, d_epred, d_ti, d_flags, d_force, d_tc, d_cinfo, d_ls, d_repl);
             KT_END(ctx, HCNV_K_VIT_P2);
+            KT_BEGIN(ctx, HCNV_K_VIT_P2B);
+            k_vit_p2b<<<gc, 64, 0, ctx->stream>>>(dprobs, d_segbase, d_cbase, n_problems, (int)NC, d_ti, d_cinfo, d_ls);
+            KT_END(ctx, HCNV_K_VIT_P2B);
+            ctx->launches += 2;
             KT_BEGIN(ctx, HCNV_K_VIT_P3);
             k_vit_p3<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_ls, d_force);
             KT_END(ctx, HCNV_K_VIT_P3);

@@ -22,7 +22,7 @@
 #pragma once
 #include <cuda_pipeline.h>
 
-#define VSEG_DEFAULT 128
+#define VSEG_DEFAULT 64
 #define V_EMIN 6                   // binades below 2^6: u so small that per-segment sums could overflow int32 -> replay
 #define V_INF_I (1 << 29)
 #define V_INF_F 1.0e30f

@@ -78,6 +78,8 @@ int         hcnv_ctx_synchronize(hcnv_ctx* ctx);
 #define HCNV_K_VIT_P1         11    /*   exact integer transfer matrices                         */
 #define HCNV_K_VIT_P2         12    /*   exact chaining (+ replay of flagged segments)           */
 #define HCNV_K_VIT_P3         13    /*   exact float replay per segment: calls + verification    */
+#define HCNV_K_VIT_P1B        14    /*   chunk matrices (composition of 32 segment matrices)     */
+#define HCNV_K_VIT_P2B        15    /*   per-segment start vectors inside composed chunks        */
 #define HCNV_K_COUNT          16
 float       hcnv_ctx_kernel_ms(hcnv_ctx* ctx, int which);
 /* counters of the last hcnv_segment_batch call: 0 = segments of the segment-parallel Viterbi, 1 = segments that were

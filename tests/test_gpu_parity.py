@@ -188,7 +188,7 @@ def test_segment_parallel_viterbi_is_exact(ctx, seed, M, l1, l2, depth):
     want_full = O.hmm(b["median"], mse32, tot32, b["n"], l1, l2) if M <= 130000 else None
     got = ctx.segment_batch([dict(prob)])[0]
     st = ctx.stats()
-    assert st["viterbi_segments"] == (M - 1 + 127) // 128 and st["viterbi_repairs"] == 0
+    assert st["viterbi_segments"] == (M - 1 + 63) // 64 and st["viterbi_repairs"] == 0
     assert st["viterbi_segments_replayed"] < st["viterbi_segments"]           # the matrices really carry most segments
     seq = ctx.segment_batch([dict(prob)], flags=L.HCNV_SEG_SEQUENTIAL)[0]
     assert ctx.stats()["viterbi_segments"] == 0
