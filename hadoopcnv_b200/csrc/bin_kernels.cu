@@ -137,12 +137,12 @@ struct WalkOut {
 
 // One thread walks the W difference-array entries of its bin: running depth, written back in place.
 template <int VEC>
-__device__ __forceinline__ void walk_bin(int32_t* dp, int W, int carry, WalkOut& o) {
+__device__ __forceinline__ void walk_bin(int32_t* dp, int W, int carry, int bin_carry, WalkOut& o) {
     int d = carry;
     int n = 0, first = 0x7fffffff, last = -1;
     int rel_sum = 0;
     uint32_t m0 = 0, m1 = 0, oob = 0;
-    const int base = max(carry - 31, 1);
+    const int base = max(bin_carry - 31, 1);          // window anchored at the depth carried into the BIN (shared by its threads)
     auto step = [&](int& v, int i) {
         d += v;
         v = d;
@@ -238,9 +238,11 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         return hcnv_fail(ctx, HCNV_E_INVALID, "null output array");
 
     // tile geometry: TB bins (= threads) per CTA; shared memory = difference array + one staged chunk of records
-    int TB = P.tile_bins > 0 ? P.tile_bins : 128;
+    // HS = 2 threads share a bin when the bin width is even (more warps per SM for the per-position walk)
+    const int HS = ((P.flags & 1) && W % 2 == 0 && W >= 16) ? 2 : 1;   // measured slower on B200 at W = 100; opt-in (flags bit 0)
+    int TB = P.tile_bins > 0 ? P.tile_bins : (HS == 2 ? 64 : 128);
     TB = (TB + 31) / 32 * 32;
-    if (TB > 128) TB = 128;
+    if (TB * HS > 256) TB = 256 / HS;
     auto smem_need = [&](int tb) { return (((size_t)tb * W + 4) * 4 + 15) / 16 * 16 + (size_t)(RCAP + 4) * 8; };
     while (TB > 32 && smem_need(TB) > ctx->smem_optin) TB -= 32;
     if (smem_need(TB) > ctx->smem_optin) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1600)");
@@ -373,16 +375,23 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB * HS, smem_bytes);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         const int grid = std::min(n_tiles, ctx->sm_count * per_sm);       // persistent CTAs, tiles by ticket
-        kern<<<grid, TB, smem_bytes, ctx->stream>>>(k);
+        kern<<<grid, TB * HS, smem_bytes, ctx->stream>>>(k);
         return cudaGetLastError();
     };
-    if (W % 4 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<4>));
-    else if (W % 2 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<2>));
-    else HCNV_CUDA(ctx, launch(k_bin_tiles<1>));
+    const int Wt = W / HS;                         // positions per thread
+    if (HS == 2) {
+        if (Wt % 4 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<4, 2>));
+        else if (Wt % 2 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<2, 2>));
+        else HCNV_CUDA(ctx, launch(k_bin_tiles<1, 2>));
+    } else {
+        if (Wt % 4 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<4, 1>));
+        else if (Wt % 2 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<2, 1>));
+        else HCNV_CUDA(ctx, launch(k_bin_tiles<1, 1>));
+    }
     KT_END(ctx, HCNV_K_BIN_TILES);
     ctx->launches++;
 

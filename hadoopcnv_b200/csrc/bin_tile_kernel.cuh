@@ -45,14 +45,31 @@ struct TileOut {
     double total;
 };
 
-template <int VEC>
-__global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
+struct TileMeta {                                 // what a tile needs from its contig + the tile index, staged in smem
+    const hcnv_block*      blocks;
+    const hcnv_long_block* longs;
+    const int32_t*         snp_pos;
+    const int8_t*          snp_zyg;
+    long long n_long, snp_base;
+    int contig, k, length, n_bins_max;
+    uint32_t lb, lo, hi, slo, shi;
+};
+
+#define SCAP 256                                  // SNP sites of a tile staged in shared memory (more: global path)
+
+template <int VEC, int HS>
+__global__ void __launch_bounds__(256) k_bin_tiles(BinK p) {
     extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ TileMeta s_meta[2];
+    __shared__ int s_spos[SCAP];                  // staged SNP sites: position, zygosity, (total, max) of the allele tally
+    __shared__ signed char s_szyg[SCAP];
+    __shared__ uint2 s_stm[SCAP];
+    __shared__ int s_bfirst[256], s_bcnt[256];    // per bin: first staged SNP and how many
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_tile, s_prev;
-    __shared__ int s_warp[4];
+    __shared__ int s_warp[8];
     __shared__ long long s_prefix;
-    const int tid = threadIdx.x, nthr = blockDim.x;   // == TB: a multiple of 32, at most 128
+    const int tid = threadIdx.x, nthr = blockDim.x;   // == TB * HS: a multiple of 32, at most 256
     const int lane = tid & 31, wid = tid >> 5;
     const int W = p.W, TB = p.TB;
     const int TP = TB * W;
@@ -60,7 +77,7 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
     hcnv_block* rec = reinterpret_cast<hcnv_block*>(smraw + (((size_t)(TP + 4) * 4 + 15) & ~(size_t)15));   // RCAP + 4 slots
 
     if (tid == 0) mbar_init(&s_bar, 1);
-    if (tid < 4) s_warp[tid] = 0;
+    if (tid < 8) s_warp[tid] = 0;
     __syncthreads();
     uint32_t phase = 0;
 
@@ -70,11 +87,18 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
     for (int j = 0; j < 6; ++j) po.mse[j] = 0;
     int p_t = -1, p_count = 0, p_rank = 0, p_contig = 0, p_first_of_contig = 0;
 
-    // tid 0: start the first chunk of tile `tt` (TMA bulk copy + ragged head record + predecessor's start)
-    auto issue_first_chunk = [&](int tt) {
-        const ContigDev& cc = p.contigs[p.tile_contig[tt]];
+    // tid 0: fetch the metadata of tile `tt` into s_meta[slot] and start its first chunk (TMA bulk copy + ragged
+    // head record + predecessor's start).  Done one tile ahead, so nobody waits on these dependent global loads.
+    auto issue_first_chunk = [&](int tt, int slot) {
+        const int ci = p.tile_contig[tt];
+        const ContigDev& cc = p.contigs[ci];
         const uint32_t lb_ = p.rec_lb[tt], hi_ = p.rec_hi[tt];
         const hcnv_block* blk = cc.blocks;
+        TileMeta& mm = s_meta[slot];
+        mm.blocks = blk; mm.longs = cc.longs; mm.snp_pos = cc.snp_pos; mm.snp_zyg = cc.snp_zyg;
+        mm.n_long = cc.n_long; mm.snp_base = cc.snp_base;
+        mm.contig = ci; mm.k = tt - cc.tile_base; mm.length = cc.length; mm.n_bins_max = cc.n_bins_max;
+        mm.lb = lb_; mm.lo = p.rec_lo[tt]; mm.hi = hi_; mm.slo = p.snp_lo[tt]; mm.shi = p.snp_hi[tt];
         const uint32_t a0_ = (uint32_t)((reinterpret_cast<unsigned long long>(blk) >> 3) & 1ull);
         uint32_t lbA_ = lb_ + ((a0_ + lb_) & 1u);
         if (lbA_ > hi_) lbA_ = hi_;
@@ -84,9 +108,10 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
         s_prev = (lb_ > 0) ? __ldg(&blk[lb_ - 1].start0) : (int)0x80000000;
         if (lbA_ > lb_) rec[1] = blk[lb_];
     };
-    if (tid == 0) { s_tile = (int)atomicAdd(p.ticket, 1u); if (s_tile < p.n_tiles) issue_first_chunk(s_tile); }
+    if (tid == 0) { s_tile = (int)atomicAdd(p.ticket, 1u); if (s_tile < p.n_tiles) issue_first_chunk(s_tile, 0); }
+    int cur = 0;
 
-    for (;;) {
+    for (;; cur ^= 1) {
         __syncthreads();
         const int t = s_tile;
         const bool have = t < p.n_tiles;
@@ -96,14 +121,14 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
         int c_count = 0, c_rank = 0, c_contig = 0, c_first = 0;
 
         if (have) {
-            c_contig = p.tile_contig[t];
-            const ContigDev c = p.contigs[c_contig];
-            const int k = t - c.tile_base;
+            const TileMeta& c = s_meta[cur];                        // staged by tid 0 one tile ahead
+            c_contig = c.contig;
+            const int k = c.k;
             c_first = (k == 0);
             const int T0 = k * TP;                                  // 1-based position of diff[0] (fits int: length < 2^31)
             const long long T1l = (long long)T0 + TP;
             const int T1 = (int)min(T1l, (long long)0x7fffffff);
-            const uint32_t lb = p.rec_lb[t], lo = p.rec_lo[t], hi = p.rec_hi[t];
+            const uint32_t lb = c.lb, lo = c.lo, hi = c.hi;
             if (hi < lo || lo < lb) atomicOr(&p.err[ERR_UNSORTED], 1);
             const hcnv_block* __restrict__ blocks = c.blocks;
             // 16-byte aligned sub-range [lbA, hiA) goes through TMA; a ragged head / tail record is loaded directly
@@ -117,7 +142,29 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
             // (the first chunk of this tile was issued by tid 0 before the previous tile's walk, or at kernel start)
             // ---- clear the difference array
             for (int i = tid * 4; i < TP + 4; i += nthr * 4) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
+            for (int i = tid; i < TB; i += nthr) { s_bfirst[i] = 0x7fffffff; s_bcnt[i] = 0; }
             __syncthreads();
+            // ---- stage the tile's SNP sites (VcfLookup side input) and reduce their allele tallies to (total, max)
+            const uint32_t slo = c.slo, shi = c.shi;
+            const bool snp_staged = shi - slo <= (uint32_t)SCAP;
+            if (snp_staged) {
+                for (uint32_t i = tid; i < shi - slo; i += nthr) {
+                    const uint32_t s = slo + i;
+                    const int pos = __ldg(&c.snp_pos[s]);
+                    if (s > 0 && __ldg(&c.snp_pos[s - 1]) >= pos) atomicOr(&p.err[ERR_UNSORTED], 1);
+                    const uint4* tr = reinterpret_cast<const uint4*>(p.tally + ((size_t)(c.snp_base + s)) * 16);
+                    uint32_t tot = 0, mx = 0;
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 v = __ldg(tr + j);
+                        tot += v.x + v.y + v.z + v.w;
+                        mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w));
+                    }
+                    s_spos[i] = pos; s_szyg[i] = c.snp_zyg[s]; s_stm[i] = make_uint2(tot, mx);
+                    if (pos < 0 || pos > c.length || pos < T0 || (long long)pos >= T1l) atomicOr(&p.err[ERR_RANGE], 1);
+                    else { const int bb = (pos - T0) / W; atomicMin(&s_bfirst[bb], (int)i); atomicAdd(&s_bcnt[bb], 1); }
+                }
+            }
             // ---- blocks of any length (few)
             for (long long i = tid; i < c.n_long; i += nthr) {
                 hcnv_long_block r = c.longs[i];
@@ -158,7 +205,7 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
                 __syncthreads();
                 if (last_chunk) {
                     // claim the next tile now and start its first chunk: it lands while this tile is being walked
-                    if (tid == 0) { s_tile = (int)atomicAdd(p.ticket, 1u); if (s_tile < p.n_tiles) issue_first_chunk(s_tile); }
+                    if (tid == 0) { s_tile = (int)atomicAdd(p.ticket, 1u); if (s_tile < p.n_tiles) issue_first_chunk(s_tile, cur ^ 1); }
                     break;
                 }
                 cb += cnt;
@@ -173,14 +220,16 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
             }
 
             // ---- per-bin sum of the difference array -> exclusive scan -> depth carried into each bin
-            const int b = tid;
+            // HS threads share a bin: thread (b, h) owns positions [h*Wt, (h+1)*Wt) of bin b; threads are in position order
+            const int b = tid / HS, h = tid % HS;
+            const int Wt = W / HS;
             const int nb_tile = min(TB, c.n_bins_max - k * TB);
-            int32_t* dp = diff + b * W;
+            int32_t* dp = diff + b * W + h * Wt;
             int bsum = 0;
             if (b < nb_tile) {
-                if (VEC == 4) { const int4* q = reinterpret_cast<const int4*>(dp); for (int i = 0; i < W / 4; ++i) { int4 v = q[i]; bsum += (v.x + v.y) + (v.z + v.w); } }
-                else if (VEC == 2) { const int2* q = reinterpret_cast<const int2*>(dp); for (int i = 0; i < W / 2; ++i) { int2 v = q[i]; bsum += v.x + v.y; } }
-                else { for (int i = 0; i < W; ++i) bsum += dp[i]; }
+                if (VEC == 4) { const int4* q = reinterpret_cast<const int4*>(dp); for (int i = 0; i < Wt / 4; ++i) { int4 v = q[i]; bsum += (v.x + v.y) + (v.z + v.w); } }
+                else if (VEC == 2) { const int2* q = reinterpret_cast<const int2*>(dp); for (int i = 0; i < Wt / 2; ++i) { int2 v = q[i]; bsum += v.x + v.y; } }
+                else { for (int i = 0; i < Wt; ++i) bsum += dp[i]; }
             }
             int incl = bsum;
             #pragma unroll
@@ -189,37 +238,39 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
             __syncthreads();
             int woff = 0;
             #pragma unroll
-            for (int i = 0; i < 4; ++i) if (i < wid) woff += s_warp[i];   // unused warps' slots stay 0
+            for (int i = 0; i < 8; ++i) if (i < wid) woff += s_warp[i];   // unused warps' slots stay 0
             const int carry = incl - bsum + woff;
 
-            // ---- walk, SNP sites, BinReducer record
-            if (b < nb_tile) {
-                WalkOut w;
-                walk_bin<VEC>(dp, W, carry, w);
+            // ---- walk (every thread its share), merge the shares of a bin, then SNP sites and the BinReducer record
+            WalkOut w;
+            w.n = 0; w.first = 0x7fffffff; w.last = -1; w.sum = 0; w.m0 = w.m1 = 0; w.base = 1; w.oob = 0;
+            {
+                const int bin_carry = __shfl_sync(0xffffffffu, carry, lane - h);       // depth carried into the bin (thread h = 0)
+                if (b < nb_tile) walk_bin<VEC>(dp, Wt, carry, bin_carry, w);
+                if (HS == 2) {
+                    // thread h = 1 hands its share to thread h = 0 (adjacent lanes)
+                    const int n1 = __shfl_down_sync(0xffffffffu, w.n, 1), f1 = __shfl_down_sync(0xffffffffu, w.first, 1);
+                    const int l1 = __shfl_down_sync(0xffffffffu, w.last, 1);
+                    const long long s1 = __shfl_down_sync(0xffffffffu, w.sum, 1);
+                    const uint32_t a0 = __shfl_down_sync(0xffffffffu, w.m0, 1), a1 = __shfl_down_sync(0xffffffffu, w.m1, 1);
+                    const uint32_t o1 = __shfl_down_sync(0xffffffffu, w.oob, 1);
+                    if (h == 0) {
+                        w.n += n1; w.sum += s1; w.m0 |= a0; w.m1 |= a1; w.oob |= o1;
+                        if (f1 != 0x7fffffff) w.first = min(w.first, f1 + Wt);
+                        if (l1 >= 0) w.last = l1 + Wt;
+                    }
+                }
+            }
+            dp = diff + b * W;                                     // from here on: the whole bin, thread h = 0 only
+            if (b < nb_tile && h == 0) {
                 const int bin_lo = T0 + b * W;
                 int n = w.n, first = w.first, last = w.last;
                 bool has_zero = false;
                 int nbaf = 0;
-                const uint32_t slo = p.snp_lo[t], shi = p.snp_hi[t];
-                if (shi > slo) {
-                    uint32_t s = slo + lower_bound_i32(c.snp_pos + slo, (long long)(shi - slo), (int32_t)bin_lo);
-                    for (; s < shi; ++s) {
-                        int pos = __ldg(&c.snp_pos[s]);
-                        if ((long long)pos >= (long long)bin_lo + W) break;
-                        if (s > 0 && __ldg(&c.snp_pos[s - 1]) >= pos) atomicOr(&p.err[ERR_UNSORTED], 1);
-                        if (pos < 0 || pos > c.length) { atomicOr(&p.err[ERR_RANGE], 1); continue; }
-                        int off = pos - bin_lo;
-                        int d = dp[off];
-                        const uint4* tr = reinterpret_cast<const uint4*>(p.tally + ((size_t)(c.snp_base + s)) * 16);
-                        uint32_t tot = 0, mx = 0;
-                        #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 v = __ldg(tr + j);
-                            tot += v.x + v.y + v.z + v.w;
-                            mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w));
-                        }
+                // one SNP site of this bin, in ascending position order (Reducers.java:76-82,120-129,160-185)
+                auto snp_site = [&](int off, uint32_t tot, uint32_t mx, int zyg) {
+                        const int d = dp[off];
                         if (tot != (uint32_t)d) atomicOr(&p.err[ERR_INCONSISTENT], 1);
-                        int zyg = c.snp_zyg[s];
                         if (d == 0) { ++n; first = min(first, off); last = max(last, off); has_zero = true; }
                         else if (zyg <= 0) {
                             float ptd = (float)d, mxd = (float)mx;
@@ -233,6 +284,29 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
                             else { co.mse[2] += b2; co.mse[3] += b2; co.mse[4] += b2; co.mse[5] += b2; }
                             ++nbaf;
                         }
+                };
+                if (snp_staged) {
+                    const int cntb = s_bcnt[b];
+                    if (cntb > 0) {
+                        const int f0 = s_bfirst[b];
+                        for (int i = f0; i < f0 + cntb; ++i) { const uint2 tm = s_stm[i]; snp_site(s_spos[i] - bin_lo, tm.x, tm.y, (int)s_szyg[i]); }
+                    }
+                } else if (shi > slo) {                              // crowded tile: straight from global memory
+                    uint32_t s = slo + lower_bound_i32(c.snp_pos + slo, (long long)(shi - slo), (int32_t)bin_lo);
+                    for (; s < shi; ++s) {
+                        const int pos = __ldg(&c.snp_pos[s]);
+                        if ((long long)pos >= (long long)bin_lo + W) break;
+                        if (s > 0 && __ldg(&c.snp_pos[s - 1]) >= pos) atomicOr(&p.err[ERR_UNSORTED], 1);
+                        if (pos < 0 || pos > c.length) { atomicOr(&p.err[ERR_RANGE], 1); continue; }
+                        const uint4* tr = reinterpret_cast<const uint4*>(p.tally + ((size_t)(c.snp_base + s)) * 16);
+                        uint32_t tot = 0, mx = 0;
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 v = __ldg(tr + j);
+                            tot += v.x + v.y + v.z + v.w;
+                            mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w));
+                        }
+                        snp_site(pos - bin_lo, tot, mx, (int)c.snp_zyg[s]);
                     }
                 }
                 if (nbaf > 1) { double dn = (double)nbaf; for (int j = 0; j < 6; ++j) co.mse[j] = co.mse[j] / dn; }   // :186-190
@@ -262,7 +336,7 @@ __global__ void __launch_bounds__(128, 3) k_bin_tiles(BinK p) {
             __syncthreads();
             c_rank = __popc(ball & ((1u << lane) - 1u));
             #pragma unroll
-            for (int i = 0; i < 4; ++i) { int v = s_warp[i]; if (i < wid) c_rank += v; c_count += v; }
+            for (int i = 0; i < 8; ++i) { int v = s_warp[i]; if (i < wid) c_rank += v; c_count += v; }
             if (tid == 0) {
                 volatile unsigned long long* st = p.status;
                 st[t] = ((t == 0) ? (2ull << 62) : (1ull << 62)) | (unsigned long long)c_count;

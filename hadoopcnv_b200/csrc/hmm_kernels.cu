@@ -15,6 +15,9 @@
 #include <cfloat>
 #include <vector>
 #include <algorithm>
+#include <cuda_pipeline.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -103,6 +106,42 @@ __device__ __noinline__ int shortest_decimal_direction(double d) {
     return 0;   // 17 digits always round-trip; not reached
 }
 
+// Same question answered in 128-bit integers when m * 5^k fits (every MSE value above ~1e-13 does).
+// Returns 2 when the value does not fit and the 512-bit path must be taken.
+__device__ __noinline__ int shortest_decimal_direction_u128(double d) {
+    typedef unsigned __int128 u128;
+    unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+    int E = (int)((bits >> 52) & 0x7ff) - 1023;
+    unsigned long long m = (bits & ((1ull << 52) - 1)) | (1ull << 52);
+    int q = E - 52;
+    int tz = __ffsll((long long)m) - 1;
+    m >>= tz; q += tz;                                  // d = m * 2^q, m odd
+    const int L = 64 - __clzll((long long)m);
+    if (q >= 0 || -q > 43 || L > 26) return 2;
+    const int k = -q, a = 54 - L;
+    u128 N = m, rhs = 1;
+    for (int i = 0; i < k; ++i) { N *= 5; rhs *= 5; }
+    const u128 lim = rhs >> a;                           // err * 2^a <= 5^k  <=>  err <= floor(5^k / 2^a)
+    // powers of ten up to N (no 128-bit divisions anywhere); D = number of digits of N
+    u128 pw[40];
+    int D = 1;
+    pw[0] = 1;
+    while (D < 39 && pw[D - 1] * 10 <= N) { pw[D] = pw[D - 1] * 10; ++D; }   // N < 2^127 < 10^39: no overflow
+    u128 r = N;
+    for (int n = 1; n <= 17; ++n) {
+        if (n >= D) return 0;
+        const u128 P = pw[D - n];                        // 10^(D-n)
+        unsigned dig = 0;
+        while (r >= P) { r -= P; ++dig; }                // n-th digit; r = N mod 10^(D-n)
+        const u128 twice = r << 1;
+        const bool up = twice > P || (twice == P && (dig & 1));
+        const u128 err = up ? P - r : r;
+        if (err == 0) return 0;
+        if (err <= lim) return up ? 1 : -1;
+    }
+    return 0;
+}
+
 __device__ __forceinline__ float f64_text_f32(double d) {
     float f = __double2float_rn(d);
     if (!(fabs(d) < 3.0e38) || d == 0.0 || (double)f == d) return f;     // NaN/Inf/huge/zero/exact
@@ -112,17 +151,54 @@ __device__ __forceinline__ float f64_text_f32(double d) {
     float hi = __uint_as_float(__float_as_uint(lo) + 1u);
     double mid = 0.5 * ((double)lo + (double)hi);        // exact
     if (ad != mid) return f;
-    int dir = shortest_decimal_direction(ad);
+    int dir = shortest_decimal_direction_u128(ad);
+    if (dir == 2) dir = shortest_decimal_direction(ad);
     float r = dir > 0 ? hi : (dir < 0 ? lo : af /* tie: parse rounds to even like the cast */);
     return d < 0 ? -r : r;
 }
 
+// Streaming pass: the plain cast is right except for doubles that sit exactly half way between two floats
+// (low 29 significand bits == 1 followed by 28 zeros, in the normal float range) and for the denormal float range;
+// those few go to a work list that k_text_roundtrip_fix resolves with full-width lanes.
+__device__ __forceinline__ bool needs_decimal_check(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    const unsigned long long ab = b & 0x7fffffffffffffffull;
+    if (ab >= 0x47f0000000000000ull) return false;                  // >= 2^128, Inf, NaN: the cast decides
+    if (ab < 0x3810000000000000ull) return ab != 0;                 // below 2^-126 (denormal floats): rare, check fully
+    return (b & 0x1fffffffull) == 0x10000000ull;
+}
 __global__ void k_text_roundtrip(const double* __restrict__ mse, const double* __restrict__ total, long long n,
-                                 float* __restrict__ mse32, float* __restrict__ total32) {
+                                 float* __restrict__ mse32, float* __restrict__ total32,
+                                 long long* __restrict__ work, unsigned long long* __restrict__ work_n, long long work_cap) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n6 = n * 6, nall = total ? n6 + n : n6;
+    for (long long j = i; j < nall; j += stride) {
+        const double d = (j < n6) ? __ldg(&mse[j]) : __ldg(&total[j - n6]);
+        float f = __double2float_rn(d);
+        if (needs_decimal_check(d)) {
+            unsigned long long slot = atomicAdd(work_n, 1ull);
+            if ((long long)slot < work_cap) work[slot] = j;          // else: the host sees work_n > cap and runs k_text_roundtrip_all
+        }
+        if (j < n6) mse32[j] = f; else total32[j - n6] = f;
+    }
+}
+// pathological inputs (more half-way values than the work list holds): every element through the full function
+__global__ void k_text_roundtrip_all(const double* __restrict__ mse, const double* __restrict__ total, long long n,
+                                     float* __restrict__ mse32, float* __restrict__ total32) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = i; j < n * 6; j += stride) mse32[j] = f64_text_f32(mse[j]);
     if (total) for (long long j = i; j < n; j += stride) total32[j] = f64_text_f32(total[j]);
+}
+__global__ void k_text_roundtrip_fix(const double* __restrict__ mse, const double* __restrict__ total, long long n,
+                                     float* __restrict__ mse32, float* __restrict__ total32,
+                                     const long long* __restrict__ work, const unsigned long long* __restrict__ work_n, long long work_cap) {
+    const long long cnt = min((long long)*work_n, work_cap), n6 = n * 6;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < cnt; w += (long long)gridDim.x * blockDim.x) {
+        const long long j = work[w];
+        if (j < n6) mse32[j] = f64_text_f32(mse[j]); else total32[j - n6] = f64_text_f32(total[j - n6]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -175,14 +251,7 @@ __global__ void k_mean_coverage(SegDev* probs, int n_probs) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The same sequential float sum, evaluated exactly in parallel (one CTA per chromosome).
-// Per-bin totals are non-negative integers.  Below 2^24 every partial sum is exact.  Inside a binade
-// [2^e, 2^(e+1)), e >= 24, the sum is a multiple of u = 2^(e-23); with S = s*u and t = q*u + r:
-//   fl(S + t) = (s + q + c) * u,  c = 0 if r < u/2, 1 if r > u/2, and for r == u/2 (a tie) c = (s + q) & 1.
-// So each element is a map  s -> s + a[s & 1]  and maps compose associatively: a block scan over a window of
-// elements gives the exact running sum.  When the sum leaves the binade, the crossing element is added with one
-// real float add and the next binade starts behind it.  Totals that are not non-negative integers fall back to the
-// sequential warp kernel above.
+// maps s -> s + a[s & 1] used by the exact parallel mean coverage (mean_cluster.cuh)
 struct PMap { long long a0, a1; };
 __device__ __forceinline__ PMap pm_compose(const PMap& f, const PMap& g) {     // f first, then g
     PMap r;
@@ -193,101 +262,7 @@ __device__ __forceinline__ PMap pm_compose(const PMap& f, const PMap& g) {     /
 __device__ __forceinline__ PMap pm_shfl_up(const PMap& m, int o) {
     PMap r; r.a0 = __shfl_up_sync(0xffffffffu, m.a0, o); r.a1 = __shfl_up_sync(0xffffffffu, m.a1, o); return r;
 }
-#define MC_T 512
-#define MC_K 16
-__global__ void __launch_bounds__(MC_T) k_mean_coverage_par(SegDev* probs) {
-    __shared__ float s_el[MC_T * (MC_K + 1)];
-    __shared__ PMap s_w[MC_T / 32];
-    __shared__ long long s_sbefore;
-    __shared__ int s_cross, s_int[2];
-    SegDev& P = probs[blockIdx.x];
-    const long long M = P.M;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const float* __restrict__ tot = P.total;
-    // pass 0: int sum of sites (wraps like Java's int) and the "non-negative integers" test
-    int sites = 0, okint = 1;
-    for (long long i = tid; i < M; i += MC_T) {
-        float t = __ldg(&tot[i]);
-        sites += __ldg(&P.n[i]);
-        okint &= (t >= 0.f && t < 9.0e18f && t == truncf(t)) ? 1 : 0;
-    }
-    if (tid == 0) { s_int[0] = 0; s_int[1] = 1; }
-    __syncthreads();
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { sites += __shfl_xor_sync(0xffffffffu, sites, o); okint &= __shfl_xor_sync(0xffffffffu, okint, o); }
-    if (lane == 0) { atomicAdd(&s_int[0], sites); atomicAnd(&s_int[1], okint); }
-    __syncthreads();
-    sites = s_int[0];
-    if (!s_int[1]) { if (tid == 0) P.mean = __int_as_float(0x7fc00001); P.pad = 1; return; }   // marker: sequential kernel takes over
-    float S = 0.f;
-    long long pos = 0;
-    while (pos < M) {
-        const int e = (S >= 16777216.f) ? (int)((__float_as_uint(S) >> 23) & 0xffu) - 127 : 23;
-        const int sh = e - 23;
-        const long long msk = (1ll << sh) - 1, half = sh > 0 ? (1ll << (sh - 1)) : -1;
-        const long long thr = 1ll << 24;
-        const long long s_start = (long long)S >> sh;
-        const int wlen = (int)min((long long)MC_T * MC_K, M - pos);
-        __syncthreads();
-        for (int g = tid; g < wlen; g += MC_T) s_el[(g / MC_K) * (MC_K + 1) + (g % MC_K)] = __ldg(&tot[pos + g]);
-        if (tid == 0) s_cross = 0x7fffffff;
-        __syncthreads();
-        const int first = tid * MC_K, cnt = max(0, min(MC_K, wlen - first));
-        PMap f; f.a0 = 0; f.a1 = 0;
-        for (int k2 = 0; k2 < cnt; ++k2) {
-            long long ti = (long long)s_el[tid * (MC_K + 1) + k2];
-            long long q = ti >> sh, r = ti & msk;
-            long long up = r > half && sh > 0 ? 1 : 0;
-            bool tie = r == half;
-            f.a0 += q + (tie ? ((f.a0 + q) & 1) : up);
-            f.a1 += q + (tie ? ((1 + f.a1 + q) & 1) : up);
-        }
-        // ordered block scan of the maps
-        PMap inc = f;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { PMap u = pm_shfl_up(inc, o); if (lane >= o) inc = pm_compose(u, inc); }
-        if (lane == 31) s_w[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            PMap w; w.a0 = 0; w.a1 = 0;
-            if (lane < MC_T / 32) w = s_w[lane];
-            PMap wi = w;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { PMap u = pm_shfl_up(wi, o); if (lane >= o) wi = pm_compose(u, wi); }
-            if (lane < MC_T / 32) s_w[lane] = wi;                      // inclusive over warps
-        }
-        __syncthreads();
-        const PMap wtot = s_w[MC_T / 32 - 1];
-        const long long s_end = s_start + ((s_start & 1) ? wtot.a1 : wtot.a0);
-        if (s_end < thr) { S = (float)(s_end << sh); pos += wlen; continue; }
-        // the sum leaves the binade inside this window: find the first element whose result reaches 2^(e+1)
-        PMap ex; ex.a0 = 0; ex.a1 = 0;                                  // exclusive prefix of this thread
-        {
-            PMap prevw; prevw.a0 = 0; prevw.a1 = 0;
-            if (wid > 0) prevw = s_w[wid - 1];
-            PMap lanex = pm_shfl_up(inc, 1);
-            if (lane == 0) { lanex.a0 = 0; lanex.a1 = 0; }
-            ex = pm_compose(prevw, lanex);
-        }
-        long long sv = s_start + ((s_start & 1) ? ex.a1 : ex.a0);
-        int mycross = 0x7fffffff; long long mybefore = 0;
-        for (int k2 = 0; k2 < cnt; ++k2) {
-            long long ti = (long long)s_el[tid * (MC_K + 1) + k2];
-            long long q = ti >> sh, r = ti & msk;
-            long long nx = sv + q + ((r == half) ? ((sv + q) & 1) : ((r > half && sh > 0) ? 1 : 0));
-            if (nx >= thr && mycross == 0x7fffffff) { mycross = first + k2; mybefore = sv; }
-            sv = nx;
-        }
-        if (mycross != 0x7fffffff) atomicMin(&s_cross, mycross);
-        __syncthreads();
-        const int ic = s_cross;
-        if (mycross == ic) s_sbefore = mybefore;
-        __syncthreads();
-        S = __fadd_rn((float)(s_sbefore << sh), s_el[(ic / MC_K) * (MC_K + 1) + (ic % MC_K)]);   // the one real float add
-        pos += ic + 1;
-    }
-    if (tid == 0) P.mean = __fdiv_rn(S, (float)sites);
-}
+#include "mean_cluster.cuh"
 
 // scale_depth, Hmm.java:121-135 (element-wise; all problems in one launch via a block->problem map)
 __global__ void k_scale_depth(SegDev* probs, const int* __restrict__ blk_prob, const long long* __restrict__ blk_first) {
@@ -458,7 +433,7 @@ __global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_prob, con
 
 // ---------------------------------------------------------------------------------------------------
 namespace {
-enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR };
+enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR, H_RT_WORK };
 }
 
 int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
@@ -480,10 +455,25 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
         d_mse = di; d_tot = total ? di + 6 * n : nullptr; d_m32 = fo; d_t32 = total ? fo + 6 * n : nullptr;
     }
     int grid = (int)std::min<long long>((n * 6 + 255) / 256, (long long)ctx->sm_count * 32);
+    const long long work_cap = n;
+    HCNV_CUDA(ctx, ctx->buf[H_RT_WORK].reserve(8 * (size_t)work_cap + 64));
+    unsigned long long* d_wn = ctx->buf[H_RT_WORK].as<unsigned long long>();
+    long long* d_work = (long long*)(d_wn + 8);
+    HCNV_CUDA(ctx, cudaMemsetAsync(d_wn, 0, 8, ctx->stream));
     KT_BEGIN(ctx, HCNV_K_TEXT_ROUNDTRIP);
-    k_text_roundtrip<<<grid, 256, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32);
+    k_text_roundtrip<<<grid, 256, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32, d_work, d_wn, work_cap);
+    k_text_roundtrip_fix<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32, d_work, d_wn, work_cap);
     KT_END(ctx, HCNV_K_TEXT_ROUNDTRIP);
-    ctx->launches++;
+    ctx->launches += 2;
+    {
+        unsigned long long wn = 0;
+        HCNV_CUDA(ctx, cudaMemcpyAsync(&wn, d_wn, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((long long)wn > work_cap) {
+            k_text_roundtrip_all<<<grid, 256, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32);
+            ctx->launches++;
+        }
+    }
     HCNV_CUDA(ctx, cudaGetLastError());
     if (!dev) {
         HCNV_CUDA(ctx, cudaMemcpyAsync(mse_f32, d_m32, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -569,7 +559,7 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
 
     const int wpb = 4;   // warps per block for the one-warp-per-chromosome kernels
     KT_BEGIN(ctx, HCNV_K_MEAN_COVERAGE);
-    k_mean_coverage_par<<<n_problems, MC_T, 0, ctx->stream>>>(dprobs);
+    k_mean_coverage_cluster<<<n_problems * MCC_CS, MCC_T, 0, ctx->stream>>>(dprobs);
     k_mean_coverage<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
     KT_END(ctx, HCNV_K_MEAN_COVERAGE);
     KT_BEGIN(ctx, HCNV_K_SCALE_DEPTH);

@@ -89,6 +89,14 @@ def test_binning_edge_cases(ctx):
     assert list(w3["bin"]) == [100] and list(w3["start"]) == [100]
 
 
+def test_binning_dense_snp_sites(ctx):
+    """More SNP sites per tile than the shared-memory staging holds: the kernel's global-memory SNP path."""
+    g = synth.make_genome(coverage=15, scale=0.001, device="cpu", contigs=["chr19", "chr22"], seed=8, het_per_bp=0.03, hom_per_bp=0.02)
+    res = ctx.bin_contigs(synth.to_api_contigs(g, host=True), max_block_len=150)
+    for i, c in enumerate(g):
+        assert_bins_equal(res.contig(i), oracle_bins(c, 100))
+
+
 def test_binning_mapq_threshold(ctx):
     g = synth.make_genome(coverage=20, scale=0.001, device="cpu", contigs=["chr21"], seed=5, het_per_bp=0, hom_per_bp=0)
     thr = 0.9                                      # 1 - 10^(-q/10) >= 0.9  <=>  q >= 10
