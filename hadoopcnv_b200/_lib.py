@@ -67,6 +67,8 @@ EXPORTS = [
     "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_ctx_stat", "hcnv_bin_params_default", "hcnv_bin_contigs",
     "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
     "hcnv_write_bins_text", "hcnv_write_results_text",
+    "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
+    "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_free",
 ]
 
 _lib = None
@@ -115,5 +117,17 @@ def lib():
     L.hcnv_format_double.argtypes = [C.c_double, C.c_char_p]
     L.hcnv_write_bins_text.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64] + [C.c_void_p] * 7
     L.hcnv_write_results_text.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64] + [C.c_void_p] * 6
+    L.hcnv_vcf_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.hcnv_snp_table_n_contigs.argtypes = [C.c_void_p]
+    L.hcnv_snp_table_get.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.hcnv_snp_table_free.argtypes = [C.c_void_p]
+    L.hcnv_snp_table_free.restype = None
+    L.hcnv_bam_pack.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.hcnv_pack_n_contigs.argtypes = [C.c_void_p]
+    L.hcnv_pack_n_records.argtypes = [C.c_void_p]
+    L.hcnv_pack_n_records.restype = C.c_int64
+    L.hcnv_pack_contig.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(ContigInput), C.POINTER(C.c_int32)]
+    L.hcnv_pack_free.argtypes = [C.c_void_p]
+    L.hcnv_pack_free.restype = None
     _lib = L
     return L

@@ -1,0 +1,81 @@
+"""Host side of B1 (no GPU): VCF side input and BAM/BGZF packer, bound from libhcnv.so.
+
+    VcfLookup.parseVcf2Text  (VcfLookup.java:135-196)  -> SnpTable
+    SAMRecordWindowMapper's view of a SAMRecord (Mappers.java:174-212, htsjdk getAlignmentBlocks) -> pack_bam
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .api import BLOCK_DTYPE, LONG_BLOCK_DTYPE, Contig
+
+
+class SnpTable:
+    """hcnv_snp_table: per-contig ascending unique 1-based SNP positions with zygosity in {0,-1,-2}."""
+
+    def __init__(self, vcf_path: str):
+        self._lib = L.lib()
+        h = C.c_void_p()
+        st = self._lib.hcnv_vcf_load(vcf_path.encode(), C.byref(h))
+        if st != 0:
+            raise L.HcnvError(st, "hcnv_vcf_load(%s): %s (the reference prints an error and exits here)"
+                              % (vcf_path, self._lib.hcnv_strerror(st).decode()))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hcnv_snp_table_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def contigs(self) -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
+        out = {}
+        for i in range(self._lib.hcnv_snp_table_n_contigs(self._h)):
+            name, pos, zyg, n = C.c_char_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+            self._lib.hcnv_snp_table_get(self._h, i, C.byref(name), C.byref(pos), C.byref(zyg), C.byref(n))
+            k = n.value
+            p = np.ctypeslib.as_array(C.cast(pos, C.POINTER(C.c_int32)), (k,)).copy() if k else np.zeros(0, np.int32)
+            z = np.ctypeslib.as_array(C.cast(zyg, C.POINTER(C.c_int8)), (k,)).copy() if k else np.zeros(0, np.int8)
+            out[name.value.decode()] = (p, z)
+        return out
+
+    def vcf_txt_lines(self) -> List[str]:
+        """The `vcf.txt` lines parseVcf2Text would write: chr \\t pos \\t zygosity \\t 0 (VcfLookup.java:175), de-duplicated."""
+        return ["%s\t%d\t%d\t0" % (c, int(p), int(z)) for c, (ps, zs) in self.contigs().items() for p, z in zip(ps, zs)]
+
+
+def pack_bam(bam_path: str, snps: Optional[SnpTable] = None):
+    """hcnv_bam_pack -> (names, [Contig with numpy arrays], [max_block_len], n_records).  Arrays are copies."""
+    lib = L.lib()
+    h = C.c_void_p()
+    st = lib.hcnv_bam_pack(bam_path.encode(), snps._h if snps is not None else None, C.byref(h))
+    if st != 0:
+        raise L.HcnvError(st, "hcnv_bam_pack(%s): %s" % (bam_path, lib.hcnv_strerror(st).decode()))
+    try:
+        names, contigs, maxlens = [], [], []
+        for i in range(lib.hcnv_pack_n_contigs(h)):
+            name, ci, ml = C.c_char_p(), L.ContigInput(), C.c_int32()
+            lib.hcnv_pack_contig(h, i, C.byref(name), C.byref(ci), C.byref(ml))
+
+            def arr(ptr, n, dtype):
+                if not n:
+                    return None
+                nbytes = n * np.dtype(dtype).itemsize
+                return np.frombuffer((C.c_char * nbytes).from_address(ptr), dtype=dtype).copy()
+            names.append(name.value.decode())
+            maxlens.append(int(ml.value))
+            contigs.append(Contig(ci.length, arr(ci.blocks, ci.n_blocks, BLOCK_DTYPE), arr(ci.long_blocks, ci.n_long, LONG_BLOCK_DTYPE),
+                                  arr(ci.snp_pos1, ci.n_snp, np.int32), arr(ci.snp_zyg, ci.n_snp, np.int8),
+                                  arr(ci.obs, ci.n_obs, np.uint32)))
+        return names, contigs, maxlens, int(lib.hcnv_pack_n_records(h))
+    finally:
+        lib.hcnv_pack_free(h)

@@ -136,6 +136,29 @@ typedef struct {
 int hcnv_bin_contigs(hcnv_ctx* ctx, const hcnv_bin_params* params,
                      int32_t n_contigs, const hcnv_contig_input* contigs, hcnv_bins* out);
 
+/* ---- B1, host side: VCF side input and BAM/BGZF packer (no GPU needed) ---------------------------- */
+/* VcfLookup.parseVcf2Text (VcfLookup.java:135-196) with Utils.getZygosity / getVarType (Utils.java:15-99): skips '#'
+ * lines, prefixes "chr", keeps rows whose varType is "0", zygosity from column 10 (0 when the row has < 10 columns).
+ * Where the reference would System.exit (unknown genotype, malformed row) this returns HCNV_E_PARSE.  Duplicate
+ * positions: the last row wins.  Tables are per contig, ascending unique 1-based positions. */
+typedef struct hcnv_snp_table hcnv_snp_table;
+int     hcnv_vcf_load(const char* path, hcnv_snp_table** out);
+int32_t hcnv_snp_table_n_contigs(const hcnv_snp_table* t);
+int     hcnv_snp_table_get(const hcnv_snp_table* t, int32_t i, const char** name, const int32_t** pos1, const int8_t** zyg, int64_t* n);
+void    hcnv_snp_table_free(hcnv_snp_table* t);
+
+/* What SAMRecordWindowMapper.map reads from each SAMRecord (Mappers.java:174-212), with htsjdk 1.118's
+ * SAMRecord.getAlignmentBlocks rules (M/=/X make a block; I,S advance the read; D,N advance the reference; H,P do
+ * nothing), no flag filter, "chr" prefix, 'A' when the read has no base at that offset (SEQ=*, Mappers.java:248-256).
+ * Produces, per @SQ contig, the sorted hcnv_block stream, the long blocks and the observations against `snps`. */
+typedef struct hcnv_pack hcnv_pack;
+int     hcnv_bam_pack(const char* bam_path, const hcnv_snp_table* snps, hcnv_pack** out);
+int32_t hcnv_pack_n_contigs(const hcnv_pack* p);
+int64_t hcnv_pack_n_records(const hcnv_pack* p);
+/* fills `in` with pointers into the pack (valid until hcnv_pack_free); max_block_len for hcnv_bin_params */
+int     hcnv_pack_contig(const hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
+void    hcnv_pack_free(hcnv_pack* p);
+
 /* ---- between B1 and B2: what Hmm.init's text parsing does to a bins record ---------------------- */
 /* Double.toString -> Float.valueOf round trip of mse (Reducers.java:191-192 -> Hmm.java:364) and of total
  * (Reducers.java:202 -> Hmm.java:369); n values.  Bit-identical to printing and re-parsing the text. */

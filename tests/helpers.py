@@ -115,3 +115,41 @@ def random_bins(rng, M, snp_fraction=0.08, cnv=True, mean_depth=30):
     mse[has] = m
     start = np.arange(M, dtype=np.int32) * 100
     return dict(bin=start.copy(), start=start + (start == 0), end=start + 99, median=median, mse=mse, total=total, n=n)
+
+
+# ---------------------------------------------------------------------------------------------- tiny BAM writer
+def _bgzf_block(payload: bytes) -> bytes:
+    import struct
+    import zlib
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    cdata = co.compress(payload) + co.flush()
+    bsize = len(cdata) + 25                                   # total block size - 1
+    hdr = struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, bsize)
+    return hdr + cdata + struct.pack("<II", zlib.crc32(payload) & 0xFFFFFFFF, len(payload))
+
+
+def write_bam(path, refs, reads):
+    """refs: [(name, length)]; reads: [(ref_id, pos0, cigar, bases(bytes, b'' for SEQ=*), mapq, flag)].  Coordinate order is the
+    caller's business.  Writes a real BGZF file (BC extra field, EOF marker)."""
+    import struct
+    body = bytearray()
+    text = b"@HD\tVN:1.4\tSO:coordinate\n" + b"".join(b"@SQ\tSN:%s\tLN:%d\n" % (n.encode(), l) for n, l in refs)
+    body += b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for n, l in refs:
+        body += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+    ops = "MIDNSHP=X"
+    for i, (ref_id, pos0, cigar, bases, mapq, flag) in enumerate(reads):
+        name = b"r%d\0" % i
+        cig = [] if cigar == "*" else [(int(l), ops.index(o)) for l, o in Lit._CIGAR_RE.findall(cigar)]
+        l_seq = len(bases)
+        seq = bytearray((l_seq + 1) // 2)
+        for j, b in enumerate(bases):
+            code = BASE4[chr(b)]
+            seq[j >> 1] |= code << 4 if (j & 1) == 0 else code
+        rec = struct.pack("<iiBBHHHiiii", ref_id, pos0, len(name), mapq, 4680, len(cig), flag, l_seq, -1, -1, 0)
+        rec += name + b"".join(struct.pack("<I", (l << 4) | o) for l, o in cig) + bytes(seq) + bytes([30] * l_seq)
+        body += struct.pack("<i", len(rec)) + rec
+    with open(path, "wb") as f:
+        for i in range(0, len(body), 60000):
+            f.write(_bgzf_block(bytes(body[i:i + 60000])))
+        f.write(_bgzf_block(b""))                                # BGZF EOF marker

@@ -1,0 +1,111 @@
+"""CPU tests of the host side of B1: VCF -> SNP table and BAM/BGZF -> packed records, against the
+line-by-line restatement (oracle/literal.py) and the htsjdk-semantics reference packer in tests/helpers.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import hadoopcnv_b200 as H
+from hadoopcnv_b200 import _lib as L
+from hadoopcnv_b200 import hostio
+from oracle import literal as Lit
+from oracle import oracle as O
+from tests import helpers as Hp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_vcf_table_matches_parse_vcf_to_text(tmp_path):
+    lines = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1",
+             "1\t100\t.\tA\tG\t.\t.\t.\tGT\t0/1:3", "chr1\t200\t.\tAT\tG\t.\t.\t.\tGT\t1/1", "1\t300\t.\tA\t<DEL>\t.\t.\t.\tGT\t0|0",
+             "1\t400\t.\tN\tG\t.\t.\t.\tGT\t1|2", "1\t500\t.\tA\tG", "2\t50\t.\tC\tT\t.\t.\t.\tGT:DP\t2/2:9", "1\t100\t.\tA\tC\t.\t.\t.\tGT\t1/1",
+             "X\t7\t.\tg\tA\t.\t.\t.\tGT\t0/2", "1\t90\t.\tA\tA,C\t.\t.\t.\tGT\t2|1\r"]
+    p = tmp_path / "x.vcf"
+    p.write_text("\n".join(lines) + "\n")
+    t = hostio.SnpTable(str(p))
+    got = t.contigs()
+    # the literal restatement keeps duplicates in file order; BinReducer lets the last VCF record of a position win
+    want = {}
+    for ln in Lit.parse_vcf_to_text(lines):
+        c, pos, z, _ = ln.split("\t")
+        want.setdefault(c, {})[int(pos)] = int(z)
+    assert set(got) == set(want)
+    for c in want:
+        assert list(got[c][0]) == sorted(want[c]) and [int(z) for z in got[c][1]] == [want[c][q] for q in sorted(want[c])]
+    assert list(got["chr1"][0]) == [90, 100, 300, 400, 500] and list(got["chr1"][1]) == [-1, -2, 0, -1, 0]
+
+
+@pytest.mark.parametrize("bad", ["1\t100\t.\tA\tG\t.\t.\t.\tGT\t./.", "1\t100\t.\tA", "1\tabc\t.\tA\tG", ""])
+def test_vcf_rows_the_reference_exits_on(tmp_path, bad):
+    p = tmp_path / "bad.vcf"
+    p.write_text("#h\n" + bad + "\n1\t5\t.\tA\tG\n")
+    with pytest.raises(H.HcnvError) as e:
+        hostio.SnpTable(str(p))
+    assert e.value.status == L.HCNV_E_PARSE
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_bam_pack_matches_htsjdk_semantics(tmp_path, seed):
+    rng = np.random.default_rng(seed)
+    length = 40000
+    reads = Hp.random_reads(rng, 1500, length - 600, refname="7")
+    reads.append(("7", 30000, "5000M", b"", b"", 0))                       # a long SEQ=* block (baseline-BAM style)
+    reads.sort(key=lambda r: r[1])
+    snps = sorted(set(int(x) for x in rng.integers(1, length, 400)))
+    vcf = tmp_path / "s.vcf"
+    vcf.write_text("\n".join(Hp.vcf_lines_for("7", [(q, int(rng.choice([0, -1, -2]))) for q in snps])) + "\n")
+    bam = tmp_path / "s.bam"
+    recs = [(0, r[1] - 1, r[2], r[3], r[5], 0) for r in reads] + [(-1, -1, "*", b"ACGT", 0, 4)]
+    Hp.write_bam(str(bam), [("7", length), ("8", 1000)], recs)
+    table = hostio.SnpTable(str(vcf))
+    names, contigs, maxlens, nrec = hostio.pack_bam(str(bam), table)
+    assert names == ["chr7", "chr8"] and nrec == len(recs)
+    c = contigs[0]
+    want_blocks, want_longs, want_obs = Hp.pack_reads(reads, snps)
+    assert (np.diff(c.blocks["start0"]) >= 0).all()                          # emitted sorted by start0
+    assert sorted(map(tuple, c.blocks.tolist())) == sorted(map(tuple, want_blocks.tolist()))
+    assert sorted((int(b["start0"]), int(b["len"]), int(b["mapq"])) for b in c.long_blocks) == sorted(want_longs)
+    assert sorted(c.obs.tolist()) == sorted(want_obs.tolist())
+    assert maxlens[0] == int((want_blocks["len_mapq"] & 0xFFFFFF).max())
+    assert contigs[1].blocks is None and contigs[1].length == 1000
+    # and the packed records bin to the same thing as the text-level pipeline
+    zyg = dict(zip(*[x.tolist() for x in table.contigs()["chr7"]]))
+    want = Lit.binner(Lit.depth_caller([(r[0], r[1], r[2], r[3], r[4], r[5]) for r in reads]) + table.vcf_txt_lines())
+    depth, tally = O.depth_from_blocks(c.blocks, length, c.obs, len(snps))
+    for b in c.long_blocks:
+        depth[b["start0"] + 1: b["start0"] + 1 + b["len"]] += 1
+    got = O.bin_reduce(depth, length, 100, c.snp_pos1, c.snp_zyg, tally)
+    assert Hp.bins_to_lines("chr7", got) == want
+    assert zyg
+
+
+def test_unsorted_bam_is_sorted_by_the_packer(tmp_path):
+    reads = [(0, 500, "50M", b"A" * 50, 60, 0), (0, 100, "20M30N20M", b"C" * 40, 60, 0), (0, 300, "10M", b"G" * 10, 3, 0)]
+    bam = tmp_path / "u.bam"
+    Hp.write_bam(str(bam), [("chr1", 5000)], reads)
+    _, contigs, _, _ = hostio.pack_bam(str(bam))
+    assert contigs[0].blocks["start0"].tolist() == [100, 150, 300, 500]
+    assert contigs[0].obs is None and contigs[0].snp_pos1 is None
+
+
+def test_reference_baseline_bam_fixture():
+    """The reference's example/hg19.extra.bam (581 artificial whole-interval reads): only where the reference tree exists."""
+    bam = "/root/reference/example/hg19.extra.bam"
+    if not os.path.exists(bam):
+        pytest.skip("reference tree not present (GPU box)")
+    shape = json.load(open(os.path.join(ROOT, "hadoopcnv_b200", "data", "hg19_shape.json")))
+    names, contigs, _, nrec = hostio.pack_bam(bam)
+    # 241 of the 581 records carry refID -1 (the unplaced hg19 scaffolds): htsjdk names their reference "*", so the
+    # mapper files them under "chr*" (Mappers.java:176-180) -- a 25th pseudo contig after the 24 @SQ ones
+    assert nrec == 581 and names == [c["name"] for c in shape["contigs"]] + ["chr*"]
+    got = []
+    for i, c in enumerate(contigs):
+        ci = i if i < 24 else -1
+        if c.long_blocks is not None:
+            got += [(ci, int(b["start0"]), int(b["len"]), int(b["mapq"])) for b in c.long_blocks]
+        if c.blocks is not None:                                         # the few intervals <= HCNV_SHORT_MAX bp
+            got += [(ci, int(b["start0"]), int(b["len_mapq"]) & 0xFFFFFF, int(b["len_mapq"]) >> 24) for b in c.blocks]
+    assert sorted(got) == sorted(tuple(b) for b in shape["baseline_blocks"])
+    assert sum(b[2] for b in got) == 2911652393
+    assert contigs[24].length == max(b[1] + b[2] for b in shape["baseline_blocks"] if b[0] == -1)
