@@ -34,20 +34,28 @@ struct ContigDev {
 
 enum { ERR_RANGE = 0, ERR_UNSORTED = 1, ERR_INCONSISTENT = 2, ERR_INTERNAL = 3, ERR_CAPACITY = 4, ERR_N = 8 };
 
+// What a tile needs, precomputed by k_tile_index so that the tile kernel never chases dependent global loads.
+struct __align__(16) TileRec {                   // 48 bytes, TMA-prefetched by the tile kernel
+    int32_t  contig, k;                          // contig id; tile number within the contig
+    uint32_t lb, hi;                             // record range [lb, hi): look-back records + records that start in the tile
+    uint32_t slo, shi;                           // SNP sites of the tile
+    int32_t  prev_start, pad;                    // start0 of record lb - 1 (INT_MIN if none): sortedness across tiles
+    hcnv_block head, tail;                       // records lb and hi - 1 (a ragged end cannot go through a 16-byte bulk copy)
+};
+
 struct BinK {
     const ContigDev* contigs;
     int   n_contigs;
     int   W, TB, n_tiles, maxlen;
     uint32_t mapq_pass[8];
-    // per-tile index, filled by k_tile_index
-    int32_t*  tile_contig;
-    uint32_t *rec_lb, *rec_lo, *rec_hi, *snp_lo, *snp_hi;
+    TileRec*  tile_rec;              // per-tile index, filled by k_tile_index
     uint32_t* tally;
+    int32_t*  snp_depth;             // coverage at every SNP site (tile kernel -> k_snp_mse)
+    long long n_snp_total;
     // outputs
     int32_t *o_bin, *o_start, *o_end; float* o_median; double* o_mse; double* o_total; int32_t* o_n;
     long long capacity;
     unsigned long long* status;      // look-back words, one per tile
-    unsigned int*       ticket;
     int32_t*            err;
     long long*          contig_offset;   // n_contigs + 1
 };
@@ -86,15 +94,20 @@ __global__ void k_tile_index(BinK p) {
     // a block with 0-based start s covers 1-based positions s+1 .. s+len
     // own blocks:      T0 <= s+1 < T1   <=>  T0-1 <= s < T1-1
     // look-back blocks: s+1 >= T0 - maxlen
-    long long k_lo = T0 - 1, k_hi = T1 - 1, k_lb = T0 - 1 - p.maxlen;
+    long long k_hi = T1 - 1, k_lb = T0 - 1 - p.maxlen;
     auto clampk = [](long long v) { return (int32_t)(v < -2147483647LL ? -2147483647LL : (v > 2147483647LL ? 2147483647LL : v)); };
-    uint32_t r_lo = (k == 0) ? 0u : lower_bound_blocks(c.blocks, c.n_blocks, clampk(k_lo));
-    uint32_t r_hi = (k == c.n_tiles - 1) ? (uint32_t)c.n_blocks : lower_bound_blocks(c.blocks, c.n_blocks, clampk(k_hi));
-    uint32_t r_lb = (k == 0) ? 0u : lower_bound_blocks(c.blocks, c.n_blocks, clampk(k_lb));
-    p.tile_contig[t] = lo;
-    p.rec_lb[t] = r_lb; p.rec_lo[t] = r_lo; p.rec_hi[t] = r_hi;
-    p.snp_lo[t] = (k == 0) ? 0u : lower_bound_i32(c.snp_pos, c.n_snp, clampk(T0));
-    p.snp_hi[t] = (k == c.n_tiles - 1) ? (uint32_t)c.n_snp : lower_bound_i32(c.snp_pos, c.n_snp, clampk(T1));
+    TileRec r;
+    r.contig = lo; r.k = k; r.pad = 0;
+    r.hi = (k == c.n_tiles - 1) ? (uint32_t)c.n_blocks : lower_bound_blocks(c.blocks, c.n_blocks, clampk(k_hi));
+    r.lb = (k == 0) ? 0u : lower_bound_blocks(c.blocks, c.n_blocks, clampk(k_lb));
+    r.slo = (k == 0) ? 0u : lower_bound_i32(c.snp_pos, c.n_snp, clampk(T0));
+    r.shi = (k == c.n_tiles - 1) ? (uint32_t)c.n_snp : lower_bound_i32(c.snp_pos, c.n_snp, clampk(T1));
+    if (r.shi < r.slo) r.shi = r.slo;                        // unsorted SNP table: k_snp_mse reports it
+    r.prev_start = (r.lb > 0) ? __ldg(&c.blocks[r.lb - 1].start0) : (int)0x80000000;
+    hcnv_block z; z.start0 = 0; z.len_mapq = 0;
+    r.head = (r.hi > r.lb) ? c.blocks[r.lb] : z;
+    r.tail = (r.hi > r.lb) ? c.blocks[r.hi - 1] : z;
+    p.tile_rec[t] = r;
 }
 
 // Allele tallies at SNP sites: tally[snp][base4] += 1 (AlleleDepthWindowReducer's per-allele map, Reducers.java:381-391)
@@ -110,97 +123,69 @@ __global__ void k_tally(const uint32_t* __restrict__ obs, long long n_obs, long 
     }
 }
 
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t a, uint32_t b) {   // PTX shl clamps shift amounts >= 32 to 32 -> 0
-    uint32_t d;
-    asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-
-// position of the k-th (0-based) set bit of a 64-bit mask held as two words
-__device__ __forceinline__ int kth_set_bit(uint32_t m0, uint32_t m1, int k) {
-    int c0 = __popc(m0);
-    uint32_t m = m0; int base = 0;
-    if (k >= c0) { k -= c0; m = m1; base = 32; }
-    for (int i = 0; i < k; ++i) m &= m - 1;       // clear k lowest set bits
-    return base + __ffs(m) - 1;
-}
-
-struct WalkOut {
-    int       n;          // positions with depth > 0
-    int       first, last;   // offsets within the bin of the first / last such position (first = INT_MAX if none)
-    long long sum;        // total depth
-    uint32_t  m0, m1;     // distinct-depth bitmap, bit j <-> depth base + j
-    int       base;
-    uint32_t  oob;        // >= 64 if some depth fell outside [base, base + 64)
-    int       dmin, dmax;
-};
-
-// One thread walks the W difference-array entries of its bin: running depth, written back in place.
-template <int VEC>
-__device__ __forceinline__ void walk_bin(int32_t* dp, int W, int carry, int bin_carry, WalkOut& o) {
-    int d = carry;
-    int n = 0, first = 0x7fffffff, last = -1;
-    int rel_sum = 0;
-    uint32_t m0 = 0, m1 = 0, oob = 0;
-    const int base = max(bin_carry - 31, 1);          // window anchored at the depth carried into the BIN (shared by its threads)
-    auto step = [&](int& v, int i) {
-        d += v;
-        v = d;
-        rel_sum += d - carry;
-        bool present = d > 0;
-        uint32_t t = (uint32_t)(d - base);
-        m0 |= shl_clamp(1u, t);
-        m1 |= shl_clamp(1u, t - 32u);
-        if (present) { ++n; last = i; first = min(first, i); oob |= t; }
-    };
-    if (VEC == 4) {
-        int4* q = reinterpret_cast<int4*>(dp);
-        for (int i = 0; i < W / 4; ++i) {
-            int4 v = q[i];
-            step(v.x, 4 * i); step(v.y, 4 * i + 1); step(v.z, 4 * i + 2); step(v.w, 4 * i + 3);
-            q[i] = v;
-        }
-    } else if (VEC == 2) {
-        int2* q = reinterpret_cast<int2*>(dp);
-        for (int i = 0; i < W / 2; ++i) {
-            int2 v = q[i];
-            step(v.x, 2 * i); step(v.y, 2 * i + 1);
-            q[i] = v;
-        }
-    } else {
-        for (int i = 0; i < W; ++i) { int v = dp[i]; step(v, i); dp[i] = v; }
-    }
-    // depth 0 positions shifted 1 << (0 - base) only when base <= 0, which never happens (base >= 1): absent positions leave the bitmap alone
-    o.n = n; o.first = first; o.last = last; o.sum = (long long)carry * W + rel_sum;
-    o.m0 = m0; o.m1 = m1; o.base = base; o.oob = oob;
-}
-
-// Slow path for a bin whose depths span more than the 64-value window: distinct count and the
-// (size/2 - 1)-th smallest distinct positive depth by sweeping 64-value windows over [dmin, dmax].
-__device__ __noinline__ void distinct_wide(const int32_t* dp, int W, int& n_distinct_pos, int want_k, int& kth_value) {
-    int dmin = 0x7fffffff, dmax = 0;
-    for (int i = 0; i < W; ++i) { int d = dp[i]; if (d > 0) { dmin = min(dmin, d); dmax = max(dmax, d); } }
-    int count = 0; kth_value = 0;
-    bool found = false;
-    for (long long wb = dmin; wb <= dmax; wb += 64) {
-        unsigned long long m = 0;
-        for (int i = 0; i < W; ++i) {
-            long long t = (long long)dp[i] - wb;
-            if (dp[i] > 0 && t >= 0 && t < 64) m |= 1ull << t;
-        }
-        int c = __popcll(m);
-        if (!found && want_k >= 0 && want_k < count + c) {
-            int k = want_k - count;
-            for (int i = 0; i < k; ++i) m &= m - 1;
-            kth_value = (int)(wb + __ffsll((long long)m) - 1);
-            found = true;
-        }
-        count += c;
-    }
-    n_distinct_pos = count;
-}
-
 #include "bin_tile_kernel.cuh"
+
+// BinReducer's BAF statistics (Reducers.java:76-82,102-129,160-190), one thread per SNP site; the first site of a
+// bin walks the bin's sites in ascending position (the f64 sums are order dependent), then finds the bin's output row.
+__global__ void k_snp_mse(BinK p) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n_snp_total) return;
+    int lo = 0, hi = p.n_contigs - 1;
+    while (lo < hi) {                        // last contig with snp_base <= g (contigs without sites share a base: take the last)
+        int mid = (lo + hi + 1) >> 1;
+        if (p.contigs[mid].snp_base <= g) lo = mid; else hi = mid - 1;
+    }
+    while (lo > 0 && p.contigs[lo].n_snp == 0) --lo;
+    const ContigDev& c = p.contigs[lo];
+    const long long s = g - c.snp_base;
+    if (s < 0 || s >= c.n_snp) return;
+    const int W = p.W;
+    const int pos = __ldg(&c.snp_pos[s]);
+    if (pos < 0 || pos > c.length) { atomicOr(&p.err[ERR_RANGE], 1); return; }
+    const int prev = s > 0 ? __ldg(&c.snp_pos[s - 1]) : -1;
+    if (s > 0 && prev >= pos) { atomicOr(&p.err[ERR_UNSORTED], 1); return; }
+    const int bin = pos / W;
+    if (s > 0 && prev / W == bin) return;                     // not the first site of its bin
+    double mse[6] = {0, 0, 0, 0, 0, 0};
+    int nbaf = 0;
+    for (long long q = s; q < c.n_snp; ++q) {
+        const int pq = __ldg(&c.snp_pos[q]);
+        if (pq / W != bin || pq > c.length) break;
+        if (q > s && __ldg(&c.snp_pos[q - 1]) >= pq) break;   // reported by that site's own thread
+        const uint4* tr = reinterpret_cast<const uint4*>(p.tally + ((size_t)(c.snp_base + q)) * 16);
+        uint32_t tot = 0, mx = 0;
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 v = __ldg(tr + j);
+            tot += v.x + v.y + v.z + v.w;
+            mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w));
+        }
+        const int d = p.snp_depth[c.snp_base + q];
+        if (tot != (uint32_t)d) atomicOr(&p.err[ERR_INCONSISTENT], 1);
+        const int zyg = (int)c.snp_zyg[q];
+        if (d > 0 && zyg <= 0) {
+            float ptd = (float)d, mxd = (float)mx;
+            float baf = __fdiv_rn(__fsub_rn(ptd, mxd), ptd);             // Reducers.java:126
+            float baf2 = __fmul_rn(baf, baf);                             // :163 (an f32 product, widened)
+            double bb = (double)baf, b2 = (double)baf2;
+            double a = (0.5 - bb) * (0.5 - bb), qq = (0.25 - bb) * (0.25 - bb);
+            mse[0] += fmin(b2, fmin(a, qq));                              // :164
+            mse[1] += b2;
+            if (zyg == -1) { mse[2] += b2; mse[3] += a; mse[4] += (0.33 - bb) * (0.33 - bb); mse[5] += fmin(qq, a); }
+            else { mse[2] += b2; mse[3] += b2; mse[4] += b2; mse[5] += b2; }
+            ++nbaf;
+        }
+    }
+    if (nbaf == 0) return;                                     // the dummy (baf 0, het 0) record: all six stay 0 (:135-138)
+    if (nbaf > 1) { const double dn = (double)nbaf; for (int j = 0; j < 6; ++j) mse[j] = mse[j] / dn; }   // :186-190
+    // the bin's row: bins of a contig are ascending in o_bin between the contig's offsets
+    const long long r0 = p.contig_offset[lo], r1 = p.contig_offset[lo + 1];
+    if (r1 > p.capacity) return;                               // ERR_CAPACITY was raised by the tile kernel
+    const long long r = r0 + lower_bound_i32(p.o_bin + r0, r1 - r0, bin * W);
+    if (r >= r1 || p.o_bin[r] != bin * W) { atomicOr(&p.err[ERR_INTERNAL], 2); return; }
+    double2* m = reinterpret_cast<double2*>(p.o_mse + r * 6);
+    m[0] = make_double2(mse[0], mse[1]); m[1] = make_double2(mse[2], mse[3]); m[2] = make_double2(mse[4], mse[5]);
+}
 
 }  // namespace
 
@@ -209,7 +194,7 @@ __device__ __noinline__ void distinct_wide(const int32_t* dp, int W, int& n_dist
 // ---------------------------------------------------------------------------------------------------
 namespace {
 enum { B_CONTIGS = 0, B_TILEIDX, B_TALLY, B_STATUS, B_MISC, B_IN_BLOCKS, B_IN_LONG, B_IN_SNPPOS, B_IN_SNPZYG, B_IN_OBS,
-       B_OUT_I32, B_OUT_F32, B_OUT_F64 };
+       B_OUT_I32, B_OUT_F32, B_OUT_F64, B_SNPDEPTH = 24 };
 
 template <class T>
 int stage_in(hcnv_ctx* ctx, int kind, const T* src, long long n, T* dst) {
@@ -237,15 +222,13 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     if (!out->bin || !out->start || !out->end || !out->median || !out->mse || !out->total || !out->n || !out->contig_offset)
         return hcnv_fail(ctx, HCNV_E_INVALID, "null output array");
 
-    // tile geometry: TB bins (= threads) per CTA; shared memory = difference array + one staged chunk of records
-    // HS = 2 threads share a bin when the bin width is even (more warps per SM for the per-position walk)
-    const int HS = ((P.flags & 1) && W % 2 == 0 && W >= 16) ? 2 : 1;   // measured slower on B200 at W = 100; opt-in (flags bit 0)
-    int TB = P.tile_bins > 0 ? P.tile_bins : (HS == 2 ? 64 : 128);
+    // tile geometry: TB bins (= threads) per CTA; shared memory = difference array + carries + two staged chunks of records
+    int TB = P.tile_bins > 0 ? P.tile_bins : 128;
     TB = (TB + 31) / 32 * 32;
-    if (TB * HS > 256) TB = 256 / HS;
-    auto smem_need = [&](int tb) { return (((size_t)tb * W + 4) * 4 + 15) / 16 * 16 + (size_t)(RCAP + 4) * 8; };
-    while (TB > 32 && smem_need(TB) > ctx->smem_optin) TB -= 32;
-    if (smem_need(TB) > ctx->smem_optin) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1600)");
+    if (TB > BIN_MAX_THREADS) TB = BIN_MAX_THREADS;
+    auto smem_need = [&](int tb) { return (((size_t)tb * W + 4 + tb) * 4 + 15) / 16 * 16 + (size_t)NRBUF * (RCAP + 4) * 8; };
+    while (TB > 32 && smem_need(TB) > ctx->smem_optin - 2048) TB -= 32;
+    if (smem_need(TB) > ctx->smem_optin - 2048) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1600)");
     const size_t smem_bytes = smem_need(TB);
 
     // pointer kinds
@@ -317,7 +300,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     BinK k{};
     HCNV_CUDA(ctx, ctx->buf[B_CONTIGS].reserve(sizeof(ContigDev) * (size_t)n_contigs));
     HCNV_CUDA(ctx, cudaMemcpyAsync(ctx->buf[B_CONTIGS].p, hc.data(), sizeof(ContigDev) * (size_t)n_contigs, cudaMemcpyHostToDevice, ctx->stream));
-    HCNV_CUDA(ctx, ctx->buf[B_TILEIDX].reserve(4 * 6 * (size_t)n_tiles));
+    HCNV_CUDA(ctx, ctx->buf[B_TILEIDX].reserve(sizeof(TileRec) * (size_t)n_tiles));
+    HCNV_CUDA(ctx, ctx->buf[B_SNPDEPTH].reserve(4 * (size_t)(tot_snp + 1)));
     HCNV_CUDA(ctx, ctx->buf[B_TALLY].reserve(64 * (size_t)(tot_snp + 1)));
     HCNV_CUDA(ctx, ctx->buf[B_STATUS].reserve(8 * (size_t)n_tiles));
     HCNV_CUDA(ctx, ctx->buf[B_MISC].reserve(4096 + 8 * (size_t)(n_contigs + 1)));
@@ -327,14 +311,13 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         double mapprob = 1. - std::pow(10.0, -q * .1);            // Mappers.java:193
         if (mapprob >= P.mapping_quality_threshold) k.mapq_pass[q >> 5] |= 1u << (q & 31);   // :200
     }
-    int32_t* ti = ctx->buf[B_TILEIDX].as<int32_t>();
-    k.tile_contig = ti;
-    k.rec_lb = (uint32_t*)(ti + (size_t)n_tiles); k.rec_lo = (uint32_t*)(ti + 2 * (size_t)n_tiles); k.rec_hi = (uint32_t*)(ti + 3 * (size_t)n_tiles);
-    k.snp_lo = (uint32_t*)(ti + 4 * (size_t)n_tiles); k.snp_hi = (uint32_t*)(ti + 5 * (size_t)n_tiles);
+    k.tile_rec = ctx->buf[B_TILEIDX].as<TileRec>();
+    k.snp_depth = ctx->buf[B_SNPDEPTH].as<int32_t>();
+    k.n_snp_total = tot_snp;
     k.tally = ctx->buf[B_TALLY].as<uint32_t>();
     k.status = ctx->buf[B_STATUS].as<unsigned long long>();
     char* misc = ctx->buf[B_MISC].as<char>();
-    k.err = (int32_t*)misc; k.ticket = (unsigned int*)(misc + 64); k.contig_offset = (long long*)(misc + 128);
+    k.err = (int32_t*)misc; k.contig_offset = (long long*)(misc + 128);
     k.capacity = out->capacity;
 
     // outputs: directly into the caller's device arrays, or into scratch followed by a D2H copy
@@ -371,29 +354,31 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     }
     KT_END(ctx, HCNV_K_TALLY);
     KT_BEGIN(ctx, HCNV_K_BIN_TILES);
+    bool filter = false;                           // the reference's threshold is the constant 0: every MAPQ passes
+    for (int q = 0; q < 8; ++q) if (k.mapq_pass[q] != 0xFFFFFFFFu) filter = true;
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB * HS, smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem_bytes);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
-        const int grid = std::min(n_tiles, ctx->sm_count * per_sm);       // persistent CTAs, tiles by ticket
-        kern<<<grid, TB * HS, smem_bytes, ctx->stream>>>(k);
+        const int grid = std::min(n_tiles, ctx->sm_count * per_sm);       // persistent, co-resident CTAs; tiles round-robin
+        kern<<<grid, TB, smem_bytes, ctx->stream>>>(k);
         return cudaGetLastError();
     };
-    const int Wt = W / HS;                         // positions per thread
-    if (HS == 2) {
-        if (Wt % 4 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<4, 2>));
-        else if (Wt % 2 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<2, 2>));
-        else HCNV_CUDA(ctx, launch(k_bin_tiles<1, 2>));
-    } else {
-        if (Wt % 4 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<4, 1>));
-        else if (Wt % 2 == 0) HCNV_CUDA(ctx, launch(k_bin_tiles<2, 1>));
-        else HCNV_CUDA(ctx, launch(k_bin_tiles<1, 1>));
-    }
+    if (W % 4 == 0)      HCNV_CUDA(ctx, filter ? launch(k_bin_tiles<4, true>) : launch(k_bin_tiles<4, false>));
+    else if (W % 2 == 0) HCNV_CUDA(ctx, filter ? launch(k_bin_tiles<2, true>) : launch(k_bin_tiles<2, false>));
+    else                 HCNV_CUDA(ctx, filter ? launch(k_bin_tiles<1, true>) : launch(k_bin_tiles<1, false>));
     KT_END(ctx, HCNV_K_BIN_TILES);
     ctx->launches++;
+    if (tot_snp) {
+        KT_BEGIN(ctx, HCNV_K_SNP_MSE);
+        k_snp_mse<<<(unsigned)((tot_snp + 255) / 256), 256, 0, ctx->stream>>>(k);
+        HCNV_CUDA(ctx, cudaGetLastError());
+        KT_END(ctx, HCNV_K_SNP_MSE);
+        ctx->launches++;
+    }
 
     // results: error flags + contig offsets always come back to the host
     HCNV_CUDA(ctx, ctx->pin[0].reserve(128 + 8 * (size_t)(n_contigs + 1)));
@@ -401,7 +386,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     HCNV_CUDA(ctx, cudaMemcpyAsync(hm, misc, 128 + 8 * (size_t)(n_contigs + 1), cudaMemcpyDeviceToHost, ctx->stream));
     HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const int32_t* herr = (const int32_t*)hm;
-    if (herr[ERR_INTERNAL]) return hcnv_fail(ctx, HCNV_E_INTERNAL, "look-back spin limit reached");
+    if (herr[ERR_INTERNAL]) return hcnv_fail(ctx, HCNV_E_INTERNAL, herr[ERR_INTERNAL] & 2 ? "a bin with SNP sites has no output row" : "look-back spin limit reached");
     if (herr[ERR_UNSORTED]) return hcnv_fail(ctx, HCNV_E_UNSORTED, "blocks or SNP table not sorted by position");
     if (herr[ERR_RANGE]) return hcnv_fail(ctx, HCNV_E_RANGE, "record outside the contig, longer than max_block_len, or SNP index out of range");
     if (herr[ERR_INCONSISTENT]) return hcnv_fail(ctx, HCNV_E_INCONSISTENT, "allele observations at a SNP site do not add up to its coverage");

@@ -1,25 +1,41 @@
 // bin_tile_kernel.cuh -- the persistent tile kernel of B1 (included by bin_kernels.cu after its helpers).
 //
-// One CTA = TB threads = TB bins per tile; CTAs are persistent and take tiles from an atomic ticket, so tile ids
-// are claimed in order (the decoupled look-back below relies on that).  Per tile:
-//   1. TMA bulk copy (cp.async.bulk + mbarrier) streams the tile's slice of the sorted block records into shared
-//      memory in chunks of RCAP records while the CTA clears its difference array;
-//   2. +1/-1 shared-memory atomics per block (clipped to the tile); sortedness and range checks against the
-//      neighbour record, both read from shared memory;
-//   3. per-bin prefix, one-thread-per-bin walk, SNP sites, BinReducer record (as before);
-//   4. the tile publishes its count of non-empty bins; its global output offset is resolved AFTER the next tile's
-//      record phase (deferred look-back), so the wait for predecessors overlaps useful work.
+// One CTA = TB threads = TB bins per tile; CTAs are persistent and take tiles round-robin (tile = blockIdx.x +
+// i * gridDim.x), so everything a tile needs is known one tile ahead and nothing on the critical path waits for a
+// dependent global load:
+//   0. the 48-byte tile record written by k_tile_index (record range, SNP range, the ragged head / tail records and
+//      the predecessor's start) is TMA-prefetched two tiles ahead; contig descriptors sit in shared memory;
+//   1. the tile's slice of the sorted block stream is staged by TMA bulk copies (cp.async.bulk + mbarrier) in
+//      chunks of RCAP records through two buffers: chunk q + 1 is in flight while chunk q is processed, and chunk 0
+//      of the NEXT tile is issued before this tile's walk;
+//   2. +1 / -1 shared-memory atomics per block (clamped to the tile), error flags accumulated in registers;
+//   3. ONE THREAD PER BIN walks its W entries ONCE, in relative terms (depth - depth carried into the bin): running
+//      sum written back in place, sum, min, max and a 32-bit modular bitmap of the depths seen (bit d & 31).  All of
+//      these are translation-covariant, so the walk needs no prior per-bin prefix pass: the bin totals fall out of
+//      it, a block scan turns them into carries, and the carries are applied afterwards (rotate the bitmap);
+//   4. a bin that is covered everywhere with a depth range < 32 (almost all of them) is finished from those five
+//      numbers; anything else (gap edges, contig ends, SNP sites at uncovered positions, huge ranges) re-walks its W
+//      positions in a careful slow path;
+//   5. depth at the tile's SNP sites goes to a side array for k_snp_mse (the f64 BAF statistics are not in here);
+//   6. the tile publishes its count of non-empty bins; its global output offset is resolved AFTER the next tile's
+//      record phase (deferred decoupled look-back), so the wait for predecessors overlaps useful work.
 #pragma once
 
-#define RCAP 2048                                 // records per staged chunk (16 KB)
+#define RCAP 1024                                 // records per staged chunk (8 KB)
+#define NRBUF 2                                   // chunk buffers in flight
+#define CTC 32                                    // contig descriptors cached in shared memory
+#define BIN_MAX_THREADS 512
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -38,305 +54,355 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-struct TileOut {
-    int    n, start, end, binpos;
-    float  median;
-    double mse[6];
-    double total;
-};
-
-struct TileMeta {                                 // what a tile needs from its contig + the tile index, staged in smem
+struct ContigLite {                               // what a tile needs from its contig
     const hcnv_block*      blocks;
     const hcnv_long_block* longs;
     const int32_t*         snp_pos;
-    const int8_t*          snp_zyg;
     long long n_long, snp_base;
-    int contig, k, length, n_bins_max;
-    uint32_t lb, lo, hi, slo, shi;
+    int length, n_bins_max;
 };
 
-#define SCAP 256                                  // SNP sites of a tile staged in shared memory (more: global path)
+__device__ __forceinline__ uint32_t bit_of(int d) { return __funnelshift_l(0u, 1u, (uint32_t)d); }   // 1u << (d & 31), one SHF
 
-template <int VEC, int HS>
-__global__ void __launch_bounds__(256) k_bin_tiles(BinK p) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ TileMeta s_meta[2];
-    __shared__ int s_spos[SCAP];                  // staged SNP sites: position, zygosity, (total, max) of the allele tally
-    __shared__ signed char s_szyg[SCAP];
-    __shared__ uint2 s_stm[SCAP];
-    __shared__ int s_bfirst[256], s_bcnt[256];    // per bin: first staged SNP and how many
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_tile, s_prev;
-    __shared__ int s_warp[8];
-    __shared__ long long s_prefix;
-    const int tid = threadIdx.x, nthr = blockDim.x;   // == TB * HS: a multiple of 32, at most 256
-    const int lane = tid & 31, wid = tid >> 5;
-    const int W = p.W, TB = p.TB;
-    const int TP = TB * W;
-    int32_t* diff = reinterpret_cast<int32_t*>(smraw);                 // TP + 4 entries; entry TP sinks ends at the tile edge
-    hcnv_block* rec = reinterpret_cast<hcnv_block*>(smraw + (((size_t)(TP + 4) * 4 + 15) & ~(size_t)15));   // RCAP + 4 slots
+// The walk.  dp[0..W) holds the bin's difference entries and receives the running sum RELATIVE to the bin start.
+template <int VEC, bool WIDE>
+__device__ __forceinline__ void walk_rel(int32_t* dp, int W, int& rel_end, long long& sum, int& mn, int& mx, uint32_t& mask) {
+    int d = 0, lo = 0x7fffffff, hi = (int)0x80000000, s32 = 0;
+    long long s64 = 0;
+    uint32_t m = 0;
+    if (VEC == 4) {
+        int4* q = reinterpret_cast<int4*>(dp);
+        #pragma unroll 5
+        for (int i = 0; i < W / 4; ++i) {
+            const int4 v = q[i];
+            const int xy = v.x + v.y, zw = v.z + v.w;
+            const int d1 = d + v.x, d2 = d + xy, d3 = d2 + v.z, d4 = d2 + zw;
+            q[i] = make_int4(d1, d2, d3, d4);
+            lo = min(min(lo, d1), min(min(d2, d3), d4));
+            hi = max(max(hi, d1), max(max(d2, d3), d4));
+            m |= (bit_of(d1) | bit_of(d2)) | (bit_of(d3) | bit_of(d4));
+            const int s4 = (d1 + d2) + (d3 + d4);
+            if (WIDE) s64 += s4; else s32 += s4;
+            d = d4;
+        }
+    } else if (VEC == 2) {
+        int2* q = reinterpret_cast<int2*>(dp);
+        #pragma unroll 5
+        for (int i = 0; i < W / 2; ++i) {
+            const int2 v = q[i];
+            const int d1 = d + v.x, d2 = d1 + v.y;
+            q[i] = make_int2(d1, d2);
+            lo = min(lo, min(d1, d2));
+            hi = max(hi, max(d1, d2));
+            m |= bit_of(d1) | bit_of(d2);
+            if (WIDE) s64 += (long long)d1 + d2; else s32 += d1 + d2;
+            d = d2;
+        }
+    } else {
+        #pragma unroll 4
+        for (int i = 0; i < W; ++i) {
+            d += dp[i];
+            dp[i] = d;
+            lo = min(lo, d); hi = max(hi, d);
+            m |= bit_of(d);
+            if (WIDE) s64 += d; else s32 += d;
+        }
+    }
+    rel_end = d; sum = WIDE ? s64 : (long long)s32; mn = lo; mx = hi; mask = m;
+}
 
-    if (tid == 0) mbar_init(&s_bar, 1);
-    if (tid < 8) s_warp[tid] = 0;
-    __syncthreads();
-    uint32_t phase = 0;
-
-    bool pending = false;
-    TileOut po; po.n = 0; po.start = po.end = po.binpos = 0; po.median = 0.f; po.total = 0;
-    #pragma unroll
-    for (int j = 0; j < 6; ++j) po.mse[j] = 0;
-    int p_t = -1, p_count = 0, p_rank = 0, p_contig = 0, p_first_of_contig = 0;
-
-    // tid 0: fetch the metadata of tile `tt` into s_meta[slot] and start its first chunk (TMA bulk copy + ragged
-    // head record + predecessor's start).  Done one tile ahead, so nobody waits on these dependent global loads.
-    auto issue_first_chunk = [&](int tt, int slot) {
-        const int ci = p.tile_contig[tt];
-        const ContigDev& cc = p.contigs[ci];
-        const uint32_t lb_ = p.rec_lb[tt], hi_ = p.rec_hi[tt];
-        const hcnv_block* blk = cc.blocks;
-        TileMeta& mm = s_meta[slot];
-        mm.blocks = blk; mm.longs = cc.longs; mm.snp_pos = cc.snp_pos; mm.snp_zyg = cc.snp_zyg;
-        mm.n_long = cc.n_long; mm.snp_base = cc.snp_base;
-        mm.contig = ci; mm.k = tt - cc.tile_base; mm.length = cc.length; mm.n_bins_max = cc.n_bins_max;
-        mm.lb = lb_; mm.lo = p.rec_lo[tt]; mm.hi = hi_; mm.slo = p.snp_lo[tt]; mm.shi = p.snp_hi[tt];
-        const uint32_t a0_ = (uint32_t)((reinterpret_cast<unsigned long long>(blk) >> 3) & 1ull);
-        uint32_t lbA_ = lb_ + ((a0_ + lb_) & 1u);
-        if (lbA_ > hi_) lbA_ = hi_;
-        const uint32_t hiA_ = lbA_ + ((hi_ - lbA_) & ~1u);
-        const uint32_t cnt_ = min((uint32_t)RCAP, hiA_ - lbA_);
-        if (cnt_) { fence_proxy_async(); mbar_expect_tx(&s_bar, cnt_ * 8u); tma_load_1d(rec + 2, blk + lbA_, cnt_ * 8u, &s_bar); }
-        s_prev = (lb_ > 0) ? __ldg(&blk[lb_ - 1].start0) : (int)0x80000000;
-        if (lbA_ > lb_) rec[1] = blk[lb_];
-    };
-    if (tid == 0) { s_tile = (int)atomicAdd(p.ticket, 1u); if (s_tile < p.n_tiles) issue_first_chunk(s_tile, 0); }
-    int cur = 0;
-
-    for (;; cur ^= 1) {
-        __syncthreads();
-        const int t = s_tile;
-        const bool have = t < p.n_tiles;
-        TileOut co; co.n = 0; co.start = co.end = co.binpos = 0; co.median = 0.f; co.total = 0;
-        #pragma unroll
-        for (int j = 0; j < 6; ++j) co.mse[j] = 0;
-        int c_count = 0, c_rank = 0, c_contig = 0, c_first = 0;
-
-        if (have) {
-            const TileMeta& c = s_meta[cur];                        // staged by tid 0 one tile ahead
-            c_contig = c.contig;
-            const int k = c.k;
-            c_first = (k == 0);
-            const int T0 = k * TP;                                  // 1-based position of diff[0] (fits int: length < 2^31)
-            const long long T1l = (long long)T0 + TP;
-            const int T1 = (int)min(T1l, (long long)0x7fffffff);
-            const uint32_t lb = c.lb, lo = c.lo, hi = c.hi;
-            if (hi < lo || lo < lb) atomicOr(&p.err[ERR_UNSORTED], 1);
-            const hcnv_block* __restrict__ blocks = c.blocks;
-            // 16-byte aligned sub-range [lbA, hiA) goes through TMA; a ragged head / tail record is loaded directly
-            const uint32_t a0 = (uint32_t)((reinterpret_cast<unsigned long long>(blocks) >> 3) & 1ull);
-            uint32_t lbA = lb + ((a0 + lb) & 1u);
-            if (lbA > hi) lbA = hi;
-            const uint32_t hiA = lbA + ((hi - lbA) & ~1u);
-            const bool head = lbA > lb, tail = hiA < hi;
-            uint32_t cb = lbA;
-            uint32_t cnt = min((uint32_t)RCAP, hiA - cb);
-            // (the first chunk of this tile was issued by tid 0 before the previous tile's walk, or at kernel start)
-            // ---- clear the difference array
-            for (int i = tid * 4; i < TP + 4; i += nthr * 4) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
-            for (int i = tid; i < TB; i += nthr) { s_bfirst[i] = 0x7fffffff; s_bcnt[i] = 0; }
-            __syncthreads();
-            // ---- stage the tile's SNP sites (VcfLookup side input) and reduce their allele tallies to (total, max)
-            const uint32_t slo = c.slo, shi = c.shi;
-            const bool snp_staged = shi - slo <= (uint32_t)SCAP;
-            if (snp_staged) {
-                for (uint32_t i = tid; i < shi - slo; i += nthr) {
-                    const uint32_t s = slo + i;
-                    const int pos = __ldg(&c.snp_pos[s]);
-                    if (s > 0 && __ldg(&c.snp_pos[s - 1]) >= pos) atomicOr(&p.err[ERR_UNSORTED], 1);
-                    const uint4* tr = reinterpret_cast<const uint4*>(p.tally + ((size_t)(c.snp_base + s)) * 16);
-                    uint32_t tot = 0, mx = 0;
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 v = __ldg(tr + j);
-                        tot += v.x + v.y + v.z + v.w;
-                        mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w));
-                    }
-                    s_spos[i] = pos; s_szyg[i] = c.snp_zyg[s]; s_stm[i] = make_uint2(tot, mx);
-                    if (pos < 0 || pos > c.length || pos < T0 || (long long)pos >= T1l) atomicOr(&p.err[ERR_RANGE], 1);
-                    else { const int bb = (pos - T0) / W; atomicMin(&s_bfirst[bb], (int)i); atomicAdd(&s_bcnt[bb], 1); }
+// Slow path for one bin: dp[] holds relative running sums (after walk_rel), carry the depth before the bin.
+// Handles uncovered positions, SNP sites at uncovered positions (VCF records alone make a position count,
+// Reducers.java:62-82,102-138) and any depth range.  Returns n (0 = empty bin).
+__device__ __noinline__ int bin_slow(const int32_t* dp, int W, int carry, int dmin, int dmax, int bin_lo,
+                                     const int32_t* snp_pos, uint32_t slo, uint32_t shi,
+                                     int& first, int& last, int& median) {
+    int n = 0; first = 0x7fffffff; last = -1;
+    const int base = max(dmin, 1);
+    const bool narrow = (long long)dmax - base < 64;
+    unsigned long long m = 0;
+    for (int i = 0; i < W; ++i) {
+        const int d = carry + dp[i];
+        if (d > 0) { ++n; last = i; first = min(first, i); if (narrow) m |= 1ull << (d - base); }
+    }
+    // VCF records of this bin that sit on uncovered positions
+    bool has_zero = false;
+    if (shi > slo) {
+        uint32_t s = slo + lower_bound_i32(snp_pos + slo, (long long)(shi - slo), (int32_t)bin_lo);
+        for (; s < shi; ++s) {
+            const int pos = __ldg(&snp_pos[s]);
+            const int off = pos - bin_lo;
+            if (off >= W) break;
+            if (off < 0) continue;
+            if (carry + dp[off] == 0) {
+                if (s > slo && __ldg(&snp_pos[s - 1]) == pos) continue;      // a duplicated site (flagged by k_snp_mse) counts once
+                ++n; first = min(first, off); last = max(last, off); has_zero = true;
+            }
+        }
+    }
+    median = 0;
+    if (n > 0) {
+        int size, npos = 0;
+        if (narrow) npos = __popcll(m);
+        else {
+            // distinct positive depths by sweeping 64-value windows over [base, dmax]
+            for (long long wb = base; wb <= dmax; wb += 64) {
+                unsigned long long mm = 0;
+                for (int i = 0; i < W; ++i) { long long t = (long long)carry + dp[i] - wb; if (t >= 0 && t < 64 && carry + dp[i] > 0) mm |= 1ull << t; }
+                npos += __popcll(mm);
+            }
+        }
+        size = npos + (has_zero ? 1 : 0);
+        int kk = size / 2 - 1 - (has_zero ? 1 : 0);                  // index among the positive distinct depths
+        if (size >= 2 && kk >= 0) {
+            if (narrow) {
+                for (int i = 0; i < kk; ++i) m &= m - 1;
+                median = base + __ffsll((long long)m) - 1;
+            } else {
+                int count = 0;
+                for (long long wb = base; wb <= dmax; wb += 64) {
+                    unsigned long long mm = 0;
+                    for (int i = 0; i < W; ++i) { long long t = (long long)carry + dp[i] - wb; if (t >= 0 && t < 64 && carry + dp[i] > 0) mm |= 1ull << t; }
+                    const int c = __popcll(mm);
+                    if (kk < count + c) { for (int i = 0; i < kk - count; ++i) mm &= mm - 1; median = (int)(wb + __ffsll((long long)mm) - 1); break; }
+                    count += c;
                 }
             }
+        }
+    }
+    return n;
+}
+
+template <int VEC, bool FILTER>
+__global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ __align__(16) TileRec s_tm[3];     // tile records, prefetched two tiles ahead
+    __shared__ ContigLite s_ct[CTC];
+    __shared__ __align__(8) uint64_t s_rbar[NRBUF], s_mbar[3];
+    __shared__ int s_warp[BIN_MAX_THREADS / 32];
+    __shared__ long long s_prefix;
+    const int tid = threadIdx.x, nthr = blockDim.x;   // == TB: a multiple of 32, at most BIN_MAX_THREADS
+    const int lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
+    const int W = p.W, TB = p.TB;
+    const int TP = TB * W;
+    const int G = (int)gridDim.x;
+    int32_t* diff = reinterpret_cast<int32_t*>(smraw);                 // TP + 4 entries; entry TP sinks ends at the tile edge
+    int32_t* s_carry = diff + (TP + 4);                                // TB entries: depth carried into each bin
+    hcnv_block* recbuf = reinterpret_cast<hcnv_block*>(smraw + ((((size_t)(TP + 4 + TB)) * 4 + 15) & ~(size_t)15));   // NRBUF x (RCAP + 4) slots
+    const bool ct_cached = p.n_contigs <= CTC;
+
+    if (tid == 0) {
+        for (int i = 0; i < NRBUF; ++i) mbar_init(&s_rbar[i], 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&s_mbar[i], 1);
+        mbar_init_fence();
+    }
+    if (ct_cached)
+        for (int i = tid; i < p.n_contigs; i += nthr) {
+            const ContigDev& g = p.contigs[i];
+            ContigLite c; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
+            c.length = g.length; c.n_bins_max = g.n_bins_max;
+            s_ct[i] = c;
+        }
+    for (int i = tid; i < nwarp; i += nthr) s_warp[i] = 0;
+    __syncthreads();
+
+    auto contig_of = [&](int ci) -> ContigLite {
+        if (ct_cached) return s_ct[ci];
+        const ContigDev& g = p.contigs[ci];
+        ContigLite c; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
+        c.length = g.length; c.n_bins_max = g.n_bins_max;
+        return c;
+    };
+    // tid 0 only: prefetch the tile record of tile tt into ring slot `slot`
+    auto fetch_tile_rec = [&](int tt, int slot) {
+        if (tt < p.n_tiles) { fence_proxy_async(); mbar_expect_tx(&s_mbar[slot], (uint32_t)sizeof(TileRec)); tma_load_1d(&s_tm[slot], p.tile_rec + tt, (uint32_t)sizeof(TileRec), &s_mbar[slot]); }
+    };
+    // tid 0 only: start chunk q of a tile (records [lb, hi) of `blocks`) into chunk buffer `buf`
+    auto issue_chunk = [&](const hcnv_block* blocks, const TileRec& tm, uint32_t q, int buf) {
+        const uint32_t lb = tm.lb, hi = tm.hi;
+        const uint32_t a0 = (uint32_t)((reinterpret_cast<unsigned long long>(blocks) >> 3) & 1ull);
+        uint32_t A = lb + ((a0 + lb) & 1u);                             // first 16-byte aligned record at or after lb
+        if (A > hi) A = hi;
+        const uint32_t ta = A + q * RCAP, tb = min(ta + (uint32_t)RCAP, hi);
+        const uint32_t cnt = (tb - ta) & ~1u;                           // aligned part; a ragged last record is the tile's tail
+        hcnv_block* R = recbuf + (size_t)buf * (RCAP + 4);
+        const bool head = (q == 0 && A > lb);
+        if (head) R[1] = tm.head;
+        if (cnt < tb - ta) R[2 + cnt] = tm.tail;
+        R[head ? 0 : 1].start0 = (int)0x80000000;                       // the slot before the first record never looks unsorted
+        fence_proxy_async();
+        if (cnt) { mbar_expect_tx(&s_rbar[buf], cnt * 8u); tma_load_1d(R + 2, blocks + ta, cnt * 8u, &s_rbar[buf]); }
+        else mbar_arrive(&s_rbar[buf]);
+    };
+
+    int prev_last = 0;                             // tid 0: start of the last record of the previous chunk
+    uint32_t consumed = 0;                        // chunks consumed so far by this CTA (uniform): buffer = consumed % 2, parity = (consumed / 2) & 1
+    int t = (int)blockIdx.x;
+    if (tid == 0) {
+        fetch_tile_rec(t, 0);
+        fetch_tile_rec(t + G, 1);
+        if (t < p.n_tiles) {
+            mbar_wait(&s_mbar[0], 0);
+            const TileRec& tm = s_tm[0];
+            if (tm.hi > tm.lb) issue_chunk(contig_of(tm.contig).blocks, tm, 0, 0);
+        }
+    }
+
+    bool pending = false;
+    int po_n = 0, po_start = 0, po_end = 0, po_bin = 0, po_median = 0;
+    long long po_total = 0;
+    int p_t = -1, p_count = 0, p_rank = 0, p_contig = 0, p_first_of_contig = 0;
+
+    for (int it = 0;; ++it, t += G) {
+        const int slot = it % 3;
+        const bool have = t < p.n_tiles;
+        int co_n = 0, co_start = 0, co_end = 0, co_bin = 0, co_median = 0;
+        long long co_total = 0;
+        int c_count = 0, c_rank = 0, c_contig = 0, c_first = 0;
+        __syncthreads();                          // previous tile: everybody is done with diff / s_warp
+
+        if (have) {
+            mbar_wait(&s_mbar[slot], (uint32_t)(it / 3) & 1u);       // landed long ago (tid 0 waited on it one tile earlier)
+            const TileRec tm = s_tm[slot];
+            const ContigLite c = contig_of(tm.contig);
+            c_contig = tm.contig;
+            const int k = tm.k;
+            c_first = (k == 0);
+            const int T0 = k * TP;                                   // 1-based position of diff[0] (fits int: length < 2^31)
+            const long long T1l = (long long)T0 + TP;
+            const uint32_t lb = tm.lb, hi = tm.hi;
+            const hcnv_block* __restrict__ blocks = c.blocks;
+            int bad = (hi < lb) ? 1 : 0;                              // bit 0: unsorted, bit 1: out of range
+            const uint32_t a0 = (uint32_t)((reinterpret_cast<unsigned long long>(blocks) >> 3) & 1ull);
+            uint32_t A = lb + ((a0 + lb) & 1u);
+            if (A > hi) A = hi;
+            const uint32_t nch = (hi > lb) ? max(1u, (hi - A + RCAP - 1) / RCAP) : 0u;
+            // chunk 1 can start right away: its buffer was released at the end of the previous tile's record phase
+            if (tid == 0 && nch > 1) issue_chunk(blocks, tm, 1, (int)((consumed + 1) & 1u));
+            // ---- clear the difference array
+            for (int i = tid * 4; i < TP + 4; i += nthr * 4) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
+            __syncthreads();
             // ---- blocks of any length (few)
             for (long long i = tid; i < c.n_long; i += nthr) {
                 hcnv_long_block r = c.longs[i];
                 long long s1 = (long long)r.start0 + 1, e1 = s1 + r.len;
-                if (r.len < 0 || r.start0 < 0 || e1 - 1 > c.length) { atomicOr(&p.err[ERR_RANGE], 1); continue; }
+                if (r.len < 0 || r.start0 < 0 || e1 - 1 > c.length) { bad |= 2; continue; }
                 uint32_t mq = (uint32_t)r.mapq & 255u;
-                if (!((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u)) continue;
+                if (FILTER && !((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u)) continue;
                 long long s = max(s1, (long long)T0), e = min(e1, T1l);
                 if (e > s) { atomicAdd(&diff[(int)(s - T0)], 1); atomicAdd(&diff[(int)(e - T0)], -1); }
             }
             // ---- the sorted short-block stream, chunk by chunk
-            bool first_chunk = true;
-            for (;;) {
-                const bool last_chunk = cb + cnt >= hiA;
-                const int lo_slot = (first_chunk && head) ? 1 : 2;
-                int hi_slot = 2 + (int)cnt;
-                if (last_chunk && tail) { if (tid == nthr - 1) rec[hi_slot] = blocks[hi - 1]; ++hi_slot; }
-                if (cnt) mbar_wait(&s_bar, phase);
-                __syncthreads();
-                if (cnt) phase ^= 1u;
-                const int sprev = s_prev;
+            const int T0m1 = T0 - 1;
+            const int maxlen = p.maxlen, length = c.length;
+            for (uint32_t q = 0; q < nch; ++q) {
+                const int buf = (int)(consumed & 1u);
+                const uint32_t ta = A + q * RCAP, tb = min(ta + (uint32_t)RCAP, hi);
+                const int lo_slot = (q == 0 && A > lb) ? 1 : 2;
+                const int hi_slot = 2 + (int)(tb - ta);
+                const hcnv_block* R = recbuf + (size_t)buf * (RCAP + 4);
+                mbar_wait(&s_rbar[buf], (consumed >> 1) & 1u);
+                #pragma unroll 4
                 for (int j = lo_slot + tid; j < hi_slot; j += nthr) {
-                    const int2 raw = *reinterpret_cast<const int2*>(rec + j);
+                    const int2 raw = *reinterpret_cast<const int2*>(R + j);
+                    const int prev = R[j - 1].start0;
                     const int start0 = raw.x;
                     const uint32_t lm = (uint32_t)raw.y;
-                    const int prev = (j > lo_slot) ? rec[j - 1].start0 : sprev;
                     const int len = (int)(lm & 0xFFFFFFu);
-                    const uint32_t mq = lm >> 24;
-                    // blocks are <= 4095 long, so start0 + 1 + len cannot overflow once start0 <= length is known
-                    const bool bad_range = len > p.maxlen || start0 < 0 || start0 > c.length || start0 + len > c.length;
-                    if (prev > start0) atomicOr(&p.err[ERR_UNSORTED], 1);
-                    if (bad_range) atomicOr(&p.err[ERR_RANGE], 1);
-                    else if ((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u) {
-                        const int s = max(start0 + 1, T0) - T0, e = min(start0 + 1 + len, T1) - T0;
-                        if (e > s) { atomicAdd(&diff[s], 1); atomicAdd(&diff[e], -1); }
-                    }
+                    // blocks are <= 4095 long, so nothing here can overflow once the range checks hold
+                    bad |= (prev > start0) ? 1 : 0;
+                    bad |= (start0 < 0 || start0 > length - len || len > maxlen) ? 2 : 0;
+                    int s = start0 - T0m1, e = s + len;
+                    s = min(max(s, 0), TP); e = min(max(e, 0), TP);   // clamped: memory-safe whatever the record says
+                    if (FILTER) { const uint32_t mq = lm >> 24; if (!((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u)) continue; }
+                    atomicAdd(&diff[s], 1); atomicAdd(&diff[e], -1);  // a block that ends before the tile cancels itself in diff[0]
                 }
-                __syncthreads();
-                if (last_chunk) {
-                    // claim the next tile now and start its first chunk: it lands while this tile is being walked
-                    if (tid == 0) { s_tile = (int)atomicAdd(p.ticket, 1u); if (s_tile < p.n_tiles) issue_first_chunk(s_tile, cur ^ 1); }
-                    break;
-                }
-                cb += cnt;
-                cnt = min((uint32_t)RCAP, hiA - cb);
-                first_chunk = false;
                 if (tid == 0) {
-                    s_prev = rec[hi_slot - 1].start0;                 // before the next copy overwrites it
-                    fence_proxy_async();
-                    mbar_expect_tx(&s_bar, cnt * 8u);
-                    tma_load_1d(rec + 2, blocks + cb, cnt * 8u, &s_bar);
+                    const int first = R[lo_slot].start0;
+                    bad |= ((q == 0 ? tm.prev_start : prev_last) > first) ? 1 : 0;
+                }
+                ++consumed;
+                __syncthreads();                                      // all reads of this buffer are done; its atomics are issued
+                if (tid == 0) {
+                    prev_last = R[hi_slot - 1].start0;
+                    if (q + 2 < nch) issue_chunk(blocks, tm, q + 2, buf);
                 }
             }
-
-            // ---- per-bin sum of the difference array -> exclusive scan -> depth carried into each bin
-            // HS threads share a bin: thread (b, h) owns positions [h*Wt, (h+1)*Wt) of bin b; threads are in position order
-            const int b = tid / HS, h = tid % HS;
-            const int Wt = W / HS;
-            const int nb_tile = min(TB, c.n_bins_max - k * TB);
-            int32_t* dp = diff + b * W + h * Wt;
-            int bsum = 0;
-            if (b < nb_tile) {
-                if (VEC == 4) { const int4* q = reinterpret_cast<const int4*>(dp); for (int i = 0; i < Wt / 4; ++i) { int4 v = q[i]; bsum += (v.x + v.y) + (v.z + v.w); } }
-                else if (VEC == 2) { const int2* q = reinterpret_cast<const int2*>(dp); for (int i = 0; i < Wt / 2; ++i) { int2 v = q[i]; bsum += v.x + v.y; } }
-                else { for (int i = 0; i < Wt; ++i) bsum += dp[i]; }
+            if (nch == 0) __syncthreads();                            // long-block atomics before the walk
+            // ---- next tile: its record is here (prefetched a tile ago); start its first chunk, prefetch the record after it
+            if (tid == 0) {
+                const int tn = t + G;
+                if (tn < p.n_tiles) {
+                    const int ns = (it + 1) % 3;
+                    mbar_wait(&s_mbar[ns], (uint32_t)((it + 1) / 3) & 1u);
+                    const TileRec& tn_rec = s_tm[ns];
+                    if (tn_rec.hi > tn_rec.lb) issue_chunk(contig_of(tn_rec.contig).blocks, tn_rec, 0, (int)(consumed & 1u));
+                }
+                fetch_tile_rec(t + 2 * G, (it + 2) % 3);
             }
-            int incl = bsum;
+            if (bad & 1) atomicOr(&p.err[ERR_UNSORTED], 1);
+            if (bad & 2) atomicOr(&p.err[ERR_RANGE], 1);
+
+            // ---- the walk: one thread per bin, relative to the depth carried into the bin
+            const int b = tid;
+            const int nb_tile = min(TB, c.n_bins_max - k * TB);
+            int32_t* dp = diff + b * W;
+            int rel_end = 0, mn = 0, mx = 0; long long rsum = 0; uint32_t mask = 0;
+            if (b < nb_tile) {
+                // |relative depth| <= records of the tile; 64-bit sums only when W * that could leave int32
+                const bool wide = (unsigned long long)(hi - lb + (unsigned long long)c.n_long + 1ull) * (unsigned long long)W >= 0x7fffffffull;
+                if (wide) walk_rel<VEC, true>(dp, W, rel_end, rsum, mn, mx, mask);
+                else walk_rel<VEC, false>(dp, W, rel_end, rsum, mn, mx, mask);
+            }
+            // ---- bin totals -> exclusive scan -> depth carried into each bin
+            int incl = rel_end;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             if (lane == 31) s_warp[wid] = incl;
             __syncthreads();
             int woff = 0;
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) if (i < wid) woff += s_warp[i];   // unused warps' slots stay 0
-            const int carry = incl - bsum + woff;
+            for (int i = 0; i < wid; ++i) woff += s_warp[i];
+            const int carry = incl - rel_end + woff;
+            s_carry[b] = carry;
 
-            // ---- walk (every thread its share), merge the shares of a bin, then SNP sites and the BinReducer record
-            WalkOut w;
-            w.n = 0; w.first = 0x7fffffff; w.last = -1; w.sum = 0; w.m0 = w.m1 = 0; w.base = 1; w.oob = 0;
-            {
-                const int bin_carry = __shfl_sync(0xffffffffu, carry, lane - h);       // depth carried into the bin (thread h = 0)
-                if (b < nb_tile) walk_bin<VEC>(dp, Wt, carry, bin_carry, w);
-                if (HS == 2) {
-                    // thread h = 1 hands its share to thread h = 0 (adjacent lanes)
-                    const int n1 = __shfl_down_sync(0xffffffffu, w.n, 1), f1 = __shfl_down_sync(0xffffffffu, w.first, 1);
-                    const int l1 = __shfl_down_sync(0xffffffffu, w.last, 1);
-                    const long long s1 = __shfl_down_sync(0xffffffffu, w.sum, 1);
-                    const uint32_t a0 = __shfl_down_sync(0xffffffffu, w.m0, 1), a1 = __shfl_down_sync(0xffffffffu, w.m1, 1);
-                    const uint32_t o1 = __shfl_down_sync(0xffffffffu, w.oob, 1);
-                    if (h == 0) {
-                        w.n += n1; w.sum += s1; w.m0 |= a0; w.m1 |= a1; w.oob |= o1;
-                        if (f1 != 0x7fffffff) w.first = min(w.first, f1 + Wt);
-                        if (l1 >= 0) w.last = l1 + Wt;
-                    }
-                }
-            }
-            dp = diff + b * W;                                     // from here on: the whole bin, thread h = 0 only
-            if (b < nb_tile && h == 0) {
+            // ---- finish the bin
+            if (b < nb_tile) {
                 const int bin_lo = T0 + b * W;
-                int n = w.n, first = w.first, last = w.last;
-                bool has_zero = false;
-                int nbaf = 0;
-                // one SNP site of this bin, in ascending position order (Reducers.java:76-82,120-129,160-185)
-                auto snp_site = [&](int off, uint32_t tot, uint32_t mx, int zyg) {
-                        const int d = dp[off];
-                        if (tot != (uint32_t)d) atomicOr(&p.err[ERR_INCONSISTENT], 1);
-                        if (d == 0) { ++n; first = min(first, off); last = max(last, off); has_zero = true; }
-                        else if (zyg <= 0) {
-                            float ptd = (float)d, mxd = (float)mx;
-                            float baf = __fdiv_rn(__fsub_rn(ptd, mxd), ptd);             // Reducers.java:126
-                            float baf2 = __fmul_rn(baf, baf);                             // :163
-                            double bb = (double)baf, b2 = (double)baf2;
-                            double a = (0.5 - bb) * (0.5 - bb), q = (0.25 - bb) * (0.25 - bb);
-                            co.mse[0] += fmin(b2, fmin(a, q));                            // :164
-                            co.mse[1] += b2;
-                            if (zyg == -1) { co.mse[2] += b2; co.mse[3] += a; co.mse[4] += (0.33 - bb) * (0.33 - bb); co.mse[5] += fmin(q, a); }
-                            else { co.mse[2] += b2; co.mse[3] += b2; co.mse[4] += b2; co.mse[5] += b2; }
-                            ++nbaf;
-                        }
-                };
-                if (snp_staged) {
-                    const int cntb = s_bcnt[b];
-                    if (cntb > 0) {
-                        const int f0 = s_bfirst[b];
-                        for (int i = f0; i < f0 + cntb; ++i) { const uint2 tm = s_stm[i]; snp_site(s_spos[i] - bin_lo, tm.x, tm.y, (int)s_szyg[i]); }
+                const int dmin = carry + mn, dmax = carry + mx;
+                co_bin = bin_lo;
+                if (dmin > 0 && dmax - dmin < 32) {
+                    // covered everywhere, narrow range: the distinct depths are the bits of the rotated bitmap
+                    co_n = W; co_start = bin_lo; co_end = bin_lo + W - 1;
+                    co_total = (long long)carry * W + rsum;
+                    uint32_t mr = __funnelshift_r(mask, mask, (uint32_t)mn);             // mask bit = relative depth & 31; now bit i <-> depth dmin + i
+                    const int size = __popc(mr);
+                    if (size >= 2) {                                                       // element size/2 - 1 of the sorted distinct set
+                        const int kk = size / 2 - 1;
+                        for (int i = 0; i < kk; ++i) mr &= mr - 1;
+                        co_median = dmin + __ffs((int)mr) - 1;
                     }
-                } else if (shi > slo) {                              // crowded tile: straight from global memory
-                    uint32_t s = slo + lower_bound_i32(c.snp_pos + slo, (long long)(shi - slo), (int32_t)bin_lo);
-                    for (; s < shi; ++s) {
-                        const int pos = __ldg(&c.snp_pos[s]);
-                        if ((long long)pos >= (long long)bin_lo + W) break;
-                        if (s > 0 && __ldg(&c.snp_pos[s - 1]) >= pos) atomicOr(&p.err[ERR_UNSORTED], 1);
-                        if (pos < 0 || pos > c.length) { atomicOr(&p.err[ERR_RANGE], 1); continue; }
-                        const uint4* tr = reinterpret_cast<const uint4*>(p.tally + ((size_t)(c.snp_base + s)) * 16);
-                        uint32_t tot = 0, mx = 0;
-                        #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 v = __ldg(tr + j);
-                            tot += v.x + v.y + v.z + v.w;
-                            mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w));
-                        }
-                        snp_site(pos - bin_lo, tot, mx, (int)c.snp_zyg[s]);
+                } else if (dmax > 0 || tm.shi > tm.slo) {
+                    int first, last, med;
+                    const int n = bin_slow(dp, W, carry, dmin, dmax, bin_lo, c.snp_pos, tm.slo, tm.shi, first, last, med);
+                    if (n > 0) {
+                        co_n = n; co_start = bin_lo + first; co_end = bin_lo + last; co_median = med;
+                        co_total = (long long)carry * W + rsum;
                     }
                 }
-                if (nbaf > 1) { double dn = (double)nbaf; for (int j = 0; j < 6; ++j) co.mse[j] = co.mse[j] / dn; }   // :186-190
-                if (n > 0) {
-                    int size, want, val = 0;
-                    if (w.oob < 64u) {
-                        size = __popc(w.m0) + __popc(w.m1) + (has_zero ? 1 : 0);
-                        want = size / 2 - 1;
-                        if (size >= 2) { int kk = want - (has_zero ? 1 : 0); val = (kk < 0) ? 0 : w.base + kth_set_bit(w.m0, w.m1, kk); }
-                    } else {
-                        int npos = 0, dummy = 0;
-                        distinct_wide(dp, W, npos, -1, dummy);
-                        size = npos + (has_zero ? 1 : 0);
-                        want = size / 2 - 1;
-                        if (size >= 2) { int kk = want - (has_zero ? 1 : 0); if (kk >= 0) distinct_wide(dp, W, npos, kk, val); }
-                    }
-                    co.median = (float)val;
-                    co.n = n; co.start = bin_lo + first; co.end = bin_lo + last;
-                    co.total = (double)w.sum;
-                }
-                co.binpos = bin_lo;
             }
             // ---- rank among the tile's non-empty bins; publish the tile aggregate for the look-back
-            const unsigned ball = __ballot_sync(0xffffffffu, co.n > 0);
-            __syncthreads();                              // s_warp reuse (and: every thread is done with diff / rec)
+            const unsigned ball = __ballot_sync(0xffffffffu, co_n > 0);
+            __syncthreads();                              // s_warp reuse; s_carry complete
             if (lane == 0) s_warp[wid] = __popc(ball);
+            // ---- depth at the tile's SNP sites, for k_snp_mse
+            for (uint32_t i = tid; i < tm.shi - tm.slo; i += nthr) {
+                const uint32_t s = tm.slo + i;
+                const int off = __ldg(&c.snp_pos[s]) - T0;
+                if (off >= 0 && off < TP) p.snp_depth[c.snp_base + s] = s_carry[off / W] + diff[off];
+            }
             __syncthreads();
             c_rank = __popc(ball & ((1u << lane) - 1u));
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) { int v = s_warp[i]; if (i < wid) c_rank += v; c_count += v; }
+            for (int i = 0; i < nwarp; ++i) { int v = s_warp[i]; if (i < wid) c_rank += v; c_count += v; }
             if (tid == 0) {
                 volatile unsigned long long* st = p.status;
                 st[t] = ((t == 0) ? (2ull << 62) : (1ull << 62)) | (unsigned long long)c_count;
@@ -383,19 +449,20 @@ __global__ void __launch_bounds__(256) k_bin_tiles(BinK p) {
                 }
             }
             __syncthreads();
-            if (po.n > 0) {
+            if (po_n > 0) {
                 long long r = s_prefix + p_rank;
                 if (r >= p.capacity) atomicOr(&p.err[ERR_CAPACITY], 1);
                 else {
-                    p.o_bin[r] = po.binpos; p.o_start[r] = po.start; p.o_end[r] = po.end; p.o_median[r] = po.median;
-                    double2* m = reinterpret_cast<double2*>(p.o_mse + r * 6);
-                    m[0] = make_double2(po.mse[0], po.mse[1]); m[1] = make_double2(po.mse[2], po.mse[3]); m[2] = make_double2(po.mse[4], po.mse[5]);
-                    p.o_total[r] = po.total; p.o_n[r] = po.n;
+                    p.o_bin[r] = po_bin; p.o_start[r] = po_start; p.o_end[r] = po_end; p.o_median[r] = (float)po_median;
+                    double2* m = reinterpret_cast<double2*>(p.o_mse + r * 6);     // k_snp_mse fills the bins that hold SNP sites
+                    m[0] = make_double2(0., 0.); m[1] = make_double2(0., 0.); m[2] = make_double2(0., 0.);
+                    p.o_total[r] = (double)po_total; p.o_n[r] = po_n;
                 }
             }
         }
         if (!have) break;
-        po = co; p_t = t; p_count = c_count; p_rank = c_rank; p_contig = c_contig; p_first_of_contig = c_first;
+        po_n = co_n; po_start = co_start; po_end = co_end; po_bin = co_bin; po_median = co_median; po_total = co_total;
+        p_t = t; p_count = c_count; p_rank = c_rank; p_contig = c_contig; p_first_of_contig = c_first;
         pending = true;
     }
 }

@@ -40,7 +40,7 @@ struct PinBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum { HCNV_NBUF = 24 };
+enum { HCNV_NBUF = 32 };
 
 struct hcnv_ctx {
     int          device = 0;

@@ -80,7 +80,8 @@ int         hcnv_ctx_synchronize(hcnv_ctx* ctx);
 #define HCNV_K_VIT_P3         13    /*   exact float replay per segment: calls + verification    */
 #define HCNV_K_VIT_P1B        14    /*   chunk matrices (composition of 32 segment matrices)     */
 #define HCNV_K_VIT_P2B        15    /*   per-segment start vectors inside composed chunks        */
-#define HCNV_K_COUNT          16
+#define HCNV_K_SNP_MSE        16    /* BAF statistics of the bins that hold SNP sites             */
+#define HCNV_K_COUNT          17
 float       hcnv_ctx_kernel_ms(hcnv_ctx* ctx, int which);
 /* counters of the last hcnv_segment_batch call: 0 = segments of the segment-parallel Viterbi, 1 = segments that were
  * replayed with the sequential exact step (binade crossings, rounding ties), 2 = verification failures repaired (cumulative) */
