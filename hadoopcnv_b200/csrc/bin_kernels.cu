@@ -110,16 +110,48 @@ __global__ void k_tile_index(BinK p) {
     p.tile_rec[t] = r;
 }
 
-// Allele tallies at SNP sites: tally[snp][base4] += 1 (AlleleDepthWindowReducer's per-allele map, Reducers.java:381-391)
-__global__ void k_tally(const uint32_t* __restrict__ obs, long long n_obs, long long n_snp, uint32_t* __restrict__ tally,
-                        int32_t* err) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n_obs; i += stride) {
-        uint32_t o = __ldg(&obs[i]);
-        uint32_t idx = o >> 4;
-        if ((long long)idx >= n_snp) { atomicOr(&err[ERR_RANGE], 1); continue; }
-        atomicAdd(&tally[(size_t)idx * 16 + (o & 15u)], 1u);
+// Allele tallies at SNP sites: tally[snp][base4] += 1 (AlleleDepthWindowReducer's per-allele map, Reducers.java:381-391).
+// Observations arrive in block order, so a chunk of them touches a narrow, slowly advancing window of SNP sites: each CTA
+// counts its chunk in a shared-memory window (runs of equal observations inside a warp are added as one), then adds the
+// non-zero counters to the global table; observations outside the window go to the global table directly.
+#define TALLY_WIN   1024                 // SNP sites per window (64 KB of counters)
+#define TALLY_CHUNK 16384                // observations per chunk
+__global__ void __launch_bounds__(256) k_tally(const uint32_t* __restrict__ obs, long long n_obs, long long n_snp,
+                                               uint32_t* __restrict__ tally, int32_t* err) {
+    extern __shared__ __align__(16) uint32_t s_hist[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long n_chunks = (n_obs + TALLY_CHUNK - 1) / TALLY_CHUNK;
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const long long lo = c * TALLY_CHUNK, hi = min(lo + (long long)TALLY_CHUNK, n_obs);
+        const long long first = (long long)(__ldg(&obs[lo]) >> 4);
+        const long long base = max(first - 128, 0ll);
+        for (int i = tid; i < TALLY_WIN * 4; i += 256) reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        for (long long i0 = lo; i0 < hi; i0 += 256) {
+            const long long i = i0 + tid;
+            const bool valid = i < hi;
+            const uint32_t o = valid ? __ldg(&obs[i]) : 0xFFFFFFFFu;
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, o, 1);
+            const bool head = lane == 0 || prev != o || !valid;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (head && valid) {
+                const uint32_t rest = heads & ~((2u << lane) - 1u);
+                const uint32_t cnt = (uint32_t)((rest ? __ffs((int)rest) - 1 : 32) - lane);
+                const long long idx = (long long)(o >> 4);
+                if (idx >= n_snp) atomicOr(&err[ERR_RANGE], 1);
+                else {
+                    const long long rel = idx - base;
+                    if (rel >= 0 && rel < TALLY_WIN) atomicAdd(&s_hist[rel * 16 + (o & 15u)], cnt);
+                    else atomicAdd(&tally[(size_t)idx * 16 + (o & 15u)], cnt);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < TALLY_WIN * 16; i += 256) {
+            const uint32_t v = s_hist[i];
+            if (v && base + (i >> 4) < n_snp) atomicAdd(&tally[(size_t)(base + (i >> 4)) * 16 + (i & 15)], v);
+        }
+        __syncthreads();
     }
 }
 
@@ -345,11 +377,12 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     KT_END(ctx, HCNV_K_TILE_INDEX);
     ctx->launches++;
     KT_BEGIN(ctx, HCNV_K_TALLY);
+    if (tot_obs) HCNV_CUDA(ctx, cudaFuncSetAttribute(k_tally, cudaFuncAttributeMaxDynamicSharedMemorySize, TALLY_WIN * 64));
     for (int c = 0; c < n_contigs; ++c) {
         if (hc[c].n_obs == 0) continue;
-        long long nb = (hc[c].n_obs + 255) / 256;
-        int grid = (int)std::min<long long>(nb, (long long)ctx->sm_count * 16);
-        k_tally<<<grid, 256, 0, ctx->stream>>>(hc[c].obs, hc[c].n_obs, hc[c].n_snp, k.tally + 16 * (size_t)hc[c].snp_base, k.err);
+        long long nb = (hc[c].n_obs + TALLY_CHUNK - 1) / TALLY_CHUNK;
+        int grid = (int)std::min<long long>(nb, (long long)ctx->sm_count * 3);
+        k_tally<<<grid, 256, TALLY_WIN * 64, ctx->stream>>>(hc[c].obs, hc[c].n_obs, hc[c].n_snp, k.tally + 16 * (size_t)hc[c].snp_base, k.err);
         ctx->launches++;
     }
     KT_END(ctx, HCNV_K_TALLY);

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
     __shared__ ContigLite s_ct[CTC];
     __shared__ __align__(8) uint64_t s_rbar[NRBUF], s_mbar[3];
     __shared__ int s_warp[BIN_MAX_THREADS / 32];
-    __shared__ long long s_prefix;
+    __shared__ long long s_prefix[2];
+    __shared__ int s_cnt[BIN_MAX_THREADS / 32];
     const int tid = threadIdx.x, nthr = blockDim.x;   // == TB: a multiple of 32, at most BIN_MAX_THREADS
     const int lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     const int W = p.W, TB = p.TB;
@@ -248,10 +249,15 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
         }
     }
 
-    bool pending = false;
-    int po_n = 0, po_start = 0, po_end = 0, po_bin = 0, po_median = 0;
-    long long po_total = 0;
-    int p_t = -1, p_count = 0, p_rank = 0, p_contig = 0, p_first_of_contig = 0;
+    // Outputs trail by two tiles: tile i's bins wait in registers (p_*) while tile i + 1 is processed, its global row
+    // offset is resolved by warp 0 at the end of iteration i + 1 (round look-back below), and the rows are written
+    // at the top of iteration i + 2 (pp_*), so no warp ever waits for another CTA.
+    bool p_valid = false, pp_valid = false;
+    int p_n = 0, p_start = 0, p_end = 0, p_bin = 0, p_median = 0, p_rank = 0, p_t = -1, p_contig = 0, p_first = 0, p_count = 0;
+    long long p_total = 0;
+    int pp_n = 0, pp_start = 0, pp_end = 0, pp_bin = 0, pp_median = 0, pp_rank = 0;
+    long long pp_total = 0;
+    long long round_base = 0;                     // warp 0: rows written by all earlier rounds
 
     for (int it = 0;; ++it, t += G) {
         const int slot = it % 3;
@@ -259,7 +265,20 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
         int co_n = 0, co_start = 0, co_end = 0, co_bin = 0, co_median = 0;
         long long co_total = 0;
         int c_count = 0, c_rank = 0, c_contig = 0, c_first = 0;
-        __syncthreads();                          // previous tile: everybody is done with diff / s_warp
+        __syncthreads();                          // previous tile: everybody is done with diff / s_carry; s_prefix[(it - 1) & 1] is set
+
+        // ---- rows of the tile before the previous one
+        if (pp_valid && pp_n > 0) {
+            const long long r = s_prefix[(it - 1) & 1] + pp_rank;
+            if (r >= p.capacity) atomicOr(&p.err[ERR_CAPACITY], 1);
+            else {
+                p.o_bin[r] = pp_bin; p.o_start[r] = pp_start; p.o_end[r] = pp_end; p.o_median[r] = (float)pp_median;
+                double2* m = reinterpret_cast<double2*>(p.o_mse + r * 6);     // k_snp_mse fills the bins that hold SNP sites
+                m[0] = make_double2(0., 0.); m[1] = make_double2(0., 0.); m[2] = make_double2(0., 0.);
+                p.o_total[r] = (double)pp_total; p.o_n[r] = pp_n;
+            }
+        }
+        if (!have && !p_valid) break;
 
         if (have) {
             mbar_wait(&s_mbar[slot], (uint32_t)(it / 3) & 1u);       // landed long ago (tid 0 waited on it one tile earlier)
@@ -390,79 +409,64 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
                     }
                 }
             }
-            // ---- rank among the tile's non-empty bins; publish the tile aggregate for the look-back
+            // ---- rank among the tile's non-empty bins; publish the tile's count for the round look-back
             const unsigned ball = __ballot_sync(0xffffffffu, co_n > 0);
-            __syncthreads();                              // s_warp reuse; s_carry complete
-            if (lane == 0) s_warp[wid] = __popc(ball);
+            if (lane == 0) s_cnt[wid] = __popc(ball);
+            __syncthreads();                              // s_carry and s_cnt complete
             // ---- depth at the tile's SNP sites, for k_snp_mse
             for (uint32_t i = tid; i < tm.shi - tm.slo; i += nthr) {
                 const uint32_t s = tm.slo + i;
                 const int off = __ldg(&c.snp_pos[s]) - T0;
                 if (off >= 0 && off < TP) p.snp_depth[c.snp_base + s] = s_carry[off / W] + diff[off];
             }
-            __syncthreads();
             c_rank = __popc(ball & ((1u << lane) - 1u));
-            for (int i = 0; i < nwarp; ++i) { int v = s_warp[i]; if (i < wid) c_rank += v; c_count += v; }
+            for (int i = 0; i < nwarp; ++i) { int v = s_cnt[i]; if (i < wid) c_rank += v; c_count += v; }
             if (tid == 0) {
                 volatile unsigned long long* st = p.status;
-                st[t] = ((t == 0) ? (2ull << 62) : (1ull << 62)) | (unsigned long long)c_count;
-                __threadfence();
+                st[t] = (1ull << 62) | (unsigned long long)c_count;   // the word carries its own payload: no fence needed
             }
         }
 
-        // ---- deferred epilogue of the previous tile: resolve its offset (predecessors are long done), write its bins
-        if (pending) {
-            if (wid == 0) {
-                const unsigned long long FLAG_PRE = 2ull << 62, VAL = (1ull << 62) - 1;
-                volatile unsigned long long* st = p.status;
-                long long excl = 0;
-                if (p_t > 0) {
-                    int j = p_t - 1;
-                    bool done = false;
+        // ---- row offset of the previous tile.  Tiles are dealt round-robin, so the tiles before it are all earlier
+        // rounds (their total is carried in round_base) plus the lower-numbered CTAs' tiles of its own round: warp 0
+        // reads the whole round's counts with independent loads (one L2 round trip; they were published about one
+        // tile time ago), which gives this tile's offset and the round total at once.  No CTA waits for another
+        // CTA's offset, only for its count.
+        if (p_valid && wid == 0) {
+            volatile unsigned long long* st = p.status;
+            const unsigned long long VAL = (1ull << 62) - 1;
+            const int r0 = p_t - (int)blockIdx.x;                       // first tile of that round
+            const int nr = min(G, p.n_tiles - r0);
+            long long before = 0, total = 0;
+            for (int kq = lane; kq < nr; kq += 128) {
+                unsigned long long v[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (kq + 32 * u < nr) ? st[r0 + kq + 32 * u] : (1ull << 62);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
                     long long spins = 0;
-                    while (!done) {
-                        int idx = j - lane;
-                        unsigned long long v = (idx >= 0) ? st[idx] : FLAG_PRE;
-                        unsigned flagged = __ballot_sync(0xffffffffu, (v >> 62) != 0);
-                        unsigned pre = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                        unsigned not_flagged = ~flagged;
-                        int first_gap = not_flagged ? (__ffs(not_flagged) - 1) : 32;
-                        int first_pre = pre ? (__ffs(pre) - 1) : 32;
-                        int take = (first_pre < first_gap) ? first_pre + 1 : first_gap;
-                        long long contrib = (lane < take) ? (long long)(v & VAL) : 0;
-                        #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                        excl += contrib;
-                        j -= take;
-                        if (first_pre < first_gap) done = true;
-                        else if (take == 0) {
-                            if (++spins > (1ll << 22)) { if (lane == 0) atomicOr(&p.err[ERR_INTERNAL], 1); done = true; }
-                            __nanosleep(100);
-                        }
+                    while ((v[u] >> 62) == 0) {
+                        __nanosleep(64);
+                        v[u] = st[r0 + kq + 32 * u];
+                        if (++spins > (1ll << 24)) { atomicOr(&p.err[ERR_INTERNAL], 1); break; }
                     }
-                    if (lane == 0) { __threadfence(); st[p_t] = FLAG_PRE | (unsigned long long)(excl + p_count); }
-                }
-                if (lane == 0) {
-                    s_prefix = excl;
-                    if (p_first_of_contig) p.contig_offset[p_contig] = excl;
-                    if (p_t == p.n_tiles - 1) p.contig_offset[p.n_contigs] = excl + p_count;
+                    const long long val = (long long)(v[u] & VAL);
+                    total += val;
+                    if (kq + 32 * u < (int)blockIdx.x) before += val;
                 }
             }
-            __syncthreads();
-            if (po_n > 0) {
-                long long r = s_prefix + p_rank;
-                if (r >= p.capacity) atomicOr(&p.err[ERR_CAPACITY], 1);
-                else {
-                    p.o_bin[r] = po_bin; p.o_start[r] = po_start; p.o_end[r] = po_end; p.o_median[r] = (float)po_median;
-                    double2* m = reinterpret_cast<double2*>(p.o_mse + r * 6);     // k_snp_mse fills the bins that hold SNP sites
-                    m[0] = make_double2(0., 0.); m[1] = make_double2(0., 0.); m[2] = make_double2(0., 0.);
-                    p.o_total[r] = (double)po_total; p.o_n[r] = po_n;
-                }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+            const long long excl = round_base + before;
+            round_base += total;
+            if (lane == 0) {
+                s_prefix[it & 1] = excl;
+                if (p_first) p.contig_offset[p_contig] = excl;
+                if (p_t == p.n_tiles - 1) p.contig_offset[p.n_contigs] = excl + p_count;
             }
         }
-        if (!have) break;
-        po_n = co_n; po_start = co_start; po_end = co_end; po_bin = co_bin; po_median = co_median; po_total = co_total;
-        p_t = t; p_count = c_count; p_rank = c_rank; p_contig = c_contig; p_first_of_contig = c_first;
-        pending = true;
+        pp_valid = p_valid; pp_n = p_n; pp_start = p_start; pp_end = p_end; pp_bin = p_bin; pp_median = p_median; pp_rank = p_rank; pp_total = p_total;
+        p_valid = have; p_n = co_n; p_start = co_start; p_end = co_end; p_bin = co_bin; p_median = co_median; p_rank = c_rank; p_total = co_total;
+        p_t = t; p_contig = c_contig; p_first = c_first; p_count = c_count;
     }
 }
