@@ -56,6 +56,8 @@ struct BinK {
     int32_t *o_bin, *o_start, *o_end; float* o_median; double* o_mse; double* o_total; int32_t* o_n;
     long long capacity;
     unsigned long long* status;      // look-back words, one per tile
+    unsigned long long *grp, *grp_pre;   // per group of 32 tiles: sum + arrivals; rows before the end of the group
+    unsigned int*       ticket;
     int32_t*            err;
     long long*          contig_offset;   // n_contigs + 1
 };
@@ -111,47 +113,28 @@ __global__ void k_tile_index(BinK p) {
 }
 
 // Allele tallies at SNP sites: tally[snp][base4] += 1 (AlleleDepthWindowReducer's per-allele map, Reducers.java:381-391).
-// Observations arrive in block order, so a chunk of them touches a narrow, slowly advancing window of SNP sites: each CTA
-// counts its chunk in a shared-memory window (runs of equal observations inside a warp are added as one), then adds the
-// non-zero counters to the global table; observations outside the window go to the global table directly.
-#define TALLY_WIN   1024                 // SNP sites per window (64 KB of counters)
-#define TALLY_CHUNK 16384                // observations per chunk
+// Observations arrive in block order, so the 32 consecutive observations of a warp name only a handful of distinct
+// (site, base) pairs: the warp elects a leader per distinct value and adds the multiplicity with ONE global atomic.
 __global__ void __launch_bounds__(256) k_tally(const uint32_t* __restrict__ obs, long long n_obs, long long n_snp,
                                                uint32_t* __restrict__ tally, int32_t* err) {
-    extern __shared__ __align__(16) uint32_t s_hist[];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const long long n_chunks = (n_obs + TALLY_CHUNK - 1) / TALLY_CHUNK;
-    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const long long lo = c * TALLY_CHUNK, hi = min(lo + (long long)TALLY_CHUNK, n_obs);
-        const long long first = (long long)(__ldg(&obs[lo]) >> 4);
-        const long long base = max(first - 128, 0ll);
-        for (int i = tid; i < TALLY_WIN * 4; i += 256) reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        for (long long i0 = lo; i0 < hi; i0 += 256) {
-            const long long i = i0 + tid;
-            const bool valid = i < hi;
-            const uint32_t o = valid ? __ldg(&obs[i]) : 0xFFFFFFFFu;
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, o, 1);
-            const bool head = lane == 0 || prev != o || !valid;
-            const uint32_t heads = __ballot_sync(0xffffffffu, head);
-            if (head && valid) {
-                const uint32_t rest = heads & ~((2u << lane) - 1u);
-                const uint32_t cnt = (uint32_t)((rest ? __ffs((int)rest) - 1 : 32) - lane);
-                const long long idx = (long long)(o >> 4);
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n_obs; i0 += stride) {
+        const long long i = i0 + lane;
+        const bool valid = i < n_obs;
+        const uint32_t o = valid ? __ldg(&obs[i]) : 0u;
+        uint32_t remaining = __ballot_sync(0xffffffffu, valid);
+        while (remaining) {
+            const int leader = __ffs((int)remaining) - 1;
+            const uint32_t v = __shfl_sync(0xffffffffu, o, leader);
+            const uint32_t same = __ballot_sync(0xffffffffu, o == v) & remaining;
+            if (lane == leader) {
+                const long long idx = (long long)(v >> 4);
                 if (idx >= n_snp) atomicOr(&err[ERR_RANGE], 1);
-                else {
-                    const long long rel = idx - base;
-                    if (rel >= 0 && rel < TALLY_WIN) atomicAdd(&s_hist[rel * 16 + (o & 15u)], cnt);
-                    else atomicAdd(&tally[(size_t)idx * 16 + (o & 15u)], cnt);
-                }
+                else atomicAdd(&tally[(size_t)idx * 16 + (v & 15u)], (uint32_t)__popc(same));
             }
+            remaining &= ~same;
         }
-        __syncthreads();
-        for (int i = tid; i < TALLY_WIN * 16; i += 256) {
-            const uint32_t v = s_hist[i];
-            if (v && base + (i >> 4) < n_snp) atomicAdd(&tally[(size_t)(base + (i >> 4)) * 16 + (i & 15)], v);
-        }
-        __syncthreads();
     }
 }
 
@@ -335,7 +318,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     HCNV_CUDA(ctx, ctx->buf[B_TILEIDX].reserve(sizeof(TileRec) * (size_t)n_tiles));
     HCNV_CUDA(ctx, ctx->buf[B_SNPDEPTH].reserve(4 * (size_t)(tot_snp + 1)));
     HCNV_CUDA(ctx, ctx->buf[B_TALLY].reserve(64 * (size_t)(tot_snp + 1)));
-    HCNV_CUDA(ctx, ctx->buf[B_STATUS].reserve(8 * (size_t)n_tiles));
+    HCNV_CUDA(ctx, ctx->buf[B_STATUS].reserve(8 * ((size_t)n_tiles + 2 * ((size_t)n_tiles / 32 + 1))));
     HCNV_CUDA(ctx, ctx->buf[B_MISC].reserve(4096 + 8 * (size_t)(n_contigs + 1)));
     k.contigs = ctx->buf[B_CONTIGS].as<ContigDev>();
     k.n_contigs = n_contigs; k.W = W; k.TB = TB; k.n_tiles = n_tiles; k.maxlen = maxlen;
@@ -348,8 +331,9 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     k.n_snp_total = tot_snp;
     k.tally = ctx->buf[B_TALLY].as<uint32_t>();
     k.status = ctx->buf[B_STATUS].as<unsigned long long>();
+    k.grp = k.status + n_tiles; k.grp_pre = k.grp + (n_tiles / 32 + 1);
     char* misc = ctx->buf[B_MISC].as<char>();
-    k.err = (int32_t*)misc; k.contig_offset = (long long*)(misc + 128);
+    k.err = (int32_t*)misc; k.ticket = (unsigned int*)(misc + 64); k.contig_offset = (long long*)(misc + 128);
     k.capacity = out->capacity;
 
     // outputs: directly into the caller's device arrays, or into scratch followed by a D2H copy
@@ -369,7 +353,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     }
 
     HCNV_CUDA(ctx, cudaMemsetAsync(misc, 0, 128 + 8 * (size_t)(n_contigs + 1), ctx->stream));
-    HCNV_CUDA(ctx, cudaMemsetAsync(k.status, 0, 8 * (size_t)n_tiles, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemsetAsync(k.status, 0, 8 * ((size_t)n_tiles + 2 * ((size_t)n_tiles / 32 + 1)), ctx->stream));
     if (tot_snp) HCNV_CUDA(ctx, cudaMemsetAsync(k.tally, 0, 64 * (size_t)tot_snp, ctx->stream));
 
     KT_BEGIN(ctx, HCNV_K_TILE_INDEX);
@@ -377,12 +361,11 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     KT_END(ctx, HCNV_K_TILE_INDEX);
     ctx->launches++;
     KT_BEGIN(ctx, HCNV_K_TALLY);
-    if (tot_obs) HCNV_CUDA(ctx, cudaFuncSetAttribute(k_tally, cudaFuncAttributeMaxDynamicSharedMemorySize, TALLY_WIN * 64));
     for (int c = 0; c < n_contigs; ++c) {
         if (hc[c].n_obs == 0) continue;
-        long long nb = (hc[c].n_obs + TALLY_CHUNK - 1) / TALLY_CHUNK;
-        int grid = (int)std::min<long long>(nb, (long long)ctx->sm_count * 3);
-        k_tally<<<grid, 256, TALLY_WIN * 64, ctx->stream>>>(hc[c].obs, hc[c].n_obs, hc[c].n_snp, k.tally + 16 * (size_t)hc[c].snp_base, k.err);
+        long long nb = (hc[c].n_obs + 255) / 256;
+        int grid = (int)std::min<long long>(nb, (long long)ctx->sm_count * 16);
+        k_tally<<<grid, 256, 0, ctx->stream>>>(hc[c].obs, hc[c].n_obs, hc[c].n_snp, k.tally + 16 * (size_t)hc[c].snp_base, k.err);
         ctx->launches++;
     }
     KT_END(ctx, HCNV_K_TALLY);
@@ -393,11 +376,11 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB + 32, smem_bytes);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         const int grid = std::min(n_tiles, ctx->sm_count * per_sm);       // persistent, co-resident CTAs; tiles round-robin
-        kern<<<grid, TB, smem_bytes, ctx->stream>>>(k);
+        kern<<<grid, TB + 32, smem_bytes, ctx->stream>>>(k);       // TB compute threads + the look-back warp
         return cudaGetLastError();
     };
     if (W % 4 == 0)      HCNV_CUDA(ctx, filter ? launch(k_bin_tiles<4, true>) : launch(k_bin_tiles<4, false>));

@@ -24,7 +24,7 @@
 #define RCAP 1024                                 // records per staged chunk (8 KB)
 #define NRBUF 2                                   // chunk buffers in flight
 #define CTC 32                                    // contig descriptors cached in shared memory
-#define BIN_MAX_THREADS 512
+#define BIN_MAX_THREADS 224
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -52,6 +52,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
+__device__ __forceinline__ void bar_compute(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }   // the compute warps only
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct ContigLite {                               // what a tile needs from its contig
@@ -174,19 +175,21 @@ __device__ __noinline__ int bin_slow(const int32_t* dp, int W, int carry, int dm
 }
 
 template <int VEC, bool FILTER>
-__global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
+__global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ __align__(16) TileRec s_tm[3];     // tile records, prefetched two tiles ahead
     __shared__ ContigLite s_ct[CTC];
     __shared__ __align__(8) uint64_t s_rbar[NRBUF], s_mbar[3];
     __shared__ int s_warp[BIN_MAX_THREADS / 32];
-    __shared__ long long s_prefix[2];
     __shared__ int s_cnt[BIN_MAX_THREADS / 32];
-    const int tid = threadIdx.x, nthr = blockDim.x;   // == TB: a multiple of 32, at most BIN_MAX_THREADS
+    __shared__ int s_tk[3];
+    __shared__ __align__(8) uint64_t s_cbar[4], s_pbar[4];   // tile count published / row offset resolved (ring of 4 tiles)
+    __shared__ int s_lt[4], s_lc[4], s_lcontig[4], s_lfirst[4];
+    __shared__ long long s_lpre[4];                       // tickets (tile ids) of iterations it, it + 1, it + 2
+    const int tid = threadIdx.x, nthr = blockDim.x - 32;   // compute threads == TB (a multiple of 32, at most BIN_MAX_THREADS); + the look-back warp
     const int lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     const int W = p.W, TB = p.TB;
     const int TP = TB * W;
-    const int G = (int)gridDim.x;
     int32_t* diff = reinterpret_cast<int32_t*>(smraw);                 // TP + 4 entries; entry TP sinks ends at the tile edge
     int32_t* s_carry = diff + (TP + 4);                                // TB entries: depth carried into each bin
     hcnv_block* recbuf = reinterpret_cast<hcnv_block*>(smraw + ((((size_t)(TP + 4 + TB)) * 4 + 15) & ~(size_t)15));   // NRBUF x (RCAP + 4) slots
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
     if (tid == 0) {
         for (int i = 0; i < NRBUF; ++i) mbar_init(&s_rbar[i], 1);
         for (int i = 0; i < 3; ++i) mbar_init(&s_mbar[i], 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_cbar[i], 1); mbar_init(&s_pbar[i], 1); }
         mbar_init_fence();
     }
     if (ct_cached)
@@ -206,6 +210,63 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
         }
     for (int i = tid; i < nwarp; i += nthr) s_warp[i] = 0;
     __syncthreads();
+
+    // ---- the look-back warp: resolves every tile's global row offset, off the compute warps' critical path.
+    // Two levels, so that one L2 round trip of three independent loads per lane is enough however many tiles are in
+    // flight: status[t] (count of tile t), grp[g] (atomic sum + arrival count of the 32 tiles of group g) and
+    // grp_pre[g] (rows before the end of group g, published by whoever resolves the group's last tile).  A tile's
+    // offset = nearest published group prefix + the complete groups after it + the earlier tiles of its own group.
+    // Every word carries its own payload, so no fences are needed.  A tile is resolved one tile late (when the next
+    // tile's count arrives): by then its predecessors, claimed before it, have almost always published.
+    if (wid == nwarp) {
+        const unsigned long long FLAG_PRE = 2ull << 62, VAL = (1ull << 62) - 1, GVAL = (1ull << 40) - 1;
+        volatile unsigned long long* st = p.status;
+        volatile unsigned long long* grp = p.grp;
+        volatile unsigned long long* gpre = p.grp_pre;
+        int q_t = -1, q_count = 0, q_contig = 0, q_first = 0, q_slot = 0;          // the tile waiting to be resolved
+        for (int i = 0;; ++i) {
+            const int ls = i & 3;
+            mbar_wait(&s_cbar[ls], (uint32_t)(i >> 2) & 1u);
+            const int lt = s_lt[ls], lcount = s_lc[ls], lcontig = s_lcontig[ls], lfirst = s_lfirst[ls];
+            if (q_t >= 0) {
+                const int g = q_t >> 5, r = q_t & 31;
+                long long excl = 0, spins = 0;
+                for (;;) {
+                    const unsigned long long a = (lane < r) ? st[q_t - 1 - lane] : (1ull << 62);
+                    const int gq = g - 1 - lane;
+                    const unsigned long long bq = (gq >= 0) ? grp[gq] : (32ull << 40);
+                    const unsigned long long cq = (gq >= 0) ? gpre[gq] : FLAG_PRE;
+                    const unsigned own_missing = __ballot_sync(0xffffffffu, (a >> 62) == 0);
+                    const unsigned pre = __ballot_sync(0xffffffffu, (cq >> 62) == 2);
+                    const unsigned incomplete = __ballot_sync(0xffffffffu, (bq >> 40) != 32ull);
+                    const int first_pre = pre ? (__ffs((int)pre) - 1) : 32;
+                    const unsigned need = (first_pre >= 32) ? 0xffffffffu : ((1u << first_pre) - 1u);   // groups nearer than the prefix
+                    if (!own_missing && first_pre < 32 && !(incomplete & need)) {
+                        long long contrib = (lane < r) ? (long long)(a & VAL) : 0;
+                        if (lane < first_pre) contrib += (long long)(bq & GVAL);
+                        if (lane == first_pre) contrib += (long long)(cq & VAL);
+                        #pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                        excl = contrib;
+                        break;
+                    }
+                    if (++spins > (1ll << 22)) { if (lane == 0) atomicOr(&p.err[ERR_INTERNAL], 1); break; }
+                    __nanosleep(200);
+                }
+                if (lane == 0) {
+                    if (r == 31 || q_t == p.n_tiles - 1) gpre[g] = FLAG_PRE | (unsigned long long)(excl + q_count);
+                    s_lpre[q_slot] = excl;
+                    if (q_first) p.contig_offset[q_contig] = excl;
+                    if (q_t == p.n_tiles - 1) p.contig_offset[p.n_contigs] = excl + q_count;
+                    mbar_arrive(&s_pbar[q_slot]);
+                }
+                __syncwarp();
+            }
+            if (lt < 0) break;
+            q_t = lt; q_count = lcount; q_contig = lcontig; q_first = lfirst; q_slot = ls;
+        }
+        return;
+    }
 
     auto contig_of = [&](int ci) -> ContigLite {
         if (ct_cached) return s_ct[ci];
@@ -238,47 +299,58 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
 
     int prev_last = 0;                             // tid 0: start of the last record of the previous chunk
     uint32_t consumed = 0;                        // chunks consumed so far by this CTA (uniform): buffer = consumed % 2, parity = (consumed / 2) & 1
-    int t = (int)blockIdx.x;
+    // Tiles are claimed from an atomic ticket, in order (the look-back relies on that), two tiles ahead: the ticket
+    // for iteration it + 2 is requested at the top of iteration it and only looked at after the record phase.
     if (tid == 0) {
-        fetch_tile_rec(t, 0);
-        fetch_tile_rec(t + G, 1);
-        if (t < p.n_tiles) {
+        const int t0 = (int)atomicAdd(p.ticket, 1u), t1 = (int)atomicAdd(p.ticket, 1u);
+        s_tk[0] = t0; s_tk[1] = t1;
+        fetch_tile_rec(t0, 0);
+        fetch_tile_rec(t1, 1);
+        if (t0 < p.n_tiles) {
             mbar_wait(&s_mbar[0], 0);
             const TileRec& tm = s_tm[0];
             if (tm.hi > tm.lb) issue_chunk(contig_of(tm.contig).blocks, tm, 0, 0);
         }
     }
+    bool finished = false;                        // tickets only grow: once one is past the end, all later ones are
 
     // Outputs trail by two tiles: tile i's bins wait in registers (p_*) while tile i + 1 is processed, its global row
     // offset is resolved by warp 0 at the end of iteration i + 1 (round look-back below), and the rows are written
     // at the top of iteration i + 2 (pp_*), so no warp ever waits for another CTA.
-    bool p_valid = false, pp_valid = false;
-    int p_n = 0, p_start = 0, p_end = 0, p_bin = 0, p_median = 0, p_rank = 0, p_t = -1, p_contig = 0, p_first = 0, p_count = 0;
+    bool p_valid = false, pp_valid = false, p3_valid = false;
+    int p_n = 0, p_start = 0, p_end = 0, p_bin = 0, p_median = 0, p_rank = 0;
     long long p_total = 0;
     int pp_n = 0, pp_start = 0, pp_end = 0, pp_bin = 0, pp_median = 0, pp_rank = 0;
     long long pp_total = 0;
-    long long round_base = 0;                     // warp 0: rows written by all earlier rounds
+    int p3_n = 0, p3_start = 0, p3_end = 0, p3_bin = 0, p3_median = 0, p3_rank = 0;
+    long long p3_total = 0;
 
-    for (int it = 0;; ++it, t += G) {
+    for (int it = 0;; ++it) {
         const int slot = it % 3;
-        const bool have = t < p.n_tiles;
         int co_n = 0, co_start = 0, co_end = 0, co_bin = 0, co_median = 0;
         long long co_total = 0;
         int c_count = 0, c_rank = 0, c_contig = 0, c_first = 0;
-        __syncthreads();                          // previous tile: everybody is done with diff / s_carry; s_prefix[(it - 1) & 1] is set
+        bar_compute(nthr);                          // previous tile: everybody is done with diff / s_carry; s_prefix[(it - 1) & 1] and s_tk[slot] are set
+        const int t = finished ? p.n_tiles : s_tk[slot];
+        const bool have = t < p.n_tiles;
+        if (!have && !finished && tid == 0) { s_lt[it & 3] = -1; mbar_arrive(&s_cbar[it & 3]); }   // tell the look-back warp to leave
+        finished = !have;
+        unsigned int tk2 = 0;
+        if (tid == 0 && have) tk2 = atomicAdd(p.ticket, 1u);        // ticket of iteration it + 2; consumed after the record phase
 
         // ---- rows of the tile before the previous one
-        if (pp_valid && pp_n > 0) {
-            const long long r = s_prefix[(it - 1) & 1] + pp_rank;
+        if (p3_valid) mbar_wait(&s_pbar[(it - 3) & 3], (uint32_t)((it - 3) >> 2) & 1u);      // resolved by the look-back warp, normally long ago
+        if (p3_valid && p3_n > 0) {
+            const long long r = s_lpre[(it - 3) & 3] + p3_rank;
             if (r >= p.capacity) atomicOr(&p.err[ERR_CAPACITY], 1);
             else {
-                p.o_bin[r] = pp_bin; p.o_start[r] = pp_start; p.o_end[r] = pp_end; p.o_median[r] = (float)pp_median;
+                p.o_bin[r] = p3_bin; p.o_start[r] = p3_start; p.o_end[r] = p3_end; p.o_median[r] = (float)p3_median;
                 double2* m = reinterpret_cast<double2*>(p.o_mse + r * 6);     // k_snp_mse fills the bins that hold SNP sites
                 m[0] = make_double2(0., 0.); m[1] = make_double2(0., 0.); m[2] = make_double2(0., 0.);
-                p.o_total[r] = (double)pp_total; p.o_n[r] = pp_n;
+                p.o_total[r] = (double)p3_total; p.o_n[r] = p3_n;
             }
         }
-        if (!have && !p_valid) break;
+        if (!have && !p_valid && !pp_valid) break;
 
         if (have) {
             mbar_wait(&s_mbar[slot], (uint32_t)(it / 3) & 1u);       // landed long ago (tid 0 waited on it one tile earlier)
@@ -300,7 +372,7 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
             if (tid == 0 && nch > 1) issue_chunk(blocks, tm, 1, (int)((consumed + 1) & 1u));
             // ---- clear the difference array
             for (int i = tid * 4; i < TP + 4; i += nthr * 4) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
-            __syncthreads();
+            bar_compute(nthr);
             // ---- blocks of any length (few)
             for (long long i = tid; i < c.n_long; i += nthr) {
                 hcnv_long_block r = c.longs[i];
@@ -341,23 +413,32 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
                     bad |= ((q == 0 ? tm.prev_start : prev_last) > first) ? 1 : 0;
                 }
                 ++consumed;
-                __syncthreads();                                      // all reads of this buffer are done; its atomics are issued
+                bar_compute(nthr);                                      // all reads of this buffer are done; its atomics are issued
                 if (tid == 0) {
                     prev_last = R[hi_slot - 1].start0;
                     if (q + 2 < nch) issue_chunk(blocks, tm, q + 2, buf);
                 }
             }
-            if (nch == 0) __syncthreads();                            // long-block atomics before the walk
+            if (nch == 0) bar_compute(nthr);                            // long-block atomics before the walk
             // ---- next tile: its record is here (prefetched a tile ago); start its first chunk, prefetch the record after it
             if (tid == 0) {
-                const int tn = t + G;
+                const int tn = s_tk[(it + 1) % 3];
                 if (tn < p.n_tiles) {
                     const int ns = (it + 1) % 3;
                     mbar_wait(&s_mbar[ns], (uint32_t)((it + 1) / 3) & 1u);
                     const TileRec& tn_rec = s_tm[ns];
-                    if (tn_rec.hi > tn_rec.lb) issue_chunk(contig_of(tn_rec.contig).blocks, tn_rec, 0, (int)(consumed & 1u));
+                    if (tn_rec.hi > tn_rec.lb) {
+                        const hcnv_block* nb = contig_of(tn_rec.contig).blocks;
+                        issue_chunk(nb, tn_rec, 0, (int)(consumed & 1u));
+                        // the rest of its records: into L2 now, so that the later chunks are L2 hits
+                        const unsigned long long pa = (reinterpret_cast<unsigned long long>(nb + tn_rec.lb) + 15ull) & ~15ull;
+                        const unsigned long long pe = reinterpret_cast<unsigned long long>(nb + tn_rec.hi) & ~15ull;
+                        if (pe > pa + (unsigned long long)RCAP * 8ull)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa + (unsigned long long)RCAP * 8ull), "r"((uint32_t)(pe - pa - (unsigned long long)RCAP * 8ull)) : "memory");
+                    }
                 }
-                fetch_tile_rec(t + 2 * G, (it + 2) % 3);
+                s_tk[(it + 2) % 3] = (int)tk2;
+                fetch_tile_rec((int)tk2, (it + 2) % 3);
             }
             if (bad & 1) atomicOr(&p.err[ERR_UNSORTED], 1);
             if (bad & 2) atomicOr(&p.err[ERR_RANGE], 1);
@@ -378,7 +459,7 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             if (lane == 31) s_warp[wid] = incl;
-            __syncthreads();
+            bar_compute(nthr);
             int woff = 0;
             for (int i = 0; i < wid; ++i) woff += s_warp[i];
             const int carry = incl - rel_end + woff;
@@ -412,7 +493,7 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
             // ---- rank among the tile's non-empty bins; publish the tile's count for the round look-back
             const unsigned ball = __ballot_sync(0xffffffffu, co_n > 0);
             if (lane == 0) s_cnt[wid] = __popc(ball);
-            __syncthreads();                              // s_carry and s_cnt complete
+            bar_compute(nthr);                              // s_carry and s_cnt complete
             // ---- depth at the tile's SNP sites, for k_snp_mse
             for (uint32_t i = tid; i < tm.shi - tm.slo; i += nthr) {
                 const uint32_t s = tm.slo + i;
@@ -423,50 +504,15 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS) k_bin_tiles(BinK p) {
             for (int i = 0; i < nwarp; ++i) { int v = s_cnt[i]; if (i < wid) c_rank += v; c_count += v; }
             if (tid == 0) {
                 volatile unsigned long long* st = p.status;
-                st[t] = (1ull << 62) | (unsigned long long)c_count;   // the word carries its own payload: no fence needed
+                st[t] = (1ull << 62) | (unsigned long long)c_count;      // the word carries its own payload: no fence needed
+                atomicAdd(p.grp + (t >> 5), (1ull << 40) | (unsigned long long)c_count);
+                s_lt[it & 3] = t; s_lc[it & 3] = c_count; s_lcontig[it & 3] = c_contig; s_lfirst[it & 3] = c_first;
+                mbar_arrive(&s_cbar[it & 3]);                         // hand the tile to the look-back warp
             }
         }
 
-        // ---- row offset of the previous tile.  Tiles are dealt round-robin, so the tiles before it are all earlier
-        // rounds (their total is carried in round_base) plus the lower-numbered CTAs' tiles of its own round: warp 0
-        // reads the whole round's counts with independent loads (one L2 round trip; they were published about one
-        // tile time ago), which gives this tile's offset and the round total at once.  No CTA waits for another
-        // CTA's offset, only for its count.
-        if (p_valid && wid == 0) {
-            volatile unsigned long long* st = p.status;
-            const unsigned long long VAL = (1ull << 62) - 1;
-            const int r0 = p_t - (int)blockIdx.x;                       // first tile of that round
-            const int nr = min(G, p.n_tiles - r0);
-            long long before = 0, total = 0;
-            for (int kq = lane; kq < nr; kq += 128) {
-                unsigned long long v[4];
-                #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = (kq + 32 * u < nr) ? st[r0 + kq + 32 * u] : (1ull << 62);
-                #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    long long spins = 0;
-                    while ((v[u] >> 62) == 0) {
-                        __nanosleep(64);
-                        v[u] = st[r0 + kq + 32 * u];
-                        if (++spins > (1ll << 24)) { atomicOr(&p.err[ERR_INTERNAL], 1); break; }
-                    }
-                    const long long val = (long long)(v[u] & VAL);
-                    total += val;
-                    if (kq + 32 * u < (int)blockIdx.x) before += val;
-                }
-            }
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
-            const long long excl = round_base + before;
-            round_base += total;
-            if (lane == 0) {
-                s_prefix[it & 1] = excl;
-                if (p_first) p.contig_offset[p_contig] = excl;
-                if (p_t == p.n_tiles - 1) p.contig_offset[p.n_contigs] = excl + p_count;
-            }
-        }
+        p3_valid = pp_valid; p3_n = pp_n; p3_start = pp_start; p3_end = pp_end; p3_bin = pp_bin; p3_median = pp_median; p3_rank = pp_rank; p3_total = pp_total;
         pp_valid = p_valid; pp_n = p_n; pp_start = p_start; pp_end = p_end; pp_bin = p_bin; pp_median = p_median; pp_rank = p_rank; pp_total = p_total;
         p_valid = have; p_n = co_n; p_start = co_start; p_end = co_end; p_bin = co_bin; p_median = co_median; p_rank = c_rank; p_total = co_total;
-        p_t = t; p_contig = c_contig; p_first = c_first; p_count = c_count;
     }
 }
