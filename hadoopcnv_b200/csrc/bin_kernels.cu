@@ -56,7 +56,8 @@ struct BinK {
     int32_t *o_bin, *o_start, *o_end; float* o_median; double* o_mse; double* o_total; int32_t* o_n;
     long long capacity;
     unsigned long long* status;      // look-back words, one per tile
-    unsigned long long *grp, *grp_pre;   // per group of 32 tiles: sum + arrivals; rows before the end of the group
+    unsigned long long *grp, *sgrp, *sgrp_pre;   // per group of 32 tiles / super-group of 1024: sum + arrivals; rows before the end of the super-group
+    unsigned int warp_smem;          // bytes of shared memory per warp (tile kernel)
     unsigned int*       ticket;
     int32_t*            err;
     long long*          contig_offset;   // n_contigs + 1
@@ -237,14 +238,13 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     if (!out->bin || !out->start || !out->end || !out->median || !out->mse || !out->total || !out->n || !out->contig_offset)
         return hcnv_fail(ctx, HCNV_E_INVALID, "null output array");
 
-    // tile geometry: TB bins (= threads) per CTA; shared memory = difference array + carries + two staged chunks of records
-    int TB = P.tile_bins > 0 ? P.tile_bins : 128;
-    TB = (TB + 31) / 32 * 32;
-    if (TB > BIN_MAX_THREADS) TB = BIN_MAX_THREADS;
-    auto smem_need = [&](int tb) { return (((size_t)tb * W + 4 + tb) * 4 + 15) / 16 * 16 + (size_t)NRBUF * (RCAP + 4) * 8; };
-    while (TB > 32 && smem_need(TB) > ctx->smem_optin - 2048) TB -= 32;
-    if (smem_need(TB) > ctx->smem_optin - 2048) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1600)");
-    const size_t smem_bytes = smem_need(TB);
+    // tile geometry: one warp = one tile of 32 bins; a warp's shared-memory slice = tile records + two record chunks +
+    // the difference array of its 32 * W positions; as many warps per SM as fit
+    const int TB = 32;
+    const size_t warp_smem = ((sizeof(WarpSmem) + 15) & ~(size_t)15) + (size_t)NRBUF * (RCAP + 4) * 8 + (((size_t)32 * W + 4) * 4 + 15) / 16 * 16;
+    const int NW = (int)std::min<size_t>(BIN_MAX_WARPS, (ctx->smem_optin - 3072) / warp_smem);
+    if (NW < 1) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1700)");
+    const size_t smem_bytes = warp_smem * (size_t)NW;
 
     // pointer kinds
     int in_kind = -1;
@@ -318,7 +318,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     HCNV_CUDA(ctx, ctx->buf[B_TILEIDX].reserve(sizeof(TileRec) * (size_t)n_tiles));
     HCNV_CUDA(ctx, ctx->buf[B_SNPDEPTH].reserve(4 * (size_t)(tot_snp + 1)));
     HCNV_CUDA(ctx, ctx->buf[B_TALLY].reserve(64 * (size_t)(tot_snp + 1)));
-    HCNV_CUDA(ctx, ctx->buf[B_STATUS].reserve(8 * ((size_t)n_tiles + 2 * ((size_t)n_tiles / 32 + 1))));
+    const size_t n_status = (size_t)n_tiles + ((size_t)n_tiles / 32 + 1) + 2 * ((size_t)n_tiles / 1024 + 1);
+    HCNV_CUDA(ctx, ctx->buf[B_STATUS].reserve(8 * n_status));
     HCNV_CUDA(ctx, ctx->buf[B_MISC].reserve(4096 + 8 * (size_t)(n_contigs + 1)));
     k.contigs = ctx->buf[B_CONTIGS].as<ContigDev>();
     k.n_contigs = n_contigs; k.W = W; k.TB = TB; k.n_tiles = n_tiles; k.maxlen = maxlen;
@@ -331,7 +332,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     k.n_snp_total = tot_snp;
     k.tally = ctx->buf[B_TALLY].as<uint32_t>();
     k.status = ctx->buf[B_STATUS].as<unsigned long long>();
-    k.grp = k.status + n_tiles; k.grp_pre = k.grp + (n_tiles / 32 + 1);
+    k.grp = k.status + n_tiles; k.sgrp = k.grp + (n_tiles / 32 + 1); k.sgrp_pre = k.sgrp + (n_tiles / 1024 + 1);
+    k.warp_smem = (unsigned int)warp_smem;
     char* misc = ctx->buf[B_MISC].as<char>();
     k.err = (int32_t*)misc; k.ticket = (unsigned int*)(misc + 64); k.contig_offset = (long long*)(misc + 128);
     k.capacity = out->capacity;
@@ -353,7 +355,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     }
 
     HCNV_CUDA(ctx, cudaMemsetAsync(misc, 0, 128 + 8 * (size_t)(n_contigs + 1), ctx->stream));
-    HCNV_CUDA(ctx, cudaMemsetAsync(k.status, 0, 8 * ((size_t)n_tiles + 2 * ((size_t)n_tiles / 32 + 1)), ctx->stream));
+    HCNV_CUDA(ctx, cudaMemsetAsync(k.status, 0, 8 * n_status, ctx->stream));
     if (tot_snp) HCNV_CUDA(ctx, cudaMemsetAsync(k.tally, 0, 64 * (size_t)tot_snp, ctx->stream));
 
     KT_BEGIN(ctx, HCNV_K_TILE_INDEX);
@@ -375,12 +377,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB + 32, smem_bytes);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        const int grid = std::min(n_tiles, ctx->sm_count * per_sm);       // persistent, co-resident CTAs; tiles round-robin
-        kern<<<grid, TB + 32, smem_bytes, ctx->stream>>>(k);       // TB compute threads + the look-back warp
+        const int grid = std::min((n_tiles + NW - 1) / NW, ctx->sm_count);   // one persistent CTA per SM, NW independent warps each
+        kern<<<grid, NW * 32, smem_bytes, ctx->stream>>>(k);
         return cudaGetLastError();
     };
     if (W % 4 == 0)      HCNV_CUDA(ctx, filter ? launch(k_bin_tiles<4, true>) : launch(k_bin_tiles<4, false>));

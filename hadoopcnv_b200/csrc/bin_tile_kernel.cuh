@@ -1,30 +1,35 @@
 // bin_tile_kernel.cuh -- the persistent tile kernel of B1 (included by bin_kernels.cu after its helpers).
 //
-// One CTA = TB threads = TB bins per tile; CTAs are persistent and take tiles round-robin (tile = blockIdx.x +
-// i * gridDim.x), so everything a tile needs is known one tile ahead and nothing on the critical path waits for a
-// dependent global load:
-//   0. the 48-byte tile record written by k_tile_index (record range, SNP range, the ragged head / tail records and
-//      the predecessor's start) is TMA-prefetched two tiles ahead; contig descriptors sit in shared memory;
+// ONE WARP = ONE TILE of 32 bins (lane b owns bin b), and warps never synchronise with each other: there is no
+// CTA-wide barrier after set-up, so the LSU-heavy record phase of one warp overlaps the ALU-heavy walk of another
+// and a warp that waits for memory stalls nobody else.  Each warp owns a slice of shared memory (difference array +
+// two record chunk buffers + a ring of three tile records) and runs this loop:
+//   0. tiles are claimed in order from a global ticket (a batch per CTA, handed out through shared memory); the 48-byte
+//      tile record written by k_tile_index (record range, SNP range, the ragged head / tail records and the
+//      predecessor's start) is TMA-prefetched two tiles ahead; contig descriptors sit in shared memory: nothing on
+//      the critical path chases a dependent global load;
 //   1. the tile's slice of the sorted block stream is staged by TMA bulk copies (cp.async.bulk + mbarrier) in
-//      chunks of RCAP records through two buffers: chunk q + 1 is in flight while chunk q is processed, and chunk 0
-//      of the NEXT tile is issued before this tile's walk;
+//      chunks of RCAP records through two buffers; chunk 0 of the NEXT tile is issued before this tile's walk and
+//      the rest of its records are prefetched into L2;
 //   2. +1 / -1 shared-memory atomics per block (clamped to the tile), error flags accumulated in registers;
-//   3. ONE THREAD PER BIN walks its W entries ONCE, in relative terms (depth - depth carried into the bin): running
-//      sum written back in place, sum, min, max and a 32-bit modular bitmap of the depths seen (bit d & 31).  All of
-//      these are translation-covariant, so the walk needs no prior per-bin prefix pass: the bin totals fall out of
-//      it, a block scan turns them into carries, and the carries are applied afterwards (rotate the bitmap);
+//   3. each lane walks the W entries of its bin ONCE, in relative terms (depth - depth carried into the bin):
+//      running sum written back in place, sum, min, max and a 32-bit modular bitmap of the depths seen (bit d & 31).
+//      All of these are translation-covariant, so no prior per-bin prefix pass is needed: the bin totals fall out
+//      of the walk, a warp scan turns them into carries, and the carries are applied afterwards (rotate the bitmap);
 //   4. a bin that is covered everywhere with a depth range < 32 (almost all of them) is finished from those five
 //      numbers; anything else (gap edges, contig ends, SNP sites at uncovered positions, huge ranges) re-walks its W
 //      positions in a careful slow path;
 //   5. depth at the tile's SNP sites goes to a side array for k_snp_mse (the f64 BAF statistics are not in here);
-//   6. the tile publishes its count of non-empty bins; its global output offset is resolved AFTER the next tile's
-//      record phase (deferred decoupled look-back), so the wait for predecessors overlaps useful work.
+//   6. the tile publishes its count of non-empty bins; its global row offset is resolved two tiles later by a
+//      three-level decoupled look-back (tile / group of 32 tiles / super-group of 1024 tiles) whose four loads per
+//      lane are issued at the start of that iteration and consumed at its end: one L2 round trip, fully overlapped.
 #pragma once
 
-#define RCAP 1024                                 // records per staged chunk (8 KB)
-#define NRBUF 2                                   // chunk buffers in flight
+#define RCAP 256                                  // records per staged chunk (2 KB)
+#define NRBUF 2                                   // chunk buffers in flight per warp
 #define CTC 32                                    // contig descriptors cached in shared memory
-#define BIN_MAX_THREADS 224
+#define BIN_MAX_WARPS 16
+#define TBATCH 8                                  // consecutive tiles a CTA claims per global ticket
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -52,7 +57,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
-__device__ __forceinline__ void bar_compute(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }   // the compute warps only
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct ContigLite {                               // what a tile needs from its contig
@@ -174,99 +178,41 @@ __device__ __noinline__ int bin_slow(const int32_t* dp, int W, int carry, int dm
     return n;
 }
 
+
+struct WarpSmem {                                 // fixed part of a warp's slice, at its start (16-byte aligned)
+    TileRec  tm[3];                               // tile records, prefetched two tiles ahead
+    uint64_t rbar[NRBUF], mbar[3];
+};
+
 template <int VEC, bool FILTER>
-__global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
+__global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ __align__(16) TileRec s_tm[3];     // tile records, prefetched two tiles ahead
     __shared__ ContigLite s_ct[CTC];
-    __shared__ __align__(8) uint64_t s_rbar[NRBUF], s_mbar[3];
-    __shared__ int s_warp[BIN_MAX_THREADS / 32];
-    __shared__ int s_cnt[BIN_MAX_THREADS / 32];
-    __shared__ int s_tk[3];
-    __shared__ __align__(8) uint64_t s_cbar[4], s_pbar[4];   // tile count published / row offset resolved (ring of 4 tiles)
-    __shared__ int s_lt[4], s_lc[4], s_lcontig[4], s_lfirst[4];
-    __shared__ long long s_lpre[4];                       // tickets (tile ids) of iterations it, it + 1, it + 2
-    const int tid = threadIdx.x, nthr = blockDim.x - 32;   // compute threads == TB (a multiple of 32, at most BIN_MAX_THREADS); + the look-back warp
-    const int lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
-    const int W = p.W, TB = p.TB;
-    const int TP = TB * W;
-    int32_t* diff = reinterpret_cast<int32_t*>(smraw);                 // TP + 4 entries; entry TP sinks ends at the tile edge
-    int32_t* s_carry = diff + (TP + 4);                                // TB entries: depth carried into each bin
-    hcnv_block* recbuf = reinterpret_cast<hcnv_block*>(smraw + ((((size_t)(TP + 4 + TB)) * 4 + 15) & ~(size_t)15));   // NRBUF x (RCAP + 4) slots
+    __shared__ unsigned long long s_state;        // the CTA's current batch of tiles (see claim)
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int W = p.W;
+    const int TP = 32 * W;                                              // positions per tile
+    unsigned char* slice = smraw + (size_t)wid * p.warp_smem;
+    WarpSmem* ws = reinterpret_cast<WarpSmem*>(slice);
+    hcnv_block* recbuf = reinterpret_cast<hcnv_block*>(slice + ((sizeof(WarpSmem) + 15) & ~(size_t)15));    // NRBUF x (RCAP + 4) slots
+    int32_t* diff = reinterpret_cast<int32_t*>(recbuf + NRBUF * (RCAP + 4));                              // TP + 4 entries; entry TP sinks ends at the tile edge
     const bool ct_cached = p.n_contigs <= CTC;
 
-    if (tid == 0) {
-        for (int i = 0; i < NRBUF; ++i) mbar_init(&s_rbar[i], 1);
-        for (int i = 0; i < 3; ++i) mbar_init(&s_mbar[i], 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_cbar[i], 1); mbar_init(&s_pbar[i], 1); }
+    if (tid == 0) s_state = 0;
+    if (lane == 0) {
+        for (int i = 0; i < NRBUF; ++i) mbar_init(&ws->rbar[i], 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&ws->mbar[i], 1);
         mbar_init_fence();
     }
     if (ct_cached)
-        for (int i = tid; i < p.n_contigs; i += nthr) {
+        for (int i = tid; i < p.n_contigs; i += blockDim.x) {
             const ContigDev& g = p.contigs[i];
             ContigLite c; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
             c.length = g.length; c.n_bins_max = g.n_bins_max;
             s_ct[i] = c;
         }
-    for (int i = tid; i < nwarp; i += nthr) s_warp[i] = 0;
-    __syncthreads();
-
-    // ---- the look-back warp: resolves every tile's global row offset, off the compute warps' critical path.
-    // Two levels, so that one L2 round trip of three independent loads per lane is enough however many tiles are in
-    // flight: status[t] (count of tile t), grp[g] (atomic sum + arrival count of the 32 tiles of group g) and
-    // grp_pre[g] (rows before the end of group g, published by whoever resolves the group's last tile).  A tile's
-    // offset = nearest published group prefix + the complete groups after it + the earlier tiles of its own group.
-    // Every word carries its own payload, so no fences are needed.  A tile is resolved one tile late (when the next
-    // tile's count arrives): by then its predecessors, claimed before it, have almost always published.
-    if (wid == nwarp) {
-        const unsigned long long FLAG_PRE = 2ull << 62, VAL = (1ull << 62) - 1, GVAL = (1ull << 40) - 1;
-        volatile unsigned long long* st = p.status;
-        volatile unsigned long long* grp = p.grp;
-        volatile unsigned long long* gpre = p.grp_pre;
-        int q_t = -1, q_count = 0, q_contig = 0, q_first = 0, q_slot = 0;          // the tile waiting to be resolved
-        for (int i = 0;; ++i) {
-            const int ls = i & 3;
-            mbar_wait(&s_cbar[ls], (uint32_t)(i >> 2) & 1u);
-            const int lt = s_lt[ls], lcount = s_lc[ls], lcontig = s_lcontig[ls], lfirst = s_lfirst[ls];
-            if (q_t >= 0) {
-                const int g = q_t >> 5, r = q_t & 31;
-                long long excl = 0, spins = 0;
-                for (;;) {
-                    const unsigned long long a = (lane < r) ? st[q_t - 1 - lane] : (1ull << 62);
-                    const int gq = g - 1 - lane;
-                    const unsigned long long bq = (gq >= 0) ? grp[gq] : (32ull << 40);
-                    const unsigned long long cq = (gq >= 0) ? gpre[gq] : FLAG_PRE;
-                    const unsigned own_missing = __ballot_sync(0xffffffffu, (a >> 62) == 0);
-                    const unsigned pre = __ballot_sync(0xffffffffu, (cq >> 62) == 2);
-                    const unsigned incomplete = __ballot_sync(0xffffffffu, (bq >> 40) != 32ull);
-                    const int first_pre = pre ? (__ffs((int)pre) - 1) : 32;
-                    const unsigned need = (first_pre >= 32) ? 0xffffffffu : ((1u << first_pre) - 1u);   // groups nearer than the prefix
-                    if (!own_missing && first_pre < 32 && !(incomplete & need)) {
-                        long long contrib = (lane < r) ? (long long)(a & VAL) : 0;
-                        if (lane < first_pre) contrib += (long long)(bq & GVAL);
-                        if (lane == first_pre) contrib += (long long)(cq & VAL);
-                        #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                        excl = contrib;
-                        break;
-                    }
-                    if (++spins > (1ll << 22)) { if (lane == 0) atomicOr(&p.err[ERR_INTERNAL], 1); break; }
-                    __nanosleep(200);
-                }
-                if (lane == 0) {
-                    if (r == 31 || q_t == p.n_tiles - 1) gpre[g] = FLAG_PRE | (unsigned long long)(excl + q_count);
-                    s_lpre[q_slot] = excl;
-                    if (q_first) p.contig_offset[q_contig] = excl;
-                    if (q_t == p.n_tiles - 1) p.contig_offset[p.n_contigs] = excl + q_count;
-                    mbar_arrive(&s_pbar[q_slot]);
-                }
-                __syncwarp();
-            }
-            if (lt < 0) break;
-            q_t = lt; q_count = lcount; q_contig = lcontig; q_first = lfirst; q_slot = ls;
-        }
-        return;
-    }
+    __syncthreads();                              // the only CTA-wide barrier
 
     auto contig_of = [&](int ci) -> ContigLite {
         if (ct_cached) return s_ct[ci];
@@ -275,11 +221,11 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
         c.length = g.length; c.n_bins_max = g.n_bins_max;
         return c;
     };
-    // tid 0 only: prefetch the tile record of tile tt into ring slot `slot`
+    // lane 0 only: prefetch the tile record of tile tt into ring slot `slot`
     auto fetch_tile_rec = [&](int tt, int slot) {
-        if (tt < p.n_tiles) { fence_proxy_async(); mbar_expect_tx(&s_mbar[slot], (uint32_t)sizeof(TileRec)); tma_load_1d(&s_tm[slot], p.tile_rec + tt, (uint32_t)sizeof(TileRec), &s_mbar[slot]); }
+        if (tt < p.n_tiles) { fence_proxy_async(); mbar_expect_tx(&ws->mbar[slot], (uint32_t)sizeof(TileRec)); tma_load_1d(&ws->tm[slot], p.tile_rec + tt, (uint32_t)sizeof(TileRec), &ws->mbar[slot]); }
     };
-    // tid 0 only: start chunk q of a tile (records [lb, hi) of `blocks`) into chunk buffer `buf`
+    // lane 0 only: start chunk q of a tile (records [lb, hi) of `blocks`) into chunk buffer `buf`
     auto issue_chunk = [&](const hcnv_block* blocks, const TileRec& tm, uint32_t q, int buf) {
         const uint32_t lb = tm.lb, hi = tm.hi;
         const uint32_t a0 = (uint32_t)((reinterpret_cast<unsigned long long>(blocks) >> 3) & 1ull);
@@ -293,68 +239,91 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
         if (cnt < tb - ta) R[2 + cnt] = tm.tail;
         R[head ? 0 : 1].start0 = (int)0x80000000;                       // the slot before the first record never looks unsorted
         fence_proxy_async();
-        if (cnt) { mbar_expect_tx(&s_rbar[buf], cnt * 8u); tma_load_1d(R + 2, blocks + ta, cnt * 8u, &s_rbar[buf]); }
-        else mbar_arrive(&s_rbar[buf]);
+        if (cnt) { mbar_expect_tx(&ws->rbar[buf], cnt * 8u); tma_load_1d(R + 2, blocks + ta, cnt * 8u, &ws->rbar[buf]); }
+        else mbar_arrive(&ws->rbar[buf]);
     };
 
-    int prev_last = 0;                             // tid 0: start of the last record of the previous chunk
-    uint32_t consumed = 0;                        // chunks consumed so far by this CTA (uniform): buffer = consumed % 2, parity = (consumed / 2) & 1
-    // Tiles are claimed from an atomic ticket, in order (the look-back relies on that), two tiles ahead: the ticket
-    // for iteration it + 2 is requested at the top of iteration it and only looked at after the record phase.
-    if (tid == 0) {
-        const int t0 = (int)atomicAdd(p.ticket, 1u), t1 = (int)atomicAdd(p.ticket, 1u);
-        s_tk[0] = t0; s_tk[1] = t1;
-        fetch_tile_rec(t0, 0);
-        fetch_tile_rec(t1, 1);
-        if (t0 < p.n_tiles) {
-            mbar_wait(&s_mbar[0], 0);
-            const TileRec& tm = s_tm[0];
+    // ---- this warp's tile sequence.  Tiles are claimed in order from a global ticket (a tile's predecessors are then
+    // always in progress on warps that started earlier, which keeps the row-offset look-back short and free of lockstep),
+    // but a single counter claimed a million times per launch is a bottleneck of its own, so the CTA claims TBATCH
+    // consecutive tiles at a time and its warps take them one by one from a shared-memory word (compare-and-swap; the
+    // warp that finds the batch empty locks the word, fetches the next batch and publishes it).
+    // A warp claims two tiles ahead (the tile record has to be prefetched).
+    auto claim = [&]() -> int {                   // lane 0 only
+        const unsigned long long LOCKED = ~0ull;
+        volatile unsigned long long* S = &s_state;            // next tile of the CTA's batch << 32 | tiles left in it
+        for (;;) {
+            const unsigned long long old = *S;
+            if (old == LOCKED) { __nanosleep(20); continue; }            // somebody is fetching the next batch
+            const unsigned rem = (unsigned)old, next = (unsigned)(old >> 32);
+            if (rem > 0) {
+                if (atomicCAS(&s_state, old, ((unsigned long long)(next + 1u) << 32) | (rem - 1u)) == old)
+                    return next >= (unsigned)p.n_tiles ? p.n_tiles : (int)next;
+            } else if (atomicCAS(&s_state, old, LOCKED) == old) {
+                const unsigned base = atomicAdd(p.ticket, (unsigned)TBATCH);
+                *S = ((unsigned long long)(base + 1u) << 32) | (unsigned)(TBATCH - 1);
+                return base >= (unsigned)p.n_tiles ? p.n_tiles : (int)base;
+            }
+        }
+    };
+    int tk_cur, tk_n1;
+    {
+        int a = 0, b = 0;
+        if (lane == 0) { a = claim(); b = claim(); }
+        tk_cur = __shfl_sync(0xffffffffu, a, 0);
+        tk_n1 = __shfl_sync(0xffffffffu, b, 0);
+        if (tk_n1 < tk_cur) { const int x = tk_cur; tk_cur = tk_n1; tk_n1 = x; }      // (cannot happen: one lane claims twice in order)
+    }
+    if (lane == 0) {
+        fetch_tile_rec(tk_cur, 0);
+        fetch_tile_rec(tk_n1, 1);
+        if (tk_cur < p.n_tiles) {
+            mbar_wait(&ws->mbar[0], 0);
+            const TileRec& tm = ws->tm[0];
             if (tm.hi > tm.lb) issue_chunk(contig_of(tm.contig).blocks, tm, 0, 0);
         }
     }
-    bool finished = false;                        // tickets only grow: once one is past the end, all later ones are
+    int prev_last = 0;                            // lane 0: start of the last record of the previous chunk
+    uint32_t consumed = 0;                        // chunks consumed so far by this warp: buffer = consumed % 2, parity = (consumed / 2) & 1
 
-    // Outputs trail by two tiles: tile i's bins wait in registers (p_*) while tile i + 1 is processed, its global row
-    // offset is resolved by warp 0 at the end of iteration i + 1 (round look-back below), and the rows are written
-    // at the top of iteration i + 2 (pp_*), so no warp ever waits for another CTA.
-    bool p_valid = false, pp_valid = false, p3_valid = false;
-    int p_n = 0, p_start = 0, p_end = 0, p_bin = 0, p_median = 0, p_rank = 0;
+    // the two previous tiles: their bins wait in registers; the older one's row offset is resolved in this iteration
+    // (look-back loads at the top, one full tile time after it published; consumed at the end)
+    bool p_valid = false, q_valid = false;
+    int p_n = 0, p_start = 0, p_end = 0, p_bin = 0, p_median = 0, p_rank = 0, p_t = 0, p_count = 0, p_contig = 0, p_first = 0;
     long long p_total = 0;
-    int pp_n = 0, pp_start = 0, pp_end = 0, pp_bin = 0, pp_median = 0, pp_rank = 0;
-    long long pp_total = 0;
-    int p3_n = 0, p3_start = 0, p3_end = 0, p3_bin = 0, p3_median = 0, p3_rank = 0;
-    long long p3_total = 0;
+    int q_n = 0, q_start = 0, q_end = 0, q_bin = 0, q_median = 0, q_rank = 0, q_t = 0, q_count = 0, q_contig = 0, q_first = 0;
+    long long q_total = 0;
+    volatile unsigned long long* st = p.status;
+    volatile unsigned long long* grp = p.grp;
+    volatile unsigned long long* sgrp = p.sgrp;
+    volatile unsigned long long* sgpre = p.sgrp_pre;
+    const unsigned long long FLAG_PRE = 2ull << 62, VAL = (1ull << 62) - 1, GVAL = (1ull << 40) - 1;
 
     for (int it = 0;; ++it) {
         const int slot = it % 3;
-        int co_n = 0, co_start = 0, co_end = 0, co_bin = 0, co_median = 0;
-        long long co_total = 0;
-        int c_count = 0, c_rank = 0, c_contig = 0, c_first = 0;
-        bar_compute(nthr);                          // previous tile: everybody is done with diff / s_carry; s_prefix[(it - 1) & 1] and s_tk[slot] are set
-        const int t = finished ? p.n_tiles : s_tk[slot];
+        const int t = tk_cur;
         const bool have = t < p.n_tiles;
-        if (!have && !finished && tid == 0) { s_lt[it & 3] = -1; mbar_arrive(&s_cbar[it & 3]); }   // tell the look-back warp to leave
-        finished = !have;
-        unsigned int tk2 = 0;
-        if (tid == 0 && have) tk2 = atomicAdd(p.ticket, 1u);        // ticket of iteration it + 2; consumed after the record phase
+        if (!have && !p_valid && !q_valid) break;
+        int tk_n2 = p.n_tiles;                                        // the tile of iteration it + 2
+        if (have) { int x = 0; if (lane == 0) x = claim(); tk_n2 = __shfl_sync(0xffffffffu, x, 0); }
+        // look-back loads of the previous tile, consumed at the end of this iteration
+        unsigned long long lb_a = 0, lb_b = 0, lb_c = 0, lb_d = 0;
+        auto lookback_load = [&]() {
+            const int g = q_t >> 5, r = q_t & 31, sg = g >> 5, rg = g & 31;
+            lb_a = (lane < r) ? st[q_t - 1 - lane] : (1ull << 62);
+            lb_b = (lane < rg) ? grp[g - 1 - lane] : (32ull << 40);
+            const int sq = sg - 1 - lane;
+            lb_c = (sq >= 0) ? sgrp[sq] : (1024ull << 40);
+            lb_d = (sq >= 0) ? sgpre[sq] : FLAG_PRE;
+        };
+        if (q_valid) lookback_load();
 
-        // ---- rows of the tile before the previous one
-        if (p3_valid) mbar_wait(&s_pbar[(it - 3) & 3], (uint32_t)((it - 3) >> 2) & 1u);      // resolved by the look-back warp, normally long ago
-        if (p3_valid && p3_n > 0) {
-            const long long r = s_lpre[(it - 3) & 3] + p3_rank;
-            if (r >= p.capacity) atomicOr(&p.err[ERR_CAPACITY], 1);
-            else {
-                p.o_bin[r] = p3_bin; p.o_start[r] = p3_start; p.o_end[r] = p3_end; p.o_median[r] = (float)p3_median;
-                double2* m = reinterpret_cast<double2*>(p.o_mse + r * 6);     // k_snp_mse fills the bins that hold SNP sites
-                m[0] = make_double2(0., 0.); m[1] = make_double2(0., 0.); m[2] = make_double2(0., 0.);
-                p.o_total[r] = (double)p3_total; p.o_n[r] = p3_n;
-            }
-        }
-        if (!have && !p_valid && !pp_valid) break;
+        int co_n = 0, co_start = 0, co_end = 0, co_bin = 0, co_median = 0, c_count = 0, c_rank = 0, c_contig = 0, c_first = 0;
+        long long co_total = 0;
 
         if (have) {
-            mbar_wait(&s_mbar[slot], (uint32_t)(it / 3) & 1u);       // landed long ago (tid 0 waited on it one tile earlier)
-            const TileRec tm = s_tm[slot];
+            mbar_wait(&ws->mbar[slot], (uint32_t)(it / 3) & 1u);     // landed long ago (lane 0 waited on it one tile earlier)
+            const TileRec tm = ws->tm[slot];
             const ContigLite c = contig_of(tm.contig);
             c_contig = tm.contig;
             const int k = tm.k;
@@ -369,12 +338,13 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
             if (A > hi) A = hi;
             const uint32_t nch = (hi > lb) ? max(1u, (hi - A + RCAP - 1) / RCAP) : 0u;
             // chunk 1 can start right away: its buffer was released at the end of the previous tile's record phase
-            if (tid == 0 && nch > 1) issue_chunk(blocks, tm, 1, (int)((consumed + 1) & 1u));
+            if (lane == 0 && nch > 1) issue_chunk(blocks, tm, 1, (int)((consumed + 1) & 1u));
             // ---- clear the difference array
-            for (int i = tid * 4; i < TP + 4; i += nthr * 4) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
-            bar_compute(nthr);
+            #pragma unroll 5
+            for (int i = lane * 4; i < TP + 4; i += 128) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
+            __syncwarp();
             // ---- blocks of any length (few)
-            for (long long i = tid; i < c.n_long; i += nthr) {
+            for (long long i = lane; i < c.n_long; i += 32) {
                 hcnv_long_block r = c.longs[i];
                 long long s1 = (long long)r.start0 + 1, e1 = s1 + r.len;
                 if (r.len < 0 || r.start0 < 0 || e1 - 1 > c.length) { bad |= 2; continue; }
@@ -392,9 +362,9 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
                 const int lo_slot = (q == 0 && A > lb) ? 1 : 2;
                 const int hi_slot = 2 + (int)(tb - ta);
                 const hcnv_block* R = recbuf + (size_t)buf * (RCAP + 4);
-                mbar_wait(&s_rbar[buf], (consumed >> 1) & 1u);
+                mbar_wait(&ws->rbar[buf], (consumed >> 1) & 1u);
                 #pragma unroll 4
-                for (int j = lo_slot + tid; j < hi_slot; j += nthr) {
+                for (int j = lo_slot + lane; j < hi_slot; j += 32) {
                     const int2 raw = *reinterpret_cast<const int2*>(R + j);
                     const int prev = R[j - 1].start0;
                     const int start0 = raw.x;
@@ -408,44 +378,40 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
                     if (FILTER) { const uint32_t mq = lm >> 24; if (!((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u)) continue; }
                     atomicAdd(&diff[s], 1); atomicAdd(&diff[e], -1);  // a block that ends before the tile cancels itself in diff[0]
                 }
-                if (tid == 0) {
-                    const int first = R[lo_slot].start0;
-                    bad |= ((q == 0 ? tm.prev_start : prev_last) > first) ? 1 : 0;
-                }
                 ++consumed;
-                bar_compute(nthr);                                      // all reads of this buffer are done; its atomics are issued
-                if (tid == 0) {
+                __syncwarp();                                         // all reads of this buffer are done
+                if (lane == 0) {
+                    bad |= ((q == 0 ? tm.prev_start : prev_last) > R[lo_slot].start0) ? 1 : 0;
                     prev_last = R[hi_slot - 1].start0;
                     if (q + 2 < nch) issue_chunk(blocks, tm, q + 2, buf);
                 }
             }
-            if (nch == 0) bar_compute(nthr);                            // long-block atomics before the walk
             // ---- next tile: its record is here (prefetched a tile ago); start its first chunk, prefetch the record after it
-            if (tid == 0) {
-                const int tn = s_tk[(it + 1) % 3];
+            if (lane == 0) {
+                const int tn = tk_n1;
                 if (tn < p.n_tiles) {
                     const int ns = (it + 1) % 3;
-                    mbar_wait(&s_mbar[ns], (uint32_t)((it + 1) / 3) & 1u);
-                    const TileRec& tn_rec = s_tm[ns];
+                    mbar_wait(&ws->mbar[ns], (uint32_t)((it + 1) / 3) & 1u);
+                    const TileRec& tn_rec = ws->tm[ns];
                     if (tn_rec.hi > tn_rec.lb) {
-                        const hcnv_block* nb = contig_of(tn_rec.contig).blocks;
-                        issue_chunk(nb, tn_rec, 0, (int)(consumed & 1u));
+                        const hcnv_block* nbk = contig_of(tn_rec.contig).blocks;
+                        issue_chunk(nbk, tn_rec, 0, (int)(consumed & 1u));
                         // the rest of its records: into L2 now, so that the later chunks are L2 hits
-                        const unsigned long long pa = (reinterpret_cast<unsigned long long>(nb + tn_rec.lb) + 15ull) & ~15ull;
-                        const unsigned long long pe = reinterpret_cast<unsigned long long>(nb + tn_rec.hi) & ~15ull;
+                        const unsigned long long pa = (reinterpret_cast<unsigned long long>(nbk + tn_rec.lb) + 15ull) & ~15ull;
+                        const unsigned long long pe = reinterpret_cast<unsigned long long>(nbk + tn_rec.hi) & ~15ull;
                         if (pe > pa + (unsigned long long)RCAP * 8ull)
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa + (unsigned long long)RCAP * 8ull), "r"((uint32_t)(pe - pa - (unsigned long long)RCAP * 8ull)) : "memory");
                     }
                 }
-                s_tk[(it + 2) % 3] = (int)tk2;
-                fetch_tile_rec((int)tk2, (it + 2) % 3);
+                fetch_tile_rec(tk_n2, (it + 2) % 3);
             }
             if (bad & 1) atomicOr(&p.err[ERR_UNSORTED], 1);
             if (bad & 2) atomicOr(&p.err[ERR_RANGE], 1);
+            __syncwarp();                                             // every lane's atomics are done before the walk
 
-            // ---- the walk: one thread per bin, relative to the depth carried into the bin
-            const int b = tid;
-            const int nb_tile = min(TB, c.n_bins_max - k * TB);
+            // ---- the walk: one lane per bin, relative to the depth carried into the bin
+            const int b = lane;
+            const int nb_tile = min(32, c.n_bins_max - k * 32);
             int32_t* dp = diff + b * W;
             int rel_end = 0, mn = 0, mx = 0; long long rsum = 0; uint32_t mask = 0;
             if (b < nb_tile) {
@@ -458,12 +424,8 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
             int incl = rel_end;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            if (lane == 31) s_warp[wid] = incl;
-            bar_compute(nthr);
-            int woff = 0;
-            for (int i = 0; i < wid; ++i) woff += s_warp[i];
-            const int carry = incl - rel_end + woff;
-            s_carry[b] = carry;
+            const int carry = incl - rel_end;
+            __syncwarp();                                             // the walk's stores are visible to the other lanes (SNP sites)
 
             // ---- finish the bin
             if (b < nb_tile) {
@@ -490,29 +452,76 @@ __global__ void __launch_bounds__(BIN_MAX_THREADS + 32) k_bin_tiles(BinK p) {
                     }
                 }
             }
-            // ---- rank among the tile's non-empty bins; publish the tile's count for the round look-back
+            // ---- rank among the tile's non-empty bins; publish the tile's count for the look-back
             const unsigned ball = __ballot_sync(0xffffffffu, co_n > 0);
-            if (lane == 0) s_cnt[wid] = __popc(ball);
-            bar_compute(nthr);                              // s_carry and s_cnt complete
-            // ---- depth at the tile's SNP sites, for k_snp_mse
-            for (uint32_t i = tid; i < tm.shi - tm.slo; i += nthr) {
-                const uint32_t s = tm.slo + i;
-                const int off = __ldg(&c.snp_pos[s]) - T0;
-                if (off >= 0 && off < TP) p.snp_depth[c.snp_base + s] = s_carry[off / W] + diff[off];
-            }
+            c_count = __popc(ball);
             c_rank = __popc(ball & ((1u << lane) - 1u));
-            for (int i = 0; i < nwarp; ++i) { int v = s_cnt[i]; if (i < wid) c_rank += v; c_count += v; }
-            if (tid == 0) {
-                volatile unsigned long long* st = p.status;
-                st[t] = (1ull << 62) | (unsigned long long)c_count;      // the word carries its own payload: no fence needed
+            if (lane == 0) {
+                st[t] = (1ull << 62) | (unsigned long long)c_count;      // every word carries its own payload: no fences needed
                 atomicAdd(p.grp + (t >> 5), (1ull << 40) | (unsigned long long)c_count);
-                s_lt[it & 3] = t; s_lc[it & 3] = c_count; s_lcontig[it & 3] = c_contig; s_lfirst[it & 3] = c_first;
-                mbar_arrive(&s_cbar[it & 3]);                         // hand the tile to the look-back warp
+                atomicAdd(p.sgrp + (t >> 10), (1ull << 40) | (unsigned long long)c_count);
             }
+            // ---- depth at the tile's SNP sites, for k_snp_mse
+            for (uint32_t i0 = 0; i0 < tm.shi - tm.slo; i0 += 32) {
+                const uint32_t s = tm.slo + i0 + lane;
+                const bool valid = s < tm.shi;
+                const int off = valid ? __ldg(&c.snp_pos[s]) - T0 : -1;
+                const bool ok = off >= 0 && off < TP;
+                const int bb = ok ? off / W : 0;
+                const int cv = __shfl_sync(0xffffffffu, carry, bb);
+                if (ok) p.snp_depth[c.snp_base + s] = cv + diff[off];
+            }
+            __syncwarp();                                             // done with diff before the next tile clears it
         }
 
-        p3_valid = pp_valid; p3_n = pp_n; p3_start = pp_start; p3_end = pp_end; p3_bin = pp_bin; p3_median = pp_median; p3_rank = pp_rank; p3_total = pp_total;
-        pp_valid = p_valid; pp_n = p_n; pp_start = p_start; pp_end = p_end; pp_bin = p_bin; pp_median = p_median; pp_rank = p_rank; pp_total = p_total;
+        // ---- row offset of the previous tile: three-level decoupled look-back over the ticket order.  Its offset =
+        // nearest published super-group prefix + the complete super-groups after it + the complete groups of its own
+        // super-group before its group + the earlier tiles of its own group.  The four loads were issued at the top of
+        // this iteration (one tile time after the tile published), so normally everything is there at first look.
+        if (q_valid) {
+            const int g = q_t >> 5, r = q_t & 31, rg = g & 31;
+            long long excl = 0, spins = 0;
+            for (;;) {
+                const unsigned own_missing = __ballot_sync(0xffffffffu, (lb_a >> 62) == 0);
+                const unsigned grp_incomplete = __ballot_sync(0xffffffffu, (lb_b >> 40) != 32ull);
+                const unsigned pre = __ballot_sync(0xffffffffu, (lb_d >> 62) == 2);
+                const unsigned sg_incomplete = __ballot_sync(0xffffffffu, (lb_c >> 40) != 1024ull);
+                const int first_pre = pre ? (__ffs((int)pre) - 1) : 32;
+                const unsigned need = (first_pre >= 32) ? 0xffffffffu : ((1u << first_pre) - 1u);   // super-groups nearer than the prefix
+                if (!own_missing && !grp_incomplete && first_pre < 32 && !(sg_incomplete & need)) {
+                    long long contrib = (lane < r) ? (long long)(lb_a & VAL) : 0;
+                    if (lane < rg) contrib += (long long)(lb_b & GVAL);
+                    if (lane < first_pre) contrib += (long long)(lb_c & GVAL);
+                    if (lane == first_pre) contrib += (long long)(lb_d & VAL);
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                    excl = contrib;
+                    break;
+                }
+                if (++spins > (1ll << 22)) { if (lane == 0) atomicOr(&p.err[ERR_INTERNAL], 1); break; }
+                __nanosleep(100);
+                lookback_load();
+            }
+            if (lane == 0) {
+                if ((q_t & 1023) == 1023) sgpre[q_t >> 10] = FLAG_PRE | (unsigned long long)(excl + q_count);
+                if (q_first) p.contig_offset[q_contig] = excl;
+                if (q_t == p.n_tiles - 1) p.contig_offset[p.n_contigs] = excl + q_count;
+            }
+            if (q_n > 0) {
+                const long long r_ = excl + q_rank;
+                if (r_ >= p.capacity) atomicOr(&p.err[ERR_CAPACITY], 1);
+                else {
+                    p.o_bin[r_] = q_bin; p.o_start[r_] = q_start; p.o_end[r_] = q_end; p.o_median[r_] = (float)q_median;
+                    double2* m = reinterpret_cast<double2*>(p.o_mse + r_ * 6);     // k_snp_mse fills the bins that hold SNP sites
+                    m[0] = make_double2(0., 0.); m[1] = make_double2(0., 0.); m[2] = make_double2(0., 0.);
+                    p.o_total[r_] = (double)q_total; p.o_n[r_] = q_n;
+                }
+            }
+        }
+        q_valid = p_valid; q_n = p_n; q_start = p_start; q_end = p_end; q_bin = p_bin; q_median = p_median; q_rank = p_rank; q_total = p_total;
+        q_t = p_t; q_count = p_count; q_contig = p_contig; q_first = p_first;
         p_valid = have; p_n = co_n; p_start = co_start; p_end = co_end; p_bin = co_bin; p_median = co_median; p_rank = c_rank; p_total = co_total;
+        p_t = t; p_count = c_count; p_contig = c_contig; p_first = c_first;
+        tk_cur = tk_n1; tk_n1 = tk_n2;
     }
 }
