@@ -25,7 +25,9 @@
 //      lane are issued at the start of that iteration and consumed at its end: one L2 round trip, fully overlapped.
 #pragma once
 
+#ifndef RCAP
 #define RCAP 256                                  // records per staged chunk (2 KB)
+#endif
 #define NRBUF 2                                   // chunk buffers in flight per warp
 #define CTC 32                                    // contig descriptors cached in shared memory
 #define BIN_MAX_WARPS 16
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
         const bool head = (q == 0 && A > lb);
         if (head) R[1] = tm.head;
         if (cnt < tb - ta) R[2 + cnt] = tm.tail;
-        R[head ? 0 : 1].start0 = (int)0x80000000;                       // the slot before the first record never looks unsorted
+        R[head ? 0 : 1].start0 = -1;                                    // the slot before the first record never looks unsorted
         fence_proxy_async();
         if (cnt) { mbar_expect_tx(&ws->rbar[buf], cnt * 8u); tma_load_1d(R + 2, blocks + ta, cnt * 8u, &ws->rbar[buf]); }
         else mbar_arrive(&ws->rbar[buf]);
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
                 const int hi_slot = 2 + (int)(tb - ta);
                 const hcnv_block* R = recbuf + (size_t)buf * (RCAP + 4);
                 mbar_wait(&ws->rbar[buf], (consumed >> 1) & 1u);
+                int acc_u = 0, acc_r = 0;
                 #pragma unroll 4
                 for (int j = lo_slot + lane; j < hi_slot; j += 32) {
                     const int2 raw = *reinterpret_cast<const int2*>(R + j);
@@ -370,14 +373,17 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
                     const int start0 = raw.x;
                     const uint32_t lm = (uint32_t)raw.y;
                     const int len = (int)(lm & 0xFFFFFFu);
-                    // blocks are <= 4095 long, so nothing here can overflow once the range checks hold
-                    bad |= (prev > start0) ? 1 : 0;
-                    bad |= (start0 < 0 || start0 > length - len || len > maxlen) ? 2 : 0;
+                    // sign-bit accumulators (one OR per test, looked at once per tile): bad order if start0 - prev < 0 (prev is
+                    // -1 in front of the first record; a start0 that could overflow this is out of range anyway), bad range if
+                    // start0 < 0, the room after the block length - len - start0 < 0, or maxlen - len < 0
+                    acc_u |= start0 - prev;
+                    acc_r |= start0 | (length - len - start0) | (maxlen - len);
                     int s = start0 - T0m1, e = s + len;
                     s = min(max(s, 0), TP); e = min(max(e, 0), TP);   // clamped: memory-safe whatever the record says
                     if (FILTER) { const uint32_t mq = lm >> 24; if (!((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u)) continue; }
                     atomicAdd(&diff[s], 1); atomicAdd(&diff[e], -1);  // a block that ends before the tile cancels itself in diff[0]
                 }
+                bad |= (acc_u < 0 ? 1 : 0) | (acc_r < 0 ? 2 : 0);
                 ++consumed;
                 __syncwarp();                                         // all reads of this buffer are done
                 if (lane == 0) {
@@ -482,13 +488,10 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
             const int g = q_t >> 5, r = q_t & 31, rg = g & 31;
             long long excl = 0, spins = 0;
             for (;;) {
-                const unsigned own_missing = __ballot_sync(0xffffffffu, (lb_a >> 62) == 0);
-                const unsigned grp_incomplete = __ballot_sync(0xffffffffu, (lb_b >> 40) != 32ull);
                 const unsigned pre = __ballot_sync(0xffffffffu, (lb_d >> 62) == 2);
-                const unsigned sg_incomplete = __ballot_sync(0xffffffffu, (lb_c >> 40) != 1024ull);
-                const int first_pre = pre ? (__ffs((int)pre) - 1) : 32;
-                const unsigned need = (first_pre >= 32) ? 0xffffffffu : ((1u << first_pre) - 1u);   // super-groups nearer than the prefix
-                if (!own_missing && !grp_incomplete && first_pre < 32 && !(sg_incomplete & need)) {
+                const int first_pre = pre ? (__ffs((int)pre) - 1) : 32;      // nearest published super-group prefix
+                const bool lane_ok = (lb_a >> 62) != 0 && (lb_b >> 40) == 32ull && ((lb_c >> 40) == 1024ull || lane >= first_pre);
+                if (first_pre < 32 && __all_sync(0xffffffffu, lane_ok)) {
                     long long contrib = (lane < r) ? (long long)(lb_a & VAL) : 0;
                     if (lane < rg) contrib += (long long)(lb_b & GVAL);
                     if (lane < first_pre) contrib += (long long)(lb_c & GVAL);
