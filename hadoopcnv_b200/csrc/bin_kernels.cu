@@ -26,6 +26,7 @@ struct ContigDev {
     const uint32_t*        obs;
     long long n_blocks, n_long, n_snp, n_obs;
     long long snp_base;     // row offset of this contig in the tally table
+    long long obs_base32;   // start of this contig's observations in the launch-wide index space (each contig rounded up to 32)
     int32_t   length;       // positions 1..length
     int32_t   n_bins_max;   // length / W + 1
     int32_t   tile_base;    // global id of this contig's first tile
@@ -39,7 +40,7 @@ struct __align__(16) TileRec {                   // 48 bytes, TMA-prefetched by 
     int32_t  contig, k;                          // contig id; tile number within the contig
     uint32_t lb, hi;                             // record range [lb, hi): look-back records + records that start in the tile
     uint32_t slo, shi;                           // SNP sites of the tile
-    int32_t  prev_start, pad;                    // start0 of record lb - 1 (INT_MIN if none): sortedness across tiles
+    int32_t  prev_start, pad;                    // start0 of record lb - 1 (INT_MIN if none): sortedness across tiles; pad = 1: inconsistent searches
     hcnv_block head, tail;                       // records lb and hi - 1 (a ragged end cannot go through a 16-byte bulk copy)
 };
 
@@ -80,32 +81,58 @@ __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* a, long long 
     return (uint32_t)lo;
 }
 
-// One thread per tile: which contig, which record range (own + look-back), which SNP range.
-__global__ void k_tile_index(BinK p) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.n_tiles) return;
-    int lo = 0, hi = p.n_contigs - 1;
-    while (lo < hi) {                        // last contig with tile_base <= t
-        int mid = (lo + hi + 1) >> 1;
-        if (p.contigs[mid].tile_base <= t) lo = mid; else hi = mid - 1;
-    }
-    const ContigDev c = p.contigs[lo];
-    int k = t - c.tile_base;
-    long long TP = (long long)p.TB * p.W;
-    long long T0 = (long long)k * TP;        // first 1-based position of the tile (position 0 never holds a read)
-    long long T1 = T0 + TP;
-    // a block with 0-based start s covers 1-based positions s+1 .. s+len
-    // own blocks:      T0 <= s+1 < T1   <=>  T0-1 <= s < T1-1
-    // look-back blocks: s+1 >= T0 - maxlen
-    long long k_hi = T1 - 1, k_lb = T0 - 1 - p.maxlen;
+// One thread per tile: which contig, which record range (own + look-back), which SNP range.  Two full binary searches
+// per tile (first record / first SNP site at or after the tile's first position); the ends are the next tile's
+// beginnings (shared memory), and the look-back start is a short gallop backwards from the tile's first record.
+__global__ void __launch_bounds__(256) k_tile_index(BinK p) {
+    __shared__ uint32_t s_lo[257], s_slo[257];
+    const int t0 = blockIdx.x * 256;
+    const long long TP = (long long)p.TB * p.W;
     auto clampk = [](long long v) { return (int32_t)(v < -2147483647LL ? -2147483647LL : (v > 2147483647LL ? 2147483647LL : v)); };
+    int my_contig = 0, my_k = 0;
+    for (int slot = threadIdx.x; slot < 257; slot += 256) {
+        const int t = t0 + slot;
+        if (t >= p.n_tiles) { s_lo[slot] = 0; s_slo[slot] = 0; continue; }
+        int lo = 0, hi = p.n_contigs - 1;
+        while (lo < hi) {                        // last contig with tile_base <= t
+            int mid = (lo + hi + 1) >> 1;
+            if (p.contigs[mid].tile_base <= t) lo = mid; else hi = mid - 1;
+        }
+        const ContigDev& c = p.contigs[lo];
+        const int k = t - c.tile_base;
+        const long long T0 = (long long)k * TP;  // first 1-based position of the tile (position 0 never holds a read)
+        // a block with 0-based start s covers 1-based positions s+1 .. s+len: it starts in the tile iff T0-1 <= s < T0+TP-1
+        s_lo[slot] = (k == 0) ? 0u : lower_bound_blocks(c.blocks, c.n_blocks, clampk(T0 - 1));
+        s_slo[slot] = (k == 0) ? 0u : lower_bound_i32(c.snp_pos, c.n_snp, clampk(T0));
+        if (slot < 256) { my_contig = lo; my_k = k; }
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t >= p.n_tiles) return;
+    const ContigDev& c = p.contigs[my_contig];
+    const int k = my_k;
+    const bool last = (k == c.n_tiles - 1);
     TileRec r;
-    r.contig = lo; r.k = k; r.pad = 0;
-    r.hi = (k == c.n_tiles - 1) ? (uint32_t)c.n_blocks : lower_bound_blocks(c.blocks, c.n_blocks, clampk(k_hi));
-    r.lb = (k == 0) ? 0u : lower_bound_blocks(c.blocks, c.n_blocks, clampk(k_lb));
-    r.slo = (k == 0) ? 0u : lower_bound_i32(c.snp_pos, c.n_snp, clampk(T0));
-    r.shi = (k == c.n_tiles - 1) ? (uint32_t)c.n_snp : lower_bound_i32(c.snp_pos, c.n_snp, clampk(T1));
+    r.contig = my_contig; r.k = k; r.pad = 0;
+    const uint32_t lo = s_lo[threadIdx.x];
+    r.hi = last ? (uint32_t)c.n_blocks : s_lo[threadIdx.x + 1];
+    r.slo = s_slo[threadIdx.x];
+    r.shi = last ? (uint32_t)c.n_snp : s_slo[threadIdx.x + 1];
     if (r.shi < r.slo) r.shi = r.slo;                        // unsorted SNP table: k_snp_mse reports it
+    // look-back: blocks that start before the tile but may reach into it, s + 1 >= T0 - maxlen
+    uint32_t lb = lo;
+    if (lo > 0) {
+        const int32_t key = clampk((long long)k * TP - 1 - p.maxlen);
+        uint32_t low = lo, step = 16;
+        while (low > 0) {
+            low = (low > step) ? low - step : 0u;
+            if (__ldg(&c.blocks[low].start0) < key) break;
+            step <<= 1;
+        }
+        lb = low + lower_bound_blocks(c.blocks + low, (long long)(lo - low), key);
+    }
+    r.lb = lb;
+    if (r.hi < r.lb) { r.hi = r.lb; r.pad = 1; }             // only unsorted blocks do this: the tile kernel reports it
     r.prev_start = (r.lb > 0) ? __ldg(&c.blocks[r.lb - 1].start0) : (int)0x80000000;
     hcnv_block z; z.start0 = 0; z.len_mapq = 0;
     r.head = (r.hi > r.lb) ? c.blocks[r.lb] : z;
@@ -116,14 +143,22 @@ __global__ void k_tile_index(BinK p) {
 // Allele tallies at SNP sites: tally[snp][base4] += 1 (AlleleDepthWindowReducer's per-allele map, Reducers.java:381-391).
 // Observations arrive in block order, so the 32 consecutive observations of a warp name only a handful of distinct
 // (site, base) pairs: the warp elects a leader per distinct value and adds the multiplicity with ONE global atomic.
-__global__ void __launch_bounds__(256) k_tally(const uint32_t* __restrict__ obs, long long n_obs, long long n_snp,
-                                               uint32_t* __restrict__ tally, int32_t* err) {
+__global__ void __launch_bounds__(256) k_tally(BinK p, long long n_obs_total) {
     const int lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n_obs; i0 += stride) {
-        const long long i = i0 + lane;
-        const bool valid = i < n_obs;
-        const uint32_t o = valid ? __ldg(&obs[i]) : 0u;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    // all contigs in one launch: groups of 32 observations never straddle contigs (each contig's share is rounded up)
+    for (long long g0 = warp * 32; g0 < n_obs_total; g0 += n_warps * 32) {
+        int lo = 0, hi = p.n_contigs - 1;
+        while (lo < hi) {                        // last contig with obs_base32 <= g0
+            int mid = (lo + hi + 1) >> 1;
+            if (p.contigs[mid].obs_base32 <= g0) lo = mid; else hi = mid - 1;
+        }
+        const ContigDev& c = p.contigs[lo];
+        const long long i = g0 - c.obs_base32 + lane;
+        const bool valid = i < c.n_obs;
+        const uint32_t o = valid ? __ldg(&c.obs[i]) : 0u;
+        uint32_t* tally = p.tally + 16 * (size_t)c.snp_base;
         uint32_t remaining = __ballot_sync(0xffffffffu, valid);
         while (remaining) {
             const int leader = __ffs((int)remaining) - 1;
@@ -131,7 +166,7 @@ __global__ void __launch_bounds__(256) k_tally(const uint32_t* __restrict__ obs,
             const uint32_t same = __ballot_sync(0xffffffffu, o == v) & remaining;
             if (lane == leader) {
                 const long long idx = (long long)(v >> 4);
-                if (idx >= n_snp) atomicOr(&err[ERR_RANGE], 1);
+                if (idx >= c.n_snp) atomicOr(&p.err[ERR_RANGE], 1);
                 else atomicAdd(&tally[(size_t)idx * 16 + (v & 15u)], (uint32_t)__popc(same));
             }
             remaining &= ~same;
@@ -242,7 +277,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     // the difference array of its 32 * W positions; as many warps per SM as fit
     const int TB = 32;
     const size_t warp_smem = ((sizeof(WarpSmem) + 15) & ~(size_t)15) + (size_t)NRBUF * (RCAP + 4) * 8 + (((size_t)32 * W + 4) * 4 + 15) / 16 * 16;
-    const int NW = (int)std::min<size_t>(BIN_MAX_WARPS, (ctx->smem_optin - 3072) / warp_smem);
+    int NW = (int)std::min<size_t>(BIN_MAX_WARPS, (ctx->smem_optin - 3072) / warp_smem);
+    if (P.tile_bins > 0 && P.tile_bins < NW) NW = P.tile_bins;          // tuning knob: fewer warps per SM
     if (NW < 1) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1700)");
     const size_t smem_bytes = warp_smem * (size_t)NW;
 
@@ -284,7 +320,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         HCNV_CUDA(ctx, ctx->buf[B_IN_SNPZYG].reserve((size_t)tot_snp + 16 * n_contigs));
         HCNV_CUDA(ctx, ctx->buf[B_IN_OBS].reserve(4 * (size_t)tot_obs));
     }
-    long long ob = 0, ol = 0, os = 0, oo = 0;
+    long long ob = 0, ol = 0, os = 0, oo = 0, obs32_total = 0;
     int tile_base = 0;
     for (int c = 0; c < n_contigs; ++c) {
         const hcnv_contig_input& ci = contigs[c];
@@ -305,6 +341,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             if ((rc = stage_in(ctx, in_kind, ci.obs, ci.n_obs, const_cast<uint32_t*>(d.obs)))) return rc;
         }
         d.n_blocks = ci.n_blocks; d.n_long = ci.n_long; d.n_snp = ci.n_snp; d.n_obs = ci.n_obs;
+        d.obs_base32 = obs32_total; obs32_total += (ci.n_obs + 31) / 32 * 32;
         d.snp_base = os; d.length = ci.length; d.n_bins_max = ci.length / W + 1;
         d.tile_base = tile_base; d.n_tiles = (d.n_bins_max + TB - 1) / TB;
         tile_base += d.n_tiles;
@@ -363,11 +400,11 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     KT_END(ctx, HCNV_K_TILE_INDEX);
     ctx->launches++;
     KT_BEGIN(ctx, HCNV_K_TALLY);
-    for (int c = 0; c < n_contigs; ++c) {
-        if (hc[c].n_obs == 0) continue;
-        long long nb = (hc[c].n_obs + 255) / 256;
-        int grid = (int)std::min<long long>(nb, (long long)ctx->sm_count * 16);
-        k_tally<<<grid, 256, 0, ctx->stream>>>(hc[c].obs, hc[c].n_obs, hc[c].n_snp, k.tally + 16 * (size_t)hc[c].snp_base, k.err);
+    if (tot_obs) {
+        const long long nb = (obs32_total + 255) / 256;
+        const int grid = (int)std::min<long long>(nb, (long long)ctx->sm_count * 16);
+        k_tally<<<grid, 256, 0, ctx->stream>>>(k, obs32_total);
+        HCNV_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
     }
     KT_END(ctx, HCNV_K_TALLY);

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
             const long long T1l = (long long)T0 + TP;
             const uint32_t lb = tm.lb, hi = tm.hi;
             const hcnv_block* __restrict__ blocks = c.blocks;
-            int bad = (hi < lb) ? 1 : 0;                              // bit 0: unsorted, bit 1: out of range
+            int bad = (hi < lb || tm.pad) ? 1 : 0;                    // bit 0: unsorted, bit 1: out of range
             const uint32_t a0 = (uint32_t)((reinterpret_cast<unsigned long long>(blocks) >> 3) & 1ull);
             uint32_t A = lb + ((a0 + lb) & 1u);
             if (A > hi) A = hi;

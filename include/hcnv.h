@@ -102,7 +102,7 @@ typedef struct {
     int32_t bin_width;                  /* Constants.bin_width (Constants.java:33), default 100 */
     int32_t max_block_len;              /* upper bound of len over the short blocks (<= HCNV_SHORT_MAX); 0 = HCNV_SHORT_MAX */
     double  mapping_quality_threshold;  /* Constants.mapping_quality_threshold (Constants.java:21), default 0 */
-    int32_t tile_bins;                  /* tuning: bins per CTA tile, 0 = default */
+    int32_t tile_bins;                  /* tuning: cap on warps (= concurrent 32-bin tiles) per SM, 0 = as many as fit */
     int32_t flags;                      /* reserved, 0 */
 } hcnv_bin_params;
 void hcnv_bin_params_default(hcnv_bin_params* p);
