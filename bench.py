@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--tile-bins", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true", help="debug: skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="worker contexts of the end-to-end leg")
     return ap.parse_args()
 
 
@@ -316,32 +317,42 @@ def run_b200(args):
             host_contigs.append(hc)
             h2d += c.blocks.numel() * 4 + c.long_blocks.numel() * 4 + c.snp_pos1.numel() * 4 + c.snp_zyg.numel() + c.obs.numel() * 4
         torch.cuda.synchronize()
-        # results.txt columns: start, end, scaled, state, cn, mse[6] (Hmm.java:479-490)
-        h_i32 = torch.empty((4, cap), dtype=torch.int32, pin_memory=True)
-        h_f32 = torch.empty((7, cap), dtype=torch.float32, pin_memory=True)
+        # results.txt columns: start, end, scaled, state, cn, mse[6] (Hmm.java:479-490), per chromosome, into pinned arrays.
+        # The call a user makes: GenomePipeline.run = per chromosome hcnv_bin_contigs -> hcnv_bins_to_hmm_input ->
+        # hcnv_segment_batch -> D2H, on a few worker threads (one Context each) so PCIe runs both ways behind the kernels.
+        from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
+        pipe = GenomePipeline(local, workers=args.e2e_workers)
+        gout = GenomeOutput([c.length for c in contigs], W)
+        cnames = [c.name for c in contigs]
         d2h = 0
+        e2e_state = {}
 
         def step_e2e():
             nonlocal d2h
-            r, m32, _ = hot_path(host_contigs)
-            nb = len(r)
-            with torch.cuda.stream(stream):
-                h_i32[0, :nb].copy_(r.start, non_blocking=True); h_i32[1, :nb].copy_(r.end, non_blocking=True)
-                h_i32[2, :nb].copy_(seg_state[:nb], non_blocking=True); h_i32[3, :nb].copy_(seg_cn[:nb], non_blocking=True)
-                h_f32[0, :nb].copy_(seg_scaled[:nb], non_blocking=True)
-                h_f32[1:7].view(-1)[: nb * 6].copy_(m32.reshape(-1), non_blocking=True)
-            stream.synchronize()
-            d2h = nb * (4 * 5 + 24)
+            rs = pipe.run(host_contigs, cnames, gout, bin_width=W, max_block_len=READ_LEN, lambda1=LAMBDA1, lambda2=LAMBDA2)
+            d2h = sum(r.n_bins for r in rs) * gout.bytes_per_bin
+            e2e_state["rs"] = rs
 
         for _ in range(2):
             step_e2e()
-        ms_e2e, ms_e2e_wall = timed(step_e2e, max(2, min(args.steps, 3)))
+        l0 = pipe.kernel_launches
+        n_e2e = max(2, min(args.steps, 3))
+        ms_e2e, ms_e2e_wall = timed(step_e2e, n_e2e)
+        e2e_launches = (pipe.kernel_launches - l0) // n_e2e
+        # the end-to-end leg returns the same calls as the resident leg (same inputs): states of every chromosome
+        for i, r in enumerate(e2e_state["rs"]):
+            a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
+            assert r.n_bins == b - a, "e2e / resident bin count mismatch on %s" % r.name
+            got = gout.i32[2, r.offset:r.offset + r.n_bins]
+            assert bool((got == seg_state[a:b].cpu()).all()), "e2e / resident state mismatch on %s" % r.name
         t2 = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t2)
         e2e = {"value": g_reads / (ms_e2e_wall / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(t2[0]), "d2h_bytes_per_step": int(t2[1]),
-               "ms_per_step": ms_e2e_wall, "device_ms_per_step": ms_e2e,
-               "note": "host pinned inputs through Context.bin_contigs -> bins_to_hmm_input -> segment_batch; results.txt columns copied back"}
+               "ms_per_step": ms_e2e_wall, "workers": args.e2e_workers, "gpu_launches_per_step": int(e2e_launches),
+               "note": "pinned host inputs -> GenomePipeline.run (per chromosome: hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> "
+                       "hcnv_segment_batch on %d worker contexts) -> results.txt columns in pinned host arrays" % args.e2e_workers}
+        pipe.close()
 
     # ---- roofline of the dominant kernel (and of the binning kernel), from live CUDA-event timings
     peaks = {}
