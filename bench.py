@@ -92,17 +92,6 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def lpt_partition(weights, n_parts):
-    """Longest-processing-time assignment of contigs to ranks."""
-    order = sorted(range(len(weights)), key=lambda i: -weights[i])
-    loads, parts = [0.0] * n_parts, [[] for _ in range(n_parts)]
-    for i in order:
-        r = loads.index(min(loads))
-        parts[r].append(i)
-        loads[r] += weights[i]
-    return [sorted(p) for p in parts]
-
-
 def contig_weights(scale):
     from hadoopcnv_b200 import synth
     shape = synth.hg19_shape()
@@ -214,7 +203,8 @@ def run_b200(args):
 
     # ---- the workload: one 30X hg19-shaped genome, chromosome-sharded across ranks (LPT by non-N bp)
     names, w = contig_weights(args.scale)
-    mine = lpt_partition(w, world)[rank]
+    from hadoopcnv_b200 import sharding
+    mine = sharding.partition_contigs(w, world)[rank]
     t_gen = time.perf_counter()
     contigs = synth.make_genome(coverage=args.coverage, seed=SEED, device=dev, contigs=[names[i] for i in mine], scale=args.scale)
     torch.cuda.synchronize()
@@ -295,6 +285,11 @@ def run_b200(args):
     res = state["res"]
     n_bins = len(res)
     final_losses = [float(c["final_loss"]) for c in state["calls"]]
+    # the only exchange of the sharded path: per-chromosome summaries to rank 0 (no data-path collective)
+    local_summary = {contigs[i].name: dict(rank=rank, n_bins=int(res.contig_offset[i + 1] - res.contig_offset[i])) for i in range(len(contigs))}
+    for c_, fl in zip([c for i, c in enumerate(contigs) if res.contig_offset[i + 1] > res.contig_offset[i]], final_losses):
+        local_summary[c_.name]["final_loss"] = fl
+    summary = sharding.gather_summaries(local_summary, rank, world)
 
     # cross-rank totals (the only collective: summary statistics)
     tot = torch.tensor([n_reads, n_bins, n_blocks, n_obs, n_snp, launches, n_long], dtype=torch.float64, device=dev)
@@ -411,7 +406,7 @@ def run_b200(args):
             "reads_per_s_binned": g_reads / (sum(kavg.get(k_, 0) for k_ in ("tile_index", "tally", "bin_tiles")) / 1e3) if kavg.get("bin_tiles") else None,
             "kernel_ms": kavg, "gpu_launches": g_launches, "clocks": clock_info,
             "roofline": roofline, "roofline_binning": roofline_binning, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "checks": {"final_loss_sum_rank0": float(np.sum(final_losses)), "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
+            "checks": {"final_loss_sum": float(np.sum([v.get("final_loss", 0.0) for v in summary.values()])), "chromosomes": len(summary), "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
         }
         print(json.dumps(line))
     sys.stdout.flush()
