@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--tile-bins", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true", help="debug: skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--block-format", default="compact", choices=["compact", "records"],
+                    help="compact: 4-byte delta-coded block stream (include/hcnv.h hcnv_cblock); records: 8-byte hcnv_block")
     ap.add_argument("--e2e-workers", type=int, default=3, help="worker contexts of the end-to-end leg")
     return ap.parse_args()
 
@@ -209,7 +211,9 @@ def run_b200(args):
     contigs = synth.make_genome(coverage=args.coverage, seed=SEED, device=dev, contigs=[names[i] for i in mine], scale=args.scale)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
-    api_dev = synth.to_api_contigs(contigs)
+    compact = args.block_format == "compact"
+    api_dev = synth.to_api_contigs(contigs, compact=compact)
+    n_stream = sum(int(a.cblocks.shape[0]) for a in api_dev if a.cblocks is not None) if compact else 0
     n_reads = sum(c.n_reads for c in contigs)
     n_blocks = sum(int(c.blocks.shape[0]) for c in contigs)
     n_long = sum(int(c.long_blocks.shape[0]) for c in contigs)
@@ -308,9 +312,16 @@ def run_b200(args):
                 h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                 h.copy_(t)
                 return h.numpy()
-            hc = H.Contig(c.length, pin(c.blocks), pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs))
+            if compact:
+                a = api_dev[len(host_contigs)]
+                hc = H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs),
+                              pin(a.cblocks) if a.cblocks is not None else None, pin(a.anchors) if a.anchors is not None else None)
+                h2d += (a.cblocks.numel() + a.anchors.numel()) * 4 if a.cblocks is not None else 0
+            else:
+                hc = H.Contig(c.length, pin(c.blocks), pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs))
+                h2d += c.blocks.numel() * 4
             host_contigs.append(hc)
-            h2d += c.blocks.numel() * 4 + c.long_blocks.numel() * 4 + c.snp_pos1.numel() * 4 + c.snp_zyg.numel() + c.obs.numel() * 4
+            h2d += c.long_blocks.numel() * 4 + c.snp_pos1.numel() * 4 + c.snp_zyg.numel() + c.obs.numel() * 4
         torch.cuda.synchronize()
         # results.txt columns: start, end, scaled, state, cn, mse[6] (Hmm.java:479-490), per chromosome, into pinned arrays.
         # The call a user makes: GenomePipeline.run = per chromosome hcnv_bin_contigs -> hcnv_bins_to_hmm_input ->
@@ -360,7 +371,8 @@ def run_b200(args):
     kavg = {k_: float(np.mean(v)) for k_, v in kacc.items()}
     # algorithmic bytes per launch: binning = 8 B/block + 16 B/long block + 4 B/obs + 5 B/SNP + 72 B/bin out;
     # Viterbi = 28 B in (f32 scaled + 6 f32 mse) + 8 B out (state, cn) per bin
-    bytes_bin = 8 * n_blocks + 16 * n_long + 4 * n_obs + 5 * n_snp + 72 * n_bins
+    # (compact stream: 4 B per stream record, fillers and padding included, + one 4-byte anchor per 128 records)
+    bytes_bin = (4 * n_stream + 4 * (n_stream // 128) if compact else 8 * n_blocks) + 16 * n_long + 4 * n_obs + 5 * n_snp + 72 * n_bins
     bytes_vit = 36 * n_bins
     def roof(kname, nbytes):
         ms = kavg.get(kname)
@@ -399,7 +411,7 @@ def run_b200(args):
             "dtype": "int32 counts / f32+f64 statistics / f32 Viterbi", "data": "synthetic",
             "config": {"workload": "hg19_30x_wgs" if args.scale == 1.0 else "hg19_30x_wgs_scaled_%g" % args.scale, "coverage": args.coverage,
                        "bin_width": W, "read_len": READ_LEN, "reads": g_reads, "alignment_blocks": g_blocks, "bins": g_bins, "snp_sites": g_snp,
-                       "snp_observations": g_obs, "lambda1": LAMBDA1, "lambda2": LAMBDA2, "parallelism": "chromosome-sharded x%d (LPT)" % world,
+                       "snp_observations": g_obs, "block_format": args.block_format, "lambda1": LAMBDA1, "lambda2": LAMBDA2, "parallelism": "chromosome-sharded x%d (LPT)" % world,
                        "l2": "inputs (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (bytes_bin / 1e9)},
             "genome_wall_time_s": ms_dev / 1e3, "wall_ms_per_step": ms_wall,
             "bins_per_s_segmented": g_bins / (sum(kavg.get(k_, 0) for k_ in ("mean_coverage", "scale_depth", "sd", "viterbi", "traceback")) / 1e3) if kavg.get("viterbi") else None,

@@ -15,6 +15,7 @@ HCNV_E_INVALID, HCNV_E_CUDA, HCNV_E_NOMEM, HCNV_E_RANGE, HCNV_E_UNSORTED = -1, -
 HCNV_E_INCONSISTENT, HCNV_E_NO_MINIMUM, HCNV_E_IO, HCNV_E_PARSE, HCNV_E_CAPACITY, HCNV_E_INTERNAL = -6, -7, -8, -9, -10, -11
 HCNV_SHORT_MAX = 4095
 HCNV_SEG_SEQUENTIAL = 1
+HCNV_CGROUP = 128
 KERNELS = dict(tile_index=0, tally=1, bin_tiles=2, text_roundtrip=3, mean_coverage=4, scale_depth=5, sd=6, viterbi=7, traceback=8,
                vit_p0=9, vit_p0c=10, vit_p1=11, vit_p2=12, vit_p3=13, vit_p1b=14, vit_p2b=15, snp_mse=16)
 
@@ -35,7 +36,8 @@ class ContigInput(C.Structure):
                 ("blocks", C.c_void_p), ("n_blocks", C.c_int64),
                 ("long_blocks", C.c_void_p), ("n_long", C.c_int64),
                 ("snp_pos1", C.c_void_p), ("snp_zyg", C.c_void_p), ("n_snp", C.c_int64),
-                ("obs", C.c_void_p), ("n_obs", C.c_int64)]
+                ("obs", C.c_void_p), ("n_obs", C.c_int64),
+                ("cblocks", C.c_void_p), ("anchors", C.c_void_p), ("n_cblocks", C.c_int64)]
 
 
 class Bins(C.Structure):
@@ -68,7 +70,7 @@ EXPORTS = [
     "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
     "hcnv_write_bins_text", "hcnv_write_results_text",
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
-    "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_free",
+    "hcnv_compact_blocks", "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_free",
 ]
 
 _lib = None
@@ -98,6 +100,8 @@ def lib():
     L.hcnv_last_error.restype = C.c_char_p
     L.hcnv_strerror.argtypes = [C.c_int]
     L.hcnv_strerror.restype = C.c_char_p
+    L.hcnv_compact_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+    L.hcnv_compact_blocks.restype = C.c_int64
     L.hcnv_ctx_stream.argtypes = [C.c_void_p]
     L.hcnv_ctx_stream.restype = C.c_void_p
     L.hcnv_ctx_kernel_launches.argtypes = [C.c_void_p]

@@ -51,6 +51,40 @@ def pack_blocks(start0, length, mapq=None) -> np.ndarray:
     return b
 
 
+def compact_blocks(blocks: np.ndarray):
+    """hcnv_compact_blocks: sorted hcnv_block records -> (cblocks uint32, anchors int32): 4 bytes per block, delta-coded,
+    one absolute anchor per HCNV_CGROUP records, fillers for gaps above 4095, padded to a whole group."""
+    lib = L.lib()
+    blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+    n = lib.hcnv_compact_blocks(blocks.ctypes.data, len(blocks), None, None, 0)
+    if n < 0:
+        raise L.HcnvError(int(n), "hcnv_compact_blocks: %s" % lib.hcnv_strerror(int(n)).decode())
+    raw = np.empty(n + 4, np.uint32)                         # 16-byte aligned start
+    shift = (-raw.ctypes.data // 4) % 4
+    cb = raw[shift:shift + n]
+    anchors = np.empty(max(1, n // L.HCNV_CGROUP), np.int32)
+    m = lib.hcnv_compact_blocks(blocks.ctypes.data, len(blocks), cb.ctypes.data, anchors.ctypes.data, n)
+    assert m == n
+    return cb, anchors[: n // L.HCNV_CGROUP]
+
+
+def expand_cblocks(cblocks, anchors) -> np.ndarray:
+    """Inverse of compact_blocks on the host (numpy): hcnv_block records of every non-filler entry (test helper)."""
+    cb = np.asarray(cblocks, dtype=np.uint32)
+    d = (cb & 0xFFF).astype(np.int64)
+    g = L.HCNV_CGROUP
+    d[::g] = 0
+    c = np.cumsum(d)
+    first = np.repeat(c[::g], g)[: len(cb)]
+    start = np.repeat(np.asarray(anchors, dtype=np.int64), g)[: len(cb)] + (c - first)
+    ln = (cb >> 12) & 0xFFF
+    keep = ln > 0
+    out = np.empty(int(keep.sum()), BLOCK_DTYPE)
+    out["start0"] = start[keep]
+    out["len_mapq"] = ln[keep] | ((cb[keep] >> 24) << np.uint32(24))
+    return out
+
+
 def pack_long_blocks(start0, length, mapq=None) -> np.ndarray:
     b = np.zeros(len(start0), dtype=LONG_BLOCK_DTYPE)
     b["start0"] = start0
@@ -69,6 +103,8 @@ class Contig:
     snp_pos1: object = None        # int32, ascending unique
     snp_zyg: object = None         # int8 in {0,-1,-2}
     obs: object = None             # uint32 (torch: int32) snp_index << 4 | base4
+    cblocks: object = None         # alternative to blocks: hcnv_cblock stream (uint32 / torch int32), 16-byte aligned
+    anchors: object = None         # int32, one per HCNV_CGROUP compact records
 
 
 @dataclass
@@ -163,7 +199,8 @@ class Context:
             arr[i].long_blocks, arr[i].n_long = _ptr(c.long_blocks), _len(c.long_blocks)
             arr[i].snp_pos1, arr[i].snp_zyg, arr[i].n_snp = _ptr(c.snp_pos1), _ptr(c.snp_zyg), _len(c.snp_pos1)
             arr[i].obs, arr[i].n_obs = _ptr(c.obs), _len(c.obs)
-            for x in (c.blocks, c.long_blocks, c.snp_pos1, c.obs):
+            arr[i].cblocks, arr[i].anchors, arr[i].n_cblocks = _ptr(c.cblocks), _ptr(c.anchors), _len(c.cblocks)
+            for x in (c.blocks, c.cblocks, c.long_blocks, c.snp_pos1, c.obs):
                 if x is not None and _is_torch(x):
                     on_device = True
         cap = capacity if capacity is not None else sum(int(c.length) // bin_width + 1 for c in contigs)

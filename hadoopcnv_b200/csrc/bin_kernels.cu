@@ -15,11 +15,15 @@
 #include "hcnv_internal.h"
 #include <cmath>
 #include <algorithm>
+#include <type_traits>
 
 namespace {
 
 struct ContigDev {
-    const hcnv_block*      blocks;
+    const hcnv_cblock*     cblocks;   // compact stream (n_cblocks records, a multiple of HCNV_CGROUP) and its anchors, or ...
+    const int32_t*         anchors;
+    long long              n_cblocks;
+    const hcnv_block*      blocks;    // ... 8-byte records
     const hcnv_long_block* longs;
     const int32_t*         snp_pos;
     const int8_t*          snp_zyg;
@@ -48,6 +52,7 @@ struct BinK {
     const ContigDev* contigs;
     int   n_contigs;
     int   W, TB, n_tiles, maxlen;
+    int   compact;                   // 1: the contigs carry compact streams
     uint32_t mapq_pass[8];
     TileRec*  tile_rec;              // per-tile index, filled by k_tile_index
     uint32_t* tally;
@@ -102,7 +107,9 @@ __global__ void __launch_bounds__(256) k_tile_index(BinK p) {
         const int k = t - c.tile_base;
         const long long T0 = (long long)k * TP;  // first 1-based position of the tile (position 0 never holds a read)
         // a block with 0-based start s covers 1-based positions s+1 .. s+len: it starts in the tile iff T0-1 <= s < T0+TP-1
-        s_lo[slot] = (k == 0) ? 0u : lower_bound_blocks(c.blocks, c.n_blocks, clampk(T0 - 1));
+        // (compact stream: in units of groups, by the anchors: first group whose first record starts at or after the tile)
+        s_lo[slot] = (k == 0) ? 0u : (p.compact ? lower_bound_i32(c.anchors, c.n_cblocks / HCNV_CGROUP, clampk(T0 - 1))
+                                                 : lower_bound_blocks(c.blocks, c.n_blocks, clampk(T0 - 1)));
         s_slo[slot] = (k == 0) ? 0u : lower_bound_i32(c.snp_pos, c.n_snp, clampk(T0));
         if (slot < 256) { my_contig = lo; my_k = k; }
     }
@@ -115,6 +122,35 @@ __global__ void __launch_bounds__(256) k_tile_index(BinK p) {
     TileRec r;
     r.contig = my_contig; r.k = k; r.pad = 0;
     const uint32_t lo = s_lo[threadIdx.x];
+    if (p.compact) {
+        // group granular superset: from the group before the first group that starts at or after T0 - 1 - maxlen (its
+        // later records may reach the tile) up to the first group that starts at or after the tile's end
+        const uint32_t ng = (uint32_t)(c.n_cblocks / HCNV_CGROUP);
+        uint32_t ghi = last ? ng : s_lo[threadIdx.x + 1];
+        uint32_t glb = 0;
+        if (lo > 0) {
+            const int32_t key = clampk((long long)k * TP - 1 - p.maxlen);
+            uint32_t low = lo, step = 2;
+            while (low > 0) {
+                low = (low > step) ? low - step : 0u;
+                if (__ldg(&c.anchors[low]) < key) break;
+                step <<= 1;
+            }
+            glb = low + lower_bound_i32(c.anchors + low, (long long)(lo - low), key);
+            if (glb > 0) --glb;
+        }
+        r.pad = 0;
+        if (ghi < glb) { ghi = glb; r.pad = 1; }
+        r.lb = glb * HCNV_CGROUP; r.hi = ghi * HCNV_CGROUP;
+        r.slo = s_slo[threadIdx.x];
+        r.shi = last ? (uint32_t)c.n_snp : s_slo[threadIdx.x + 1];
+        if (r.shi < r.slo) r.shi = r.slo;
+        r.prev_start = (int)0x80000000;
+        hcnv_block z; z.start0 = 0; z.len_mapq = 0;
+        r.head = z; r.tail = z;
+        p.tile_rec[t] = r;
+        return;
+    }
     r.hi = last ? (uint32_t)c.n_blocks : s_lo[threadIdx.x + 1];
     r.slo = s_slo[threadIdx.x];
     r.shi = last ? (uint32_t)c.n_snp : s_slo[threadIdx.x + 1];
@@ -245,7 +281,7 @@ __global__ void k_snp_mse(BinK p) {
 // ---------------------------------------------------------------------------------------------------
 namespace {
 enum { B_CONTIGS = 0, B_TILEIDX, B_TALLY, B_STATUS, B_MISC, B_IN_BLOCKS, B_IN_LONG, B_IN_SNPPOS, B_IN_SNPZYG, B_IN_OBS,
-       B_OUT_I32, B_OUT_F32, B_OUT_F64, B_SNPDEPTH = 24 };
+       B_OUT_I32, B_OUT_F32, B_OUT_F64, B_SNPDEPTH = 24, B_IN_ANCHORS = 25 };
 
 template <class T>
 int stage_in(hcnv_ctx* ctx, int kind, const T* src, long long n, T* dst) {
@@ -273,10 +309,27 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     if (!out->bin || !out->start || !out->end || !out->median || !out->mse || !out->total || !out->n || !out->contig_offset)
         return hcnv_fail(ctx, HCNV_E_INVALID, "null output array");
 
+    // which form of the block stream: compact (4 bytes, delta coded) or 8-byte records; one form per call
+    int compact = -1;
+    for (int c = 0; c < n_contigs; ++c) {
+        const hcnv_contig_input& ci = contigs[c];
+        if (ci.n_cblocks < 0 || (ci.n_cblocks > 0 && ci.n_blocks > 0)) return hcnv_fail(ctx, HCNV_E_INVALID, "give blocks or cblocks, not both");
+        const int f = ci.n_cblocks > 0 ? 1 : (ci.n_blocks > 0 ? 0 : -1);
+        if (f >= 0) { if (compact < 0) compact = f; else if (compact != f) return hcnv_fail(ctx, HCNV_E_INVALID, "all contigs of a call must use the same block format"); }
+        if (ci.n_cblocks > 0) {
+            if (ci.n_cblocks % HCNV_CGROUP) return hcnv_fail(ctx, HCNV_E_INVALID, "n_cblocks must be a multiple of HCNV_CGROUP (pad with fillers)");
+            if (!ci.cblocks || !ci.anchors) return hcnv_fail(ctx, HCNV_E_INVALID, "null cblocks / anchors");
+            if (reinterpret_cast<uintptr_t>(ci.cblocks) & 15) return hcnv_fail(ctx, HCNV_E_INVALID, "cblocks must be 16-byte aligned");
+            if (ci.n_cblocks >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many records in one contig");
+        }
+    }
+    if (compact < 0) compact = 0;
+
     // tile geometry: one warp = one tile of 32 bins; a warp's shared-memory slice = tile records + two record chunks +
     // the difference array of its 32 * W positions; as many warps per SM as fit
     const int TB = 32;
-    const size_t warp_smem = ((sizeof(WarpSmem) + 15) & ~(size_t)15) + (size_t)NRBUF * (RCAP + 4) * 8 + (((size_t)32 * W + 4) * 4 + 15) / 16 * 16;
+    const size_t warp_smem = ((sizeof(WarpSmem) + 15) & ~(size_t)15) + (compact ? (size_t)NRBUF * RCAP * 4 : (size_t)NRBUF * (RCAP + 4) * 8) +
+                             (((size_t)32 * W + 4) * 4 + 15) / 16 * 16;
     int NW = (int)std::min<size_t>(BIN_MAX_WARPS, (ctx->smem_optin - 3072) / warp_smem);
     if (P.tile_bins > 0 && P.tile_bins < NW) NW = P.tile_bins;          // tuning knob: fewer warps per SM
     if (NW < 1) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1700)");
@@ -284,24 +337,25 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
 
     // pointer kinds
     int in_kind = -1;
-    long long tot_blocks = 0, tot_long = 0, tot_snp = 0, tot_obs = 0, tot_bins_max = 0;
+    long long tot_blocks = 0, tot_cblocks = 0, tot_long = 0, tot_snp = 0, tot_obs = 0, tot_bins_max = 0;
     for (int c = 0; c < n_contigs; ++c) {
         const hcnv_contig_input& ci = contigs[c];
         if (ci.length < 0 || ci.n_blocks < 0 || ci.n_long < 0 || ci.n_snp < 0 || ci.n_obs < 0) return hcnv_fail(ctx, HCNV_E_INVALID, "negative count");
         if (ci.n_blocks >= (1ll << 31) || ci.n_snp >= (1ll << 28)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many records in one contig");
         if (ci.length > 0x7fffffff - 2 * HCNV_SHORT_MAX - 4096 * 128) return hcnv_fail(ctx, HCNV_E_INVALID, "contig too long");
         if (ci.n_blocks && (reinterpret_cast<uintptr_t>(ci.blocks) & 7)) return hcnv_fail(ctx, HCNV_E_INVALID, "blocks must be 8-byte aligned");
-        const void* ptrs[5] = { ci.n_blocks ? (const void*)ci.blocks : nullptr, ci.n_long ? (const void*)ci.long_blocks : nullptr,
+        const void* ptrs[7] = { ci.n_blocks ? (const void*)ci.blocks : nullptr, ci.n_long ? (const void*)ci.long_blocks : nullptr,
                                 ci.n_snp ? (const void*)ci.snp_pos1 : nullptr, ci.n_snp ? (const void*)ci.snp_zyg : nullptr,
-                                ci.n_obs ? (const void*)ci.obs : nullptr };
-        const long long cnts[5] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs };
-        for (int j = 0; j < 5; ++j) {
+                                ci.n_obs ? (const void*)ci.obs : nullptr, ci.n_cblocks ? (const void*)ci.cblocks : nullptr,
+                                ci.n_cblocks ? (const void*)ci.anchors : nullptr };
+        const long long cnts[7] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs, ci.n_cblocks, ci.n_cblocks };
+        for (int j = 0; j < 7; ++j) {
             if (cnts[j] == 0) continue;
             if (!ptrs[j]) return hcnv_fail(ctx, HCNV_E_INVALID, "null input array with non-zero count");
             int kd = hcnv_ptr_kind(ptrs[j]) == 2 ? 2 : 0;
             if (in_kind < 0) in_kind = kd; else if (in_kind != kd) return hcnv_fail(ctx, HCNV_E_INVALID, "mixed host/device input pointers");
         }
-        tot_blocks += ci.n_blocks; tot_long += ci.n_long; tot_snp += ci.n_snp; tot_obs += ci.n_obs;
+        tot_blocks += ci.n_blocks; tot_cblocks += ci.n_cblocks; tot_long += ci.n_long; tot_snp += ci.n_snp; tot_obs += ci.n_obs;
         tot_bins_max += ci.length / W + 1;
     }
     if (in_kind < 0) in_kind = 0;
@@ -314,20 +368,24 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     // stage inputs that live on the host
     std::vector<ContigDev> hc(n_contigs);
     if (in_kind != 2) {
-        HCNV_CUDA(ctx, ctx->buf[B_IN_BLOCKS].reserve(sizeof(hcnv_block) * (size_t)tot_blocks));
+        HCNV_CUDA(ctx, ctx->buf[B_IN_BLOCKS].reserve(sizeof(hcnv_block) * (size_t)tot_blocks + 4 * (size_t)tot_cblocks));
+        HCNV_CUDA(ctx, ctx->buf[B_IN_ANCHORS].reserve(4 * (size_t)(tot_cblocks / HCNV_CGROUP) + 16));
         HCNV_CUDA(ctx, ctx->buf[B_IN_LONG].reserve(sizeof(hcnv_long_block) * (size_t)tot_long));
         HCNV_CUDA(ctx, ctx->buf[B_IN_SNPPOS].reserve(4 * (size_t)tot_snp));
         HCNV_CUDA(ctx, ctx->buf[B_IN_SNPZYG].reserve((size_t)tot_snp + 16 * n_contigs));
         HCNV_CUDA(ctx, ctx->buf[B_IN_OBS].reserve(4 * (size_t)tot_obs));
     }
-    long long ob = 0, ol = 0, os = 0, oo = 0, obs32_total = 0;
+    long long ob = 0, ocb = 0, ol = 0, os = 0, oo = 0, obs32_total = 0;
     int tile_base = 0;
     for (int c = 0; c < n_contigs; ++c) {
         const hcnv_contig_input& ci = contigs[c];
         ContigDev& d = hc[c];
         if (in_kind == 2) {
             d.blocks = ci.blocks; d.longs = ci.long_blocks; d.snp_pos = ci.snp_pos1; d.snp_zyg = ci.snp_zyg; d.obs = ci.obs;
+            d.cblocks = ci.cblocks; d.anchors = ci.anchors;
         } else {
+            d.cblocks = ctx->buf[B_IN_BLOCKS].as<hcnv_cblock>() + ocb;            // (a call uses one form, so the buffer is shared)
+            d.anchors = ctx->buf[B_IN_ANCHORS].as<int32_t>() + ocb / HCNV_CGROUP;
             d.blocks = ctx->buf[B_IN_BLOCKS].as<hcnv_block>() + ob;
             d.longs = ctx->buf[B_IN_LONG].as<hcnv_long_block>() + ol;
             d.snp_pos = ctx->buf[B_IN_SNPPOS].as<int32_t>() + os;
@@ -335,17 +393,19 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             d.obs = ctx->buf[B_IN_OBS].as<uint32_t>() + oo;
             int rc;
             if ((rc = stage_in(ctx, in_kind, ci.blocks, ci.n_blocks, const_cast<hcnv_block*>(d.blocks)))) return rc;
+            if ((rc = stage_in(ctx, in_kind, ci.cblocks, ci.n_cblocks, const_cast<hcnv_cblock*>(d.cblocks)))) return rc;
+            if ((rc = stage_in(ctx, in_kind, ci.anchors, ci.n_cblocks / HCNV_CGROUP, const_cast<int32_t*>(d.anchors)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.long_blocks, ci.n_long, const_cast<hcnv_long_block*>(d.longs)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.snp_pos1, ci.n_snp, const_cast<int32_t*>(d.snp_pos)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.snp_zyg, ci.n_snp, const_cast<int8_t*>(d.snp_zyg)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.obs, ci.n_obs, const_cast<uint32_t*>(d.obs)))) return rc;
         }
-        d.n_blocks = ci.n_blocks; d.n_long = ci.n_long; d.n_snp = ci.n_snp; d.n_obs = ci.n_obs;
+        d.n_blocks = ci.n_blocks; d.n_cblocks = ci.n_cblocks; d.n_long = ci.n_long; d.n_snp = ci.n_snp; d.n_obs = ci.n_obs;
         d.obs_base32 = obs32_total; obs32_total += (ci.n_obs + 31) / 32 * 32;
         d.snp_base = os; d.length = ci.length; d.n_bins_max = ci.length / W + 1;
         d.tile_base = tile_base; d.n_tiles = (d.n_bins_max + TB - 1) / TB;
         tile_base += d.n_tiles;
-        ob += ci.n_blocks; ol += ci.n_long; os += ci.n_snp; oo += ci.n_obs;
+        ob += ci.n_blocks; ocb += ci.n_cblocks; ol += ci.n_long; os += ci.n_snp; oo += ci.n_obs;
     }
     const int n_tiles = tile_base;
 
@@ -359,7 +419,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     HCNV_CUDA(ctx, ctx->buf[B_STATUS].reserve(8 * n_status));
     HCNV_CUDA(ctx, ctx->buf[B_MISC].reserve(4096 + 8 * (size_t)(n_contigs + 1)));
     k.contigs = ctx->buf[B_CONTIGS].as<ContigDev>();
-    k.n_contigs = n_contigs; k.W = W; k.TB = TB; k.n_tiles = n_tiles; k.maxlen = maxlen;
+    k.n_contigs = n_contigs; k.W = W; k.TB = TB; k.n_tiles = n_tiles; k.maxlen = maxlen; k.compact = compact;
     for (int q = 0; q < 256; ++q) {
         double mapprob = 1. - std::pow(10.0, -q * .1);            // Mappers.java:193
         if (mapprob >= P.mapping_quality_threshold) k.mapq_pass[q >> 5] |= 1u << (q & 31);   // :200
@@ -418,9 +478,14 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         kern<<<grid, NW * 32, smem_bytes, ctx->stream>>>(k);
         return cudaGetLastError();
     };
-    if (W % 4 == 0)      HCNV_CUDA(ctx, filter ? launch(k_bin_tiles<4, true>) : launch(k_bin_tiles<4, false>));
-    else if (W % 2 == 0) HCNV_CUDA(ctx, filter ? launch(k_bin_tiles<2, true>) : launch(k_bin_tiles<2, false>));
-    else                 HCNV_CUDA(ctx, filter ? launch(k_bin_tiles<1, true>) : launch(k_bin_tiles<1, false>));
+    auto launch_vec = [&](auto vec_tag) -> cudaError_t {
+        constexpr int V = decltype(vec_tag)::value;
+        if (compact) return filter ? launch(k_bin_tiles<V, true, true>) : launch(k_bin_tiles<V, false, true>);
+        return filter ? launch(k_bin_tiles<V, true, false>) : launch(k_bin_tiles<V, false, false>);
+    };
+    if (W % 4 == 0)      HCNV_CUDA(ctx, launch_vec(std::integral_constant<int, 4>()));
+    else if (W % 2 == 0) HCNV_CUDA(ctx, launch_vec(std::integral_constant<int, 2>()));
+    else                 HCNV_CUDA(ctx, launch_vec(std::integral_constant<int, 1>()));
     KT_END(ctx, HCNV_K_BIN_TILES);
     ctx->launches++;
     if (tot_snp) {

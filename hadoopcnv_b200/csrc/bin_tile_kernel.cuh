@@ -62,7 +62,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct ContigLite {                               // what a tile needs from its contig
-    const hcnv_block*      blocks;
+    const hcnv_cblock*     cblocks;               // compact stream (COMPACT kernels) ...
+    const int32_t*         anchors;
+    long long              n_groups;
+    const hcnv_block*      blocks;                // ... or the 8-byte records
     const hcnv_long_block* longs;
     const int32_t*         snp_pos;
     long long n_long, snp_base;
@@ -186,7 +189,7 @@ struct WarpSmem {                                 // fixed part of a warp's slic
     uint64_t rbar[NRBUF], mbar[3];
 };
 
-template <int VEC, bool FILTER>
+template <int VEC, bool FILTER, bool COMPACT>
 __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ ContigLite s_ct[CTC];
@@ -197,8 +200,10 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
     const int TP = 32 * W;                                              // positions per tile
     unsigned char* slice = smraw + (size_t)wid * p.warp_smem;
     WarpSmem* ws = reinterpret_cast<WarpSmem*>(slice);
-    hcnv_block* recbuf = reinterpret_cast<hcnv_block*>(slice + ((sizeof(WarpSmem) + 15) & ~(size_t)15));    // NRBUF x (RCAP + 4) slots
-    int32_t* diff = reinterpret_cast<int32_t*>(recbuf + NRBUF * (RCAP + 4));                              // TP + 4 entries; entry TP sinks ends at the tile edge
+    unsigned char* recraw = slice + ((sizeof(WarpSmem) + 15) & ~(size_t)15);
+    hcnv_block* recbuf = reinterpret_cast<hcnv_block*>(recraw);         // 8-byte records: NRBUF x (RCAP + 4) slots
+    hcnv_cblock* cbuf = reinterpret_cast<hcnv_cblock*>(recraw);         // compact records: NRBUF x RCAP words
+    int32_t* diff = reinterpret_cast<int32_t*>(recraw + (COMPACT ? (size_t)NRBUF * RCAP * 4 : (size_t)NRBUF * (RCAP + 4) * 8));   // TP + 4 entries; entry TP sinks ends at the tile edge
     const bool ct_cached = p.n_contigs <= CTC;
 
     if (tid == 0) s_state = 0;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
     if (ct_cached)
         for (int i = tid; i < p.n_contigs; i += blockDim.x) {
             const ContigDev& g = p.contigs[i];
-            ContigLite c; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
+            ContigLite c; c.cblocks = g.cblocks; c.anchors = g.anchors; c.n_groups = g.n_cblocks / HCNV_CGROUP; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
             c.length = g.length; c.n_bins_max = g.n_bins_max;
             s_ct[i] = c;
         }
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
     auto contig_of = [&](int ci) -> ContigLite {
         if (ct_cached) return s_ct[ci];
         const ContigDev& g = p.contigs[ci];
-        ContigLite c; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
+        ContigLite c; c.cblocks = g.cblocks; c.anchors = g.anchors; c.n_groups = g.n_cblocks / HCNV_CGROUP; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
         c.length = g.length; c.n_bins_max = g.n_bins_max;
         return c;
     };
@@ -243,6 +248,28 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
         fence_proxy_async();
         if (cnt) { mbar_expect_tx(&ws->rbar[buf], cnt * 8u); tma_load_1d(R + 2, blocks + ta, cnt * 8u, &ws->rbar[buf]); }
         else mbar_arrive(&ws->rbar[buf]);
+    };
+
+    // lane 0 only: compact stream, chunk q of a tile = records [lb + q * RCAP, ...) (whole groups, 16-byte aligned)
+    auto issue_chunk_c = [&](const hcnv_cblock* cb, const TileRec& tm, uint32_t q, int buf) {
+        const uint32_t ta = tm.lb + q * RCAP, tb = min(ta + (uint32_t)RCAP, tm.hi);
+        fence_proxy_async();
+        mbar_expect_tx(&ws->rbar[buf], (tb - ta) * 4u);
+        tma_load_1d(cbuf + (size_t)buf * RCAP, cb + ta, (tb - ta) * 4u, &ws->rbar[buf]);
+    };
+    auto issue_first = [&](const TileRec& tm, int buf) {      // chunk 0 of a tile + the rest of its records into L2
+        const ContigLite cc = contig_of(tm.contig);
+        if (COMPACT) {
+            issue_chunk_c(cc.cblocks, tm, 0, buf);
+            if (tm.hi - tm.lb > (uint32_t)RCAP)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cc.cblocks + tm.lb + RCAP), "r"((tm.hi - tm.lb - (uint32_t)RCAP) * 4u) : "memory");
+        } else {
+            issue_chunk(cc.blocks, tm, 0, buf);
+            const unsigned long long pa = (reinterpret_cast<unsigned long long>(cc.blocks + tm.lb) + 15ull) & ~15ull;
+            const unsigned long long pe = reinterpret_cast<unsigned long long>(cc.blocks + tm.hi) & ~15ull;
+            if (pe > pa + (unsigned long long)RCAP * 8ull)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa + (unsigned long long)RCAP * 8ull), "r"((uint32_t)(pe - pa - (unsigned long long)RCAP * 8ull)) : "memory");
+        }
     };
 
     // ---- this warp's tile sequence.  Tiles are claimed in order from a global ticket (a tile's predecessors are then
@@ -282,7 +309,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
         if (tk_cur < p.n_tiles) {
             mbar_wait(&ws->mbar[0], 0);
             const TileRec& tm = ws->tm[0];
-            if (tm.hi > tm.lb) issue_chunk(contig_of(tm.contig).blocks, tm, 0, 0);
+            if (tm.hi > tm.lb) issue_first(tm, 0);
         }
     }
     int prev_last = 0;                            // lane 0: start of the last record of the previous chunk
@@ -338,9 +365,9 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
             const uint32_t a0 = (uint32_t)((reinterpret_cast<unsigned long long>(blocks) >> 3) & 1ull);
             uint32_t A = lb + ((a0 + lb) & 1u);
             if (A > hi) A = hi;
-            const uint32_t nch = (hi > lb) ? max(1u, (hi - A + RCAP - 1) / RCAP) : 0u;
+            const uint32_t nch = COMPACT ? (hi - lb + RCAP - 1) / RCAP : ((hi > lb) ? max(1u, (hi - A + RCAP - 1) / RCAP) : 0u);
             // chunk 1 can start right away: its buffer was released at the end of the previous tile's record phase
-            if (lane == 0 && nch > 1) issue_chunk(blocks, tm, 1, (int)((consumed + 1) & 1u));
+            if (lane == 0 && nch > 1) { if (COMPACT) issue_chunk_c(c.cblocks, tm, 1, (int)((consumed + 1) & 1u)); else issue_chunk(blocks, tm, 1, (int)((consumed + 1) & 1u)); }
             // ---- clear the difference array
             #pragma unroll 5
             for (int i = lane * 4; i < TP + 4; i += 128) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
@@ -358,6 +385,52 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
             // ---- the sorted short-block stream, chunk by chunk
             const int T0m1 = T0 - 1;
             const int maxlen = p.maxlen, length = c.length;
+            if (COMPACT) {
+                // compact stream: whole groups of HCNV_CGROUP records; lane l decodes records 4l .. 4l+3 of a group (one
+                // LDS.128): deltas -> lane prefix -> warp scan -> + the group's anchor.  The range handed over by
+                // k_tile_index is a superset (group granular); what lies outside the tile clamps to an empty interval.
+                for (uint32_t q = 0; q < nch; ++q) {
+                    const int buf = (int)(consumed & 1u);
+                    const uint32_t ta = lb + q * RCAP, tb = min(ta + (uint32_t)RCAP, hi);
+                    const uint32_t g0 = ta / HCNV_CGROUP, ng = (tb - ta) / HCNV_CGROUP;
+                    // anchors of this chunk's groups and of the group after it (consistency): issued before the wait
+                    int anc[RCAP / HCNV_CGROUP + 1];
+                    #pragma unroll
+                    for (uint32_t g = 0; g <= RCAP / HCNV_CGROUP; ++g)
+                        anc[g] = (g <= ng && (long long)(g0 + g) < c.n_groups) ? __ldg(&c.anchors[g0 + g]) : 0x7fffffff;
+                    const hcnv_cblock* R = cbuf + (size_t)buf * RCAP;
+                    mbar_wait(&ws->rbar[buf], (consumed >> 1) & 1u);
+                    int acc_u = 0, acc_r = 0;
+                    #pragma unroll
+                    for (uint32_t g = 0; g < RCAP / HCNV_CGROUP; ++g) {
+                        if (g >= ng) break;
+                        const uint4 w = reinterpret_cast<const uint4*>(R + g * HCNV_CGROUP)[lane];
+                        const int p0 = lane == 0 ? 0 : (int)(w.x & 0xFFFu);
+                        const int p1 = p0 + (int)(w.y & 0xFFFu), p2 = p1 + (int)(w.z & 0xFFFu), p3 = p2 + (int)(w.w & 0xFFFu);
+                        int incl = p3;
+                        #pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                        const int base = anc[g] + (incl - p3);
+                        // the group must end at or before the next group's anchor (they are one sorted stream)
+                        if (lane == 31) acc_u |= anc[g + 1] - (base + p3);
+                        acc_u |= anc[g];
+                        auto one = [&](uint32_t word, int start0) {
+                            const int len = (int)((word >> 12) & 0xFFFu);
+                            acc_r |= start0 | (length - len - start0) | (maxlen - len);
+                            int s_ = start0 - T0m1, e_ = s_ + len;
+                            s_ = min(max(s_, 0), TP); e_ = min(max(e_, 0), TP);      // clamped: memory-safe whatever the record says
+                            bool on = e_ > s_;                                       // fillers, padding, records outside the tile
+                            if (FILTER) { const uint32_t mq = word >> 24; on = on && ((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u); }
+                            if (on) { atomicAdd(&diff[s_], 1); atomicAdd(&diff[e_], -1); }
+                        };
+                        one(w.x, base + p0); one(w.y, base + p1); one(w.z, base + p2); one(w.w, base + p3);
+                    }
+                    bad |= (acc_u < 0 ? 1 : 0) | (acc_r < 0 ? 2 : 0);
+                    ++consumed;
+                    __syncwarp();                                     // all reads of this buffer are done
+                    if (lane == 0 && q + 2 < nch) issue_chunk_c(c.cblocks, tm, q + 2, buf);
+                }
+            } else
             for (uint32_t q = 0; q < nch; ++q) {
                 const int buf = (int)(consumed & 1u);
                 const uint32_t ta = A + q * RCAP, tb = min(ta + (uint32_t)RCAP, hi);
@@ -399,15 +472,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
                     const int ns = (it + 1) % 3;
                     mbar_wait(&ws->mbar[ns], (uint32_t)((it + 1) / 3) & 1u);
                     const TileRec& tn_rec = ws->tm[ns];
-                    if (tn_rec.hi > tn_rec.lb) {
-                        const hcnv_block* nbk = contig_of(tn_rec.contig).blocks;
-                        issue_chunk(nbk, tn_rec, 0, (int)(consumed & 1u));
-                        // the rest of its records: into L2 now, so that the later chunks are L2 hits
-                        const unsigned long long pa = (reinterpret_cast<unsigned long long>(nbk + tn_rec.lb) + 15ull) & ~15ull;
-                        const unsigned long long pe = reinterpret_cast<unsigned long long>(nbk + tn_rec.hi) & ~15ull;
-                        if (pe > pa + (unsigned long long)RCAP * 8ull)
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa + (unsigned long long)RCAP * 8ull), "r"((uint32_t)(pe - pa - (unsigned long long)RCAP * 8ull)) : "memory");
-                    }
+                    if (tn_rec.hi > tn_rec.lb) issue_first(tn_rec, (int)(consumed & 1u));
                 }
                 fetch_tile_rec(tk_n2, (it + 2) % 3);
             }

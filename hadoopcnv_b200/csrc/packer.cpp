@@ -287,6 +287,36 @@ int hcnv_bam_pack(const char* bam_path, const hcnv_snp_table* snps, hcnv_pack** 
     return HCNV_OK;
 }
 
+int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, hcnv_cblock* out, int32_t* anchors, int64_t capacity) {
+    if (n < 0 || (n > 0 && !blocks) || (out && !anchors)) return HCNV_E_INVALID;
+    int64_t k = 0;                                          // compact records written (or counted) so far
+    int32_t prev = 0;
+    auto put = [&](int32_t start0, uint32_t delta, uint32_t len, uint32_t mapq) -> bool {
+        if (out) {
+            if (k >= capacity) return false;
+            if (k % HCNV_CGROUP == 0) anchors[k / HCNV_CGROUP] = start0;
+            out[k] = delta | (len << 12) | (mapq << 24);
+        }
+        ++k;
+        return true;
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t s = blocks[i].start0;
+        const uint32_t len = blocks[i].len_mapq & 0xFFFFFFu, mapq = blocks[i].len_mapq >> 24;
+        if (s < 0 || len > (uint32_t)HCNV_SHORT_MAX) return HCNV_E_RANGE;
+        if (i > 0 && s < prev) return HCNV_E_UNSORTED;
+        int64_t gap = (i == 0) ? 0 : (int64_t)s - prev;
+        while (gap > 4095) {                               // fillers: len 0, advance 4095
+            prev += 4095; gap -= 4095;
+            if (!put(prev, 4095u, 0u, 0u)) return HCNV_E_CAPACITY;
+        }
+        if (!put(s, (uint32_t)gap, len, mapq)) return HCNV_E_CAPACITY;
+        prev = s;
+    }
+    while (k % HCNV_CGROUP) if (!put(prev, 0u, 0u, 0u)) return HCNV_E_CAPACITY;
+    return k;
+}
+
 int32_t hcnv_pack_n_contigs(const hcnv_pack* p) { return p ? (int32_t)p->contigs.size() : 0; }
 int64_t hcnv_pack_n_records(const hcnv_pack* p) { return p ? p->n_records : 0; }
 

@@ -94,6 +94,16 @@ int64_t     hcnv_ctx_stat(const hcnv_ctx* ctx, int which);
  * len_mapq = length | mapq << 24 (mapq as in Mappers.java:192).  Sorted by start0 within a contig. */
 typedef struct { int32_t start0; uint32_t len_mapq; } hcnv_block;
 
+/* The same stream at 4 bytes per block, delta-coded (what the host should send: the upload is what bounds the path
+ * end to end):   bits 0-11  start0 - start0 of the previous record (0..4095)
+ *                bits 12-23 len (0..HCNV_SHORT_MAX)      bits 24-31 mapq
+ * Every HCNV_CGROUP records there is an absolute anchor, anchors[g] = start0 of record HCNV_CGROUP * g (the delta field
+ * of that record is ignored).  A gap above 4095 is bridged by filler records (len 0, delta up to 4095), and the stream
+ * is padded with fillers (delta 0, len 0) to a multiple of HCNV_CGROUP records: n_cblocks counts them all.  A filler
+ * covers no position and changes nothing.  cblocks must be 16-byte aligned.  hcnv_compact_blocks builds the stream. */
+typedef uint32_t hcnv_cblock;
+#define HCNV_CGROUP 128
+
 /* A block of any length (e.g. the baseline BAM's artificial whole-interval reads, example/preprocessBAM.py).
  * Not required to be sorted.  Splitting a block is results-neutral: only per-position counts matter. */
 typedef struct { int32_t start0; int32_t len; int32_t mapq; int32_t reserved; } hcnv_long_block;
@@ -118,7 +128,15 @@ typedef struct {
     const hcnv_long_block* long_blocks; int64_t n_long;
     const int32_t*         snp_pos1;    const int8_t* snp_zyg; int64_t n_snp;
     const uint32_t*        obs;         int64_t n_obs;
+    /* alternative to `blocks` (give one or the other; all contigs of a call use the same form) */
+    const hcnv_cblock*     cblocks;     const int32_t* anchors; int64_t n_cblocks;
 } hcnv_contig_input;
+
+/* Host helper (no GPU): sorted hcnv_block records -> compact stream.  Returns the number of compact records (fillers and
+ * padding included, a multiple of HCNV_CGROUP) or a negative status; with out == NULL only counts.  anchors needs
+ * result / HCNV_CGROUP entries.  HCNV_E_UNSORTED if the input is not sorted by start0, HCNV_E_RANGE for a negative
+ * start0 or len > HCNV_SHORT_MAX, HCNV_E_CAPACITY if `capacity` (in records) is too small. */
+int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, hcnv_cblock* out, int32_t* anchors, int64_t capacity);
 
 /* Outputs: one record per non-empty bin, all contigs concatenated in input order, bins ascending within a
  * contig (the (chr,bin) secondary sort, PennCnvSeq.java:382-414).  Field meaning = the columns BinReducer

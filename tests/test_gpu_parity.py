@@ -50,6 +50,46 @@ def test_binning_matches_oracle_host_buffers(ctx, W, cov, tile_bins):
         assert_bins_equal(res.contig(i), oracle_bins(c, W))
 
 
+@pytest.mark.parametrize("W,cov,thr", [(100, 30, 0.0), (50, 100, 0.0), (7, 30, 0.0), (1000, 30, 0.0), (100, 30, 0.9)])
+def test_binning_compact_stream_matches_oracle(ctx, W, cov, thr):
+    """The 4-byte delta-coded block stream (fillers over the N gaps, group anchors) gives the same bins, from host and
+    from device buffers."""
+    kw = dict(het_per_bp=0, hom_per_bp=0) if thr > 0 else {}       # (a filter needs the packer to drop the filtered reads' observations)
+    g = synth.make_genome(coverage=cov, scale=0.0015, device="cpu", contigs=["chr10", "chr11", "chr21", "chrY"], seed=4321 + W, **kw)
+    for host in (True, False):
+        gg = g if host else [synth.SynthContig(c.name, c.length, c.blocks.cuda(), c.long_blocks.cuda(), c.snp_pos1.cuda(), c.snp_zyg.cuda(),
+                                               c.obs.cuda(), c.n_reads, c.truth) for c in g]
+        res = ctx.bin_contigs(synth.to_api_contigs(gg, host=host, compact=True), bin_width=W, max_block_len=synth.READ_LEN,
+                              mapping_quality_threshold=thr)
+        for i, c in enumerate(g):
+            r = res.contig(i)
+            got = r if host else H.BinsResult(*[x.cpu().numpy() for x in (r.bin, r.start, r.end, r.median, r.mse, r.total, r.n)], r.contig_offset)
+            assert_bins_equal(got, oracle_bins(c, W, thr))
+
+
+def test_binning_compact_stream_edge_cases(ctx):
+    # one record, a 40 kb gap bridged by fillers, a pile-up on one position, records on the contig's last base
+    starts = [5, 5, 5, 5, 40000, 40010, 99989]
+    lens = [10, 20, 30, 1, 100, 5, 10]
+    b = H.pack_blocks(starts, lens, [60] * len(starts))
+    cb, an = H.compact_blocks(b)
+    assert len(cb) % 128 == 0 and len(an) == len(cb) // 128
+    e = H.expand_cblocks(cb, an)
+    assert e["start0"].tolist() == starts and (e["len_mapq"] & 0xFFFFFF).tolist() == lens
+    want = ctx.bin_contigs([H.Contig(100000, b)], bin_width=100)
+    got = ctx.bin_contigs([H.Contig(100000, None, None, None, None, None, cb, an)], bin_width=100)
+    for k in ("bin", "start", "end", "n", "median", "total"):
+        np.testing.assert_array_equal(getattr(got, k), getattr(want, k), err_msg=k)
+    # bad streams are refused, not mis-binned
+    bad = cb.copy(); bad[1] = (bad[1] & ~np.uint32(0xFFF << 12)) | np.uint32(200 << 12)
+    with pytest.raises(H.HcnvError) as ei:
+        ctx.bin_contigs([H.Contig(100000, None, None, None, None, None, bad, an)], bin_width=100, max_block_len=150)
+    assert ei.value.status == L.HCNV_E_RANGE
+    with pytest.raises(H.HcnvError) as ei:
+        ctx.bin_contigs([H.Contig(100000, None, None, None, None, None, cb[:100], an)], bin_width=100)
+    assert ei.value.status == L.HCNV_E_INVALID
+
+
 def test_binning_device_buffers_and_default_lookback(ctx):
     import torch
     g = synth.make_genome(coverage=30, scale=0.003, device="cuda", contigs=["chr1", "chr2", "chrX"], seed=99)

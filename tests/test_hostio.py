@@ -109,3 +109,27 @@ def test_reference_baseline_bam_fixture():
     assert sorted(got) == sorted(tuple(b) for b in shape["baseline_blocks"])
     assert sum(b[2] for b in got) == 2911652393
     assert contigs[24].length == max(b[1] + b[2] for b in shape["baseline_blocks"] if b[0] == -1)
+
+
+def test_compact_block_stream_round_trip():
+    """hcnv_compact_blocks (host, no GPU): delta coding, fillers over gaps, padding to whole groups, anchors."""
+    rng = np.random.default_rng(11)
+    n = 5000
+    gaps = rng.integers(0, 30, n)
+    gaps[rng.random(n) < 0.01] = 50000
+    start = np.cumsum(gaps)
+    ln = rng.integers(1, 200, n)
+    mq = rng.integers(0, 256, n)
+    b = H.pack_blocks(start, ln, mq)
+    cb, an = H.compact_blocks(b)
+    assert cb.ctypes.data % 16 == 0 and len(cb) % L.HCNV_CGROUP == 0 and len(an) == len(cb) // L.HCNV_CGROUP
+    assert ((cb & 0xFFF) <= 4095).all() and (np.diff(an) >= 0).all()
+    e = H.expand_cblocks(cb, an)
+    assert (e["start0"] == b["start0"]).all() and (e["len_mapq"] == b["len_mapq"]).all()
+    n_fill = int(((cb >> 12) & 0xFFF == 0).sum())
+    assert len(cb) == n + n_fill                                          # every extra record is a filler
+    with pytest.raises(H.HcnvError) as ei:
+        H.compact_blocks(H.pack_blocks([10, 5], [3, 3]))
+    assert ei.value.status == L.HCNV_E_UNSORTED
+    cb0, an0 = H.compact_blocks(H.pack_blocks([], []))
+    assert len(cb0) == 0 and len(an0) == 0
