@@ -69,8 +69,9 @@ EXPORTS = [
     "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_ctx_stat", "hcnv_bin_params_default", "hcnv_bin_contigs",
     "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
     "hcnv_write_bins_text", "hcnv_write_results_text",
+    "hcnv_read_bins_text", "hcnv_bins_text_n_chromosomes", "hcnv_bins_text_get", "hcnv_bins_text_free",
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
-    "hcnv_compact_blocks", "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_free",
+    "hcnv_compact_blocks", "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
 ]
 
 _lib = None
@@ -100,6 +101,11 @@ def lib():
     L.hcnv_last_error.restype = C.c_char_p
     L.hcnv_strerror.argtypes = [C.c_int]
     L.hcnv_strerror.restype = C.c_char_p
+    L.hcnv_read_bins_text.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.hcnv_bins_text_n_chromosomes.argtypes = [C.c_void_p]
+    L.hcnv_bins_text_get.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)] + [C.POINTER(C.c_void_p)] * 7
+    L.hcnv_bins_text_free.argtypes = [C.c_void_p]
+    L.hcnv_bins_text_free.restype = None
     L.hcnv_compact_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
     L.hcnv_compact_blocks.restype = C.c_int64
     L.hcnv_ctx_stream.argtypes = [C.c_void_p]

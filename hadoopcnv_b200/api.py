@@ -340,3 +340,30 @@ def write_results_text(path: str, chrom: str, start, end, scaled, state, cn, mse
     st = L.lib().hcnv_write_results_text(path.encode(), int(append), chrom.encode(), len(args[0]), *[_ptr(a) for a in args])
     if st != 0:
         raise L.HcnvError(st, "hcnv_write_results_text")
+
+
+def read_bins_text(path: str) -> dict:
+    """hcnv_read_bins_text: a bins part file -> {chrom: dict(bin, start, end, median, mse, total, n)} in first-seen order,
+    parsed the way job 3 parses it (Integer.parseInt / Float.valueOf, bins ascending per chromosome): the float32 arrays
+    are segment_batch's inputs as they are."""
+    lib = L.lib()
+    h = C.c_void_p()
+    st = lib.hcnv_read_bins_text(path.encode(), C.byref(h))
+    if st != 0:
+        raise L.HcnvError(st, "hcnv_read_bins_text(%s): %s" % (path, lib.hcnv_strerror(st).decode()))
+    try:
+        out = {}
+        for i in range(lib.hcnv_bins_text_n_chromosomes(h)):
+            name, n = C.c_char_p(), C.c_int64()
+            ptrs = [C.c_void_p() for _ in range(7)]
+            lib.hcnv_bins_text_get(h, i, C.byref(name), C.byref(n), *[C.byref(p) for p in ptrs])
+            k = n.value
+
+            def arr(p, dtype, count):
+                return np.frombuffer((C.c_char * (count * np.dtype(dtype).itemsize)).from_address(p.value), dtype=dtype).copy() if count else np.zeros(0, dtype)
+            out[name.value.decode()] = dict(bin=arr(ptrs[0], np.int32, k), start=arr(ptrs[1], np.int32, k), end=arr(ptrs[2], np.int32, k),
+                                            median=arr(ptrs[3], np.float32, k), mse=arr(ptrs[4], np.float32, 6 * k).reshape(k, 6),
+                                            total=arr(ptrs[5], np.float32, k), n=arr(ptrs[6], np.int32, k))
+        return out
+    finally:
+        lib.hcnv_bins_text_free(h)

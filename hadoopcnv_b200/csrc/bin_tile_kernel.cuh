@@ -401,29 +401,38 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
                     const hcnv_cblock* R = cbuf + (size_t)buf * RCAP;
                     mbar_wait(&ws->rbar[buf], (consumed >> 1) & 1u);
                     int acc_u = 0, acc_r = 0;
+                    // both groups of the chunk are decoded together (their scans interleave); a chunk with one group
+                    // decodes stale words for the second one and ignores them
+                    constexpr int NG = RCAP / HCNV_CGROUP;
+                    uint4 w[NG]; int p0[NG], p1[NG], p2[NG], p3[NG], incl[NG];
                     #pragma unroll
-                    for (uint32_t g = 0; g < RCAP / HCNV_CGROUP; ++g) {
-                        if (g >= ng) break;
-                        const uint4 w = reinterpret_cast<const uint4*>(R + g * HCNV_CGROUP)[lane];
-                        const int p0 = lane == 0 ? 0 : (int)(w.x & 0xFFFu);
-                        const int p1 = p0 + (int)(w.y & 0xFFFu), p2 = p1 + (int)(w.z & 0xFFFu), p3 = p2 + (int)(w.w & 0xFFFu);
-                        int incl = p3;
+                    for (int g = 0; g < NG; ++g) {
+                        w[g] = reinterpret_cast<const uint4*>(R + g * HCNV_CGROUP)[lane];
+                        p0[g] = lane == 0 ? 0 : (int)(w[g].x & 0xFFFu);
+                        p1[g] = p0[g] + (int)(w[g].y & 0xFFFu); p2[g] = p1[g] + (int)(w[g].z & 0xFFFu); p3[g] = p2[g] + (int)(w[g].w & 0xFFFu);
+                        incl[g] = p3[g];
+                    }
+                    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
                         #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                        const int base = anc[g] + (incl - p3);
+                        for (int g = 0; g < NG; ++g) { const int v = __shfl_up_sync(0xffffffffu, incl[g], o); if (lane >= o) incl[g] += v; }
+                    }
+                    #pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const bool live = (uint32_t)g < ng;
+                        const int base = anc[g] + (incl[g] - p3[g]);
                         // the group must end at or before the next group's anchor (they are one sorted stream)
-                        if (lane == 31) acc_u |= anc[g + 1] - (base + p3);
-                        acc_u |= anc[g];
+                        if (live) { if (lane == 31) acc_u |= anc[g + 1] - (base + p3[g]); acc_u |= anc[g]; }
                         auto one = [&](uint32_t word, int start0) {
                             const int len = (int)((word >> 12) & 0xFFFu);
-                            acc_r |= start0 | (length - len - start0) | (maxlen - len);
                             int s_ = start0 - T0m1, e_ = s_ + len;
                             s_ = min(max(s_, 0), TP); e_ = min(max(e_, 0), TP);      // clamped: memory-safe whatever the record says
-                            bool on = e_ > s_;                                       // fillers, padding, records outside the tile
+                            bool on = live && e_ > s_;                               // fillers, padding, records outside the tile
+                            if (live) acc_r |= start0 | (length - len - start0) | (maxlen - len);
                             if (FILTER) { const uint32_t mq = word >> 24; on = on && ((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u); }
                             if (on) { atomicAdd(&diff[s_], 1); atomicAdd(&diff[e_], -1); }
                         };
-                        one(w.x, base + p0); one(w.y, base + p1); one(w.z, base + p2); one(w.w, base + p3);
+                        one(w[g].x, base + p0[g]); one(w[g].y, base + p1[g]); one(w[g].z, base + p2[g]); one(w[g].w, base + p3[g]);
                     }
                     bad |= (acc_u < 0 ? 1 : 0) | (acc_r < 0 ? 2 : 0);
                     ++consumed;

@@ -28,6 +28,7 @@ struct hcnv_pack {
     struct Contig {
         std::string name; int32_t length = 0; int32_t max_len = 0;
         std::vector<hcnv_block> blocks; std::vector<hcnv_long_block> longs; std::vector<uint32_t> obs;
+        std::vector<hcnv_cblock> cstore; std::vector<int32_t> anchors; hcnv_cblock* cblocks = nullptr; int64_t n_cblocks = -1;   // built on demand
         const std::vector<int32_t>* snp_pos = nullptr; const std::vector<int8_t>* snp_zyg = nullptr;
     };
     std::vector<Contig> contigs;
@@ -331,6 +332,26 @@ int hcnv_pack_contig(const hcnv_pack* p, int32_t i, const char** name, hcnv_cont
     if (c.snp_pos) { in->snp_pos1 = c.snp_pos->data(); in->snp_zyg = c.snp_zyg->data(); in->n_snp = (int64_t)c.snp_pos->size(); }
     in->obs = c.obs.data(); in->n_obs = (int64_t)c.obs.size();
     if (max_block_len) *max_block_len = c.max_len;
+    return HCNV_OK;
+}
+
+int hcnv_pack_contig_compact(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len) {
+    int rc = hcnv_pack_contig(p, i, name, in, max_block_len);
+    if (rc) return rc;
+    hcnv_pack::Contig& c = p->contigs[(size_t)i];
+    if (c.n_cblocks < 0) {                                  // first request: build the 4-byte stream, 16-byte aligned
+        const int64_t n = hcnv_compact_blocks(c.blocks.data(), (int64_t)c.blocks.size(), nullptr, nullptr, 0);
+        if (n < 0) return (int)n;
+        c.cstore.resize((size_t)n + 4);
+        const uintptr_t a = reinterpret_cast<uintptr_t>(c.cstore.data());
+        c.cblocks = c.cstore.data() + ((16 - (a & 15)) & 15) / 4;
+        c.anchors.resize((size_t)(n / HCNV_CGROUP) + 1);
+        const int64_t m = hcnv_compact_blocks(c.blocks.data(), (int64_t)c.blocks.size(), c.cblocks, c.anchors.data(), n);
+        if (m != n) return HCNV_E_INTERNAL;
+        c.n_cblocks = n;
+    }
+    in->blocks = nullptr; in->n_blocks = 0;
+    in->cblocks = c.n_cblocks ? c.cblocks : nullptr; in->anchors = c.n_cblocks ? c.anchors.data() : nullptr; in->n_cblocks = c.n_cblocks;
     return HCNV_OK;
 }
 

@@ -10,8 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -239,5 +241,97 @@ int hcnv_write_results_text(const char* path, int append, const char* chr, int64
     }
     return fclose(f) == 0 ? HCNV_OK : HCNV_E_IO;
 }
+
+// ---- bins part files back in: what BinSortMapper + the (chr, bin) secondary sort + Hmm.init do to them ----------
+}  // extern "C"
+
+struct hcnv_bins_text {
+    struct Chrom {
+        std::string name;
+        std::vector<int32_t> bin, start, end, n;
+        std::vector<float> median, mse, total;
+    };
+    std::vector<Chrom> chroms;
+    std::map<std::string, int> index;
+};
+
+extern "C" {
+
+int hcnv_read_bins_text(const char* path, hcnv_bins_text** out) {
+    if (!path || !out) return HCNV_E_INVALID;
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return HCNV_E_IO;
+    hcnv_bins_text* t = new hcnv_bins_text();
+    std::string line; int ch; int rc = HCNV_OK;
+    auto handle = [&](const std::string& ln) -> int {
+        if (ln.empty()) return HCNV_OK;
+        std::vector<std::string> parts; size_t s = 0;
+        for (;;) { size_t e = ln.find('\t', s); parts.push_back(ln.substr(s, e == std::string::npos ? e : e - s)); if (e == std::string::npos) break; s = e + 1; }
+        if (parts.size() < 13) return HCNV_E_PARSE;            // BinSortMapper reads parts[0..1], Hmm.init parts[0..10] of the value
+        int32_t bin, st, en, cnt;
+        float med, tot, m[6];
+        // Integer.parseInt for bin (Mappers.java:75), start, end, n (Hmm.java:360-373); Float.valueOf for the rest
+        if (!parse_int(parts[1], &bin) || !parse_int(parts[2], &st) || !parse_int(parts[3], &en) || !parse_int(parts[12], &cnt)) return HCNV_E_PARSE;
+        if (!parse_float(parts[4], &med) || !parse_float(parts[11], &tot)) return HCNV_E_PARSE;
+        for (int j = 0; j < 6; ++j) if (!parse_float(parts[5 + j], &m[j])) return HCNV_E_PARSE;
+        auto it = t->index.find(parts[0]);
+        int ci;
+        if (it == t->index.end()) { ci = (int)t->chroms.size(); t->index[parts[0]] = ci; t->chroms.emplace_back(); t->chroms.back().name = parts[0]; }
+        else ci = it->second;
+        hcnv_bins_text::Chrom& c = t->chroms[(size_t)ci];
+        c.bin.push_back(bin); c.start.push_back(st); c.end.push_back(en); c.n.push_back(cnt);
+        c.median.push_back(med); c.total.push_back(tot);
+        for (int j = 0; j < 6; ++j) c.mse.push_back(m[j]);
+        return HCNV_OK;
+    };
+    while ((ch = fgetc(f)) != EOF) {
+        if (ch == '\n') { if (!line.empty() && line.back() == '\r') line.pop_back(); rc = handle(line); line.clear(); if (rc) break; }
+        else line.push_back((char)ch);
+    }
+    if (!rc && !line.empty()) rc = handle(line);
+    fclose(f);
+    if (rc) { delete t; return rc; }
+    // the reducer sees a chromosome's bins in ascending bin order (RefBinKey.compareTo, Keys.java:226-238); part files
+    // written by this library already are, files merged from several reducers may not be
+    for (auto& c : t->chroms) {
+        const size_t n = c.bin.size();
+        bool sorted = true;
+        for (size_t i = 1; i < n; ++i) if (c.bin[i] < c.bin[i - 1]) { sorted = false; break; }
+        if (sorted) continue;
+        std::vector<size_t> o(n);
+        for (size_t i = 0; i < n; ++i) o[i] = i;
+        std::stable_sort(o.begin(), o.end(), [&](size_t a, size_t b) { return c.bin[a] < c.bin[b]; });
+        hcnv_bins_text::Chrom d; d.name = c.name;
+        for (size_t i : o) {
+            d.bin.push_back(c.bin[i]); d.start.push_back(c.start[i]); d.end.push_back(c.end[i]); d.n.push_back(c.n[i]);
+            d.median.push_back(c.median[i]); d.total.push_back(c.total[i]);
+            for (int j = 0; j < 6; ++j) d.mse.push_back(c.mse[6 * i + j]);
+        }
+        c = d;
+    }
+    *out = t;
+    return HCNV_OK;
+}
+
+int32_t hcnv_bins_text_n_chromosomes(const hcnv_bins_text* t) { return t ? (int32_t)t->chroms.size() : 0; }
+
+int hcnv_bins_text_get(const hcnv_bins_text* t, int32_t i, const char** chrom, int64_t* n, const int32_t** bin, const int32_t** start,
+                       const int32_t** end, const float** median, const float** mse, const float** total, const int32_t** cnt) {
+    if (!t || i < 0 || i >= (int32_t)t->chroms.size()) return HCNV_E_INVALID;
+    const hcnv_bins_text::Chrom& c = t->chroms[(size_t)i];
+    if (chrom) *chrom = c.name.c_str();
+    if (n) *n = (int64_t)c.bin.size();
+    if (bin) *bin = c.bin.data();
+    if (start) *start = c.start.data();
+    if (end) *end = c.end.data();
+    if (median) *median = c.median.data();
+    if (mse) *mse = c.mse.data();
+    if (total) *total = c.total.data();
+    if (cnt) *cnt = c.n.data();
+    return HCNV_OK;
+}
+
+void hcnv_bins_text_free(hcnv_bins_text* t) { delete t; }
 
 }  // extern "C"

@@ -53,8 +53,9 @@ class SnpTable:
         return ["%s\t%d\t%d\t0" % (c, int(p), int(z)) for c, (ps, zs) in self.contigs().items() for p, z in zip(ps, zs)]
 
 
-def pack_bam(bam_path: str, snps: Optional[SnpTable] = None):
-    """hcnv_bam_pack -> (names, [Contig with numpy arrays], [max_block_len], n_records).  Arrays are copies."""
+def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = False):
+    """hcnv_bam_pack -> (names, [Contig with numpy arrays], [max_block_len], n_records).  Arrays are copies.
+    compact=True: the block stream comes in the 4-byte delta-coded form (Contig.cblocks / anchors)."""
     lib = L.lib()
     h = C.c_void_p()
     st = lib.hcnv_bam_pack(bam_path.encode(), snps._h if snps is not None else None, C.byref(h))
@@ -64,7 +65,7 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None):
         names, contigs, maxlens = [], [], []
         for i in range(lib.hcnv_pack_n_contigs(h)):
             name, ci, ml = C.c_char_p(), L.ContigInput(), C.c_int32()
-            lib.hcnv_pack_contig(h, i, C.byref(name), C.byref(ci), C.byref(ml))
+            (lib.hcnv_pack_contig_compact if compact else lib.hcnv_pack_contig)(h, i, C.byref(name), C.byref(ci), C.byref(ml))
 
             def arr(ptr, n, dtype):
                 if not n:
@@ -73,9 +74,17 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None):
                 return np.frombuffer((C.c_char * nbytes).from_address(ptr), dtype=dtype).copy()
             names.append(name.value.decode())
             maxlens.append(int(ml.value))
+            def arr16(ptr, n):                                   # 16-byte aligned copy of the compact stream
+                if not n:
+                    return None
+                raw = np.empty(n + 4, np.uint32)
+                sh = (-raw.ctypes.data // 4) % 4
+                raw[sh:sh + n] = np.frombuffer((C.c_char * (4 * n)).from_address(ptr), dtype=np.uint32)
+                return raw[sh:sh + n]
             contigs.append(Contig(ci.length, arr(ci.blocks, ci.n_blocks, BLOCK_DTYPE), arr(ci.long_blocks, ci.n_long, LONG_BLOCK_DTYPE),
                                   arr(ci.snp_pos1, ci.n_snp, np.int32), arr(ci.snp_zyg, ci.n_snp, np.int8),
-                                  arr(ci.obs, ci.n_obs, np.uint32)))
+                                  arr(ci.obs, ci.n_obs, np.uint32), arr16(ci.cblocks, ci.n_cblocks),
+                                  arr(ci.anchors, ci.n_cblocks // L.HCNV_CGROUP, np.int32)))
         return names, contigs, maxlens, int(lib.hcnv_pack_n_records(h))
     finally:
         lib.hcnv_pack_free(h)

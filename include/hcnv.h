@@ -176,6 +176,8 @@ int32_t hcnv_pack_n_contigs(const hcnv_pack* p);
 int64_t hcnv_pack_n_records(const hcnv_pack* p);
 /* fills `in` with pointers into the pack (valid until hcnv_pack_free); max_block_len for hcnv_bin_params */
 int     hcnv_pack_contig(const hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
+/* the same with the block stream in the compact form (built on the first request): in->cblocks / anchors / n_cblocks */
+int     hcnv_pack_contig_compact(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
 void    hcnv_pack_free(hcnv_pack* p);
 
 /* ---- between B1 and B2: what Hmm.init's text parsing does to a bins record ---------------------- */
@@ -231,6 +233,18 @@ int hcnv_format_double(double v, char* buf);
 int hcnv_write_bins_text(const char* path, int append, const char* chr, int64_t n,
                          const int32_t* bin, const int32_t* start, const int32_t* end, const float* median,
                          const double* mse, const double* total, const int32_t* cnt);
+/* the way back: parse bins part files the way job 3 does -- BinSortMapper (Mappers.java:71-81) keys by (chr, bin), the
+ * secondary sort hands a chromosome's bins to CnvReducer ascending, and Hmm.init (Hmm.java:355-373) reads start, end,
+ * n with Integer.parseInt and median, mse0..5, total with Float.valueOf (correctly rounded, f/d suffix allowed).
+ * Chromosomes come back in first-seen order; arrays stay valid until hcnv_bins_text_free.  These float arrays are
+ * exactly hcnv_segment_batch's inputs (no hcnv_bins_to_hmm_input in between: the text already went through it). */
+typedef struct hcnv_bins_text hcnv_bins_text;
+int     hcnv_read_bins_text(const char* path, hcnv_bins_text** out);
+int32_t hcnv_bins_text_n_chromosomes(const hcnv_bins_text* t);
+int     hcnv_bins_text_get(const hcnv_bins_text* t, int32_t i, const char** chrom, int64_t* n, const int32_t** bin,
+                           const int32_t** start, const int32_t** end, const float** median, const float** mse,
+                           const float** total, const int32_t** cnt);
+void    hcnv_bins_text_free(hcnv_bins_text* t);
 /* results.txt lines "chr\tstart\tend\tscaled\tstate\tcn\tmse0..5" (Hmm.java:479-490, Reducers.java:238-241) */
 int hcnv_write_results_text(const char* path, int append, const char* chr, int64_t n,
                             const int32_t* start, const int32_t* end, const float* scaled,

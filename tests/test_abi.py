@@ -137,3 +137,35 @@ def test_text_writers(tmp_path, lib):
     H.write_results_text(str(r), "chr15", [20000300], [20000399], [np.float32(9.808615e-4)], [2], [2], np.zeros((1, 6), np.float32), append=True)
     assert r.read_text().splitlines() == ["chr15\t20000007\t20000099\t-0.6997057\t2\t2\t0.0\t0.0\t0.0\t0.0\t0.0\t0.0",
                                           "chr15\t20000300\t20000399\t9.808615E-4\t2\t2\t0.0\t0.0\t0.0\t0.0\t0.0\t0.0"]
+
+
+def test_read_bins_text_parses_like_job_3(tmp_path, lib):
+    """bins part file -> arrays: the golden bins lines parse to what the literal restatement's Hmm.init sees, bins come back
+    ascending per chromosome even from a shuffled file, and malformed lines are refused."""
+    import json
+    from oracle import literal as Lit
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "case_2.json")))
+    lines = d["bins_lines"]
+    other = [ln.replace("chr7\t", "chr8\t", 1) for ln in lines[:50]]
+    rng = np.random.default_rng(3)
+    mixed = lines + other
+    rng.shuffle(mixed)
+    p = tmp_path / "part-r-00000"
+    p.write_text("\n".join(mixed) + "\n")
+    got = H.read_bins_text(str(p))
+    assert set(got) == {"chr7", "chr8"}
+    c = got["chr7"]
+    want = [ln.split("\t") for ln in lines]
+    assert c["bin"].tolist() == [int(w[1]) for w in want] and (np.diff(c["bin"]) > 0).all()
+    assert c["start"].tolist() == [int(w[2]) for w in want] and c["end"].tolist() == [int(w[3]) for w in want]
+    assert c["n"].tolist() == [int(w[12]) for w in want]
+    f = lambda s: np.float32(Lit.java_float_value_of(s))
+    assert (c["median"].view(np.uint32) == np.array([f(w[4]) for w in want], np.float32).view(np.uint32)).all()
+    assert (c["total"].view(np.uint32) == np.array([f(w[11]) for w in want], np.float32).view(np.uint32)).all()
+    assert (c["mse"].view(np.uint32) == np.array([[f(x) for x in w[5:11]] for w in want], np.float32).view(np.uint32)).all()
+    assert len(got["chr8"]["bin"]) == 50
+    bad = tmp_path / "bad"
+    bad.write_text("chr1\t0\t1\t99\tnot-a-number\t0\t0\t0\t0\t0\t0\t10.0\t3\n")
+    with pytest.raises(H.HcnvError) as e:
+        H.read_bins_text(str(bad))
+    assert e.value.status == L.HCNV_E_PARSE

@@ -68,3 +68,46 @@ def test_cuda_path_reproduces_the_golden_lines(k, tmp_path):
         assert pr.read_text().splitlines() == d["results_lines"]
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", CASES)
+def test_hmm_only_rerun_from_the_bins_part_file(k, tmp_path):
+    """Stage toggle RUN_CNV_CALL only (example/config.txt:7-12): the bins part file is read back the way job 3 reads it
+    and segmented; results.txt lines equal the golden ones."""
+    d = load(k)
+    p = tmp_path / "part-r-00000"
+    p.write_text("\n".join(d["bins_lines"]) + "\n")
+    b = H.read_bins_text(str(p))[d["chrom"]]
+    ctx = H.Context(0)
+    try:
+        call = ctx.segment_batch([dict(median=b["median"], mse=b["mse"], total=b["total"], n=b["n"], lambda1=d["lambda1"], lambda2=d["lambda2"])])[0]
+        pr = tmp_path / "results.txt"
+        H.write_results_text(str(pr), d["chrom"], b["start"], b["end"], call["scaled"], call["state"], call["cn"], b["mse"])
+        assert pr.read_text().splitlines() == d["results_lines"]
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_cohort_penalty_sweep_matches_oracle():
+    """BASELINE.json configs[4] in small: several samples' precomputed bins x a grid of (ABBERATION_PENALTY,
+    TRANSITION_PENALTY) pairs in ONE hcnv_segment_batch call; every (sample, pair) equals the oracle per bin."""
+    rng = np.random.default_rng(64)
+    samples = [Hp.random_bins(rng, int(M), snp_fraction=0.1) for M in (700, 5000, 9000)]
+    grid = [(l1, l2) for l1 in (0.01, 0.05, 0.1, 0.3) for l2 in (0.4, 0.8, 1.6, 3.2)]
+    probs, want = [], []
+    for b in samples:
+        m32, t32 = O.f64_text_f32(b["mse"]), O.f64_text_f32(b["total"])      # what the bins text round trip hands to Hmm.init
+        for l1, l2 in grid:
+            probs.append(dict(median=b["median"], mse=m32, total=t32, n=b["n"], lambda1=l1, lambda2=l2))
+            want.append(O.hmm(b["median"], m32, t32, b["n"], l1, l2))
+    ctx = H.Context(0)
+    try:
+        got = ctx.segment_batch(probs)
+    finally:
+        ctx.close()
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g["state"], w["state"])
+        np.testing.assert_array_equal(g["cn"], w["cn"])
+        assert np.float32(g["final_loss"]).view(np.uint32) == np.float32(w["final_loss"]).view(np.uint32)

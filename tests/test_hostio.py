@@ -69,6 +69,12 @@ def test_bam_pack_matches_htsjdk_semantics(tmp_path, seed):
     assert sorted(c.obs.tolist()) == sorted(want_obs.tolist())
     assert maxlens[0] == int((want_blocks["len_mapq"] & 0xFFFFFF).max())
     assert contigs[1].blocks is None and contigs[1].length == 1000
+    # the same pack in the compact form expands to the same records
+    _, cc, _, _ = hostio.pack_bam(str(bam), table, compact=True)
+    assert cc[0].blocks is None and cc[0].cblocks.ctypes.data % 16 == 0
+    e = H.expand_cblocks(cc[0].cblocks, cc[0].anchors)
+    nz = (c.blocks["len_mapq"] & 0xFFFFFF) > 0
+    assert (e["start0"] == c.blocks["start0"][nz]).all() and (e["len_mapq"] == c.blocks["len_mapq"][nz]).all()
     # and the packed records bin to the same thing as the text-level pipeline
     zyg = dict(zip(*[x.tolist() for x in table.contigs()["chr7"]]))
     want = Lit.binner(Lit.depth_caller([(r[0], r[1], r[2], r[3], r[4], r[5]) for r in reads]) + table.vcf_txt_lines())
