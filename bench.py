@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-format", default="compact", choices=["compact", "records"],
                     help="compact: 4-byte delta-coded block stream (include/hcnv.h hcnv_cblock); records: 8-byte hcnv_block")
-    ap.add_argument("--e2e-workers", type=int, default=3, help="worker contexts of the end-to-end leg")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
     return ap.parse_args()
 
 
