@@ -328,9 +328,10 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     // tile geometry: one warp = one tile of 32 bins; a warp's shared-memory slice = tile records + two record chunks +
     // the difference array of its 32 * W positions; as many warps per SM as fit
     const int TB = 32;
-    const size_t warp_smem = ((sizeof(WarpSmem) + 15) & ~(size_t)15) + (compact ? (size_t)NRBUF * RCAP * 4 : (size_t)NRBUF * (RCAP + 4) * 8) +
+    const size_t warp_smem = ((sizeof(WarpSmem) + 15) & ~(size_t)15) + (compact ? (size_t)0 : (size_t)NRBUF * (RCAP + 4) * 8) +
                              (((size_t)32 * W + 4) * 4 + 15) / 16 * 16;
     int NW = (int)std::min<size_t>(BIN_MAX_WARPS, (ctx->smem_optin - 3072) / warp_smem);
+    if (NW > BIN_MAX_WARPS) NW = BIN_MAX_WARPS;
     if (P.tile_bins > 0 && P.tile_bins < NW) NW = P.tile_bins;          // tuning knob: fewer warps per SM
     if (NW < 1) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width too large for shared memory (max about 1700)");
     const size_t smem_bytes = warp_smem * (size_t)NW;

@@ -30,7 +30,9 @@
 #endif
 #define NRBUF 2                                   // chunk buffers in flight per warp
 #define CTC 32                                    // contig descriptors cached in shared memory
+#ifndef BIN_MAX_WARPS
 #define BIN_MAX_WARPS 16
+#endif
 #define TBATCH 8                                  // consecutive tiles a CTA claims per global ticket
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -190,7 +192,7 @@ struct WarpSmem {                                 // fixed part of a warp's slic
 };
 
 template <int VEC, bool FILTER, bool COMPACT>
-__global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
+__global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ ContigLite s_ct[CTC];
     __shared__ unsigned long long s_state;        // the CTA's current batch of tiles (see claim)
@@ -202,8 +204,8 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
     WarpSmem* ws = reinterpret_cast<WarpSmem*>(slice);
     unsigned char* recraw = slice + ((sizeof(WarpSmem) + 15) & ~(size_t)15);
     hcnv_block* recbuf = reinterpret_cast<hcnv_block*>(recraw);         // 8-byte records: NRBUF x (RCAP + 4) slots
-    hcnv_cblock* cbuf = reinterpret_cast<hcnv_cblock*>(recraw);         // compact records: NRBUF x RCAP words
-    int32_t* diff = reinterpret_cast<int32_t*>(recraw + (COMPACT ? (size_t)NRBUF * RCAP * 4 : (size_t)NRBUF * (RCAP + 4) * 8));   // TP + 4 entries; entry TP sinks ends at the tile edge
+    // (the compact stream is not staged: a lane's share of a chunk is two 16-byte loads, prefetched into registers)
+    int32_t* diff = reinterpret_cast<int32_t*>(recraw + (COMPACT ? (size_t)0 : (size_t)NRBUF * (RCAP + 4) * 8));   // TP + 4 entries; entry TP sinks ends at the tile edge
     const bool ct_cached = p.n_contigs <= CTC;
 
     if (tid == 0) s_state = 0;
@@ -250,26 +252,38 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
         else mbar_arrive(&ws->rbar[buf]);
     };
 
-    // lane 0 only: compact stream, chunk q of a tile = records [lb + q * RCAP, ...) (whole groups, 16-byte aligned)
-    auto issue_chunk_c = [&](const hcnv_cblock* cb, const TileRec& tm, uint32_t q, int buf) {
-        const uint32_t ta = tm.lb + q * RCAP, tb = min(ta + (uint32_t)RCAP, tm.hi);
-        fence_proxy_async();
-        mbar_expect_tx(&ws->rbar[buf], (tb - ta) * 4u);
-        tma_load_1d(cbuf + (size_t)buf * RCAP, cb + ta, (tb - ta) * 4u, &ws->rbar[buf]);
+    // compact stream: chunk q of a tile = records [lb + q * RCAP, ...) = up to RCAP / HCNV_CGROUP whole groups.  Every lane
+    // loads its 4 records of each group (one 16-byte load, coalesced over the warp) and the anchors of the chunk's groups
+    // plus the one after (consistency check); the loads are issued one chunk ahead and wait in registers.
+    constexpr int NG = RCAP / HCNV_CGROUP;
+    uint4 pw[NG]; int panc[NG + 1];                 // the prefetched chunk
+    #pragma unroll
+    for (int g = 0; g < NG; ++g) pw[g] = make_uint4(0, 0, 0, 0);
+    #pragma unroll
+    for (int g = 0; g <= NG; ++g) panc[g] = 0x7fffffff;
+    auto load_chunk = [&](const ContigLite& cc, uint32_t ta, uint32_t tb) {
+        const uint32_t g0 = ta / HCNV_CGROUP, ng = (tb - ta) / HCNV_CGROUP;
+        #pragma unroll
+        for (int g = 0; g < NG; ++g)
+            pw[g] = ((uint32_t)g < ng) ? __ldg(reinterpret_cast<const uint4*>(cc.cblocks + ta + g * HCNV_CGROUP) + lane) : make_uint4(0, 0, 0, 0);
+        #pragma unroll
+        for (int g = 0; g <= NG; ++g)
+            panc[g] = ((uint32_t)g <= ng && (long long)(g0 + g) < cc.n_groups) ? __ldg(&cc.anchors[g0 + g]) : 0x7fffffff;
     };
-    auto issue_first = [&](const TileRec& tm, int buf) {      // chunk 0 of a tile + the rest of its records into L2
+    // all lanes: first chunk of a tile into registers; lane 0: the rest of its records into L2
+    auto first_chunk_c = [&](const TileRec& tm) {
         const ContigLite cc = contig_of(tm.contig);
-        if (COMPACT) {
-            issue_chunk_c(cc.cblocks, tm, 0, buf);
-            if (tm.hi - tm.lb > (uint32_t)RCAP)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cc.cblocks + tm.lb + RCAP), "r"((tm.hi - tm.lb - (uint32_t)RCAP) * 4u) : "memory");
-        } else {
-            issue_chunk(cc.blocks, tm, 0, buf);
-            const unsigned long long pa = (reinterpret_cast<unsigned long long>(cc.blocks + tm.lb) + 15ull) & ~15ull;
-            const unsigned long long pe = reinterpret_cast<unsigned long long>(cc.blocks + tm.hi) & ~15ull;
-            if (pe > pa + (unsigned long long)RCAP * 8ull)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa + (unsigned long long)RCAP * 8ull), "r"((uint32_t)(pe - pa - (unsigned long long)RCAP * 8ull)) : "memory");
-        }
+        load_chunk(cc, tm.lb, min(tm.lb + (uint32_t)RCAP, tm.hi));
+        if (lane == 0 && tm.hi - tm.lb > (uint32_t)RCAP)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cc.cblocks + tm.lb + RCAP), "r"((tm.hi - tm.lb - (uint32_t)RCAP) * 4u) : "memory");
+    };
+    auto issue_first = [&](const TileRec& tm, int buf) {      // lane 0, 8-byte records: chunk 0 of a tile + the rest of its records into L2
+        const ContigLite cc = contig_of(tm.contig);
+        issue_chunk(cc.blocks, tm, 0, buf);
+        const unsigned long long pa = (reinterpret_cast<unsigned long long>(cc.blocks + tm.lb) + 15ull) & ~15ull;
+        const unsigned long long pe = reinterpret_cast<unsigned long long>(cc.blocks + tm.hi) & ~15ull;
+        if (pe > pa + (unsigned long long)RCAP * 8ull)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa + (unsigned long long)RCAP * 8ull), "r"((uint32_t)(pe - pa - (unsigned long long)RCAP * 8ull)) : "memory");
     };
 
     // ---- this warp's tile sequence.  Tiles are claimed in order from a global ticket (a tile's predecessors are then
@@ -306,11 +320,12 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
     if (lane == 0) {
         fetch_tile_rec(tk_cur, 0);
         fetch_tile_rec(tk_n1, 1);
-        if (tk_cur < p.n_tiles) {
-            mbar_wait(&ws->mbar[0], 0);
-            const TileRec& tm = ws->tm[0];
-            if (tm.hi > tm.lb) issue_first(tm, 0);
-        }
+    }
+    __syncwarp();
+    if (tk_cur < p.n_tiles) {
+        mbar_wait(&ws->mbar[0], 0);
+        const TileRec tm = ws->tm[0];
+        if (tm.hi > tm.lb) { if (COMPACT) first_chunk_c(tm); else if (lane == 0) issue_first(tm, 0); }
     }
     int prev_last = 0;                            // lane 0: start of the last record of the previous chunk
     uint32_t consumed = 0;                        // chunks consumed so far by this warp: buffer = consumed % 2, parity = (consumed / 2) & 1
@@ -367,7 +382,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
             if (A > hi) A = hi;
             const uint32_t nch = COMPACT ? (hi - lb + RCAP - 1) / RCAP : ((hi > lb) ? max(1u, (hi - A + RCAP - 1) / RCAP) : 0u);
             // chunk 1 can start right away: its buffer was released at the end of the previous tile's record phase
-            if (lane == 0 && nch > 1) { if (COMPACT) issue_chunk_c(c.cblocks, tm, 1, (int)((consumed + 1) & 1u)); else issue_chunk(blocks, tm, 1, (int)((consumed + 1) & 1u)); }
+            if (!COMPACT && lane == 0 && nch > 1) issue_chunk(blocks, tm, 1, (int)((consumed + 1) & 1u));
             // ---- clear the difference array
             #pragma unroll 5
             for (int i = lane * 4; i < TP + 4; i += 128) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
@@ -390,24 +405,19 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
                 // LDS.128): deltas -> lane prefix -> warp scan -> + the group's anchor.  The range handed over by
                 // k_tile_index is a superset (group granular); what lies outside the tile clamps to an empty interval.
                 for (uint32_t q = 0; q < nch; ++q) {
-                    const int buf = (int)(consumed & 1u);
                     const uint32_t ta = lb + q * RCAP, tb = min(ta + (uint32_t)RCAP, hi);
-                    const uint32_t g0 = ta / HCNV_CGROUP, ng = (tb - ta) / HCNV_CGROUP;
-                    // anchors of this chunk's groups and of the group after it (consistency): issued before the wait
-                    int anc[RCAP / HCNV_CGROUP + 1];
+                    const uint32_t ng = (tb - ta) / HCNV_CGROUP;
+                    // this chunk is in registers (loaded one chunk / one tile ago); start the next one now
+                    uint4 w[NG]; int anc[NG + 1];
                     #pragma unroll
-                    for (uint32_t g = 0; g <= RCAP / HCNV_CGROUP; ++g)
-                        anc[g] = (g <= ng && (long long)(g0 + g) < c.n_groups) ? __ldg(&c.anchors[g0 + g]) : 0x7fffffff;
-                    const hcnv_cblock* R = cbuf + (size_t)buf * RCAP;
-                    mbar_wait(&ws->rbar[buf], (consumed >> 1) & 1u);
+                    for (int g = 0; g < NG; ++g) w[g] = pw[g];
+                    #pragma unroll
+                    for (int g = 0; g <= NG; ++g) anc[g] = panc[g];
+                    if (q + 1 < nch) load_chunk(c, tb, min(tb + (uint32_t)RCAP, hi));
                     int acc_u = 0, acc_r = 0;
-                    // both groups of the chunk are decoded together (their scans interleave); a chunk with one group
-                    // decodes stale words for the second one and ignores them
-                    constexpr int NG = RCAP / HCNV_CGROUP;
-                    uint4 w[NG]; int p0[NG], p1[NG], p2[NG], p3[NG], incl[NG];
+                    int p0[NG], p1[NG], p2[NG], p3[NG], incl[NG];
                     #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        w[g] = reinterpret_cast<const uint4*>(R + g * HCNV_CGROUP)[lane];
                         p0[g] = lane == 0 ? 0 : (int)(w[g].x & 0xFFFu);
                         p1[g] = p0[g] + (int)(w[g].y & 0xFFFu); p2[g] = p1[g] + (int)(w[g].z & 0xFFFu); p3[g] = p2[g] + (int)(w[g].w & 0xFFFu);
                         incl[g] = p3[g];
@@ -435,9 +445,6 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
                         one(w[g].x, base + p0[g]); one(w[g].y, base + p1[g]); one(w[g].z, base + p2[g]); one(w[g].w, base + p3[g]);
                     }
                     bad |= (acc_u < 0 ? 1 : 0) | (acc_r < 0 ? 2 : 0);
-                    ++consumed;
-                    __syncwarp();                                     // all reads of this buffer are done
-                    if (lane == 0 && q + 2 < nch) issue_chunk_c(c.cblocks, tm, q + 2, buf);
                 }
             } else
             for (uint32_t q = 0; q < nch; ++q) {
@@ -475,9 +482,17 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32) k_bin_tiles(BinK p) {
                 }
             }
             // ---- next tile: its record is here (prefetched a tile ago); start its first chunk, prefetch the record after it
+            if (COMPACT) {
+                if (tk_n1 < p.n_tiles) {                              // all lanes: the next tile's first chunk into registers
+                    const int ns = (it + 1) % 3;
+                    mbar_wait(&ws->mbar[ns], (uint32_t)((it + 1) / 3) & 1u);
+                    const TileRec tn_rec = ws->tm[ns];
+                    if (tn_rec.hi > tn_rec.lb) first_chunk_c(tn_rec);
+                }
+            }
             if (lane == 0) {
                 const int tn = tk_n1;
-                if (tn < p.n_tiles) {
+                if (!COMPACT && tn < p.n_tiles) {
                     const int ns = (it + 1) % 3;
                     mbar_wait(&ws->mbar[ns], (uint32_t)((it + 1) / 3) & 1u);
                     const TileRec& tn_rec = ws->tm[ns];
