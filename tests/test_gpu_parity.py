@@ -327,3 +327,35 @@ def test_end_to_end_bins_to_calls(ctx):
         np.testing.assert_array_equal(got["state"], want["state"])
         np.testing.assert_array_equal(got["scaled"].view(np.uint32), want["scaled"].view(np.uint32))
         assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+
+
+def test_genome_pipeline_equals_the_single_call_path(ctx):
+    """GenomePipeline (one chromosome = one end-to-end task on a worker context, compact stream from pinned-like host
+    buffers) returns the same results.txt columns as binning all contigs in one call and segmenting them as a batch."""
+    from hadoopcnv_b200.pipeline import GenomePipeline
+    names = ["chr18", "chr19", "chr20", "chr21", "chr22", "chrY"]
+    g = synth.make_genome(coverage=30, scale=0.002, device="cpu", contigs=names, seed=2024)
+    res = ctx.bin_contigs(synth.to_api_contigs(g, host=True), max_block_len=150)
+    m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total)
+    probs = []
+    for i in range(len(g)):
+        a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
+        probs.append(dict(median=res.median[a:b], mse=m32[a:b], total=t32[a:b], n=res.n[a:b], lambda1=0.01, lambda2=1.6))
+    calls = ctx.segment_batch(probs)
+    pipe = GenomePipeline(0, workers=3)
+    try:
+        rs = pipe.run(synth.to_api_contigs(g, host=True, compact=True), [c.name for c in g], max_block_len=150)
+        out = pipe.last_output
+        for i, r in enumerate(rs):
+            a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
+            assert r.name == g[i].name and r.n_bins == b - a
+            sl = slice(r.offset, r.offset + r.n_bins)
+            np.testing.assert_array_equal(out.i32[0, sl].numpy(), res.start[a:b])
+            np.testing.assert_array_equal(out.i32[1, sl].numpy(), res.end[a:b])
+            np.testing.assert_array_equal(out.i32[2, sl].numpy(), calls[i]["state"])
+            np.testing.assert_array_equal(out.i32[3, sl].numpy(), calls[i]["cn"])
+            np.testing.assert_array_equal(out.scaled[sl].numpy().view(np.uint32), calls[i]["scaled"].view(np.uint32))
+            np.testing.assert_array_equal(out.mse[sl].numpy().view(np.uint32), m32[a:b].view(np.uint32))
+            assert np.float32(r.final_loss).view(np.uint32) == np.float32(calls[i]["final_loss"]).view(np.uint32)
+    finally:
+        pipe.close()
