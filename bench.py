@@ -374,13 +374,21 @@ def run_b200(args):
     # (compact stream: 4 B per stream record, fillers and padding included, + one 4-byte anchor per 128 records)
     bytes_bin = (4 * n_stream + 4 * (n_stream // 128) if compact else 8 * n_blocks) + 16 * n_long + 4 * n_obs + 5 * n_snp + 72 * n_bins
     bytes_vit = 36 * n_bins
+    traffic = None                      # DRAM bytes per launch of the tile kernel from the committed ncu capture of this very workload
+    try:
+        if args.scale == 1.0 and args.coverage == 30.0 and W == 100:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "bin_tiles_traffic.json")))
+            traffic = tj.get("hg19_30x_wgs/%s/%d" % (args.block_format, world), {}).get("dram_bytes")
+    except Exception:
+        pass
+
     def roof(kname, nbytes):
         ms = kavg.get(kname)
         if not ms:
             return None
         ach = nbytes / (ms * 1e-3) / 1e9
         return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src}
+                "traffic": traffic if kname == "bin_tiles" else None, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src}
     dominant = max(kavg, key=kavg.get) if kavg else None
     roofline = roof(dominant, bytes_vit if dominant in ("viterbi", "mean_coverage", "traceback", "scale_depth", "sd") else bytes_bin) if dominant else None
     roofline_binning = roof("bin_tiles", bytes_bin)
