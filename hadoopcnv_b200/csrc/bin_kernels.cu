@@ -30,7 +30,7 @@ struct ContigDev {
     const uint32_t*        obs;
     long long n_blocks, n_long, n_snp, n_obs;
     long long snp_base;     // row offset of this contig in the tally table
-    long long obs_base32;   // start of this contig's observations in the launch-wide index space (each contig rounded up to 32)
+    long long obs_base32;   // start of this contig's observations in the launch-wide index space (each contig rounded up to 256)
     int32_t   length;       // positions 1..length
     int32_t   n_bins_max;   // length / W + 1
     int32_t   tile_base;    // global id of this contig's first tile
@@ -183,29 +183,32 @@ __global__ void __launch_bounds__(256) k_tally(BinK p, long long n_obs_total) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    // all contigs in one launch: groups of 32 observations never straddle contigs (each contig's share is rounded up)
-    for (long long g0 = warp * 32; g0 < n_obs_total; g0 += n_warps * 32) {
+    // all contigs in one launch: spans of 256 observations never straddle contigs (each contig's share is rounded up)
+    for (long long g0 = warp * 256; g0 < n_obs_total; g0 += n_warps * 256) {
         int lo = 0, hi = p.n_contigs - 1;
-        while (lo < hi) {                        // last contig with obs_base32 <= g0
+        while (lo < hi) {                        // last contig with obs_base <= g0
             int mid = (lo + hi + 1) >> 1;
             if (p.contigs[mid].obs_base32 <= g0) lo = mid; else hi = mid - 1;
         }
         const ContigDev& c = p.contigs[lo];
-        const long long i = g0 - c.obs_base32 + lane;
-        const bool valid = i < c.n_obs;
-        const uint32_t o = valid ? __ldg(&c.obs[i]) : 0u;
+        const long long i0 = g0 - c.obs_base32 + lane, n_obs = c.n_obs, n_snp = c.n_snp;
+        const uint32_t* __restrict__ obs = c.obs;
         uint32_t* tally = p.tally + 16 * (size_t)c.snp_base;
-        uint32_t remaining = __ballot_sync(0xffffffffu, valid);
-        while (remaining) {
-            const int leader = __ffs((int)remaining) - 1;
-            const uint32_t v = __shfl_sync(0xffffffffu, o, leader);
-            const uint32_t same = __ballot_sync(0xffffffffu, o == v) & remaining;
-            if (lane == leader) {
-                const long long idx = (long long)(v >> 4);
-                if (idx >= c.n_snp) atomicOr(&p.err[ERR_RANGE], 1);
-                else atomicAdd(&tally[(size_t)idx * 16 + (v & 15u)], (uint32_t)__popc(same));
+        uint32_t ov[8];
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) ov[u] = (i0 + 32 * u < n_obs) ? __ldg(&obs[i0 + 32 * u]) : 0xFFFFFFFFu;    // eight loads in flight
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t o = ov[u];
+            const bool valid = i0 + 32 * u < n_obs;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (!valid) continue;
+            const unsigned same = __match_any_sync(act, o);         // lanes that saw the same (site, base)
+            if (lane == __ffs((int)same) - 1) {
+                const long long idx = (long long)(o >> 4);
+                if (idx >= n_snp) atomicOr(&p.err[ERR_RANGE], 1);
+                else atomicAdd(&tally[(size_t)idx * 16 + (o & 15u)], (uint32_t)__popc(same));
             }
-            remaining &= ~same;
         }
     }
 }
@@ -402,7 +405,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             if ((rc = stage_in(ctx, in_kind, ci.obs, ci.n_obs, const_cast<uint32_t*>(d.obs)))) return rc;
         }
         d.n_blocks = ci.n_blocks; d.n_cblocks = ci.n_cblocks; d.n_long = ci.n_long; d.n_snp = ci.n_snp; d.n_obs = ci.n_obs;
-        d.obs_base32 = obs32_total; obs32_total += (ci.n_obs + 31) / 32 * 32;
+        d.obs_base32 = obs32_total; obs32_total += (ci.n_obs + 255) / 256 * 256;
         d.snp_base = os; d.length = ci.length; d.n_bins_max = ci.length / W + 1;
         d.tile_base = tile_base; d.n_tiles = (d.n_bins_max + TB - 1) / TB;
         tile_base += d.n_tiles;
@@ -462,8 +465,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     ctx->launches++;
     KT_BEGIN(ctx, HCNV_K_TALLY);
     if (tot_obs) {
-        const long long nb = (obs32_total + 255) / 256;
-        const int grid = (int)std::min<long long>(nb, (long long)ctx->sm_count * 16);
+        const long long nb = (obs32_total / 256 + 7) / 8;                 // 8 warps per CTA, one 256-observation span per warp and pass
+        const int grid = (int)std::max<long long>(1, std::min<long long>(nb, (long long)ctx->sm_count * 16));
         k_tally<<<grid, 256, 0, ctx->stream>>>(k, obs32_total);
         HCNV_CUDA(ctx, cudaGetLastError());
         ctx->launches++;

@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
                     #pragma unroll
                     for (int g = 0; g <= NG; ++g) anc[g] = panc[g];
                     if (q + 1 < nch) load_chunk(c, tb, min(tb + (uint32_t)RCAP, hi));
-                    int acc_u = 0, acc_r = 0;
+                    int acc_u = 0;
+                    int mx_end = (int)0x80000000, mx_len = 0;          // range checks: furthest end (tile relative) and longest block
                     int p0[NG], p1[NG], p2[NG], p3[NG], incl[NG];
                     #pragma unroll
                     for (int g = 0; g < NG; ++g) {
@@ -435,16 +436,18 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
                         if (live) { if (lane == 31) acc_u |= anc[g + 1] - (base + p3[g]); acc_u |= anc[g]; }
                         auto one = [&](uint32_t word, int start0) {
                             const int len = (int)((word >> 12) & 0xFFFu);
-                            int s_ = start0 - T0m1, e_ = s_ + len;
-                            s_ = min(max(s_, 0), TP); e_ = min(max(e_, 0), TP);      // clamped: memory-safe whatever the record says
-                            bool on = live && e_ > s_;                               // fillers, padding, records outside the tile
-                            if (live) acc_r |= start0 | (length - len - start0) | (maxlen - len);
+                            const int s_ = start0 - T0m1, e_ = s_ + len;                 // tile-relative [s_, e_)
+                            // one-sided clamps are enough: a record off the tile gets e <= s and touches nothing
+                            const int sc = max(s_, 0), ec = min(e_, TP);
+                            bool on = live && ec > sc;                               // fillers, padding, records outside the tile
+                            if (live) { mx_end = max(mx_end, e_); mx_len = max(mx_len, len); }
                             if (FILTER) { const uint32_t mq = word >> 24; on = on && ((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u); }
-                            if (on) { atomicAdd(&diff[s_], 1); atomicAdd(&diff[e_], -1); }
+                            if (on) { atomicAdd(&diff[sc], 1); atomicAdd(&diff[ec], -1); }
                         };
                         one(w[g].x, base + p0[g]); one(w[g].y, base + p1[g]); one(w[g].z, base + p2[g]); one(w[g].w, base + p3[g]);
                     }
-                    bad |= (acc_u < 0 ? 1 : 0) | (acc_r < 0 ? 2 : 0);
+                    // starts are >= their group's anchor (deltas are unsigned), so a non-negative anchor covers start0 >= 0
+                    bad |= (acc_u < 0 ? 1 : 0) | ((mx_len > maxlen || (long long)mx_end + T0m1 > (long long)length) ? 2 : 0);
                 }
             } else
             for (uint32_t q = 0; q < nch; ++q) {

@@ -53,11 +53,13 @@ class GenomePipeline:
         self.ctxs = [Context(device) for _ in range(max(1, workers))]
         self._pool = ThreadPoolExecutor(max_workers=len(self.ctxs))
         self._scratch = {}
+        self._d2h = {}
         self.trace = None                               # set to a list to collect (name, worker, [bin, text, segment, d2h] ms, start ms)
         self._t0 = 0.0
 
     def close(self):
         self._pool.shutdown(wait=True)
+        self._scratch = {}
         for c in self.ctxs:
             c.close()
         self.ctxs = []
@@ -91,7 +93,11 @@ class GenomePipeline:
         call = ctx.segment_batch([dict(median=res.median, mse=m32, total=t32, n=res.n, lambda1=lambda1, lambda2=lambda2,
                                        scaled=scaled[:nb], state=state[:nb], cn=cn[:nb])])[0]
         t_.append(time.perf_counter())
-        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        # (the library calls above return with their stream drained, so the download needs no dependency on it; it runs on a
+        # torch-owned stream per worker: torch's pinned-memory allocator remembers the streams a block was used on)
+        stream = self._d2h.get(w)
+        if stream is None:
+            stream = self._d2h[w] = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(stream):
             out.i32[0, o:o + nb].copy_(res.start, non_blocking=True)
             out.i32[1, o:o + nb].copy_(res.end, non_blocking=True)
