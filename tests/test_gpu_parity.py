@@ -359,3 +359,69 @@ def test_genome_pipeline_equals_the_single_call_path(ctx):
             assert np.float32(r.final_loss).view(np.uint32) == np.float32(calls[i]["final_loss"]).view(np.uint32)
     finally:
         pipe.close()
+
+
+def _random_contig(rng, length, n_reads, read_len, n_snp, pile=None):
+    """blocks (sorted), snp table and consistent observations for one contig; optional pile-up (pos, count)."""
+    starts = rng.integers(0, max(1, length - read_len), n_reads)
+    lens = rng.integers(1, read_len + 1, n_reads)
+    if pile is not None:
+        starts = np.concatenate([starts, np.full(pile[1], pile[0])]); lens = np.concatenate([lens, np.full(pile[1], read_len)])
+    lens = np.minimum(lens, length - starts)
+    order = np.argsort(starts, kind="stable")
+    blocks = H.pack_blocks(starts[order], lens[order], rng.integers(0, 61, len(starts)))
+    snp = np.unique(rng.integers(1, length + 1, n_snp)).astype(np.int32) if n_snp else np.zeros(0, np.int32)
+    zyg = rng.choice(np.array([0, -1, -2], np.int8), len(snp))
+    depth, _ = O.depth_from_blocks(blocks, length)
+    obs = [(si << 4) | int(b) for si, p in enumerate(snp) for b in rng.choice([1, 2, 4, 8], int(depth[p]))]
+    return blocks, snp, zyg, np.array(obs, np.uint32)
+
+
+@pytest.mark.parametrize("W", [1, 3, 10, 64, 100, 250, 1600])
+def test_binning_random_small_contigs_both_formats(ctx, W):
+    """Many small contigs (more than the kernel's shared-memory contig cache holds), odd and tiny bin widths, a pile-up of
+    70 000 reads on one position (more records in one tile than 16 bits hold), both block formats, against the oracle."""
+    rng = np.random.default_rng(1000 + W)
+    cases = []
+    for i in range(40):
+        length = int(rng.integers(1, 6000))
+        n_reads = int(rng.integers(0, 400))
+        pile = (int(rng.integers(0, max(1, length - 60))), 70000) if i == 7 else None
+        cases.append((length,) + _random_contig(rng, length, n_reads, min(60, length), int(rng.integers(0, 30)), pile))
+    want = [O.bin_contig(b.view(O.BLOCK_DTYPE), L_, W, s if len(s) else None, z if len(s) else None, o if len(s) else None)
+            for (L_, b, s, z, o) in cases]
+    for compact in (False, True):
+        contigs = []
+        for (L_, b, s, z, o) in cases:
+            snp_args = (s, z, o if len(o) else None) if len(s) else (None, None, None)
+            if compact and len(b):
+                cb, an = H.compact_blocks(b)
+                contigs.append(H.Contig(L_, None, None, *snp_args, cb, an))
+            else:
+                contigs.append(H.Contig(L_, b if len(b) else None, None, *snp_args))
+        if compact and not any(c.cblocks is not None for c in contigs):
+            continue
+        if compact:                                   # one form per call: contigs without blocks carry neither
+            pass
+        res = ctx.bin_contigs(contigs, bin_width=W, max_block_len=60)
+        for i in range(len(cases)):
+            assert_bins_equal(res.contig(i), want[i])
+
+
+def test_binning_long_blocks_over_many_tiles_and_bad_snp_tables(ctx):
+    rng = np.random.default_rng(77)
+    length = 200000
+    b, s, z, o = _random_contig(rng, length, 3000, 100, 0)
+    longs = H.pack_long_blocks([0, 50000, 120000, 199000], [60000, 100000, 30000, 1000], [60, 0, 30, 60])
+    depth, _ = O.depth_from_blocks(b, length)
+    for lb in longs:
+        depth[lb["start0"] + 1: lb["start0"] + 1 + lb["len"]] += 1
+    want = O.bin_reduce(depth, length, 100, None, None, None)
+    for contig in (H.Contig(length, b, longs), H.Contig(length, None, longs, None, None, None, *H.compact_blocks(b))):
+        assert_bins_equal(ctx.bin_contigs([contig], bin_width=100).contig(0), want)
+    # SNP tables the reference could never produce are refused
+    for snp, code in ((np.array([50, 40], np.int32), L.HCNV_E_UNSORTED), (np.array([40, 40], np.int32), L.HCNV_E_UNSORTED),
+                      (np.array([length + 1], np.int32), L.HCNV_E_RANGE)):
+        with pytest.raises(H.HcnvError) as e:
+            ctx.bin_contigs([H.Contig(length, b, None, snp, np.zeros(len(snp), np.int8), None)], bin_width=100)
+        assert e.value.status == code
