@@ -66,7 +66,7 @@ class Config(C.Structure):
 # every symbol include/hcnv.h declares (tests check the library exports all of them)
 EXPORTS = [
     "hcnv_abi_sizes", "hcnv_ctx_create", "hcnv_ctx_destroy", "hcnv_last_error", "hcnv_strerror", "hcnv_version", "hcnv_ctx_stream",
-    "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_ctx_stat", "hcnv_bin_params_default", "hcnv_bin_contigs",
+    "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_ctx_set_kernel_timing", "hcnv_ctx_stat", "hcnv_bin_params_default", "hcnv_bin_contigs",
     "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
     "hcnv_write_bins_text", "hcnv_write_results_text",
     "hcnv_read_bins_text", "hcnv_bins_text_n_chromosomes", "hcnv_bins_text_get", "hcnv_bins_text_free",
@@ -113,6 +113,8 @@ def lib():
     L.hcnv_ctx_kernel_launches.argtypes = [C.c_void_p]
     L.hcnv_ctx_kernel_launches.restype = C.c_int64
     L.hcnv_ctx_synchronize.argtypes = [C.c_void_p]
+    L.hcnv_ctx_set_kernel_timing.argtypes = [C.c_void_p, C.c_uint32]
+    L.hcnv_ctx_set_kernel_timing.restype = None
     L.hcnv_ctx_kernel_ms.argtypes = [C.c_void_p, C.c_int]
     L.hcnv_ctx_kernel_ms.restype = C.c_float
     L.hcnv_ctx_stat.argtypes = [C.c_void_p, C.c_int]

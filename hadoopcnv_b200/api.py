@@ -164,6 +164,18 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._lib.hcnv_ctx_kernel_launches(self._h))
 
+    def set_kernel_timing(self, which="all"):
+        """Which kernels get CUDA timing events: "all", "default" (the dominant binning kernel only) or names from _lib.KERNELS."""
+        if which == "all":
+            mask = 0xFFFFFFFF
+        elif which == "default":
+            mask = 1 << L.KERNELS["bin_tiles"]
+        else:
+            mask = 0
+            for name in which:
+                mask |= 1 << L.KERNELS[name]
+        self._lib.hcnv_ctx_set_kernel_timing(self._h, mask)
+
     def kernel_ms(self) -> dict:
         """Device time (ms, CUDA events on the context's stream) of the most recent launch of each kernel."""
         out = {}

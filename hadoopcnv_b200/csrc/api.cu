@@ -80,6 +80,8 @@ int64_t hcnv_ctx_stat(const hcnv_ctx* c, int which) {
     switch (which) { case 0: return c->vit_segments; case 1: return c->vit_replayed; case 2: return c->vit_repairs; default: return -1; }
 }
 
+void hcnv_ctx_set_kernel_timing(hcnv_ctx* c, uint32_t mask) { if (c) c->kt_mask = mask; }
+
 float hcnv_ctx_kernel_ms(hcnv_ctx* c, int which) {
     if (!c || which < 0 || which >= HCNV_K_COUNT || !c->kt_valid[which]) return -1.f;
     float ms = -1.f;

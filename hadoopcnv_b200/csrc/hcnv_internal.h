@@ -57,9 +57,13 @@ struct hcnv_ctx {
     cudaEvent_t  kt_a[HCNV_K_COUNT] = {};  // per-kernel start/stop events on `stream`
     cudaEvent_t  kt_b[HCNV_K_COUNT] = {};
     bool         kt_valid[HCNV_K_COUNT] = {};
+    uint32_t     kt_mask = 1u << HCNV_K_BIN_TILES;   // which kernels get timing events (default: the dominant one only)
 };
-#define KT_BEGIN(ctx, slot) cudaEventRecord((ctx)->kt_a[slot], (ctx)->stream)
-#define KT_END(ctx, slot)   do { cudaEventRecord((ctx)->kt_b[slot], (ctx)->stream); (ctx)->kt_valid[slot] = true; } while (0)
+// per-kernel timing events are recorded only for the kernels selected in kt_mask (hcnv_ctx_set_kernel_timing): an event
+// pair between every two launches of a step that lasts ~10 ms is a measurable share of it
+#define KT_ON(ctx, slot)    (((ctx)->kt_mask >> (slot)) & 1u)
+#define KT_BEGIN(ctx, slot) do { if (KT_ON(ctx, slot)) cudaEventRecord((ctx)->kt_a[slot], (ctx)->stream); } while (0)
+#define KT_END(ctx, slot)   do { if (KT_ON(ctx, slot)) { cudaEventRecord((ctx)->kt_b[slot], (ctx)->stream); (ctx)->kt_valid[slot] = true; } else (ctx)->kt_valid[slot] = false; } while (0)
 
 #define HCNV_CUDA(ctx, call)                                                                   \
     do {                                                                                       \

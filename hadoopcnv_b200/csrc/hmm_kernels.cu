@@ -465,21 +465,28 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
     k_text_roundtrip_fix<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32, d_work, d_wn, work_cap);
     KT_END(ctx, HCNV_K_TEXT_ROUNDTRIP);
     ctx->launches += 2;
-    {
-        unsigned long long wn = 0;
-        HCNV_CUDA(ctx, cudaMemcpyAsync(&wn, d_wn, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if ((long long)wn > work_cap) {
-            k_text_roundtrip_all<<<grid, 256, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32);
-            ctx->launches++;
-        }
-    }
     HCNV_CUDA(ctx, cudaGetLastError());
-    if (!dev) {
-        HCNV_CUDA(ctx, cudaMemcpyAsync(mse_f32, d_m32, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        if (total) HCNV_CUDA(ctx, cudaMemcpyAsync(total_f32, d_t32, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    // one host round trip in the common case: the work-list counter comes back with the results; only if the list
+    // overflowed (more than one value in seven exactly half way between two floats) is everything redone the slow way
+    HCNV_CUDA(ctx, ctx->pin[1].reserve(64));
+    unsigned long long* h_wn = ctx->pin[1].as<unsigned long long>();
+    HCNV_CUDA(ctx, cudaMemcpyAsync(h_wn, d_wn, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    auto download = [&]() -> int {
+        if (!dev) {
+            HCNV_CUDA(ctx, cudaMemcpyAsync(mse_f32, d_m32, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+            if (total) HCNV_CUDA(ctx, cudaMemcpyAsync(total_f32, d_t32, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return HCNV_OK;
+    };
+    int rc = download();
+    if (rc) return rc;
+    if ((long long)*h_wn > work_cap) {
+        k_text_roundtrip_all<<<grid, 256, 0, ctx->stream>>>(d_mse, d_tot, n, d_m32, d_t32);
+        ctx->launches++;
+        HCNV_CUDA(ctx, cudaGetLastError());
+        if ((rc = download())) return rc;
     }
-    HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return HCNV_OK;
 }
 
@@ -606,6 +613,7 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         k_vit_p1<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_epred, d_ti, d_flags);
         KT_END(ctx, HCNV_K_VIT_P1);
         ctx->launches += 3;
+        std::vector<int> repl(n_problems, 0);
         for (int iter = 0; ; ++iter) {
             const unsigned gc = (unsigned)((NC + 63) / 64);
             KT_BEGIN(ctx, HCNV_K_VIT_P1B);
@@ -623,7 +631,10 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
             KT_END(ctx, HCNV_K_VIT_P3);
             ctx->launches += 2;
             HCNV_CUDA(ctx, cudaGetLastError());
+            // one host round trip per pass: the verification verdicts, the replay counters and the diagnostics together
             HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), dprobs, sizeof(SegDev) * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyAsync(repl.data(), d_repl, 4 * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyFromSymbolAsync(ctx->vdbg, g_vdbg, sizeof ctx->vdbg, 0, cudaMemcpyDeviceToHost, ctx->stream));
             HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             bool again = false;
             for (int i = 0; i < n_problems; ++i)
@@ -632,10 +643,6 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
             ctx->vit_repairs++;
             if (iter >= 16) return hcnv_fail(ctx, HCNV_E_INTERNAL, "segment-parallel Viterbi did not converge");
         }
-        std::vector<int> repl(n_problems, 0);
-        HCNV_CUDA(ctx, cudaMemcpyAsync(repl.data(), d_repl, 4 * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaMemcpyFromSymbolAsync(ctx->vdbg, g_vdbg, sizeof ctx->vdbg, 0, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->vit_segments = total_segs; ctx->vit_replayed = 0;
         for (int i = 0; i < n_problems; ++i) if (h[i].par && !h[i].irregular && !h[i].skip) ctx->vit_replayed += repl[i];
     } else { ctx->vit_segments = 0; ctx->vit_replayed = 0; }

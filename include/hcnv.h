@@ -83,6 +83,9 @@ int         hcnv_ctx_synchronize(hcnv_ctx* ctx);
 #define HCNV_K_SNP_MSE        16    /* BAF statistics of the bins that hold SNP sites             */
 #define HCNV_K_COUNT          17
 float       hcnv_ctx_kernel_ms(hcnv_ctx* ctx, int which);
+/* which kernels get timing events: bit k = HCNV_K_* number k; default 1 << HCNV_K_BIN_TILES (an event pair around every
+ * launch costs a measurable share of a ~10 ms step); ~0u times them all */
+void        hcnv_ctx_set_kernel_timing(hcnv_ctx* ctx, uint32_t mask);
 /* counters of the last hcnv_segment_batch call: 0 = segments of the segment-parallel Viterbi, 1 = segments that were
  * replayed with the sequential exact step (binade crossings, rounding ties), 2 = verification failures repaired (cumulative) */
 int64_t     hcnv_ctx_stat(const hcnv_ctx* ctx, int which);
