@@ -265,9 +265,17 @@ __device__ __forceinline__ PMap pm_shfl_up(const PMap& m, int o) {
 #include "mean_cluster.cuh"
 
 // scale_depth, Hmm.java:121-135 (element-wise; all problems in one launch via a block->problem map)
-__global__ void k_scale_depth(SegDev* probs, const int* __restrict__ blk_prob, const long long* __restrict__ blk_first) {
-    SegDev& P = probs[blk_prob[blockIdx.x]];
-    long long i = blk_first[blockIdx.x] + threadIdx.x;
+// block -> (chromosome, first marker): blk_base[i] = number of 256-marker blocks before chromosome i (n_probs + 1 entries)
+__device__ __forceinline__ int blk_find(const int* __restrict__ blk_base, int n_probs, int b) {
+    int lo = 0, hi = n_probs - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (__ldg(&blk_base[mid]) <= b) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+__global__ void k_scale_depth(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
+    const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
+    SegDev& P = probs[pi];
+    long long i = (long long)((int)blockIdx.x - __ldg(&blk_base[pi])) * 256 + threadIdx.x;
     if (i >= P.M) return;
     float mean = P.mean;
     float s = __fdiv_rn(__fsub_rn(__ldg(&P.median[i]), mean), mean);
@@ -410,9 +418,10 @@ __global__ void __launch_bounds__(32) k_viterbi_seq(SegDev* probs, float alpha) 
 }
 
 // best_state / cn columns (Hmm.java:234-237, 483-484)
-__global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_prob, const long long* __restrict__ blk_first) {
-    SegDev& P = probs[blk_prob[blockIdx.x]];
-    long long i = blk_first[blockIdx.x] + threadIdx.x;
+__global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
+    const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
+    SegDev& P = probs[pi];
+    long long i = (long long)((int)blockIdx.x - __ldg(&blk_base[pi])) * 256 + threadIdx.x;
     const long long M = P.M;
     if (i >= M) return;
     if (P.par && !P.irregular && !P.skip) return;    // k_vit_p3 already wrote the calls
@@ -519,7 +528,7 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         HCNV_CUDA(ctx, ctx->buf[H_OUT_I32].reserve(4 * 2 * (size_t)totM));
     }
     long long off = 0;
-    std::vector<int> blk_prob; std::vector<long long> blk_first;
+    std::vector<int> blk_base(n_problems + 1, 0);          // 256-marker blocks before each chromosome (scale / traceback grids)
     const int VSEG = VSEG_DEFAULT;
     std::vector<int> seg_base(n_problems + 1, 0);
     for (int i = 0; i < n_problems; ++i) {
@@ -546,7 +555,8 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
             d.state = ctx->buf[H_OUT_I32].as<int32_t>() + off;
             d.cn = ctx->buf[H_OUT_I32].as<int32_t>() + totM + off;
         }
-        for (long long b = 0; b < M; b += 256) { blk_prob.push_back(i); blk_first.push_back(b); }
+        if ((M + 255) / 256 + blk_base[i] > 0x7fffffffLL) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers in one call");
+        blk_base[i + 1] = blk_base[i] + (int)((M + 255) / 256);
         off += M;
         d.par = (!(flags & HCNV_SEG_SEQUENTIAL) && M >= V_PAR_MIN_MARKERS) ? 1 : 0;
         d.n_seg = d.par ? (int)((M - 1 + VSEG - 1) / VSEG) : 0;
@@ -554,15 +564,13 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         seg_base[i + 1] = seg_base[i] + d.n_seg;
     }
     const int total_segs = seg_base[n_problems];
-    const size_t nblk = blk_prob.size();
+    const size_t nblk = (size_t)blk_base[n_problems];
     HCNV_CUDA(ctx, ctx->buf[H_PROBS].reserve(sizeof(SegDev) * (size_t)n_problems));
-    HCNV_CUDA(ctx, ctx->buf[H_BLKMAP].reserve(12 * nblk + 64));
+    HCNV_CUDA(ctx, ctx->buf[H_BLKMAP].reserve(4 * (size_t)(n_problems + 1) + 64));
     SegDev* dprobs = ctx->buf[H_PROBS].as<SegDev>();
-    long long* d_first = ctx->buf[H_BLKMAP].as<long long>();
-    int* d_prob = (int*)(d_first + nblk);
+    int* d_blkbase = ctx->buf[H_BLKMAP].as<int>();
     HCNV_CUDA(ctx, cudaMemcpyAsync(dprobs, h.data(), sizeof(SegDev) * (size_t)n_problems, cudaMemcpyHostToDevice, ctx->stream));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(d_first, blk_first.data(), 8 * nblk, cudaMemcpyHostToDevice, ctx->stream));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(d_prob, blk_prob.data(), 4 * nblk, cudaMemcpyHostToDevice, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemcpyAsync(d_blkbase, blk_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream));
 
     const int wpb = 4;   // warps per block for the one-warp-per-chromosome kernels
     KT_BEGIN(ctx, HCNV_K_MEAN_COVERAGE);
@@ -570,7 +578,7 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
     k_mean_coverage<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
     KT_END(ctx, HCNV_K_MEAN_COVERAGE);
     KT_BEGIN(ctx, HCNV_K_SCALE_DEPTH);
-    k_scale_depth<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_prob, d_first);
+    k_scale_depth<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_blkbase, n_problems);
     KT_END(ctx, HCNV_K_SCALE_DEPTH);
     KT_BEGIN(ctx, HCNV_K_SD);
     k_sd<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems, alpha);
@@ -651,7 +659,7 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
     k_viterbi_seq<<<n_problems, 32, 0, ctx->stream>>>(dprobs, alpha);
     KT_END(ctx, HCNV_K_VITERBI);
     KT_BEGIN(ctx, HCNV_K_TRACEBACK);
-    k_traceback<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_prob, d_first);
+    k_traceback<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_blkbase, n_problems);
     KT_END(ctx, HCNV_K_TRACEBACK);
     ctx->launches += 2;
     HCNV_CUDA(ctx, cudaGetLastError());
