@@ -595,7 +595,7 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         for (int i = 0; i < n_problems; ++i) chunk_base[i + 1] = chunk_base[i] + (h[i].n_seg + VCH - 1) / VCH;
         const size_t NC = (size_t)chunk_base[n_problems];
         size_t o_ls = o_ti + 288 * S, o_tc = (o_ls + 24 * (S + (size_t)n_problems) + 255) / 256 * 256;
-        size_t o_cinfo = o_tc + 288 * NC, o_cbase = o_cinfo + 4 * NC, bytes = o_cbase + 4 * (size_t)(n_problems + 1);
+        size_t o_cinfo = o_tc + 288 * NC, o_cbase = o_cinfo + 4 * NC, o_tie = o_cbase + 4 * (size_t)(n_problems + 1), bytes = o_tie + 4 * (S + 4);
         HCNV_CUDA(ctx, ctx->buf[H_VPAR].reserve(bytes));
         char* vb = ctx->buf[H_VPAR].as<char>();
         int* d_tc = (int*)(vb + o_tc); int* d_cinfo = (int*)(vb + o_cinfo); int* d_cbase = (int*)(vb + o_cbase);
@@ -604,6 +604,8 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         int* d_force = (int*)(vb + o_force); int* d_repl = (int*)(vb + o_repl);
         float* d_tf = (float*)(vb + o_tf); int* d_ti = (int*)(vb + o_ti); float* d_ls = (float*)(vb + o_ls);
         HCNV_CUDA(ctx, cudaMemcpyAsync(d_segbase, seg_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream));
+        int* d_tiecnt = (int*)(vb + o_tie); int* d_tielist = d_tiecnt + 4;      // segments that met a rounding tie (P1's second pass)
+        HCNV_CUDA(ctx, cudaMemsetAsync(d_tiecnt, 0, 16, ctx->stream));
         HCNV_CUDA(ctx, cudaMemsetAsync(d_force, 0, 4 * S, ctx->stream));
         { int z[16] = {0}; HCNV_CUDA(ctx, cudaMemcpyToSymbolAsync(g_vdbg, z, sizeof z, 0, cudaMemcpyHostToDevice, ctx->stream)); }
         const unsigned gs = (unsigned)((S + 127) / 128);
@@ -618,7 +620,9 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         }
         KT_END(ctx, HCNV_K_VIT_P0C);
         KT_BEGIN(ctx, HCNV_K_VIT_P1);
-        k_vit_p1<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_epred, d_ti, d_flags);
+        k_vit_p1<false><<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_epred, d_ti, d_flags, d_tielist, d_tiecnt);
+        k_vit_p1<true><<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_epred, d_ti, d_flags, d_tielist, d_tiecnt);
+        ctx->launches++;
         KT_END(ctx, HCNV_K_VIT_P1);
         ctx->launches += 3;
         std::vector<int> repl(n_problems, 0);

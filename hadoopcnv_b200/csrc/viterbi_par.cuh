@@ -218,10 +218,16 @@ __device__ __forceinline__ void vadd(int q, bool tie, int& inc, int& par) {
 // holds min path costs relative to the start value; the absolute parity of an entry w is (pi + w) & 1, which is
 // all a later tie needs.  Without ties the two parity variants are identical.
 #define VT_WORDS 72
+// Two instantiations: FULL = false runs every segment with the one matrix that is enough as long as no addend is an exact
+// half-unit tie (92 % of the segments; half the registers, so more resident warps) and hands a segment that meets a tie
+// over to a work list; FULL = true redoes the listed segments with both parity variants.
+template <bool FULL>
 __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __restrict__ seg_base, int n_probs, int total_segs,
                                                 int VSEG, float alpha, const int* __restrict__ epred,
-                                                int* __restrict__ Ti, int* __restrict__ flags) {
+                                                int* __restrict__ Ti, int* __restrict__ flags,
+                                                int* __restrict__ tie_list, int* __restrict__ tie_count) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (FULL) { if (g >= *tie_count) return; g = tie_list[g]; }
     if (g >= total_segs) return;
     int pi = find_prob(seg_base, n_probs, g);
     SegDev& P = probs[pi];
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __rest
     #pragma unroll
     for (int i = 0; i < 6; ++i)
         #pragma unroll
-        for (int c = 0; c < 6; ++c) { v0[i][c] = (i == c) ? 0 : V_INF_I; v1[i][c] = v0[i][c]; }
+        for (int c = 0; c < 6; ++c) { v0[i][c] = (i == c) ? 0 : V_INF_I; if (FULL) v1[i][c] = v0[i][c]; }
     bool split = false;                             // v1 differs from v0 only after the first tie
     for (long long m = a; m < b; ++m) {
         float sd, mse[6], A[6], B[6];
@@ -273,7 +279,10 @@ __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __rest
                 }
             };
             plain(v0);
-            if (split) plain(v1);
+            if (FULL) { if (split) plain(v1); }
+        } else if (!FULL) {
+            tie_list[atomicAdd(tie_count, 1)] = g;      // a tie: the two-matrix kernel takes this segment over
+            return;
         } else {
             if (!split) {
                 split = true;
@@ -322,12 +331,12 @@ __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __rest
     for (int i = 0; i < 6; ++i)
         #pragma unroll
         for (int c = 0; c < 6; ++c) {
-            const int w1 = split ? v1[i][c] : v0[i][c];
+            const int w1 = (FULL && split) ? v1[i][c] : v0[i][c];
             out[i * 6 + c] = v0[i][c]; out[36 + i * 6 + c] = w1;
             bad |= v0[i][c] >= (V_INF_I >> 1) || w1 >= (V_INF_I >> 1);
         }
     flags[g] = bad ? 0 : 1;
-    atomicAdd(&g_vdbg[0], 1); if (ovf) atomicAdd(&g_vdbg[1], 1); if (bad && !ovf) atomicAdd(&g_vdbg[2], 1); if (split) atomicAdd(&g_vdbg[3], 1);
+    atomicAdd(&g_vdbg[0], 1); if (ovf) atomicAdd(&g_vdbg[1], 1); if (bad && !ovf) atomicAdd(&g_vdbg[2], 1); if (FULL && split) atomicAdd(&g_vdbg[3], 1);
 }
 
 // ---------------------------------------------------------------------------------------------- exact float step
