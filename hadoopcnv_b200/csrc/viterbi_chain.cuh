@@ -221,6 +221,7 @@ __device__ __forceinline__ float vit_replay(const SegDev& P, const VitConsts& k,
         #pragma unroll
         for (int i = 0; i < 6; ++i) { long long idx = m0 * 6 + i * 32 + lane; mv[i] = (idx < b * 6) ? __ldg(&P.mse[idx]) : 0.f; }
         const int cnt = (int)min((long long)32, b - m0);
+        #pragma unroll 4
         for (int jj = 0; jj < cnt; ++jj) {
             const float sdj = __shfl_sync(0xffffffffu, sdv, jj);
             const int el = jj * 6 + c;
@@ -230,7 +231,7 @@ __device__ __forceinline__ float vit_replay(const SegDev& P, const VitConsts& k,
             const float dev = __fsub_rn(sdj, c_mu[c]);
             const float A = __fmul_rn(k.oma, __fmul_rn(dev, dev)), B = __fmul_rn(k.alpha, msel);
             L = lanes_step(L, A, B, c3, c4);
-            if ((double)L == 1e10) bad1e10 = 1;
+            if (L == 1e10f) bad1e10 = 1;           // (1e10 is a float: 9765625 * 2^10)
         }
     }
     return L;

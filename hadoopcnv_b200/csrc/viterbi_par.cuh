@@ -23,7 +23,9 @@
 #include <cuda_pipeline.h>
 
 #define VSEG_DEFAULT 64
-#define V_EMIN 6                   // binades below 2^6: u so small that per-segment sums could overflow int32 -> replay
+#ifndef V_EMIN
+#define V_EMIN 4                   // binades below 2^4: u so small that per-segment sums get close to int32 -> replay (P3 verifies every segment anyway)
+#endif
 #define V_INF_I (1 << 29)
 #define V_INF_F 1.0e30f
 #define V_PAR_MIN_MARKERS 4096     // shorter chromosomes go to the one-warp kernel
