@@ -327,6 +327,8 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
         const TileRec tm = ws->tm[0];
         if (tm.hi > tm.lb) { if (COMPACT) first_chunk_c(tm); else if (lane == 0) issue_first(tm, 0); }
     }
+    int lb_contig = -1;                           // contig whose first 64 long blocks are in lbk0 / lbk1
+    hcnv_long_block lbk0 = {0, 0, 0, 0}, lbk1 = {0, 0, 0, 0};
     int prev_last = 0;                            // lane 0: start of the last record of the previous chunk
     uint32_t consumed = 0;                        // chunks consumed so far by this warp: buffer = consumed % 2, parity = (consumed / 2) & 1
 
@@ -387,16 +389,26 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
             #pragma unroll 5
             for (int i = lane * 4; i < TP + 4; i += 128) *reinterpret_cast<int4*>(diff + i) = make_int4(0, 0, 0, 0);
             __syncwarp();
-            // ---- blocks of any length (few)
-            for (long long i = lane; i < c.n_long; i += 32) {
-                hcnv_long_block r = c.longs[i];
+            // ---- blocks of any length (few).  The first 64 of the contig stay in registers (lane l holds blocks l and l + 32)
+            // from tile to tile: a warp's consecutive tiles are nearly always on the same contig, and a dependent
+            // global load per tile was a few per cent of the tile time.
+            if (lb_contig != tm.contig) {
+                lb_contig = tm.contig;
+                const hcnv_long_block z = {0, 0, 0, 0};
+                lbk0 = (lane < c.n_long) ? c.longs[lane] : z;
+                lbk1 = (lane + 32 < c.n_long) ? c.longs[lane + 32] : z;
+            }
+            auto long_block = [&](const hcnv_long_block& r) {
                 long long s1 = (long long)r.start0 + 1, e1 = s1 + r.len;
-                if (r.len < 0 || r.start0 < 0 || e1 - 1 > c.length) { bad |= 2; continue; }
+                if (r.len < 0 || r.start0 < 0 || e1 - 1 > c.length) { bad |= 2; return; }
                 uint32_t mq = (uint32_t)r.mapq & 255u;
-                if (FILTER && !((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u)) continue;
+                if (FILTER && !((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u)) return;
                 long long s = max(s1, (long long)T0), e = min(e1, T1l);
                 if (e > s) { atomicAdd(&diff[(int)(s - T0)], 1); atomicAdd(&diff[(int)(e - T0)], -1); }
-            }
+            };
+            if (lane < c.n_long) long_block(lbk0);
+            if (lane + 32 < c.n_long) long_block(lbk1);
+            for (long long i = 64 + lane; i < c.n_long; i += 32) long_block(c.longs[i]);
             // ---- the sorted short-block stream, chunk by chunk
             const int T0m1 = T0 - 1;
             const int maxlen = p.maxlen, length = c.length;
