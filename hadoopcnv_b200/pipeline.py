@@ -8,12 +8,15 @@ the three C-ABI seams on one worker:
     ->  the results.txt columns (Hmm.java:479-490) copied back into the caller's pinned arrays
 
 Workers are threads with one `Context` (= one CUDA stream pair and its scratch memory) each, like the task slots of a
-Hadoop node; `ctypes` releases the GIL inside the library, so while one worker's chromosome is being uploaded another
-one computes and a third one downloads: PCIe runs in both directions at once and the kernels hide behind the copies.
+Hadoop node; `ctypes` releases the GIL inside the library.  The upload is what bounds the path, so it never pauses: one
+copy stream sends every chromosome's packed records (longest first) into device staging buffers back to back, a worker
+picks a chromosome up as soon as its records have landed, and its kernels and the download of its results run behind
+the uploads of the chromosomes after it: PCIe is busy in both directions from the first byte to the last.
 There is no CPU fallback anywhere on this path.
 """
 from __future__ import annotations
 
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Sequence
 
@@ -54,12 +57,16 @@ class GenomePipeline:
         self._pool = ThreadPoolExecutor(max_workers=len(self.ctxs))
         self._scratch = {}
         self._d2h = {}
+        self._copy = None                               # the upload stream
+        self._staging = {}                              # chromosome index -> device staging buffers of its packed arrays
         self.trace = None                               # set to a list to collect (name, worker, [bin, text, segment, d2h] ms, start ms)
         self._t0 = 0.0
+        self._max_cap = 1
 
     def close(self):
         self._pool.shutdown(wait=True)
         self._scratch = {}
+        self._staging = {}
         for c in self.ctxs:
             c.close()
         self.ctxs = []
@@ -75,9 +82,9 @@ class GenomePipeline:
         t_ = [time.perf_counter()]
         ctx = self.ctxs[w]
         dev = torch.device("cuda", self.device)
-        cap = int(contig.length) // bin_width + 1
+        cap = max(int(contig.length) // bin_width + 1, self._max_cap)
         sc = self._scratch.get(w)
-        if sc is None or sc[0] < cap:                          # per-worker device scratch, grown to its largest chromosome
+        if sc is None or sc[0] < cap:                          # per-worker device scratch, sized for the largest chromosome
             sc = (cap, ctx.alloc_bins(cap, True, 1), torch.empty(cap, dtype=torch.float32, device=dev),
                   torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev))
             self._scratch[w] = sc
@@ -111,6 +118,43 @@ class GenomePipeline:
             self.trace.append((name, w, [round(1e3 * (b - a), 2) for a, b in zip(t_, t_[1:])], round(1e3 * (t_[0] - self._t0), 2)))
         return ChromosomeResult(name, o, nb, call["mean_coverage"], call["final_loss"], call["lambda1"], call["lambda2"], call["status"])
 
+    def _upload(self, contigs, order):
+        """All chromosomes' packed arrays host -> device on one copy stream, in task order, one event per chromosome.
+        The device staging buffers are kept from run to run (same shapes: no allocation in a steady state)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(device=dev)
+
+        def as_tensor(x):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray):
+                if x.dtype.fields is not None:                       # structured records: hcnv_block / hcnv_long_block
+                    x = x.view(np.int32).reshape(len(x), -1)
+                elif x.dtype == np.uint32:
+                    x = x.view(np.int32)
+                return torch.from_numpy(x)
+            return x
+        events, dev_contigs = {}, {}
+        with torch.cuda.stream(self._copy):
+            for i in order:
+                c = contigs[i]
+                fields = [as_tensor(v) for v in (c.blocks, c.long_blocks, c.snp_pos1, c.snp_zyg, c.obs, c.cblocks, c.anchors)]
+                key = tuple(None if f is None else (tuple(f.shape), f.dtype) for f in fields)
+                slot = self._staging.get(i)
+                if slot is None or slot[0] != key:
+                    slot = (key, [None if f is None else torch.empty(f.shape, dtype=f.dtype, device=dev) for f in fields])
+                    self._staging[i] = slot
+                for d, f in zip(slot[1], fields):
+                    if f is not None:
+                        d.copy_(f, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy)
+                events[i] = ev
+                dev_contigs[i] = Contig(c.length, *slot[1])
+        return events, dev_contigs
+
     def run(self, contigs: Sequence[Contig], names: Optional[Sequence[str]] = None, out: Optional[GenomeOutput] = None,
             bin_width: int = 100, max_block_len: int = 0, lambda1: float = 0.01, lambda2: float = 1.6) -> List[ChromosomeResult]:
         """One sample end to end.  `contigs` hold HOST arrays (pinned for full PCIe speed); results land in `out`."""
@@ -119,19 +163,24 @@ class GenomePipeline:
         if out is None:
             out = GenomeOutput([c.length for c in contigs], bin_width)
         self.last_output = out
+        self._max_cap = max([int(c.length) // bin_width + 1 for c in contigs] + [1])
         self._t0 = time.perf_counter()
-        # static longest-first assignment: the same chromosome always lands on the same worker, so a worker's scratch
-        # memory stops growing after the first run, and the tail of every worker's list is made of short chromosomes
+        # longest chromosome first: the tail of the schedule is made of short ones
         order = sorted(range(len(contigs)), key=lambda i: -int(contigs[i].length))
-        loads, lists = [0] * len(self.ctxs), [[] for _ in self.ctxs]
-        for i in order:
-            w = loads.index(min(loads))
-            lists[w].append(i)
-            loads[w] += int(contigs[i].length)
+        events, dev_contigs = self._upload(contigs, order)
+        nxt = iter(order)
+        lock = threading.Lock()
 
         def work(w):
-            return [(i, self._task(w, i, contigs[i], names[i], out, bin_width, max_block_len, lambda1, lambda2)) for i in lists[w]]
-        done = {}
+            done = []
+            while True:
+                with lock:
+                    i = next(nxt, None)
+                if i is None:
+                    return done
+                events[i].synchronize()                              # this chromosome's records are on the device
+                done.append((i, self._task(w, i, dev_contigs[i], names[i], out, bin_width, max_block_len, lambda1, lambda2)))
+        res = {}
         for f in [self._pool.submit(work, w) for w in range(len(self.ctxs))]:
-            done.update(dict(f.result()))
-        return [done[i] for i in range(len(contigs))]
+            res.update(dict(f.result()))
+        return [res[i] for i in range(len(contigs))]
