@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="debug: skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-format", default="compact", choices=["compact", "records"],
-                    help="compact: 4-byte delta-coded block stream (include/hcnv.h hcnv_cblock); records: 8-byte hcnv_block")
+                    help="compact: 2-byte delta-coded block stream (include/hcnv.h hcnv_cblock); records: 8-byte hcnv_block")
     ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
     return ap.parse_args()
 
@@ -326,7 +326,7 @@ def run_b200(args):
                 a = api_dev[len(host_contigs)]
                 hc = H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs),
                               pin(a.cblocks) if a.cblocks is not None else None, pin(a.anchors) if a.anchors is not None else None)
-                h2d += (a.cblocks.numel() + a.anchors.numel()) * 4 if a.cblocks is not None else 0
+                h2d += a.cblocks.numel() * 2 + a.anchors.numel() * 4 if a.cblocks is not None else 0
             else:
                 hc = H.Contig(c.length, pin(c.blocks), pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs))
                 h2d += c.blocks.numel() * 4
@@ -381,8 +381,8 @@ def run_b200(args):
     kavg = {k_: float(np.mean(v)) for k_, v in kacc.items()}
     # algorithmic bytes per launch: binning = 8 B/block + 16 B/long block + 4 B/obs + 5 B/SNP + 72 B/bin out;
     # Viterbi = 28 B in (f32 scaled + 6 f32 mse) + 8 B out (state, cn) per bin
-    # (compact stream: 4 B per stream record, fillers and padding included, + one 4-byte anchor per 128 records)
-    bytes_bin = (4 * n_stream + 4 * (n_stream // 128) if compact else 8 * n_blocks) + 16 * n_long + 4 * n_obs + 5 * n_snp + 72 * n_bins
+    # (compact stream: 2 B per stream record, fillers and padding included, + one 4-byte anchor per 128 records)
+    bytes_bin = (2 * n_stream + 4 * (n_stream // 128) if compact else 8 * n_blocks) + 16 * n_long + 4 * n_obs + 5 * n_snp + 72 * n_bins
     bytes_vit = 36 * n_bins
     traffic = None                      # DRAM bytes per launch of the tile kernel from the committed ncu capture of this very workload
     try:

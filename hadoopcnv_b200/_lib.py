@@ -106,7 +106,7 @@ def lib():
     L.hcnv_bins_text_get.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)] + [C.POINTER(C.c_void_p)] * 7
     L.hcnv_bins_text_free.argtypes = [C.c_void_p]
     L.hcnv_bins_text_free.restype = None
-    L.hcnv_compact_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+    L.hcnv_compact_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
     L.hcnv_compact_blocks.restype = C.c_int64
     L.hcnv_ctx_stream.argtypes = [C.c_void_p]
     L.hcnv_ctx_stream.restype = C.c_void_p

@@ -51,37 +51,39 @@ def pack_blocks(start0, length, mapq=None) -> np.ndarray:
     return b
 
 
-def compact_blocks(blocks: np.ndarray):
-    """hcnv_compact_blocks: sorted hcnv_block records -> (cblocks uint32, anchors int32): 4 bytes per block, delta-coded,
-    one absolute anchor per HCNV_CGROUP records, fillers for gaps above 4095, padded to a whole group."""
+def compact_blocks(blocks: np.ndarray, mapping_quality_threshold: float = 0.0):
+    """hcnv_compact_blocks: sorted hcnv_block records -> (cblocks uint16, anchors int32): 2 bytes per block (delta:8 | len:8),
+    one absolute anchor per HCNV_CGROUP records, fillers for gaps above 255, blocks above 255 bases in pieces, blocks whose
+    MAPQ fails the threshold dropped, padded to a whole group, 16-byte aligned."""
     lib = L.lib()
     blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
-    n = lib.hcnv_compact_blocks(blocks.ctypes.data, len(blocks), None, None, 0)
+    n = lib.hcnv_compact_blocks(blocks.ctypes.data, len(blocks), float(mapping_quality_threshold), None, None, 0)
     if n < 0:
         raise L.HcnvError(int(n), "hcnv_compact_blocks: %s" % lib.hcnv_strerror(int(n)).decode())
-    raw = np.empty(n + 4, np.uint32)                         # 16-byte aligned start
-    shift = (-raw.ctypes.data // 4) % 4
+    raw = np.empty(n + 8, np.uint16)                         # 16-byte aligned start
+    shift = (-raw.ctypes.data // 2) % 8
     cb = raw[shift:shift + n]
     anchors = np.empty(max(1, n // L.HCNV_CGROUP), np.int32)
-    m = lib.hcnv_compact_blocks(blocks.ctypes.data, len(blocks), cb.ctypes.data, anchors.ctypes.data, n)
+    m = lib.hcnv_compact_blocks(blocks.ctypes.data, len(blocks), float(mapping_quality_threshold), cb.ctypes.data, anchors.ctypes.data, n)
     assert m == n
     return cb, anchors[: n // L.HCNV_CGROUP]
 
 
 def expand_cblocks(cblocks, anchors) -> np.ndarray:
-    """Inverse of compact_blocks on the host (numpy): hcnv_block records of every non-filler entry (test helper)."""
-    cb = np.asarray(cblocks, dtype=np.uint32)
-    d = (cb & 0xFFF).astype(np.int64)
+    """Inverse of compact_blocks on the host (numpy): one hcnv_block record (MAPQ 0) per non-filler entry, i.e. per PIECE
+    of a block (test helper; pieces of a block above 255 bases stay separate, which is results-neutral)."""
+    cb = np.asarray(cblocks, dtype=np.uint16).astype(np.int64)
+    d = cb & 0xFF
     g = L.HCNV_CGROUP
     d[::g] = 0
     c = np.cumsum(d)
     first = np.repeat(c[::g], g)[: len(cb)]
     start = np.repeat(np.asarray(anchors, dtype=np.int64), g)[: len(cb)] + (c - first)
-    ln = (cb >> 12) & 0xFFF
+    ln = cb >> 8
     keep = ln > 0
     out = np.empty(int(keep.sum()), BLOCK_DTYPE)
     out["start0"] = start[keep]
-    out["len_mapq"] = ln[keep] | ((cb[keep] >> 24) << np.uint32(24))
+    out["len_mapq"] = ln[keep].astype(np.uint32)
     return out
 
 
@@ -103,7 +105,7 @@ class Contig:
     snp_pos1: object = None        # int32, ascending unique
     snp_zyg: object = None         # int8 in {0,-1,-2}
     obs: object = None             # uint32 (torch: int32) snp_index << 4 | base4
-    cblocks: object = None         # alternative to blocks: hcnv_cblock stream (uint32 / torch int32), 16-byte aligned
+    cblocks: object = None         # alternative to blocks: hcnv_cblock stream (uint16 / torch int16), 16-byte aligned
     anchors: object = None         # int32, one per HCNV_CGROUP compact records
 
 

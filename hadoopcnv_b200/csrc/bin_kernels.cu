@@ -372,7 +372,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     // stage inputs that live on the host
     std::vector<ContigDev> hc(n_contigs);
     if (in_kind != 2) {
-        HCNV_CUDA(ctx, ctx->buf[B_IN_BLOCKS].reserve(sizeof(hcnv_block) * (size_t)tot_blocks + 4 * (size_t)tot_cblocks));
+        HCNV_CUDA(ctx, ctx->buf[B_IN_BLOCKS].reserve(sizeof(hcnv_block) * (size_t)tot_blocks + sizeof(hcnv_cblock) * (size_t)tot_cblocks));
         HCNV_CUDA(ctx, ctx->buf[B_IN_ANCHORS].reserve(4 * (size_t)(tot_cblocks / HCNV_CGROUP) + 16));
         HCNV_CUDA(ctx, ctx->buf[B_IN_LONG].reserve(sizeof(hcnv_long_block) * (size_t)tot_long));
         HCNV_CUDA(ctx, ctx->buf[B_IN_SNPPOS].reserve(4 * (size_t)tot_snp));
@@ -423,7 +423,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     HCNV_CUDA(ctx, ctx->buf[B_STATUS].reserve(8 * n_status));
     HCNV_CUDA(ctx, ctx->buf[B_MISC].reserve(4096 + 8 * (size_t)(n_contigs + 1)));
     k.contigs = ctx->buf[B_CONTIGS].as<ContigDev>();
-    k.n_contigs = n_contigs; k.W = W; k.TB = TB; k.n_tiles = n_tiles; k.maxlen = maxlen; k.compact = compact;
+    k.n_contigs = n_contigs; k.W = W; k.TB = TB; k.n_tiles = n_tiles; k.compact = compact;
+    k.maxlen = compact ? std::min(maxlen, 255) : maxlen;      // pieces of the compact stream are at most 255 long
     for (int q = 0; q < 256; ++q) {
         double mapprob = 1. - std::pow(10.0, -q * .1);            // Mappers.java:193
         if (mapprob >= P.mapping_quality_threshold) k.mapq_pass[q >> 5] |= 1u << (q & 31);   // :200
@@ -475,6 +476,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     KT_BEGIN(ctx, HCNV_K_BIN_TILES);
     bool filter = false;                           // the reference's threshold is the constant 0: every MAPQ passes
     for (int q = 0; q < 8; ++q) if (k.mapq_pass[q] != 0xFFFFFFFFu) filter = true;
+    if (filter && compact && tot_cblocks > 0)
+        return hcnv_fail(ctx, HCNV_E_INVALID, "the compact stream carries no MAPQ: filter while compacting (hcnv_compact_blocks) or send hcnv_block records");
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;

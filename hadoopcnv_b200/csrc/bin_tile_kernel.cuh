@@ -253,19 +253,19 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
     };
 
     // compact stream: chunk q of a tile = records [lb + q * RCAP, ...) = up to RCAP / HCNV_CGROUP whole groups.  Every lane
-    // loads its 4 records of each group (one 16-byte load, coalesced over the warp) and the anchors of the chunk's groups
+    // loads its 4 records of each group (one 8-byte load, coalesced over the warp) and the anchors of the chunk's groups
     // plus the one after (consistency check); the loads are issued one chunk ahead and wait in registers.
     constexpr int NG = RCAP / HCNV_CGROUP;
-    uint4 pw[NG]; int panc[NG + 1];                 // the prefetched chunk
+    uint2 pw[NG]; int panc[NG + 1];                 // the prefetched chunk
     #pragma unroll
-    for (int g = 0; g < NG; ++g) pw[g] = make_uint4(0, 0, 0, 0);
+    for (int g = 0; g < NG; ++g) pw[g] = make_uint2(0, 0);
     #pragma unroll
     for (int g = 0; g <= NG; ++g) panc[g] = 0x7fffffff;
     auto load_chunk = [&](const ContigLite& cc, uint32_t ta, uint32_t tb) {
         const uint32_t g0 = ta / HCNV_CGROUP, ng = (tb - ta) / HCNV_CGROUP;
         #pragma unroll
         for (int g = 0; g < NG; ++g)
-            pw[g] = ((uint32_t)g < ng) ? __ldg(reinterpret_cast<const uint4*>(cc.cblocks + ta + g * HCNV_CGROUP) + lane) : make_uint4(0, 0, 0, 0);
+            pw[g] = ((uint32_t)g < ng) ? __ldg(reinterpret_cast<const uint2*>(cc.cblocks + ta + g * HCNV_CGROUP) + lane) : make_uint2(0, 0);
         #pragma unroll
         for (int g = 0; g <= NG; ++g)
             panc[g] = ((uint32_t)g <= ng && (long long)(g0 + g) < cc.n_groups) ? __ldg(&cc.anchors[g0 + g]) : 0x7fffffff;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
         const ContigLite cc = contig_of(tm.contig);
         load_chunk(cc, tm.lb, min(tm.lb + (uint32_t)RCAP, tm.hi));
         if (lane == 0 && tm.hi - tm.lb > (uint32_t)RCAP)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cc.cblocks + tm.lb + RCAP), "r"((tm.hi - tm.lb - (uint32_t)RCAP) * 4u) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cc.cblocks + tm.lb + RCAP), "r"((tm.hi - tm.lb - (uint32_t)RCAP) * (uint32_t)sizeof(hcnv_cblock)) : "memory");
     };
     auto issue_first = [&](const TileRec& tm, int buf) {      // lane 0, 8-byte records: chunk 0 of a tile + the rest of its records into L2
         const ContigLite cc = contig_of(tm.contig);
@@ -414,25 +414,26 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
             const int maxlen = p.maxlen, length = c.length;
             if (COMPACT) {
                 // compact stream: whole groups of HCNV_CGROUP records; lane l decodes records 4l .. 4l+3 of a group (one
-                // LDS.128): deltas -> lane prefix -> warp scan -> + the group's anchor.  The range handed over by
+                // 8-byte load): deltas -> lane prefix -> warp scan -> + the group's anchor.  The range handed over by
                 // k_tile_index is a superset (group granular); what lies outside the tile clamps to an empty interval.
                 for (uint32_t q = 0; q < nch; ++q) {
                     const uint32_t ta = lb + q * RCAP, tb = min(ta + (uint32_t)RCAP, hi);
                     const uint32_t ng = (tb - ta) / HCNV_CGROUP;
                     // this chunk is in registers (loaded one chunk / one tile ago); start the next one now
-                    uint4 w[NG]; int anc[NG + 1];
+                    uint2 w[NG]; int anc[NG + 1];
                     #pragma unroll
                     for (int g = 0; g < NG; ++g) w[g] = pw[g];
                     #pragma unroll
                     for (int g = 0; g <= NG; ++g) anc[g] = panc[g];
                     if (q + 1 < nch) load_chunk(c, tb, min(tb + (uint32_t)RCAP, hi));
                     int acc_u = 0;
-                    int mx_end = (int)0x80000000, mx_len = 0;          // range checks: furthest end (tile relative) and longest block
+                    int mx_end = (int)0x80000000, mx_len = 0;          // range checks: furthest end (tile relative) and longest piece
                     int p0[NG], p1[NG], p2[NG], p3[NG], incl[NG];
                     #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        p0[g] = lane == 0 ? 0 : (int)(w[g].x & 0xFFFu);
-                        p1[g] = p0[g] + (int)(w[g].y & 0xFFFu); p2[g] = p1[g] + (int)(w[g].z & 0xFFFu); p3[g] = p2[g] + (int)(w[g].w & 0xFFFu);
+                        // four 16-bit records per lane: delta in the low byte, length in the high byte
+                        p0[g] = lane == 0 ? 0 : (int)(w[g].x & 0xFFu);
+                        p1[g] = p0[g] + (int)((w[g].x >> 16) & 0xFFu); p2[g] = p1[g] + (int)(w[g].y & 0xFFu); p3[g] = p2[g] + (int)((w[g].y >> 16) & 0xFFu);
                         incl[g] = p3[g];
                     }
                     #pragma unroll
@@ -446,19 +447,19 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
                         const int base = anc[g] + (incl[g] - p3[g]);
                         // the group must end at or before the next group's anchor (they are one sorted stream)
                         if (live) { if (lane == 31) acc_u |= anc[g + 1] - (base + p3[g]); acc_u |= anc[g]; }
-                        auto one = [&](uint32_t word, int start0) {
-                            const int len = (int)((word >> 12) & 0xFFFu);
+                        auto one = [&](int len, int start0) {
                             const int s_ = start0 - T0m1, e_ = s_ + len;                 // tile-relative [s_, e_)
                             // one-sided clamps are enough: a record off the tile gets e <= s and touches nothing
                             const int sc = max(s_, 0), ec = min(e_, TP);
-                            bool on = live && ec > sc;                               // fillers, padding, records outside the tile
+                            const bool on = live && ec > sc;                         // fillers, padding, records outside the tile
                             if (live) { mx_end = max(mx_end, e_); mx_len = max(mx_len, len); }
-                            if (FILTER) { const uint32_t mq = word >> 24; on = on && ((p.mapq_pass[mq >> 5] >> (mq & 31)) & 1u); }
                             if (on) { atomicAdd(&diff[sc], 1); atomicAdd(&diff[ec], -1); }
                         };
-                        one(w[g].x, base + p0[g]); one(w[g].y, base + p1[g]); one(w[g].z, base + p2[g]); one(w[g].w, base + p3[g]);
+                        one((int)((w[g].x >> 8) & 0xFFu), base + p0[g]); one((int)(w[g].x >> 24), base + p1[g]);
+                        one((int)((w[g].y >> 8) & 0xFFu), base + p2[g]); one((int)(w[g].y >> 24), base + p3[g]);
                     }
                     // starts are >= their group's anchor (deltas are unsigned), so a non-negative anchor covers start0 >= 0
+                    // (a piece longer than max_block_len would have been missed by the look-back of an earlier tile)
                     bad |= (acc_u < 0 ? 1 : 0) | ((mx_len > maxlen || (long long)mx_end + T0m1 > (long long)length) ? 2 : 0);
                 }
             } else

@@ -8,9 +8,11 @@
 #include "../../include/hcnv.h"
 #include <zlib.h>
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <queue>
 #include <string>
@@ -288,33 +290,50 @@ int hcnv_bam_pack(const char* bam_path, const hcnv_snp_table* snps, hcnv_pack** 
     return HCNV_OK;
 }
 
-int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, hcnv_cblock* out, int32_t* anchors, int64_t capacity) {
+int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, double mapping_quality_threshold,
+                            hcnv_cblock* out, int32_t* anchors, int64_t capacity) {
     if (n < 0 || (n > 0 && !blocks) || (out && !anchors)) return HCNV_E_INVALID;
+    bool pass[256];
+    for (int q = 0; q < 256; ++q) pass[q] = (1. - std::pow(10.0, -q * .1)) >= mapping_quality_threshold;   // Mappers.java:193,200
     int64_t k = 0;                                          // compact records written (or counted) so far
-    int32_t prev = 0;
-    auto put = [&](int32_t start0, uint32_t delta, uint32_t len, uint32_t mapq) -> bool {
+    int64_t prev = 0;                                       // start0 of the last record written
+    bool first = true;
+    auto put = [&](int64_t start0, uint32_t delta, uint32_t len) -> bool {
         if (out) {
             if (k >= capacity) return false;
-            if (k % HCNV_CGROUP == 0) anchors[k / HCNV_CGROUP] = start0;
-            out[k] = delta | (len << 12) | (mapq << 24);
+            if (k % HCNV_CGROUP == 0) anchors[k / HCNV_CGROUP] = (int32_t)start0;
+            out[k] = (hcnv_cblock)(delta | (len << 8));
         }
         ++k;
         return true;
     };
+    // one record of at most 255 bases at `pos` (>= every record written so far): fillers over the gap, then the record
+    auto emit = [&](int64_t pos, uint32_t piece) -> bool {
+        int64_t gap = first ? 0 : pos - prev;
+        while (gap > 255) {                                 // fillers: len 0, advance 255
+            prev += 255; gap -= 255;
+            if (!put(prev, 255u, 0u)) return false;
+        }
+        if (!put(pos, (uint32_t)gap, piece)) return false;
+        prev = pos; first = false;
+        return true;
+    };
+    // the later pieces of a block above 255 bases wait here until the input catches up, so the stream stays sorted
+    std::priority_queue<std::pair<int64_t, uint32_t>, std::vector<std::pair<int64_t, uint32_t>>, std::greater<std::pair<int64_t, uint32_t>>> later;
+    int32_t last_in = 0;
     for (int64_t i = 0; i < n; ++i) {
         const int32_t s = blocks[i].start0;
-        const uint32_t len = blocks[i].len_mapq & 0xFFFFFFu, mapq = blocks[i].len_mapq >> 24;
+        uint32_t len = blocks[i].len_mapq & 0xFFFFFFu; const uint32_t mapq = blocks[i].len_mapq >> 24;
         if (s < 0 || len > (uint32_t)HCNV_SHORT_MAX) return HCNV_E_RANGE;
-        if (i > 0 && s < prev) return HCNV_E_UNSORTED;
-        int64_t gap = (i == 0) ? 0 : (int64_t)s - prev;
-        while (gap > 4095) {                               // fillers: len 0, advance 4095
-            prev += 4095; gap -= 4095;
-            if (!put(prev, 4095u, 0u, 0u)) return HCNV_E_CAPACITY;
-        }
-        if (!put(s, (uint32_t)gap, len, mapq)) return HCNV_E_CAPACITY;
-        prev = s;
+        if (i > 0 && s < last_in) return HCNV_E_UNSORTED;
+        last_in = s;
+        if (!pass[mapq]) continue;
+        while (!later.empty() && later.top().first <= s) { if (!emit(later.top().first, later.top().second)) return HCNV_E_CAPACITY; later.pop(); }
+        if (!emit(s, len > 255u ? 255u : len)) return HCNV_E_CAPACITY;
+        for (int64_t pos = (int64_t)s + 255; len > 255u; pos += 255) { len -= 255u; later.push({pos, len > 255u ? 255u : len}); }
     }
-    while (k % HCNV_CGROUP) if (!put(prev, 0u, 0u, 0u)) return HCNV_E_CAPACITY;
+    while (!later.empty()) { if (!emit(later.top().first, later.top().second)) return HCNV_E_CAPACITY; later.pop(); }
+    while (k % HCNV_CGROUP) if (!put(prev, 0u, 0u)) return HCNV_E_CAPACITY;
     return k;
 }
 
@@ -339,14 +358,14 @@ int hcnv_pack_contig_compact(hcnv_pack* p, int32_t i, const char** name, hcnv_co
     int rc = hcnv_pack_contig(p, i, name, in, max_block_len);
     if (rc) return rc;
     hcnv_pack::Contig& c = p->contigs[(size_t)i];
-    if (c.n_cblocks < 0) {                                  // first request: build the 4-byte stream, 16-byte aligned
-        const int64_t n = hcnv_compact_blocks(c.blocks.data(), (int64_t)c.blocks.size(), nullptr, nullptr, 0);
+    if (c.n_cblocks < 0) {                                  // first request: build the 2-byte stream, 16-byte aligned
+        const int64_t n = hcnv_compact_blocks(c.blocks.data(), (int64_t)c.blocks.size(), 0.0, nullptr, nullptr, 0);
         if (n < 0) return (int)n;
-        c.cstore.resize((size_t)n + 4);
+        c.cstore.resize((size_t)n + 8);
         const uintptr_t a = reinterpret_cast<uintptr_t>(c.cstore.data());
-        c.cblocks = c.cstore.data() + ((16 - (a & 15)) & 15) / 4;
+        c.cblocks = c.cstore.data() + ((16 - (a & 15)) & 15) / 2;
         c.anchors.resize((size_t)(n / HCNV_CGROUP) + 1);
-        const int64_t m = hcnv_compact_blocks(c.blocks.data(), (int64_t)c.blocks.size(), c.cblocks, c.anchors.data(), n);
+        const int64_t m = hcnv_compact_blocks(c.blocks.data(), (int64_t)c.blocks.size(), 0.0, c.cblocks, c.anchors.data(), n);
         if (m != n) return HCNV_E_INTERNAL;
         c.n_cblocks = n;
     }

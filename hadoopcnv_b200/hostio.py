@@ -55,7 +55,7 @@ class SnpTable:
 
 def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = False):
     """hcnv_bam_pack -> (names, [Contig with numpy arrays], [max_block_len], n_records).  Arrays are copies.
-    compact=True: the block stream comes in the 4-byte delta-coded form (Contig.cblocks / anchors)."""
+    compact=True: the block stream comes in the 2-byte delta-coded form (Contig.cblocks / anchors)."""
     lib = L.lib()
     h = C.c_void_p()
     st = lib.hcnv_bam_pack(bam_path.encode(), snps._h if snps is not None else None, C.byref(h))
@@ -77,9 +77,9 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
             def arr16(ptr, n):                                   # 16-byte aligned copy of the compact stream
                 if not n:
                     return None
-                raw = np.empty(n + 4, np.uint32)
-                sh = (-raw.ctypes.data // 4) % 4
-                raw[sh:sh + n] = np.frombuffer((C.c_char * (4 * n)).from_address(ptr), dtype=np.uint32)
+                raw = np.empty(n + 8, np.uint16)
+                sh = (-raw.ctypes.data // 2) % 8
+                raw[sh:sh + n] = np.frombuffer((C.c_char * (2 * n)).from_address(ptr), dtype=np.uint16)
                 return raw[sh:sh + n]
             contigs.append(Contig(ci.length, arr(ci.blocks, ci.n_blocks, BLOCK_DTYPE), arr(ci.long_blocks, ci.n_long, LONG_BLOCK_DTYPE),
                                   arr(ci.snp_pos1, ci.n_snp, np.int32), arr(ci.snp_zyg, ci.n_snp, np.int8),

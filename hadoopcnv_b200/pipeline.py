@@ -134,6 +134,8 @@ class GenomePipeline:
                     x = x.view(np.int32).reshape(len(x), -1)
                 elif x.dtype == np.uint32:
                     x = x.view(np.int32)
+                elif x.dtype == np.uint16:
+                    x = x.view(np.int16)
                 return torch.from_numpy(x)
             return x
         events, dev_contigs = {}, {}

@@ -210,40 +210,42 @@ def make_genome(coverage: float = 30.0, seed: int = 0xC0FFEE, device="cpu", cont
 
 
 def compact_on_device(blocks: torch.Tensor):
-    """hcnv_compact_blocks with torch ops, on whatever device `blocks` (int32 [n, 2], sorted by start0) lives: the
-    4-byte delta-coded stream + one anchor per HCNV_CGROUP records (include/hcnv.h).  Returns (cblocks int32, anchors int32);
-    the stream's first element is 16-byte aligned (a fresh torch allocation)."""
-    G = 128
+    """hcnv_compact_blocks (threshold 0) with torch ops, on whatever device `blocks` (int32 [n, 2], sorted by start0, every
+    block at most 255 bases) lives: the 2-byte delta-coded stream + one anchor per HCNV_CGROUP records (include/hcnv.h).
+    Returns (cblocks int16, anchors int32); the stream's first element is 16-byte aligned (a fresh torch allocation)."""
+    G, D = 128, 255
     dev = blocks.device
     n = int(blocks.shape[0])
     if n == 0:
-        return torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
+        return torch.zeros(0, dtype=torch.int16, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
     start = blocks[:, 0].to(torch.int64)
-    lm = blocks[:, 1].to(torch.int64) & 0xFFFFFFFF
+    ln = blocks[:, 1].to(torch.int64) & 0xFFFFFF
+    if int(ln.max().item()) > D:
+        raise ValueError("compact_on_device handles blocks of at most 255 bases; use api.compact_blocks (it splits longer ones)")
     delta = torch.zeros_like(start)
     delta[1:] = start[1:] - start[:-1]
-    fill = torch.clamp(delta - 1, min=0) // 4095                 # fillers in front of each record
+    fill = torch.clamp(delta - 1, min=0) // D                    # fillers in front of each record
     pos = torch.arange(n, device=dev, dtype=torch.int64) + torch.cumsum(fill, 0)   # output index of each record
     total = int(pos[-1].item()) + 1
     padded = (total + G - 1) // G * G
-    # every slot is a filler (delta 4095, len 0) unless a record lands on it; the padding tail advances nothing
-    dout = torch.full((padded,), 4095, dtype=torch.int64, device=dev)
+    # every slot is a filler (delta 255, len 0) unless a record lands on it; the padding tail advances nothing
+    dout = torch.full((padded,), D, dtype=torch.int64, device=dev)
     dout[total:] = 0
-    code = torch.full((padded,), 4095, dtype=torch.int64, device=dev)
+    code = torch.full((padded,), D, dtype=torch.int64, device=dev)
     code[total:] = 0
-    d_rec = delta - 4095 * fill
+    d_rec = delta - D * fill
     dout[pos] = d_rec
-    code[pos] = d_rec | ((lm & 0xFFF) << 12) | ((lm >> 24) << 24)
+    code[pos] = d_rec | (ln << 8)
     dout[0] = 0
     absolute = start[0] + torch.cumsum(dout, 0)
     anchors = absolute[::G].to(torch.int32).contiguous()
-    code = torch.where(code >= (1 << 31), code - (1 << 32), code).to(torch.int32).contiguous()
+    code = torch.where(code >= (1 << 15), code - (1 << 16), code).to(torch.int16).contiguous()
     return code, anchors
 
 
 def to_api_contigs(contigs: List[SynthContig], host: bool = False, compact: bool = False):
     """SynthContig -> hadoopcnv_b200.api.Contig (torch tensors stay where they are; host=True -> numpy).
-    compact=True sends the block stream in the 4-byte delta-coded form."""
+    compact=True sends the block stream in the 2-byte delta-coded form."""
     from .api import Contig
     if compact:
         res = []
@@ -251,15 +253,15 @@ def to_api_contigs(contigs: List[SynthContig], host: bool = False, compact: bool
             cb, an = compact_on_device(c.blocks)
             if host:
                 import numpy as np
-                raw = np.empty(cb.shape[0] + 4, np.int32)
-                sh = (-raw.ctypes.data // 4) % 4
+                raw = np.empty(cb.shape[0] + 8, np.int16)
+                sh = (-raw.ctypes.data // 2) % 8
                 cbh = raw[sh:sh + cb.shape[0]]
                 cbh[:] = cb.cpu().numpy()
                 res.append(Contig(c.length, None, c.long_blocks.cpu().numpy() if c.long_blocks.shape[0] else None,
                                   c.snp_pos1.cpu().numpy() if c.snp_pos1.shape[0] else None,
                                   c.snp_zyg.cpu().numpy() if c.snp_zyg.shape[0] else None,
                                   c.obs.cpu().numpy() if c.obs.shape[0] else None,
-                                  cbh.view(np.uint32) if cb.shape[0] else None, an.cpu().numpy() if cb.shape[0] else None))
+                                  cbh.view(np.uint16) if cb.shape[0] else None, an.cpu().numpy() if cb.shape[0] else None))
             else:
                 res.append(Contig(c.length, None, c.long_blocks if c.long_blocks.shape[0] else None,
                                   c.snp_pos1 if c.snp_pos1.shape[0] else None, c.snp_zyg if c.snp_zyg.shape[0] else None,

@@ -97,14 +97,16 @@ int64_t     hcnv_ctx_stat(const hcnv_ctx* ctx, int which);
  * len_mapq = length | mapq << 24 (mapq as in Mappers.java:192).  Sorted by start0 within a contig. */
 typedef struct { int32_t start0; uint32_t len_mapq; } hcnv_block;
 
-/* The same stream at 4 bytes per block, delta-coded (what the host should send: the upload is what bounds the path
- * end to end):   bits 0-11  start0 - start0 of the previous record (0..4095)
- *                bits 12-23 len (0..HCNV_SHORT_MAX)      bits 24-31 mapq
+/* The same stream at 2 bytes per block, delta-coded (what the host should send: the upload is what bounds the path end
+ * to end):   bits 0-7  start0 - start0 of the previous record (0..255)      bits 8-15  len (0..255)
  * Every HCNV_CGROUP records there is an absolute anchor, anchors[g] = start0 of record HCNV_CGROUP * g (the delta field
- * of that record is ignored).  A gap above 4095 is bridged by filler records (len 0, delta up to 4095), and the stream
- * is padded with fillers (delta 0, len 0) to a multiple of HCNV_CGROUP records: n_cblocks counts them all.  A filler
- * covers no position and changes nothing.  cblocks must be 16-byte aligned.  hcnv_compact_blocks builds the stream. */
-typedef uint32_t hcnv_cblock;
+ * of that record is ignored).  A gap above 255 is bridged by filler records (len 0, delta up to 255), a block longer than
+ * 255 is sent as consecutive pieces (splitting a block is results-neutral: only per-position counts matter), and the
+ * stream is padded with fillers (delta 0, len 0) to a multiple of HCNV_CGROUP records: n_cblocks counts them all.  A filler
+ * covers no position and changes nothing.  The stream carries no MAPQ: the reference's threshold is the constant 0
+ * (Constants.java:21); a host that sets one filters while compacting (hcnv_compact_blocks does).  cblocks must be 16-byte
+ * aligned. */
+typedef uint16_t hcnv_cblock;
 #define HCNV_CGROUP 128
 
 /* A block of any length (e.g. the baseline BAM's artificial whole-interval reads, example/preprocessBAM.py).
@@ -135,11 +137,13 @@ typedef struct {
     const hcnv_cblock*     cblocks;     const int32_t* anchors; int64_t n_cblocks;
 } hcnv_contig_input;
 
-/* Host helper (no GPU): sorted hcnv_block records -> compact stream.  Returns the number of compact records (fillers and
- * padding included, a multiple of HCNV_CGROUP) or a negative status; with out == NULL only counts.  anchors needs
+/* Host helper (no GPU): sorted hcnv_block records -> compact stream; blocks whose MAPQ fails mapping_quality_threshold
+ * (1 - 10^(-q/10) >= threshold, Mappers.java:193,200) are dropped.  Returns the number of compact records (pieces, fillers
+ * and padding included, a multiple of HCNV_CGROUP) or a negative status; with out == NULL only counts.  anchors needs
  * result / HCNV_CGROUP entries.  HCNV_E_UNSORTED if the input is not sorted by start0, HCNV_E_RANGE for a negative
  * start0 or len > HCNV_SHORT_MAX, HCNV_E_CAPACITY if `capacity` (in records) is too small. */
-int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, hcnv_cblock* out, int32_t* anchors, int64_t capacity);
+int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, double mapping_quality_threshold,
+                            hcnv_cblock* out, int32_t* anchors, int64_t capacity);
 
 /* Outputs: one record per non-empty bin, all contigs concatenated in input order, bins ascending within a
  * contig (the (chr,bin) secondary sort, PennCnvSeq.java:382-414).  Field meaning = the columns BinReducer

@@ -59,8 +59,23 @@ def test_binning_compact_stream_matches_oracle(ctx, W, cov, thr):
     for host in (True, False):
         gg = g if host else [synth.SynthContig(c.name, c.length, c.blocks.cuda(), c.long_blocks.cuda(), c.snp_pos1.cuda(), c.snp_zyg.cuda(),
                                                c.obs.cuda(), c.n_reads, c.truth) for c in g]
-        res = ctx.bin_contigs(synth.to_api_contigs(gg, host=host, compact=True), bin_width=W, max_block_len=synth.READ_LEN,
-                              mapping_quality_threshold=thr)
+        api_c = synth.to_api_contigs(gg, host=host, compact=True)
+        if thr > 0:                                   # the compact stream carries no MAPQ: the filter is applied while compacting
+            with pytest.raises(H.HcnvError) as ei:
+                ctx.bin_contigs(api_c, bin_width=W, max_block_len=synth.READ_LEN, mapping_quality_threshold=thr)
+            assert ei.value.status == L.HCNV_E_INVALID
+            if not host:
+                continue
+            def keep_long(lb):                         # the host filters the long blocks too (q >= 10 passes 0.9)
+                if lb is None:
+                    return None
+                lb = lb.view(np.int32).reshape(-1, 4)
+                lb = np.ascontiguousarray(lb[lb[:, 2] >= 10])
+                return lb if len(lb) else None
+            api_c = [H.Contig(c.length, None, keep_long(a.long_blocks), a.snp_pos1, a.snp_zyg, a.obs, *H.compact_blocks(H.pack_blocks(
+                c.blocks[:, 0].numpy(), c.blocks[:, 1].numpy() & 0xFFFFFF, (c.blocks[:, 1].numpy().view(np.uint32) >> 24)), thr))
+                for c, a in zip(g, api_c)]
+        res = ctx.bin_contigs(api_c, bin_width=W, max_block_len=synth.READ_LEN)
         for i, c in enumerate(g):
             r = res.contig(i)
             got = r if host else H.BinsResult(*[x.cpu().numpy() for x in (r.bin, r.start, r.end, r.median, r.mse, r.total, r.n)], r.contig_offset)
@@ -76,12 +91,13 @@ def test_binning_compact_stream_edge_cases(ctx):
     assert len(cb) % 128 == 0 and len(an) == len(cb) // 128
     e = H.expand_cblocks(cb, an)
     assert e["start0"].tolist() == starts and (e["len_mapq"] & 0xFFFFFF).tolist() == lens
+    assert cb.dtype == np.uint16 and len(cb) >= 128 * (40000 // (255 * 128))          # the 40 kb gap is bridged by fillers
     want = ctx.bin_contigs([H.Contig(100000, b)], bin_width=100)
     got = ctx.bin_contigs([H.Contig(100000, None, None, None, None, None, cb, an)], bin_width=100)
     for k in ("bin", "start", "end", "n", "median", "total"):
         np.testing.assert_array_equal(getattr(got, k), getattr(want, k), err_msg=k)
     # bad streams are refused, not mis-binned
-    bad = cb.copy(); bad[1] = (bad[1] & ~np.uint32(0xFFF << 12)) | np.uint32(200 << 12)
+    bad = cb.copy(); bad[1] = (bad[1] & np.uint16(0xFF)) | np.uint16(200 << 8)
     with pytest.raises(H.HcnvError) as ei:
         ctx.bin_contigs([H.Contig(100000, None, None, None, None, None, bad, an)], bin_width=100, max_block_len=150)
     assert ei.value.status == L.HCNV_E_RANGE

@@ -73,8 +73,9 @@ def test_bam_pack_matches_htsjdk_semantics(tmp_path, seed):
     _, cc, _, _ = hostio.pack_bam(str(bam), table, compact=True)
     assert cc[0].blocks is None and cc[0].cblocks.ctypes.data % 16 == 0
     e = H.expand_cblocks(cc[0].cblocks, cc[0].anchors)
-    nz = (c.blocks["len_mapq"] & 0xFFFFFF) > 0
-    assert (e["start0"] == c.blocks["start0"][nz]).all() and (e["len_mapq"] == c.blocks["len_mapq"][nz]).all()
+    d_a, _ = O.depth_from_blocks(c.blocks, length)
+    d_b, _ = O.depth_from_blocks(e, length)
+    assert (d_a == d_b).all() and (np.diff(e["start0"]) >= 0).all()
     # and the packed records bin to the same thing as the text-level pipeline
     zyg = dict(zip(*[x.tolist() for x in table.contigs()["chr7"]]))
     want = Lit.binner(Lit.depth_caller([(r[0], r[1], r[2], r[3], r[4], r[5]) for r in reads]) + table.vcf_txt_lines())
@@ -118,7 +119,8 @@ def test_reference_baseline_bam_fixture():
 
 
 def test_compact_block_stream_round_trip():
-    """hcnv_compact_blocks (host, no GPU): delta coding, fillers over gaps, padding to whole groups, anchors."""
+    """hcnv_compact_blocks (host, no GPU): delta coding, fillers over gaps, blocks above 255 bases in pieces (stream stays
+    sorted), MAPQ filter, padding to whole groups, anchors."""
     rng = np.random.default_rng(11)
     n = 5000
     gaps = rng.integers(0, 30, n)
@@ -128,12 +130,25 @@ def test_compact_block_stream_round_trip():
     mq = rng.integers(0, 256, n)
     b = H.pack_blocks(start, ln, mq)
     cb, an = H.compact_blocks(b)
-    assert cb.ctypes.data % 16 == 0 and len(cb) % L.HCNV_CGROUP == 0 and len(an) == len(cb) // L.HCNV_CGROUP
-    assert ((cb & 0xFFF) <= 4095).all() and (np.diff(an) >= 0).all()
+    assert cb.dtype == np.uint16 and cb.ctypes.data % 16 == 0 and len(cb) % L.HCNV_CGROUP == 0 and len(an) == len(cb) // L.HCNV_CGROUP
+    assert (np.diff(an) >= 0).all()
     e = H.expand_cblocks(cb, an)
-    assert (e["start0"] == b["start0"]).all() and (e["len_mapq"] == b["len_mapq"]).all()
-    n_fill = int(((cb >> 12) & 0xFFF == 0).sum())
+    assert (e["start0"] == b["start0"]).all() and ((e["len_mapq"] & 0xFFFFFF) == (b["len_mapq"] & 0xFFFFFF)).all()
+    n_fill = int(((cb >> 8) == 0).sum())
     assert len(cb) == n + n_fill                                          # every extra record is a filler
+    # long blocks come out in pieces, and the pieces stay in start order among the blocks that follow
+    b2 = H.pack_blocks([10, 20, 300, 301, 4000], [1000, 5, 700, 30, 4095], [60] * 5)
+    cb2, an2 = H.compact_blocks(b2)
+    e2 = H.expand_cblocks(cb2, an2)
+    assert (np.diff(e2["start0"]) >= 0).all() and int((e2["len_mapq"] & 0xFFFFFF).max()) <= 255
+    d_want, _ = O.depth_from_blocks(b2, 9000)
+    d_got, _ = O.depth_from_blocks(e2, 9000)
+    assert (d_want == d_got).all()
+    # the MAPQ filter is applied while compacting (1 - 10^(-q/10) >= 0.9 <=> q >= 10)
+    cb3, an3 = H.compact_blocks(b, 0.9)
+    e3 = H.expand_cblocks(cb3, an3)
+    keep = mq >= 10
+    assert (e3["start0"] == b["start0"][keep]).all()
     with pytest.raises(H.HcnvError) as ei:
         H.compact_blocks(H.pack_blocks([10, 5], [3, 3]))
     assert ei.value.status == L.HCNV_E_UNSORTED
