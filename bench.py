@@ -346,7 +346,7 @@ def run_b200(args):
         def step_e2e():
             nonlocal d2h
             rs = pipe.run(host_contigs, cnames, gout, bin_width=W, max_block_len=READ_LEN, lambda1=LAMBDA1, lambda2=LAMBDA2)
-            d2h = sum(r.n_bins for r in rs) * gout.bytes_per_bin
+            d2h = sum(r.n_bins for r in rs) * gout.bytes_per_bin + int(gout.mse_count.sum()) * gout.bytes_per_mse_row
             e2e_state["rs"] = rs
 
         for _ in range(2):
@@ -359,15 +359,17 @@ def run_b200(args):
         for i, r in enumerate(e2e_state["rs"]):
             a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
             assert r.n_bins == b - a, "e2e / resident bin count mismatch on %s" % r.name
-            got = gout.i32[2, r.offset:r.offset + r.n_bins]
-            assert bool((got == seg_state[a:b].cpu()).all()), "e2e / resident state mismatch on %s" % r.name
+            got = gout.state[r.offset:r.offset + r.n_bins]
+            assert bool((got == seg_state[a:b].cpu().to(torch.int8)).all()), "e2e / resident state mismatch on %s" % r.name
+            assert (gout.dense_mse(i).view(np.uint32) == state["m32"][a:b].cpu().numpy().view(np.uint32)).all(), "e2e / resident MSE mismatch on %s" % r.name
         t2 = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t2)
         e2e = {"value": g_reads / (ms_e2e_wall / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(t2[0]), "d2h_bytes_per_step": int(t2[1]),
                "ms_per_step": ms_e2e_wall, "workers": args.e2e_workers, "gpu_launches_per_step": int(e2e_launches),
                "note": "pinned host inputs -> GenomePipeline.run (per chromosome: hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> "
-                       "hcnv_segment_batch on %d worker contexts) -> results.txt columns in pinned host arrays" % args.e2e_workers}
+                       "hcnv_segment_batch on %d worker contexts) -> results.txt columns in pinned host arrays (int8 calls, MSE rows listed "
+                       "where non-zero)" % args.e2e_workers}
         pipe.close()
 
     # ---- roofline of the dominant kernel (and of the binning kernel), from live CUDA-event timings

@@ -40,6 +40,15 @@ class ContigInput(C.Structure):
                 ("cblocks", C.c_void_p), ("anchors", C.c_void_p), ("n_cblocks", C.c_int64)]
 
 
+class ResultsDownload(C.Structure):
+    _fields_ = [("n", C.c_int64),
+                ("start", C.c_void_p), ("end", C.c_void_p), ("scaled", C.c_void_p), ("state", C.c_void_p), ("cn", C.c_void_p),
+                ("mse", C.c_void_p),
+                ("h_start", C.c_void_p), ("h_end", C.c_void_p), ("h_scaled", C.c_void_p), ("h_state", C.c_void_p), ("h_cn", C.c_void_p),
+                ("h_mse_rows", C.c_void_p), ("h_mse_vals", C.c_void_p), ("mse_capacity", C.c_int64),
+                ("n_mse_rows", C.c_int64)]
+
+
 class Bins(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("bin", C.c_void_p), ("start", C.c_void_p), ("end", C.c_void_p),
                 ("median", C.c_void_p), ("mse", C.c_void_p), ("total", C.c_void_p), ("n", C.c_void_p),
@@ -67,7 +76,7 @@ class Config(C.Structure):
 EXPORTS = [
     "hcnv_abi_sizes", "hcnv_ctx_create", "hcnv_ctx_destroy", "hcnv_last_error", "hcnv_strerror", "hcnv_version", "hcnv_ctx_stream",
     "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_ctx_set_kernel_timing", "hcnv_ctx_stat", "hcnv_bin_params_default", "hcnv_bin_contigs",
-    "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
+    "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_download_results", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
     "hcnv_write_bins_text", "hcnv_write_results_text",
     "hcnv_read_bins_text", "hcnv_bins_text_n_chromosomes", "hcnv_bins_text_get", "hcnv_bins_text_free",
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
@@ -106,6 +115,7 @@ def lib():
     L.hcnv_bins_text_get.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)] + [C.POINTER(C.c_void_p)] * 7
     L.hcnv_bins_text_free.argtypes = [C.c_void_p]
     L.hcnv_bins_text_free.restype = None
+    L.hcnv_download_results.argtypes = [C.c_void_p, C.POINTER(ResultsDownload)]
     L.hcnv_compact_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
     L.hcnv_compact_blocks.restype = C.c_int64
     L.hcnv_ctx_stream.argtypes = [C.c_void_p]

@@ -262,6 +262,18 @@ class Context:
         self._check(self._lib.hcnv_bins_to_hmm_input(self._h, n, _ptr(mse), _ptr(total), _ptr(m32), _ptr(t32)))
         return m32, t32
 
+    def download_results(self, start, end, scaled, state, cn, mse, h_start, h_end, h_scaled, h_state, h_cn, h_mse_rows, h_mse_vals) -> int:
+        """hcnv_download_results: one chromosome's results.txt columns, device -> host in their narrowest lossless form
+        (int8 calls, MSE rows listed where non-zero).  The h_* arguments are host arrays / pinned tensors of at least n rows.
+        Returns the number of listed MSE rows."""
+        d = L.ResultsDownload()
+        d.n = _len(start)
+        d.start, d.end, d.scaled, d.state, d.cn, d.mse = _ptr(start), _ptr(end), _ptr(scaled), _ptr(state), _ptr(cn), _ptr(mse)
+        d.h_start, d.h_end, d.h_scaled, d.h_state, d.h_cn = _ptr(h_start), _ptr(h_end), _ptr(h_scaled), _ptr(h_state), _ptr(h_cn)
+        d.h_mse_rows, d.h_mse_vals, d.mse_capacity = _ptr(h_mse_rows), _ptr(h_mse_vals), _len(h_mse_rows)
+        self._check(self._lib.hcnv_download_results(self._h, C.byref(d)))
+        return int(d.n_mse_rows)
+
     # ------------------------------------------------------------------ B2
     def segment_batch(self, problems: List[dict], alpha: float = 0.5, flags: int = 0, raise_on_exit: bool = True) -> List[dict]:
         """hcnv_segment_batch.  Each problem: dict(median, mse, total, n, lambda1, lambda2[, want_sd][, scaled/state/cn

@@ -104,6 +104,12 @@ int hcnv_bins_to_hmm_input(hcnv_ctx* ctx, int64_t n, const double* mse, const do
     return hcnv_bins_to_hmm_input_impl(ctx, n, mse, total, mse_f32, total_f32);
 }
 
+int hcnv_download_results(hcnv_ctx* ctx, hcnv_results_download* d) {
+    if (!ctx) return HCNV_E_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return hcnv_fail(ctx, HCNV_E_CUDA, "cudaSetDevice failed");
+    return hcnv_download_results_impl(ctx, d);
+}
+
 int hcnv_segment_batch(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems, int32_t flags) {
     if (!ctx) return HCNV_E_INVALID;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return hcnv_fail(ctx, HCNV_E_CUDA, "cudaSetDevice failed");

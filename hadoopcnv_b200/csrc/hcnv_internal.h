@@ -98,5 +98,6 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
                           const hcnv_contig_input* contigs, hcnv_bins* out);
 int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
                                 float* mse_f32, float* total_f32);
+int hcnv_download_results_impl(hcnv_ctx* ctx, hcnv_results_download* d);
 int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems,
                             int32_t flags);

@@ -438,11 +438,40 @@ __global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_base, int
 #include "viterbi_par.cuh"
 #include "viterbi_chain.cuh"
 
+// results download: int8 calls and the non-zero MSE rows (row, six values), compacted per warp with one atomic
+__global__ void k_pack_results(long long n, const int32_t* __restrict__ state, const int32_t* __restrict__ cn, const float* __restrict__ mse,
+                               int8_t* __restrict__ state8, int8_t* __restrict__ cn8, int32_t* __restrict__ rows, float* __restrict__ vals,
+                               unsigned long long* __restrict__ count, long long capacity) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool nz = false;
+    float m[6] = {0, 0, 0, 0, 0, 0};
+    if (i < n) {
+        state8[i] = (int8_t)state[i];
+        cn8[i] = (int8_t)cn[i];
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) { m[c] = __ldg(&mse[i * 6 + c]); nz |= __float_as_uint(m[c]) != 0u; }   // (-0.0 and NaN are listed too)
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, nz);
+    if (!ball) return;
+    unsigned long long base = 0;
+    if (lane == __ffs((int)ball) - 1) base = atomicAdd(count, (unsigned long long)__popc(ball));
+    base = __shfl_sync(0xffffffffu, base, __ffs((int)ball) - 1);
+    if (nz) {
+        const long long k = (long long)base + __popc(ball & ((1u << lane) - 1u));
+        if (k < capacity) {
+            rows[k] = (int32_t)i;
+            #pragma unroll
+            for (int c = 0; c < 6; ++c) vals[k * 6 + c] = m[c];
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
 namespace {
-enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR, H_RT_WORK };
+enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR, H_RT_WORK, H_DOWNLOAD = 26 };
 }
 
 int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
@@ -496,6 +525,46 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
         HCNV_CUDA(ctx, cudaGetLastError());
         if ((rc = download())) return rc;
     }
+    return HCNV_OK;
+}
+
+int hcnv_download_results_impl(hcnv_ctx* ctx, hcnv_results_download* d)
+{
+    if (!ctx || !d || d->n < 0) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    d->n_mse_rows = 0;
+    const long long n = d->n;
+    if (n == 0) return HCNV_OK;
+    if (n >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many rows");
+    if (!d->start || !d->end || !d->scaled || !d->state || !d->cn || !d->mse || !d->h_start || !d->h_end || !d->h_scaled || !d->h_state ||
+        !d->h_cn || !d->h_mse_rows || !d->h_mse_vals) return hcnv_fail(ctx, HCNV_E_INVALID, "null array");
+    const long long cap = std::min<long long>(d->mse_capacity, n);
+    HCNV_CUDA(ctx, ctx->buf[H_DOWNLOAD].reserve((size_t)n * 2 + (size_t)cap * 28 + 256));
+    char* b = ctx->buf[H_DOWNLOAD].as<char>();
+    unsigned long long* d_count = (unsigned long long*)b;
+    float* d_vals = (float*)(b + 64); int32_t* d_rows = (int32_t*)(b + 64 + (size_t)cap * 24);
+    int8_t* d_state8 = (int8_t*)(b + 64 + (size_t)cap * 28); int8_t* d_cn8 = d_state8 + n;
+    HCNV_CUDA(ctx, cudaMemsetAsync(d_count, 0, 8, ctx->stream));
+    k_pack_results<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, d->state, d->cn, d->mse, d_state8, d_cn8, d_rows, d_vals, d_count, cap);
+    HCNV_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    HCNV_CUDA(ctx, ctx->pin[2].reserve(64));
+    unsigned long long* h_count = ctx->pin[2].as<unsigned long long>();
+    HCNV_CUDA(ctx, cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_start, d->start, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_end, d->end, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_scaled, d->scaled, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_state, d_state8, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_cn, d_cn8, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    // the row count is on the host after the first of these copies; the listed rows follow in a second, short round
+    HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const long long k = (long long)*h_count;
+    if (k > cap) return hcnv_fail(ctx, HCNV_E_CAPACITY, "mse_capacity too small for the non-zero MSE rows");
+    if (k > 0) {
+        HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_mse_rows, d_rows, 4 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_mse_vals, d_vals, 24 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    d->n_mse_rows = k;
     return HCNV_OK;
 }
 

@@ -35,19 +35,38 @@ class ChromosomeResult:
 
 
 class GenomeOutput:
-    """Pinned host arrays for the results.txt columns of a whole genome: start, end, scaled depth, state, copy number
-    and the six BAF MSEs.  Chromosome i owns rows [offset[i], offset[i] + capacity[i]); only its first n_bins rows are
-    written (capacity = length / bin_width + 1 is the upper bound BinReducer can reach)."""
+    """Pinned host arrays for the results.txt columns of a whole genome (Hmm.java:479-490): start, end, scaled depth, HMM
+    state, copy number and the six BAF MSEs.  Chromosome i owns rows [offset[i], offset[i] + capacity[i]); only its first
+    n_bins rows are written (capacity = length / bin_width + 1 is the upper bound BinReducer can reach).
+
+    The download shares the PCIe budget with the upload (measured: ~60 GB/s for both directions together), so the columns
+    travel in their narrowest lossless form: state and copy number as int8, and the MSE columns -- all six are 0.0 for
+    every bin without a SNP site, about 92 % of them -- as (row, six floats) pairs for the rows that hold a non-zero value;
+    `dense_mse` rebuilds the (n_bins, 6) block of a chromosome."""
 
     def __init__(self, lengths: Sequence[int], bin_width: int):
         import torch
         cap = [int(l) // bin_width + 1 for l in lengths]
         self.offset = np.concatenate([[0], np.cumsum(cap)]).astype(np.int64)
         n = int(self.offset[-1])
-        self.i32 = torch.empty((4, n), dtype=torch.int32, pin_memory=True)       # start, end, state, cn (one contiguous row each)
+        self.start = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        self.end = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        self.state = torch.empty(n, dtype=torch.int8, pin_memory=True)
+        self.cn = torch.empty(n, dtype=torch.int8, pin_memory=True)
         self.scaled = torch.empty(n, dtype=torch.float32, pin_memory=True)
-        self.mse = torch.empty((n, 6), dtype=torch.float32, pin_memory=True)     # every copy below is one contiguous DMA
-        self.bytes_per_bin = 4 * 4 + 7 * 4
+        self.mse_rows = torch.empty(n, dtype=torch.int32, pin_memory=True)       # chromosome-relative row of every listed MSE row
+        self.mse_vals = torch.empty((n, 6), dtype=torch.float32, pin_memory=True)
+        self.mse_count = np.zeros(len(cap), np.int64)                            # listed rows per chromosome
+        self.n_bins = np.zeros(len(cap), np.int64)
+        self.bytes_per_bin = 4 + 4 + 1 + 1 + 4
+        self.bytes_per_mse_row = 4 + 24
+
+    def dense_mse(self, i: int) -> np.ndarray:
+        """The (n_bins, 6) float32 MSE columns of chromosome i."""
+        o, nb, k = int(self.offset[i]), int(self.n_bins[i]), int(self.mse_count[i])
+        m = np.zeros((nb, 6), np.float32)
+        m[self.mse_rows[o:o + k].numpy()] = self.mse_vals[o:o + k].numpy()
+        return m
 
 
 class GenomePipeline:
@@ -56,12 +75,15 @@ class GenomePipeline:
         self.ctxs = [Context(device) for _ in range(max(1, workers))]
         self._pool = ThreadPoolExecutor(max_workers=len(self.ctxs))
         self._scratch = {}
-        self._d2h = {}
         self._copy = None                               # the upload stream
         self._staging = {}                              # chromosome index -> device staging buffers of its packed arrays
         self.trace = None                               # set to a list to collect (name, worker, [bin, text, segment, d2h] ms, start ms)
         self._t0 = 0.0
         self._max_cap = 1
+        self.upload_piece_bytes = 4 << 20
+        import os
+        self._skip = os.environ.get("HCNV_PIPE_SKIP", "")      # experiments only (tools/e2e_experiment.py): stages to leave out
+        self.last_upload_ms = 0.0
 
     def close(self):
         self._pool.shutdown(wait=True)
@@ -89,30 +111,32 @@ class GenomePipeline:
                   torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev))
             self._scratch[w] = sc
         _, bins_buf, scaled, state, cn = sc
+        skip = self._skip
+        if "bin" in skip:
+            return ChromosomeResult(name, int(out.offset[i]), 0, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
         res = ctx.bin_contigs([contig], bin_width=bin_width, max_block_len=max_block_len, out=bins_buf, capacity=sc[0])
         nb = len(res)
         t_.append(time.perf_counter())
         o = int(out.offset[i])
         if nb == 0:
             return ChromosomeResult(name, o, 0, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
+        if "text" in skip:
+            return ChromosomeResult(name, o, nb, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
         m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total)
         t_.append(time.perf_counter())
+        if "seg" in skip:
+            return ChromosomeResult(name, o, nb, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
         call = ctx.segment_batch([dict(median=res.median, mse=m32, total=t32, n=res.n, lambda1=lambda1, lambda2=lambda2,
                                        scaled=scaled[:nb], state=state[:nb], cn=cn[:nb])])[0]
         t_.append(time.perf_counter())
-        # (the library calls above return with their stream drained, so the download needs no dependency on it; it runs on a
-        # torch-owned stream per worker: torch's pinned-memory allocator remembers the streams a block was used on)
-        stream = self._d2h.get(w)
-        if stream is None:
-            stream = self._d2h[w] = torch.cuda.Stream(device=dev)
-        with torch.cuda.stream(stream):
-            out.i32[0, o:o + nb].copy_(res.start, non_blocking=True)
-            out.i32[1, o:o + nb].copy_(res.end, non_blocking=True)
-            out.i32[2, o:o + nb].copy_(state[:nb], non_blocking=True)
-            out.i32[3, o:o + nb].copy_(cn[:nb], non_blocking=True)
-            out.scaled[o:o + nb].copy_(scaled[:nb], non_blocking=True)
-            out.mse[o:o + nb].copy_(m32, non_blocking=True)
-        stream.synchronize()
+        if "d2h" in skip:
+            return ChromosomeResult(name, o, nb, call["mean_coverage"], call["final_loss"], call["lambda1"], call["lambda2"], call["status"])
+        # one library call: int8 calls and the non-zero MSE rows are packed on the device, then everything is copied
+        k = ctx.download_results(res.start, res.end, scaled[:nb], state[:nb], cn[:nb], m32,
+                                 out.start[o:o + nb], out.end[o:o + nb], out.scaled[o:o + nb], out.state[o:o + nb], out.cn[o:o + nb],
+                                 out.mse_rows[o:o + nb], out.mse_vals[o:o + nb])
+        out.mse_count[i] = k
+        out.n_bins[i] = nb
         t_.append(time.perf_counter())
         if self.trace is not None:
             self.trace.append((name, w, [round(1e3 * (b - a), 2) for a, b in zip(t_, t_[1:])], round(1e3 * (t_[0] - self._t0), 2)))
@@ -149,8 +173,13 @@ class GenomePipeline:
                     slot = (key, [None if f is None else torch.empty(f.shape, dtype=f.dtype, device=dev) for f in fields])
                     self._staging[i] = slot
                 for d, f in zip(slot[1], fields):
-                    if f is not None:
-                        d.copy_(f, non_blocking=True)
+                    if f is None:
+                        continue
+                    # in pieces of a few MB: the workers' own small host<->device copies (descriptor tables, counters)
+                    # go through the same copy engine and must not queue behind a 100 MB transfer
+                    step = max(1, self.upload_piece_bytes // max(1, f[0:1].numel() * f.element_size()))
+                    for a0 in range(0, f.shape[0], step):
+                        d[a0:a0 + step].copy_(f[a0:a0 + step], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy)
                 events[i] = ev
@@ -183,6 +212,10 @@ class GenomePipeline:
                 events[i].synchronize()                              # this chromosome's records are on the device
                 done.append((i, self._task(w, i, dev_contigs[i], names[i], out, bin_width, max_block_len, lambda1, lambda2)))
         res = {}
-        for f in [self._pool.submit(work, w) for w in range(len(self.ctxs))]:
+        futs = [self._pool.submit(work, w) for w in range(len(self.ctxs))]
+        if self._skip:
+            events[order[-1]].synchronize()
+            self.last_upload_ms = 1e3 * (time.perf_counter() - self._t0)
+        for f in futs:
             res.update(dict(f.result()))
         return [res[i] for i in range(len(contigs))]

@@ -221,6 +221,22 @@ typedef struct {
 #define HCNV_SEG_SEQUENTIAL 1       /* flags: force the one-warp-per-chromosome exact kernel */
 int hcnv_segment_batch(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems, int32_t flags);
 
+/* ---- results download ------------------------------------------------------------------------------ */
+/* One chromosome's results.txt columns (Hmm.java:479-490) from device arrays to host (ideally pinned) arrays, in their
+ * narrowest lossless form -- the download shares the PCIe budget with the upload: start, end, scaled as they are, state
+ * and copy number as int8, and the six MSE columns only for the rows that hold a non-zero value (all six are 0.0 for
+ * every bin without a SNP site): h_mse_rows[k] = row, h_mse_vals[6k .. 6k+5] = its values, n_mse_rows of them, in no
+ * particular order.  mse_capacity = rows the two host arrays can take (n always suffices). */
+typedef struct {
+    int64_t n;
+    const int32_t* start; const int32_t* end; const float* scaled; const int32_t* state; const int32_t* cn;   /* device, n */
+    const float* mse;                                                                                        /* device, n * 6 */
+    int32_t* h_start; int32_t* h_end; float* h_scaled; int8_t* h_state; int8_t* h_cn;                        /* host, n */
+    int32_t* h_mse_rows; float* h_mse_vals; int64_t mse_capacity;                                            /* host */
+    int64_t n_mse_rows;                                                                                      /* out */
+} hcnv_results_download;
+int hcnv_download_results(hcnv_ctx* ctx, hcnv_results_download* d);
+
 /* ---- B3: config and text layouts -------------------------------------------------------------- */
 typedef struct {
     char    bam_file[1024];

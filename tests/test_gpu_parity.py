@@ -366,12 +366,12 @@ def test_genome_pipeline_equals_the_single_call_path(ctx):
             a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
             assert r.name == g[i].name and r.n_bins == b - a
             sl = slice(r.offset, r.offset + r.n_bins)
-            np.testing.assert_array_equal(out.i32[0, sl].numpy(), res.start[a:b])
-            np.testing.assert_array_equal(out.i32[1, sl].numpy(), res.end[a:b])
-            np.testing.assert_array_equal(out.i32[2, sl].numpy(), calls[i]["state"])
-            np.testing.assert_array_equal(out.i32[3, sl].numpy(), calls[i]["cn"])
+            np.testing.assert_array_equal(out.start[sl].numpy(), res.start[a:b])
+            np.testing.assert_array_equal(out.end[sl].numpy(), res.end[a:b])
+            np.testing.assert_array_equal(out.state[sl].numpy(), calls[i]["state"])
+            np.testing.assert_array_equal(out.cn[sl].numpy(), calls[i]["cn"])
             np.testing.assert_array_equal(out.scaled[sl].numpy().view(np.uint32), calls[i]["scaled"].view(np.uint32))
-            np.testing.assert_array_equal(out.mse[sl].numpy().view(np.uint32), m32[a:b].view(np.uint32))
+            np.testing.assert_array_equal(out.dense_mse(i).view(np.uint32), m32[a:b].view(np.uint32))
             assert np.float32(r.final_loss).view(np.uint32) == np.float32(calls[i]["final_loss"]).view(np.uint32)
     finally:
         pipe.close()

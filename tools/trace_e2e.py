@@ -9,7 +9,9 @@ contigs = synth.make_genome(coverage=30, seed=0xC0FFEE + 1, device="cuda", conti
 def pin(t):
     if t.shape[0] == 0: return None
     h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True); h.copy_(t); return h.numpy()
-hc = [H.Contig(c.length, pin(c.blocks), pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs)) for c in contigs]
+api = synth.to_api_contigs(contigs, compact=True)
+hc = [H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs), pin(a.cblocks), pin(a.anchors)) for c, a in zip(contigs, api)]
+del api
 lens = [c.length for c in contigs]; nm = [c.name for c in contigs]
 del contigs; torch.cuda.empty_cache()
 for workers in WORKERS:
@@ -18,7 +20,7 @@ for workers in WORKERS:
     pipe.trace = []
     torch.cuda.synchronize(); t0 = time.perf_counter(); pipe.run(hc, nm, out, max_block_len=150); torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print("workers", workers, "total ms", round(1e3 * dt, 1))
-    for r in sorted(pipe.trace, key=lambda r: r[3])[:6]: print(r)
+    for r in sorted(pipe.trace, key=lambda r: r[3]): print(r)
     tot = np.sum([r[2] for r in pipe.trace], axis=0); print("sum per phase [bin,text,seg,d2h] ms", tot)
     pipe.close()
 import os
