@@ -441,3 +441,36 @@ def test_binning_long_blocks_over_many_tiles_and_bad_snp_tables(ctx):
         with pytest.raises(H.HcnvError) as e:
             ctx.bin_contigs([H.Contig(length, b, None, snp, np.zeros(len(snp), np.int8), None)], bin_width=100)
         assert e.value.status == code
+
+
+def test_download_results_is_lossless(ctx):
+    """hcnv_download_results: int8 calls and listed non-zero MSE rows rebuild the dense columns bit for bit (-0.0 and NaN
+    count as non-zero), and a too small MSE capacity is refused."""
+    import torch
+    rng = np.random.default_rng(9)
+    n = 70000
+    start = torch.tensor(rng.integers(0, 1 << 30, n).astype(np.int32), device="cuda")
+    end = start + 99
+    scaled = torch.tensor(rng.standard_normal(n).astype(np.float32), device="cuda")
+    state = torch.tensor(rng.integers(0, 6, n).astype(np.int32), device="cuda")
+    cn = torch.tensor(rng.integers(0, 5, n).astype(np.int32), device="cuda")
+    mse = np.zeros((n, 6), np.float32)
+    hot = rng.random(n) < 0.08
+    mse[hot] = rng.random((int(hot.sum()), 6)).astype(np.float32)
+    mse[5, 3] = -0.0; mse[6, 0] = np.nan; mse[n - 1, 5] = 1e-38
+    d_mse = torch.tensor(mse, device="cuda")
+    h = dict(start=np.empty(n, np.int32), end=np.empty(n, np.int32), scaled=np.empty(n, np.float32), state=np.empty(n, np.int8),
+             cn=np.empty(n, np.int8), rows=np.empty(n, np.int32), vals=np.empty((n, 6), np.float32))
+    k = ctx.download_results(start, end, scaled, state, cn, d_mse, h["start"], h["end"], h["scaled"], h["state"], h["cn"], h["rows"], h["vals"])
+    listed = (mse.view(np.uint32) != 0).any(axis=1)
+    assert k == int(listed.sum()) and sorted(h["rows"][:k].tolist()) == np.flatnonzero(listed).tolist()
+    dense = np.zeros((n, 6), np.float32)
+    dense[h["rows"][:k]] = h["vals"][:k]
+    assert (dense.view(np.uint32) == mse.view(np.uint32)).all()
+    for name, t in (("start", start), ("end", end), ("scaled", scaled)):
+        assert (h[name].view(np.uint32) == t.cpu().numpy().view(np.uint32)).all()
+    assert (h["state"] == state.cpu().numpy()).all() and (h["cn"] == cn.cpu().numpy()).all()
+    with pytest.raises(H.HcnvError) as e:
+        ctx.download_results(start, end, scaled, state, cn, d_mse, h["start"], h["end"], h["scaled"], h["state"], h["cn"],
+                             h["rows"][:10], h["vals"][:10])
+    assert e.value.status == L.HCNV_E_CAPACITY
