@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--block-format", default="compact", choices=["compact", "records"],
                     help="compact: 2-byte delta-coded block stream (include/hcnv.h hcnv_cblock); records: 8-byte hcnv_block")
     ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
+    ap.add_argument("--e2e-groups", type=int, default=8, help="tasks (groups of chromosomes) per genome in the end-to-end leg")
     return ap.parse_args()
 
 
@@ -337,7 +338,7 @@ def run_b200(args):
         # The call a user makes: GenomePipeline.run = per chromosome hcnv_bin_contigs -> hcnv_bins_to_hmm_input ->
         # hcnv_segment_batch -> D2H, on a few worker threads (one Context each) so PCIe runs both ways behind the kernels.
         from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
-        pipe = GenomePipeline(local, workers=args.e2e_workers)
+        pipe = GenomePipeline(local, workers=args.e2e_workers, groups=args.e2e_groups)
         gout = GenomeOutput([c.length for c in contigs], W)
         cnames = [c.name for c in contigs]
         d2h = 0

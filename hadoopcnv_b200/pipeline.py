@@ -70,7 +70,7 @@ class GenomeOutput:
 
 
 class GenomePipeline:
-    def __init__(self, device: int = 0, workers: int = 3):
+    def __init__(self, device: int = 0, workers: int = 3, groups: int = 8):
         self.device = device
         self.ctxs = [Context(device) for _ in range(max(1, workers))]
         self._pool = ThreadPoolExecutor(max_workers=len(self.ctxs))
@@ -81,6 +81,7 @@ class GenomePipeline:
         self._t0 = 0.0
         self._max_cap = 1
         self.upload_piece_bytes = 4 << 20
+        self.groups = groups                            # tasks per genome (chromosomes are grouped in upload order)
         import os
         self._skip = os.environ.get("HCNV_PIPE_SKIP", "")      # experiments only (tools/e2e_experiment.py): stages to leave out
         self.last_upload_ms = 0.0
@@ -97,50 +98,57 @@ class GenomePipeline:
     def kernel_launches(self) -> int:
         return sum(c.kernel_launches for c in self.ctxs)
 
-    def _task(self, w: int, i: int, contig: Contig, name: str, out: GenomeOutput, bin_width: int, max_block_len: int,
-              lambda1: float, lambda2: float) -> ChromosomeResult:
+    def _task(self, w: int, idx: Sequence[int], contigs: Sequence[Contig], names: Sequence[str], out: GenomeOutput, bin_width: int,
+              max_block_len: int, lambda1: float, lambda2: float) -> List[ChromosomeResult]:
+        """One task = a few chromosomes (`idx`, device-resident inputs) end to end on worker w: one hcnv_bin_contigs, one
+        hcnv_bins_to_hmm_input, one hcnv_segment_batch for the group, then one hcnv_download_results per chromosome."""
         import time
         import torch
         t_ = [time.perf_counter()]
         ctx = self.ctxs[w]
         dev = torch.device("cuda", self.device)
-        cap = max(int(contig.length) // bin_width + 1, self._max_cap)
+        cap = max(sum(int(c.length) // bin_width + 1 for c in contigs), self._max_cap)
         sc = self._scratch.get(w)
-        if sc is None or sc[0] < cap:                          # per-worker device scratch, sized for the largest chromosome
-            sc = (cap, ctx.alloc_bins(cap, True, 1), torch.empty(cap, dtype=torch.float32, device=dev),
+        if sc is None or sc[0] < cap:                          # per-worker device scratch, sized for the largest group
+            sc = (cap, ctx.alloc_bins(cap, True, len(contigs)), torch.empty(cap, dtype=torch.float32, device=dev),
                   torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev))
             self._scratch[w] = sc
         _, bins_buf, scaled, state, cn = sc
         skip = self._skip
+        empty = lambda i, nm, nb=0: ChromosomeResult(nm, int(out.offset[i]), nb, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
         if "bin" in skip:
-            return ChromosomeResult(name, int(out.offset[i]), 0, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
-        res = ctx.bin_contigs([contig], bin_width=bin_width, max_block_len=max_block_len, out=bins_buf, capacity=sc[0])
-        nb = len(res)
+            return [empty(i, nm) for i, nm in zip(idx, names)]
+        res = ctx.bin_contigs(list(contigs), bin_width=bin_width, max_block_len=max_block_len, out=bins_buf, capacity=sc[0])
+        off = [int(x) for x in res.contig_offset]
         t_.append(time.perf_counter())
-        o = int(out.offset[i])
-        if nb == 0:
-            return ChromosomeResult(name, o, 0, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
-        if "text" in skip:
-            return ChromosomeResult(name, o, nb, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
+        if len(res) == 0 or "text" in skip:
+            return [empty(i, nm, off[j + 1] - off[j]) for j, (i, nm) in enumerate(zip(idx, names))]
         m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total)
         t_.append(time.perf_counter())
         if "seg" in skip:
-            return ChromosomeResult(name, o, nb, np.float32(0), np.float32(0), np.float32(lambda1), np.float32(lambda2), 0)
-        call = ctx.segment_batch([dict(median=res.median, mse=m32, total=t32, n=res.n, lambda1=lambda1, lambda2=lambda2,
-                                       scaled=scaled[:nb], state=state[:nb], cn=cn[:nb])])[0]
+            return [empty(i, nm, off[j + 1] - off[j]) for j, (i, nm) in enumerate(zip(idx, names))]
+        live = [j for j in range(len(idx)) if off[j + 1] > off[j]]
+        calls = ctx.segment_batch([dict(median=res.median[off[j]:off[j + 1]], mse=m32[off[j]:off[j + 1]], total=t32[off[j]:off[j + 1]],
+                                        n=res.n[off[j]:off[j + 1]], lambda1=lambda1, lambda2=lambda2, scaled=scaled[off[j]:off[j + 1]],
+                                        state=state[off[j]:off[j + 1]], cn=cn[off[j]:off[j + 1]]) for j in live])
         t_.append(time.perf_counter())
-        if "d2h" in skip:
-            return ChromosomeResult(name, o, nb, call["mean_coverage"], call["final_loss"], call["lambda1"], call["lambda2"], call["status"])
-        # one library call: int8 calls and the non-zero MSE rows are packed on the device, then everything is copied
-        k = ctx.download_results(res.start, res.end, scaled[:nb], state[:nb], cn[:nb], m32,
-                                 out.start[o:o + nb], out.end[o:o + nb], out.scaled[o:o + nb], out.state[o:o + nb], out.cn[o:o + nb],
-                                 out.mse_rows[o:o + nb], out.mse_vals[o:o + nb])
-        out.mse_count[i] = k
-        out.n_bins[i] = nb
+        results = [empty(i, nm) for i, nm in zip(idx, names)]
+        for j, call in zip(live, calls):
+            i, a, b = idx[j], off[j], off[j + 1]
+            nb, o = b - a, int(out.offset[idx[j]])
+            k = 0
+            if "d2h" not in skip:
+                # one library call: int8 calls and the non-zero MSE rows are packed on the device, then everything is copied
+                k = ctx.download_results(res.start[a:b], res.end[a:b], scaled[a:b], state[a:b], cn[a:b], m32[a:b],
+                                         out.start[o:o + nb], out.end[o:o + nb], out.scaled[o:o + nb], out.state[o:o + nb], out.cn[o:o + nb],
+                                         out.mse_rows[o:o + nb], out.mse_vals[o:o + nb])
+            out.mse_count[i] = k
+            out.n_bins[i] = nb
+            results[j] = ChromosomeResult(names[j], o, nb, call["mean_coverage"], call["final_loss"], call["lambda1"], call["lambda2"], call["status"])
         t_.append(time.perf_counter())
         if self.trace is not None:
-            self.trace.append((name, w, [round(1e3 * (b - a), 2) for a, b in zip(t_, t_[1:])], round(1e3 * (t_[0] - self._t0), 2)))
-        return ChromosomeResult(name, o, nb, call["mean_coverage"], call["final_loss"], call["lambda1"], call["lambda2"], call["status"])
+            self.trace.append(("+".join(names), w, [round(1e3 * (y - x), 2) for x, y in zip(t_, t_[1:])], round(1e3 * (t_[0] - self._t0), 2)))
+        return results
 
     def _upload(self, contigs, order):
         """All chromosomes' packed arrays host -> device on one copy stream, in task order, one event per chromosome.
@@ -199,18 +207,32 @@ class GenomePipeline:
         # longest chromosome first: the tail of the schedule is made of short ones
         order = sorted(range(len(contigs)), key=lambda i: -int(contigs[i].length))
         events, dev_contigs = self._upload(contigs, order)
-        nxt = iter(order)
+        # tasks = groups of consecutive chromosomes of the upload order with about equal bytes: a group's calls amortise the
+        # per-call latencies (the segmentation of one chromosome is a latency-bound chain) without holding up the pipeline
+        total_len = sum(int(c.length) for c in contigs) or 1
+        groups, cur, acc = [], [], 0
+        for i in order:
+            cur.append(i)
+            acc += int(contigs[i].length)
+            if acc * self.groups >= total_len * (len(groups) + 1):
+                groups.append(cur)
+                cur = []
+        if cur:
+            groups.append(cur)
+        self._max_cap = max([sum(int(contigs[i].length) // bin_width + 1 for i in g_) for g_ in groups] + [1])
+        nxt = iter(groups)
         lock = threading.Lock()
 
         def work(w):
             done = []
             while True:
                 with lock:
-                    i = next(nxt, None)
-                if i is None:
+                    g_ = next(nxt, None)
+                if g_ is None:
                     return done
-                events[i].synchronize()                              # this chromosome's records are on the device
-                done.append((i, self._task(w, i, dev_contigs[i], names[i], out, bin_width, max_block_len, lambda1, lambda2)))
+                events[g_[-1]].synchronize()                         # the group's records are on the device (uploads are in order)
+                rs = self._task(w, g_, [dev_contigs[i] for i in g_], [names[i] for i in g_], out, bin_width, max_block_len, lambda1, lambda2)
+                done.extend(zip(g_, rs))
         res = {}
         futs = [self._pool.submit(work, w) for w in range(len(self.ctxs))]
         if self._skip:
