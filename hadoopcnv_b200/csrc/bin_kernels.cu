@@ -487,7 +487,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     };
     auto launch_vec = [&](auto vec_tag) -> cudaError_t {
         constexpr int V = decltype(vec_tag)::value;
-        if (compact) return filter ? launch(k_bin_tiles<V, true, true>) : launch(k_bin_tiles<V, false, true>);
+        if (compact) return launch(k_bin_tiles<V, false, true>);      // (the compact stream carries no MAPQ: checked above)
         return filter ? launch(k_bin_tiles<V, true, false>) : launch(k_bin_tiles<V, false, false>);
     };
     if (W % 4 == 0)      HCNV_CUDA(ctx, launch_vec(std::integral_constant<int, 4>()));
