@@ -62,11 +62,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// +1 / -1 on a word of shared memory given by its shared-window address (no return value: a reduction)
+__device__ __forceinline__ void red_inc(int addr) { asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory"); }
+__device__ __forceinline__ void red_dec(int addr) { asm volatile("red.shared.add.u32 [%0], 0xffffffff;" :: "r"(addr) : "memory"); }
 
 struct ContigLite {                               // what a tile needs from its contig
     const hcnv_cblock*     cblocks;               // compact stream (COMPACT kernels) ...
     const int32_t*         anchors;
-    long long              n_groups;
+    uint32_t               n_groups;              // (a tile's record range is 32-bit, so the stream has fewer than 2^32 records)
     const hcnv_block*      blocks;                // ... or the 8-byte records
     const hcnv_long_block* longs;
     const int32_t*         snp_pos;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
     if (ct_cached)
         for (int i = tid; i < p.n_contigs; i += blockDim.x) {
             const ContigDev& g = p.contigs[i];
-            ContigLite c; c.cblocks = g.cblocks; c.anchors = g.anchors; c.n_groups = g.n_cblocks / HCNV_CGROUP; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
+            ContigLite c; c.cblocks = g.cblocks; c.anchors = g.anchors; c.n_groups = (uint32_t)(g.n_cblocks / HCNV_CGROUP); c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
             c.length = g.length; c.n_bins_max = g.n_bins_max;
             s_ct[i] = c;
         }
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
     auto contig_of = [&](int ci) -> ContigLite {
         if (ct_cached) return s_ct[ci];
         const ContigDev& g = p.contigs[ci];
-        ContigLite c; c.cblocks = g.cblocks; c.anchors = g.anchors; c.n_groups = g.n_cblocks / HCNV_CGROUP; c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
+        ContigLite c; c.cblocks = g.cblocks; c.anchors = g.anchors; c.n_groups = (uint32_t)(g.n_cblocks / HCNV_CGROUP); c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
         c.length = g.length; c.n_bins_max = g.n_bins_max;
         return c;
     };
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
             pw[g] = ((uint32_t)g < ng) ? __ldg(reinterpret_cast<const uint2*>(cc.cblocks + ta + g * HCNV_CGROUP) + lane) : make_uint2(0, 0);
         #pragma unroll
         for (int g = 0; g <= NG; ++g)
-            panc[g] = ((uint32_t)g <= ng && (long long)(g0 + g) < cc.n_groups) ? __ldg(&cc.anchors[g0 + g]) : 0x7fffffff;
+            panc[g] = ((uint32_t)g <= ng && g0 + g < cc.n_groups) ? __ldg(&cc.anchors[g0 + g]) : 0x7fffffff;
     };
     // all lanes: first chunk of a tile into registers; lane 0: the rest of its records into L2
     auto first_chunk_c = [&](const TileRec& tm) {
@@ -416,51 +419,78 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
                 // compact stream: whole groups of HCNV_CGROUP records; lane l decodes records 4l .. 4l+3 of a group (one
                 // 8-byte load): deltas -> lane prefix -> warp scan -> + the group's anchor.  The range handed over by
                 // k_tile_index is a superset (group granular); what lies outside the tile clamps to an empty interval.
+                // Everything after the scan is done in shared-memory ADDRESS units (diff's address + 4 * tile-relative
+                // position), so a record costs two multiply-adds, two clamps, one compare and two predicated reductions.
+                static_assert(NG == 2, "the packed scan carries two groups per register");
+                const int diffA = (int)smem_u32(diff), diffE = diffA + TP * 4;
+                // every record is range-checked in the tile it starts in; its end can only pass the contig's end there if
+                // that tile is the contig's last or the one before (the last tile sees the rest of the stream as well)
+                const bool chk_end = (long long)T0 + TP + 256 > (long long)length;
+                const int limA = chk_end ? diffA + (length - T0m1) * 4 : 0x7fffffff;
+                const uint32_t lane0_mask = lane == 0 ? 0xFFFFFF00u : 0xFFFFFFFFu;   // a group's first delta is void: the anchor is its start
                 for (uint32_t q = 0; q < nch; ++q) {
                     const uint32_t ta = lb + q * RCAP, tb = min(ta + (uint32_t)RCAP, hi);
                     const uint32_t ng = (tb - ta) / HCNV_CGROUP;
                     // this chunk is in registers (loaded one chunk / one tile ago); start the next one now
                     uint2 w[NG]; int anc[NG + 1];
                     #pragma unroll
-                    for (int g = 0; g < NG; ++g) w[g] = pw[g];
+                    for (int g = 0; g < NG; ++g) { w[g] = pw[g]; w[g].x &= lane0_mask; }
                     #pragma unroll
                     for (int g = 0; g <= NG; ++g) anc[g] = panc[g];
                     if (q + 1 < nch) load_chunk(c, tb, min(tb + (uint32_t)RCAP, hi));
-                    int acc_u = 0;
-                    int mx_end = (int)0x80000000, mx_len = 0;          // range checks: furthest end (tile relative) and longest piece
-                    int p0[NG], p1[NG], p2[NG], p3[NG], incl[NG];
+                    // four 16-bit records per lane: delta in the low byte, length in the high byte.  A lane's four deltas add
+                    // up to at most 1020 and a group's to 32 640, so both groups' warp scans share one register (16 bits each)
+                    int d1[NG], d2[NG], d3[NG], p3[NG];
                     #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        // four 16-bit records per lane: delta in the low byte, length in the high byte
-                        p0[g] = lane == 0 ? 0 : (int)(w[g].x & 0xFFu);
-                        p1[g] = p0[g] + (int)((w[g].x >> 16) & 0xFFu); p2[g] = p1[g] + (int)(w[g].y & 0xFFu); p3[g] = p2[g] + (int)((w[g].y >> 16) & 0xFFu);
-                        incl[g] = p3[g];
+                        d1[g] = (int)__byte_perm(w[g].x, 0, 0x4442); d2[g] = (int)(w[g].y & 0xFFu); d3[g] = (int)__byte_perm(w[g].y, 0, 0x4442);
+                        p3[g] = ((int)(w[g].x & 0xFFu) + d1[g]) + (d2[g] + d3[g]);
                     }
+                    uint32_t incl2 = (uint32_t)p3[0] | ((uint32_t)p3[1] << 16);
                     #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        #pragma unroll
-                        for (int g = 0; g < NG; ++g) { const int v = __shfl_up_sync(0xffffffffu, incl[g], o); if (lane >= o) incl[g] += v; }
-                    }
+                    for (int o = 1; o < 32; o <<= 1)
+                        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.u32 %0, %0, t;\n\t}" : "+r"(incl2) : "r"(o));
+                    const uint32_t tot2 = __shfl_sync(0xffffffffu, incl2, 31);         // both groups' spans (last start - anchor)
+                    int acc_u = 0, mx_end = (int)0x80000000;
+                    uint32_t mx_len = 0;
                     #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        const bool live = (uint32_t)g < ng;
-                        const int base = anc[g] + (incl[g] - p3[g]);
-                        // the group must end at or before the next group's anchor (they are one sorted stream)
-                        if (live) { if (lane == 31) acc_u |= anc[g + 1] - (base + p3[g]); acc_u |= anc[g]; }
-                        auto one = [&](int len, int start0) {
-                            const int s_ = start0 - T0m1, e_ = s_ + len;                 // tile-relative [s_, e_)
-                            // one-sided clamps are enough: a record off the tile gets e <= s and touches nothing
-                            const int sc = max(s_, 0), ec = min(e_, TP);
-                            const bool on = live && ec > sc;                         // fillers, padding, records outside the tile
-                            if (live) { mx_end = max(mx_end, e_); mx_len = max(mx_len, len); }
-                            if (on) { atomicAdd(&diff[sc], 1); atomicAdd(&diff[ec], -1); }
-                        };
-                        one((int)((w[g].x >> 8) & 0xFFu), base + p0[g]); one((int)(w[g].x >> 24), base + p1[g]);
-                        one((int)((w[g].y >> 8) & 0xFFu), base + p2[g]); one((int)(w[g].y >> 24), base + p3[g]);
+                        if ((uint32_t)g < ng) {                                           // warp-uniform
+                            const int incl = (int)(g == 0 ? (incl2 & 0xFFFFu) : (incl2 >> 16));
+                            const int tot = (int)(g == 0 ? (tot2 & 0xFFFFu) : (tot2 >> 16));
+                            // the group must end at or before the next group's anchor (they are one sorted stream); the scan is
+                            // monotonic over the lanes, so testing every lane's last start tests the group's
+                            acc_u |= anc[g] | (anc[g + 1] - anc[g] - incl);
+                            const int rel0 = anc[g] - T0m1;                               // tile-relative start of the group
+                            const uint32_t l0 = __byte_perm(w[g].x, 0, 0x4441), l1 = w[g].x >> 24, l2 = __byte_perm(w[g].y, 0, 0x4441), l3 = w[g].y >> 24;
+                            mx_len = max(max(mx_len, l0), max(max(l1, l2), l3));
+                            const int d0 = (int)(w[g].x & 0xFFu);
+                            if (!chk_end && rel0 >= 0 && rel0 + tot + 255 <= TP) {
+                                // interior group (most): every record starts and ends inside the tile by arithmetic alone (deltas
+                                // and lengths are bytes), so no clamps, no tests: two multiply-adds and two reductions per record
+                                const int S0 = diffA + 4 * (rel0 + (incl - p3[g])) + 4 * d0;
+                                const int S1 = S0 + 4 * d1[g], S2 = S1 + 4 * d2[g], S3 = S2 + 4 * d3[g];
+                                const int E0 = S0 + 4 * (int)l0, E1 = S1 + 4 * (int)l1, E2 = S2 + 4 * (int)l2, E3 = S3 + 4 * (int)l3;
+                                red_inc(S0); red_dec(E0); red_inc(S1); red_dec(E1); red_inc(S2); red_dec(E2); red_inc(S3); red_dec(E3);
+                            } else {
+                                int rel = rel0 + (incl - p3[g]);                         // tile-relative start of the lane's first record, less its delta
+                                rel = min(max(rel, -(1 << 27)), 1 << 27);                // (so that 4 * rel cannot wrap, whatever the stream says)
+                                const int S0 = diffA + 4 * rel + 4 * d0;
+                                const int S1 = S0 + 4 * d1[g], S2 = S1 + 4 * d2[g], S3 = S2 + 4 * d3[g];
+                                const int E0 = S0 + 4 * (int)l0, E1 = S1 + 4 * (int)l1, E2 = S2 + 4 * (int)l2, E3 = S3 + 4 * (int)l3;
+                                if (chk_end) mx_end = max(max(mx_end, E0), max(max(E1, E2), E3));
+                                // one-sided clamps are enough: a record off the tile (or a filler) gets e <= s and touches nothing
+                                auto one = [&](int S, int E) {
+                                    const int sA = max(S, diffA), eA = min(E, diffE);
+                                    if (eA > sA) { red_inc(sA); red_dec(eA); }
+                                };
+                                one(S0, E0); one(S1, E1); one(S2, E2); one(S3, E3);
+                            }
+                        }
                     }
                     // starts are >= their group's anchor (deltas are unsigned), so a non-negative anchor covers start0 >= 0
                     // (a piece longer than max_block_len would have been missed by the look-back of an earlier tile)
-                    bad |= (acc_u < 0 ? 1 : 0) | ((mx_len > maxlen || (long long)mx_end + T0m1 > (long long)length) ? 2 : 0);
+                    bad |= (acc_u < 0 ? 1 : 0) | (((int)mx_len > maxlen || mx_end > limA) ? 2 : 0);
                 }
             } else
             for (uint32_t q = 0; q < nch; ++q) {
