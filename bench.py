@@ -429,6 +429,21 @@ def run_b200(args):
                         "sample": "%s of the same genome: %d reads, %d bins, %.1f s on one host core" % ("+".join(contigs[i].name for i in sample), s_reads, s_bins, t_cpu),
                         "bins_per_s": s_bins / t_cpu}
 
+    # segmentation side (B2): every kernel of hcnv_bins_to_hmm_input + hcnv_segment_batch.  With 24 chains per genome it is
+    # bound by the latency of the chr1 chain, not by a throughput roofline; both throughput fractions are
+    # reported so that this is visible: 36 algorithmic bytes and 204 non-FMA FP32 operations per bin.
+    SEG_KERNELS = ("text_roundtrip", "mean_coverage", "scale_depth", "sd", "viterbi", "traceback", "vit_p0", "vit_p0c", "vit_p1", "vit_p1b", "vit_p2", "vit_p2b", "vit_p3")
+    seg_ms = sum(kavg.get(k_, 0.0) for k_ in SEG_KERNELS)
+    roofline_segmentation = None
+    if seg_ms:
+        fp32_peak = 148 * 128 * 1.965e9
+        roofline_segmentation = {"kernels": [k_ for k_ in SEG_KERNELS if kavg.get(k_)], "ms_per_step": seg_ms, "bound": "latency (24 chains; chr1's chain is the critical path)",
+                                 "hbm": {"achieved": bytes_vit / (seg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_vit / (seg_ms * 1e-3) / 1e9 / hbm_peak,
+                                         "algorithmic_bytes_per_bin": 36},
+                                 "fp32_issue": {"achieved": 204 * n_bins / (seg_ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12, "unit": "Tops/s (no FMA)",
+                                                "frac": 204 * n_bins / (seg_ms * 1e-3) / fp32_peak, "ops_per_bin": 204},
+                                 "throughput_case": "tools/bench_cohort.py (configs[4]: 384 chains per call)"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": g_reads / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -439,10 +454,10 @@ def run_b200(args):
                        "snp_observations": g_obs, "block_format": args.block_format, "lambda1": LAMBDA1, "lambda2": LAMBDA2, "parallelism": "chromosome-sharded x%d (LPT)" % world,
                        "l2": "inputs (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (bytes_enc / 1e9)},
             "genome_wall_time_s": ms_dev / 1e3, "wall_ms_per_step": ms_wall,
-            "bins_per_s_segmented": g_bins / (sum(kavg.get(k_, 0) for k_ in ("mean_coverage", "scale_depth", "sd", "viterbi", "traceback")) / 1e3) if kavg.get("viterbi") else None,
+            "bins_per_s_segmented": g_bins / (seg_ms / 1e3) if seg_ms else None,
             "reads_per_s_binned": g_reads / (sum(kavg.get(k_, 0) for k_ in ("tile_index", "tally", "bin_tiles")) / 1e3) if kavg.get("bin_tiles") else None,
             "kernel_ms": kavg, "gpu_launches": g_launches, "clocks": clock_info,
-            "roofline": roofline, "roofline_binning": roofline_binning, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "roofline_binning": roofline_binning, "roofline_segmentation": roofline_segmentation, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "checks": {"final_loss_sum": float(np.sum([v.get("final_loss", 0.0) for v in summary.values()])), "chromosomes": len(summary), "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
         }
         print(json.dumps(line))

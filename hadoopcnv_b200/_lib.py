@@ -15,9 +15,11 @@ HCNV_E_INVALID, HCNV_E_CUDA, HCNV_E_NOMEM, HCNV_E_RANGE, HCNV_E_UNSORTED = -1, -
 HCNV_E_INCONSISTENT, HCNV_E_NO_MINIMUM, HCNV_E_IO, HCNV_E_PARSE, HCNV_E_CAPACITY, HCNV_E_INTERNAL = -6, -7, -8, -9, -10, -11
 HCNV_SHORT_MAX = 4095
 HCNV_SEG_SEQUENTIAL = 1
+HCNV_SEG_THROUGHPUT = 2
+HCNV_SEG_LATENCY = 4
 HCNV_CGROUP = 128
 KERNELS = dict(tile_index=0, tally=1, bin_tiles=2, text_roundtrip=3, mean_coverage=4, scale_depth=5, sd=6, viterbi=7, traceback=8,
-               vit_p0=9, vit_p0c=10, vit_p1=11, vit_p2=12, vit_p3=13, vit_p1b=14, vit_p2b=15, snp_mse=16)
+               vit_p0=9, vit_p0c=10, vit_p1=11, vit_p2=12, vit_p3=13, vit_p1b=14, vit_p2b=15, snp_mse=16, vit_many=17)
 
 
 class HcnvError(RuntimeError):

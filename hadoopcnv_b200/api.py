@@ -278,6 +278,11 @@ class Context:
     def segment_batch(self, problems: List[dict], alpha: float = 0.5, flags: int = 0, raise_on_exit: bool = True) -> List[dict]:
         """hcnv_segment_batch.  Each problem: dict(median, mse, total, n, lambda1, lambda2[, want_sd][, scaled/state/cn
         preallocated outputs]).  Returns one dict per problem with scaled/state/cn and the scalar outputs."""
+        return self.run_segment_batch(self.prepare_segment_batch(problems), alpha, flags, raise_on_exit)
+
+    def prepare_segment_batch(self, problems: List[dict]):
+        """The hcnv_segment_problem array of a batch, built once: a cohort sweep calls the library with thousands of
+        problems whose pointers do not change from call to call (a compiled host fills this array once, too)."""
         k = len(problems)
         arr = (L.SegmentProblem * k)()
         keep = []
@@ -309,9 +314,17 @@ class Context:
             a.lambda1, a.lambda2 = float(q["lambda1"]), float(q["lambda2"])
             a.scaled, a.state, a.cn = _ptr(scaled), _ptr(state), _ptr(cn)
             a.want_sd = int(q.get("want_sd", 0))
+        return arr, keep
+
+    def run_segment_batch(self, prepared, alpha: float = 0.5, flags: int = 0, raise_on_exit: bool = True, scalars_only: bool = False):
+        """hcnv_segment_batch on a prepared array.  scalars_only: return (status, final_loss) arrays instead of one dict per problem."""
+        arr, keep = prepared
+        k = len(arr)
         st = self._lib.hcnv_segment_batch(self._h, float(alpha), k, arr, flags)
         if st < 0 and (raise_on_exit or st != L.HCNV_E_NO_MINIMUM):
             self._check(st)
+        if scalars_only:
+            return (np.fromiter((arr[i].status for i in range(k)), np.int32, k), np.fromiter((arr[i].final_loss for i in range(k)), np.float32, k))
         res = []
         for i in range(k):
             a = arr[i]

@@ -14,6 +14,8 @@
 #include "hcnv_internal.h"
 #include <cfloat>
 #include <vector>
+#include <map>
+#include <tuple>
 #include <algorithm>
 #include <cuda_pipeline.h>
 #include <cooperative_groups.h>
@@ -215,6 +217,8 @@ struct SegDev {
     int            par;            // 1: exact segment-parallel path (viterbi_par.cuh), 0: one-warp sequential kernel
     int            irregular;      // NaN / negative / infinite inputs or penalties: only the literal sequential kernel is exact
     int            n_seg, first_bad, pad;
+    int            many;           // k_viterbi_many owns this chromosome (throughput path for large batches)
+    int            mean_src1;      // 1 + index of an earlier problem with the same total / n arrays (its mean coverage is copied), 0: none
 };
 
 __constant__ float c_mu[6] = {-1.0f, -0.5f, 0.f, 0.f, 0.5f, 1.0f};   // Hmm.java:34
@@ -226,6 +230,7 @@ __global__ void k_mean_coverage(SegDev* probs, int n_probs) {
     if (w >= n_probs) return;
     SegDev& P = probs[w];
     if (!P.pad) return;                              // k_mean_coverage_par already did it exactly
+    if (P.mean_src1) return;                         // copied from the problem that shares its inputs (k_mean_copy)
     const long long M = P.M;
     float s = 0.f;
     int sites = 0;
@@ -272,16 +277,33 @@ __device__ __forceinline__ int blk_find(const int* __restrict__ blk_base, int n_
     return lo;
 }
 
-__global__ void k_scale_depth(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
+// penalty sweeps hand the same chromosome in many times: its mean coverage is computed once
+__global__ void k_mean_copy(SegDev* probs, int n_probs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_probs) return;
+    const int src = probs[i].mean_src1;
+    if (src) probs[i].mean = probs[src - 1].mean;
+}
+
+#define SEG_BLK 1024          // markers per block of the per-marker kernels (four per thread: the chromosome look-up is paid once)
+__global__ void __launch_bounds__(256) k_scale_depth(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
     const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
     SegDev& P = probs[pi];
-    long long i = (long long)((int)blockIdx.x - __ldg(&blk_base[pi])) * 256 + threadIdx.x;
-    if (i >= P.M) return;
-    float mean = P.mean;
-    float s = __fdiv_rn(__fsub_rn(__ldg(&P.median[i]), mean), mean);
-    if (s < -2.0f) s = -2.0f;
-    if (s > 2.0f) s = 2.0f;
-    P.scaled[i] = s;
+    const long long i0 = (long long)((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
+    const long long M = P.M;
+    const float mean = P.mean;
+    const float* __restrict__ med = P.median;
+    float* __restrict__ out = P.scaled;
+    #pragma unroll
+    for (int k = 0; k < SEG_BLK / 256; ++k) {
+        const long long i = i0 + k * 256;
+        if (i < M) {
+            float s = __fdiv_rn(__fsub_rn(__ldg(&med[i]), mean), mean);
+            if (s < -2.0f) s = -2.0f;
+            if (s > 2.0f) s = 2.0f;
+            out[i] = s;
+        }
+    }
 }
 
 // get_sd, Hmm.java:103-119: two sequential float passes; one warp per chromosome
@@ -345,6 +367,7 @@ __global__ void __launch_bounds__(32) k_viterbi_seq(SegDev* probs, float alpha) 
     const long long M = P.M;
     if (P.skip) return;
     if (P.par && !P.irregular) return;               // done by the segment-parallel path
+    if (P.many) return;                              // done by k_viterbi_many
     const int c = lane < 6 ? lane : 0;
     const float oma = __fsub_rn(1.f, alpha);
     const float l1 = P.l1u, l2 = P.l2u;
@@ -417,22 +440,191 @@ __global__ void __launch_bounds__(32) k_viterbi_seq(SegDev* probs, float alpha) 
     }
 }
 
+// Throughput form of the same literal recurrence for LARGE batches (cohort sweeps: hundreds to thousands of
+// chromosome x penalty problems, BASELINE.json configs[4]): five chromosomes per warp, lanes 6g .. 6g+5 own the six
+// current states of chain g, the six predecessors' losses come from __shfl and the arg-min is the reference's strict '<'
+// over ascending p.  Nothing is re-associated, so it is exact for every input (NaN, negative penalties ...).  With at
+// least a few warps per scheduler it is bound by instruction issue (about 12 instructions per marker and chain); the
+// segment-parallel path above does six times the arithmetic per marker (6x6 matrix products) to cut the LATENCY of a
+// single chain, which is the right trade for 24 chains and the wrong one for thousands.
+// Traceback codes: every lane packs its own 3-bit arg-min of VM_PACK consecutive markers into one word (no cross-lane
+// assembly): codes[c * ceil(M / VM_PACK) + m / VM_PACK], read back by k_traceback for the column s*.
+#define VM_CH 5
+#define VM_U 16
+#define VM_PACK 10
+#define VM_MIN_MARKERS 64
+// One marker of one chain on the six lanes that own it.  LITERAL = false is the same function of the six candidates
+// written for latency: a NaN-ignoring min tree (FMNMX) and the first index that attains it, instead of the reference's
+// serial compare-and-keep over ascending p.  The two agree whenever equal candidates are bit-identical, i.e. no
+// candidate is -0.0, which holds when the penalties have a clear sign bit (the last two addends are then >= +0.0):
+// chains flagged `irregular` by k_sd (negative or non-finite penalties or alpha) take LITERAL = true.
+template <bool LITERAL>
+__device__ __forceinline__ void vm_step(float& L, int& bad, int& arg_out, float sd, float ms, float muc, float oma, float alpha,
+                                        float c3, const float (&c4)[6], int src) {
+    const float dev = __fsub_rn(sd, muc);
+    const float A = __fmul_rn(oma, __fmul_rn(dev, dev));
+    const float B = __fmul_rn(alpha, ms);
+    float loss[6];
+    #pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const float Lp = __shfl_sync(0xffffffffu, L, src + p);
+        loss[p] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(Lp, A), B), c3), c4[p]);
+    }
+    if (LITERAL) {
+        float mn = FLT_MAX, Ln = 0.f; int arg = 0;
+        #pragma unroll
+        for (int p = 0; p < 6; ++p) if (loss[p] < mn) { mn = loss[p]; Ln = mn; arg = p; }      // Hmm.java:184,199-203
+        if ((double)mn == 1e10) bad = 1;                                                        // Hmm.java:205-215
+        L = Ln; arg_out = arg;
+    } else {
+        const float mnv = fminf(fminf(fminf(loss[0], loss[1]), fminf(loss[2], loss[3])), fminf(loss[4], loss[5]));
+        const bool valid = mnv < FLT_MAX;               // false: every candidate is NaN, infinite or FLT_MAX -> loss 0, traceback 0
+        int arg = 5;
+        if (loss[4] == mnv) arg = 4;
+        if (loss[3] == mnv) arg = 3;
+        if (loss[2] == mnv) arg = 2;
+        if (loss[1] == mnv) arg = 1;
+        if (loss[0] == mnv) arg = 0;
+        if (valid && mnv == 1e10f) bad = 1;             // (1e10 is a float: the reference's double compare sees the same value)
+        L = valid ? mnv : 0.f;
+        arg_out = valid ? arg : 0;
+    }
+}
+
+template <bool LITERAL>
+__device__ __forceinline__ void vm_run(const float* __restrict__ sdp, const float* __restrict__ mp, uint32_t* __restrict__ mycodes, int M, int Mmin, int Mmax,
+                                       float& L, int& bad, float muc, float oma, float alpha, float c3, const float (&c4)[6], int src) {
+    uint32_t word = 0;
+    int sh = 3, wi = 0;                                    // marker 1 sits at bits 3..5 of word 0 (marker 0 has no traceback)
+    float nsd[VM_U], nm[VM_U];
+    auto fetch = [&](int m0) {
+        #pragma unroll
+        for (int j = 0; j < VM_U; ++j) {
+            const int m = m0 + j;
+            const bool in = m < M;
+            nsd[j] = in ? __ldg(&sdp[m]) : 0.f;
+            nm[j] = in ? __ldg(&mp[(long long)m * 6]) : 0.f;
+        }
+    };
+    fetch(1);
+    int m0 = 1;
+    // whole chunks while every chain of the warp is alive: no per-marker tests
+    for (; m0 + VM_U <= Mmin; m0 += VM_U) {
+        float csd[VM_U], cm[VM_U];
+        #pragma unroll
+        for (int j = 0; j < VM_U; ++j) { csd[j] = nsd[j]; cm[j] = nm[j]; }
+        fetch(m0 + VM_U);
+        #pragma unroll
+        for (int j = 0; j < VM_U; ++j) {
+            int arg;
+            vm_step<LITERAL>(L, bad, arg, csd[j], cm[j], muc, oma, alpha, c3, c4, src);
+            word |= (uint32_t)arg << sh;
+            sh += 3;
+            if (sh == 3 * VM_PACK) { if (mycodes) mycodes[wi] = word; ++wi; word = 0; sh = 0; }
+        }
+    }
+    // the rest: chains end at different markers
+    for (; m0 < Mmax; m0 += VM_U) {
+        float csd[VM_U], cm[VM_U];
+        #pragma unroll
+        for (int j = 0; j < VM_U; ++j) { csd[j] = nsd[j]; cm[j] = nm[j]; }
+        if (m0 + VM_U < Mmax) fetch(m0 + VM_U);
+        #pragma unroll
+        for (int j = 0; j < VM_U; ++j) {
+            const int m = m0 + j;
+            float Lk = L; int badk = bad, arg;
+            vm_step<LITERAL>(Lk, badk, arg, csd[j], cm[j], muc, oma, alpha, c3, c4, src);
+            if (m < M) {
+                L = Lk; bad = badk;
+                word |= (uint32_t)arg << sh;
+                sh += 3;
+                if (sh == 3 * VM_PACK || m == M - 1) { if (mycodes) mycodes[wi] = word; ++wi; word = 0; sh = 0; }
+            }
+        }
+    }
+    if (sh != 0 && mycodes && M > 1) mycodes[wi] = word;      // a chain that ended with the last whole chunk (the tail loop flushes at m == M - 1)
+}
+
+__global__ void __launch_bounds__(32) k_viterbi_many(SegDev* probs, const int* __restrict__ order, int n_slots, float alpha) {
+    const int lane = threadIdx.x;
+    const int g = lane / 6, c = lane - 6 * g;              // lanes 30 and 31 (g = 5) idle along
+    const int slot = blockIdx.x * VM_CH + g;
+    const int pi = (g < VM_CH && slot < n_slots) ? __ldg(&order[slot]) : -1;
+    const int src = min(g, VM_CH - 1) * 6;                 // first lane of the chain this lane reads predecessors from
+    int M = 0, irregular = 0;
+    const float* __restrict__ sdp = nullptr; const float* __restrict__ msep = nullptr;
+    uint32_t* codes = nullptr;
+    float l1 = 0.f, l2 = 0.f;
+    if (pi >= 0) {
+        const SegDev& P = probs[pi];
+        if (P.many && !P.skip) { M = (int)P.M; sdp = P.scaled; msep = P.mse; codes = P.codes; l1 = P.l1u; l2 = P.l2u; irregular = P.irregular; }
+    }
+    const int Mmax = __reduce_max_sync(0xffffffffu, M);
+    if (Mmax == 0) return;
+    const int Mmin = __reduce_min_sync(0xffffffffu, M > 0 ? M : 0x7fffffff);
+    const float oma = __fsub_rn(1.f, alpha);
+    const float muc = c_mu[c];
+    const float c3 = __fmul_rn(l1, fabsf(muc));
+    float c4[6];
+    #pragma unroll
+    for (int p = 0; p < 6; ++p) c4[p] = __fmul_rn(l2, fabsf(__fsub_rn(muc, c_mu[p])));
+    const int stride = (M + VM_PACK - 1) / VM_PACK;
+    uint32_t* mycodes = codes ? codes + (long long)c * stride : nullptr;
+
+    // marker 0 (Hmm.java:179-181); emissions are all zero when markers < 2 (Hmm.java:148-150)
+    float L = 0.f;
+    if (M > 0) {
+        float lrr = 0.f, baf = 0.f;
+        if (M >= 2) { const float dev = __fsub_rn(__ldg(&sdp[0]), muc); lrr = __fmul_rn(dev, dev); baf = __ldg(&msep[c]); }
+        L = __fadd_rn(__fadd_rn(__fmul_rn(oma, lrr), __fmul_rn(alpha, baf)), c3);
+    }
+    int bad = 0;
+    if (__any_sync(0xffffffffu, irregular != 0)) vm_run<true>(sdp, msep + c, mycodes, M, Mmin, Mmax, L, bad, muc, oma, alpha, c3, c4, src);
+    else vm_run<false>(sdp, msep + c, mycodes, M, Mmin, Mmax, L, bad, muc, oma, alpha, c3, c4, src);
+    // final arg-min over the last row (Hmm.java:220-232), per chain
+    int min_index = 1; float mn = FLT_MAX; float row[6]; int anybad = 0;
+    #pragma unroll
+    for (int s2 = 0; s2 < 6; ++s2) {
+        row[s2] = __shfl_sync(0xffffffffu, L, src + s2);
+        anybad |= __shfl_sync(0xffffffffu, bad, src + s2);
+        if (row[s2] < mn) { mn = row[s2]; min_index = s2; }
+    }
+    if (M > 0 && c == 0 && g < VM_CH) {
+        SegDev& P = probs[pi];
+        for (int s2 = 0; s2 < 6; ++s2) P.last_row[s2] = row[s2];
+        P.sstar = min_index;
+        P.final_loss = mn;
+        if (anybad || mn == FLT_MAX) { P.status = HCNV_E_NO_MINIMUM; P.skip = 2; }
+    }
+}
+
 // best_state / cn columns (Hmm.java:234-237, 483-484)
-__global__ void k_traceback(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
+__global__ void __launch_bounds__(256) k_traceback(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
     const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
     SegDev& P = probs[pi];
-    long long i = (long long)((int)blockIdx.x - __ldg(&blk_base[pi])) * 256 + threadIdx.x;
+    const long long i0 = (long long)((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
     const long long M = P.M;
-    if (i >= M) return;
     if (P.par && !P.irregular && !P.skip) return;    // k_vit_p3 already wrote the calls
-    int st = 0;
-    if (!P.skip) {
-        int s = P.sstar;
-        if (i == M - 1) st = c_cn[s];                                         // (sic) Hmm.java:234
-        else st = (int)((P.codes[i + 1] >> (3 * s)) & 7u);                    // traceback[m+1][s*], Hmm.java:236
+    const int skip = P.skip, s = P.sstar, many = P.many;
+    const uint32_t* __restrict__ codes = P.codes;
+    int32_t* __restrict__ o_state = P.state; int32_t* __restrict__ o_cn = P.cn;
+    const long long stride = (M + VM_PACK - 1) / VM_PACK;
+    #pragma unroll
+    for (int k = 0; k < SEG_BLK / 256; ++k) {
+        const long long i = i0 + k * 256;
+        if (i >= M) break;
+        int st = 0;
+        if (!skip) {
+            if (i == M - 1) st = c_cn[s];                                         // (sic) Hmm.java:234
+            else if (many) {                                                      // per-state code words of k_viterbi_many
+                const long long m = i + 1;
+                st = (int)((__ldg(&codes[s * stride + m / VM_PACK]) >> (3 * (int)(m % VM_PACK))) & 7u);
+            }
+            else st = (int)((__ldg(&codes[i + 1]) >> (3 * s)) & 7u);              // traceback[m+1][s*], Hmm.java:236
+        }
+        if (o_state) o_state[i] = st;
+        if (o_cn) o_cn[i] = c_cn[st];
     }
-    if (P.state) P.state[i] = st;
-    if (P.cn) P.cn[i] = c_cn[st];
 }
 
 #include "viterbi_par.cuh"
@@ -471,7 +663,7 @@ __global__ void k_pack_results(long long n, const int32_t* __restrict__ state, c
 
 // ---------------------------------------------------------------------------------------------------
 namespace {
-enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR, H_RT_WORK, H_DOWNLOAD = 26 };
+enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR, H_RT_WORK, H_ORDER, H_DOWNLOAD = 26 };
 }
 
 int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
@@ -580,12 +772,55 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         if (q.n_markers >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers");
         if (!q.median || !q.mse || !q.total || !q.n) return hcnv_fail(ctx, HCNV_E_INVALID, "null input array");
         const void* ptrs[7] = { q.median, q.mse, q.total, q.n, q.scaled, q.state, q.cn };
+        // (a pointer query costs about a microsecond: every pointer of the first 64 problems, then one input and one output each)
         for (int j = 0; j < 7; ++j) {
-            if (!ptrs[j]) continue;
+            if (!ptrs[j] || (i >= 64 && j != 0 && j != 4)) continue;
             int kd = hcnv_ptr_kind(ptrs[j]) == 2 ? 2 : 0;
             if (kind < 0) kind = kd; else if (kind != kd) return hcnv_fail(ctx, HCNV_E_INVALID, "mixed host/device pointers");
         }
         totM += q.n_markers;
+    }
+    // Which Viterbi for which chromosome?  route[i] = 0: the literal one-warp kernel (short chromosomes, or forced),
+    // 1: the segment-parallel kernels, 2: the many-chains kernel.  The segment-parallel path costs ~0.076 ns per marker (six
+    // times the arithmetic; measured on the 384- and 1 536-problem sweeps) but a chain's latency hardly grows with its
+    // length; the many-chains kernel costs <= 0.029 ns per marker (6 144 problems) and never less than ~70 ns x its
+    // longest chain (one warp walks it).  They run one after the other (side by side on two streams the lone warps of the
+    // many-chains kernel lose their issue slots to the wide kernels: 335 ms instead of 201 / 242 ms on the 1 536-problem
+    // sweep), so the longest chromosomes go to the first and the rest to the second, split where the sum of the two
+    // estimates is smallest: a genome's 24 chains all take the first path, a cohort's thousands all take the second.
+    std::vector<char> route(n_problems, 0);
+    std::vector<int> order;                                 // the many-chains kernel's chromosomes, longest first
+    if (!(flags & HCNV_SEG_SEQUENTIAL)) {
+        std::vector<int> lng;
+        int n_short = 0;
+        for (int i = 0; i < n_problems; ++i) {
+            if (probs[i].n_markers >= V_PAR_MIN_MARKERS) lng.push_back(i);
+            else if (probs[i].n_markers >= VM_MIN_MARKERS) ++n_short;
+        }
+        std::stable_sort(lng.begin(), lng.end(), [&](int a, int b) { return probs[a].n_markers > probs[b].n_markers; });
+        size_t k_par = lng.size();                          // lng[0 .. k_par) -> segment-parallel, the rest -> many-chains
+        if (flags & HCNV_SEG_THROUGHPUT) k_par = 0;
+        else if (!(flags & HCNV_SEG_LATENCY) && !lng.empty()) {
+            std::vector<double> suffix(lng.size() + 1, 0.0);
+            for (size_t j = lng.size(); j-- > 0;) suffix[j] = suffix[j + 1] + (double)probs[lng[j]].n_markers;
+            double best = 1e300, prefix = 0.0;
+            for (size_t k = 0; k <= lng.size(); ++k) {
+                if (k == 0 || k == lng.size() || probs[lng[k]].n_markers != probs[lng[k - 1]].n_markers) {
+                    const double t_par = k ? 1.5e-3 + 0.076e-9 * prefix : 0.0;
+                    const double t_many = k < lng.size() ? std::max(70e-9 * (double)probs[lng[k]].n_markers, 0.029e-9 * suffix[k]) + 0.2e-3 : 0.0;
+                    const double t = t_par + t_many;
+                    if (t < best) { best = t; k_par = k; }
+                }
+                if (k < lng.size()) prefix += (double)probs[lng[k]].n_markers;
+            }
+        }
+        for (size_t j = 0; j < lng.size(); ++j) route[lng[j]] = j < k_par ? 1 : 2;
+        const bool many_short = (flags & HCNV_SEG_THROUGHPUT) || (!(flags & HCNV_SEG_LATENCY) && (k_par < lng.size() || n_short >= 64));
+        if (many_short)
+            for (int i = 0; i < n_problems; ++i)
+                if (probs[i].n_markers < V_PAR_MIN_MARKERS && probs[i].n_markers >= VM_MIN_MARKERS) route[i] = 2;
+        for (int i = 0; i < n_problems; ++i) if (route[i] == 2) order.push_back(i);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return probs[a].n_markers > probs[b].n_markers; });
     }
     const bool dev = kind == 2;
     std::vector<SegDev> h(n_problems);
@@ -597,9 +832,11 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         HCNV_CUDA(ctx, ctx->buf[H_OUT_I32].reserve(4 * 2 * (size_t)totM));
     }
     long long off = 0;
-    std::vector<int> blk_base(n_problems + 1, 0);          // 256-marker blocks before each chromosome (scale / traceback grids)
+    std::vector<int> blk_base(n_problems + 1, 0);          // SEG_BLK-marker blocks before each chromosome (scale / traceback grids)
     const int VSEG = VSEG_DEFAULT;
     std::vector<int> seg_base(n_problems + 1, 0);
+    std::map<std::tuple<const void*, const void*, long long>, int> mean_first;
+    bool any_mean_copy = false;
     for (int i = 0; i < n_problems; ++i) {
         hcnv_segment_problem& q = probs[i];
         SegDev& d = h[i];
@@ -624,10 +861,16 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
             d.state = ctx->buf[H_OUT_I32].as<int32_t>() + off;
             d.cn = ctx->buf[H_OUT_I32].as<int32_t>() + totM + off;
         }
-        if ((M + 255) / 256 + blk_base[i] > 0x7fffffffLL) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers in one call");
-        blk_base[i + 1] = blk_base[i] + (int)((M + 255) / 256);
+        if ((M + SEG_BLK - 1) / SEG_BLK + blk_base[i] > 0x7fffffffLL) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers in one call");
+        blk_base[i + 1] = blk_base[i] + (int)((M + SEG_BLK - 1) / SEG_BLK);
         off += M;
-        d.par = (!(flags & HCNV_SEG_SEQUENTIAL) && M >= V_PAR_MIN_MARKERS) ? 1 : 0;
+        {
+            auto key = std::make_tuple((const void*)q.total, (const void*)q.n, (long long)M);
+            auto it = mean_first.find(key);
+            if (it == mean_first.end()) mean_first.emplace(key, i); else { d.mean_src1 = it->second + 1; any_mean_copy = true; }
+        }
+        d.many = route[i] == 2 ? 1 : 0;
+        d.par = route[i] == 1 ? 1 : 0;
         d.n_seg = d.par ? (int)((M - 1 + VSEG - 1) / VSEG) : 0;
         d.first_bad = 0x7fffffff;
         seg_base[i + 1] = seg_base[i] + d.n_seg;
@@ -645,6 +888,7 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
     KT_BEGIN(ctx, HCNV_K_MEAN_COVERAGE);
     k_mean_coverage_cluster<<<n_problems * MCC_CS, MCC_T, 0, ctx->stream>>>(dprobs);
     k_mean_coverage<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
+    if (any_mean_copy) { k_mean_copy<<<(n_problems + 255) / 256, 256, 0, ctx->stream>>>(dprobs, n_problems); ctx->launches++; }
     KT_END(ctx, HCNV_K_MEAN_COVERAGE);
     KT_BEGIN(ctx, HCNV_K_SCALE_DEPTH);
     k_scale_depth<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_blkbase, n_problems);
@@ -653,6 +897,18 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
     k_sd<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems, alpha);
     KT_END(ctx, HCNV_K_SD);
     ctx->launches += 4;
+
+    // ---- large batches: the many-chains kernel (five chromosomes per warp, longest first)
+    if (!order.empty()) {
+        HCNV_CUDA(ctx, ctx->buf[H_ORDER].reserve(4 * order.size()));
+        int* d_order = ctx->buf[H_ORDER].as<int>();
+        HCNV_CUDA(ctx, cudaMemcpyAsync(d_order, order.data(), 4 * order.size(), cudaMemcpyHostToDevice, ctx->stream));
+        KT_BEGIN(ctx, HCNV_K_VIT_MANY);
+        k_viterbi_many<<<(unsigned)((order.size() + VM_CH - 1) / VM_CH), 32, 0, ctx->stream>>>(dprobs, d_order, (int)order.size(), alpha);
+        KT_END(ctx, HCNV_K_VIT_MANY);
+        HCNV_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
 
     // ---- exact segment-parallel Viterbi for the long chromosomes (viterbi_par.cuh)
     if (total_segs > 0) {
@@ -727,8 +983,8 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
         ctx->vit_segments = total_segs; ctx->vit_replayed = 0;
         for (int i = 0; i < n_problems; ++i) if (h[i].par && !h[i].irregular && !h[i].skip) ctx->vit_replayed += repl[i];
     } else { ctx->vit_segments = 0; ctx->vit_replayed = 0; }
-    // ---- everything else (short chromosomes, irregular inputs): the literal one-warp kernel
     KT_BEGIN(ctx, HCNV_K_VITERBI);
+    // ---- everything else (short chromosomes, irregular inputs): the literal one-warp kernel
     k_viterbi_seq<<<n_problems, 32, 0, ctx->stream>>>(dprobs, alpha);
     KT_END(ctx, HCNV_K_VITERBI);
     KT_BEGIN(ctx, HCNV_K_TRACEBACK);

@@ -81,7 +81,8 @@ int         hcnv_ctx_synchronize(hcnv_ctx* ctx);
 #define HCNV_K_VIT_P1B        14    /*   chunk matrices (composition of 32 segment matrices)     */
 #define HCNV_K_VIT_P2B        15    /*   per-segment start vectors inside composed chunks        */
 #define HCNV_K_SNP_MSE        16    /* BAF statistics of the bins that hold SNP sites             */
-#define HCNV_K_COUNT          17
+#define HCNV_K_VIT_MANY       17    /* many-chains Viterbi (large batches)                        */
+#define HCNV_K_COUNT          18
 float       hcnv_ctx_kernel_ms(hcnv_ctx* ctx, int which);
 /* which kernels get timing events: bit k = HCNV_K_* number k; default 1 << HCNV_K_BIN_TILES (an event pair around every
  * launch costs a measurable share of a ~10 ms step); ~0u times them all */
@@ -219,6 +220,8 @@ typedef struct {
 } hcnv_segment_problem;
 
 #define HCNV_SEG_SEQUENTIAL 1       /* flags: force the one-warp-per-chromosome exact kernel */
+#define HCNV_SEG_THROUGHPUT 2       /* flags: force the many-chains kernel (five chromosomes per warp): the choice for large batches */
+#define HCNV_SEG_LATENCY    4       /* flags: force the segment-parallel kernels for long chromosomes: the choice for a few chains */
 int hcnv_segment_batch(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems, int32_t flags);
 
 /* ---- results download ------------------------------------------------------------------------------ */

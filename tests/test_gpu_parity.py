@@ -250,7 +250,7 @@ def test_segment_parallel_viterbi_is_exact(ctx, seed, M, l1, l2, depth):
     prob = dict(median=b["median"], mse=mse32, total=tot32, n=b["n"], lambda1=l1, lambda2=l2)
     want = O.hmm(b["median"], mse32, tot32, b["n"], l1, l2, fast=True)
     want_full = O.hmm(b["median"], mse32, tot32, b["n"], l1, l2) if M <= 130000 else None
-    got = ctx.segment_batch([dict(prob)])[0]
+    got = ctx.segment_batch([dict(prob)], flags=L.HCNV_SEG_LATENCY)[0]      # (a single short chromosome would go to the many-chains kernel)
     st = ctx.stats()
     assert st["viterbi_segments"] == (M - 1 + 63) // 64 and st["viterbi_repairs"] == 0
     assert st["viterbi_segments_replayed"] < st["viterbi_segments"]           # the matrices really carry most segments
@@ -298,6 +298,79 @@ def test_segment_parallel_mixed_batch(ctx):
         if want["rc"] >= 0:
             np.testing.assert_array_equal(got["state"], want["state"])
             assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+
+
+def test_many_chains_viterbi_is_exact(ctx):
+    """The throughput path for large batches (five chromosomes per warp, literal recurrence): a mixed batch -- lengths that
+    are no multiple of the chunk or of the code-word packing, auto penalties, a skipped chromosome, NaN inputs, fewer
+    chromosomes than a warp holds in the last warp -- must agree with the oracle call for call, and with the default path."""
+    rng = np.random.default_rng(71)
+    spec = [(50000, 0.01, 1.6, False), (30001, 0.3, 0.4, False), (20000, 0.01, 0.004, False), (64, 0.3, 0.4, False), (9007, 0.1, 0.8, False),
+            (12345, -1.0, -1.0, False), (70, 0.05, 3.2, False), (30000, 0.01, 1.6, True), (33, 0.01, 1.6, False), (1, 0.01, 1.6, False),
+            (2, 0.01, 1.6, False), (4099, 0.5, 1.0, False), (65, 0.01, 1.6, False)]
+    probs, wants = [], []
+    for M, l1, l2, nan in spec:
+        b = Hp.random_bins(rng, M)
+        mse32 = O.f64_text_f32(b["mse"]); tot32 = b["total"].astype(np.float32)
+        if nan:
+            mse32[M // 2, 3] = np.nan
+        probs.append(dict(median=b["median"], mse=mse32, total=tot32, n=b["n"], lambda1=l1, lambda2=l2))
+        wants.append(O.hmm(b["median"], mse32, tot32, b["n"], l1, l2, fast=M > 20000))
+    gots = ctx.segment_batch([dict(q) for q in probs], flags=L.HCNV_SEG_THROUGHPUT, raise_on_exit=False)
+    assert ctx.stats()["viterbi_segments"] == 0                      # nothing went through the segment-parallel kernels
+    dflt = ctx.segment_batch([dict(q) for q in probs], raise_on_exit=False)
+    for got, d, want in zip(gots, dflt, wants):
+        assert got["status"] == (L.HCNV_E_NO_MINIMUM if want["rc"] < 0 else want["rc"])
+        assert got["status"] == d["status"]
+        if want["rc"] >= 0:
+            np.testing.assert_array_equal(got["state"], want["state"])
+            np.testing.assert_array_equal(got["cn"], want["cn"])
+            np.testing.assert_array_equal(got["state"], d["state"])
+            assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+            if want["rc"] == 0:
+                np.testing.assert_array_equal(got["last_row"].view(np.uint32), d["last_row"].view(np.uint32))
+
+
+def test_penalty_sweep_shares_the_mean_coverage(ctx):
+    """A penalty sweep hands the same arrays in once per pair: the mean coverage is computed for the first and copied to the
+    others (device inputs: the same tensors; the sequential float sum above 2^24 must still be the reference's)."""
+    import torch
+    rng = np.random.default_rng(73)
+    M = 30000
+    b = Hp.random_bins(rng, M)
+    b2 = Hp.random_bins(rng, 5000)
+    tot = (b["total"] * 700).astype(np.float32)                      # running sum far above 2^24
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    med, mse, tt, nn = dev(b["median"]), dev(b["mse"].astype(np.float32)), dev(tot), dev(b["n"])
+    pairs = [(0.01, 1.6), (0.3, 0.4), (-1.0, -1.0), (0.05, 3.2)]
+    probs = [dict(median=med, mse=mse, total=tt, n=nn, lambda1=l1, lambda2=l2) for l1, l2 in pairs]
+    probs.insert(2, dict(median=dev(b2["median"]), mse=dev(b2["mse"].astype(np.float32)), total=dev(b2["total"].astype(np.float32)), n=dev(b2["n"]), lambda1=0.01, lambda2=1.6))
+    gots = ctx.segment_batch(probs)
+    wants = [O.hmm(b["median"], b["mse"].astype(np.float32), tot, b["n"], l1, l2, fast=True) for l1, l2 in pairs]
+    wants.insert(2, O.hmm(b2["median"], b2["mse"].astype(np.float32), b2["total"].astype(np.float32), b2["n"], 0.01, 1.6, fast=True))
+    for got, want in zip(gots, wants):
+        assert f32(got["mean_coverage"]).view(np.uint32) == f32(want["mean_coverage"]).view(np.uint32)
+        np.testing.assert_array_equal(got["state"].cpu().numpy(), want["state"])
+        assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+
+
+def test_many_chains_is_chosen_for_large_batches(ctx):
+    """2 000 chromosome x penalty problems in one call: the library picks the many-chains kernel by itself, and the calls are
+    those of the forced segment-parallel path."""
+    rng = np.random.default_rng(72)
+    base = [Hp.random_bins(rng, M) for M in (6000, 5000, 4500, 4100)]
+    probs = []
+    for i in range(2000):
+        b = base[i % 4]
+        probs.append(dict(median=b["median"], mse=b["mse"].astype(np.float32), total=b["total"].astype(np.float32), n=b["n"],
+                          lambda1=0.01 * (1 + i % 7), lambda2=0.4 * (1 + i % 5)))
+    got = ctx.segment_batch([dict(q) for q in probs])
+    assert ctx.stats()["viterbi_segments"] == 0
+    ref = ctx.segment_batch([dict(q) for q in probs], flags=L.HCNV_SEG_LATENCY)
+    assert ctx.stats()["viterbi_segments"] > 0
+    for g, r in zip(got, ref):
+        np.testing.assert_array_equal(g["state"], r["state"])
+        assert f32(g["final_loss"]).view(np.uint32) == f32(r["final_loss"]).view(np.uint32)
 
 
 @pytest.mark.parametrize("seed,M,hi,frac", [(61, 1000000, 6000, False), (62, 300000, 1 << 26, False), (63, 50000, 40, False),
