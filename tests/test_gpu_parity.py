@@ -547,3 +547,75 @@ def test_download_results_is_lossless(ctx):
         ctx.download_results(start, end, scaled, state, cn, d_mse, h["start"], h["end"], h["scaled"], h["state"], h["cn"],
                              h["rows"][:10], h["vals"][:10])
     assert e.value.status == L.HCNV_E_CAPACITY
+
+
+def test_full_genome_properties():
+    """BASELINE.json configs[1] at FULL size (30X hg19-shaped genome, 572 M reads, 28.6 M bins): too large for the oracle,
+    so parity is checked through size-independent properties -- the checksum of the bins (sum of total depth = aligned
+    bases of the input), structure of every row, both input encodings agreeing bit for bit, a chromosome subset agreeing
+    with its rows of the whole-genome call (shard invariance), idempotence, and the exact segment-parallel Viterbi
+    agreeing with the literal one-warp recurrence on every chromosome (chr1: 2.49 M markers)."""
+    import torch
+    W = 100
+    names = [c["name"] for c in synth.hg19_shape()["contigs"]]
+    g = synth.make_genome(coverage=30.0, seed=0xC0FFEE + 1, device="cuda", contigs=names, scale=1.0)
+    ctx = H.Context(0)
+    try:
+        cap = sum(c.length // W + 1 for c in g)
+        api_c = synth.to_api_contigs(g, compact=True)
+        res = ctx.bin_contigs(api_c, bin_width=W, max_block_len=150, out=ctx.alloc_bins(cap, True, len(g)), capacity=cap)
+        off = [int(x) for x in res.contig_offset]
+        nb = off[-1]
+        assert 28_000_000 < nb < 31_000_000
+        # checksum: every aligned base is counted once in exactly one bin
+        aligned = sum(int((c.blocks[:, 1] & 0xFFFFFF).sum()) + int(c.long_blocks[:, 1].sum()) for c in g)
+        assert int(res.total[:nb].sum(dtype=torch.float64)) == aligned
+        # structure of every row
+        b, s, e, n = res.bin[:nb], res.start[:nb], res.end[:nb], res.n[:nb]
+        assert bool(((b % W) == 0).all()) and bool((s >= b).all()) and bool((e >= s).all()) and bool((e <= b + W - 1).all())
+        assert bool((n >= 1).all()) and bool((n <= e - s + 1).all())
+        for i in range(len(g)):
+            bi = b[off[i]:off[i + 1]]
+            assert bool((bi[1:] > bi[:-1]).all())                                    # ascending within a chromosome (the shuffle's order)
+            assert int(e[off[i]:off[i + 1]].max()) <= g[i].length
+        keep = {k: getattr(res, k)[:nb].clone() for k in ("bin", "start", "end", "median", "total", "n")}
+        keep["mse"] = res.mse[:nb].clone()
+        # idempotence + the 8-byte record encoding of the same reads
+        for api in (api_c, synth.to_api_contigs(g, compact=False)):
+            r2 = ctx.bin_contigs(api, bin_width=W, max_block_len=150, out=ctx.alloc_bins(cap, True, len(g)), capacity=cap)
+            assert [int(x) for x in r2.contig_offset] == off
+            for k, v in keep.items():
+                a2 = getattr(r2, k)[:nb]
+                assert bool((a2.view(torch.int64) == v.view(torch.int64)).all()) if v.dtype == torch.float64 else bool((a2 == v).all()), k
+            del r2
+        # shard invariance: two chromosomes on their own
+        sub = [names.index("chr21"), names.index("chrX")]
+        cap3 = sum(g[i].length // W + 1 for i in sub)
+        r3 = ctx.bin_contigs([api_c[i] for i in sub], bin_width=W, max_block_len=150, out=ctx.alloc_bins(cap3, True, len(sub)), capacity=cap3)
+        o3 = [int(x) for x in r3.contig_offset]
+        for j, i in enumerate(sub):
+            for k in ("bin", "start", "end", "median", "total", "n"):
+                assert bool((getattr(r3, k)[o3[j]:o3[j + 1]] == keep[k][off[i]:off[i + 1]]).all()), (names[i], k)
+            assert bool((r3.mse[o3[j]:o3[j + 1]].view(torch.int64) == keep["mse"][off[i]:off[i + 1]].view(torch.int64)).all())
+        # segmentation: exact segment-parallel path == literal recurrence, all 24 chromosomes
+        m32, t32 = ctx.bins_to_hmm_input(keep["mse"], keep["total"])
+        probs = [dict(median=keep["median"][off[i]:off[i + 1]], mse=m32[off[i]:off[i + 1]], total=t32[off[i]:off[i + 1]], n=keep["n"][off[i]:off[i + 1]],
+                      lambda1=0.01, lambda2=1.6) for i in range(len(g))]
+        par = ctx.segment_batch([dict(q) for q in probs])
+        st = ctx.stats()
+        assert st["viterbi_segments"] > 400_000 and st["viterbi_repairs"] == 0
+        seq = ctx.segment_batch([dict(q) for q in probs], flags=L.HCNV_SEG_SEQUENTIAL)
+        many = ctx.segment_batch([dict(q) for q in probs], flags=L.HCNV_SEG_THROUGHPUT)
+        cn_of = torch.tensor([0, 1, 2, 2, 3, 4], device="cuda", dtype=torch.int32)
+        for p_, s_, m_ in zip(par, seq, many):
+            assert p_["status"] == 0 and s_["status"] == 0 and m_["status"] == 0
+            for other in (s_, m_):
+                assert bool((p_["state"] == other["state"]).all()) and bool((p_["cn"] == other["cn"]).all())
+                assert f32(p_["final_loss"]).view(np.uint32) == f32(other["final_loss"]).view(np.uint32)
+                assert (p_["last_row"].view(np.uint32) == other["last_row"].view(np.uint32)).all()
+                assert bool((p_["scaled"].view(torch.int32) == other["scaled"].view(torch.int32)).all())
+            assert int(p_["state"].min()) >= 0 and int(p_["state"].max()) <= 5
+            assert bool((p_["cn"] == cn_of[p_["state"].long()]).all())                # Hmm.java:483-484
+            assert float(p_["scaled"].min()) >= -2.0 and float(p_["scaled"].max()) <= 2.0
+    finally:
+        ctx.close()
