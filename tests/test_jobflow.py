@@ -1,0 +1,84 @@
+"""The stage flow of hadoopcnv_b200.jobflow (PennCnvSeq.run's stages, toggles and workdir layout) against the
+line-by-line restatement at the reference's text level: BAM + VCF + config.txt in, bins part file and results.txt out,
+compared VERBATIM; then single stages re-run from what the first run left on disk."""
+import os
+
+import numpy as np
+import pytest
+
+from hadoopcnv_b200 import jobflow, sharding
+from oracle import literal as Lit
+from tests import helpers as Hp
+
+
+def _sample(tmp_path, seed=5):
+    rng = np.random.default_rng(seed)
+    refs = [("7", 26000), ("chr15", 9000), ("X", 700)]
+    reads = []
+    for name, length in refs[:2]:
+        rs = Hp.random_reads(rng, 900 if name == "7" else 300, length - 400, refname=name)
+        rs.append((name, 1, "%dM" % length, b"", b"", 0))                  # the baseline BAM's whole-interval SEQ=* read
+        reads += rs
+    snps = {"7": sorted(set(int(x) for x in rng.integers(1, 26000, 250))), "chr15": sorted(set(int(x) for x in rng.integers(1, 9000, 60)))}
+    vcf_lines = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1"]
+    for name in ("7", "chr15"):
+        vcf_lines += Hp.vcf_lines_for(name, [(q, int(rng.choice([0, -1, -2]))) for q in snps[name]])[2:]
+    vcf = tmp_path / "s.vcf"
+    vcf.write_text("\n".join(vcf_lines) + "\n")
+    bam = tmp_path / "child.sort.bam"
+    ref_id = {n: i for i, (n, _) in enumerate(refs)}
+    recs = sorted([(ref_id[r[0]], r[1] - 1, r[2], r[3], r[5], 0) for r in reads], key=lambda t: (t[0], t[1]))
+    Hp.write_bam(str(bam), refs, recs)
+    return reads, vcf_lines, str(bam), str(vcf)
+
+
+def _config(tmp_path, bam, vcf, **toggles):
+    t = dict(RUN_DEPTH_CALLER="true", RUN_GLOBAL_SORT="false", INIT_VCF_LOOKUP="true", RUN_BINNER="true", RUN_CNV_CALLER="true", RUN_SR_PE_EXTRACTER="false")
+    t.update(toggles)
+    p = tmp_path / "config.txt"
+    p.write_text("# test\nBAM_FILE: %s\nVCF_FILE: %s\n" % (bam, vcf) + "".join("%s: %s\n" % kv for kv in t.items()) +
+                 "BAM_FILE_REDUCERS: 800\nTEXT_FILE_REDUCERS: 100\nREDUCER_TASKS: 24\nABBERATION_PENALTY: 0.01f\nTRANSITION_PENALTY: 1.6f\n")
+    return str(p)
+
+
+def test_stage_dirs_follow_the_reference():
+    d = jobflow.stage_dirs("/bamfiles/child_hg19_SVs_v2.sort.bam")
+    assert d == {"depth": "workdir/depth/child_hg19_SVs_v2.sort", "bins": "workdir/bins/child_hg19_SVs_v2.sort", "cnv": "workdir/cnv/child_hg19_SVs_v2.sort"}
+
+
+@pytest.mark.gpu
+def test_job_flow_matches_the_text_level_restatement(tmp_path):
+    reads, vcf_lines, bam, vcf = _sample(tmp_path)
+    wd = str(tmp_path / "workdir")
+    rep = jobflow.run(_config(tmp_path, bam, vcf), workdir=wd, results_path=str(tmp_path / "results.txt"))
+    # what the three jobs of the reference would have written
+    want_vcf = Lit.parse_vcf_to_text(vcf_lines)
+    want_bins = Lit.binner(Lit.depth_caller(reads) + want_vcf)
+    want_res = Lit.cnv_caller(want_bins, np.float32(0.01), np.float32(1.6))
+    d = rep["dirs"]
+    assert d["cnv"].endswith(os.path.join("cnv", "child.sort"))
+    assert sorted(open(os.path.join(d["depth"], "vcf.txt")).read().splitlines()) == sorted(set(want_vcf))
+    got_bins = open(os.path.join(d["bins"], "part-r-00000")).read().splitlines()
+    assert sorted(got_bins) == sorted(want_bins) and len(got_bins) == rep["stages"]["RUN_BINNER"]["bins"]
+    # results.txt: part files in reducer order, chromosomes in String order inside a part (PennCnvSeq.java:382-414)
+    chroms = sorted({ln.split("\t")[0] for ln in want_res})
+    by_chr = {c: [ln for ln in want_res if ln.split("\t")[0] == c] for c in chroms}
+    merged = [ln for c in sorted(chroms, key=lambda c: (sharding.reducer_of(c, 24), c)) for ln in by_chr[c]]
+    got_res = open(tmp_path / "results.txt").read().splitlines()
+    assert got_res == merged
+    assert len([p for p in os.listdir(d["cnv"]) if p.startswith("part-r-")]) == 24
+    first = got_res[:]
+
+    # RUN_CNV_CALLER alone, from the bins part file on disk (the penalty-sweep workflow), split over two part files
+    lines = got_bins
+    os.remove(os.path.join(d["bins"], "part-r-00000"))
+    open(os.path.join(d["bins"], "part-r-00000"), "w").write("".join(ln + "\n" for ln in lines[0::2]))
+    open(os.path.join(d["bins"], "part-r-00001"), "w").write("".join(ln + "\n" for ln in lines[1::2]))
+    os.remove(tmp_path / "results.txt")
+    jobflow.run(_config(tmp_path, bam, vcf, RUN_DEPTH_CALLER="false", INIT_VCF_LOOKUP="false", RUN_BINNER="false"), workdir=wd,
+                results_path=str(tmp_path / "results.txt"))
+    assert open(tmp_path / "results.txt").read().splitlines() == first
+
+    # RUN_BINNER alone, from the packed records the depth-caller stage left behind
+    rep3 = jobflow.run(_config(tmp_path, bam, vcf, RUN_DEPTH_CALLER="false", INIT_VCF_LOOKUP="false", RUN_CNV_CALLER="false"), workdir=wd)
+    assert sorted(open(rep3["stages"]["RUN_BINNER"]["file"]).read().splitlines()) == sorted(want_bins)
