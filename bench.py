@@ -234,13 +234,12 @@ def run_b200(args):
         res = ctx.bin_contigs(api_contigs, bin_width=W, max_block_len=READ_LEN, tile_bins=args.tile_bins, out=out, capacity=cap)
         kms = ctx.kernel_ms()
         m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total)
-        probs = []
-        for i in range(len(api_contigs)):
-            a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
-            if b > a:
-                probs.append(dict(median=res.median[a:b], mse=m32[a:b], total=t32[a:b], n=res.n[a:b], lambda1=LAMBDA1, lambda2=LAMBDA2,
-                                  scaled=seg_scaled[a:b], state=seg_state[a:b], cn=seg_cn[a:b]))
-        calls = ctx.segment_batch(probs) if probs else []
+        # one Hmm per non-empty chromosome (row ranges of the same arrays: the problem array is filled by pointer arithmetic)
+        prep, live = ctx.prepare_segments_of_bins(res, m32, t32, LAMBDA1, LAMBDA2, seg_scaled, seg_state, seg_cn)
+        calls = []
+        if live:
+            status, loss = ctx.run_segment_batch(prep, scalars_only=True)
+            calls = [dict(status=int(s_), final_loss=float(l_)) for s_, l_ in zip(status, loss)]
         kms.update(ctx.kernel_ms())
         state.update(res=res, m32=m32, calls=calls, kms=kms)
         return res, m32, calls
@@ -442,7 +441,7 @@ def run_b200(args):
                                          "algorithmic_bytes_per_bin": 36},
                                  "fp32_issue": {"achieved": 204 * n_bins / (seg_ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12, "unit": "Tops/s (no FMA)",
                                                 "frac": 204 * n_bins / (seg_ms * 1e-3) / fp32_peak, "ops_per_bin": 204},
-                                 "throughput_case": "tools/bench_cohort.py (configs[4]: 384 chains per call)"}
+                                 "throughput_case": "tools/bench_cohort.py (configs[4]: thousands of chains per call; profiles/r01_v12_cohort_*.json)"}
 
     if rank == 0:
         line = {

@@ -316,15 +316,40 @@ class Context:
             a.want_sd = int(q.get("want_sd", 0))
         return arr, keep
 
+    def prepare_segments_of_bins(self, res: "BinsResult", m32, t32, lambda1: float, lambda2: float, scaled, state, cn):
+        """One hcnv_segment_problem per non-empty chromosome of a binning result (CnvReducer gets one call per chromosome,
+        Reducers.java:225-243): the chromosomes are row ranges of the same arrays, so the problems are filled by pointer
+        arithmetic.  m32 / t32: hcnv_bins_to_hmm_input's outputs; scaled / state / cn: output arrays of len(res) rows.
+        Returns (prepared, chromosome indices)."""
+        off = [int(x) for x in res.contig_offset]
+        live = [i for i in range(len(off) - 1) if off[i + 1] > off[i]]
+        arr = (L.SegmentProblem * len(live))()
+        pm, pe, pt, pn, ps, pst, pc = _ptr(res.median), _ptr(m32), _ptr(t32), _ptr(res.n), _ptr(scaled), _ptr(state), _ptr(cn)
+        for j, i in enumerate(live):
+            a, q = off[i], arr[j]
+            q.n_markers = off[i + 1] - a
+            q.median, q.mse, q.total, q.n = pm + 4 * a, pe + 24 * a, pt + 4 * a, pn + 4 * a
+            q.lambda1, q.lambda2 = float(lambda1), float(lambda2)
+            q.scaled, q.state, q.cn = ps + 4 * a, pst + 4 * a, pc + 4 * a
+        keep = [(res, m32, t32, scaled, state, cn)]                 # the arrays the pointers point into (scalars_only results)
+        return (arr, keep), live
+
+    @staticmethod
+    def segment_scalars(prepared) -> np.ndarray:
+        """The problem array as a numpy record view: mean_coverage, sd, lambda1_used, lambda2_used, final_loss, last_row, status."""
+        return np.frombuffer(prepared[0], dtype=np.dtype(L.SegmentProblem))
+
     def run_segment_batch(self, prepared, alpha: float = 0.5, flags: int = 0, raise_on_exit: bool = True, scalars_only: bool = False):
-        """hcnv_segment_batch on a prepared array.  scalars_only: return (status, final_loss) arrays instead of one dict per problem."""
+        """hcnv_segment_batch on a prepared array.  scalars_only: return (status, final_loss) arrays instead of one dict per
+        problem (`segment_scalars(prepared)` gives the other scalar outputs)."""
         arr, keep = prepared
         k = len(arr)
         st = self._lib.hcnv_segment_batch(self._h, float(alpha), k, arr, flags)
         if st < 0 and (raise_on_exit or st != L.HCNV_E_NO_MINIMUM):
             self._check(st)
         if scalars_only:
-            return (np.fromiter((arr[i].status for i in range(k)), np.int32, k), np.fromiter((arr[i].final_loss for i in range(k)), np.float32, k))
+            v = np.frombuffer(arr, dtype=np.dtype(L.SegmentProblem))          # a view of the problem array: every scalar output by name
+            return v["status"].copy(), v["final_loss"].copy()
         res = []
         for i in range(k):
             a = arr[i]

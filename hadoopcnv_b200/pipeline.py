@@ -127,10 +127,12 @@ class GenomePipeline:
         t_.append(time.perf_counter())
         if "seg" in skip:
             return [empty(i, nm, off[j + 1] - off[j]) for j, (i, nm) in enumerate(zip(idx, names))]
-        live = [j for j in range(len(idx)) if off[j + 1] > off[j]]
-        calls = ctx.segment_batch([dict(median=res.median[off[j]:off[j + 1]], mse=m32[off[j]:off[j + 1]], total=t32[off[j]:off[j + 1]],
-                                        n=res.n[off[j]:off[j + 1]], lambda1=lambda1, lambda2=lambda2, scaled=scaled[off[j]:off[j + 1]],
-                                        state=state[off[j]:off[j + 1]], cn=cn[off[j]:off[j + 1]]) for j in live])
+        prep, live = ctx.prepare_segments_of_bins(res, m32, t32, lambda1, lambda2, scaled, state, cn)
+        if live:
+            ctx.run_segment_batch(prep, scalars_only=True)
+        sc_ = ctx.segment_scalars(prep)
+        calls = [dict(mean_coverage=np.float32(r_["mean_coverage"]), final_loss=np.float32(r_["final_loss"]), lambda1=np.float32(r_["lambda1_used"]),
+                      lambda2=np.float32(r_["lambda2_used"]), status=int(r_["status"])) for r_ in sc_]
         t_.append(time.perf_counter())
         results = [empty(i, nm) for i, nm in zip(idx, names)]
         for j, call in zip(live, calls):
