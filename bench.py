@@ -223,6 +223,7 @@ def run_b200(args):
     cap = sum(c.length // W + 1 for c in contigs)
 
     ctx = H.Context(local)
+    api_dev_prepared = ctx.prepare_contigs(api_dev)          # resident inputs: the call's input array is built once
     out = ctx.alloc_bins(cap, True, len(contigs))
     seg_scaled = torch.empty(cap, dtype=torch.float32, device=dev)
     seg_state = torch.empty(cap, dtype=torch.int32, device=dev)
@@ -272,14 +273,14 @@ def run_b200(args):
 
     # ---- resident-input leg (value): warm-up, then K timed steps
     for _ in range(max(args.warmup, 3)):
-        hot_path(api_dev)
+        hot_path(api_dev_prepared)
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = ctx.kernel_launches
     kacc = {}
 
     def step_resident():
-        hot_path(api_dev)
+        hot_path(api_dev_prepared)
         for k_, v in state["kms"].items():
             kacc.setdefault(k_, []).append(v)
 
