@@ -16,7 +16,13 @@ lens = [c.length for c in contigs]; nm = [c.name for c in contigs]
 del contigs; torch.cuda.empty_cache()
 for workers in WORKERS:
     pipe = GenomePipeline(0, workers); out = GenomeOutput(lens, 100)
-    for _ in range(2): pipe.run(hc, nm, out, max_block_len=150)
+    import os
+    if os.environ.get('HCNV_PIECE_MB'): pipe.upload_piece_bytes = int(float(os.environ['HCNV_PIECE_MB']) * (1 << 20))
+    for _ in range(3): pipe.run(hc, nm, out, max_block_len=150)
+    ts = []
+    for _ in range(5):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); pipe.run(hc, nm, out, max_block_len=150); torch.cuda.synchronize(); ts.append(round(1e3 * (time.perf_counter() - t0), 1))
+    print('piece MB', os.environ.get('HCNV_PIECE_MB'), 'runs ms', ts)
     pipe.trace = []
     torch.cuda.synchronize(); t0 = time.perf_counter(); pipe.run(hc, nm, out, max_block_len=150); torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print("workers", workers, "total ms", round(1e3 * dt, 1))
