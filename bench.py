@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="debug: skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-format", default="compact", choices=["compact", "records"],
-                    help="compact: 2-byte delta-coded block stream (include/hcnv.h hcnv_cblock); records: 8-byte hcnv_block")
+                    help="compact: 2-byte delta-coded block stream and 2-byte observations (include/hcnv.h hcnv_cblock, hcnv_cobs); records: 8-byte hcnv_block, 4-byte observations")
     ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
     ap.add_argument("--e2e-groups", type=int, default=8, help="tasks (groups of chromosomes) per genome in the end-to-end leg")
     return ap.parse_args()
@@ -213,7 +213,8 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     compact = args.block_format == "compact"
-    api_dev = synth.to_api_contigs(contigs, compact=compact)
+    api_dev = synth.to_api_contigs(contigs, compact=compact, compact_observations=compact)     # compact: 2-byte blocks AND 2-byte observations
+    n_cobs = sum(int(a.cobs.shape[0]) for a in api_dev if a.cobs is not None)
     n_stream = sum(int(a.cblocks.shape[0]) for a in api_dev if a.cblocks is not None) if compact else 0
     n_reads = sum(c.n_reads for c in contigs)
     n_blocks = sum(int(c.blocks.shape[0]) for c in contigs)
@@ -325,14 +326,16 @@ def run_b200(args):
                 return h.numpy()
             if compact:
                 a = api_dev[len(host_contigs)]
-                hc = H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs),
-                              pin(a.cblocks) if a.cblocks is not None else None, pin(a.anchors) if a.anchors is not None else None)
+                hc = H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), None,
+                              pin(a.cblocks) if a.cblocks is not None else None, pin(a.anchors) if a.anchors is not None else None,
+                              pin(a.cobs) if a.cobs is not None else None, pin(a.cobs_anchors) if a.cobs is not None else None)
                 h2d += a.cblocks.numel() * 2 + a.anchors.numel() * 4 if a.cblocks is not None else 0
+                h2d += a.cobs.numel() * 2 + a.cobs_anchors.numel() * 4 if a.cobs is not None else 0
             else:
                 hc = H.Contig(c.length, pin(c.blocks), pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs))
                 h2d += c.blocks.numel() * 4
             host_contigs.append(hc)
-            h2d += c.long_blocks.numel() * 4 + c.snp_pos1.numel() * 4 + c.snp_zyg.numel() + c.obs.numel() * 4
+            h2d += c.long_blocks.numel() * 4 + c.snp_pos1.numel() * 4 + c.snp_zyg.numel() + (0 if compact else c.obs.numel() * 4)
         torch.cuda.synchronize()
         # results.txt columns: start, end, scaled, state, cn, mse[6] (Hmm.java:479-490), per chromosome, into pinned arrays.
         # The call a user makes: GenomePipeline.run = per chromosome hcnv_bin_contigs -> hcnv_bins_to_hmm_input ->
@@ -387,7 +390,7 @@ def run_b200(args):
     # at 30X).  What the kernel really reads is LESS (bytes_enc: the 2-byte delta-coded stream + anchors, or the 8-byte
     # records): the encoding is an optimisation of the same algorithmic work; both are reported.
     bytes_bin = 12 * (n_blocks + n_long) + 4 * n_obs + 8 * n_snp + 72 * n_bins
-    bytes_enc = (2 * n_stream + 4 * (n_stream // 128) if compact else 8 * n_blocks) + 16 * n_long + 4 * n_obs + 5 * n_snp + 72 * n_bins
+    bytes_enc = (2 * n_stream + 4 * (n_stream // 128) + 2 * n_cobs + 4 * (n_cobs // 256) if compact else 8 * n_blocks + 4 * n_obs) + 16 * n_long + 5 * n_snp + 72 * n_bins
     bytes_vit = 36 * n_bins
     traffic = None                      # DRAM bytes per launch of the tile kernel from the committed ncu capture of this very workload
     try:

@@ -14,6 +14,7 @@ HCNV_VITERBI_SKIPPED = 1
 HCNV_E_INVALID, HCNV_E_CUDA, HCNV_E_NOMEM, HCNV_E_RANGE, HCNV_E_UNSORTED = -1, -2, -3, -4, -5
 HCNV_E_INCONSISTENT, HCNV_E_NO_MINIMUM, HCNV_E_IO, HCNV_E_PARSE, HCNV_E_CAPACITY, HCNV_E_INTERNAL = -6, -7, -8, -9, -10, -11
 HCNV_SHORT_MAX = 4095
+HCNV_OGROUP = 256
 HCNV_SEG_SEQUENTIAL = 1
 HCNV_SEG_THROUGHPUT = 2
 HCNV_SEG_LATENCY = 4
@@ -39,7 +40,8 @@ class ContigInput(C.Structure):
                 ("long_blocks", C.c_void_p), ("n_long", C.c_int64),
                 ("snp_pos1", C.c_void_p), ("snp_zyg", C.c_void_p), ("n_snp", C.c_int64),
                 ("obs", C.c_void_p), ("n_obs", C.c_int64),
-                ("cblocks", C.c_void_p), ("anchors", C.c_void_p), ("n_cblocks", C.c_int64)]
+                ("cblocks", C.c_void_p), ("anchors", C.c_void_p), ("n_cblocks", C.c_int64),
+                ("cobs", C.c_void_p), ("cobs_anchors", C.c_void_p), ("n_cobs", C.c_int64)]
 
 
 class ResultsDownload(C.Structure):
@@ -82,7 +84,7 @@ EXPORTS = [
     "hcnv_write_bins_text", "hcnv_write_results_text",
     "hcnv_read_bins_text", "hcnv_bins_text_n_chromosomes", "hcnv_bins_text_get", "hcnv_bins_text_free",
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
-    "hcnv_compact_blocks", "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
+    "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
 ]
 
 _lib = None
@@ -120,6 +122,8 @@ def lib():
     L.hcnv_download_results.argtypes = [C.c_void_p, C.POINTER(ResultsDownload)]
     L.hcnv_compact_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
     L.hcnv_compact_blocks.restype = C.c_int64
+    L.hcnv_compact_obs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+    L.hcnv_compact_obs.restype = C.c_int64
     L.hcnv_ctx_stream.argtypes = [C.c_void_p]
     L.hcnv_ctx_stream.restype = C.c_void_p
     L.hcnv_ctx_kernel_launches.argtypes = [C.c_void_p]

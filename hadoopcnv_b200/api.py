@@ -69,6 +69,30 @@ def compact_blocks(blocks: np.ndarray, mapping_quality_threshold: float = 0.0):
     return cb, anchors[: n // L.HCNV_CGROUP]
 
 
+def compact_obs(obs: np.ndarray):
+    """hcnv_compact_obs: observations (snp index << 4 | base4) -> (cobs uint16, cobs_anchors int32): 2 bytes each
+    (index - group anchor : 12 | base4 : 4), one anchor per HCNV_OGROUP entries, a group closed early with fillers where the
+    indices jump by more than 4094, padded to a whole group."""
+    lib = L.lib()
+    obs = np.ascontiguousarray(obs, dtype=np.uint32)
+    n = lib.hcnv_compact_obs(obs.ctypes.data, len(obs), None, None, 0)
+    if n < 0:
+        raise L.HcnvError(int(n), "hcnv_compact_obs: %s" % lib.hcnv_strerror(int(n)).decode())
+    co = np.empty(n, np.uint16)
+    anchors = np.empty(max(1, n // L.HCNV_OGROUP), np.int32)
+    m = lib.hcnv_compact_obs(obs.ctypes.data, len(obs), co.ctypes.data, anchors.ctypes.data, n)
+    assert m == n
+    return co, anchors[: n // L.HCNV_OGROUP]
+
+
+def expand_cobs(cobs, cobs_anchors) -> np.ndarray:
+    """Inverse of compact_obs on the host (numpy): the 4-byte observations, fillers dropped."""
+    co = np.asarray(cobs, dtype=np.uint16).astype(np.uint32)
+    idx = np.repeat(np.asarray(cobs_anchors, dtype=np.int64), L.HCNV_OGROUP)[: len(co)] + (co >> 4)
+    keep = (co >> 4) != 4095
+    return ((idx[keep] << 4) | (co[keep] & 15)).astype(np.uint32)
+
+
 def expand_cblocks(cblocks, anchors) -> np.ndarray:
     """Inverse of compact_blocks on the host (numpy): one hcnv_block record (MAPQ 0) per non-filler entry, i.e. per PIECE
     of a block (test helper; pieces of a block above 255 bases stay separate, which is results-neutral)."""
@@ -107,6 +131,8 @@ class Contig:
     obs: object = None             # uint32 (torch: int32) snp_index << 4 | base4
     cblocks: object = None         # alternative to blocks: hcnv_cblock stream (uint16 / torch int16), 16-byte aligned
     anchors: object = None         # int32, one per HCNV_CGROUP compact records
+    cobs: object = None            # alternative to obs: hcnv_cobs stream (uint16 / torch int16)
+    cobs_anchors: object = None    # int32, one per HCNV_OGROUP compact observations
 
 
 @dataclass
@@ -247,7 +273,8 @@ class Context:
             arr[i].snp_pos1, arr[i].snp_zyg, arr[i].n_snp = _ptr(c.snp_pos1), _ptr(c.snp_zyg), _len(c.snp_pos1)
             arr[i].obs, arr[i].n_obs = _ptr(c.obs), _len(c.obs)
             arr[i].cblocks, arr[i].anchors, arr[i].n_cblocks = _ptr(c.cblocks), _ptr(c.anchors), _len(c.cblocks)
-            for x in (c.blocks, c.cblocks, c.long_blocks, c.snp_pos1, c.obs):
+            arr[i].cobs, arr[i].cobs_anchors, arr[i].n_cobs = _ptr(c.cobs), _ptr(c.cobs_anchors), _len(c.cobs)
+            for x in (c.blocks, c.cblocks, c.long_blocks, c.snp_pos1, c.obs, c.cobs):
                 if x is not None and _is_torch(x):
                     on_device = True
         return PreparedContigs(list(contigs), arr, on_device)

@@ -27,7 +27,9 @@ struct ContigDev {
     const hcnv_long_block* longs;
     const int32_t*         snp_pos;
     const int8_t*          snp_zyg;
-    const uint32_t*        obs;
+    const uint32_t*        obs;       // observations at 4 bytes, or ...
+    const hcnv_cobs*       cobs;      // ... at 2 bytes (n_obs entries, a multiple of HCNV_OGROUP) with their anchors
+    const int32_t*         cobs_anchors;
     long long n_blocks, n_long, n_snp, n_obs;
     long long snp_base;     // row offset of this contig in the tally table
     long long obs_base32;   // start of this contig's observations in the launch-wide index space (each contig rounded up to 256)
@@ -193,14 +195,25 @@ __global__ void __launch_bounds__(256) k_tally(BinK p, long long n_obs_total) {
         const ContigDev& c = p.contigs[lo];
         const long long i0 = g0 - c.obs_base32 + lane, n_obs = c.n_obs, n_snp = c.n_snp;
         const uint32_t* __restrict__ obs = c.obs;
+        const hcnv_cobs* __restrict__ cobs = c.cobs;
         uint32_t* tally = p.tally + 16 * (size_t)c.snp_base;
         uint32_t ov[8];
-        #pragma unroll
-        for (int u = 0; u < 8; ++u) ov[u] = (i0 + 32 * u < n_obs) ? __ldg(&obs[i0 + 32 * u]) : 0xFFFFFFFFu;    // eight loads in flight
+        if (cobs) {
+            // 2-byte observations: a span is one group (HCNV_OGROUP = 256 entries) with one anchor; a filler names no site
+            const uint32_t anchor = (uint32_t)__ldg(&c.cobs_anchors[(g0 - c.obs_base32) / HCNV_OGROUP]);
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t v = (i0 + 32 * u < n_obs) ? (uint32_t)__ldg(&cobs[i0 + 32 * u]) : HCNV_COBS_FILLER;
+                ov[u] = (v >> 4) == 4095u ? 0xFFFFFFFFu : (((anchor + (v >> 4)) << 4) | (v & 15u));
+            }
+        } else {
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) ov[u] = (i0 + 32 * u < n_obs) ? __ldg(&obs[i0 + 32 * u]) : 0xFFFFFFFFu;    // eight loads in flight
+        }
         #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const uint32_t o = ov[u];
-            const bool valid = i0 + 32 * u < n_obs;
+            const bool valid = cobs ? (o != 0xFFFFFFFFu) : (i0 + 32 * u < n_obs);
             const unsigned act = __ballot_sync(0xffffffffu, valid);
             if (!valid) continue;
             const unsigned same = __match_any_sync(act, o);         // lanes that saw the same (site, base)
@@ -327,6 +340,13 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         }
     }
     if (compact < 0) compact = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+        const hcnv_contig_input& ci = contigs[c];
+        if (ci.n_cobs < 0 || (ci.n_cobs > 0 && ci.n_obs > 0)) return hcnv_fail(ctx, HCNV_E_INVALID, "give obs or cobs, not both");
+        if (ci.n_cobs % HCNV_OGROUP) return hcnv_fail(ctx, HCNV_E_INVALID, "n_cobs must be a multiple of HCNV_OGROUP (pad with fillers)");
+        if (ci.n_cobs > 0 && (!ci.cobs || !ci.cobs_anchors)) return hcnv_fail(ctx, HCNV_E_INVALID, "null cobs / cobs_anchors");
+        if (ci.n_cobs > 0 && (reinterpret_cast<uintptr_t>(ci.cobs) & 1)) return hcnv_fail(ctx, HCNV_E_INVALID, "cobs must be 2-byte aligned");
+    }
 
     // tile geometry: one warp = one tile of 32 bins; a warp's shared-memory slice = tile records + two record chunks +
     // the difference array of its 32 * W positions; as many warps per SM as fit
@@ -341,25 +361,26 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
 
     // pointer kinds
     int in_kind = -1;
-    long long tot_blocks = 0, tot_cblocks = 0, tot_long = 0, tot_snp = 0, tot_obs = 0, tot_bins_max = 0;
+    long long tot_blocks = 0, tot_cblocks = 0, tot_long = 0, tot_snp = 0, tot_obs = 0, tot_cobs = 0, tot_bins_max = 0;
     for (int c = 0; c < n_contigs; ++c) {
         const hcnv_contig_input& ci = contigs[c];
         if (ci.length < 0 || ci.n_blocks < 0 || ci.n_long < 0 || ci.n_snp < 0 || ci.n_obs < 0) return hcnv_fail(ctx, HCNV_E_INVALID, "negative count");
         if (ci.n_blocks >= (1ll << 31) || ci.n_snp >= (1ll << 28)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many records in one contig");
         if (ci.length > 0x7fffffff - 2 * HCNV_SHORT_MAX - 4096 * 128) return hcnv_fail(ctx, HCNV_E_INVALID, "contig too long");
         if (ci.n_blocks && (reinterpret_cast<uintptr_t>(ci.blocks) & 7)) return hcnv_fail(ctx, HCNV_E_INVALID, "blocks must be 8-byte aligned");
-        const void* ptrs[7] = { ci.n_blocks ? (const void*)ci.blocks : nullptr, ci.n_long ? (const void*)ci.long_blocks : nullptr,
+        const void* ptrs[9] = { ci.n_blocks ? (const void*)ci.blocks : nullptr, ci.n_long ? (const void*)ci.long_blocks : nullptr,
                                 ci.n_snp ? (const void*)ci.snp_pos1 : nullptr, ci.n_snp ? (const void*)ci.snp_zyg : nullptr,
                                 ci.n_obs ? (const void*)ci.obs : nullptr, ci.n_cblocks ? (const void*)ci.cblocks : nullptr,
-                                ci.n_cblocks ? (const void*)ci.anchors : nullptr };
-        const long long cnts[7] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs, ci.n_cblocks, ci.n_cblocks };
-        for (int j = 0; j < 7; ++j) {
+                                ci.n_cblocks ? (const void*)ci.anchors : nullptr, ci.n_cobs ? (const void*)ci.cobs : nullptr,
+                                ci.n_cobs ? (const void*)ci.cobs_anchors : nullptr };
+        const long long cnts[9] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs, ci.n_cblocks, ci.n_cblocks, ci.n_cobs, ci.n_cobs };
+        for (int j = 0; j < 9; ++j) {
             if (cnts[j] == 0) continue;
             if (!ptrs[j]) return hcnv_fail(ctx, HCNV_E_INVALID, "null input array with non-zero count");
             int kd = hcnv_ptr_kind(ptrs[j]) == 2 ? 2 : 0;
             if (in_kind < 0) in_kind = kd; else if (in_kind != kd) return hcnv_fail(ctx, HCNV_E_INVALID, "mixed host/device input pointers");
         }
-        tot_blocks += ci.n_blocks; tot_cblocks += ci.n_cblocks; tot_long += ci.n_long; tot_snp += ci.n_snp; tot_obs += ci.n_obs;
+        tot_blocks += ci.n_blocks; tot_cblocks += ci.n_cblocks; tot_long += ci.n_long; tot_snp += ci.n_snp; tot_obs += ci.n_obs; tot_cobs += ci.n_cobs;
         tot_bins_max += ci.length / W + 1;
     }
     if (in_kind < 0) in_kind = 0;
@@ -377,9 +398,12 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         HCNV_CUDA(ctx, ctx->buf[B_IN_LONG].reserve(sizeof(hcnv_long_block) * (size_t)tot_long));
         HCNV_CUDA(ctx, ctx->buf[B_IN_SNPPOS].reserve(4 * (size_t)tot_snp));
         HCNV_CUDA(ctx, ctx->buf[B_IN_SNPZYG].reserve((size_t)tot_snp + 16 * n_contigs));
-        HCNV_CUDA(ctx, ctx->buf[B_IN_OBS].reserve(4 * (size_t)tot_obs));
+        HCNV_CUDA(ctx, ctx->buf[B_IN_OBS].reserve(4 * (size_t)tot_obs + 2 * (size_t)tot_cobs + 4 * (size_t)(tot_cobs / HCNV_OGROUP) + 128));
     }
-    long long ob = 0, ocb = 0, ol = 0, os = 0, oo = 0, obs32_total = 0;
+    long long ob = 0, ocb = 0, ol = 0, os = 0, oo = 0, oco = 0, obs32_total = 0;
+    // (host inputs) B_IN_OBS holds the 4-byte observations, then the 2-byte ones, then their anchors
+    char* const obs_stage = ctx->buf[B_IN_OBS].as<char>();
+    const size_t cobs_at = (4 * (size_t)tot_obs + 15) / 16 * 16, canc_at = (cobs_at + 2 * (size_t)tot_cobs + 15) / 16 * 16;
     int tile_base = 0;
     for (int c = 0; c < n_contigs; ++c) {
         const hcnv_contig_input& ci = contigs[c];
@@ -387,6 +411,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         if (in_kind == 2) {
             d.blocks = ci.blocks; d.longs = ci.long_blocks; d.snp_pos = ci.snp_pos1; d.snp_zyg = ci.snp_zyg; d.obs = ci.obs;
             d.cblocks = ci.cblocks; d.anchors = ci.anchors;
+            d.cobs = ci.n_cobs ? ci.cobs : nullptr; d.cobs_anchors = ci.cobs_anchors;
         } else {
             d.cblocks = ctx->buf[B_IN_BLOCKS].as<hcnv_cblock>() + ocb;            // (a call uses one form, so the buffer is shared)
             d.anchors = ctx->buf[B_IN_ANCHORS].as<int32_t>() + ocb / HCNV_CGROUP;
@@ -403,13 +428,17 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             if ((rc = stage_in(ctx, in_kind, ci.snp_pos1, ci.n_snp, const_cast<int32_t*>(d.snp_pos)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.snp_zyg, ci.n_snp, const_cast<int8_t*>(d.snp_zyg)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.obs, ci.n_obs, const_cast<uint32_t*>(d.obs)))) return rc;
+            d.cobs = ci.n_cobs ? reinterpret_cast<const hcnv_cobs*>(obs_stage + cobs_at) + oco : nullptr;
+            d.cobs_anchors = reinterpret_cast<const int32_t*>(obs_stage + canc_at) + oco / HCNV_OGROUP;
+            if ((rc = stage_in(ctx, in_kind, ci.cobs, ci.n_cobs, const_cast<hcnv_cobs*>(reinterpret_cast<const hcnv_cobs*>(obs_stage + cobs_at) + oco)))) return rc;
+            if ((rc = stage_in(ctx, in_kind, ci.cobs_anchors, ci.n_cobs / HCNV_OGROUP, const_cast<int32_t*>(d.cobs_anchors)))) return rc;
         }
-        d.n_blocks = ci.n_blocks; d.n_cblocks = ci.n_cblocks; d.n_long = ci.n_long; d.n_snp = ci.n_snp; d.n_obs = ci.n_obs;
-        d.obs_base32 = obs32_total; obs32_total += (ci.n_obs + 255) / 256 * 256;
+        d.n_blocks = ci.n_blocks; d.n_cblocks = ci.n_cblocks; d.n_long = ci.n_long; d.n_snp = ci.n_snp; d.n_obs = ci.n_cobs ? ci.n_cobs : ci.n_obs;
+        d.obs_base32 = obs32_total; obs32_total += (d.n_obs + 255) / 256 * 256;
         d.snp_base = os; d.length = ci.length; d.n_bins_max = ci.length / W + 1;
         d.tile_base = tile_base; d.n_tiles = (d.n_bins_max + TB - 1) / TB;
         tile_base += d.n_tiles;
-        ob += ci.n_blocks; ocb += ci.n_cblocks; ol += ci.n_long; os += ci.n_snp; oo += ci.n_obs;
+        ob += ci.n_blocks; ocb += ci.n_cblocks; ol += ci.n_long; os += ci.n_snp; oo += ci.n_obs; oco += ci.n_cobs;
     }
     const int n_tiles = tile_base;
 
@@ -465,7 +494,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     KT_END(ctx, HCNV_K_TILE_INDEX);
     ctx->launches++;
     KT_BEGIN(ctx, HCNV_K_TALLY);
-    if (tot_obs) {
+    if (tot_obs + tot_cobs) {
         const long long nb = (obs32_total / 256 + 7) / 8;                 // 8 warps per CTA, one 256-observation span per warp and pass
         const int grid = (int)std::max<long long>(1, std::min<long long>(nb, (long long)ctx->sm_count * 16));
         k_tally<<<grid, 256, 0, ctx->stream>>>(k, obs32_total);

@@ -31,6 +31,7 @@ struct hcnv_pack {
         std::string name; int32_t length = 0; int32_t max_len = 0;
         std::vector<hcnv_block> blocks; std::vector<hcnv_long_block> longs; std::vector<uint32_t> obs;
         std::vector<hcnv_cblock> cstore; std::vector<int32_t> anchors; hcnv_cblock* cblocks = nullptr; int64_t n_cblocks = -1;   // built on demand
+        std::vector<hcnv_cobs> cobs; std::vector<int32_t> cobs_anchors; int64_t n_cobs = -1;                                        // built on demand
         const std::vector<int32_t>* snp_pos = nullptr; const std::vector<int8_t>* snp_zyg = nullptr;
     };
     std::vector<Contig> contigs;
@@ -337,6 +338,33 @@ int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, double mapping_
     return k;
 }
 
+int64_t hcnv_compact_obs(const uint32_t* obs, int64_t n, hcnv_cobs* out, int32_t* anchors, int64_t capacity) {
+    if (n < 0 || (n > 0 && !obs) || (out && !anchors)) return HCNV_E_INVALID;
+    int64_t k = 0;                                          // entries written (or counted) so far
+    int64_t i = 0;
+    while (i < n) {
+        // one group: as many of the next observations as keep max - min of the indices within 4094, at most HCNV_OGROUP
+        uint32_t lo = obs[i] >> 4, hi = lo;
+        if (lo >= (1u << 28) - 1) return HCNV_E_RANGE;
+        int64_t j = i + 1;
+        for (; j < n && j - i < HCNV_OGROUP; ++j) {
+            const uint32_t x = obs[j] >> 4;
+            const uint32_t nlo = x < lo ? x : lo, nhi = x > hi ? x : hi;
+            if (nhi - nlo > 4094u) break;
+            lo = nlo; hi = nhi;
+        }
+        if (out) {
+            if (k + HCNV_OGROUP > capacity) return HCNV_E_CAPACITY;
+            anchors[k / HCNV_OGROUP] = (int32_t)lo;
+            for (int64_t t = i; t < j; ++t) out[k + (t - i)] = (hcnv_cobs)((((obs[t] >> 4) - lo) << 4) | (obs[t] & 15u));
+            for (int64_t t = j - i; t < HCNV_OGROUP; ++t) out[k + t] = (hcnv_cobs)HCNV_COBS_FILLER;
+        }
+        k += HCNV_OGROUP;
+        i = j;
+    }
+    return k;
+}
+
 int32_t hcnv_pack_n_contigs(const hcnv_pack* p) { return p ? (int32_t)p->contigs.size() : 0; }
 int64_t hcnv_pack_n_records(const hcnv_pack* p) { return p ? p->n_records : 0; }
 
@@ -369,8 +397,19 @@ int hcnv_pack_contig_compact(hcnv_pack* p, int32_t i, const char** name, hcnv_co
         if (m != n) return HCNV_E_INTERNAL;
         c.n_cblocks = n;
     }
+    if (c.n_cobs < 0) {                                     // and the 2-byte observations
+        const int64_t n = hcnv_compact_obs(c.obs.data(), (int64_t)c.obs.size(), nullptr, nullptr, 0);
+        if (n < 0) return (int)n;
+        c.cobs.resize((size_t)n);
+        c.cobs_anchors.resize((size_t)(n / HCNV_OGROUP) + 1);
+        const int64_t m = hcnv_compact_obs(c.obs.data(), (int64_t)c.obs.size(), c.cobs.data(), c.cobs_anchors.data(), n);
+        if (m != n) return HCNV_E_INTERNAL;
+        c.n_cobs = n;
+    }
     in->blocks = nullptr; in->n_blocks = 0;
     in->cblocks = c.n_cblocks ? c.cblocks : nullptr; in->anchors = c.n_cblocks ? c.anchors.data() : nullptr; in->n_cblocks = c.n_cblocks;
+    in->obs = nullptr; in->n_obs = 0;
+    in->cobs = c.n_cobs ? c.cobs.data() : nullptr; in->cobs_anchors = c.n_cobs ? c.cobs_anchors.data() : nullptr; in->n_cobs = c.n_cobs;
     return HCNV_OK;
 }
 

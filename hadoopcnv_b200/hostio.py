@@ -55,7 +55,8 @@ class SnpTable:
 
 def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = False):
     """hcnv_bam_pack -> (names, [Contig with numpy arrays], [max_block_len], n_records).  Arrays are copies.
-    compact=True: the block stream comes in the 2-byte delta-coded form (Contig.cblocks / anchors)."""
+    compact=True: the block stream comes in the 2-byte delta-coded form (Contig.cblocks / anchors) and the observations in
+    their 2-byte form (Contig.cobs / cobs_anchors)."""
     lib = L.lib()
     h = C.c_void_p()
     st = lib.hcnv_bam_pack(bam_path.encode(), snps._h if snps is not None else None, C.byref(h))
@@ -84,7 +85,8 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
             contigs.append(Contig(ci.length, arr(ci.blocks, ci.n_blocks, BLOCK_DTYPE), arr(ci.long_blocks, ci.n_long, LONG_BLOCK_DTYPE),
                                   arr(ci.snp_pos1, ci.n_snp, np.int32), arr(ci.snp_zyg, ci.n_snp, np.int8),
                                   arr(ci.obs, ci.n_obs, np.uint32), arr16(ci.cblocks, ci.n_cblocks),
-                                  arr(ci.anchors, ci.n_cblocks // L.HCNV_CGROUP, np.int32)))
+                                  arr(ci.anchors, ci.n_cblocks // L.HCNV_CGROUP, np.int32),
+                                  arr(ci.cobs, ci.n_cobs, np.uint16), arr(ci.cobs_anchors, ci.n_cobs // L.HCNV_OGROUP, np.int32)))
         return names, contigs, maxlens, int(lib.hcnv_pack_n_records(h))
     finally:
         lib.hcnv_pack_free(h)

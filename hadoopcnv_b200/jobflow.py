@@ -34,7 +34,7 @@ from . import hostio
 from .api import (Contig, Context, config_load, read_bins_text, write_bins_text, write_results_text)
 from .sharding import reducer_of
 
-_FIELDS = ("blocks", "long_blocks", "snp_pos1", "snp_zyg", "obs", "cblocks", "anchors")
+_FIELDS = ("blocks", "long_blocks", "snp_pos1", "snp_zyg", "obs", "cblocks", "anchors", "cobs", "cobs_anchors")
 
 
 def stage_dirs(bam_file: str, workdir: str = "workdir") -> Dict[str, str]:

@@ -179,7 +179,7 @@ class GenomePipeline:
         with torch.cuda.stream(self._copy):
             for i in order:
                 c = contigs[i]
-                fields = [as_tensor(v) for v in (c.blocks, c.long_blocks, c.snp_pos1, c.snp_zyg, c.obs, c.cblocks, c.anchors)]
+                fields = [as_tensor(v) for v in (c.blocks, c.long_blocks, c.snp_pos1, c.snp_zyg, c.obs, c.cblocks, c.anchors, c.cobs, c.cobs_anchors)]
                 key = tuple(None if f is None else (tuple(f.shape), f.dtype) for f in fields)
                 slot = self._staging.get(i)
                 if slot is None or slot[0] != key:

@@ -243,10 +243,27 @@ def compact_on_device(blocks: torch.Tensor):
     return code, anchors
 
 
-def to_api_contigs(contigs: List[SynthContig], host: bool = False, compact: bool = False):
+def to_api_contigs(contigs: List[SynthContig], host: bool = False, compact: bool = False, compact_observations: bool = False):
     """SynthContig -> hadoopcnv_b200.api.Contig (torch tensors stay where they are; host=True -> numpy).
-    compact=True sends the block stream in the 2-byte delta-coded form."""
+    compact=True sends the block stream in the 2-byte delta-coded form; compact_observations=True the observations in their
+    2-byte form as well (built on the host by hcnv_compact_obs, then placed where the other arrays are)."""
     from .api import Contig
+    if compact_observations:
+        import numpy as np
+        import torch
+        from .api import compact_obs
+        res = to_api_contigs(contigs, host, compact, False)
+        for a, c in zip(res, contigs):
+            if c.obs.shape[0] == 0:
+                continue
+            co, an = compact_obs(c.obs.cpu().numpy().view(np.uint32))
+            a.obs = None
+            if host:
+                a.cobs, a.cobs_anchors = co, an
+            else:
+                a.cobs = torch.from_numpy(co.view(np.int16)).to(c.obs.device)
+                a.cobs_anchors = torch.from_numpy(an).to(c.obs.device)
+        return res
     if compact:
         res = []
         for c in contigs:

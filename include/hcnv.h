@@ -110,6 +110,15 @@ typedef struct { int32_t start0; uint32_t len_mapq; } hcnv_block;
 typedef uint16_t hcnv_cblock;
 #define HCNV_CGROUP 128
 
+/* The observations at SNP sites at 2 bytes each (at 4 bytes they are a fifth of what a 30X genome uploads):
+ *   bits 0-3  BAM 4-bit base code      bits 4-15  snp index - cobs_anchors[k / HCNV_OGROUP]   (0..4094; 4095 = filler, no observation)
+ * Observations arrive in block order, so the indices of HCNV_OGROUP consecutive ones lie close together; where they do not
+ * (a jump of more than 4094 sites inside a group) the group is closed early with fillers.  The stream is padded with fillers
+ * to a multiple of HCNV_OGROUP entries: n_cobs counts them all.  hcnv_compact_obs builds it. */
+typedef uint16_t hcnv_cobs;
+#define HCNV_OGROUP 256
+#define HCNV_COBS_FILLER 0xFFF0u
+
 /* A block of any length (e.g. the baseline BAM's artificial whole-interval reads, example/preprocessBAM.py).
  * Not required to be sorted.  Splitting a block is results-neutral: only per-position counts matter. */
 typedef struct { int32_t start0; int32_t len; int32_t mapq; int32_t reserved; } hcnv_long_block;
@@ -136,6 +145,8 @@ typedef struct {
     const uint32_t*        obs;         int64_t n_obs;
     /* alternative to `blocks` (give one or the other; all contigs of a call use the same form) */
     const hcnv_cblock*     cblocks;     const int32_t* anchors; int64_t n_cblocks;
+    /* alternative to `obs` (give one or the other, per contig): the observations at 2 bytes each, see hcnv_cobs */
+    const hcnv_cobs*       cobs;        const int32_t* cobs_anchors; int64_t n_cobs;
 } hcnv_contig_input;
 
 /* Host helper (no GPU): sorted hcnv_block records -> compact stream; blocks whose MAPQ fails mapping_quality_threshold
@@ -145,6 +156,11 @@ typedef struct {
  * start0 or len > HCNV_SHORT_MAX, HCNV_E_CAPACITY if `capacity` (in records) is too small. */
 int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, double mapping_quality_threshold,
                             hcnv_cblock* out, int32_t* anchors, int64_t capacity);
+
+/* Host helper (no GPU): obs (snp index << 4 | base4, any order) -> the 2-byte stream.  Returns the number of entries
+ * (fillers and padding included, a multiple of HCNV_OGROUP) or a negative status; with out == NULL only counts.  anchors
+ * needs result / HCNV_OGROUP entries.  HCNV_E_RANGE for an index of 2^28 or more, HCNV_E_CAPACITY if `capacity` is too small. */
+int64_t hcnv_compact_obs(const uint32_t* obs, int64_t n, hcnv_cobs* out, int32_t* anchors, int64_t capacity);
 
 /* Outputs: one record per non-empty bin, all contigs concatenated in input order, bins ascending within a
  * contig (the (chr,bin) secondary sort, PennCnvSeq.java:382-414).  Field meaning = the columns BinReducer

@@ -80,6 +80,14 @@ def test_binning_compact_stream_matches_oracle(ctx, W, cov, thr):
             r = res.contig(i)
             got = r if host else H.BinsResult(*[x.cpu().numpy() for x in (r.bin, r.start, r.end, r.median, r.mse, r.total, r.n)], r.contig_offset)
             assert_bins_equal(got, oracle_bins(c, W, thr))
+        if thr == 0:                                   # and with the observations in their 2-byte form as well
+            api_o = synth.to_api_contigs(gg, host=host, compact=True, compact_observations=True)
+            assert any(a.cobs is not None for a in api_o) and all(a.obs is None for a in api_o)
+            res = ctx.bin_contigs(api_o, bin_width=W, max_block_len=synth.READ_LEN)
+            for i, c in enumerate(g):
+                r = res.contig(i)
+                got = r if host else H.BinsResult(*[x.cpu().numpy() for x in (r.bin, r.start, r.end, r.median, r.mse, r.total, r.n)], r.contig_offset)
+                assert_bins_equal(got, oracle_bins(c, W, thr))
 
 
 def test_binning_compact_stream_edge_cases(ctx):
@@ -298,6 +306,33 @@ def test_segment_parallel_mixed_batch(ctx):
         if want["rc"] >= 0:
             np.testing.assert_array_equal(got["state"], want["state"])
             assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+
+
+def test_compact_observations_edge_cases(ctx):
+    """2-byte observations: index jumps that close a group early, a contig whose observations are all fillers' worth of
+    padding, an out-of-range index (HCNV_E_RANGE), obs and cobs together (HCNV_E_INVALID), a stream that is no whole group."""
+    rng = np.random.default_rng(81)
+    length, W = 60000, 100
+    blocks, snp, zyg, obs = _random_contig(rng, length, 3000, 80, 9000)         # ~9 000 sites: shuffled observations jump by thousands
+    obs = obs[rng.permutation(len(obs))]
+    want = ctx.bin_contigs([H.Contig(length, blocks, None, snp, zyg, obs)], bin_width=W)
+    co, an = H.compact_obs(obs)
+    assert len(co) % 256 == 0 and len(an) == len(co) // 256 and len(co) > len(obs)    # groups were closed early
+    assert sorted(H.expand_cobs(co, an).tolist()) == sorted(obs.tolist())
+    got = ctx.bin_contigs([H.Contig(length, blocks, None, snp, zyg, None, None, None, co, an)], bin_width=W)
+    for k in ("bin", "start", "end", "n", "median", "total"):
+        np.testing.assert_array_equal(getattr(got, k), getattr(want, k))
+    np.testing.assert_array_equal(got.mse.view(np.uint64), want.mse.view(np.uint64))
+    with pytest.raises(H.HcnvError) as e:
+        ctx.bin_contigs([H.Contig(length, blocks, None, snp, zyg, obs, None, None, co, an)], bin_width=W)
+    assert e.value.status == L.HCNV_E_INVALID
+    with pytest.raises(H.HcnvError) as e:
+        ctx.bin_contigs([H.Contig(length, blocks, None, snp, zyg, None, None, None, co[:-1], an)], bin_width=W)
+    assert e.value.status == L.HCNV_E_INVALID
+    bad = an.copy(); bad[-1] = len(snp)                                         # an index at or above n_snp
+    with pytest.raises(H.HcnvError) as e:
+        ctx.bin_contigs([H.Contig(length, blocks, None, snp, zyg, None, None, None, co, bad)], bin_width=W)
+    assert e.value.status in (L.HCNV_E_RANGE, L.HCNV_E_INCONSISTENT)
 
 
 def test_many_chains_viterbi_is_exact(ctx):

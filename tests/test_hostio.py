@@ -72,6 +72,7 @@ def test_bam_pack_matches_htsjdk_semantics(tmp_path, seed):
     # the same pack in the compact form expands to the same records
     _, cc, _, _ = hostio.pack_bam(str(bam), table, compact=True)
     assert cc[0].blocks is None and cc[0].cblocks.ctypes.data % 16 == 0
+    assert cc[0].obs is None and sorted(H.expand_cobs(cc[0].cobs, cc[0].cobs_anchors).tolist()) == sorted(want_obs.tolist())
     e = H.expand_cblocks(cc[0].cblocks, cc[0].anchors)
     d_a, _ = O.depth_from_blocks(c.blocks, length)
     d_b, _ = O.depth_from_blocks(e, length)
@@ -116,6 +117,22 @@ def test_reference_baseline_bam_fixture():
     assert sorted(got) == sorted(tuple(b) for b in shape["baseline_blocks"])
     assert sum(b[2] for b in got) == 2911652393
     assert contigs[24].length == max(b[1] + b[2] for b in shape["baseline_blocks"] if b[0] == -1)
+
+
+def test_compact_observations_round_trip():
+    rng = np.random.default_rng(3)
+    idx = np.clip(np.sort(rng.integers(0, 50000, 100000)) + rng.integers(-3, 4, 100000), 0, None)
+    obs = ((idx.astype(np.uint32) << 4) | rng.integers(0, 16, len(idx)).astype(np.uint32)).astype(np.uint32)
+    co, an = H.compact_obs(obs)
+    assert len(co) % 256 == 0 and len(co) - len(obs) < 256 and (H.expand_cobs(co, an) == obs).all()
+    jumps = np.array([0, 5000, 3, 9000, 9001, 100000, 99999, (1 << 28) - 2], np.uint32)
+    obs = (jumps << 4) | np.arange(8, dtype=np.uint32)
+    co, an = H.compact_obs(obs)
+    assert (H.expand_cobs(co, an) == obs).all() and len(an) == 6
+    assert len(H.compact_obs(np.zeros(0, np.uint32))[0]) == 0
+    with pytest.raises(H.HcnvError) as e:
+        H.compact_obs(np.array([((1 << 28) - 1) << 4], np.uint32))
+    assert e.value.status == L.HCNV_E_RANGE
 
 
 def test_compact_block_stream_round_trip():

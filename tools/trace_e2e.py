@@ -9,8 +9,8 @@ contigs = synth.make_genome(coverage=30, seed=0xC0FFEE + 1, device="cuda", conti
 def pin(t):
     if t.shape[0] == 0: return None
     h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True); h.copy_(t); return h.numpy()
-api = synth.to_api_contigs(contigs, compact=True)
-hc = [H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs), pin(a.cblocks), pin(a.anchors)) for c, a in zip(contigs, api)]
+api = synth.to_api_contigs(contigs, compact=True, compact_observations=True)
+hc = [H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), None, pin(a.cblocks), pin(a.anchors), pin(a.cobs), pin(a.cobs_anchors)) for c, a in zip(contigs, api)]
 del api
 lens = [c.length for c in contigs]; nm = [c.name for c in contigs]
 del contigs; torch.cuda.empty_cache()
