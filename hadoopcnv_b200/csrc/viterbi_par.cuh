@@ -22,7 +22,9 @@
 #pragma once
 #include <cuda_pipeline.h>
 
+#ifndef VSEG_DEFAULT
 #define VSEG_DEFAULT 64
+#endif
 #ifndef V_EMIN
 #define V_EMIN 4                   // binades below 2^4: u so small that per-segment sums get close to int32 -> replay (P3 verifies every segment anyway)
 #endif
