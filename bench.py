@@ -445,7 +445,7 @@ def run_b200(args):
                                          "algorithmic_bytes_per_bin": 36},
                                  "fp32_issue": {"achieved": 204 * n_bins / (seg_ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12, "unit": "Tops/s (no FMA)",
                                                 "frac": 204 * n_bins / (seg_ms * 1e-3) / fp32_peak, "ops_per_bin": 204},
-                                 "throughput_case": "tools/bench_cohort.py (configs[4]: thousands of chains per call; profiles/r01_v12_cohort_*.json)"}
+                                 "throughput_case": "tools/bench_cohort.py (configs[4]: thousands of chains per call; profiles/r01_v13_cohort_*.json)"}
 
     if rank == 0:
         line = {

@@ -289,16 +289,19 @@ __global__ void k_mean_copy(SegDev* probs, int n_probs) {
 __global__ void __launch_bounds__(256) k_scale_depth(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
     const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
     SegDev& P = probs[pi];
-    const long long i0 = (long long)((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
-    const long long M = P.M;
+    const int M = (int)P.M;                              // (markers per chromosome fit an int: checked on entry)
+    const int i0 = ((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
     const float mean = P.mean;
     const float* __restrict__ med = P.median;
     float* __restrict__ out = P.scaled;
+    float v[SEG_BLK / 256];
+    #pragma unroll
+    for (int k = 0; k < SEG_BLK / 256; ++k) { const int i = i0 + k * 256; v[k] = i < M ? __ldg(&med[i]) : 0.f; }     // all loads in flight
     #pragma unroll
     for (int k = 0; k < SEG_BLK / 256; ++k) {
-        const long long i = i0 + k * 256;
+        const int i = i0 + k * 256;
         if (i < M) {
-            float s = __fdiv_rn(__fsub_rn(__ldg(&med[i]), mean), mean);
+            float s = __fdiv_rn(__fsub_rn(v[k], mean), mean);
             if (s < -2.0f) s = -2.0f;
             if (s > 2.0f) s = 2.0f;
             out[i] = s;
@@ -602,23 +605,23 @@ __global__ void __launch_bounds__(32) k_viterbi_many(SegDev* probs, const int* _
 __global__ void __launch_bounds__(256) k_traceback(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
     const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
     SegDev& P = probs[pi];
-    const long long i0 = (long long)((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
-    const long long M = P.M;
+    const int M = (int)P.M;                              // (markers per chromosome fit an int: checked on entry)
+    const int i0 = ((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
     if (P.par && !P.irregular && !P.skip) return;    // k_vit_p3 already wrote the calls
     const int skip = P.skip, s = P.sstar, many = P.many;
     const uint32_t* __restrict__ codes = P.codes;
     int32_t* __restrict__ o_state = P.state; int32_t* __restrict__ o_cn = P.cn;
-    const long long stride = (M + VM_PACK - 1) / VM_PACK;
+    const uint32_t* __restrict__ mine = codes + (size_t)s * (size_t)((M + VM_PACK - 1) / VM_PACK);      // column s* of k_viterbi_many's code words
     #pragma unroll
     for (int k = 0; k < SEG_BLK / 256; ++k) {
-        const long long i = i0 + k * 256;
+        const int i = i0 + k * 256;
         if (i >= M) break;
         int st = 0;
         if (!skip) {
             if (i == M - 1) st = c_cn[s];                                         // (sic) Hmm.java:234
-            else if (many) {                                                      // per-state code words of k_viterbi_many
-                const long long m = i + 1;
-                st = (int)((__ldg(&codes[s * stride + m / VM_PACK]) >> (3 * (int)(m % VM_PACK))) & 7u);
+            else if (many) {
+                const unsigned m = (unsigned)i + 1u;
+                st = (int)((__ldg(&mine[m / VM_PACK]) >> (3u * (m % VM_PACK))) & 7u);
             }
             else st = (int)((__ldg(&codes[i + 1]) >> (3 * s)) & 7u);              // traceback[m+1][s*], Hmm.java:236
         }
