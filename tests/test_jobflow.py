@@ -46,6 +46,36 @@ def test_stage_dirs_follow_the_reference():
     assert d == {"depth": "workdir/depth/child_hg19_SVs_v2.sort", "bins": "workdir/bins/child_hg19_SVs_v2.sort", "cnv": "workdir/cnv/child_hg19_SVs_v2.sort"}
 
 
+def test_host_stages_run_without_a_gpu(tmp_path):
+    """INIT_VCF_LOOKUP and RUN_DEPTH_CALLER are host work (VCF table, BAM packer): vcf.txt equals parseVcf2Text's lines and
+    the packed records survive the trip through packed.npz, compact streams included."""
+    import hadoopcnv_b200 as H
+    from oracle import oracle as O
+    reads, vcf_lines, bam, vcf = _sample(tmp_path)
+    wd = str(tmp_path / "workdir")
+    rep = jobflow.run(_config(tmp_path, bam, vcf, RUN_BINNER="false", RUN_CNV_CALLER="false"), workdir=wd)
+    assert set(rep["stages"]) == {"INIT_VCF_LOOKUP", "RUN_DEPTH_CALLER"}
+    assert sorted(open(os.path.join(rep["dirs"]["depth"], "vcf.txt")).read().splitlines()) == sorted(set(Lit.parse_vcf_to_text(vcf_lines)))
+    names, contigs, maxlens = jobflow._load_packed(rep["stages"]["RUN_DEPTH_CALLER"]["file"])
+    assert names == ["chr7", "chr15", "chrX"] and [c.length for c in contigs] == [26000, 9000, 700]
+    c = contigs[0]
+    assert c.blocks is None and c.obs is None and c.cblocks.ctypes.data % 16 == 0
+    # the compact streams expand to what the text-level depth caller counts: per-position depth and per-site allele tallies
+    blocks = H.expand_cblocks(c.cblocks, c.anchors)
+    obs = H.expand_cobs(c.cobs, c.cobs_anchors)
+    depth, tally = O.depth_from_blocks(blocks, c.length, obs, len(c.snp_pos1))
+    for b in c.long_blocks:
+        depth[b["start0"] + 1: b["start0"] + 1 + b["len"]] += 1
+    want = {}
+    for ln in Lit.depth_caller([r for r in reads if r[0] == "7"]):
+        _, pos, _allele, cnt = ln.split("\t")
+        want[int(pos)] = want.get(int(pos), 0) + int(float(cnt))
+    assert {p: int(d) for p, d in enumerate(depth) if d} == want
+    with pytest.raises(FileNotFoundError):
+        jobflow.run(_config(tmp_path, bam, vcf, RUN_DEPTH_CALLER="false", INIT_VCF_LOOKUP="false", RUN_BINNER="false"), workdir=str(tmp_path / "empty"),
+                    ctx=object())
+
+
 @pytest.mark.gpu
 def test_job_flow_matches_the_text_level_restatement(tmp_path):
     reads, vcf_lines, bam, vcf = _sample(tmp_path)
