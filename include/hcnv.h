@@ -200,7 +200,8 @@ int32_t hcnv_pack_n_contigs(const hcnv_pack* p);
 int64_t hcnv_pack_n_records(const hcnv_pack* p);
 /* fills `in` with pointers into the pack (valid until hcnv_pack_free); max_block_len for hcnv_bin_params */
 int     hcnv_pack_contig(const hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
-/* the same with the block stream in the compact form (built on the first request): in->cblocks / anchors / n_cblocks */
+/* the same with both streams in their 2-byte forms (built on the first request): in->cblocks / anchors / n_cblocks and
+ * in->cobs / cobs_anchors / n_cobs; in->blocks and in->obs are null */
 int     hcnv_pack_contig_compact(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
 void    hcnv_pack_free(hcnv_pack* p);
 
