@@ -104,83 +104,125 @@ def contig_weights(scale):
     return [c["name"] for c in shape["contigs"]], w
 
 
-def oracle_contig(blocks_np, long_np, length, snp_pos, snp_zyg, obs, W):
-    """The CPU restatement over one contig: depth caller + binner + text round trip + HMM.  Returns #bins."""
-    from oracle import oracle as O
-    ob = np.empty(len(blocks_np), O.BLOCK_DTYPE)
-    ob["start0"] = blocks_np[:, 0]; ob["len_mapq"] = blocks_np[:, 1].view(np.uint32)
-    n_snp = len(snp_pos)
-    depth, tally = O.depth_from_blocks(ob, length, obs.view(np.uint32) if n_snp else None, n_snp)
-    for s, l, _mq, _ in long_np:
-        depth[s + 1: s + 1 + l] += 1
-    b = O.bin_reduce(depth, length, W, snp_pos if n_snp else None, snp_zyg if n_snp else None, tally)
-    nz = np.flatnonzero(b["mse"].any(axis=1))
-    m32 = np.zeros(b["mse"].shape, np.float32)
-    if len(nz):
-        m32[nz] = O.f64_text_f32(b["mse"][nz])
-    t32 = b["total"].astype(np.float32)             # integer-valued doubles print exactly: the cast is the round trip
-    r = O.hmm(b["median"], m32, t32, b["n"], LAMBDA1, LAMBDA2, fast=True)
-    return len(b["bin"]), r
+def workload_config(args, world):
+    """The `config` object of the JSON line: the named workload and its parameters, identical on both arms."""
+    return {"workload": "hg19_30x_wgs" if (args.scale == 1.0 and args.coverage == 30.0 and args.bin_width == 100) else
+            "hg19_%gx_wgs_bin%d%s" % (args.coverage, args.bin_width, "" if args.scale == 1.0 else "_scaled_%g" % args.scale),
+            "coverage": args.coverage, "bin_width": args.bin_width, "read_len": READ_LEN, "lambda1": LAMBDA1, "lambda2": LAMBDA2,
+            "genome": "hg19 shape: 24 contigs, 3 095 677 412 bp, non-N intervals of example/hg19.extra.bam",
+            "parallelism": "one genome region-sharded over %d GPU(s)" % world,
+            "l2": "inputs (GBs per GPU) far larger than the 126 MB L2; no flush needed"}
 
 
-_WORKER_CACHE = {}
+# the CPU arm's fixed, bounded sample of the workload: the same four whole chromosomes on every box and at every N
+REF_SAMPLE = ("chr20", "chr21", "chr22", "chrY")
+REF_REGION_BP = 4_000_000
+
+_REF = {}          # contig name -> numpy arrays (filled before the pool forks: the workers inherit the pages)
 
 
-def _ref_worker(task):
-    """Reference arm worker (one process per contig): generate the contig once, then time the oracle on it."""
-    name, coverage, scale, W, seed_base, ci = task
+def _ref_generate(args, names):
     import torch
-    torch.set_num_threads(1)
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     from hadoopcnv_b200 import synth
-    if name not in _WORKER_CACHE:
-        c = synth.make_genome(coverage=coverage, seed=seed_base, device="cpu", contigs=[name], scale=scale)[0]
-        _WORKER_CACHE[name] = (c.blocks.numpy(), c.long_blocks.numpy(), c.length, c.snp_pos1.numpy(), c.snp_zyg.numpy(), c.obs.numpy(), c.n_reads)
-    blocks, longs, length, sp, sz, obs, n_reads = _WORKER_CACHE[name]
+    for nm in names:
+        c = synth.make_genome(coverage=args.coverage, seed=SEED, device="cpu", contigs=[nm], scale=args.scale)[0]
+        _REF[nm] = dict(blocks=c.blocks.numpy(), longs=c.long_blocks.numpy(), length=c.length, sp=c.snp_pos1.numpy(),
+                        sz=c.snp_zyg.numpy(), obs=c.obs.numpy(), n_reads=c.n_reads,
+                        maxlen=int((c.blocks[:, 1] & 0xFFFFFF).max()) if c.blocks.shape[0] else 0)
+
+
+def _ref_region_task(task):
+    """Depth caller + binner of the CPU restatement over one region of one contig."""
+    nm, r0, r1, W, fast = task
+    from oracle import regions as R
+    d = _REF[nm]
     t0 = time.perf_counter()
-    nb, _ = oracle_contig(blocks, longs, length, sp, sz, obs, W)
-    return name, n_reads, nb, time.perf_counter() - t0
+    b = R.region_bins(d["blocks"], d["longs"], d["sp"], d["sz"], d["obs"], r0, r1, W, fast, d["maxlen"])
+    nz = np.flatnonzero(b["mse"].any(axis=1))
+    return nm, r0, dict(median=b["median"], total=b["total"], n=b["n"], nz=nz, mse_nz=b["mse"][nz], n_bins=len(b["bin"])), time.perf_counter() - t0
+
+
+def _ref_hmm_task(task):
+    """Text round trip + Hmm of the CPU restatement for one chromosome (CnvReducer gets one chromosome per call)."""
+    nm, parts = task
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    M = sum(p["n_bins"] for p in parts)
+    median = np.concatenate([p["median"] for p in parts]); total = np.concatenate([p["total"] for p in parts])
+    n = np.concatenate([p["n"] for p in parts])
+    m32 = np.zeros((M, 6), np.float32)
+    off = 0
+    for p in parts:
+        if len(p["nz"]):
+            m32[off + p["nz"]] = O.f64_text_f32(p["mse_nz"])
+        off += p["n_bins"]
+    r = O.hmm(median, m32, total.astype(np.float32), n, LAMBDA1, LAMBDA2, fast=True)   # integer-valued doubles print exactly
+    return nm, M, float(r["final_loss"]), time.perf_counter() - t0
+
+
+def cpu_sample_step(pool, names, W, fast):
+    """One pass of the CPU restatement over the sample: region tasks on every worker, then one Hmm per chromosome."""
+    from oracle import regions as R
+    tasks = [(nm, a, b, W, fast) for nm in names for a, b in R.cut_regions(_REF[nm]["length"], W, REF_REGION_BP)]
+    t0 = time.perf_counter()
+    parts = {nm: [] for nm in names}
+    busy = 0.0
+    for nm, r0, part, dt in pool.imap_unordered(_ref_region_task, tasks, chunksize=1):
+        parts[nm].append((r0, part)); busy += dt
+    res = pool.map(_ref_hmm_task, [(nm, [p for _, p in sorted(parts[nm], key=lambda x: x[0])]) for nm in names], chunksize=1)
+    wall = time.perf_counter() - t0
+    busy += sum(r[3] for r in res)
+    return wall, busy, sum(r[1] for r in res), {r[0]: r[2] for r in res}
 
 
 # --------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """The reference's CPU implementation of the path.  The reference is Java on Hadoop and cannot run on this image (no JVM,
+    SURVEY.md 8c), so this times its literal C restatement (oracle/hcnv_oracle.c: per-base depth loop, per-bin reducer,
+    sequential float Viterbi) with every host core, on a FIXED bounded sample of the workload: chr20 + chr21 + chr22 + chrY of
+    the same synthetic genome (5 % of its reads), cut into 4 Mbp region tasks.  Same sample on every box and at every N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     from oracle import oracle as O
     O.build()
-    names, w = contig_weights(args.scale)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    names = list(REF_SAMPLE)
+    t_gen = time.perf_counter()
+    _ref_generate(args, names)
+    t_gen = time.perf_counter() - t_gen
+    reads = sum(_REF[nm]["n_reads"] for nm in names)
     cores = os.cpu_count() or 1
-    k = min(cores, len(names))
-    order = sorted(range(len(names)), key=lambda i: w[i])[:k]          # the k smallest contigs: a bounded sample
-    tasks = [(names[i], args.coverage, args.scale, args.bin_width, SEED, i) for i in order]
     ctx = mp.get_context("fork")
-    with ctx.Pool(processes=k, maxtasksperchild=None) as pool:
-        # chunksize=1 with k workers and k tasks: each worker keeps (and caches) one contig
-        times = []
-        reads = bins = 0
+    with ctx.Pool(processes=cores) as pool:
+        walls, busys, bins = [], [], 0
         for step in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            res = pool.map(_ref_worker, tasks, chunksize=1)
-            dt = time.perf_counter() - t0
-            if step == 0:
-                dt = max(r[3] for r in res)             # first step also generated the inputs: keep only the oracle time
-            reads = sum(r[1] for r in res); bins = sum(r[2] for r in res)
+            wall, busy, bins, _ = cpu_sample_step(pool, names, args.bin_width, fast=False)
             if step >= args.warmup:
-                times.append(dt)
-    ms = 1e3 * float(np.mean(times))
+                walls.append(wall); busys.append(busy)
+        wall_opt, busy_opt, _, _ = cpu_sample_step(pool, names, args.bin_width, fast=True)      # the optimised variant, once
+    ms = 1e3 * float(np.mean(walls))
     value = reads / (ms / 1e3)
-    sample = "%d smallest contigs of the 30X hg19-shaped genome (%s): %d reads, %d bins per step" % (k, ",".join(t[0] for t in tasks), reads, bins)
+    sample = ("%s of the 30X hg19-shaped genome (whole chromosomes, %d reads = %.1f %% of the genome's, %d bins per step) in %d-Mbp "
+              "region tasks on %d processes" % ("+".join(names), reads, 100.0 * reads / 571515274 if args.scale == 1.0 and args.coverage == 30.0 else float("nan"),
+                                                bins, REF_REGION_BP // 1000000, cores))
+    per_core = reads / float(np.mean(busys))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32 counts / f32+f64 statistics / f32 Viterbi", "data": "synthetic",
-        "config": {"workload": "hg19_30x_wgs", "coverage": args.coverage, "bin_width": args.bin_width, "read_len": READ_LEN,
-                   "lambda1": LAMBDA1, "lambda2": LAMBDA2, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": k, "kind": "port", "sample": sample,
-                         "note": "the reference is Java on Hadoop and cannot run here (no JVM); this is the C restatement oracle/hcnv_oracle.c, one process per contig"},
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "reads_per_s_per_busy_core": per_core,
+                         "optimised": {"value": reads / wall_opt, "unit": UNIT, "cores": cores,
+                                       "what": "the same restatement with a difference array + prefix sum instead of the reference's per-base depth loop (orc_depth_from_blocks_fast)",
+                                       "reads_per_s_per_busy_core": reads / busy_opt},
+                         "note": "the reference is Java on Hadoop and cannot run here (no JVM); this is the literal C restatement oracle/hcnv_oracle.c. "
+                                 "value = sample reads / wall time of a step (all cores); a step is a bounded sample, so the genome would take %.0f x as long" % (571515274 / reads if args.scale == 1.0 and args.coverage == 30.0 else float("nan"))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "bins_per_s": bins / (ms / 1e3),
+        "bins_per_s": bins / (ms / 1e3), "input_generation_s": t_gen,
     }))
 
 
@@ -243,7 +285,7 @@ def run_b200(args):
             status, loss = ctx.run_segment_batch(prep, scalars_only=True)
             calls = [dict(status=int(s_), final_loss=float(l_)) for s_, l_ in zip(status, loss)]
         kms.update(ctx.kernel_ms())
-        state.update(res=res, m32=m32, calls=calls, kms=kms)
+        state.update(res=res, m32=m32, t32=t32, calls=calls, kms=kms, calls_by_contig=[(i_, c_["final_loss"]) for i_, c_ in zip(live, calls)])
         return res, m32, calls
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -356,7 +398,7 @@ def run_b200(args):
         for _ in range(2):
             step_e2e()
         l0 = pipe.kernel_launches
-        n_e2e = max(2, min(args.steps, 3))
+        n_e2e = args.steps
         ms_e2e, ms_e2e_wall = timed(step_e2e, n_e2e)
         e2e_launches = (pipe.kernel_launches - l0) // n_e2e
         # the end-to-end leg returns the same calls as the resident leg (same inputs): states of every chromosome
@@ -392,11 +434,14 @@ def run_b200(args):
     bytes_bin = 12 * (n_blocks + n_long) + 4 * n_obs + 8 * n_snp + 72 * n_bins
     bytes_enc = (2 * n_stream + 4 * (n_stream // 128) + 2 * n_cobs + 4 * (n_cobs // 256) if compact else 8 * n_blocks + 4 * n_obs) + 16 * n_long + 5 * n_snp + 72 * n_bins
     bytes_vit = 36 * n_bins
-    traffic = None                      # DRAM bytes per launch of the tile kernel from the committed ncu capture of this very workload
+    # DRAM bytes per launch of the tile kernel: ncu cannot run inside a timed bench, so this is the figure of the committed
+    # `ncu --set full` capture of this very command (profiles/bin_tiles_traffic.json names the capture it was read from)
+    traffic, traffic_src = None, None
     try:
         if args.scale == 1.0 and args.coverage == 30.0 and W == 100:
             tj = json.load(open(os.path.join(ROOT, "profiles", "bin_tiles_traffic.json")))
-            traffic = tj.get("hg19_30x_wgs/%s/%d" % (args.block_format, world), {}).get("dram_bytes")
+            ent = tj.get("hg19_30x_wgs/%s/%d" % (args.block_format, world), {})
+            traffic, traffic_src = ent.get("dram_bytes"), ent.get("source")
     except Exception:
         pass
 
@@ -406,31 +451,66 @@ def run_b200(args):
             return None
         ach = nbytes / (ms * 1e-3) / 1e9
         return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": traffic if kname == "bin_tiles" else None,
+                "traffic": traffic if kname == "bin_tiles" else None, "traffic_source": traffic_src if kname == "bin_tiles" else None,
                 "encoded_bytes_per_launch": bytes_enc if kname == "bin_tiles" else None,
                 "frac_of_encoded_bytes": (bytes_enc / (ms * 1e-3) / 1e9 / hbm_peak) if kname == "bin_tiles" else None, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src}
+    # the dominant kernel of THIS rank's step and its own byte model: the binning kernels move SURVEY 8(d)'s binning bytes, every
+    # kernel of the segmentation side (text round trip, mean coverage, scale, sd, Viterbi passes, traceback) 36 B per bin
+    BIN_KERNELS = ("tile_index", "tally", "bin_tiles", "snp_mse")
     dominant = max(kavg, key=kavg.get) if kavg else None
-    roofline = roof(dominant, bytes_vit if dominant in ("viterbi", "mean_coverage", "traceback", "scale_depth", "sd") else bytes_bin) if dominant else None
+    roofline = roof(dominant, bytes_bin if dominant in BIN_KERNELS else bytes_vit) if dominant else None
+    if roofline is not None and dominant not in BIN_KERNELS:
+        roofline["note"] = "a latency-bound chain kernel of the segmentation side (one warp / one CTA per chromosome): its HBM fraction is not a quality measure, see roofline_segmentation"
     roofline_binning = roof("bin_tiles", bytes_bin)
 
-    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample of the same workload
+    # ---- CPU baseline (rank 0): the oracle on a bounded sample of the same workload, on ONE host core -- the literal
+    # restatement (per-base depth loop, like the reference) and its optimised variant (difference array) -- checked against
+    # what the GPU step produced for the same chromosomes; plus the longest chain of this rank against orc_hmm_fast
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    oracle_checks = {}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        from oracle import regions as R
+        O.build()
         sample = sorted(range(len(contigs)), key=lambda i: contigs[i].n_reads)[:2]
-        t_cpu, s_reads, s_bins = 0.0, 0, 0
+        t_cpu, t_opt, s_reads, s_bins = 0.0, 0.0, 0, 0
         for i in sample:
             c = contigs[i]
-            arrs = (c.blocks.cpu().numpy(), c.long_blocks.cpu().numpy(), c.length, c.snp_pos1.cpu().numpy(), c.snp_zyg.cpu().numpy(), c.obs.cpu().numpy())
-            t0 = time.perf_counter()
-            nb, r = oracle_contig(*arrs, W)
-            t_cpu += time.perf_counter() - t0
-            s_reads += c.n_reads; s_bins += nb
-            # the timed GPU step and the oracle agree on this sample (cheap sanity; the parity tests are the real check)
+            arrs = (c.blocks.cpu().numpy(), c.long_blocks.cpu().numpy(), c.snp_pos1.cpu().numpy(), c.snp_zyg.cpu().numpy(), c.obs.cpu().numpy())
             a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
-            assert b - a == nb and (seg_state[a:b].cpu().numpy() == r["state"]).all(), "GPU/oracle mismatch on the cpu_baseline sample"
+            for fast in (False, True):
+                t0 = time.perf_counter()
+                bb = R.region_bins(*arrs, 0, c.length + 1, W, fast)
+                nz = np.flatnonzero(bb["mse"].any(axis=1))
+                m32o = np.zeros(bb["mse"].shape, np.float32)
+                if len(nz):
+                    m32o[nz] = O.f64_text_f32(bb["mse"][nz])
+                r = O.hmm(bb["median"], m32o, bb["total"].astype(np.float32), bb["n"], LAMBDA1, LAMBDA2, fast=True)
+                dt = time.perf_counter() - t0
+                if fast:
+                    t_opt += dt
+                else:
+                    t_cpu += dt
+                # the timed GPU step and the oracle agree on this sample: every bins column and every call, bit for bit
+                assert b - a == len(bb["bin"]), "GPU/oracle bin count mismatch on %s" % c.name
+                for k_ in ("bin", "start", "end", "n", "median", "total", "mse"):
+                    assert (getattr(res, k_)[a:b].cpu().numpy().view(np.uint8) == bb[k_].view(np.uint8)).all(), "GPU/oracle %s mismatch on %s" % (k_, c.name)
+                assert (seg_state[a:b].cpu().numpy() == r["state"]).all(), "GPU/oracle state mismatch on %s" % c.name
+            s_reads += c.n_reads; s_bins += b - a
+        oracle_checks["sample_bins_and_calls_bit_exact"] = "+".join(contigs[i].name for i in sample)
+        # the longest chromosome of this rank (chr1 at N = 1: 2.4 M markers, loss up to 2^16) against the sequential oracle
+        i = max(range(len(contigs)), key=lambda j: int(res.contig_offset[j + 1] - res.contig_offset[j]))
+        a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
+        r = O.hmm(res.median[a:b].cpu().numpy(), state["m32"][a:b].cpu().numpy(), state["t32"][a:b].cpu().numpy(), res.n[a:b].cpu().numpy(), LAMBDA1, LAMBDA2, fast=True)
+        assert (seg_state[a:b].cpu().numpy() == r["state"]).all() and (seg_scaled[a:b].cpu().numpy().view(np.uint32) == r["scaled"].view(np.uint32)).all(), "GPU/oracle mismatch on %s" % contigs[i].name
+        fl = [c_ for c_ in state["calls_by_contig"] if c_[0] == i][0][1]
+        assert np.float32(fl).view(np.uint32) == np.float32(r["final_loss"]).view(np.uint32), "GPU/oracle final loss mismatch on %s" % contigs[i].name
+        oracle_checks["longest_chain_bit_exact"] = "%s: %d markers, final loss %r" % (contigs[i].name, b - a, float(r["final_loss"]))
         cpu_baseline = {"value": s_reads / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                         "sample": "%s of the same genome: %d reads, %d bins, %.1f s on one host core" % ("+".join(contigs[i].name for i in sample), s_reads, s_bins, t_cpu),
-                        "bins_per_s": s_bins / t_cpu}
+                        "bins_per_s": s_bins / t_cpu,
+                        "optimised": {"value": s_reads / t_opt, "unit": UNIT, "cores": 1,
+                                      "what": "difference array + prefix sum instead of the reference's per-base depth loop; %.1f s" % t_opt}}
 
     # segmentation side (B2): every kernel of hcnv_bins_to_hmm_input + hcnv_segment_batch.  With 24 chains per genome it is
     # bound by the latency of the chr1 chain, not by a throughput roofline; both throughput fractions are
@@ -452,25 +532,26 @@ def run_b200(args):
             "metric": METRIC, "value": g_reads / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 counts / f32+f64 statistics / f32 Viterbi", "data": "synthetic",
-            "config": {"workload": "hg19_30x_wgs" if args.scale == 1.0 else "hg19_30x_wgs_scaled_%g" % args.scale, "coverage": args.coverage,
-                       "bin_width": W, "read_len": READ_LEN, "reads": g_reads, "alignment_blocks": g_blocks, "bins": g_bins, "snp_sites": g_snp,
-                       "snp_observations": g_obs, "block_format": args.block_format, "lambda1": LAMBDA1, "lambda2": LAMBDA2, "parallelism": "chromosome-sharded x%d (LPT)" % world,
-                       "l2": "inputs (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (bytes_enc / 1e9)},
+            "config": workload_config(args, world),
+            "workload_counts": {"reads": g_reads, "alignment_blocks": g_blocks, "bins": g_bins, "snp_sites": g_snp, "snp_observations": g_obs,
+                                "block_format": args.block_format, "encoded_input_bytes_rank0": bytes_enc},
             "genome_wall_time_s": ms_dev / 1e3, "wall_ms_per_step": ms_wall,
             "bins_per_s_segmented": g_bins / (seg_ms / 1e3) if seg_ms else None,
             "reads_per_s_binned": g_reads / (sum(kavg.get(k_, 0) for k_ in ("tile_index", "tally", "bin_tiles")) / 1e3) if kavg.get("bin_tiles") else None,
             "kernel_ms": kavg, "gpu_launches": g_launches, "clocks": clock_info,
             "roofline": roofline, "roofline_binning": roofline_binning, "roofline_segmentation": roofline_segmentation, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "checks": {"final_loss_sum": float(np.sum([v.get("final_loss", 0.0) for v in summary.values()])), "chromosomes": len(summary), "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
+            "checks": {"oracle": oracle_checks, "final_loss_sum": float(np.sum([v.get("final_loss", 0.0) for v in summary.values()])), "chromosomes": len(summary), "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
         }
         print(json.dumps(line))
     sys.stdout.flush()
     barrier()
     if dist is not None:
         dist.destroy_process_group()
-    # torch still holds tensors that were used on the context's stream; leave without running their destructors
-    # against a destroyed stream
-    os._exit(0)
+    # orderly teardown: nothing of torch's may still be queued on the context's stream when the context goes
+    ctx.synchronize()
+    del stream
+    torch.cuda.synchronize()
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -433,11 +433,12 @@ def config_load(path: str) -> dict:
 
 
 def write_bins_text(path: str, chrom: str, bins: BinsResult, append: bool = False):
-    st = L.lib().hcnv_write_bins_text(path.encode(), int(append), chrom.encode(), len(bins.bin),
-                                      _ptr(np.ascontiguousarray(bins.bin)), _ptr(np.ascontiguousarray(bins.start)),
-                                      _ptr(np.ascontiguousarray(bins.end)), _ptr(np.ascontiguousarray(bins.median)),
-                                      _ptr(np.ascontiguousarray(bins.mse)), _ptr(np.ascontiguousarray(bins.total)),
-                                      _ptr(np.ascontiguousarray(bins.n)))
+    # coerced copies are kept in locals until the call returns (a temporary's buffer would be freed before it)
+    args = [np.ascontiguousarray(bins.bin, dtype=np.int32), np.ascontiguousarray(bins.start, dtype=np.int32),
+            np.ascontiguousarray(bins.end, dtype=np.int32), np.ascontiguousarray(bins.median, dtype=np.float32),
+            np.ascontiguousarray(bins.mse, dtype=np.float64), np.ascontiguousarray(bins.total, dtype=np.float64),
+            np.ascontiguousarray(bins.n, dtype=np.int32)]
+    st = L.lib().hcnv_write_bins_text(path.encode(), int(append), chrom.encode(), len(args[0]), *[_ptr(a) for a in args])
     if st != 0:
         raise L.HcnvError(st, "hcnv_write_bins_text")
 

@@ -312,8 +312,7 @@ __global__ void k_snp_mse(BinK p) {
 // host side
 // ---------------------------------------------------------------------------------------------------
 namespace {
-enum { B_CONTIGS = 0, B_TILEIDX, B_TALLY, B_STATUS, B_MISC, B_IN_BLOCKS, B_IN_LONG, B_IN_SNPPOS, B_IN_SNPZYG, B_IN_OBS,
-       B_OUT_I32, B_OUT_F32, B_OUT_F64, B_SNPDEPTH = 24, B_IN_ANCHORS = 25 };
+// (scratch slot ids: hcnv_internal.h)
 
 template <class T>
 int stage_in(hcnv_ctx* ctx, int kind, const T* src, long long n, T* dst) {

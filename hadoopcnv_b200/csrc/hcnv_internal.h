@@ -40,7 +40,18 @@ struct PinBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum { HCNV_NBUF = 32 };
+// Every named scratch slot of hcnv_ctx::buf, in ONE place (two translation units used to number their own and collided).
+enum {
+    // binning (bin_kernels.cu)
+    B_CONTIGS = 0, B_TILEIDX, B_TALLY, B_STATUS, B_MISC, B_IN_BLOCKS, B_IN_LONG, B_IN_SNPPOS, B_IN_SNPZYG, B_IN_OBS,
+    B_OUT_I32, B_OUT_F32, B_OUT_F64, B_SNPDEPTH, B_IN_ANCHORS,
+    // segmentation (hmm_kernels.cu)
+    H_PROBS, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR, H_RT_WORK, H_ORDER, H_DOWNLOAD,
+    // genome pipeline (genome.cu)
+    G_BINS_I32, G_BINS_F32, G_BINS_F64, G_M32, G_SEG_F32, G_SEG_I32, G_STAGE_A, G_STAGE_B,
+    HCNV_NBUF
+};
+static_assert(HCNV_NBUF <= 48, "scratch slots");
 
 struct hcnv_ctx {
     int          device = 0;

@@ -665,9 +665,7 @@ __global__ void k_pack_results(long long n, const int32_t* __restrict__ state, c
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
-namespace {
-enum { H_PROBS = 13, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR, H_RT_WORK, H_ORDER, H_DOWNLOAD = 26 };
-}
+// (scratch slot ids: hcnv_internal.h)
 
 int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
                                 float* mse_f32, float* total_f32)

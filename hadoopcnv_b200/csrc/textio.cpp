@@ -44,6 +44,19 @@ void shortest_digits(T v, char* digits, int* nd_out, int* e10_out) {
             snprintf(dg, sizeof dg, "%0*llu", nd, m);
             snprintf(cand, sizeof cand, "%c.%se%d", dg[0], dg[1] ? dg + 1 : "0", e);
             if (parse_as<T>(cand) == v) {
+                if (p == 1) {
+                    // Double.toString (JDK >= 19 wording): when the shortest decimal that rounds to v has ONE digit, the
+                    // answer is the closest decimal of length TWO (4.9E-324 for Double.MIN_VALUE, 1.4E-45 for Float.MIN_VALUE;
+                    // it differs from d.0 only for subnormals).  The nearest two-digit decimal lies between v and the
+                    // one-digit one, so it rounds to v as well.
+                    snprintf(tmp, sizeof tmp, "%.1e", (double)v);
+                    dg[0] = tmp[0]; dg[1] = tmp[2]; dg[2] = 0;
+                    e = atoi(strchr(tmp, 'e') + 1);
+                    int k2 = dg[1] == '0' ? 1 : 2;
+                    memcpy(digits, dg, (size_t)k2); digits[k2] = 0;
+                    *nd_out = k2; *e10_out = e;
+                    return;
+                }
                 int k = nd;
                 while (k > 1 && dg[k - 1] == '0') --k;
                 memcpy(digits, dg, (size_t)k); digits[k] = 0;

@@ -66,7 +66,9 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
         names, contigs, maxlens = [], [], []
         for i in range(lib.hcnv_pack_n_contigs(h)):
             name, ci, ml = C.c_char_p(), L.ContigInput(), C.c_int32()
-            (lib.hcnv_pack_contig_compact if compact else lib.hcnv_pack_contig)(h, i, C.byref(name), C.byref(ci), C.byref(ml))
+            rc = (lib.hcnv_pack_contig_compact if compact else lib.hcnv_pack_contig)(h, i, C.byref(name), C.byref(ci), C.byref(ml))
+            if rc != 0:
+                raise L.HcnvError(rc, "hcnv_pack_contig%s(%s, contig %d): %s" % ("_compact" if compact else "", bam_path, i, lib.hcnv_strerror(rc).decode()))
 
             def arr(ptr, n, dtype):
                 if not n:

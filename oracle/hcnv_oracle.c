@@ -48,6 +48,40 @@ int orc_depth_from_blocks(const orc_block* blocks, int64_t n_blocks, double mapq
     return 0;
 }
 
+/* The same function of the inputs computed with a difference array and one prefix sum instead of the
+ * reference's per-base loop: the "optimised CPU" baseline of bench.py.
+ * Must stay result-identical to orc_depth_from_blocks (tests check). */
+int orc_depth_from_blocks_fast(const orc_block* blocks, int64_t n_blocks, double mapq_threshold,
+                               int32_t extent, int32_t* depth,
+                               const uint32_t* obs, int64_t n_obs, int64_t n_snp, uint32_t* tally)
+{
+    int pass[256];
+    for (int q = 0; q < 256; ++q) pass[q] = (1. - pow(10, -q * .1)) >= mapq_threshold;
+    int32_t* diff = (int32_t*)calloc((size_t)extent + 2, sizeof(int32_t));
+    if (!diff) return -4;
+    for (int64_t i = 0; i < n_blocks; ++i) {
+        if (!pass[blocks[i].len_mapq >> 24]) continue;
+        int64_t len = blocks[i].len_mapq & 0xFFFFFFu;
+        if (len == 0) continue;
+        int64_t s1 = (int64_t)blocks[i].start0 + 1, e1 = s1 + len;      /* covers s1 .. e1 - 1 */
+        if (s1 < 1 || e1 - 1 > extent) { free(diff); return -1; }
+        diff[s1] += 1; diff[e1] -= 1;
+    }
+    int32_t run = 0;
+    depth[0] = 0;
+    for (int64_t p = 1; p <= extent; ++p) { run += diff[p]; depth[p] = run; }
+    free(diff);
+    if (tally) {
+        memset(tally, 0, sizeof(uint32_t) * 16 * (size_t)n_snp);
+        for (int64_t i = 0; i < n_obs; ++i) {
+            uint32_t idx = obs[i] >> 4, b = obs[i] & 15u;
+            if ((int64_t)idx >= n_snp) return -2;
+            tally[(size_t)idx * 16 + b] += 1;
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------
  * A3  BinMapper.map (Mappers.java:52-53: bin = (bp / W) * W on 1-based bp) and
  *     BinReducer.reduce (Reducers.java:55-204).  Position iteration order: ascending (the
@@ -163,6 +197,12 @@ static int java_fmt(int is_float, double v, char* buf)
         snprintf(tmp, sizeof tmp, "%.*e", p - 1, v);
         int ok;
         if (is_float) ok = strtof(tmp, NULL) == (float)v; else ok = strtod(tmp, NULL) == v;
+        if (ok && p == 1) {
+            /* one digit is enough: Double.toString then takes the closest decimal of length TWO (JDK >= 19 javadoc;
+             * "4.9E-324" for Double.MIN_VALUE, "1.4E-45" for Float.MIN_VALUE) */
+            snprintf(tmp, sizeof tmp, "%.1e", v);
+            break;
+        }
         if (ok) break;
         /* the rounding interval is asymmetric at powers of two: the nearest p-digit decimal may fall
          * outside it while its neighbour (one unit in the last place up or down) is inside */
@@ -182,6 +222,7 @@ static int java_fmt(int is_float, double v, char* buf)
             if (is_float) ok = strtof(t2, NULL) == (float)v; else ok = strtod(t2, NULL) == v;
             if (ok) { strcpy(tmp, t2); found = 1; }
         }
+        if (found && p == 1) { snprintf(tmp, sizeof tmp, "%.1e", v); break; }
         if (found) break;
     }
     /* tmp = [-]d[.ddd]e[+-]xx */
@@ -224,6 +265,11 @@ float orc_f64_text_f32(double d)
     char buf[64];
     orc_double_to_string(d, buf);
     return strtof(buf, NULL);
+}
+
+void orc_f64_text_f32_array(const double* d, int64_t n, float* out)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = (d[i] == 0.0 && !signbit(d[i])) ? 0.0f : orc_f64_text_f32(d[i]);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -343,9 +389,10 @@ int orc_hmm(int64_t M, const float* median, const float* mse6, const float* tota
  * used as the timed CPU baseline.  Must stay result-identical to orc_hmm (tests check). */
 int orc_hmm_fast(int64_t M, const float* median, const float* mse6, const float* total, const int32_t* n,
                  float lambda1, float lambda2, float alpha,
-                 float* o_scaled, int32_t* o_state, int32_t* o_cn, float* stats)
+                 float* o_scaled, int32_t* o_state, int32_t* o_cn, float* stats, float* o_loss_last6)
 {
     if (M < 1) return -10;
+    if (o_loss_last6) for (int s = 0; s < 6; ++s) o_loss_last6[s] = 0;
     hmm_prepare(M, median, total, n, &lambda1, &lambda2, o_scaled, stats);
     int skipped = hmm_search(&lambda2);
     stats[2] = lambda1; stats[3] = lambda2; stats[4] = 0;
@@ -378,6 +425,7 @@ int orc_hmm_fast(int64_t M, const float* median, const float* mse6, const float*
         if (rc) break;
         memcpy(prev, cur, sizeof prev);
     }
+    if (o_loss_last6) for (int s = 0; s < 6; ++s) o_loss_last6[s] = prev[s];
     if (rc == 0) {
         int min_index = 1; float min = FLT_MAX;
         for (int c = 0; c < 6; ++c) if (prev[c] < min) { min = prev[c]; min_index = c; }

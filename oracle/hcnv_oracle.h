@@ -58,7 +58,15 @@ int orc_hmm(int64_t M, const float* median, const float* mse6, const float* tota
 /* optimisation-free forward only (used by cpu_baseline timing): same recurrence, no big matrices */
 int orc_hmm_fast(int64_t M, const float* median, const float* mse6, const float* total, const int32_t* n,
                  float lambda1, float lambda2, float alpha,
-                 float* o_scaled, int32_t* o_state, int32_t* o_cn, float* stats);
+                 float* o_scaled, int32_t* o_state, int32_t* o_cn, float* stats,
+                 float* o_loss_last6 /* optional: last row of loss_mat */);
+
+/* orc_depth_from_blocks with a difference array + prefix sum instead of the per-base loop (same results;
+ * the "optimised CPU" baseline).  orc_f64_text_f32 over an array. */
+int orc_depth_from_blocks_fast(const orc_block* blocks, int64_t n_blocks, double mapq_threshold,
+                               int32_t extent, int32_t* depth,
+                               const uint32_t* obs, int64_t n_obs, int64_t n_snp, uint32_t* tally);
+void orc_f64_text_f32_array(const double* d, int64_t n, float* out);
 
 #ifdef __cplusplus
 }

@@ -272,9 +272,43 @@ def bin_mapper(line: str, bin_width=BIN_WIDTH):
     return (parts[0], b), "\t".join(parts[1:4])
 
 
-def bin_reducer(key, values):
+def java_hashmap_order(keys, version="java8", capacity=None):
+    """Iteration order of a java.util.HashMap<Integer, ...> that received `keys` (distinct ints) in this order --
+    BinReducer walks binMapDepth.keySet() (Reducers.java:92-100), and that order decides the order of the f64 MSE sums.
+    Buckets are visited by ascending index; Integer.hashCode() is the value; the index is
+      Java 8:  (h ^ (h >>> 16)) & (cap - 1), a bucket keeps insertion order (tail append, order-preserving resize);
+      Java 7:  h ^= (h >>> 20) ^ (h >>> 12); (h ^ (h >>> 7) ^ (h >>> 4)) & (cap - 1), newest entry first (head insertion).
+    `capacity` is the table size: the maps are members that BinReducer clear()s, which never shrinks the table, so it is the
+    power of two the fullest bin seen so far by this reducer task has grown it to (16 at first; 256 after one full 100-position
+    bin under Java 8's `++size > 0.75 * cap` rule).  Default: what this bin alone would need."""
+    keys = list(keys)
+    if capacity is None:
+        capacity = 16
+        while len(keys) > 0.75 * capacity:
+            capacity *= 2
+    def index(k):
+        h = k & 0xFFFFFFFF
+        if version == "java8":
+            h ^= h >> 16
+        elif version == "java7":
+            h ^= (h >> 20) ^ (h >> 12)
+            h = h ^ (h >> 7) ^ (h >> 4)
+        else:
+            raise ValueError(version)
+        return h & (capacity - 1)
+    buckets = {}
+    for k in keys:
+        buckets.setdefault(index(k), []).append(k)
+    out = []
+    for i in sorted(buckets):
+        out += buckets[i] if version == "java8" else buckets[i][::-1]
+    return out
+
+
+def bin_reducer(key, values, order="ascending", capacity=None):
     """BinReducer.reduce, Reducers.java:55-204 -> 'chr\\tbin\\tstart\\tend\\tmedian\\tmse0..5\\ttotal\\tn'.
-    Position iteration order is ascending (documented deviation from HashMap order)."""
+    Position iteration order: "ascending" (the oracle's and the kernels' order: a documented deviation), or "java7" /
+    "java8" = the reference's HashMap order under that JVM (java_hashmap_order; tests/test_oracle.py quantifies the effect)."""
     bin_map_in_vcf, bin_map_depth = {}, {}
     startbp, endbp = 2**31 - 1, -2**31
     for text in values:
@@ -292,7 +326,7 @@ def bin_reducer(key, values):
         bin_map_depth.setdefault(bp, []).append(depth)
     depth_set, baf_list, het_list = set(), [], []
     total_depth, n = 0.0, 0
-    for bp in sorted(bin_map_depth):
+    for bp in (sorted(bin_map_depth) if order == "ascending" else java_hashmap_order(bin_map_depth.keys(), order, capacity)):
         max_depth, pos_total_depth = f32(0), f32(0)
         for depth in bin_map_depth[bp]:
             pos_total_depth = f32(pos_total_depth + depth)

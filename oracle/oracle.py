@@ -37,6 +37,8 @@ def lib():
         L.orc_double_to_string.argtypes = [C.c_double, C.c_char_p]
         L.orc_hmm.restype = C.c_int
         L.orc_hmm_fast.restype = C.c_int
+        L.orc_depth_from_blocks_fast.restype = C.c_int
+        L.orc_f64_text_f32_array.restype = None
         _lib = L
     return _lib
 
@@ -59,12 +61,13 @@ def pack_blocks(start0, length, mapq=None):
     return b
 
 
-def depth_from_blocks(blocks, extent, obs=None, n_snp=0, mapq_threshold=0.0):
+def depth_from_blocks(blocks, extent, obs=None, n_snp=0, mapq_threshold=0.0, fast=False):
+    """fast=True: the difference-array variant (orc_depth_from_blocks_fast), same results as the per-base loop."""
     blocks = np.ascontiguousarray(blocks)
     depth = np.empty(extent + 1, np.int32)
     tally = np.zeros((n_snp, 16), np.uint32) if obs is not None else None
     obs_c = np.ascontiguousarray(obs, dtype=np.uint32) if obs is not None else None
-    rc = lib().orc_depth_from_blocks(_p(blocks), C.c_int64(len(blocks)), C.c_double(mapq_threshold),
+    rc = (lib().orc_depth_from_blocks_fast if fast else lib().orc_depth_from_blocks)(_p(blocks), C.c_int64(len(blocks)), C.c_double(mapq_threshold),
                                      C.c_int32(extent), _p(depth), _p(obs_c),
                                      C.c_int64(0 if obs is None else len(obs_c)), C.c_int64(n_snp), _p(tally))
     if rc != 0:
@@ -90,19 +93,16 @@ def bin_reduce(depth, extent, bin_width, snp_pos1=None, snp_zyg=None, tally=None
                 total=o_total[:nb], n=o_n[:nb])
 
 
-def bin_contig(blocks, extent, bin_width=100, snp_pos1=None, snp_zyg=None, obs=None, mapq_threshold=0.0):
+def bin_contig(blocks, extent, bin_width=100, snp_pos1=None, snp_zyg=None, obs=None, mapq_threshold=0.0, fast=False):
     n_snp = 0 if snp_pos1 is None else len(snp_pos1)
-    depth, tally = depth_from_blocks(blocks, extent, obs if n_snp else None, n_snp, mapq_threshold)
+    depth, tally = depth_from_blocks(blocks, extent, obs if n_snp else None, n_snp, mapq_threshold, fast=fast)
     return bin_reduce(depth, extent, bin_width, snp_pos1, snp_zyg, tally)
 
 
 def f64_text_f32(a):
-    a = np.asarray(a, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=np.float64)
     out = np.empty(a.shape, np.float32)
-    L = lib()
-    flat_in, flat_out = a.ravel(), out.ravel()
-    for i in range(flat_in.size):
-        flat_out[i] = L.orc_f64_text_f32(float(flat_in[i]))
+    lib().orc_f64_text_f32_array(_p(a), C.c_int64(a.size), _p(out))
     return out
 
 
@@ -130,7 +130,7 @@ def hmm(median, mse6, total, n, lambda1, lambda2, alpha=0.5, fast=False):
     if fast:
         rc = lib().orc_hmm_fast(C.c_int64(M), _p(median), _p(mse6), _p(total), _p(n),
                                 C.c_float(lambda1), C.c_float(lambda2), C.c_float(alpha),
-                                _p(scaled), _p(state), _p(cn), _p(stats))
+                                _p(scaled), _p(state), _p(cn), _p(stats), _p(last))
     else:
         rc = lib().orc_hmm(C.c_int64(M), _p(median), _p(mse6), _p(total), _p(n),
                            C.c_float(lambda1), C.c_float(lambda2), C.c_float(alpha),

@@ -652,5 +652,63 @@ def test_full_genome_properties():
             assert int(p_["state"].min()) >= 0 and int(p_["state"].max()) <= 5
             assert bool((p_["cn"] == cn_of[p_["state"].long()]).all())                # Hmm.java:483-484
             assert float(p_["scaled"].min()) >= -2.0 and float(p_["scaled"].max()) <= 2.0
+        # ... and against the CPU oracle at FULL size, every chromosome (chr1: 2.4 M markers, loss up to 2^16): calls, scaled
+        # depth, final loss and the last row of the loss matrix, bit for bit
+        for q, p_ in zip(probs, par):
+            want = O.hmm(q["median"].cpu().numpy(), q["mse"].cpu().numpy(), q["total"].cpu().numpy(), q["n"].cpu().numpy(), 0.01, 1.6, fast=True)
+            assert want["rc"] == 0
+            np.testing.assert_array_equal(p_["state"].cpu().numpy(), want["state"])
+            np.testing.assert_array_equal(p_["scaled"].cpu().numpy().view(np.uint32), want["scaled"].view(np.uint32))
+            assert f32(p_["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+            np.testing.assert_array_equal(p_["last_row"].view(np.uint32), want["last_row"].view(np.uint32))
+            assert f32(p_["mean_coverage"]).view(np.uint32) == f32(want["mean_coverage"]).view(np.uint32)
+        # ... and the bins of two whole chromosomes against the oracle, every column
+        for nm in ("chr21", "chrY"):
+            i = names.index(nm)
+            want = oracle_bins(g[i], W)
+            assert off[i + 1] - off[i] == len(want["bin"])
+            for k in ("bin", "start", "end", "n", "median", "total", "mse"):
+                np.testing.assert_array_equal(keep[k][off[i]:off[i + 1]].cpu().numpy().view(np.uint8), want[k].view(np.uint8), err_msg="%s %s" % (nm, k))
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("l1,l2", [(0.01, 1.6), (0.3, 0.4), (-1.0, -1.0)])
+def test_chr1_length_chain_against_the_oracle(ctx, l1, l2):
+    """A chain as long as chr1 (2 492 507 markers: the running loss reaches 2^15 - 2^16, four more binade crossings than the
+    300 k-marker cases, with ulp(loss) the size of lambda1 * |mu|): the segment-parallel path AND the many-chains kernel
+    against the sequential CPU recurrence -- calls, final loss and last row bit for bit (Hmm.java:176-238)."""
+    M = 2_492_507
+    rng = np.random.default_rng(1001)
+    b = Hp.random_bins(rng, M, mean_depth=30)
+    mse32 = O.f64_text_f32(b["mse"]); tot32 = b["total"].astype(np.float32)
+    want = O.hmm(b["median"], mse32, tot32, b["n"], l1, l2, fast=True)
+    assert want["rc"] == 0 and float(want["final_loss"]) > 2.0 ** 13
+    prob = dict(median=b["median"], mse=mse32, total=tot32, n=b["n"], lambda1=l1, lambda2=l2)
+    par = ctx.segment_batch([dict(prob)], flags=L.HCNV_SEG_LATENCY)[0]
+    st = ctx.stats()
+    assert st["viterbi_segments"] == (M - 1 + 63) // 64 and st["viterbi_repairs"] == 0 and st["viterbi_segments_replayed"] < st["viterbi_segments"] // 4
+    many = ctx.segment_batch([dict(prob)], flags=L.HCNV_SEG_THROUGHPUT)[0]
+    assert ctx.stats()["viterbi_segments"] == 0
+    for got in (par, many):
+        assert got["status"] == 0
+        np.testing.assert_array_equal(got["state"], want["state"])
+        np.testing.assert_array_equal(got["cn"], want["cn"])
+        np.testing.assert_array_equal(got["scaled"].view(np.uint32), want["scaled"].view(np.uint32))
+        assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+        np.testing.assert_array_equal(got["last_row"].view(np.uint32), want["last_row"].view(np.uint32))
+        assert f32(got["mean_coverage"]).view(np.uint32) == f32(want["mean_coverage"]).view(np.uint32)
+
+
+@pytest.mark.parametrize("cov,W", [(30.0, 100), (100.0, 50)])
+def test_full_scale_chromosome_bins_against_the_oracle(ctx, cov, W):
+    """One chromosome at FULL scale (chr21: 48 Mbp, 7 M reads at 30X / 23 M at 100X) through both stream formats: every bins
+    column against the oracle, bit for bit -- BASELINE.json configs[1] and configs[3] (100X, 50-bp bins) shapes."""
+    g = synth.make_genome(coverage=cov, seed=0xC0FFEE + 1, device="cuda", contigs=["chr21"], scale=1.0)
+    want = oracle_bins(g[0], W)
+    for compact in (True, False):
+        api_c = synth.to_api_contigs(g, compact=compact, compact_observations=compact)
+        res = ctx.bin_contigs(api_c, bin_width=W, max_block_len=150)
+        assert len(res) == len(want["bin"]) > 300_000
+        for k in ("bin", "start", "end", "n", "median", "total", "mse"):
+            np.testing.assert_array_equal(getattr(res, k).cpu().numpy().view(np.uint8), want[k].view(np.uint8), err_msg=k)

@@ -112,3 +112,56 @@ def test_job_flow_matches_the_text_level_restatement(tmp_path):
     # RUN_BINNER alone, from the packed records the depth-caller stage left behind
     rep3 = jobflow.run(_config(tmp_path, bam, vcf, RUN_DEPTH_CALLER="false", INIT_VCF_LOOKUP="false", RUN_CNV_CALLER="false"), workdir=wd)
     assert sorted(open(rep3["stages"]["RUN_BINNER"]["file"]).read().splitlines()) == sorted(want_bins)
+
+
+def test_vcf_txt_alone_decides_the_snp_table(tmp_path):
+    """Stage semantics of PennCnvSeq.run (PennCnvSeq.java:171-316): the depth caller deletes the depth directory (a stale
+    vcf.txt with it), INIT_VCF_LOOKUP=false leaves no vcf.txt, and the binner's SNP table is whatever vcf.txt holds."""
+    import hadoopcnv_b200 as H
+    reads, vcf_lines, bam, vcf = _sample(tmp_path)
+    wd = str(tmp_path / "workdir")
+    d = jobflow.stage_dirs(bam, wd)
+    os.makedirs(d["depth"])
+    open(os.path.join(d["depth"], "vcf.txt"), "w").write("chr7\t5\t-1\t0\n")          # stale, from an earlier run
+    rep = jobflow.run(_config(tmp_path, bam, vcf, INIT_VCF_LOOKUP="false", RUN_BINNER="false", RUN_CNV_CALLER="false"), workdir=wd)
+    assert not os.path.exists(os.path.join(d["depth"], "vcf.txt")) and set(rep["stages"]) == {"RUN_DEPTH_CALLER"}
+    names, contigs, maxlens = jobflow._load_packed(rep["stages"]["RUN_DEPTH_CALLER"]["file"])
+    # no vcf.txt: no SNP site, no observation
+    n2, c2, _ = jobflow.apply_vcf_txt(names, contigs, maxlens, {})
+    assert all(c.snp_pos1 is None and c.cobs is None and c.obs is None for c in c2) and n2 == names
+    # a vcf.txt the reference left behind: a subset of the sites, other zygosities, one chromosome the BAM does not have
+    c = contigs[0]
+    sub = c.snp_pos1[::3]
+    zyg = np.where(np.arange(len(sub)) % 2 == 0, -1, -2).astype(np.int8)
+    p = tmp_path / "vcf.txt"
+    p.write_text("".join("chr7\t%d\t%d\t0\n" % (int(q), int(z)) for q, z in zip(sub, zyg)) + "chr7\t%d\t0\t0\nchrUn\t77\t-1\t0\n" % int(sub[0]))
+    sites = jobflow.read_vcf_txt(str(p))
+    assert (sites["chr7"][0] == sub).all() and sites["chr7"][1][0] == 0 and (sites["chr7"][1][1:] == zyg[1:]).all()      # the last line of a position wins
+    n3, c3, m3 = jobflow.apply_vcf_txt(names, contigs, maxlens, sites)
+    assert n3 == names + ["chrUn"] and c3[-1].length == 77 and c3[1].snp_pos1 is None
+    old = H.expand_cobs(c.cobs, c.cobs_anchors)
+    new = H.expand_cobs(c3[0].cobs, c3[0].cobs_anchors)
+    keep = np.isin(c.snp_pos1[old >> 4], sub)
+    assert (sub[new >> 4] == c.snp_pos1[old[keep] >> 4]).all() and ((new & 15) == (old[keep] & 15)).all()
+    # a site the depth caller has no alleles for
+    free = next(q for q in range(1, 26000) if q not in set(int(x) for x in c.snp_pos1))
+    with pytest.raises(ValueError):
+        jobflow.apply_vcf_txt(names, contigs, maxlens, {"chr7": (np.array([free], np.int32), np.array([-1], np.int8))})
+
+
+@pytest.mark.gpu
+def test_binner_without_and_with_a_foreign_vcf_txt(tmp_path):
+    reads, vcf_lines, bam, vcf = _sample(tmp_path)
+    wd = str(tmp_path / "workdir")
+    # INIT_VCF_LOOKUP=false: the reference has no vcf.txt, so the binner sees the depth lines only and every MSE column is 0
+    rep = jobflow.run(_config(tmp_path, bam, vcf, INIT_VCF_LOOKUP="false", RUN_CNV_CALLER="false"), workdir=wd)
+    depth_lines = Lit.depth_caller(reads)
+    got = open(rep["stages"]["RUN_BINNER"]["file"]).read().splitlines()
+    assert sorted(got) == sorted(Lit.binner(depth_lines))
+    assert all(ln.split("\t")[5:11] == ["0.0"] * 6 for ln in got)
+    # a vcf.txt written by somebody else (a subset of the sites, flipped zygosities, a chromosome without reads): binner alone
+    want_vcf = [ln for i, ln in enumerate(sorted(set(Lit.parse_vcf_to_text(vcf_lines)))) if i % 2 == 0]
+    want_vcf = ["\t".join([f[0], f[1], "-1" if f[2] == "-2" else f[2], f[3]]) for f in (ln.split("\t") for ln in want_vcf)] + ["chrUn\t250\t-1\t0"]
+    open(os.path.join(rep["dirs"]["depth"], "vcf.txt"), "w").write("".join(ln + "\n" for ln in want_vcf))
+    rep2 = jobflow.run(_config(tmp_path, bam, vcf, RUN_DEPTH_CALLER="false", INIT_VCF_LOOKUP="false", RUN_CNV_CALLER="false"), workdir=wd)
+    assert sorted(open(rep2["stages"]["RUN_BINNER"]["file"]).read().splitlines()) == sorted(Lit.binner(depth_lines + want_vcf))
