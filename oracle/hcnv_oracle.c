@@ -267,9 +267,23 @@ float orc_f64_text_f32(double d)
     return strtof(buf, NULL);
 }
 
+/* The round trip over an array.  Shortcut: the printed decimal lies within half an ulp(double) of d, so it parses to the same
+ * float as d itself unless d sits within a few ulp(double) of the midpoint between two adjacent floats; only those values (and
+ * the subnormal-float range) go through the text.  Must stay identical to orc_f64_text_f32 (tests check). */
 void orc_f64_text_f32_array(const double* d, int64_t n, float* out)
 {
-    for (int64_t i = 0; i < n; ++i) out[i] = (d[i] == 0.0 && !signbit(d[i])) ? 0.0f : orc_f64_text_f32(d[i]);
+    for (int64_t i = 0; i < n; ++i) {
+        const double v = d[i];
+        const float f = (float)v;
+        const double av = fabs(v);
+        if (v == 0.0 || (double)f == v) { out[i] = f; continue; }
+        if (!(av > 1e-37 && av < 3e38)) { out[i] = orc_f64_text_f32(v); continue; }
+        const float af = fabsf(f);
+        const float lo = ((double)af > av) ? nextafterf(af, 0.0f) : af, hi = nextafterf(lo, INFINITY);
+        const double mid = 0.5 * ((double)lo + (double)hi);               /* exact */
+        const double ulp = nextafter(av, INFINITY) - av;
+        out[i] = (fabs(av - mid) > 8 * ulp) ? f : orc_f64_text_f32(v);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------

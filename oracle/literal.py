@@ -43,6 +43,16 @@ def _java_notation(neg: bool, digits: str, e10: int, absval: float) -> str:
     return ("-" if neg else "") + s
 
 
+def _two_digit_rule(digits: str, e10: int, value: float):
+    """Double.toString / Float.toString (JDK >= 19 javadoc): when ONE digit is enough to round-trip, the result is the
+    closest decimal of length TWO ("4.9E-324" for Double.MIN_VALUE, "1.4E-45" for Float.MIN_VALUE); it differs from d.0 only
+    for subnormals."""
+    if len(digits.rstrip("0") or "0") > 1:
+        return digits, e10
+    m, ex = ("%.1e" % value).split("e")
+    return m.replace(".", ""), int(ex)
+
+
 def java_double_to_string(d: float) -> str:
     """Double.toString: shortest repr digits (Python's repr is shortest round-trip too)."""
     d = float(d)
@@ -65,6 +75,7 @@ def java_double_to_string(d: float) -> str:
     e10 = e + len(ip) - 1
     stripped = digits.lstrip("0")
     e10 -= len(digits) - len(stripped)
+    stripped, e10 = _two_digit_rule(stripped, e10, abs(d))
     return _java_notation(d < 0, stripped, e10, abs(d))
 
 
@@ -78,8 +89,8 @@ def java_float_to_string(x) -> str:
         return "-0.0" if np.signbit(x) else "0.0"
     s = np.format_float_scientific(abs(x), unique=True, trim="-")  # shortest digits for binary32
     m, ex = s.split("e")
-    digits = m.replace(".", "")
-    return _java_notation(bool(x < 0), digits, int(ex), float(abs(x)))
+    digits, e10 = _two_digit_rule(m.replace(".", ""), int(ex), float(abs(x)))
+    return _java_notation(bool(x < 0), digits, e10, float(abs(x)))
 
 
 def java_float_value_of(s: str):

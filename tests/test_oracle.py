@@ -219,7 +219,16 @@ def test_region_oracle_adds_up_to_the_contig_and_fast_depth_is_identical():
 
 def test_text_roundtrip_array_matches_scalar_and_fast_hmm_last_row():
     rng = np.random.default_rng(5)
-    x = np.concatenate([rng.random(2000) * 10.0 ** rng.integers(-12, 3, 2000), [0.0, -0.0, 1e-320, 4.9e-324, 1e300, np.nan]])
+    f = rng.random(300).astype(np.float32) * np.float32(10.0) ** rng.integers(-30, 10, 300).astype(np.float32)
+    mid = (f.astype(np.float64) + np.nextafter(f, np.float32(np.inf)).astype(np.float64)) / 2      # float rounding midpoints ...
+    near = [mid]
+    for k in (1, 2, 9):                                                                           # ... and their f64 neighbours
+        up, dn = mid.copy(), mid.copy()
+        for _ in range(k):
+            up, dn = np.nextafter(up, np.inf), np.nextafter(dn, -np.inf)
+        near += [up, dn]
+    x = np.concatenate([rng.random(2000) * 10.0 ** rng.integers(-12, 3, 2000), [0.0, -0.0, 1e-320, 4.9e-324, 1e300, np.nan, 1e-40, 1.2e-38, 5e38],
+                        -mid[:20]] + near)
     a = O.f64_text_f32(x)
     for v, f in zip(x, a):
         w = np.float32(O.lib().orc_f64_text_f32(float(v)))
