@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-format", default="compact", choices=["compact", "records"],
                     help="compact: 2-byte delta-coded block stream and 2-byte observations (include/hcnv.h hcnv_cblock, hcnv_cobs); records: 8-byte hcnv_block, 4-byte observations")
+    ap.add_argument("--bin-kernel", default="v2", choices=["v1", "v2"], help="v2: 64 bins per warp, packed 16-bit pairs (default); v1: the first form")
     ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
     ap.add_argument("--e2e-groups", type=int, default=8, help="tasks (groups of chromosomes) per genome in the end-to-end leg")
     return ap.parse_args()
@@ -275,7 +276,8 @@ def run_b200(args):
 
     def hot_path(api_contigs):
         """One pass of the hot path; inputs may be device tensors (resident) or pinned host arrays (e2e)."""
-        res = ctx.bin_contigs(api_contigs, bin_width=W, max_block_len=READ_LEN, tile_bins=args.tile_bins, out=out, capacity=cap)
+        res = ctx.bin_contigs(api_contigs, bin_width=W, max_block_len=READ_LEN, tile_bins=args.tile_bins, out=out, capacity=cap,
+                              flags=1 if args.bin_kernel == "v1" else 0)
         kms = ctx.kernel_ms()
         m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total)
         # one Hmm per non-empty chromosome (row ranges of the same arrays: the problem array is filled by pointer arithmetic)

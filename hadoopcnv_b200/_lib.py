@@ -41,7 +41,8 @@ class ContigInput(C.Structure):
                 ("snp_pos1", C.c_void_p), ("snp_zyg", C.c_void_p), ("n_snp", C.c_int64),
                 ("obs", C.c_void_p), ("n_obs", C.c_int64),
                 ("cblocks", C.c_void_p), ("anchors", C.c_void_p), ("n_cblocks", C.c_int64),
-                ("cobs", C.c_void_p), ("cobs_anchors", C.c_void_p), ("n_cobs", C.c_int64)]
+                ("cobs", C.c_void_p), ("cobs_anchors", C.c_void_p), ("n_cobs", C.c_int64),
+                ("region_first_bin", C.c_int32), ("region_n_bins", C.c_int32), ("snp_index_base", C.c_int64)]
 
 
 class ResultsDownload(C.Structure):
@@ -68,6 +69,17 @@ class SegmentProblem(C.Structure):
                 ("status", C.c_int32), ("want_sd", C.c_int32)]
 
 
+class SegmentPart(C.Structure):
+    """hcnv_segment_part: one part of a chromosome that is cut across ranks (a whole chromosome: n_parts = 1)."""
+    _fields_ = [("prob", SegmentProblem), ("n_markers_full", C.c_int64), ("row0", C.c_int64), ("part_index", C.c_int32), ("n_parts", C.c_int32),
+                ("first_vector", C.c_float * 6), ("product_approx", C.c_float * 36), ("start_approx", C.c_double * 6),
+                ("start_exact", C.c_float * 6), ("end_exact", C.c_float * 6), ("sstar", C.c_int32), ("prev_call", C.c_int32),
+                ("irregular", C.c_int32), ("skipped", C.c_int32)]
+
+
+HCNV_SEG_AGAIN = 2
+
+
 class Config(C.Structure):
     _fields_ = [("bam_file", C.c_char * 1024), ("vcf_file", C.c_char * 1024),
                 ("run_depth_caller", C.c_int32), ("run_global_sort", C.c_int32), ("init_vcf_lookup", C.c_int32),
@@ -84,6 +96,7 @@ EXPORTS = [
     "hcnv_write_bins_text", "hcnv_write_results_text",
     "hcnv_read_bins_text", "hcnv_bins_text_n_chromosomes", "hcnv_bins_text_get", "hcnv_bins_text_free",
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
+    "hcnv_seg_plan_create", "hcnv_seg_plan_stats", "hcnv_seg_plan_p0", "hcnv_seg_plan_p1", "hcnv_seg_plan_chain", "hcnv_seg_plan_finish", "hcnv_seg_plan_destroy",
     "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
 ]
 
@@ -140,6 +153,13 @@ def lib():
     L.hcnv_bin_contigs.argtypes = [C.c_void_p, C.POINTER(BinParams), C.c_int32, C.POINTER(ContigInput), C.POINTER(Bins)]
     L.hcnv_bins_to_hmm_input.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hcnv_segment_batch.argtypes = [C.c_void_p, C.c_float, C.c_int32, C.POINTER(SegmentProblem), C.c_int32]
+    L.hcnv_seg_plan_create.argtypes = [C.c_void_p, C.c_float, C.c_int32, C.POINTER(SegmentPart), C.c_int32, C.POINTER(C.c_void_p)]
+    for f in ("stats", "p0", "p1", "finish"):
+        getattr(L, "hcnv_seg_plan_" + f).argtypes = [C.c_void_p]
+    L.hcnv_seg_plan_chain.argtypes = [C.c_void_p, C.c_int32]
+    L.hcnv_seg_plan_destroy.argtypes = [C.c_void_p]
+    L.hcnv_seg_plan_destroy.restype = None
+    L.hcnv_pack_contig_compact.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(ContigInput), C.POINTER(C.c_int32)]
     L.hcnv_config_load.argtypes = [C.c_char_p, C.POINTER(Config)]
     L.hcnv_format_float.argtypes = [C.c_float, C.c_char_p]
     L.hcnv_format_double.argtypes = [C.c_double, C.c_char_p]

@@ -133,6 +133,9 @@ class Contig:
     anchors: object = None         # int32, one per HCNV_CGROUP compact records
     cobs: object = None            # alternative to obs: hcnv_cobs stream (uint16 / torch int16)
     cobs_anchors: object = None    # int32, one per HCNV_OGROUP compact observations
+    region_first_bin: int = 0      # a REGION of the contig (hcnv_contig_input): first bin (a multiple of 64), bin count (0: to the end) ...
+    region_n_bins: int = 0
+    snp_index_base: int = 0        # ... and the index of snp_pos1[0] in the contig's whole SNP table (observations keep whole-table indices)
 
 
 @dataclass
@@ -235,14 +238,14 @@ class Context:
     # ------------------------------------------------------------------ B1
     def bin_contigs(self, contigs: Sequence[Contig], bin_width: int = 100, max_block_len: int = 0,
                     mapping_quality_threshold: float = 0.0, tile_bins: int = 0, out: Optional[BinsResult] = None,
-                    capacity: Optional[int] = None) -> BinsResult:
+                    capacity: Optional[int] = None, flags: int = 0) -> BinsResult:
         """hcnv_bin_contigs.  With numpy inputs returns numpy outputs; with torch CUDA inputs returns torch CUDA
         outputs (allocate once and pass them back in as `out` to keep the timed region allocation-free)."""
         if not isinstance(contigs, PreparedContigs):
             contigs = self.prepare_contigs(contigs)
         n, arr, on_device = len(contigs.contigs), contigs.arr, contigs.on_device
         contigs = contigs.contigs
-        cap = capacity if capacity is not None else sum(int(c.length) // bin_width + 1 for c in contigs)
+        cap = capacity if capacity is not None else sum(min(int(c.region_n_bins), int(c.length) // bin_width + 1) if c.region_n_bins else int(c.length) // bin_width + 1 for c in contigs)
         if out is None:
             out = self.alloc_bins(cap, on_device, n)
         b = L.Bins()
@@ -254,6 +257,7 @@ class Context:
         p = L.BinParams()
         self._lib.hcnv_bin_params_default(C.byref(p))
         p.bin_width, p.max_block_len, p.mapping_quality_threshold, p.tile_bins = bin_width, max_block_len, mapping_quality_threshold, tile_bins
+        p.flags = flags                      # bit 0: force the first form of the tile kernel (32 bins per warp, 32-bit difference array)
         self._check(self._lib.hcnv_bin_contigs(self._h, C.byref(p), n, arr, C.byref(b)))
         nb = int(off[-1])
         return BinsResult(out.bin[:nb], out.start[:nb], out.end[:nb], out.median[:nb], out.mse[:nb], out.total[:nb],
@@ -274,6 +278,7 @@ class Context:
             arr[i].obs, arr[i].n_obs = _ptr(c.obs), _len(c.obs)
             arr[i].cblocks, arr[i].anchors, arr[i].n_cblocks = _ptr(c.cblocks), _ptr(c.anchors), _len(c.cblocks)
             arr[i].cobs, arr[i].cobs_anchors, arr[i].n_cobs = _ptr(c.cobs), _ptr(c.cobs_anchors), _len(c.cobs)
+            arr[i].region_first_bin, arr[i].region_n_bins, arr[i].snp_index_base = int(c.region_first_bin), int(c.region_n_bins), int(c.snp_index_base)
             for x in (c.blocks, c.cblocks, c.long_blocks, c.snp_pos1, c.obs, c.cobs):
                 if x is not None and _is_torch(x):
                     on_device = True
@@ -403,6 +408,41 @@ class Context:
                             final_loss=np.float32(a.final_loss), last_row=np.array(list(a.last_row), np.float32),
                             status=int(a.status)))
         return res
+
+
+class SegPlan:
+    """hcnv_seg_plan: the segmentation of a batch as phases (stats, p0, p1, chain rounds, finish), for chromosomes that are cut
+    across ranks (hadoopcnv_b200.sharding runs the exchanges between the phases).  `parts` is a ctypes array of
+    _lib.SegmentPart that the caller fills and reads between the phases; device buffers only."""
+
+    def __init__(self, ctx: "Context", parts, alpha: float = 0.5, flags: int = 0, keep=None):
+        self.ctx, self.parts, self._keep = ctx, parts, keep
+        h = C.c_void_p()
+        ctx._check(ctx._lib.hcnv_seg_plan_create(ctx._h, float(alpha), len(parts), parts, flags, C.byref(h)))
+        self._h = h
+
+    def _call(self, name, *args):
+        st = getattr(self.ctx._lib, "hcnv_seg_plan_" + name)(self._h, *args)
+        if st < 0 and st != L.HCNV_E_NO_MINIMUM:
+            self.ctx._check(st)
+        return st
+
+    def stats(self): return self._call("stats")
+    def p0(self): return self._call("p0")
+    def p1(self): return self._call("p1")
+    def chain(self, round_: int): return self._call("chain", int(round_))
+    def finish(self): return self._call("finish")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.hcnv_seg_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------- B3 (host only, no GPU needed)

@@ -116,4 +116,20 @@ int hcnv_segment_batch(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segm
     return hcnv_segment_batch_impl(ctx, alpha, n_problems, problems, flags);
 }
 
+int hcnv_seg_plan_create(hcnv_ctx* ctx, float alpha, int32_t n_parts, hcnv_segment_part* parts, int32_t flags, hcnv_seg_plan** out) {
+    if (!ctx) return HCNV_E_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return hcnv_fail(ctx, HCNV_E_CUDA, "cudaSetDevice failed");
+    return hcnv_seg_plan_create_impl(ctx, alpha, n_parts, parts, flags, out);
+}
+#define PLAN_CALL(name, ...)                                                                              \
+    if (!plan) return HCNV_E_INVALID;                                                                     \
+    if (cudaSetDevice(hcnv_seg_plan_ctx(plan)->device) != cudaSuccess) return HCNV_E_CUDA;                \
+    return name(__VA_ARGS__)
+int hcnv_seg_plan_stats(hcnv_seg_plan* plan) { PLAN_CALL(hcnv_seg_plan_stats_impl, plan); }
+int hcnv_seg_plan_p0(hcnv_seg_plan* plan) { PLAN_CALL(hcnv_seg_plan_p0_impl, plan); }
+int hcnv_seg_plan_p1(hcnv_seg_plan* plan) { PLAN_CALL(hcnv_seg_plan_p1_impl, plan); }
+int hcnv_seg_plan_chain(hcnv_seg_plan* plan, int32_t round) { PLAN_CALL(hcnv_seg_plan_chain_impl, plan, round); }
+int hcnv_seg_plan_finish(hcnv_seg_plan* plan) { PLAN_CALL(hcnv_seg_plan_finish_impl, plan); }
+void hcnv_seg_plan_destroy(hcnv_seg_plan* plan) { hcnv_seg_plan_destroy_impl(plan); }
+
 }  // extern "C"

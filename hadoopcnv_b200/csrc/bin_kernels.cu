@@ -37,6 +37,9 @@ struct ContigDev {
     int32_t   n_bins_max;   // length / W + 1
     int32_t   tile_base;    // global id of this contig's first tile
     int32_t   n_tiles;
+    int32_t   tile_lo;      // region (hcnv_contig_input::region_first_bin): number within the contig of its first tile; n_bins_max = the region's end bin
+    int32_t   region;       // 1: a region of the contig (observations of sites outside the table are ignored)
+    long long snp_index_base;
 };
 
 enum { ERR_RANGE = 0, ERR_UNSORTED = 1, ERR_INCONSISTENT = 2, ERR_INTERNAL = 3, ERR_CAPACITY = 4, ERR_N = 8 };
@@ -55,6 +58,7 @@ struct BinK {
     int   n_contigs;
     int   W, TB, n_tiles, maxlen;
     int   compact;                   // 1: the contigs carry compact streams
+    int   v2;                        // 1: the 64-bin packed tile kernel (bin_tile_kernel2.cuh): long blocks are pre-counted per tile
     uint32_t mapq_pass[8];
     TileRec*  tile_rec;              // per-tile index, filled by k_tile_index
     uint32_t* tally;
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(256) k_tile_index(BinK p) {
             if (p.contigs[mid].tile_base <= t) lo = mid; else hi = mid - 1;
         }
         const ContigDev& c = p.contigs[lo];
-        const int k = t - c.tile_base;
+        const int k = c.tile_lo + (t - c.tile_base);
         const long long T0 = (long long)k * TP;  // first 1-based position of the tile (position 0 never holds a read)
         // a block with 0-based start s covers 1-based positions s+1 .. s+len: it starts in the tile iff T0-1 <= s < T0+TP-1
         // (compact stream: in units of groups, by the anchors: first group whose first record starts at or after the tile)
@@ -120,7 +124,9 @@ __global__ void __launch_bounds__(256) k_tile_index(BinK p) {
     if (t >= p.n_tiles) return;
     const ContigDev& c = p.contigs[my_contig];
     const int k = my_k;
-    const bool last = (k == c.n_tiles - 1);
+    const bool last = (k - c.tile_lo == c.n_tiles - 1);
+    // the last tile of a REGION that is not the contig's end: its ranges end where the next tile's would begin
+    const bool region_end = last && (long long)(k + 1) * p.TB < (long long)(c.length / p.W + 1);
     TileRec r;
     r.contig = my_contig; r.k = k; r.pad = 0;
     const uint32_t lo = s_lo[threadIdx.x];
@@ -129,6 +135,7 @@ __global__ void __launch_bounds__(256) k_tile_index(BinK p) {
         // later records may reach the tile) up to the first group that starts at or after the tile's end
         const uint32_t ng = (uint32_t)(c.n_cblocks / HCNV_CGROUP);
         uint32_t ghi = last ? ng : s_lo[threadIdx.x + 1];
+        if (region_end) ghi = lower_bound_i32(c.anchors, (long long)ng, clampk((long long)(k + 1) * TP - 1));
         uint32_t glb = 0;
         if (lo > 0) {
             const int32_t key = clampk((long long)k * TP - 1 - p.maxlen);
@@ -146,8 +153,26 @@ __global__ void __launch_bounds__(256) k_tile_index(BinK p) {
         r.lb = glb * HCNV_CGROUP; r.hi = ghi * HCNV_CGROUP;
         r.slo = s_slo[threadIdx.x];
         r.shi = last ? (uint32_t)c.n_snp : s_slo[threadIdx.x + 1];
+        if (region_end) r.shi = lower_bound_i32(c.snp_pos, c.n_snp, clampk((long long)(k + 1) * TP));
         if (r.shi < r.slo) r.shi = r.slo;
         r.prev_start = (int)0x80000000;
+        if (p.v2) {
+            // long blocks: how many cover the whole tile (they become the depth carried into its first bin), and whether one has
+            // an edge inside it (only those tiles walk the list); the contig's first tile also range-checks them
+            const long long T0 = (long long)k * TP;
+            int base = 0, edge = 0, oob = 0;
+            for (long long i = 0; i < c.n_long; ++i) {
+                const hcnv_long_block lb_ = c.longs[i];
+                const long long s1 = (long long)lb_.start0 + 1 - T0, e1 = s1 + lb_.len;
+                if (k == 0 && (lb_.len < 0 || lb_.start0 < 0 || (long long)lb_.start0 + lb_.len > c.length)) oob = 1;
+                if (lb_.len <= 0) continue;
+                if (s1 <= 0 && e1 >= TP) ++base;
+                else if (e1 > 0 && s1 < TP) edge = 1;
+            }
+            if (oob) atomicOr(&p.err[ERR_RANGE], 1);
+            r.prev_start = base;
+            r.pad |= edge ? 2 : 0;
+        }
         hcnv_block z; z.start0 = 0; z.len_mapq = 0;
         r.head = z; r.tail = z;
         p.tile_rec[t] = r;
@@ -156,6 +181,10 @@ __global__ void __launch_bounds__(256) k_tile_index(BinK p) {
     r.hi = last ? (uint32_t)c.n_blocks : s_lo[threadIdx.x + 1];
     r.slo = s_slo[threadIdx.x];
     r.shi = last ? (uint32_t)c.n_snp : s_slo[threadIdx.x + 1];
+    if (region_end) {
+        r.hi = lower_bound_blocks(c.blocks, c.n_blocks, clampk((long long)(k + 1) * TP - 1));
+        r.shi = lower_bound_i32(c.snp_pos, c.n_snp, clampk((long long)(k + 1) * TP));
+    }
     if (r.shi < r.slo) r.shi = r.slo;                        // unsorted SNP table: k_snp_mse reports it
     // look-back: blocks that start before the tile but may reach into it, s + 1 >= T0 - maxlen
     uint32_t lb = lo;
@@ -218,8 +247,8 @@ __global__ void __launch_bounds__(256) k_tally(BinK p, long long n_obs_total) {
             if (!valid) continue;
             const unsigned same = __match_any_sync(act, o);         // lanes that saw the same (site, base)
             if (lane == __ffs((int)same) - 1) {
-                const long long idx = (long long)(o >> 4);
-                if (idx >= n_snp) atomicOr(&p.err[ERR_RANGE], 1);
+                const long long idx = (long long)(o >> 4) - c.snp_index_base;
+                if (idx < 0 || idx >= n_snp) { if (!c.region) atomicOr(&p.err[ERR_RANGE], 1); }     // (a region's stream may name its neighbours' sites)
                 else atomicAdd(&tally[(size_t)idx * 16 + (o & 15u)], (uint32_t)__popc(same));
             }
         }
@@ -227,6 +256,7 @@ __global__ void __launch_bounds__(256) k_tally(BinK p, long long n_obs_total) {
 }
 
 #include "bin_tile_kernel.cuh"
+#include "bin_tile_kernel2.cuh"
 
 // BinReducer's BAF statistics (Reducers.java:76-82,102-129,160-190), one thread per SNP site; the first site of a
 // bin walks the bin's sites in ascending position (the f64 sums are order dependent), then finds the bin's output row.
@@ -365,9 +395,12 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
 
     // tile geometry: one warp = one tile of 32 bins; a warp's shared-memory slice = tile records + two record chunks +
     // the difference array of its 32 * W positions; as many warps per SM as fit
-    const int TB = 32;
-    const size_t warp_smem = ((sizeof(WarpSmem) + 15) & ~(size_t)15) + (compact ? (size_t)0 : (size_t)NRBUF * (RCAP + 4) * 8) +
-                             (((size_t)32 * W + 4) * 4 + 15) / 16 * 16;
+    // second form (bin_tile_kernel2.cuh): 64 bins per warp in a packed 16-bit pair array of the same size; flags bit 0 forces the first
+    const bool v2 = compact && W <= PK_MAXW && !(P.flags & 1);
+    const int TB = v2 ? 64 : 32;
+    const size_t warp_smem = v2 ? ((sizeof(WarpSmem2) + 15) & ~(size_t)15) + (((size_t)32 * W + 4) * 4 + 15) / 16 * 16
+                                : ((sizeof(WarpSmem) + 15) & ~(size_t)15) + (compact ? (size_t)0 : (size_t)NRBUF * (RCAP + 4) * 8) +
+                                  (((size_t)32 * W + 4) * 4 + 15) / 16 * 16;
     int NW = (int)std::min<size_t>(BIN_MAX_WARPS, (ctx->smem_optin - 3072) / warp_smem);
     if (NW > BIN_MAX_WARPS) NW = BIN_MAX_WARPS;
     if (P.tile_bins > 0 && P.tile_bins < NW) NW = P.tile_bins;          // tuning knob: fewer warps per SM
@@ -396,7 +429,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             if (in_kind < 0) in_kind = kd; else if (in_kind != kd) return hcnv_fail(ctx, HCNV_E_INVALID, "mixed host/device input pointers");
         }
         tot_blocks += ci.n_blocks; tot_cblocks += ci.n_cblocks; tot_long += ci.n_long; tot_snp += ci.n_snp; tot_obs += ci.n_obs; tot_cobs += ci.n_cobs;
-        tot_bins_max += ci.length / W + 1;
+        tot_bins_max += ci.region_n_bins > 0 ? std::min<long long>(ci.region_n_bins, ci.length / W + 1) : ci.length / W + 1;
     }
     if (in_kind < 0) in_kind = 0;
     const int out_kind = hcnv_ptr_kind(out->bin) == 2 ? 2 : 0;
@@ -451,7 +484,15 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         d.n_blocks = ci.n_blocks; d.n_cblocks = ci.n_cblocks; d.n_long = ci.n_long; d.n_snp = ci.n_snp; d.n_obs = ci.n_cobs ? ci.n_cobs : ci.n_obs;
         d.obs_base32 = obs32_total; obs32_total += (d.n_obs + 255) / 256 * 256;
         d.snp_base = os; d.length = ci.length; d.n_bins_max = ci.length / W + 1;
-        d.tile_base = tile_base; d.n_tiles = (d.n_bins_max + TB - 1) / TB;
+        d.tile_lo = 0; d.region = 0; d.snp_index_base = 0;
+        if (ci.region_first_bin || ci.region_n_bins || ci.snp_index_base) {
+            if (ci.region_first_bin < 0 || ci.region_n_bins < 0 || ci.snp_index_base < 0 || ci.region_first_bin % 64 || ci.region_first_bin >= d.n_bins_max)
+                return hcnv_fail(ctx, HCNV_E_INVALID, "region_first_bin must be a multiple of 64 inside the contig");
+            d.region = 1; d.snp_index_base = ci.snp_index_base;
+            d.tile_lo = ci.region_first_bin / TB;
+            if (ci.region_n_bins > 0) d.n_bins_max = (int32_t)std::min<long long>(d.n_bins_max, (long long)ci.region_first_bin + ci.region_n_bins);
+        }
+        d.tile_base = tile_base; d.n_tiles = (d.n_bins_max - d.tile_lo * TB + TB - 1) / TB;
         tile_base += d.n_tiles;
         ob += ci.n_blocks; ocb += ci.n_cblocks; ol += ci.n_long; os += ci.n_snp; oo += ci.n_obs; oco += ci.n_cobs;
     }
@@ -467,7 +508,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     HCNV_CUDA(ctx, ctx->buf[B_STATUS].reserve(8 * n_status));
     HCNV_CUDA(ctx, ctx->buf[B_MISC].reserve(4096 + 8 * (size_t)(n_contigs + 1)));
     k.contigs = ctx->buf[B_CONTIGS].as<ContigDev>();
-    k.n_contigs = n_contigs; k.W = W; k.TB = TB; k.n_tiles = n_tiles; k.compact = compact;
+    k.n_contigs = n_contigs; k.W = W; k.TB = TB; k.n_tiles = n_tiles; k.compact = compact; k.v2 = v2 ? 1 : 0;
     k.maxlen = compact ? std::min(maxlen, 255) : maxlen;      // pieces of the compact stream are at most 255 long
     for (int q = 0; q < 256; ++q) {
         double mapprob = 1. - std::pow(10.0, -q * .1);            // Mappers.java:193
@@ -531,6 +572,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     };
     auto launch_vec = [&](auto vec_tag) -> cudaError_t {
         constexpr int V = decltype(vec_tag)::value;
+        if (v2) return launch(k_bin_tiles2<V>);
         if (compact) return launch(k_bin_tiles<V, false, true>);      // (the compact stream carries no MAPQ: checked above)
         return filter ? launch(k_bin_tiles<V, true, false>) : launch(k_bin_tiles<V, false, false>);
     };

@@ -74,7 +74,7 @@ struct ContigLite {                               // what a tile needs from its 
     const hcnv_long_block* longs;
     const int32_t*         snp_pos;
     long long n_long, snp_base;
-    int length, n_bins_max;
+    int length, n_bins_max, tile_lo;
 };
 
 __device__ __forceinline__ uint32_t bit_of(int d) { return __funnelshift_l(0u, 1u, (uint32_t)d); }   // 1u << (d & 31), one SHF
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
         for (int i = tid; i < p.n_contigs; i += blockDim.x) {
             const ContigDev& g = p.contigs[i];
             ContigLite c; c.cblocks = g.cblocks; c.anchors = g.anchors; c.n_groups = (uint32_t)(g.n_cblocks / HCNV_CGROUP); c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
-            c.length = g.length; c.n_bins_max = g.n_bins_max;
+            c.length = g.length; c.n_bins_max = g.n_bins_max; c.tile_lo = g.tile_lo;
             s_ct[i] = c;
         }
     __syncthreads();                              // the only CTA-wide barrier
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
         if (ct_cached) return s_ct[ci];
         const ContigDev& g = p.contigs[ci];
         ContigLite c; c.cblocks = g.cblocks; c.anchors = g.anchors; c.n_groups = (uint32_t)(g.n_cblocks / HCNV_CGROUP); c.blocks = g.blocks; c.longs = g.longs; c.snp_pos = g.snp_pos; c.n_long = g.n_long; c.snp_base = g.snp_base;
-        c.length = g.length; c.n_bins_max = g.n_bins_max;
+        c.length = g.length; c.n_bins_max = g.n_bins_max; c.tile_lo = g.tile_lo;
         return c;
     };
     // lane 0 only: prefetch the tile record of tile tt into ring slot `slot`
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(BIN_MAX_WARPS * 32, 1) k_bin_tiles(BinK p) {
             const ContigLite c = contig_of(tm.contig);
             c_contig = tm.contig;
             const int k = tm.k;
-            c_first = (k == 0);
+            c_first = (k == c.tile_lo);
             const int T0 = k * TP;                                   // 1-based position of diff[0] (fits int: length < 2^31)
             const long long T1l = (long long)T0 + TP;
             const uint32_t lb = tm.lb, hi = tm.hi;

@@ -112,3 +112,11 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
 int hcnv_download_results_impl(hcnv_ctx* ctx, hcnv_results_download* d);
 int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems,
                             int32_t flags);
+int  hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_part* parts, int32_t flags, hcnv_seg_plan** out);
+int  hcnv_seg_plan_stats_impl(hcnv_seg_plan* pl);
+int  hcnv_seg_plan_p0_impl(hcnv_seg_plan* pl);
+int  hcnv_seg_plan_p1_impl(hcnv_seg_plan* pl);
+int  hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round);
+int  hcnv_seg_plan_finish_impl(hcnv_seg_plan* pl);
+void hcnv_seg_plan_destroy_impl(hcnv_seg_plan* pl);
+hcnv_ctx* hcnv_seg_plan_ctx(hcnv_seg_plan* pl);

@@ -219,6 +219,17 @@ struct SegDev {
     int            n_seg, first_bad, pad;
     int            many;           // k_viterbi_many owns this chromosome (throughput path for large batches)
     int            mean_src1;      // 1 + index of an earlier problem with the same total / n arrays (its mean coverage is copied), 0: none
+    // A problem may be one PART of a chromosome that is cut across ranks (hcnv_segment_part): median / total / n / scaled_f span
+    // the whole chromosome (Mf markers: every rank that holds a part computes the chromosome's statistics itself), mse /
+    // scaled / state / cn / codes and M are the part's rows.  A whole chromosome is the part with Mf == M, first and last.
+    long long      Mf;
+    float*         scaled_f;       // scaled depth of the whole chromosome; scaled = scaled_f + the part's first row
+    int            part_index, part_first, part_last;
+    int            m0;             // first local marker of segment 0: 1 on the part that holds marker 0 (Hmm.java:179-181 starts the chain there), else 0
+    int            prev_call;      // out: best_state of the row BEFORE the part's first row (traceback of the part's marker 0, Hmm.java:236)
+    float          L_in[6];        // exact loss vector in front of the part's first marker (= the previous part's end vector)
+    double         Lf_in[6];       // the same, approximately (binade prediction)
+    float          loss0_out[6];   // out (first part): the exact loss vector after marker 0
 };
 
 __constant__ float c_mu[6] = {-1.0f, -0.5f, 0.f, 0.f, 0.5f, 1.0f};   // Hmm.java:34
@@ -231,7 +242,7 @@ __global__ void k_mean_coverage(SegDev* probs, int n_probs) {
     SegDev& P = probs[w];
     if (!P.pad) return;                              // k_mean_coverage_par already did it exactly
     if (P.mean_src1) return;                         // copied from the problem that shares its inputs (k_mean_copy)
-    const long long M = P.M;
+    const long long M = P.Mf;
     float s = 0.f;
     int sites = 0;
     float vnext = (lane < M) ? __ldg(&P.total[lane]) : 0.f;
@@ -289,11 +300,11 @@ __global__ void k_mean_copy(SegDev* probs, int n_probs) {
 __global__ void __launch_bounds__(256) k_scale_depth(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
     const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
     SegDev& P = probs[pi];
-    const int M = (int)P.M;                              // (markers per chromosome fit an int: checked on entry)
+    const int M = (int)P.Mf;                             // (markers per chromosome fit an int: checked on entry)
     const int i0 = ((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
     const float mean = P.mean;
     const float* __restrict__ med = P.median;
-    float* __restrict__ out = P.scaled;
+    float* __restrict__ out = P.scaled_f;
     float v[SEG_BLK / 256];
     #pragma unroll
     for (int k = 0; k < SEG_BLK / 256; ++k) { const int i = i0 + k * 256; v[k] = i < M ? __ldg(&med[i]) : 0.f; }     // all loads in flight
@@ -314,14 +325,15 @@ __global__ void k_sd(SegDev* probs, int n_probs, float alpha) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_probs) return;
     SegDev& P = probs[w];
-    const long long M = P.M;
+    const long long M = P.Mf;
+    const float* __restrict__ sc = P.scaled_f;
     bool need = P.want_sd || P.lambda1 < 0 || P.lambda2 < 0;
     float sd = 0.f;
     if (need && M >= 2) {
         float mean = 0.f;
         for (long long m0 = 0; m0 < M; m0 += 32) {
             long long m = m0 + lane;
-            float v = (m < M) ? P.scaled[m] : 0.f;
+            float v = (m < M) ? sc[m] : 0.f;
             int cnt = (int)min((long long)32, M - m0);
             for (int j = 0; j < cnt; ++j) mean = __fadd_rn(mean, __shfl_sync(0xffffffffu, v, j));
         }
@@ -329,7 +341,7 @@ __global__ void k_sd(SegDev* probs, int n_probs, float alpha) {
         float acc = 0.f;
         for (long long m0 = 0; m0 < M; m0 += 32) {
             long long m = m0 + lane;
-            float v = (m < M) ? P.scaled[m] : 0.f;
+            float v = (m < M) ? sc[m] : 0.f;
             float dev = __fsub_rn(v, mean);
             float d2 = __fmul_rn(dev, dev);
             int cnt = (int)min((long long)32, M - m0);
@@ -761,17 +773,64 @@ int hcnv_download_results_impl(hcnv_ctx* ctx, hcnv_results_download* d)
     return HCNV_OK;
 }
 
-int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* probs, int32_t flags)
+// ---------------------------------------------------------------------------------------------------
+// The segmentation of a batch as a PLAN of phases.  hcnv_segment_batch runs them back to back; a chromosome that is cut across
+// ranks (hcnv_segment_part, sharding.py) runs them with three small exchanges in between: the parts' approximate products after
+// p0, the exact boundary vectors between the rounds of the chain, the final state before finish.
+// ---------------------------------------------------------------------------------------------------
+struct hcnv_seg_plan {
+    hcnv_ctx* ctx = nullptr;
+    float alpha = 0.5f;
+    int n = 0, flags = 0;
+    bool dev = false, split = false;
+    hcnv_segment_part* parts = nullptr;            // the caller's array (scalar inputs / outputs live there)
+    std::vector<SegDev> h;
+    std::vector<char> route;
+    std::vector<int> order, blk_base, fblk_base, seg_base, chunk_base, repl;
+    bool any_mean_copy = false;
+    long long totM = 0, totMf = 0;
+    int total_segs = 0, VSEG = VSEG_DEFAULT;
+    size_t NC = 0;
+    SegDev* dprobs = nullptr; int* d_blkbase = nullptr; int* d_fblkbase = nullptr;
+    // segment-parallel scratch (H_VPAR)
+    int *d_segbase = nullptr, *d_epred = nullptr, *d_flags = nullptr, *d_force = nullptr, *d_repl = nullptr, *d_ti = nullptr, *d_tc = nullptr,
+        *d_cinfo = nullptr, *d_cbase = nullptr, *d_tiecnt = nullptr, *d_tielist = nullptr;
+    float *d_tf = nullptr, *d_ls = nullptr, *d_scan = nullptr;
+    int iter = 0;
+};
+
+namespace {
+// the fields of SegDev the host sets between phases (boundary vectors, final state) go up one problem at a time
+int push_prob(hcnv_seg_plan* pl, int i) {
+    HCNV_CUDA(pl->ctx, cudaMemcpyAsync(pl->dprobs + i, &pl->h[i], sizeof(SegDev), cudaMemcpyHostToDevice, pl->ctx->stream));
+    return HCNV_OK;
+}
+int pull_probs(hcnv_seg_plan* pl) {
+    HCNV_CUDA(pl->ctx, cudaMemcpyAsync(pl->h.data(), pl->dprobs, sizeof(SegDev) * (size_t)pl->n, cudaMemcpyDeviceToHost, pl->ctx->stream));
+    HCNV_CUDA(pl->ctx, cudaStreamSynchronize(pl->ctx->stream));
+    return HCNV_OK;
+}
+}  // namespace
+
+int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_part* parts, int32_t flags, hcnv_seg_plan** out)
 {
-    (void)flags;
-    if (!ctx || n_problems <= 0 || !probs) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
-    long long totM = 0;
+    if (!ctx || n_problems <= 0 || !parts || !out) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    *out = nullptr;
+    long long totM = 0, totMf = 0;
     int kind = -1;
+    bool split = false;
     for (int i = 0; i < n_problems; ++i) {
-        hcnv_segment_problem& q = probs[i];
+        hcnv_segment_part& pt = parts[i];
+        hcnv_segment_problem& q = pt.prob;
+        if (pt.n_parts < 1 || pt.part_index < 0 || pt.part_index >= pt.n_parts) return hcnv_fail(ctx, HCNV_E_INVALID, "bad part index");
         if (q.n_markers < 1) return hcnv_fail(ctx, HCNV_E_INVALID, "a chromosome needs at least one marker (CnvReducer only builds an Hmm when it has values)");
-        if (q.n_markers >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers");
+        if (pt.n_parts == 1 && (pt.row0 != 0 || pt.n_markers_full != q.n_markers)) return hcnv_fail(ctx, HCNV_E_INVALID, "a whole chromosome has row0 = 0 and n_markers_full = n_markers");
+        if (pt.row0 < 0 || pt.row0 + q.n_markers > pt.n_markers_full) return hcnv_fail(ctx, HCNV_E_INVALID, "part outside its chromosome");
+        if ((pt.part_index == 0) != (pt.row0 == 0) || (pt.part_index == pt.n_parts - 1) != (pt.row0 + q.n_markers == pt.n_markers_full))
+            return hcnv_fail(ctx, HCNV_E_INVALID, "parts must tile the chromosome in order");
+        if (pt.n_markers_full >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers");
         if (!q.median || !q.mse || !q.total || !q.n) return hcnv_fail(ctx, HCNV_E_INVALID, "null input array");
+        if (pt.n_parts > 1) split = true;
         const void* ptrs[7] = { q.median, q.mse, q.total, q.n, q.scaled, q.state, q.cn };
         // (a pointer query costs about a microsecond: every pointer of the first 64 problems, then one input and one output each)
         for (int j = 0; j < 7; ++j) {
@@ -779,8 +838,14 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
             int kd = hcnv_ptr_kind(ptrs[j]) == 2 ? 2 : 0;
             if (kind < 0) kind = kd; else if (kind != kd) return hcnv_fail(ctx, HCNV_E_INVALID, "mixed host/device pointers");
         }
-        totM += q.n_markers;
+        totM += q.n_markers; totMf += pt.n_markers_full;
     }
+    if (split && kind != 2) return hcnv_fail(ctx, HCNV_E_INVALID, "parts of a cut chromosome need device buffers");
+    hcnv_seg_plan* pl = new (std::nothrow) hcnv_seg_plan();
+    if (!pl) return HCNV_E_NOMEM;
+    pl->ctx = ctx; pl->alpha = alpha; pl->n = n_problems; pl->flags = flags; pl->parts = parts; pl->split = split;
+    pl->dev = kind == 2; pl->totM = totM; pl->totMf = totMf;
+    auto fail = [&](int rc) { delete pl; return rc; };
     // Which Viterbi for which chromosome?  route[i] = 0: the literal one-warp kernel (short chromosomes, or forced),
     // 1: the segment-parallel kernels, 2: the many-chains kernel.  The segment-parallel path costs ~0.076 ns per marker (six
     // times the arithmetic; measured on the 384- and 1 536-problem sweeps) but a chain's latency hardly grows with its
@@ -789,231 +854,384 @@ int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv
     // many-chains kernel lose their issue slots to the wide kernels: 335 ms instead of 201 / 242 ms on the 1 536-problem
     // sweep), so the longest chromosomes go to the first and the rest to the second, split where the sum of the two
     // estimates is smallest: a genome's 24 chains all take the first path, a cohort's thousands all take the second.
-    std::vector<char> route(n_problems, 0);
-    std::vector<int> order;                                 // the many-chains kernel's chromosomes, longest first
+    // A part of a cut chromosome always takes the segment-parallel path (the only one that can start from a boundary vector).
+    std::vector<char>& route = pl->route;
+    route.assign(n_problems, 0);
+    std::vector<int>& order = pl->order;                    // the many-chains kernel's chromosomes, longest first
+    auto M_of = [&](int i) { return parts[i].prob.n_markers; };
+    auto cut = [&](int i) { return parts[i].n_parts > 1; };
     if (!(flags & HCNV_SEG_SEQUENTIAL)) {
         std::vector<int> lng;
         int n_short = 0;
         for (int i = 0; i < n_problems; ++i) {
-            if (probs[i].n_markers >= V_PAR_MIN_MARKERS) lng.push_back(i);
-            else if (probs[i].n_markers >= VM_MIN_MARKERS) ++n_short;
+            if (cut(i)) continue;
+            if (M_of(i) >= V_PAR_MIN_MARKERS) lng.push_back(i);
+            else if (M_of(i) >= VM_MIN_MARKERS) ++n_short;
         }
-        std::stable_sort(lng.begin(), lng.end(), [&](int a, int b) { return probs[a].n_markers > probs[b].n_markers; });
+        std::stable_sort(lng.begin(), lng.end(), [&](int a, int b) { return M_of(a) > M_of(b); });
         size_t k_par = lng.size();                          // lng[0 .. k_par) -> segment-parallel, the rest -> many-chains
         if (flags & HCNV_SEG_THROUGHPUT) k_par = 0;
         else if (!(flags & HCNV_SEG_LATENCY) && !lng.empty()) {
             std::vector<double> suffix(lng.size() + 1, 0.0);
-            for (size_t j = lng.size(); j-- > 0;) suffix[j] = suffix[j + 1] + (double)probs[lng[j]].n_markers;
+            for (size_t j = lng.size(); j-- > 0;) suffix[j] = suffix[j + 1] + (double)M_of(lng[j]);
             double best = 1e300, prefix = 0.0;
             for (size_t k = 0; k <= lng.size(); ++k) {
-                if (k == 0 || k == lng.size() || probs[lng[k]].n_markers != probs[lng[k - 1]].n_markers) {
+                if (k == 0 || k == lng.size() || M_of(lng[k]) != M_of(lng[k - 1])) {
                     const double t_par = k ? 1.5e-3 + 0.076e-9 * prefix : 0.0;
-                    const double t_many = k < lng.size() ? std::max(70e-9 * (double)probs[lng[k]].n_markers, 0.029e-9 * suffix[k]) + 0.2e-3 : 0.0;
+                    const double t_many = k < lng.size() ? std::max(70e-9 * (double)M_of(lng[k]), 0.029e-9 * suffix[k]) + 0.2e-3 : 0.0;
                     const double t = t_par + t_many;
                     if (t < best) { best = t; k_par = k; }
                 }
-                if (k < lng.size()) prefix += (double)probs[lng[k]].n_markers;
+                if (k < lng.size()) prefix += (double)M_of(lng[k]);
             }
         }
         for (size_t j = 0; j < lng.size(); ++j) route[lng[j]] = j < k_par ? 1 : 2;
         const bool many_short = (flags & HCNV_SEG_THROUGHPUT) || (!(flags & HCNV_SEG_LATENCY) && (k_par < lng.size() || n_short >= 64));
         if (many_short)
             for (int i = 0; i < n_problems; ++i)
-                if (probs[i].n_markers < V_PAR_MIN_MARKERS && probs[i].n_markers >= VM_MIN_MARKERS) route[i] = 2;
+                if (!cut(i) && M_of(i) < V_PAR_MIN_MARKERS && M_of(i) >= VM_MIN_MARKERS) route[i] = 2;
         for (int i = 0; i < n_problems; ++i) if (route[i] == 2) order.push_back(i);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return probs[a].n_markers > probs[b].n_markers; });
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return M_of(a) > M_of(b); });
     }
-    const bool dev = kind == 2;
-    std::vector<SegDev> h(n_problems);
-    HCNV_CUDA(ctx, ctx->buf[H_CODES].reserve(4 * (size_t)totM));
-    HCNV_CUDA(ctx, ctx->buf[H_SCALED].reserve(4 * (size_t)totM));
+    for (int i = 0; i < n_problems; ++i) if (cut(i)) route[i] = 1;
+    const bool dev = pl->dev;
+    std::vector<SegDev>& h = pl->h;
+    h.resize(n_problems);
+    auto CU = [&](cudaError_t e, const char* what) -> int {
+        if (e == cudaSuccess) return HCNV_OK;
+        ctx->err = std::string(what) + " -> " + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? HCNV_E_NOMEM : HCNV_E_CUDA;
+    };
+    int rc;
+    if ((rc = CU(ctx->buf[H_CODES].reserve(4 * (size_t)totM), "codes"))) return fail(rc);
+    if ((rc = CU(ctx->buf[H_SCALED].reserve(4 * (size_t)totMf), "scaled"))) return fail(rc);
     if (!dev) {
-        HCNV_CUDA(ctx, ctx->buf[H_IN_F32].reserve(4 * 8 * (size_t)totM));     // median, mse*6, total
-        HCNV_CUDA(ctx, ctx->buf[H_IN_I32].reserve(4 * (size_t)totM));
-        HCNV_CUDA(ctx, ctx->buf[H_OUT_I32].reserve(4 * 2 * (size_t)totM));
+        if ((rc = CU(ctx->buf[H_IN_F32].reserve(4 * 8 * (size_t)totM), "inputs"))) return fail(rc);     // median, mse*6, total
+        if ((rc = CU(ctx->buf[H_IN_I32].reserve(4 * (size_t)totM), "inputs"))) return fail(rc);
+        if ((rc = CU(ctx->buf[H_OUT_I32].reserve(4 * 2 * (size_t)totM), "outputs"))) return fail(rc);
     }
-    long long off = 0;
-    std::vector<int> blk_base(n_problems + 1, 0);          // SEG_BLK-marker blocks before each chromosome (scale / traceback grids)
-    const int VSEG = VSEG_DEFAULT;
-    std::vector<int> seg_base(n_problems + 1, 0);
+    long long off = 0, foff = 0;
+    pl->blk_base.assign(n_problems + 1, 0);                // SEG_BLK-marker blocks before each part (traceback grid) ...
+    pl->fblk_base.assign(n_problems + 1, 0);               // ... and before each whole chromosome (scale grid)
+    pl->seg_base.assign(n_problems + 1, 0);
     std::map<std::tuple<const void*, const void*, long long>, int> mean_first;
-    bool any_mean_copy = false;
+    const int VSEG = pl->VSEG;
     for (int i = 0; i < n_problems; ++i) {
-        hcnv_segment_problem& q = probs[i];
+        hcnv_segment_part& pt = parts[i];
+        hcnv_segment_problem& q = pt.prob;
         SegDev& d = h[i];
         memset(&d, 0, sizeof d);
-        const long long M = q.n_markers;
-        d.M = M; d.lambda1 = q.lambda1; d.lambda2 = q.lambda2; d.want_sd = q.want_sd;
+        const long long M = q.n_markers, Mf = pt.n_markers_full;
+        d.M = M; d.Mf = Mf; d.lambda1 = q.lambda1; d.lambda2 = q.lambda2; d.want_sd = q.want_sd;
+        d.part_index = pt.part_index; d.part_first = pt.part_index == 0; d.part_last = pt.part_index == pt.n_parts - 1;
+        d.m0 = d.part_first ? 1 : 0;
+        d.prev_call = -1;
         d.codes = ctx->buf[H_CODES].as<uint32_t>() + off;
         if (dev) {
             d.median = q.median; d.mse = q.mse; d.total = q.total; d.n = q.n;
-            d.scaled = q.scaled ? q.scaled : ctx->buf[H_SCALED].as<float>() + off;
+            // a whole chromosome scales straight into the caller's array; a part keeps the whole chromosome's scaled depth in scratch
+            d.scaled_f = (q.scaled && pt.n_parts == 1) ? q.scaled : ctx->buf[H_SCALED].as<float>() + foff;
+            d.scaled = d.scaled_f + pt.row0;
             d.state = q.state; d.cn = q.cn;
         } else {
             float* f = ctx->buf[H_IN_F32].as<float>();
             float* dm = f + off; float* dmse = f + totM + 6 * off; float* dt = f + 7 * totM + off;
             int32_t* dn = ctx->buf[H_IN_I32].as<int32_t>() + off;
-            HCNV_CUDA(ctx, cudaMemcpyAsync(dm, q.median, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
-            HCNV_CUDA(ctx, cudaMemcpyAsync(dmse, q.mse, 24 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
-            HCNV_CUDA(ctx, cudaMemcpyAsync(dt, q.total, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
-            HCNV_CUDA(ctx, cudaMemcpyAsync(dn, q.n, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = CU(cudaMemcpyAsync(dm, q.median, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+            if ((rc = CU(cudaMemcpyAsync(dmse, q.mse, 24 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+            if ((rc = CU(cudaMemcpyAsync(dt, q.total, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+            if ((rc = CU(cudaMemcpyAsync(dn, q.n, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
             d.median = dm; d.mse = dmse; d.total = dt; d.n = dn;
-            d.scaled = ctx->buf[H_SCALED].as<float>() + off;
+            d.scaled_f = ctx->buf[H_SCALED].as<float>() + foff;
+            d.scaled = d.scaled_f;
             d.state = ctx->buf[H_OUT_I32].as<int32_t>() + off;
             d.cn = ctx->buf[H_OUT_I32].as<int32_t>() + totM + off;
         }
-        if ((M + SEG_BLK - 1) / SEG_BLK + blk_base[i] > 0x7fffffffLL) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers in one call");
-        blk_base[i + 1] = blk_base[i] + (int)((M + SEG_BLK - 1) / SEG_BLK);
-        off += M;
+        if ((M + SEG_BLK - 1) / SEG_BLK + pl->blk_base[i] > 0x7fffffffLL || (Mf + SEG_BLK - 1) / SEG_BLK + pl->fblk_base[i] > 0x7fffffffLL) {
+            hcnv_fail(ctx, HCNV_E_INVALID, "too many markers in one call"); return fail(HCNV_E_INVALID);
+        }
+        pl->blk_base[i + 1] = pl->blk_base[i] + (int)((M + SEG_BLK - 1) / SEG_BLK);
+        pl->fblk_base[i + 1] = pl->fblk_base[i] + (int)((Mf + SEG_BLK - 1) / SEG_BLK);
+        off += M; foff += Mf;
         {
-            auto key = std::make_tuple((const void*)q.total, (const void*)q.n, (long long)M);
+            auto key = std::make_tuple((const void*)q.total, (const void*)q.n, (long long)Mf);
             auto it = mean_first.find(key);
-            if (it == mean_first.end()) mean_first.emplace(key, i); else { d.mean_src1 = it->second + 1; any_mean_copy = true; }
+            if (it == mean_first.end()) mean_first.emplace(key, i); else { d.mean_src1 = it->second + 1; pl->any_mean_copy = true; }
         }
         d.many = route[i] == 2 ? 1 : 0;
         d.par = route[i] == 1 ? 1 : 0;
-        d.n_seg = d.par ? (int)((M - 1 + VSEG - 1) / VSEG) : 0;
+        d.n_seg = d.par ? (int)((M - d.m0 + VSEG - 1) / VSEG) : 0;
         d.first_bad = 0x7fffffff;
-        seg_base[i + 1] = seg_base[i] + d.n_seg;
+        pl->seg_base[i + 1] = pl->seg_base[i] + d.n_seg;
     }
-    const int total_segs = seg_base[n_problems];
-    const size_t nblk = (size_t)blk_base[n_problems];
-    HCNV_CUDA(ctx, ctx->buf[H_PROBS].reserve(sizeof(SegDev) * (size_t)n_problems));
-    HCNV_CUDA(ctx, ctx->buf[H_BLKMAP].reserve(4 * (size_t)(n_problems + 1) + 64));
-    SegDev* dprobs = ctx->buf[H_PROBS].as<SegDev>();
-    int* d_blkbase = ctx->buf[H_BLKMAP].as<int>();
-    HCNV_CUDA(ctx, cudaMemcpyAsync(dprobs, h.data(), sizeof(SegDev) * (size_t)n_problems, cudaMemcpyHostToDevice, ctx->stream));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(d_blkbase, blk_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream));
+    pl->total_segs = pl->seg_base[n_problems];
+    if ((rc = CU(ctx->buf[H_PROBS].reserve(sizeof(SegDev) * (size_t)n_problems), "problems"))) return fail(rc);
+    if ((rc = CU(ctx->buf[H_BLKMAP].reserve(8 * (size_t)(n_problems + 1) + 64), "block map"))) return fail(rc);
+    pl->dprobs = ctx->buf[H_PROBS].as<SegDev>();
+    pl->d_blkbase = ctx->buf[H_BLKMAP].as<int>();
+    pl->d_fblkbase = pl->d_blkbase + (n_problems + 1);
+    if ((rc = CU(cudaMemcpyAsync(pl->dprobs, h.data(), sizeof(SegDev) * (size_t)n_problems, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+    if ((rc = CU(cudaMemcpyAsync(pl->d_blkbase, pl->blk_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+    if ((rc = CU(cudaMemcpyAsync(pl->d_fblkbase, pl->fblk_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+    if (pl->total_segs > 0) {
+        const size_t S = (size_t)pl->total_segs, np1 = (size_t)(n_problems + 1);
+        pl->chunk_base.assign(n_problems + 1, 0);
+        for (int i = 0; i < n_problems; ++i) pl->chunk_base[i + 1] = pl->chunk_base[i] + (h[i].n_seg + VCH - 1) / VCH;
+        const size_t NC = pl->NC = (size_t)pl->chunk_base[n_problems];
+        size_t o_seg = 0, o_epred = o_seg + 4 * np1, o_flags = o_epred + 4 * S, o_force = o_flags + 4 * S;
+        size_t o_repl = o_force + 4 * S, o_tf = (o_repl + 4 * (size_t)n_problems + 255) / 256 * 256, o_ti = o_tf + 144 * S;
+        size_t o_ls = o_ti + 288 * S, o_tc = (o_ls + 24 * (S + (size_t)n_problems) + 255) / 256 * 256;
+        size_t o_cinfo = o_tc + 288 * NC, o_cbase = o_cinfo + 4 * NC, o_tie = o_cbase + 4 * np1;
+        size_t o_scan = (o_tie + 4 * (S + 4) + 255) / 256 * 256, bytes = o_scan + (split ? (size_t)n_problems * P0C_T * 144 : 0);
+        if ((rc = CU(ctx->buf[H_VPAR].reserve(bytes), "segment scratch"))) return fail(rc);
+        char* vb = ctx->buf[H_VPAR].as<char>();
+        pl->d_tc = (int*)(vb + o_tc); pl->d_cinfo = (int*)(vb + o_cinfo); pl->d_cbase = (int*)(vb + o_cbase);
+        pl->d_segbase = (int*)(vb + o_seg); pl->d_epred = (int*)(vb + o_epred); pl->d_flags = (int*)(vb + o_flags);
+        pl->d_force = (int*)(vb + o_force); pl->d_repl = (int*)(vb + o_repl);
+        pl->d_tf = (float*)(vb + o_tf); pl->d_ti = (int*)(vb + o_ti); pl->d_ls = (float*)(vb + o_ls);
+        pl->d_tiecnt = (int*)(vb + o_tie); pl->d_tielist = pl->d_tiecnt + 4;      // segments that met a rounding tie (P1's second pass)
+        pl->d_scan = (float*)(vb + o_scan);
+        if ((rc = CU(cudaMemcpyAsync(pl->d_cbase, pl->chunk_base.data(), 4 * np1, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+        if ((rc = CU(cudaMemcpyAsync(pl->d_segbase, pl->seg_base.data(), 4 * np1, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+        if ((rc = CU(cudaMemsetAsync(pl->d_tiecnt, 0, 16, ctx->stream), "memset"))) return fail(rc);
+        if ((rc = CU(cudaMemsetAsync(pl->d_force, 0, 4 * S, ctx->stream), "memset"))) return fail(rc);
+        { int z[16] = {0}; if ((rc = CU(cudaMemcpyToSymbolAsync(g_vdbg, z, sizeof z, 0, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc); }
+    }
+    pl->repl.assign(n_problems, 0);
+    *out = pl;
+    return HCNV_OK;
+}
 
-    const int wpb = 4;   // warps per block for the one-warp-per-chromosome kernels
+void hcnv_seg_plan_destroy_impl(hcnv_seg_plan* pl) { delete pl; }
+hcnv_ctx* hcnv_seg_plan_ctx(hcnv_seg_plan* pl) { return pl->ctx; }
+
+// mean coverage, scaled depth, sd and the penalty rules of every problem's WHOLE chromosome (Hmm.init / init_matrices)
+int hcnv_seg_plan_stats_impl(hcnv_seg_plan* pl)
+{
+    hcnv_ctx* ctx = pl->ctx;
+    const int n = pl->n, wpb = 4;   // warps per block for the one-warp-per-chromosome kernels
     KT_BEGIN(ctx, HCNV_K_MEAN_COVERAGE);
-    k_mean_coverage_cluster<<<n_problems * MCC_CS, MCC_T, 0, ctx->stream>>>(dprobs);
-    k_mean_coverage<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems);
-    if (any_mean_copy) { k_mean_copy<<<(n_problems + 255) / 256, 256, 0, ctx->stream>>>(dprobs, n_problems); ctx->launches++; }
+    k_mean_coverage_cluster<<<n * MCC_CS, MCC_T, 0, ctx->stream>>>(pl->dprobs);
+    k_mean_coverage<<<(n + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(pl->dprobs, n);
+    if (pl->any_mean_copy) { k_mean_copy<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pl->dprobs, n); ctx->launches++; }
     KT_END(ctx, HCNV_K_MEAN_COVERAGE);
     KT_BEGIN(ctx, HCNV_K_SCALE_DEPTH);
-    k_scale_depth<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_blkbase, n_problems);
+    k_scale_depth<<<(unsigned)pl->fblk_base[n], 256, 0, ctx->stream>>>(pl->dprobs, pl->d_fblkbase, n);
     KT_END(ctx, HCNV_K_SCALE_DEPTH);
     KT_BEGIN(ctx, HCNV_K_SD);
-    k_sd<<<(n_problems + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(dprobs, n_problems, alpha);
+    k_sd<<<(n + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(pl->dprobs, n, pl->alpha);
     KT_END(ctx, HCNV_K_SD);
     ctx->launches += 4;
+    HCNV_CUDA(ctx, cudaGetLastError());
+    return HCNV_OK;
+}
 
-    // ---- large batches: the many-chains kernel (five chromosomes per warp, longest first)
-    if (!order.empty()) {
-        HCNV_CUDA(ctx, ctx->buf[H_ORDER].reserve(4 * order.size()));
-        int* d_order = ctx->buf[H_ORDER].as<int>();
-        HCNV_CUDA(ctx, cudaMemcpyAsync(d_order, order.data(), 4 * order.size(), cudaMemcpyHostToDevice, ctx->stream));
-        KT_BEGIN(ctx, HCNV_K_VIT_MANY);
-        k_viterbi_many<<<(unsigned)((order.size() + VM_CH - 1) / VM_CH), 32, 0, ctx->stream>>>(dprobs, d_order, (int)order.size(), alpha);
-        KT_END(ctx, HCNV_K_VIT_MANY);
-        HCNV_CUDA(ctx, cudaGetLastError());
-        ctx->launches++;
-    }
-
-    // ---- exact segment-parallel Viterbi for the long chromosomes (viterbi_par.cuh)
-    if (total_segs > 0) {
-        const size_t S = (size_t)total_segs;
-        size_t o_seg = 0, o_epred = o_seg + 4 * (size_t)(n_problems + 1), o_flags = o_epred + 4 * S, o_force = o_flags + 4 * S;
-        size_t o_repl = o_force + 4 * S, o_tf = (o_repl + 4 * (size_t)n_problems + 255) / 256 * 256, o_ti = o_tf + 144 * S;
-        // chunks of VCH segments (viterbi_chain.cuh)
-        std::vector<int> chunk_base(n_problems + 1, 0);
-        for (int i = 0; i < n_problems; ++i) chunk_base[i + 1] = chunk_base[i] + (h[i].n_seg + VCH - 1) / VCH;
-        const size_t NC = (size_t)chunk_base[n_problems];
-        size_t o_ls = o_ti + 288 * S, o_tc = (o_ls + 24 * (S + (size_t)n_problems) + 255) / 256 * 256;
-        size_t o_cinfo = o_tc + 288 * NC, o_cbase = o_cinfo + 4 * NC, o_tie = o_cbase + 4 * (size_t)(n_problems + 1), bytes = o_tie + 4 * (S + 4);
-        HCNV_CUDA(ctx, ctx->buf[H_VPAR].reserve(bytes));
-        char* vb = ctx->buf[H_VPAR].as<char>();
-        int* d_tc = (int*)(vb + o_tc); int* d_cinfo = (int*)(vb + o_cinfo); int* d_cbase = (int*)(vb + o_cbase);
-        HCNV_CUDA(ctx, cudaMemcpyAsync(d_cbase, chunk_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream));
-        int* d_segbase = (int*)(vb + o_seg); int* d_epred = (int*)(vb + o_epred); int* d_flags = (int*)(vb + o_flags);
-        int* d_force = (int*)(vb + o_force); int* d_repl = (int*)(vb + o_repl);
-        float* d_tf = (float*)(vb + o_tf); int* d_ti = (int*)(vb + o_ti); float* d_ls = (float*)(vb + o_ls);
-        HCNV_CUDA(ctx, cudaMemcpyAsync(d_segbase, seg_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream));
-        int* d_tiecnt = (int*)(vb + o_tie); int* d_tielist = d_tiecnt + 4;      // segments that met a rounding tie (P1's second pass)
-        HCNV_CUDA(ctx, cudaMemsetAsync(d_tiecnt, 0, 16, ctx->stream));
-        HCNV_CUDA(ctx, cudaMemsetAsync(d_force, 0, 4 * S, ctx->stream));
-        { int z[16] = {0}; HCNV_CUDA(ctx, cudaMemcpyToSymbolAsync(g_vdbg, z, sizeof z, 0, cudaMemcpyHostToDevice, ctx->stream)); }
-        const unsigned gs = (unsigned)((S + 127) / 128);
+// P0: approximate transfer matrices; a plan with cut chromosomes also leaves every part's product (and whether its inputs are regular)
+int hcnv_seg_plan_p0_impl(hcnv_seg_plan* pl)
+{
+    hcnv_ctx* ctx = pl->ctx;
+    if (pl->total_segs > 0) {
+        const unsigned gs = (unsigned)(((size_t)pl->total_segs + 127) / 128);
         KT_BEGIN(ctx, HCNV_K_VIT_P0);
-        k_vit_p0<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_tf);
+        k_vit_p0<<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_tf);
         KT_END(ctx, HCNV_K_VIT_P0);
-        KT_BEGIN(ctx, HCNV_K_VIT_P0C);
-        {
-            const int sm = 2 * P0C_T * 36 * 4;
-            HCNV_CUDA(ctx, cudaFuncSetAttribute(k_vit_p0c_par, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-            k_vit_p0c_par<<<n_problems, P0C_T, sm, ctx->stream>>>(dprobs, d_segbase, alpha, d_tf, d_epred);
-        }
-        KT_END(ctx, HCNV_K_VIT_P0C);
-        KT_BEGIN(ctx, HCNV_K_VIT_P1);
-        k_vit_p1<false><<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_epred, d_ti, d_flags, d_tielist, d_tiecnt);
-        k_vit_p1<true><<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_epred, d_ti, d_flags, d_tielist, d_tiecnt);
         ctx->launches++;
-        KT_END(ctx, HCNV_K_VIT_P1);
-        ctx->launches += 3;
-        std::vector<int> repl(n_problems, 0);
-        for (int iter = 0; ; ++iter) {
-            const unsigned gc = (unsigned)((NC + 63) / 64);
-            KT_BEGIN(ctx, HCNV_K_VIT_P1B);
-            k_vit_p1b<<<gc, 64, 0, ctx->stream>>>(dprobs, d_segbase, d_cbase, n_problems, (int)NC, d_epred, d_ti, d_flags, d_force, d_tc, d_cinfo);
-            KT_END(ctx, HCNV_K_VIT_P1B);
-            KT_BEGIN(ctx, HCNV_K_VIT_P2);
-            k_vit_p2c<<<n_problems, 32, 0, ctx->stream>>>(dprobs, d_segbase, d_cbase, VSEG, alpha, d_epred, d_ti, d_flags, d_force, d_tc, d_cinfo, d_ls, d_repl);
-            KT_END(ctx, HCNV_K_VIT_P2);
-            KT_BEGIN(ctx, HCNV_K_VIT_P2B);
-            k_vit_p2b<<<gc, 64, 0, ctx->stream>>>(dprobs, d_segbase, d_cbase, n_problems, (int)NC, d_ti, d_cinfo, d_ls);
-            KT_END(ctx, HCNV_K_VIT_P2B);
-            ctx->launches += 2;
-            KT_BEGIN(ctx, HCNV_K_VIT_P3);
-            k_vit_p3<<<gs, 128, 0, ctx->stream>>>(dprobs, d_segbase, n_problems, total_segs, VSEG, alpha, d_ls, d_force);
-            KT_END(ctx, HCNV_K_VIT_P3);
-            ctx->launches += 2;
-            HCNV_CUDA(ctx, cudaGetLastError());
-            // one host round trip per pass: the verification verdicts, the replay counters and the diagnostics together
-            HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), dprobs, sizeof(SegDev) * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
-            HCNV_CUDA(ctx, cudaMemcpyAsync(repl.data(), d_repl, 4 * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
-            HCNV_CUDA(ctx, cudaMemcpyFromSymbolAsync(ctx->vdbg, g_vdbg, sizeof ctx->vdbg, 0, cudaMemcpyDeviceToHost, ctx->stream));
-            HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            bool again = false;
-            for (int i = 0; i < n_problems; ++i)
-                if (h[i].par && !h[i].irregular && !h[i].skip && h[i].first_bad != 0x7fffffff) again = true;
-            if (!again) break;
-            ctx->vit_repairs++;
-            if (iter >= 16) return hcnv_fail(ctx, HCNV_E_INTERNAL, "segment-parallel Viterbi did not converge");
+        if (pl->split) {
+            const int sm = 2 * P0C_T * 36 * 4;
+            HCNV_CUDA(ctx, cudaFuncSetAttribute(k_vit_p0c_par<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+            KT_BEGIN(ctx, HCNV_K_VIT_P0C);
+            k_vit_p0c_par<1><<<pl->n, P0C_T, sm, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
+            KT_END(ctx, HCNV_K_VIT_P0C);
+            ctx->launches++;
         }
-        ctx->vit_segments = total_segs; ctx->vit_replayed = 0;
-        for (int i = 0; i < n_problems; ++i) if (h[i].par && !h[i].irregular && !h[i].skip) ctx->vit_replayed += repl[i];
+        HCNV_CUDA(ctx, cudaGetLastError());
+    }
+    if (pl->split) {
+        int rc = pull_probs(pl);
+        if (rc) return rc;
+        for (int i = 0; i < pl->n; ++i) {
+            hcnv_segment_part& pt = pl->parts[i];
+            pt.irregular = pl->h[i].irregular; pt.skipped = pl->h[i].skip ? 1 : 0;
+            for (int c = 0; c < 6; ++c) pt.first_vector[c] = pl->h[i].loss0_out[c];
+            for (int j = 0; j < 36; ++j) pt.product_approx[j] = (j / 6 == j % 6) ? 0.f : V_INF_F;
+            if (pl->h[i].par && pl->h[i].n_seg > 0 && !pl->h[i].skip)
+                HCNV_CUDA(ctx, cudaMemcpyAsync(pt.product_approx, pl->d_scan + ((size_t)i * P0C_T + (P0C_T - 1)) * 36, 144, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return HCNV_OK;
+}
+
+// binade prediction (from parts[i].start_approx on the later parts of a cut chromosome), exact integer matrices
+int hcnv_seg_plan_p1_impl(hcnv_seg_plan* pl)
+{
+    hcnv_ctx* ctx = pl->ctx;
+    if (pl->total_segs == 0) return HCNV_OK;
+    const unsigned gs = (unsigned)(((size_t)pl->total_segs + 127) / 128);
+    const int sm = 2 * P0C_T * 36 * 4;
+    KT_BEGIN(ctx, HCNV_K_VIT_P0C);
+    if (pl->split) {
+        for (int i = 0; i < pl->n; ++i)
+            if (!pl->h[i].part_first) { for (int c = 0; c < 6; ++c) pl->h[i].Lf_in[c] = pl->parts[i].start_approx[c]; int rc = push_prob(pl, i); if (rc) return rc; }
+        HCNV_CUDA(ctx, cudaFuncSetAttribute(k_vit_p0c_par<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        k_vit_p0c_par<2><<<pl->n, P0C_T, sm, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
+    } else {
+        HCNV_CUDA(ctx, cudaFuncSetAttribute(k_vit_p0c_par<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        k_vit_p0c_par<0><<<pl->n, P0C_T, sm, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
+    }
+    KT_END(ctx, HCNV_K_VIT_P0C);
+    KT_BEGIN(ctx, HCNV_K_VIT_P1);
+    k_vit_p1<false><<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_tielist, pl->d_tiecnt);
+    k_vit_p1<true><<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_tielist, pl->d_tiecnt);
+    KT_END(ctx, HCNV_K_VIT_P1);
+    ctx->launches += 3;
+    HCNV_CUDA(ctx, cudaGetLastError());
+    return HCNV_OK;
+}
+
+// The chains.  Round r walks the parts with part_index == r from their exact start vectors (parts[i].start_exact for r > 0) and
+// leaves parts[i].end_exact; round 0 also runs every whole chromosome (all three Viterbi forms) and composes the chunk matrices.
+int hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round)
+{
+    hcnv_ctx* ctx = pl->ctx;
+    const int n = pl->n;
+    if (round == 0) {
+        if (!pl->order.empty() && pl->iter == 0) {
+            // large batches: the many-chains kernel (five chromosomes per warp, longest first)
+            HCNV_CUDA(ctx, ctx->buf[H_ORDER].reserve(4 * pl->order.size()));
+            int* d_order = ctx->buf[H_ORDER].as<int>();
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d_order, pl->order.data(), 4 * pl->order.size(), cudaMemcpyHostToDevice, ctx->stream));
+            KT_BEGIN(ctx, HCNV_K_VIT_MANY);
+            k_viterbi_many<<<(unsigned)((pl->order.size() + VM_CH - 1) / VM_CH), 32, 0, ctx->stream>>>(pl->dprobs, d_order, (int)pl->order.size(), pl->alpha);
+            KT_END(ctx, HCNV_K_VIT_MANY);
+            HCNV_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+        if (pl->total_segs > 0) {
+            const unsigned gc = (unsigned)((pl->NC + 63) / 64);
+            KT_BEGIN(ctx, HCNV_K_VIT_P1B);
+            k_vit_p1b<<<gc, 64, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->d_cbase, n, (int)pl->NC, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_force, pl->d_tc, pl->d_cinfo);
+            KT_END(ctx, HCNV_K_VIT_P1B);
+            ctx->launches++;
+        }
+    }
+    if (pl->total_segs > 0) {
+        if (round > 0)
+            for (int i = 0; i < n; ++i)
+                if (pl->h[i].part_index == round) { for (int c = 0; c < 6; ++c) pl->h[i].L_in[c] = pl->parts[i].start_exact[c]; int rc = push_prob(pl, i); if (rc) return rc; }
+        KT_BEGIN(ctx, HCNV_K_VIT_P2);
+        k_vit_p2c<<<n, 32, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->d_cbase, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_force, pl->d_tc, pl->d_cinfo, pl->d_ls, pl->d_repl, round);
+        KT_END(ctx, HCNV_K_VIT_P2);
+        ctx->launches++;
+        HCNV_CUDA(ctx, cudaGetLastError());
+    }
+    if (pl->split) {
+        // boundary vectors of this round's parts go back to the host (the caller hands them to the next rank)
+        std::vector<SegDev> tmp(n);
+        HCNV_CUDA(ctx, cudaMemcpyAsync(tmp.data(), pl->dprobs, sizeof(SegDev) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; ++i) {
+            if (pl->h[i].part_index != round) continue;
+            hcnv_segment_part& pt = pl->parts[i];
+            pl->h[i] = tmp[i];
+            for (int c = 0; c < 6; ++c) pt.end_exact[c] = tmp[i].last_row[c];
+            pt.sstar = tmp[i].sstar; pt.prob.status = tmp[i].status; pt.skipped = tmp[i].skip ? 1 : 0;
+        }
+    }
+    return HCNV_OK;
+}
+
+// Needs the final state of every cut chromosome in parts[i].sstar.  Start vectors inside the chunks, replay of every segment with
+// the reference's float arithmetic + verification, the calls; scalar outputs.  Returns HCNV_SEG_AGAIN when a verification failed:
+// run the chain rounds and finish again (never seen; it would mean a matrix was applied outside its validity).
+int hcnv_seg_plan_finish_impl(hcnv_seg_plan* pl)
+{
+    hcnv_ctx* ctx = pl->ctx;
+    const int n = pl->n;
+    hcnv_segment_part* parts = pl->parts;
+    std::vector<SegDev>& h = pl->h;
+    if (pl->split)       // (a part that is not the last holds the arg-min of its own end vector: replace it by the chromosome's)
+        for (int i = 0; i < n; ++i)
+            if (parts[i].n_parts > 1 && !h[i].part_last) { h[i].sstar = parts[i].sstar; int rc = push_prob(pl, i); if (rc) return rc; }
+    if (pl->total_segs > 0) {
+        const unsigned gs = (unsigned)(((size_t)pl->total_segs + 127) / 128), gc = (unsigned)((pl->NC + 63) / 64);
+        KT_BEGIN(ctx, HCNV_K_VIT_P2B);
+        k_vit_p2b<<<gc, 64, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->d_cbase, n, (int)pl->NC, pl->d_ti, pl->d_cinfo, pl->d_ls);
+        KT_END(ctx, HCNV_K_VIT_P2B);
+        KT_BEGIN(ctx, HCNV_K_VIT_P3);
+        k_vit_p3<<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_ls, pl->d_force);
+        KT_END(ctx, HCNV_K_VIT_P3);
+        ctx->launches += 2;
+        HCNV_CUDA(ctx, cudaGetLastError());
+        // one host round trip per pass: the verification verdicts, the replay counters and the diagnostics together
+        HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), pl->dprobs, sizeof(SegDev) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaMemcpyAsync(pl->repl.data(), pl->d_repl, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaMemcpyFromSymbolAsync(ctx->vdbg, g_vdbg, sizeof ctx->vdbg, 0, cudaMemcpyDeviceToHost, ctx->stream));
+        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        bool again = false;
+        for (int i = 0; i < n; ++i)
+            if (h[i].par && !h[i].irregular && !h[i].skip && h[i].first_bad != 0x7fffffff) again = true;
+        if (again) {
+            ctx->vit_repairs++;
+            if (++pl->iter > 16) return hcnv_fail(ctx, HCNV_E_INTERNAL, "segment-parallel Viterbi did not converge");
+            return HCNV_SEG_AGAIN;
+        }
+        ctx->vit_segments = pl->total_segs; ctx->vit_replayed = 0;
+        for (int i = 0; i < n; ++i) if (h[i].par && !h[i].irregular && !h[i].skip) ctx->vit_replayed += pl->repl[i];
     } else { ctx->vit_segments = 0; ctx->vit_replayed = 0; }
     KT_BEGIN(ctx, HCNV_K_VITERBI);
     // ---- everything else (short chromosomes, irregular inputs): the literal one-warp kernel
-    k_viterbi_seq<<<n_problems, 32, 0, ctx->stream>>>(dprobs, alpha);
+    k_viterbi_seq<<<n, 32, 0, ctx->stream>>>(pl->dprobs, pl->alpha);
     KT_END(ctx, HCNV_K_VITERBI);
     KT_BEGIN(ctx, HCNV_K_TRACEBACK);
-    k_traceback<<<(unsigned)nblk, 256, 0, ctx->stream>>>(dprobs, d_blkbase, n_problems);
+    k_traceback<<<(unsigned)pl->blk_base[n], 256, 0, ctx->stream>>>(pl->dprobs, pl->d_blkbase, n);
     KT_END(ctx, HCNV_K_TRACEBACK);
     ctx->launches += 2;
     HCNV_CUDA(ctx, cudaGetLastError());
-    HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), dprobs, sizeof(SegDev) * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
-    if (!dev) {
-        off = 0;
-        for (int i = 0; i < n_problems; ++i) {
-            hcnv_segment_problem& q = probs[i];
-            const size_t M = (size_t)q.n_markers;
+    HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), pl->dprobs, sizeof(SegDev) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        hcnv_segment_problem& q = parts[i].prob;
+        const size_t M = (size_t)q.n_markers;
+        if (!pl->dev) {
             if (q.scaled) HCNV_CUDA(ctx, cudaMemcpyAsync(q.scaled, h[i].scaled, 4 * M, cudaMemcpyDeviceToHost, ctx->stream));
             if (q.state) HCNV_CUDA(ctx, cudaMemcpyAsync(q.state, h[i].state, 4 * M, cudaMemcpyDeviceToHost, ctx->stream));
             if (q.cn) HCNV_CUDA(ctx, cudaMemcpyAsync(q.cn, h[i].cn, 4 * M, cudaMemcpyDeviceToHost, ctx->stream));
-            off += (long long)M;
-        }
+        } else if (q.scaled && parts[i].n_parts > 1)
+            HCNV_CUDA(ctx, cudaMemcpyAsync(q.scaled, h[i].scaled, 4 * M, cudaMemcpyDeviceToDevice, ctx->stream));     // the part's rows of the whole chromosome's scaled depth
     }
     HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int worst = HCNV_OK;
-    for (int i = 0; i < n_problems; ++i) {
-        hcnv_segment_problem& q = probs[i];
+    for (int i = 0; i < n; ++i) {
+        hcnv_segment_problem& q = parts[i].prob;
         q.mean_coverage = h[i].mean; q.sd = h[i].sd; q.lambda1_used = h[i].l1u; q.lambda2_used = h[i].l2u;
         q.final_loss = h[i].final_loss; q.status = h[i].status;
-        for (int s = 0; s < 6; ++s) q.last_row[s] = h[i].last_row[s];
+        for (int s2 = 0; s2 < 6; ++s2) q.last_row[s2] = h[i].last_row[s2];
+        parts[i].prev_call = h[i].prev_call; parts[i].irregular = h[i].irregular; parts[i].skipped = h[i].skip ? 1 : 0;
         if (q.status < 0) worst = q.status;
     }
     if (worst < 0) return hcnv_fail(ctx, worst, "Hmm: failed to find minimum (the reference exits here, Hmm.java:205-215,229-232)");
     return HCNV_OK;
+}
+
+int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* probs, int32_t flags)
+{
+    if (!ctx || n_problems <= 0 || !probs) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    std::vector<hcnv_segment_part> parts((size_t)n_problems);
+    for (int i = 0; i < n_problems; ++i) {
+        memset(&parts[i], 0, sizeof parts[i]);
+        parts[i].prob = probs[i];
+        parts[i].n_markers_full = probs[i].n_markers; parts[i].row0 = 0; parts[i].part_index = 0; parts[i].n_parts = 1;
+    }
+    hcnv_seg_plan* pl = nullptr;
+    int rc = hcnv_seg_plan_create_impl(ctx, alpha, n_problems, parts.data(), flags, &pl);
+    if (rc) return rc;
+    if (!(rc = hcnv_seg_plan_stats_impl(pl)) && !(rc = hcnv_seg_plan_p0_impl(pl)) && !(rc = hcnv_seg_plan_p1_impl(pl))) {
+        do {
+            if ((rc = hcnv_seg_plan_chain_impl(pl, 0))) break;
+            rc = hcnv_seg_plan_finish_impl(pl);
+        } while (rc == HCNV_SEG_AGAIN);
+    }
+    hcnv_seg_plan_destroy_impl(pl);
+    for (int i = 0; i < n_problems; ++i) probs[i] = parts[i].prob;      // scalar outputs
+    return rc;
 }

@@ -31,7 +31,7 @@ __global__ void __cluster_dims__(MCC_CS, 1, 1) __launch_bounds__(MCC_T) k_mean_c
     const int rank = (int)cluster.block_rank();
     SegDev& P = probs[blockIdx.x / MCC_CS];
     if (P.mean_src1) return;                      // (uniform over the cluster) copied from the problem that shares its inputs
-    const long long M = P.M;
+    const long long M = P.Mf;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float* __restrict__ tot = P.total;
 

@@ -58,8 +58,12 @@ __device__ __forceinline__ void fmat_load(const float* __restrict__ g, float* T)
 }
 
 #define P0C_T 256
+// MODE 0: scan and walk in one launch (whole chromosomes).  A chromosome that is cut across ranks needs the products of the
+// parts in front of it before it can walk: MODE 1 scans and leaves every thread's inclusive prefix in `scan_out` (the last one
+// is the part's product), MODE 2 walks from P.Lf_in with the prefixes of MODE 1.
+template <int MODE>
 __global__ void __launch_bounds__(P0C_T) k_vit_p0c_par(SegDev* probs, const int* __restrict__ seg_base, float alpha,
-                                                       const float* __restrict__ Tf, int* __restrict__ epred) {
+                                                       const float* __restrict__ Tf, int* __restrict__ epred, float* __restrict__ scan_out) {
     extern __shared__ __align__(16) float sm_scan[];           // [2][P0C_T][36]
     SegDev& P = probs[blockIdx.x];
     if (P.skip || !P.par) return;
@@ -69,34 +73,48 @@ __global__ void __launch_bounds__(P0C_T) k_vit_p0c_par(SegDev* probs, const int*
     const int C = (nseg + P0C_T - 1) / P0C_T;
     const int s0 = min(nseg, tid * C), s1 = min(nseg, s0 + C);
     float R[36], T[36];
-    fmat_identity(R);
-    for (int s = s0; s < s1; ++s) {
-        fmat_load(Tf + (size_t)(base + s) * 36, T);
-        fmat_mul_right(R, T);
-    }
-    // inclusive Hillis-Steele scan of the chunk products (ordered)
     int cur = 0;
-    #pragma unroll
-    for (int i = 0; i < 36; ++i) sm_scan[(cur * P0C_T + tid) * 36 + i] = R[i];
-    __syncthreads();
-    for (int o = 1; o < P0C_T; o <<= 1) {
-        if (tid >= o) {
-            const float* A = &sm_scan[(cur * P0C_T + tid - o) * 36];
-            #pragma unroll
-            for (int i = 0; i < 36; ++i) T[i] = A[i];
-            fmat_mul_left(T, R);
+    float* gscan = scan_out + (size_t)blockIdx.x * P0C_T * 36;
+    if (MODE != 2) {
+        fmat_identity(R);
+        for (int s = s0; s < s1; ++s) {
+            fmat_load(Tf + (size_t)(base + s) * 36, T);
+            fmat_mul_right(R, T);
         }
-        cur ^= 1;
+        // inclusive Hillis-Steele scan of the chunk products (ordered)
         #pragma unroll
         for (int i = 0; i < 36; ++i) sm_scan[(cur * P0C_T + tid) * 36 + i] = R[i];
         __syncthreads();
+        for (int o = 1; o < P0C_T; o <<= 1) {
+            if (tid >= o) {
+                const float* A = &sm_scan[(cur * P0C_T + tid - o) * 36];
+                #pragma unroll
+                for (int i = 0; i < 36; ++i) T[i] = A[i];
+                fmat_mul_left(T, R);
+            }
+            cur ^= 1;
+            #pragma unroll
+            for (int i = 0; i < 36; ++i) sm_scan[(cur * P0C_T + tid) * 36 + i] = R[i];
+            __syncthreads();
+        }
+        if (MODE == 1) {
+            #pragma unroll
+            for (int i = 0; i < 36; ++i) gscan[(size_t)tid * 36 + i] = R[i];
+            if (tid < 6 && P.part_first) P.loss0_out[tid] = loss0(P, k, tid);
+            return;
+        }
+    } else {
+        if (tid > 0) {
+            #pragma unroll
+            for (int i = 0; i < 36; ++i) sm_scan[(tid - 1) * 36 + i] = gscan[(size_t)(tid - 1) * 36 + i];       // only the own exclusive prefix is read back
+        }
     }
-    // exclusive prefix applied to the loss vector after marker 0, then walk the chunk with the vector
+    // exclusive prefix applied to the loss vector in front of the first segment, then walk the chunk with the vector
     double v[6];
     {
         double L0[6];
         #pragma unroll
-        for (int c = 0; c < 6; ++c) L0[c] = (double)loss0(P, k, c);
+        for (int c = 0; c < 6; ++c) L0[c] = P.part_first ? (double)loss0(P, k, c) : P.Lf_in[c];
         if (tid == 0) {
             #pragma unroll
             for (int c = 0; c < 6; ++c) v[c] = L0[c];
@@ -241,11 +259,12 @@ __global__ void __launch_bounds__(32) k_vit_p2c(SegDev* probs, const int* __rest
                                                 int VSEG, float alpha, const int* __restrict__ epred, const int* __restrict__ Ti,
                                                 const int* __restrict__ flags, const int* __restrict__ force,
                                                 const int* __restrict__ Tc, int* __restrict__ cinfo,
-                                                float* __restrict__ Lstart, int* __restrict__ replayed) {
+                                                float* __restrict__ Lstart, int* __restrict__ replayed, int round) {
     __shared__ __align__(16) int sC[2][VB * 72];          // staged chunk matrices
     __shared__ __align__(16) int sS[VCH * 72];            // staged segment matrices of one chunk (fallback walk)
     SegDev& P = probs[blockIdx.x];
     if (P.skip || !P.par || P.irregular) return;
+    if (P.part_index != round) return;                    // a later part of a cut chromosome waits for its predecessor's end vector
     const int lane = threadIdx.x, c = lane < 6 ? lane : 0;
     const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
     const float c3 = k.c3[c];
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__(32) k_vit_p2c(SegDev* probs, const int* __rest
     const int nch = (nseg + VCH - 1) / VCH;
     const long long M = P.M;
     float* ls = Lstart + ((size_t)sbase + blockIdx.x) * 6;     // n_seg + 1 vectors per chromosome
-    float L = loss0(P, k, c);
+    float L = P.part_first ? loss0(P, k, c) : P.L_in[c];
     if (lane < 6) ls[lane] = L;
     int bad1e10 = 0, n_replayed = 0;
     if (nch > 0) stage_mats(sC[0], Tc + (size_t)cbase * 72, min(VB, nch), lane, 72);
@@ -299,7 +318,7 @@ __global__ void __launch_bounds__(32) k_vit_p2c(SegDev* probs, const int* __rest
                 if (oks) oks = vit_apply(&sS[(s - s0) * 72], L, es, lane, c, Lnew);
                 if (!oks) {
                     ++n_replayed;
-                    const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+                    const long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
                     Lnew = vit_replay(P, k, L, a, b, lane, c, c3, c4, bad1e10);
                 }
                 L = Lnew;
@@ -317,7 +336,7 @@ __global__ void __launch_bounds__(32) k_vit_p2c(SegDev* probs, const int* __rest
         for (int s6 = 0; s6 < 6; ++s6) P.last_row[s6] = row[s6];
         P.sstar = min_index; P.final_loss = mn;
         P.status = HCNV_OK;
-        if (bad1e10 || mn == 3.402823466e+38f) { P.status = HCNV_E_NO_MINIMUM; P.skip = 2; }
+        if (bad1e10 || (P.part_last && mn == 3.402823466e+38f)) { P.status = HCNV_E_NO_MINIMUM; P.skip = 2; }
         P.first_bad = 0x7fffffff;
         replayed[blockIdx.x] = n_replayed;
     }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) k_vit_p0(SegDev* probs, const int* __rest
     if (P.skip || !P.par) return;
     const int s = g - seg_base[pi];
     const long long M = P.M;
-    const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+    const long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
     const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
     float v[6][6];
     #pragma unroll
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128) k_vit_p0(SegDev* probs, const int* __rest
         for (int c = 0; c < 6; ++c) v[i][c] = (i == c) ? 0.f : V_INF_F;
     bool bad = false;
     float sd, mse[6];
-    if (s == 0) {                                     // marker 0 belongs to no segment: check it here
+    if (s == 0 && P.part_first) {                     // marker 0 belongs to no segment: check it here
         load_marker(P.scaled, P.mse, 0, sd, mse);
         bad |= !(fabsf(sd) <= 2.0f);
         #pragma unroll
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128) k_vit_p0(SegDev* probs, const int* __rest
 // exact loss vector after marker 0 (Hmm.java:179-181) for lane c
 __device__ __forceinline__ float loss0(const SegDev& P, const VitConsts& k, int c) {
     float lrr = 0.f, baf = 0.f;
-    if (P.M >= 2) { float dev = __fsub_rn(P.scaled[0], c_mu[c]); lrr = __fmul_rn(dev, dev); baf = P.mse[c]; }
+    if (P.Mf >= 2) { float dev = __fsub_rn(P.scaled[0], c_mu[c]); lrr = __fmul_rn(dev, dev); baf = P.mse[c]; }
     return __fadd_rn(__fadd_rn(__fmul_rn(k.oma, lrr), __fmul_rn(k.alpha, baf)), k.c3[c]);
 }
 
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __rest
     if (e < 0 || P.irregular) { flags[g] = 0; return; }
     const int s = g - seg_base[pi];
     const long long M = P.M;
-    const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+    const long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
     const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
     const float scale = __int_as_float((127 + 23 - e) << 23);
     bool ovf = false, const_tie = false;
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(32) k_vit_p2(SegDev* probs, const int* __restr
         }
         if (!ok) {                                                    // exact replay of this segment
             ++n_replayed;
-            const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+            const long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
             Lnew = L;
             for (long long m0 = a; m0 < b; m0 += 32) {
                 long long m = m0 + lane;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __rest
     if (P.skip || !P.par || P.irregular) return;
     const int s = g - seg_base[pi];
     const long long M = P.M;
-    const long long a = 1 + (long long)s * VSEG, b = min(M, a + VSEG);
+    const long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
     const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
     const float* ls = Lstart + ((size_t)seg_base[pi] + pi) * 6 + (size_t)s * 6;
     const int sstar = P.sstar;
@@ -505,8 +505,11 @@ __global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __rest
             float cand = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(L[p], As), Bs), c3s), c4s[p]);
             if (cand == Ls && cand < 3.402823466e+38f) arg = p;
         }
-        if (P.state) P.state[m - 1] = arg;                           // best_state[m-1] = traceback[m][s*] (Hmm.java:236)
-        if (P.cn) P.cn[m - 1] = c_cn[arg];
+        if (m == 0) P.prev_call = arg;                               // (a later part's marker 0 decides the call of the previous part's last row)
+        else {
+            if (P.state) P.state[m - 1] = arg;                       // best_state[m-1] = traceback[m][s*] (Hmm.java:236)
+            if (P.cn) P.cn[m - 1] = c_cn[arg];
+        }
         #pragma unroll
         for (int c = 0; c < 6; ++c) { L[c] = Ln[c]; mse[c] = msen[c]; }
         sd = sdn;
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __rest
     for (int c = 0; c < 6; ++c) same &= __float_as_uint(L[c]) == __float_as_uint(__ldg(&nx[c]));
     if (!same) { atomicMin(&P.first_bad, s); force[g] = 1; }
     if (bad) P.status = HCNV_E_NO_MINIMUM;                          // Hmm.java:205-215 would exit
-    if (b == M) {                                                    // last marker (Hmm.java:234, sic)
+    if (b == M && P.part_last) {                                     // last marker (Hmm.java:234, sic)
         int st = c_cn[sstar];
         if (P.state) P.state[M - 1] = st;
         if (P.cn) P.cn[M - 1] = c_cn[st];

@@ -128,8 +128,9 @@ typedef struct {
     int32_t max_block_len;              /* upper bound of len over the short blocks (<= HCNV_SHORT_MAX); 0 = HCNV_SHORT_MAX */
     double  mapping_quality_threshold;  /* Constants.mapping_quality_threshold (Constants.java:21), default 0 */
     int32_t tile_bins;                  /* tuning: cap on warps (= concurrent 32-bin tiles) per SM, 0 = as many as fit */
-    int32_t flags;                      /* reserved, 0 */
+    int32_t flags;                      /* tuning: bit 0 = HCNV_BIN_FIRST_FORM (compact stream through the 32-bins-per-warp kernel), else 0 */
 } hcnv_bin_params;
+#define HCNV_BIN_FIRST_FORM 1
 void hcnv_bin_params_default(hcnv_bin_params* p);
 
 /* Inputs of one contig (= one reference sequence; the reducer key's refname, Keys.java:226-238).
@@ -147,6 +148,15 @@ typedef struct {
     const hcnv_cblock*     cblocks;     const int32_t* anchors; int64_t n_cblocks;
     /* alternative to `obs` (give one or the other, per contig): the observations at 2 bytes each, see hcnv_cobs */
     const hcnv_cobs*       cobs;        const int32_t* cobs_anchors; int64_t n_cobs;
+    /* A REGION of the contig (region sharding across GPUs; all three 0: the whole contig).  Only the bins
+     * region_first_bin .. region_first_bin + region_n_bins - 1 (bin = position / bin_width; region_n_bins 0: to the contig's
+     * end) are produced; region_first_bin must be a multiple of 64.  Bins are independent (Reducers.java:55-204), so the
+     * regions of a contig add up to the contig.  The block stream only has to hold the records that reach into the region
+     * (a superset is fine: every record is clipped), the SNP table exactly the region's sites; observations keep naming sites
+     * by their index in the contig's WHOLE table, snp_index_base is the index of snp_pos1[0] there, and observations of other
+     * sites are ignored. */
+    int32_t                region_first_bin, region_n_bins;
+    int64_t                snp_index_base;
 } hcnv_contig_input;
 
 /* Host helper (no GPU): sorted hcnv_block records -> compact stream; blocks whose MAPQ fails mapping_quality_threshold
@@ -240,6 +250,46 @@ typedef struct {
 #define HCNV_SEG_THROUGHPUT 2       /* flags: force the many-chains kernel (five chromosomes per warp): the choice for large batches */
 #define HCNV_SEG_LATENCY    4       /* flags: force the segment-parallel kernels for long chromosomes: the choice for a few chains */
 int hcnv_segment_batch(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems, int32_t flags);
+
+/* ---- B2 across ranks: one chromosome cut into parts ---------------------------------------------------------------- */
+/* The reference hands a chromosome to ONE CnvReducer call (Reducers.java:225-243, PennCnvSeq.java:382-414).  When a chromosome's
+ * bins sit on several GPUs (region sharding), every rank that holds a PART of it runs the segmentation as a plan
+ * of phases with three small exchanges in between (hadoopcnv_b200/sharding.py does them over torch.distributed / NCCL):
+ *   stats   every rank needs the chromosome's median / total / n (all-gathered before the plan is created): mean coverage is a
+ *           sequential float sum over the whole chromosome (Hmm.java:369-373), computed exactly by every rank for itself
+ *   p0      approximate 6x6 min-plus matrices of the part's segments          -> first_vector (part 0), product_approx
+ *           [exchange: start_approx of part j = first_vector (x) product_approx of parts 0 .. j-1, in f64]
+ *   p1      binade of every segment, exact integer matrices inside it
+ *   chain   round r = parts with part_index r: the exact loss vector through the part      -> end_exact (+ sstar on the last part)
+ *           [exchange after every round: start_exact of part r+1 = end_exact of part r; after the last round: sstar to every part]
+ *   finish  float replay of every segment from its exact start vector, verified bit for bit, calls of the part's rows; prev_call
+ *           = the call of the row in front of the part (Hmm.java:236 takes best_state[m-1] from marker m)
+ * A whole chromosome is the part with n_parts = 1; hcnv_segment_batch is exactly these phases back to back.  prob.median /
+ * total / n span the WHOLE chromosome (n_markers_full entries); prob.mse and the outputs prob.scaled / state / cn are the part's
+ * rows (prob.n_markers of them, starting at row0).  Parts need device buffers. */
+typedef struct {
+    hcnv_segment_problem prob;
+    int64_t n_markers_full, row0;
+    int32_t part_index, n_parts;
+    float   first_vector[HCNV_STATES];                  /* out of p0 (part 0): loss vector after marker 0 (Hmm.java:179-181) */
+    float   product_approx[HCNV_STATES * HCNV_STATES];  /* out of p0: [start state][end state] */
+    double  start_approx[HCNV_STATES];                  /* in of p1 (parts > 0) */
+    float   start_exact[HCNV_STATES];                   /* in of chain(part_index) (parts > 0) */
+    float   end_exact[HCNV_STATES];                     /* out of chain(part_index) */
+    int32_t sstar;                                      /* out of the last part's round; in of finish on the other parts */
+    int32_t prev_call;                                  /* out of finish (parts > 0) */
+    int32_t irregular;                                  /* out of p0: NaN / negative inputs -- gather the chromosome and use hcnv_segment_batch */
+    int32_t skipped;                                    /* out of p0: Hmm.search's rule applies (no Viterbi, all calls 0) */
+} hcnv_segment_part;
+#define HCNV_SEG_AGAIN 2            /* hcnv_seg_plan_finish: a verification failed, run the chain rounds and finish again */
+typedef struct hcnv_seg_plan hcnv_seg_plan;
+int  hcnv_seg_plan_create(hcnv_ctx* ctx, float alpha, int32_t n_parts, hcnv_segment_part* parts, int32_t flags, hcnv_seg_plan** out);
+int  hcnv_seg_plan_stats(hcnv_seg_plan* plan);
+int  hcnv_seg_plan_p0(hcnv_seg_plan* plan);
+int  hcnv_seg_plan_p1(hcnv_seg_plan* plan);
+int  hcnv_seg_plan_chain(hcnv_seg_plan* plan, int32_t round);
+int  hcnv_seg_plan_finish(hcnv_seg_plan* plan);
+void hcnv_seg_plan_destroy(hcnv_seg_plan* plan);
 
 /* ---- results download ------------------------------------------------------------------------------ */
 /* One chromosome's results.txt columns (Hmm.java:479-490) from device arrays to host (ideally pinned) arrays, in their

@@ -712,3 +712,32 @@ def test_full_scale_chromosome_bins_against_the_oracle(ctx, cov, W):
         assert len(res) == len(want["bin"]) > 300_000
         for k in ("bin", "start", "end", "n", "median", "total", "mse"):
             np.testing.assert_array_equal(getattr(res, k).cpu().numpy().view(np.uint8), want[k].view(np.uint8), err_msg=k)
+
+
+@pytest.mark.parametrize("W", [1, 3, 10, 50, 64, 100, 250, 1000])
+def test_both_forms_of_the_tile_kernel_agree(ctx, W):
+    """The compact stream goes through the 64-bins-per-warp packed kernel (bin_tile_kernel2.cuh) by default and through the
+    first form (32 bins, 32-bit difference array) with HCNV_BIN_FIRST_FORM: same bins from both, and from the oracle --
+    including a pile-up deep enough (> 8000 records in a tile) to send tiles down the packed kernel's heavy path, gaps, contig
+    ends inside a tile, long blocks that cover whole tiles and long blocks that end inside one."""
+    rng = np.random.default_rng(500 + W)
+    length = int(rng.integers(60 * W + 7, 200 * W + 50)) * 3
+    blocks, sp, sz, obs = _random_contig(rng, length, 3000 + 40 * W, min(150, max(2, 2 * W)), min(200, length // 3), pile=(length // 2, 12000))
+    longs = H.pack_long_blocks([0, length // 3, length // 3 + 5, 10], [length, length // 2, 70 * W, 64 * W])
+    ob = O.pack_blocks(blocks["start0"], blocks["len_mapq"] & 0xFFFFFF)
+    depth, tally = O.depth_from_blocks(ob, length, obs, len(sp))
+    for b in longs:
+        depth[b["start0"] + 1: b["start0"] + 1 + b["len"]] += 1
+    # every long block covers the SNP sites it spans: one 'A' observation each (Mappers.java:248-256)
+    extra = [np.uint32((i << 4) | 1) for b in longs for i in range(len(sp)) if b["start0"] + 1 <= sp[i] <= b["start0"] + b["len"]]
+    obs2 = np.concatenate([obs, np.array(extra, np.uint32)]) if extra else obs
+    for o_ in extra:
+        tally[int(o_) >> 4, 1] += 1
+    want = O.bin_reduce(depth, length, W, sp, sz, tally)
+    cb, an = H.compact_blocks(blocks)
+    co, can = H.compact_obs(obs2)
+    c = H.Contig(length, None, longs, sp, sz, None, cb, an, co, can)
+    got2 = ctx.bin_contigs([c], bin_width=W, max_block_len=255)
+    got1 = ctx.bin_contigs([c], bin_width=W, max_block_len=255, flags=1)
+    assert_bins_equal(got2, want)
+    assert_bins_equal(got1, want)

@@ -70,3 +70,184 @@ def test_gather_over_gloo_world_size_2():
 
 def test_gather_world_size_1_is_identity():
     assert S.gather_summaries({"chr1": dict(n_bins=3)}, 0, 1) == {"chr1": dict(n_bins=3)}
+
+
+# ---------------------------------------------------------------------------------------------- region sharding
+def test_region_partition_tiles_the_genome():
+    import numpy as np
+    shape = synth.hg19_shape()
+    lengths = [c["length"] for c in shape["contigs"]]
+    w = [0] * len(lengths)
+    for refid, _p, l, _mq in shape["baseline_blocks"]:
+        w[refid] += l
+    for W in (100, 50):
+        for world in (1, 2, 3, 4, 8, 16):
+            ranks = S.partition_regions(lengths, w, world, W)
+            assert ranks == S.partition_regions(list(lengths), list(w), world, W) and len(ranks) == world
+            cover = {}
+            for p in ranks:
+                for r in p:
+                    nb = lengths[r.contig] // W + 1
+                    cover.setdefault(r.contig, []).append((r.first_bin, r.first_bin + (r.n_bins or nb - r.first_bin), r.part_index, r.n_parts))
+                    assert r.first_bin % S.TILE_BINS == 0
+            assert sorted(cover) == list(range(len(lengths)))
+            for c, iv in cover.items():
+                assert iv == sorted(iv) and iv[0][0] == 0 and iv[-1][1] == lengths[c] // W + 1
+                assert all(a[1] == b[0] for a, b in zip(iv, iv[1:])) and [x[2] for x in iv] == list(range(len(iv))) and all(x[3] == len(iv) for x in iv)
+            # genome order: rank r's pieces come before rank r + 1's; balanced within 15 % by weight
+            flat = [(r.contig, r.first_bin) for p in ranks for r in p]
+            assert flat == sorted(flat)
+            loads = [sum(w[r.contig] * ((r.n_bins or lengths[r.contig] // W + 1 - r.first_bin) / (lengths[r.contig] // W + 1)) for r in p) for p in ranks]
+            assert max(loads) <= 1.15 * sum(w) / world
+    # a genome of tiny contigs: cuts move to the contig edges, some ranks may stay empty, nothing is lost
+    ranks = S.partition_regions([500, 120000, 700, 90000], [5, 1200, 7, 900], 3, 100)
+    assert sorted((r.contig, r.first_bin) for p in ranks for r in p)[0] == (0, 0) and {r.contig for p in ranks for r in p} == {0, 1, 2, 3}
+
+
+def test_region_views_hold_every_record_that_reaches_the_region():
+    import numpy as np
+    import hadoopcnv_b200 as H
+    rng = np.random.default_rng(8)
+    length = 400_000
+    st = np.sort(rng.integers(0, length - 300, 60000)); ln = rng.integers(1, 256, 60000)
+    cb, an = H.compact_blocks(H.pack_blocks(st, ln))
+    sp = np.unique(rng.integers(1, length, 3000)).astype(np.int32)
+    cov_lo = np.searchsorted(sp, st + 1, side="left"); cov_hi = np.searchsorted(sp, st + ln + 1, side="left")
+    obs = np.concatenate([((np.arange(a, b, dtype=np.uint32) << 4) | 1) for a, b in zip(cov_lo, cov_hi) if b > a]).astype(np.uint32)
+    co, can = H.compact_obs(obs)
+    whole = H.Contig(length, None, None, sp, np.zeros(len(sp), np.int8), None, cb, an, co, can)
+    for reg in (S.Region(0, 0, 1280, 0, 3), S.Region(0, 1280, 1344, 1, 3), S.Region(0, 2624, 0, 2, 3)):
+        c = S.region_contig(whole, reg, 100)
+        r0, r1 = reg.first_bin * 100, ((reg.first_bin + reg.n_bins) * 100 if reg.n_bins else length + 1)
+        got = H.expand_cblocks(c.cblocks, c.anchors)
+        need = (st + 1 < r1) & (st + ln + 1 > r0)                          # blocks that cover a position of [r0, r1)
+        have = set(zip(got["start0"].tolist(), (got["len_mapq"] & 0xFFFFFF).tolist()))
+        assert all((int(s_), int(l_)) in have for s_, l_ in zip(st[need], ln[need]))
+        assert c.cblocks.ctypes.data % 16 == 0 and c.region_first_bin == reg.first_bin and c.region_n_bins == reg.n_bins
+        slo, shi = np.searchsorted(sp, [r0, r1])
+        assert (c.snp_pos1 == sp[slo:shi]).all() and c.snp_index_base == slo
+        sub = H.expand_cobs(c.cobs, c.cobs_anchors)
+        want = obs[((obs >> 4) >= slo) & ((obs >> 4) < shi)]
+        inside = sub[((sub >> 4) >= slo) & ((sub >> 4) < shi)]
+        assert sorted(inside.tolist()) == sorted(want.tolist())            # every observation of the region's sites, each once
+
+
+def _exchange_roundtrip(comm, tensor_of):
+    """The three exchanges of the sharded step on any transport: all-gather of a record, point-to-point row blocks, gather."""
+    import numpy as np
+    r, n = comm.rank, comm.world
+    tab = comm.all_gather_vec(np.arange(5, dtype=np.float64) + 10 * r)
+    assert tab.shape == (n, 5) and all((tab[k] == np.arange(5) + 10 * k).all() for k in range(n))
+    nxt, prv = (r + 1) % n, (r - 1) % n
+    got = tensor_of(np.zeros(3 + prv, np.int32))
+    comm.exchange([(nxt, tensor_of(np.full(3 + r, r, np.int32)))], [(prv, got)])
+    assert (np.asarray(got) == prv).all()
+    blocks = comm.gather_rows(tensor_of(np.full(2 + r, r, np.int32)), [2 + k for k in range(n)])
+    if r == 0:
+        assert [np.asarray(b).tolist() for b in blocks] == [[k] * (2 + k) for k in range(n)]
+    else:
+        assert blocks is None
+
+
+def _gloo_worker(rank, world, port):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _exchange_roundtrip(S.TorchComm(None), lambda a: torch.from_numpy(a))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchanges_over_gloo_world_size_2_and_over_threads():
+    import threading
+    import numpy as np
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    world = S.LocalWorld(3)
+    errs = []
+
+    def run(r):
+        try:
+            _exchange_roundtrip(world.comm(r), lambda a: a)
+        except BaseException as e:                                         # noqa: BLE001
+            errs.append(e)
+            world._bar.abort()
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=60)
+    assert not errs, errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,l1,l2", [(2, 0.01, 1.6), (3, 0.3, 0.4), (4, 0.01, 1.6), (3, -1.0, -1.0), (2, 0.01, 0.004)])
+def test_a_chromosome_cut_across_ranks_equals_the_uncut_one(world, l1, l2):
+    """Region sharding end to end on ONE GPU with `world` virtual ranks (threads, one context each, sharding.LocalWorld): the
+    genome is cut into contiguous pieces, chromosomes that straddle a cut are binned in parts and segmented with the boundary
+    exchange -- bins, scaled depth, calls, final loss must equal the single-rank run bit for bit (incl. auto penalties: the
+    sd is a sequential sum over the whole chromosome; and the lambda2 < .01 rule: no Viterbi at all)."""
+    import threading
+    import numpy as np
+    import torch
+    import hadoopcnv_b200 as H
+    W = 100
+    g = synth.make_genome(coverage=30, scale=0.02, device="cuda", contigs=["chr21", "chr22", "chrX", "chrY"], seed=77)
+    api_c = synth.to_api_contigs(g, compact=True, compact_observations=True)
+    ctx0 = H.Context(0)
+    res = ctx0.bin_contigs(api_c, bin_width=W, max_block_len=150)
+    m32, t32 = ctx0.bins_to_hmm_input(res.mse, res.total)
+    off = [int(x) for x in res.contig_offset]
+    want = ctx0.segment_batch([dict(median=res.median[off[i]:off[i + 1]], mse=m32[off[i]:off[i + 1]], total=t32[off[i]:off[i + 1]], n=res.n[off[i]:off[i + 1]],
+                                    lambda1=l1, lambda2=l2) for i in range(len(g))], flags=H._lib.HCNV_SEG_LATENCY)
+    lengths = [c.length for c in g]
+    ranks = S.partition_regions(lengths, [c.n_reads for c in g], world, W, min_part_bins=S.TILE_BINS)
+    assert any(r.n_parts > 1 for p in ranks for r in p)
+    lw = S.LocalWorld(world)
+    outs, errs = [None] * world, []
+
+    def run(r):
+        try:
+            ctx = H.Context(0)
+            sg = S.ShardedGenome(ctx, lw.comm(r), ranks[r], [S.region_contig(api_c[q.contig], q, W) for q in ranks[r]], len(g), W, 150, l1, l2)
+            for _ in range(2):                                             # a second step on the same object: no state leaks
+                outs[r] = sg.run()
+            torch.cuda.synchronize()
+        except BaseException as e:                                         # noqa: BLE001
+            errs.append(e)
+            lw._bar.abort()
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not errs, errs
+    # bins: the regions in genome order are the whole genome's rows
+    for k in ("bin", "start", "end", "n", "median", "total", "mse"):
+        got = torch.cat([getattr(o.bins, k)[: int(o.row_offset[-1])] for o in outs if o.bins is not None])
+        assert got.shape == getattr(res, k).shape and bool((got.view(torch.uint8) == getattr(res, k).view(torch.uint8)).all()), k
+    state = torch.cat([o.state for o in outs]); scaled = torch.cat([o.scaled for o in outs]); cn = torch.cat([o.cn for o in outs])
+    want_state = torch.cat([w_["state"] for w_ in want]); want_scaled = torch.cat([w_["scaled"] for w_ in want])
+    assert bool((state == want_state).all()) and bool((cn == torch.cat([w_["cn"] for w_ in want])).all())
+    assert bool((scaled.view(torch.int32) == want_scaled.view(torch.int32)).all())
+    assert bool((outs[0].merged_state == want_state.to(torch.int8)).all()) and int(outs[0].merged_rows.sum()) == off[-1]
+    # the chromosome's scalars sit with the rank that holds its last part
+    for r, o in enumerate(outs):
+        for reg, sc in zip(o.regions, o.scalars):
+            w_ = want[reg.contig]
+            assert sc["status"] == w_["status"]
+            assert np.float32(sc["mean_coverage"]).view(np.uint32) == np.float32(w_["mean_coverage"]).view(np.uint32)
+            if reg.part_index == reg.n_parts - 1 and sc["final_loss"] is not None:
+                assert np.float32(sc["final_loss"]).view(np.uint32) == np.float32(w_["final_loss"]).view(np.uint32)
+    ctx0.close()
