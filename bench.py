@@ -45,8 +45,6 @@ def parse_args():
     ap.add_argument("--tile-bins", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true", help="debug: skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--block-format", default="compact", choices=["compact", "records"],
-                    help="compact: 2-byte delta-coded block stream and 2-byte observations (include/hcnv.h hcnv_cblock, hcnv_cobs); records: 8-byte hcnv_block, 4-byte observations")
     ap.add_argument("--bin-kernel", default="v2", choices=["v1", "v2"], help="v2: 64 bins per warp, packed 16-bit pairs (default); v1: the first form")
     ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
     ap.add_argument("--e2e-groups", type=int, default=8, help="tasks (groups of chromosomes) per genome in the end-to-end leg")
@@ -231,7 +229,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import hadoopcnv_b200 as H
-    from hadoopcnv_b200 import synth
+    from hadoopcnv_b200 import sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,51 +244,45 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     W = args.bin_width
+    bin_flags = 1 if args.bin_kernel == "v1" else 0
 
-    # ---- the workload: one 30X hg19-shaped genome, chromosome-sharded across ranks (LPT by non-N bp)
+    # ---- the workload: one 30X hg19-shaped genome, REGION-sharded across the ranks: the genome end to end in `world` contiguous
+    # pieces of equal weight; a chromosome that straddles a cut is binned in parts and segmented with the boundary exchange
     names, w = contig_weights(args.scale)
-    from hadoopcnv_b200 import sharding
-    mine = sharding.partition_contigs(w, world)[rank]
+    shape = synth.hg19_shape()
+    lengths = [max(1000, int(c["length"] * args.scale)) for c in shape["contigs"]]
+    ranks = sharding.partition_regions(lengths, w, world, W)
+    regions = ranks[rank]
+    ids = sorted({r.contig for r in regions})
     t_gen = time.perf_counter()
-    contigs = synth.make_genome(coverage=args.coverage, seed=SEED, device=dev, contigs=[names[i] for i in mine], scale=args.scale)
+    made = synth.make_genome(coverage=args.coverage, seed=SEED, device=dev, contigs=[names[i] for i in ids], scale=args.scale)
+    made = {names.index(c.name): c for c in made}
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
-    compact = args.block_format == "compact"
-    api_dev = synth.to_api_contigs(contigs, compact=compact, compact_observations=compact)     # compact: 2-byte blocks AND 2-byte observations
-    n_cobs = sum(int(a.cobs.shape[0]) for a in api_dev if a.cobs is not None)
-    n_stream = sum(int(a.cblocks.shape[0]) for a in api_dev if a.cblocks is not None) if compact else 0
-    n_reads = sum(c.n_reads for c in contigs)
-    n_blocks = sum(int(c.blocks.shape[0]) for c in contigs)
-    n_long = sum(int(c.long_blocks.shape[0]) for c in contigs)
-    n_snp = sum(int(c.snp_pos1.shape[0]) for c in contigs)
-    n_obs = sum(int(c.obs.shape[0]) for c in contigs)
-    cap = sum(c.length // W + 1 for c in contigs)
+    api_whole = {i: a for i, a in zip(made, synth.to_api_contigs(list(made.values()), compact=True, compact_observations=True))}
+    contigs = [sharding.region_contig(api_whole[r.contig], r, W) for r in regions]        # device views of the region's records
+    # counts of this rank's share (a block / read belongs to the region it starts in)
+    n_reads = n_blocks = n_long = n_snp = n_obs = n_stream = n_cobs = 0
+    for r, c in zip(regions, contigs):
+        sc = made[r.contig]
+        r0 = r.first_bin * W
+        r1 = (r.first_bin + r.n_bins) * W if r.n_bins else sc.length + 1
+        st = sc.blocks[:, 0]
+        nb_ = int(((st + 1 >= r0) & (st + 1 < r1)).sum())
+        n_blocks += nb_
+        n_reads += int(round(sc.n_reads * nb_ / max(1, sc.blocks.shape[0])))
+        n_long += int(sc.long_blocks.shape[0]) if r.part_index == 0 else 0
+        n_snp += 0 if c.snp_pos1 is None else int(c.snp_pos1.shape[0])
+        idx = sc.obs >> 4
+        n_obs += int(((idx >= c.snp_index_base) & (idx < c.snp_index_base + (0 if c.snp_pos1 is None else int(c.snp_pos1.shape[0])))).sum())
+        n_stream += 0 if c.cblocks is None else int(c.cblocks.shape[0])
+        n_cobs += 0 if c.cobs is None else int(c.cobs.shape[0])
 
     ctx = H.Context(local)
-    api_dev_prepared = ctx.prepare_contigs(api_dev)          # resident inputs: the call's input array is built once
-    out = ctx.alloc_bins(cap, True, len(contigs))
-    seg_scaled = torch.empty(cap, dtype=torch.float32, device=dev)
-    seg_state = torch.empty(cap, dtype=torch.int32, device=dev)
-    seg_cn = torch.empty(cap, dtype=torch.int32, device=dev)
-    state = {}
-
-    def hot_path(api_contigs):
-        """One pass of the hot path; inputs may be device tensors (resident) or pinned host arrays (e2e)."""
-        res = ctx.bin_contigs(api_contigs, bin_width=W, max_block_len=READ_LEN, tile_bins=args.tile_bins, out=out, capacity=cap,
-                              flags=1 if args.bin_kernel == "v1" else 0)
-        kms = ctx.kernel_ms()
-        m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total)
-        # one Hmm per non-empty chromosome (row ranges of the same arrays: the problem array is filled by pointer arithmetic)
-        prep, live = ctx.prepare_segments_of_bins(res, m32, t32, LAMBDA1, LAMBDA2, seg_scaled, seg_state, seg_cn)
-        calls = []
-        if live:
-            status, loss = ctx.run_segment_batch(prep, scalars_only=True)
-            calls = [dict(status=int(s_), final_loss=float(l_)) for s_, l_ in zip(status, loss)]
-        kms.update(ctx.kernel_ms())
-        state.update(res=res, m32=m32, t32=t32, calls=calls, kms=kms, calls_by_contig=[(i_, c_["final_loss"]) for i_, c_ in zip(live, calls)])
-        return res, m32, calls
-
+    comm = sharding.TorchComm(dev) if world > 1 else sharding.LocalWorld(1).comm(0)
+    sg = sharding.ShardedGenome(ctx, comm, regions, contigs, len(names), W, READ_LEN, LAMBDA1, LAMBDA2, bin_flags=bin_flags)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    state = {}
 
     def barrier():
         torch.cuda.synchronize()
@@ -316,19 +308,21 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks
         return float(t[0]) / steps, float(t[1]) / steps
 
-    # ---- resident-input leg (value): warm-up, then K timed steps
-    for _ in range(max(args.warmup, 3)):
-        hot_path(api_dev_prepared)
-    clocks = ClockSampler(local)
-    clocks.start()
-    launches0 = ctx.kernel_launches
+    # ---- resident-input leg (value): the rank's records are in HBM; one step = binning of the rank's regions -> text round
+    # trip -> segmentation (with the boundary exchange for cut chromosomes) -> int8 calls of the whole genome gathered to rank 0
     kacc = {}
 
     def step_resident():
-        hot_path(api_dev_prepared)
-        for k_, v in state["kms"].items():
+        state["out"] = sg.run(gather_calls=True)
+        for k_, v in sg.kernel_ms.items():
             kacc.setdefault(k_, []).append(v)
 
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = ctx.kernel_launches
+    kacc.clear()
     ms_dev, ms_wall = timed(step_resident, args.steps)
     launches = ctx.kernel_launches - launches0
     clock_info = clocks.stop()
@@ -342,83 +336,85 @@ def run_b200(args):
     ctx.set_kernel_timing("default")
     if bin_tiles_timed:
         kacc["bin_tiles"] = bin_tiles_timed
-    res = state["res"]
-    n_bins = len(res)
-    final_losses = [float(c["final_loss"]) for c in state["calls"]]
-    # the only exchange of the sharded path: per-chromosome summaries to rank 0 (no data-path collective)
-    local_summary = {contigs[i].name: dict(rank=rank, n_bins=int(res.contig_offset[i + 1] - res.contig_offset[i])) for i in range(len(contigs))}
-    for c_, fl in zip([c for i, c in enumerate(contigs) if res.contig_offset[i + 1] > res.contig_offset[i]], final_losses):
-        local_summary[c_.name]["final_loss"] = fl
+    out = state["out"]
+    res = out.bins
+    off = [int(x) for x in out.row_offset]
+    n_bins = off[-1]
+    # per-chromosome summaries on rank 0 (a chromosome's final loss sits with the rank that holds its last part)
+    local_summary = {}
+    for i, (r, sc_) in enumerate(zip(regions, out.scalars)):
+        d = local_summary.setdefault("%s#%d" % (names[r.contig], r.part_index), dict(rank=rank, n_bins=off[i + 1] - off[i], parts=r.n_parts))
+        if sc_["final_loss"] is not None and r.part_index == r.n_parts - 1:
+            d["final_loss"] = float(sc_["final_loss"])
     summary = sharding.gather_summaries(local_summary, rank, world)
-
-    # cross-rank totals (the only collective: summary statistics)
     tot = torch.tensor([n_reads, n_bins, n_blocks, n_obs, n_snp, launches, n_long], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tot)
     g_reads, g_bins, g_blocks, g_obs, g_snp, g_launches, g_long = [int(x) for x in tot.tolist()]
+    if rank == 0:
+        assert out.merged_state is not None and int(out.merged_state.shape[0]) == g_bins, "the merged calls on rank 0 do not cover the genome"
 
-    # ---- end-to-end leg: the same call with HOST (pinned) buffers; H2D of the inputs and D2H of the results.txt columns inside
+    # ---- end-to-end leg: the same work from HOST (pinned) buffers; H2D of the packed records and D2H of the results.txt columns
+    # inside the timed region.  N = 1: hcnv_genome_run, the C-ABI call that owns the pipeline (continuous upload, worker contexts);
+    # N > 1: every rank uploads its regions' records over its own PCIe link, runs the sharded step and downloads its rows
     e2e = None
     if not args.no_e2e:
-        host_contigs, h2d = [], 0
-        for c in contigs:
-            def pin(t):
-                if t.shape[0] == 0:
-                    return None
-                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                h.copy_(t)
-                return h.numpy()
-            if compact:
-                a = api_dev[len(host_contigs)]
-                hc = H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), None,
-                              pin(a.cblocks) if a.cblocks is not None else None, pin(a.anchors) if a.anchors is not None else None,
-                              pin(a.cobs) if a.cobs is not None else None, pin(a.cobs_anchors) if a.cobs is not None else None)
-                h2d += a.cblocks.numel() * 2 + a.anchors.numel() * 4 if a.cblocks is not None else 0
-                h2d += a.cobs.numel() * 2 + a.cobs_anchors.numel() * 4 if a.cobs is not None else 0
-            else:
-                hc = H.Contig(c.length, pin(c.blocks), pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), pin(c.obs))
-                h2d += c.blocks.numel() * 4
-            host_contigs.append(hc)
-            h2d += c.long_blocks.numel() * 4 + c.snp_pos1.numel() * 4 + c.snp_zyg.numel() + (0 if compact else c.obs.numel() * 4)
+        def pin(t):
+            if t is None or t.shape[0] == 0:
+                return None
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            a_ = h.numpy()
+            return a_.view(np.uint16) if a_.dtype == np.int16 else a_
+        host_contigs = [H.Contig(c.length, None, pin(c.long_blocks), pin(c.snp_pos1), pin(c.snp_zyg), None, pin(c.cblocks), pin(c.anchors), pin(c.cobs),
+                                 pin(c.cobs_anchors), c.region_first_bin, c.region_n_bins, c.snp_index_base) for c in contigs]
         torch.cuda.synchronize()
-        # results.txt columns: start, end, scaled, state, cn, mse[6] (Hmm.java:479-490), per chromosome, into pinned arrays.
-        # The call a user makes: GenomePipeline.run = per chromosome hcnv_bin_contigs -> hcnv_bins_to_hmm_input ->
-        # hcnv_segment_batch -> D2H, on a few worker threads (one Context each) so PCIe runs both ways behind the kernels.
-        from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
-        pipe = GenomePipeline(local, workers=args.e2e_workers, groups=args.e2e_groups)
-        gout = GenomeOutput([c.length for c in contigs], W)
-        cnames = [c.name for c in contigs]
-        d2h = 0
         e2e_state = {}
+        if world == 1:
+            from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
+            pipe = GenomePipeline(local, workers=args.e2e_workers, groups=args.e2e_groups)
+            gout = GenomeOutput([c.length for c in host_contigs], W)
+            prep = pipe.prepare(host_contigs)
+            cnames = [names[r.contig] for r in regions]
+            h2d = sum(int(x.nbytes) for c in host_contigs for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors) if x is not None)
 
-        def step_e2e():
-            nonlocal d2h
-            rs = pipe.run(host_contigs, cnames, gout, bin_width=W, max_block_len=READ_LEN, lambda1=LAMBDA1, lambda2=LAMBDA2)
-            d2h = sum(r.n_bins for r in rs) * gout.bytes_per_bin + int(gout.mse_count.sum()) * gout.bytes_per_mse_row
-            e2e_state["rs"] = rs
+            def step_e2e():
+                e2e_state["rs"] = pipe.run(prep, cnames, gout, bin_width=W, max_block_len=READ_LEN, lambda1=LAMBDA1, lambda2=LAMBDA2, bin_flags=bin_flags)
+            launches_of = lambda: pipe.kernel_launches
+            how = ("pinned host inputs -> hcnv_genome_run (one C-ABI call: continuous upload in 64 MB pieces, %d worker contexts, %d tasks of chromosomes: "
+                   "hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> hcnv_segment_batch -> hcnv_download_results) -> results.txt columns in pinned host "
+                   "arrays (int8 calls, MSE rows listed where non-zero)" % (args.e2e_workers, args.e2e_groups))
+        else:
+            sg.attach_host(host_contigs)
+            h2d = sg.h2d_bytes
 
+            def step_e2e():
+                e2e_state["out"] = sg.run_host(gather_calls=True)
+            launches_of = lambda: ctx.kernel_launches
+            how = ("every rank: pinned host records of its regions -> device (its own PCIe link) -> the region-sharded step (boundary exchange over NCCL, "
+                   "int8 calls gathered to rank 0) -> its rows of the results.txt columns in pinned host arrays")
         for _ in range(2):
             step_e2e()
-        l0 = pipe.kernel_launches
-        n_e2e = args.steps
-        ms_e2e, ms_e2e_wall = timed(step_e2e, n_e2e)
-        e2e_launches = (pipe.kernel_launches - l0) // n_e2e
-        # the end-to-end leg returns the same calls as the resident leg (same inputs): states of every chromosome
-        for i, r in enumerate(e2e_state["rs"]):
-            a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
-            assert r.n_bins == b - a, "e2e / resident bin count mismatch on %s" % r.name
-            got = gout.state[r.offset:r.offset + r.n_bins]
-            assert bool((got == seg_state[a:b].cpu().to(torch.int8)).all()), "e2e / resident state mismatch on %s" % r.name
-            assert (gout.dense_mse(i).view(np.uint32) == state["m32"][a:b].cpu().numpy().view(np.uint32)).all(), "e2e / resident MSE mismatch on %s" % r.name
-        t2 = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+        l0 = launches_of()
+        ms_e2e, ms_e2e_wall = timed(step_e2e, args.steps)
+        e2e_launches = (launches_of() - l0) // args.steps
+        # the end-to-end leg returns the same calls as the resident leg (same inputs)
+        if world == 1:
+            d2h = gout.d2h_bytes()
+            for i, r_ in enumerate(e2e_state["rs"]):
+                a, b = off[i], off[i + 1]
+                assert r_.n_bins == b - a, "e2e / resident bin count mismatch on %s" % r_.name
+                assert bool((gout.state[r_.offset:r_.offset + r_.n_bins] == out.state[a:b].cpu().to(torch.int8)).all()), "e2e / resident state mismatch on %s" % r_.name
+                assert (gout.dense_mse(i).view(np.uint32) == out.mse32[a:b].cpu().numpy().view(np.uint32)).all(), "e2e / resident MSE mismatch on %s" % r_.name
+            pipe.close()
+        else:
+            d2h = sg.d2h_bytes
+            assert bool((sg.h_state[:n_bins] == out.state.cpu().to(torch.int8)).all()), "e2e / resident state mismatch"
+        t2 = torch.tensor([h2d, d2h, e2e_launches], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t2)
         e2e = {"value": g_reads / (ms_e2e_wall / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(t2[0]), "d2h_bytes_per_step": int(t2[1]),
-               "ms_per_step": ms_e2e_wall, "workers": args.e2e_workers, "gpu_launches_per_step": int(e2e_launches),
-               "note": "pinned host inputs -> GenomePipeline.run (per chromosome: hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> "
-                       "hcnv_segment_batch on %d worker contexts) -> results.txt columns in pinned host arrays (int8 calls, MSE rows listed "
-                       "where non-zero)" % args.e2e_workers}
-        pipe.close()
+               "ms_per_step": ms_e2e_wall, "workers": args.e2e_workers if world == 1 else 1, "gpu_launches_per_step": int(t2[2]), "note": how}
 
     # ---- roofline of the dominant kernel (and of the binning kernel), from live CUDA-event timings
     peaks = {}
@@ -429,12 +425,12 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     kavg = {k_: float(np.mean(v)) for k_, v in kacc.items()}
-    # algorithmic bytes per launch: SURVEY.md 8(d)'s per-unit figure x the units of one launch -- 12 B per alignment block
-    # (int32 start, int32 len, uint8 mapq + pad), 4 B per SNP observation, 8 B per SNP site, 72 B per output bin (17 B per read
-    # at 30X).  What the kernel really reads is LESS (bytes_enc: the 2-byte delta-coded stream + anchors, or the 8-byte
-    # records): the encoding is an optimisation of the same algorithmic work; both are reported.
+    # algorithmic bytes per launch: SURVEY.md 8(d)'s per-unit figure x the units of one launch ON THIS RANK -- 12 B per alignment
+    # block (int32 start, int32 len, uint8 mapq + pad), 4 B per SNP observation, 8 B per SNP site, 72 B per output bin (17 B per
+    # read at 30X).  What the kernel really reads is LESS (bytes_enc: the 2-byte delta-coded stream + anchors): the encoding is an
+    # optimisation of the same algorithmic work; both are reported.
     bytes_bin = 12 * (n_blocks + n_long) + 4 * n_obs + 8 * n_snp + 72 * n_bins
-    bytes_enc = (2 * n_stream + 4 * (n_stream // 128) + 2 * n_cobs + 4 * (n_cobs // 256) if compact else 8 * n_blocks + 4 * n_obs) + 16 * n_long + 5 * n_snp + 72 * n_bins
+    bytes_enc = 2 * n_stream + 4 * (n_stream // 128) + 2 * n_cobs + 4 * (n_cobs // 256) + 16 * n_long + 5 * n_snp + 72 * n_bins
     bytes_vit = 36 * n_bins
     # DRAM bytes per launch of the tile kernel: ncu cannot run inside a timed bench, so this is the figure of the committed
     # `ncu --set full` capture of this very command (profiles/bin_tiles_traffic.json names the capture it was read from)
@@ -442,7 +438,7 @@ def run_b200(args):
     try:
         if args.scale == 1.0 and args.coverage == 30.0 and W == 100:
             tj = json.load(open(os.path.join(ROOT, "profiles", "bin_tiles_traffic.json")))
-            ent = tj.get("hg19_30x_wgs/%s/%d" % (args.block_format, world), {})
+            ent = tj.get("hg19_30x_wgs/%s/%d" % (args.bin_kernel, world), {})
             traffic, traffic_src = ent.get("dram_bytes"), ent.get("source")
     except Exception:
         pass
@@ -455,94 +451,111 @@ def run_b200(args):
         return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": traffic if kname == "bin_tiles" else None, "traffic_source": traffic_src if kname == "bin_tiles" else None,
                 "encoded_bytes_per_launch": bytes_enc if kname == "bin_tiles" else None,
-                "frac_of_encoded_bytes": (bytes_enc / (ms * 1e-3) / 1e9 / hbm_peak) if kname == "bin_tiles" else None, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src}
-    # the dominant kernel of THIS rank's step and its own byte model: the binning kernels move SURVEY 8(d)'s binning bytes, every
+                "frac_of_encoded_bytes": (bytes_enc / (ms * 1e-3) / 1e9 / hbm_peak) if kname == "bin_tiles" else None, "ms_per_launch": ms,
+                "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src, "rank": 0}
+    # the dominant kernel of rank 0's step and its own byte model: the binning kernels move SURVEY 8(d)'s binning bytes, every
     # kernel of the segmentation side (text round trip, mean coverage, scale, sd, Viterbi passes, traceback) 36 B per bin
     BIN_KERNELS = ("tile_index", "tally", "bin_tiles", "snp_mse")
     dominant = max(kavg, key=kavg.get) if kavg else None
     roofline = roof(dominant, bytes_bin if dominant in BIN_KERNELS else bytes_vit) if dominant else None
     if roofline is not None and dominant not in BIN_KERNELS:
-        roofline["note"] = "a latency-bound chain kernel of the segmentation side (one warp / one CTA per chromosome): its HBM fraction is not a quality measure, see roofline_segmentation"
+        roofline["note"] = "a latency-bound chain kernel of the segmentation side (one warp / one CTA per chromosome): its HBM fraction is not a quality measure, see roofline_segmentation and roofline_binning"
     roofline_binning = roof("bin_tiles", bytes_bin)
 
     # ---- CPU baseline (rank 0): the oracle on a bounded sample of the same workload, on ONE host core -- the literal
     # restatement (per-base depth loop, like the reference) and its optimised variant (difference array) -- checked against
-    # what the GPU step produced for the same chromosomes; plus the longest chain of this rank against orc_hmm_fast
+    # what the GPU step produced for the same rows; plus the longest chain of this rank against orc_hmm_fast
     cpu_baseline = None
     oracle_checks = {}
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as O
         from oracle import regions as R
         O.build()
-        sample = sorted(range(len(contigs)), key=lambda i: contigs[i].n_reads)[:2]
+        # ~25 Mbp of this rank's genome: whole small chromosomes at N = 1, the head of the rank's first region otherwise
+        whole = [i for i, r in enumerate(regions) if r.n_parts == 1]
+        sample = sorted(whole, key=lambda i: made[regions[i].contig].n_reads)[:2] if len(whole) >= 2 else [0]
         t_cpu, t_opt, s_reads, s_bins = 0.0, 0.0, 0, 0
         for i in sample:
-            c = contigs[i]
-            arrs = (c.blocks.cpu().numpy(), c.long_blocks.cpu().numpy(), c.snp_pos1.cpu().numpy(), c.snp_zyg.cpu().numpy(), c.obs.cpu().numpy())
-            a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
+            r, sc = regions[i], made[regions[i].contig]
+            arrs = (sc.blocks.cpu().numpy(), sc.long_blocks.cpu().numpy(), sc.snp_pos1.cpu().numpy(), sc.snp_zyg.cpu().numpy(), sc.obs.cpu().numpy())
+            r0 = r.first_bin * W
+            r1 = (r.first_bin + r.n_bins) * W if r.n_bins else sc.length + 1
+            if r.n_parts > 1:
+                r1 = min(r1, r0 + 25_000_000 // W * W)
+            a = off[i]
             for fast in (False, True):
                 t0 = time.perf_counter()
-                bb = R.region_bins(*arrs, 0, c.length + 1, W, fast)
+                bb = R.region_bins(*arrs, r0, r1, W, fast)
                 nz = np.flatnonzero(bb["mse"].any(axis=1))
                 m32o = np.zeros(bb["mse"].shape, np.float32)
                 if len(nz):
                     m32o[nz] = O.f64_text_f32(bb["mse"][nz])
-                r = O.hmm(bb["median"], m32o, bb["total"].astype(np.float32), bb["n"], LAMBDA1, LAMBDA2, fast=True)
+                rr = O.hmm(bb["median"], m32o, bb["total"].astype(np.float32), bb["n"], LAMBDA1, LAMBDA2, fast=True)
                 dt = time.perf_counter() - t0
                 if fast:
                     t_opt += dt
                 else:
                     t_cpu += dt
-                # the timed GPU step and the oracle agree on this sample: every bins column and every call, bit for bit
-                assert b - a == len(bb["bin"]), "GPU/oracle bin count mismatch on %s" % c.name
+                # the timed GPU step and the oracle agree on this sample: every bins column, bit for bit (and, for a whole
+                # chromosome, every call)
+                b = a + len(bb["bin"])
+                assert b <= off[i + 1] and (r.n_parts > 1 or b == off[i + 1]), "GPU/oracle bin count mismatch on %s" % sc.name
                 for k_ in ("bin", "start", "end", "n", "median", "total", "mse"):
-                    assert (getattr(res, k_)[a:b].cpu().numpy().view(np.uint8) == bb[k_].view(np.uint8)).all(), "GPU/oracle %s mismatch on %s" % (k_, c.name)
-                assert (seg_state[a:b].cpu().numpy() == r["state"]).all(), "GPU/oracle state mismatch on %s" % c.name
-            s_reads += c.n_reads; s_bins += b - a
-        oracle_checks["sample_bins_and_calls_bit_exact"] = "+".join(contigs[i].name for i in sample)
-        # the longest chromosome of this rank (chr1 at N = 1: 2.4 M markers, loss up to 2^16) against the sequential oracle
-        i = max(range(len(contigs)), key=lambda j: int(res.contig_offset[j + 1] - res.contig_offset[j]))
-        a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
-        r = O.hmm(res.median[a:b].cpu().numpy(), state["m32"][a:b].cpu().numpy(), state["t32"][a:b].cpu().numpy(), res.n[a:b].cpu().numpy(), LAMBDA1, LAMBDA2, fast=True)
-        assert (seg_state[a:b].cpu().numpy() == r["state"]).all() and (seg_scaled[a:b].cpu().numpy().view(np.uint32) == r["scaled"].view(np.uint32)).all(), "GPU/oracle mismatch on %s" % contigs[i].name
-        fl = [c_ for c_ in state["calls_by_contig"] if c_[0] == i][0][1]
-        assert np.float32(fl).view(np.uint32) == np.float32(r["final_loss"]).view(np.uint32), "GPU/oracle final loss mismatch on %s" % contigs[i].name
-        oracle_checks["longest_chain_bit_exact"] = "%s: %d markers, final loss %r" % (contigs[i].name, b - a, float(r["final_loss"]))
+                    assert (getattr(res, k_)[a:b].cpu().numpy().view(np.uint8) == bb[k_].view(np.uint8)).all(), "GPU/oracle %s mismatch on %s" % (k_, sc.name)
+                if r.n_parts == 1:
+                    assert (out.state[a:b].cpu().numpy() == rr["state"]).all(), "GPU/oracle state mismatch on %s" % sc.name
+            nb_ = int(((sc.blocks[:, 0] + 1 >= r0) & (sc.blocks[:, 0] + 1 < r1)).sum())
+            s_reads += int(round(sc.n_reads * nb_ / max(1, sc.blocks.shape[0]))); s_bins += len(bb["bin"])
+        oracle_checks["sample_bins_and_calls_bit_exact"] = "+".join(names[regions[i].contig] for i in sample)
+        # the longest whole chromosome of this rank (2.4 M markers at N = 1, loss up to 2^16) against the sequential oracle
+        if whole:
+            i = max(whole, key=lambda j: off[j + 1] - off[j])
+            a, b = off[i], off[i + 1]
+            rr = O.hmm(res.median[a:b].cpu().numpy(), out.mse32[a:b].cpu().numpy(), res.total[a:b].cpu().numpy().astype(np.float32), res.n[a:b].cpu().numpy(), LAMBDA1, LAMBDA2, fast=True)
+            assert (out.state[a:b].cpu().numpy() == rr["state"]).all() and (out.scaled[a:b].cpu().numpy().view(np.uint32) == rr["scaled"].view(np.uint32)).all(), "GPU/oracle mismatch on %s" % names[regions[i].contig]
+            assert np.float32(out.scalars[i]["final_loss"]).view(np.uint32) == np.float32(rr["final_loss"]).view(np.uint32), "GPU/oracle final loss mismatch"
+            oracle_checks["longest_chain_bit_exact"] = "%s: %d markers, final loss %r" % (names[regions[i].contig], b - a, float(rr["final_loss"]))
         cpu_baseline = {"value": s_reads / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": "%s of the same genome: %d reads, %d bins, %.1f s on one host core" % ("+".join(contigs[i].name for i in sample), s_reads, s_bins, t_cpu),
+                        "sample": "%s of the same genome: %d reads, %d bins, %.1f s on one host core" % ("+".join(names[regions[i].contig] for i in sample), s_reads, s_bins, t_cpu),
                         "bins_per_s": s_bins / t_cpu,
                         "optimised": {"value": s_reads / t_opt, "unit": UNIT, "cores": 1,
                                       "what": "difference array + prefix sum instead of the reference's per-base depth loop; %.1f s" % t_opt}}
 
-    # segmentation side (B2): every kernel of hcnv_bins_to_hmm_input + hcnv_segment_batch.  With 24 chains per genome it is
-    # bound by the latency of the chr1 chain, not by a throughput roofline; both throughput fractions are
+    # segmentation side (B2): every kernel of hcnv_bins_to_hmm_input + the segmentation plan.  With 24 chains per genome it is
+    # bound by the latency of the longest chain, not by a throughput roofline; both throughput fractions are
     # reported so that this is visible: 36 algorithmic bytes and 204 non-FMA FP32 operations per bin.
     SEG_KERNELS = ("text_roundtrip", "mean_coverage", "scale_depth", "sd", "viterbi", "traceback", "vit_p0", "vit_p0c", "vit_p1", "vit_p1b", "vit_p2", "vit_p2b", "vit_p3")
     seg_ms = sum(kavg.get(k_, 0.0) for k_ in SEG_KERNELS)
     roofline_segmentation = None
     if seg_ms:
         fp32_peak = 148 * 128 * 1.965e9
-        roofline_segmentation = {"kernels": [k_ for k_ in SEG_KERNELS if kavg.get(k_)], "ms_per_step": seg_ms, "bound": "latency (24 chains; chr1's chain is the critical path)",
+        roofline_segmentation = {"kernels": [k_ for k_ in SEG_KERNELS if kavg.get(k_)], "ms_per_step": seg_ms, "rank": 0,
+                                 "bound": "latency (24 chains; the longest chromosome's chain is the critical path)",
                                  "hbm": {"achieved": bytes_vit / (seg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_vit / (seg_ms * 1e-3) / 1e9 / hbm_peak,
                                          "algorithmic_bytes_per_bin": 36},
                                  "fp32_issue": {"achieved": 204 * n_bins / (seg_ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12, "unit": "Tops/s (no FMA)",
                                                 "frac": 204 * n_bins / (seg_ms * 1e-3) / fp32_peak, "ops_per_bin": 204},
-                                 "throughput_case": "tools/bench_cohort.py (configs[4]: thousands of chains per call; profiles/r01_v13_cohort_*.json)"}
+                                 "throughput_case": "bench.py --workload cohort (configs[4]: thousands of chains per call)"}
 
     if rank == 0:
+        cut_chroms = sorted({names[r.contig] for p_ in ranks for r in p_ if r.n_parts > 1})
         line = {
             "metric": METRIC, "value": g_reads / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 counts / f32+f64 statistics / f32 Viterbi", "data": "synthetic",
             "config": workload_config(args, world),
             "workload_counts": {"reads": g_reads, "alignment_blocks": g_blocks, "bins": g_bins, "snp_sites": g_snp, "snp_observations": g_obs,
-                                "block_format": args.block_format, "encoded_input_bytes_rank0": bytes_enc},
+                                "block_format": "compact (2-byte blocks, 2-byte observations)", "encoded_input_bytes_rank0": bytes_enc, "bin_kernel": args.bin_kernel,
+                                "chromosomes_cut_across_ranks": cut_chroms},
             "genome_wall_time_s": ms_dev / 1e3, "wall_ms_per_step": ms_wall,
-            "bins_per_s_segmented": g_bins / (seg_ms / 1e3) if seg_ms else None,
-            "reads_per_s_binned": g_reads / (sum(kavg.get(k_, 0) for k_ in ("tile_index", "tally", "bin_tiles")) / 1e3) if kavg.get("bin_tiles") else None,
+            "bins_per_s_segmented": n_bins / (seg_ms / 1e3) if seg_ms else None,
+            "reads_per_s_binned": n_reads / (sum(kavg.get(k_, 0) for k_ in ("tile_index", "tally", "bin_tiles", "snp_mse")) / 1e3) if kavg.get("bin_tiles") else None,
+            "per_rank_note": "bins_per_s_segmented, reads_per_s_binned, kernel_ms and the rooflines are rank 0's share; value and e2e are whole-job",
             "kernel_ms": kavg, "gpu_launches": g_launches, "clocks": clock_info,
             "roofline": roofline, "roofline_binning": roofline_binning, "roofline_segmentation": roofline_segmentation, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "checks": {"oracle": oracle_checks, "final_loss_sum": float(np.sum([v.get("final_loss", 0.0) for v in summary.values()])), "chromosomes": len(summary), "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
+            "checks": {"oracle": oracle_checks, "final_loss_sum": float(np.sum([v.get("final_loss", 0.0) for v in summary.values()])),
+                       "chromosomes": len({k_.split("#")[0] for k_ in summary}), "merged_calls_on_rank0": int(out.merged_state.shape[0]),
+                       "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
         }
         print(json.dumps(line))
     sys.stdout.flush()
@@ -551,7 +564,7 @@ def run_b200(args):
         dist.destroy_process_group()
     # orderly teardown: nothing of torch's may still be queued on the context's stream when the context goes
     ctx.synchronize()
-    del stream
+    del stream, sg
     torch.cuda.synchronize()
     ctx.close()
 

@@ -80,6 +80,12 @@ class SegmentPart(C.Structure):
 HCNV_SEG_AGAIN = 2
 
 
+class GenomeOutput(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("start", C.c_void_p), ("end", C.c_void_p), ("scaled", C.c_void_p), ("state", C.c_void_p), ("cn", C.c_void_p),
+                ("mse_rows", C.c_void_p), ("mse_vals", C.c_void_p), ("row_offset", C.c_void_p), ("n_bins", C.c_void_p), ("n_mse_rows", C.c_void_p),
+                ("mean_coverage", C.c_void_p), ("final_loss", C.c_void_p), ("lambda1_used", C.c_void_p), ("lambda2_used", C.c_void_p), ("status", C.c_void_p)]
+
+
 class Config(C.Structure):
     _fields_ = [("bam_file", C.c_char * 1024), ("vcf_file", C.c_char * 1024),
                 ("run_depth_caller", C.c_int32), ("run_global_sort", C.c_int32), ("init_vcf_lookup", C.c_int32),
@@ -96,6 +102,7 @@ EXPORTS = [
     "hcnv_write_bins_text", "hcnv_write_results_text",
     "hcnv_read_bins_text", "hcnv_bins_text_n_chromosomes", "hcnv_bins_text_get", "hcnv_bins_text_free",
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
+    "hcnv_genome_create", "hcnv_genome_run", "hcnv_genome_kernel_launches", "hcnv_genome_last_error", "hcnv_genome_destroy",
     "hcnv_seg_plan_create", "hcnv_seg_plan_stats", "hcnv_seg_plan_p0", "hcnv_seg_plan_p1", "hcnv_seg_plan_chain", "hcnv_seg_plan_finish", "hcnv_seg_plan_destroy",
     "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
 ]
@@ -153,6 +160,14 @@ def lib():
     L.hcnv_bin_contigs.argtypes = [C.c_void_p, C.POINTER(BinParams), C.c_int32, C.POINTER(ContigInput), C.POINTER(Bins)]
     L.hcnv_bins_to_hmm_input.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hcnv_segment_batch.argtypes = [C.c_void_p, C.c_float, C.c_int32, C.POINTER(SegmentProblem), C.c_int32]
+    L.hcnv_genome_create.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_void_p)]
+    L.hcnv_genome_run.argtypes = [C.c_void_p, C.POINTER(BinParams), C.c_float, C.c_float, C.c_float, C.c_int32, C.POINTER(ContigInput), C.c_int32, C.POINTER(GenomeOutput)]
+    L.hcnv_genome_kernel_launches.argtypes = [C.c_void_p]
+    L.hcnv_genome_kernel_launches.restype = C.c_int64
+    L.hcnv_genome_last_error.argtypes = [C.c_void_p]
+    L.hcnv_genome_last_error.restype = C.c_char_p
+    L.hcnv_genome_destroy.argtypes = [C.c_void_p]
+    L.hcnv_genome_destroy.restype = None
     L.hcnv_seg_plan_create.argtypes = [C.c_void_p, C.c_float, C.c_int32, C.POINTER(SegmentPart), C.c_int32, C.POINTER(C.c_void_p)]
     for f in ("stats", "p0", "p1", "finish"):
         getattr(L, "hcnv_seg_plan_" + f).argtypes = [C.c_void_p]

@@ -1,0 +1,261 @@
+// genome.cu -- one sample end to end behind ONE C-ABI call: what PennCnvSeq.run's three jobs do for a BAM's packed records
+// (PennCnvSeq.java:285-350: depth caller -> binner -> one CnvReducer call per chromosome, Reducers.java:225-243), from HOST
+// buffers to the results.txt columns (Hmm.java:479-490) in HOST buffers.
+//
+// The upload bounds this path (1.4 GB per 30X genome over PCIe), so it never pauses: one copy stream sends every chromosome's
+// packed records, longest chromosome first, into device staging buffers back to back in pieces of 64 MB; the chromosomes are
+// grouped into a few tasks of about equal size, and a worker thread (one hcnv_ctx = one stream + its scratch each, like the task
+// slots of a Hadoop node) takes a task as soon as its records have landed: hcnv_bin_contigs -> hcnv_bins_to_hmm_input ->
+// hcnv_segment_batch on device buffers, then hcnv_download_results per chromosome straight into the caller's arrays -- kernels
+// and downloads run behind the uploads of the tasks after it.  Everything the steady state needs (staging buffers, worker
+// scratch, streams, events) is kept from run to run.
+#include "hcnv_internal.h"
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
+
+struct hcnv_genome {
+    int device = 0;
+    std::vector<hcnv_ctx*> ctx;                   // one per worker
+    cudaStream_t copy = nullptr;
+    std::vector<DevBuf> stage;                    // 9 per contig: blocks, long, snp_pos, snp_zyg, obs, cblocks, anchors, cobs, cobs_anchors
+    std::vector<cudaEvent_t> landed;              // one per contig
+    size_t piece_bytes = (size_t)64 << 20;
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+enum { ST_BLOCKS = 0, ST_LONG, ST_SNPPOS, ST_SNPZYG, ST_OBS, ST_CBLOCKS, ST_ANCHORS, ST_COBS, ST_COBSANC, ST_N };
+
+struct Field { const void* src; size_t bytes; };
+
+void contig_fields(const hcnv_contig_input& c, Field f[ST_N]) {
+    f[ST_BLOCKS]  = { c.blocks, sizeof(hcnv_block) * (size_t)c.n_blocks };
+    f[ST_LONG]    = { c.long_blocks, sizeof(hcnv_long_block) * (size_t)c.n_long };
+    f[ST_SNPPOS]  = { c.snp_pos1, 4 * (size_t)c.n_snp };
+    f[ST_SNPZYG]  = { c.snp_zyg, (size_t)c.n_snp };
+    f[ST_OBS]     = { c.obs, 4 * (size_t)c.n_obs };
+    f[ST_CBLOCKS] = { c.cblocks, sizeof(hcnv_cblock) * (size_t)c.n_cblocks };
+    f[ST_ANCHORS] = { c.anchors, 4 * (size_t)(c.n_cblocks / HCNV_CGROUP) };
+    f[ST_COBS]    = { c.cobs, sizeof(hcnv_cobs) * (size_t)c.n_cobs };
+    f[ST_COBSANC] = { c.cobs_anchors, 4 * (size_t)(c.n_cobs / HCNV_OGROUP) };
+}
+
+int genome_fail(hcnv_genome* g, int code, const std::string& msg) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (g->err.empty()) g->err = msg;
+    return code;
+}
+}  // namespace
+
+extern "C" {
+
+int hcnv_genome_create(int device, int32_t workers, hcnv_genome** out) {
+    if (!out) return HCNV_E_INVALID;
+    *out = nullptr;
+    hcnv_genome* g = new (std::nothrow) hcnv_genome();
+    if (!g) return HCNV_E_NOMEM;
+    g->device = device;
+    const int nw = std::max(1, std::min<int>(workers > 0 ? workers : 4, 16));
+    for (int w = 0; w < nw; ++w) {
+        hcnv_ctx* c = nullptr;
+        int rc = hcnv_ctx_create(device, &c);
+        if (rc) { hcnv_genome_destroy(g); return rc; }
+        g->ctx.push_back(c);
+    }
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&g->copy, cudaStreamNonBlocking) != cudaSuccess) { hcnv_genome_destroy(g); return HCNV_E_CUDA; }
+    *out = g;
+    return HCNV_OK;
+}
+
+void hcnv_genome_destroy(hcnv_genome* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->copy) cudaStreamSynchronize(g->copy);
+    for (hcnv_ctx* c : g->ctx) hcnv_ctx_destroy(c);
+    for (auto& b : g->stage) b.release();
+    for (cudaEvent_t e : g->landed) if (e) cudaEventDestroy(e);
+    if (g->copy) cudaStreamDestroy(g->copy);
+    delete g;
+}
+
+const char* hcnv_genome_last_error(const hcnv_genome* g) { return g ? g->err.c_str() : "null genome"; }
+
+int64_t hcnv_genome_kernel_launches(const hcnv_genome* g) {
+    int64_t n = 0;
+    if (g) for (const hcnv_ctx* c : g->ctx) n += c->launches;
+    return n;
+}
+
+int hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
+                    int32_t n_contigs, const hcnv_contig_input* contigs, int32_t n_groups, hcnv_genome_output* out) {
+    if (!g || n_contigs <= 0 || !contigs || !out) return HCNV_E_INVALID;
+    if (!out->start || !out->end || !out->scaled || !out->state || !out->mse_rows || !out->mse_vals || !out->row_offset || !out->n_bins || !out->n_mse_rows)
+        return genome_fail(g, HCNV_E_INVALID, "null output array");
+    if (cudaSetDevice(g->device) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaSetDevice failed");
+    g->err.clear();
+    hcnv_bin_params P;
+    if (params) P = *params; else hcnv_bin_params_default(&P);
+    const int W = P.bin_width;
+    if (W < 1) return genome_fail(g, HCNV_E_INVALID, "bin_width");
+    // rows of contig c start at the sum of the capacities (length / W + 1: what BinReducer can reach) of the contigs before it
+    std::vector<long long> cap((size_t)n_contigs);
+    long long total_cap = 0, total_len = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+        if (contigs[c].length < 0) return genome_fail(g, HCNV_E_INVALID, "negative contig length");
+        if (contigs[c].region_first_bin || contigs[c].region_n_bins) return genome_fail(g, HCNV_E_INVALID, "hcnv_genome_run takes whole contigs");
+        cap[(size_t)c] = contigs[c].length / W + 1;
+        out->row_offset[c] = total_cap; out->n_bins[c] = 0; out->n_mse_rows[c] = 0;
+        if (out->status) out->status[c] = HCNV_OK;
+        if (out->mean_coverage) out->mean_coverage[c] = 0.f;
+        if (out->final_loss) out->final_loss[c] = 0.f;
+        if (out->lambda1_used) out->lambda1_used[c] = lambda1;
+        if (out->lambda2_used) out->lambda2_used[c] = lambda2;
+        total_cap += cap[(size_t)c]; total_len += contigs[c].length;
+    }
+    if (total_cap > out->capacity) return genome_fail(g, HCNV_E_CAPACITY, "output capacity below the sum of length / bin_width + 1");
+
+    // ---- tasks: the chromosomes longest first, grouped into about n_groups pieces of equal length
+    std::vector<int> order((size_t)n_contigs);
+    for (int c = 0; c < n_contigs; ++c) order[(size_t)c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return contigs[a].length > contigs[b].length; });
+    const int NG = std::max(1, n_groups > 0 ? n_groups : 8);
+    std::vector<std::vector<int>> groups;
+    {
+        std::vector<int> cur; long long acc = 0;
+        for (int c : order) {
+            cur.push_back(c); acc += contigs[c].length;
+            if (acc * NG >= std::max<long long>(total_len, 1) * (long long)(groups.size() + 1)) { groups.push_back(cur); cur.clear(); }
+        }
+        if (!cur.empty()) groups.push_back(cur);
+    }
+    long long max_group_cap = 1;
+    for (auto& gr : groups) { long long s = 0; for (int c : gr) s += cap[(size_t)c]; max_group_cap = std::max(max_group_cap, s); }
+
+    // ---- upload: every chromosome's arrays on one copy stream, in task order, an event per chromosome
+    if (g->stage.size() < (size_t)n_contigs * ST_N) g->stage.resize((size_t)n_contigs * ST_N);
+    while (g->landed.size() < (size_t)n_contigs) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventCreate failed");
+        g->landed.push_back(e);
+    }
+    std::vector<hcnv_contig_input> dev_in((size_t)n_contigs);
+    for (int c : order) {
+        Field f[ST_N];
+        contig_fields(contigs[c], f);
+        void* d[ST_N];
+        for (int k = 0; k < ST_N; ++k) {
+            DevBuf& b = g->stage[(size_t)c * ST_N + k];
+            d[k] = nullptr;
+            if (!f[k].bytes) continue;
+            if (!f[k].src) return genome_fail(g, HCNV_E_INVALID, "null input array with non-zero count");
+            if (b.reserve(f[k].bytes) != cudaSuccess) { cudaGetLastError(); return genome_fail(g, HCNV_E_NOMEM, "staging buffer"); }
+            d[k] = b.p;
+            for (size_t o = 0; o < f[k].bytes; o += g->piece_bytes) {
+                const size_t nb = std::min(g->piece_bytes, f[k].bytes - o);
+                if (cudaMemcpyAsync((char*)b.p + o, (const char*)f[k].src + o, nb, cudaMemcpyHostToDevice, g->copy) != cudaSuccess)
+                    return genome_fail(g, HCNV_E_CUDA, "upload failed");
+            }
+        }
+        if (cudaEventRecord(g->landed[(size_t)c], g->copy) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventRecord failed");
+        hcnv_contig_input& di = dev_in[(size_t)c];
+        di = contigs[c];
+        di.blocks = (const hcnv_block*)d[ST_BLOCKS]; di.long_blocks = (const hcnv_long_block*)d[ST_LONG];
+        di.snp_pos1 = (const int32_t*)d[ST_SNPPOS]; di.snp_zyg = (const int8_t*)d[ST_SNPZYG]; di.obs = (const uint32_t*)d[ST_OBS];
+        di.cblocks = (const hcnv_cblock*)d[ST_CBLOCKS]; di.anchors = (const int32_t*)d[ST_ANCHORS];
+        di.cobs = (const hcnv_cobs*)d[ST_COBS]; di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
+    }
+
+    // ---- workers
+    std::atomic<size_t> next{0};
+    std::atomic<int> worst{HCNV_OK};
+    auto work = [&](int w) {
+        hcnv_ctx* ctx = g->ctx[(size_t)w];
+        cudaSetDevice(g->device);
+        auto fail = [&](int rc, const char* what) {
+            genome_fail(g, rc, std::string(what) + ": " + hcnv_last_error(ctx));
+            int expect = HCNV_OK; worst.compare_exchange_strong(expect, rc);
+        };
+        const size_t C = (size_t)max_group_cap;
+        // per-worker device scratch for the largest group: BinReducer's columns, their float32 twins, the calls
+        if (ctx->buf[G_BINS_I32].reserve(4 * 4 * C + 64) != cudaSuccess || ctx->buf[G_BINS_F32].reserve(4 * C + 64) != cudaSuccess ||
+            ctx->buf[G_BINS_F64].reserve(8 * 7 * C + 64) != cudaSuccess || ctx->buf[G_M32].reserve(4 * 7 * C + 64) != cudaSuccess ||
+            ctx->buf[G_SEG_F32].reserve(4 * C + 64) != cudaSuccess || ctx->buf[G_SEG_I32].reserve(4 * 2 * C + 64) != cudaSuccess) {
+            cudaGetLastError(); ctx->err = "out of device memory"; fail(HCNV_E_NOMEM, "worker scratch"); return;
+        }
+        int32_t* bi = ctx->buf[G_BINS_I32].as<int32_t>();
+        hcnv_bins bins{};
+        bins.capacity = (int64_t)C;
+        bins.bin = bi; bins.start = bi + C; bins.end = bi + 2 * C; bins.n = bi + 3 * C;
+        bins.median = ctx->buf[G_BINS_F32].as<float>();
+        bins.mse = ctx->buf[G_BINS_F64].as<double>(); bins.total = bins.mse + 6 * C;
+        float* m32 = ctx->buf[G_M32].as<float>(); float* t32 = m32 + 6 * C;
+        float* scaled = ctx->buf[G_SEG_F32].as<float>();
+        int32_t* state = ctx->buf[G_SEG_I32].as<int32_t>(); int32_t* cn = state + C;
+        std::vector<hcnv_contig_input> in;
+        std::vector<int64_t> off;
+        std::vector<hcnv_segment_problem> probs;
+        std::vector<int> live;
+        for (;;) {
+            const size_t gi = next.fetch_add(1);
+            if (gi >= groups.size() || worst.load() != HCNV_OK) return;
+            const std::vector<int>& gr = groups[gi];
+            // the group's records are on the device once its last chromosome's event has fired (uploads are in order)
+            if (cudaStreamWaitEvent(ctx->stream, g->landed[(size_t)gr.back()], 0) != cudaSuccess) { ctx->err = "cudaStreamWaitEvent"; fail(HCNV_E_CUDA, "wait"); return; }
+            in.clear();
+            for (int c : gr) in.push_back(dev_in[(size_t)c]);
+            off.assign(gr.size() + 1, 0);
+            bins.contig_offset = off.data();
+            int rc = hcnv_bin_contigs_impl(ctx, &P, (int32_t)gr.size(), in.data(), &bins);
+            if (rc) { fail(rc, "hcnv_bin_contigs"); return; }
+            const int64_t nrows = off[gr.size()];
+            if (nrows == 0) continue;
+            rc = hcnv_bins_to_hmm_input_impl(ctx, nrows, bins.mse, bins.total, m32, t32);
+            if (rc) { fail(rc, "hcnv_bins_to_hmm_input"); return; }
+            probs.clear(); live.clear();
+            for (size_t j = 0; j < gr.size(); ++j) {
+                const int64_t a = off[j], nb = off[j + 1] - off[j];
+                if (nb <= 0) continue;
+                hcnv_segment_problem q{};
+                q.n_markers = nb; q.median = bins.median + a; q.mse = m32 + 6 * a; q.total = t32 + a; q.n = bins.n + a;
+                q.lambda1 = lambda1; q.lambda2 = lambda2; q.scaled = scaled + a; q.state = state + a; q.cn = cn + a;
+                probs.push_back(q); live.push_back((int)j);
+            }
+            rc = hcnv_segment_batch_impl(ctx, alpha, (int32_t)probs.size(), probs.data(), 0);
+            if (rc < 0 && rc != HCNV_E_NO_MINIMUM) { fail(rc, "hcnv_segment_batch"); return; }
+            for (size_t k = 0; k < live.size(); ++k) {
+                const size_t j = (size_t)live[k];
+                const int c = gr[j];
+                const int64_t a = off[j], nb = off[j + 1] - off[j], o = out->row_offset[c];
+                hcnv_results_download d{};
+                d.n = nb; d.start = bins.start + a; d.end = bins.end + a; d.scaled = scaled + a; d.state = state + a; d.cn = cn + a; d.mse = m32 + 6 * a;
+                d.h_start = out->start + o; d.h_end = out->end + o; d.h_scaled = out->scaled + o; d.h_state = out->state + o;
+                d.h_cn = out->cn ? out->cn + o : nullptr;
+                d.h_mse_rows = out->mse_rows + o; d.h_mse_vals = out->mse_vals + 6 * o; d.mse_capacity = nb;
+                rc = hcnv_download_results_impl(ctx, &d);
+                if (rc) { fail(rc, "hcnv_download_results"); return; }
+                out->n_bins[c] = nb; out->n_mse_rows[c] = d.n_mse_rows;
+                const hcnv_segment_problem& q = probs[k];
+                if (out->status) out->status[c] = q.status;
+                if (out->mean_coverage) out->mean_coverage[c] = q.mean_coverage;
+                if (out->final_loss) out->final_loss[c] = q.final_loss;
+                if (out->lambda1_used) out->lambda1_used[c] = q.lambda1_used;
+                if (out->lambda2_used) out->lambda2_used[c] = q.lambda2_used;
+                if (q.status < 0) { int expect = HCNV_OK; worst.compare_exchange_strong(expect, q.status); }
+            }
+        }
+    };
+    const int nw = (int)std::min<size_t>(g->ctx.size(), groups.size());
+    std::vector<std::thread> threads;
+    for (int w = 1; w < nw; ++w) threads.emplace_back(work, w);
+    work(0);
+    for (auto& t : threads) t.join();
+    // the staging buffers may be overwritten by the next run only after every copy of this one is done (they are: every task
+    // waited for its chromosomes' events); a failed run still drains the copy stream before the caller reuses its arrays
+    if (worst.load() != HCNV_OK) cudaStreamSynchronize(g->copy);
+    return worst.load();
+}
+
+}  // extern "C"

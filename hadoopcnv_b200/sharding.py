@@ -318,6 +318,56 @@ class ShardedGenome:
         self.rounds = 1                                  # chain rounds = the largest number of parts of any chromosome (set in run)
         self.kernel_ms = {}
 
+    # ---- the same step from HOST buffers (end to end): upload of the rank's records, the step, download of the rank's rows
+    def attach_host(self, host_contigs):
+        """host_contigs: one Contig of pinned host arrays (numpy) per region, field for field what self.contigs holds on the
+        device (the device arrays become the staging buffers of the upload).  Allocates the rank's pinned output arrays."""
+        torch = self.torch
+        pairs, nbytes = [], 0
+        for h, d in zip(host_contigs, self.contigs):
+            for f in ("long_blocks", "snp_pos1", "snp_zyg", "obs", "cblocks", "anchors", "cobs", "cobs_anchors"):
+                hv, dv = getattr(h, f), getattr(d, f)
+                if dv is None:
+                    continue
+                ht = torch.from_numpy(hv.view(np.int16) if hv.dtype == np.uint16 else (hv.view(np.int32) if hv.dtype == np.uint32 else hv))
+                assert ht.numel() * ht.element_size() == dv.numel() * dv.element_size(), f
+                pairs.append((dv.view(torch.uint8).reshape(-1), ht.view(torch.uint8).reshape(-1)))
+                nbytes += ht.numel() * ht.element_size()
+        self._pairs, self.h2d_bytes = pairs, nbytes
+        self._copy = torch.cuda.Stream(device=self.dev)
+        self._ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
+        n = max(self.cap, 1)
+        pin = lambda dt, *shape: torch.empty(shape, dtype=dt, pin_memory=True)
+        self.h_start, self.h_end, self.h_scaled = pin(torch.int32, n), pin(torch.int32, n), pin(torch.float32, n)
+        self.h_state, self.h_cn = pin(torch.int8, n), pin(torch.int8, n)
+        self.h_mse_rows, self.h_mse_vals = pin(torch.int32, n), pin(torch.float32, n, 6)
+        self.h_mse_count = np.zeros(len(self.regions), np.int64)
+        self.d2h_bytes = 0
+
+    def run_host(self, gather_calls: bool = True) -> "ShardResult":
+        torch = self.torch
+        with torch.cuda.stream(self._copy):
+            for d, h in self._pairs:
+                step = 64 << 20
+                for a in range(0, d.numel(), step):
+                    d[a:a + step].copy_(h[a:a + step], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy)
+        self._ext.wait_event(ev)
+        out = self.run(gather_calls)
+        off = out.row_offset
+        d2h = 0
+        for i in range(len(self.regions)):
+            a, b = int(off[i]), int(off[i + 1])
+            if b > a:
+                k = self.ctx.download_results(out.bins.start[a:b], out.bins.end[a:b], out.scaled[a:b], out.state[a:b], out.cn[a:b], out.mse32[a:b],
+                                              self.h_start[a:b], self.h_end[a:b], self.h_scaled[a:b], self.h_state[a:b], self.h_cn[a:b],
+                                              self.h_mse_rows[a:b], self.h_mse_vals[a:b])
+                self.h_mse_count[i] = k
+                d2h += (b - a) * 14 + k * 28
+        self.d2h_bytes = d2h
+        return out
+
     # ---- helpers
     def _record(self):
         return np.zeros((2, REC), np.float64)

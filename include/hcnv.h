@@ -307,6 +307,33 @@ typedef struct {
 } hcnv_results_download;
 int hcnv_download_results(hcnv_ctx* ctx, hcnv_results_download* d);
 
+/* ---- one sample end to end ---------------------------------------------------------------------------------------- */
+/* What PennCnvSeq.run's jobs do for one BAM's packed records (PennCnvSeq.java:285-350: depth caller -> binner -> one
+ * CnvReducer call per chromosome), in ONE call from host buffers to the results.txt columns (Hmm.java:479-490) in host buffers.
+ * The library owns the copy stream, the device staging buffers and a few worker contexts (threads): the chromosomes' records are
+ * uploaded back to back, longest first, and every task of a few chromosomes runs hcnv_bin_contigs -> hcnv_bins_to_hmm_input ->
+ * hcnv_segment_batch -> hcnv_download_results as soon as its records have landed, behind the uploads of the tasks after it.
+ * Pinned host buffers (cudaHostAlloc / cudaHostRegister) give full PCIe speed; pageable ones work.
+ * Output rows of contig c start at row_offset[c] = sum over the contigs before it of (length / bin_width + 1); n_bins[c] of them
+ * are written.  state / cn are int8; the six MSE columns are listed only for the rows that hold a non-zero value (all six are
+ * 0.0 for every bin without a SNP site): mse_rows[row_offset[c] + k] = row inside the contig, mse_vals[6 * (row_offset[c] + k) ..]
+ * = its six values, k < n_mse_rows[c].  cn and the per-contig scalar arrays may be NULL. */
+typedef struct hcnv_genome hcnv_genome;
+typedef struct {
+    int64_t  capacity;                                   /* rows of the arrays below: >= sum of (length / bin_width + 1) */
+    int32_t* start; int32_t* end; float* scaled; int8_t* state; int8_t* cn;
+    int32_t* mse_rows; float* mse_vals;                  /* capacity and 6 * capacity entries */
+    int64_t* row_offset; int64_t* n_bins; int64_t* n_mse_rows;                       /* n_contigs entries each (out) */
+    float* mean_coverage; float* final_loss; float* lambda1_used; float* lambda2_used; int32_t* status;   /* n_contigs entries each (out) */
+} hcnv_genome_output;
+int         hcnv_genome_create(int device, int32_t workers /* 0: 4 */, hcnv_genome** out);
+int         hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
+                            int32_t n_contigs, const hcnv_contig_input* contigs /* host arrays */, int32_t n_groups /* tasks per genome, 0: 8 */,
+                            hcnv_genome_output* out);
+int64_t     hcnv_genome_kernel_launches(const hcnv_genome* g);
+const char* hcnv_genome_last_error(const hcnv_genome* g);
+void        hcnv_genome_destroy(hcnv_genome* g);
+
 /* ---- B3: config and text layouts -------------------------------------------------------------- */
 typedef struct {
     char    bam_file[1024];
