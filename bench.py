@@ -251,12 +251,14 @@ def run_b200(args):
     names, w = contig_weights(args.scale)
     shape = synth.hg19_shape()
     lengths = [max(1000, int(c["length"] * args.scale)) for c in shape["contigs"]]
+    order = sharding.layout_order(w, world)                       # contigs end to end in this order: cuts fall into small chromosomes
+    names, w, lengths = [names[i] for i in order], [w[i] for i in order], [lengths[i] for i in order]
     ranks = sharding.partition_regions(lengths, w, world, W)
     regions = ranks[rank]
     ids = sorted({r.contig for r in regions})
     t_gen = time.perf_counter()
     made = synth.make_genome(coverage=args.coverage, seed=SEED, device=dev, contigs=[names[i] for i in ids], scale=args.scale)
-    made = {names.index(c.name): c for c in made}
+    made = {names.index(c.name): c for c in made}                 # (indices in layout order)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     api_whole = {i: a for i, a in zip(made, synth.to_api_contigs(list(made.values()), compact=True, compact_observations=True))}

@@ -74,7 +74,7 @@ class SegmentPart(C.Structure):
     _fields_ = [("prob", SegmentProblem), ("n_markers_full", C.c_int64), ("row0", C.c_int64), ("part_index", C.c_int32), ("n_parts", C.c_int32),
                 ("first_vector", C.c_float * 6), ("product_approx", C.c_float * 36), ("start_approx", C.c_double * 6),
                 ("start_exact", C.c_float * 6), ("end_exact", C.c_float * 6), ("sstar", C.c_int32), ("prev_call", C.c_int32),
-                ("irregular", C.c_int32), ("skipped", C.c_int32)]
+                ("irregular", C.c_int32), ("skipped", C.c_int32), ("chain_round", C.c_int32), ("reserved", C.c_int32)]
 
 
 HCNV_SEG_AGAIN = 2

@@ -225,6 +225,7 @@ struct SegDev {
     long long      Mf;
     float*         scaled_f;       // scaled depth of the whole chromosome; scaled = scaled_f + the part's first row
     int            part_index, part_first, part_last;
+    int            chain_round;    // the round of hcnv_seg_plan_chain that walks this problem
     int            m0;             // first local marker of segment 0: 1 on the part that holds marker 0 (Hmm.java:179-181 starts the chain there), else 0
     int            prev_call;      // out: best_state of the row BEFORE the part's first row (traceback of the part's marker 0, Hmm.java:236)
     float          L_in[6];        // exact loss vector in front of the part's first marker (= the previous part's end vector)
@@ -797,6 +798,7 @@ struct hcnv_seg_plan {
         *d_cinfo = nullptr, *d_cbase = nullptr, *d_tiecnt = nullptr, *d_tielist = nullptr;
     float *d_tf = nullptr, *d_ls = nullptr, *d_scan = nullptr;
     int iter = 0;
+    int whole_round = -1;                          // the chain round of the whole chromosomes (hcnv_segment_part::chain_round)
 };
 
 namespace {
@@ -925,6 +927,8 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
         d.M = M; d.Mf = Mf; d.lambda1 = q.lambda1; d.lambda2 = q.lambda2; d.want_sd = q.want_sd;
         d.part_index = pt.part_index; d.part_first = pt.part_index == 0; d.part_last = pt.part_index == pt.n_parts - 1;
         d.m0 = d.part_first ? 1 : 0;
+        d.chain_round = pt.n_parts > 1 ? pt.part_index : pt.chain_round;
+        if (pt.n_parts == 1) { if (pl->whole_round < 0) pl->whole_round = pt.chain_round; else if (pl->whole_round != pt.chain_round) { hcnv_fail(ctx, HCNV_E_INVALID, "every whole chromosome of a plan walks in the same round"); return fail(HCNV_E_INVALID); } }
         d.prev_call = -1;
         d.codes = ctx->buf[H_CODES].as<uint32_t>() + off;
         if (dev) {
@@ -1095,8 +1099,8 @@ int hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round)
 {
     hcnv_ctx* ctx = pl->ctx;
     const int n = pl->n;
-    if (round == 0) {
-        if (!pl->order.empty() && pl->iter == 0) {
+    if (round == std::max(pl->whole_round, 0) && !pl->order.empty() && pl->iter == 0) {
+        {
             // large batches: the many-chains kernel (five chromosomes per warp, longest first)
             HCNV_CUDA(ctx, ctx->buf[H_ORDER].reserve(4 * pl->order.size()));
             int* d_order = ctx->buf[H_ORDER].as<int>();
@@ -1107,6 +1111,8 @@ int hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round)
             HCNV_CUDA(ctx, cudaGetLastError());
             ctx->launches++;
         }
+    }
+    if (round == 0) {
         if (pl->total_segs > 0) {
             const unsigned gc = (unsigned)((pl->NC + 63) / 64);
             KT_BEGIN(ctx, HCNV_K_VIT_P1B);
@@ -1118,7 +1124,7 @@ int hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round)
     if (pl->total_segs > 0) {
         if (round > 0)
             for (int i = 0; i < n; ++i)
-                if (pl->h[i].part_index == round) { for (int c = 0; c < 6; ++c) pl->h[i].L_in[c] = pl->parts[i].start_exact[c]; int rc = push_prob(pl, i); if (rc) return rc; }
+                if (pl->h[i].chain_round == round && !pl->h[i].part_first) { for (int c = 0; c < 6; ++c) pl->h[i].L_in[c] = pl->parts[i].start_exact[c]; int rc = push_prob(pl, i); if (rc) return rc; }
         KT_BEGIN(ctx, HCNV_K_VIT_P2);
         k_vit_p2c<<<n, 32, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->d_cbase, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_force, pl->d_tc, pl->d_cinfo, pl->d_ls, pl->d_repl, round);
         KT_END(ctx, HCNV_K_VIT_P2);
@@ -1131,7 +1137,7 @@ int hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round)
         HCNV_CUDA(ctx, cudaMemcpyAsync(tmp.data(), pl->dprobs, sizeof(SegDev) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         for (int i = 0; i < n; ++i) {
-            if (pl->h[i].part_index != round) continue;
+            if (pl->h[i].chain_round != round) continue;
             hcnv_segment_part& pt = pl->parts[i];
             pl->h[i] = tmp[i];
             for (int c = 0; c < 6; ++c) pt.end_exact[c] = tmp[i].last_row[c];

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(32) k_vit_p2c(SegDev* probs, const int* __rest
     __shared__ __align__(16) int sS[VCH * 72];            // staged segment matrices of one chunk (fallback walk)
     SegDev& P = probs[blockIdx.x];
     if (P.skip || !P.par || P.irregular) return;
-    if (P.part_index != round) return;                    // a later part of a cut chromosome waits for its predecessor's end vector
+    if (P.chain_round != round) return;                   // a later part of a cut chromosome waits for its predecessor's end vector
     const int lane = threadIdx.x, c = lane < 6 ? lane : 0;
     const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
     const float c3 = k.c3[c];

@@ -48,6 +48,23 @@ def partition_contigs(weights: Sequence[float], n_parts: int) -> List[List[int]]
     return [sorted(p) for p in parts]
 
 
+def layout_order(weights: Sequence[float], world: int) -> List[int]:
+    """The order in which the contigs are laid end to end before the genome is cut into `world` pieces (partition_regions): the
+    longest-processing-time groups of whole chromosomes one after the other.  The groups are nearly equal, so an equal-weight
+    cut falls next to a group boundary and moves only a small piece of one chromosome to the neighbouring rank: the chain of a
+    chromosome that is cut runs rank after rank (hcnv_seg_plan_chain rounds), and a short piece costs the least there.  Every
+    rank computes the same order; the merged result is in this order."""
+    groups = partition_contigs(weights, world)
+    # lightest group first: the weight in front of every group boundary is then at most its equal share, so every cut falls AFTER
+    # the boundary, inside the next group's first chromosome -- its head (the small piece) goes to the rank before, and the chain
+    # rounds become "all the small heads" then "the tails together with every whole chromosome"
+    groups = sorted(groups, key=lambda g: (sum(weights[i] for i in g), g))
+    out: List[int] = []
+    for g in groups:
+        out += sorted(g, key=lambda i: (weights[i], i))
+    return out
+
+
 @dataclass(frozen=True)
 class Region:
     """Bins [first_bin, first_bin + n_bins) of contig `contig` (n_bins 0: to the contig's end); the contig is cut into n_parts."""
@@ -187,14 +204,30 @@ class TorchComm:
         self.device = device
 
     def all_gather_vec(self, v: np.ndarray) -> np.ndarray:
-        """One float64 vector per rank -> [world, len] on every rank."""
+        """One float64 vector per rank -> [world, len] on every rank (persistent pinned / device buffers: two small async copies
+        and one all-gather, no allocation)."""
         import torch
-        t = torch.from_numpy(np.ascontiguousarray(v, np.float64))
+        n = int(np.asarray(v).size)
+        buf = getattr(self, "_ag", {}).get(n)
+        if buf is None:
+            if not hasattr(self, "_ag"):
+                self._ag = {}
+            if self.device is not None:
+                buf = (torch.empty(n, dtype=torch.float64, pin_memory=True), torch.empty(n, dtype=torch.float64, device=self.device),
+                       torch.empty(self.world * n, dtype=torch.float64, device=self.device), torch.empty(self.world * n, dtype=torch.float64, pin_memory=True))
+            else:
+                buf = (torch.empty(n, dtype=torch.float64), None, None, torch.empty(self.world * n, dtype=torch.float64))
+            self._ag[n] = buf
+        h_in, d_in, d_out, h_out = buf
+        h_in.numpy()[:] = np.asarray(v, np.float64).ravel()
         if self.device is not None:
-            t = t.to(self.device)
-        out = torch.empty(self.world * t.numel(), dtype=torch.float64, device=t.device)
-        self.dist.all_gather_into_tensor(out, t)
-        return out.cpu().numpy().reshape(self.world, t.numel())
+            d_in.copy_(h_in, non_blocking=True)
+            self.dist.all_gather_into_tensor(d_out, d_in)
+            h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            self.dist.all_gather_into_tensor(h_out, h_in)
+        return h_out.numpy().reshape(self.world, n).copy()
 
     def exchange(self, sends, recvs):
         """sends: [(peer, tensor)], recvs: [(peer, tensor to fill)]: one batch of point-to-point copies."""
@@ -268,8 +301,8 @@ class LocalComm:
 # ---------------------------------------------------------------------------------------------- the sharded step
 # the record every rank contributes to the all-gathers: two slots (slot 0: the part that continues a chromosome from the previous
 # rank, slot 1: the part that begins a chromosome continued on the next rank), REC doubles each
-_F = dict(valid=0, contig=1, part=2, rows=3, irregular=4, skipped=5, sstar=6, prev_call=7, again=8, first=9, prod=15, end=51, status=57)
-REC = 58
+_F = dict(valid=0, contig=1, part=2, rows=3, irregular=4, skipped=5, sstar=6, prev_call=7, again=8, first=9, prod=15, end=51, status=57, nrows=58)
+REC = 59
 
 
 def _min_plus_apply(v: np.ndarray, T: np.ndarray) -> np.ndarray:
@@ -396,6 +429,7 @@ class ShardedGenome:
         cut = [i for i, r in enumerate(regions) if r.n_parts > 1]
         # ---- exchange 1: who holds what (rows of the parts of cut chromosomes)
         rec = self._record()
+        rec[0, _F["nrows"]] = int(off[-1])
         for i in cut:
             s = self.slot_of[i]
             rec[s, _F["valid"]], rec[s, _F["contig"]], rec[s, _F["part"]], rec[s, _F["rows"]] = 1, regions[i].contig, regions[i].part_index, rows[i]
@@ -453,9 +487,11 @@ class ShardedGenome:
                 # parts without rows are dropped from the chain: my part index counts the parts in front of me that have rows
                 idxs = [int(table[self._peer_part(table, me, regions[i], k)[0], self._peer_part(table, me, regions[i], k)[1], _F["rows"]]) > 0 for k in range(regions[i].n_parts)]
                 q.part_index, q.n_parts = int(sum(idxs[: regions[i].part_index])), int(sum(idxs))
+                q.chain_round = q.part_index
             else:
                 q.prob.median, q.prob.total, q.prob.n = _ptr(res.median) + 4 * a, _ptr(t32) + 4 * a, _ptr(res.n) + 4 * a
                 q.n_markers_full, q.row0, q.part_index, q.n_parts = rows[i], 0, 0, 1
+                q.chain_round = rounds - 1                # whole chromosomes walk with the last round: round 0 only sends the (small) heads on
         scal = [dict(mean_coverage=np.float32(0), final_loss=np.float32(0), lambda1=np.float32(self.l1), lambda2=np.float32(self.l2), status=0) for _ in regions]
         any_cut = bool(np.any(table[:, :, _F["valid"]] == 1))
         if live:
@@ -520,7 +556,7 @@ class ShardedGenome:
                                 r_, s_ = prev_live_part(i)
                                 for c_ in range(6):
                                     parts[j].start_exact[c_] = float(t4[r_, s_, _F["end"] + c_])
-                    if rnd == 0 or any(parts[j].part_index == rnd for _, j in my_cut_parts()):
+                    if rnd == 0 or rnd == rounds - 1 or any(parts[j].part_index == rnd for _, j in my_cut_parts()):
                         plan.chain(rnd)
                 if any_cut and comm.world > 1:
                     rec = self._record()
@@ -582,7 +618,7 @@ class ShardedGenome:
         out = ShardResult(regions, off, res, m32, self.scaled[:nrows], self.state[:nrows], self.cn[:nrows], scal)
         # ---- the merge: int8 calls of every rank to rank 0, in genome order (ranks hold consecutive pieces of the genome)
         if gather_calls:
-            counts = comm.all_gather_vec(np.array([nrows], np.float64))[:, 0].astype(np.int64) if comm.world > 1 else np.array([nrows])
+            counts = table[:, 0, _F["nrows"]].astype(np.int64)
             blocks = comm.gather_rows(self.state[:nrows].to(torch.int8), [int(x) for x in counts]) if comm.world > 1 else [self.state[:nrows].to(torch.int8)]
             if blocks is not None:
                 out.merged_state = torch.cat([b_.to(self.dev) for b_ in blocks])

@@ -280,6 +280,9 @@ typedef struct {
     int32_t prev_call;                                  /* out of finish (parts > 0) */
     int32_t irregular;                                  /* out of p0: NaN / negative inputs -- gather the chromosome and use hcnv_segment_batch */
     int32_t skipped;                                    /* out of p0: Hmm.search's rule applies (no Viterbi, all calls 0) */
+    int32_t chain_round;                                /* in: the hcnv_seg_plan_chain round that walks this problem -- part_index for a part; every whole
+                                                           chromosome of the plan the same round (e.g. the last, so that round 0 only sends the small heads on) */
+    int32_t reserved;
 } hcnv_segment_part;
 #define HCNV_SEG_AGAIN 2            /* hcnv_seg_plan_finish: a verification failed, run the chain rounds and finish again */
 typedef struct hcnv_seg_plan hcnv_seg_plan;
