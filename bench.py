@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--tile-bins", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true", help="debug: skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="genome", choices=["genome", "cohort"],
+                    help="genome: BASELINE.json configs[1] / [2] (default); cohort: configs[4], the segmentation-only penalty sweep over precomputed bins")
+    ap.add_argument("--samples", type=int, default=64, help="cohort: samples (64 in the config)")
+    ap.add_argument("--samples-per-call", type=int, default=32, help="cohort: samples per hcnv_segment_batch call")
     ap.add_argument("--bin-kernel", default="v2", choices=["v1", "v2"], help="v2: 64 bins per warp, packed 16-bit pairs (default); v1: the first form")
     ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
     ap.add_argument("--e2e-groups", type=int, default=8, help="tasks (groups of chromosomes) per genome in the end-to-end leg")
@@ -571,9 +575,132 @@ def run_b200(args):
     ctx.close()
 
 
+# --------------------------------------------------------------------------------------------- configs[4]: the cohort sweep
+COHORT_L1 = (0.01, 0.05, 0.1, 0.3)
+COHORT_L2 = (0.4, 0.8, 1.6, 3.2)
+
+
+def run_cohort(args):
+    """BASELINE.json configs[4]: S samples' precomputed bins (independent seeds) x the 16 (ABBERATION_PENALTY, TRANSITION_PENALTY)
+    pairs of SURVEY.md 8(d): the HMM-only rerun of docs/user-guide/startup.md:69.  One step = every sample segmented with every
+    pair (S x 16 x 24 Hmm problems, Hmm.java:341-391, 311-332, 176-238) in ceil(S / samples-per-call) hcnv_segment_batch calls;
+    inputs resident, outputs = the int8 state of every bin under every pair (copy number = cn_arr[state]; the scaled depth does
+    not depend on the penalties).  Unit: one bin under one pair."""
+    import torch
+    import hadoopcnv_b200 as H
+    from hadoopcnv_b200 import synth
+    from hadoopcnv_b200 import _lib as L
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    ctx = H.Context(0)
+    names = [c["name"] for c in synth.hg19_shape()["contigs"]]
+    W = args.bin_width
+    samples = []
+    t_gen = time.perf_counter()
+    for s_ in range(args.samples):
+        contigs = synth.make_genome(coverage=args.coverage, seed=0xC0FFEE + 5 + 1000 * s_, device=dev, contigs=names, scale=args.scale)
+        api = synth.to_api_contigs(contigs, compact=True, compact_observations=True)
+        res = ctx.bin_contigs(api, bin_width=W, max_block_len=READ_LEN)
+        m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total)
+        off = [int(x) for x in res.contig_offset]
+        samples.append(dict(median=res.median[:off[-1]].clone(), mse=m32[:off[-1]].clone(), total=t32[:off[-1]].clone(), n=res.n[:off[-1]].clone(), off=off))
+        del contigs, api, res, m32, t32
+        torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    pairs = [(x, y) for x in COHORT_L1 for y in COHORT_L2]
+    P, S, SC = len(pairs), len(samples), max(1, min(args.samples_per_call, len(samples)))
+    nb = max(s_["off"][-1] for s_ in samples)
+    state8 = torch.empty((S, P, nb), dtype=torch.int8, device=dev)
+    batches = []
+    for s0 in range(0, S, SC):
+        probs = []
+        for si in range(s0, min(S, s0 + SC)):
+            s_ = samples[si]
+            off = s_["off"]
+            for pi, (l1, l2) in enumerate(pairs):
+                for j in range(len(off) - 1):
+                    lo, hi = off[j], off[j + 1]
+                    if hi > lo:
+                        probs.append(dict(median=s_["median"][lo:hi], mse=s_["mse"][lo:hi], total=s_["total"][lo:hi], n=s_["n"][lo:hi], lambda1=l1, lambda2=l2,
+                                          state8=state8[si, pi, lo:hi]))
+        batches.append(ctx.prepare_segment_batch(probs))
+
+    def step():
+        tot = 0.0
+        for prep in batches:
+            status, loss = ctx.run_segment_batch(prep, scalars_only=True)
+            assert (status >= 0).all()
+            tot += float(loss.astype(np.float64).sum())
+        return tot
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    for _ in range(max(1, min(args.warmup, 2))):
+        chk = step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.kernel_launches
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / args.steps
+    ms = e0.elapsed_time(e1) / args.steps
+    clock_info = clocks.stop()
+    launches = (ctx.kernel_launches - l0) // args.steps
+    units = sum(s_["off"][-1] for s_ in samples) * P
+    # spot check against the CPU oracle: one chromosome of the last sample under two pairs, every call
+    from oracle import oracle as O
+    O.build()
+    s_ = samples[-1]
+    j = min(range(len(s_["off"]) - 1), key=lambda k: (s_["off"][k + 1] - s_["off"][k]) if s_["off"][k + 1] > s_["off"][k] else 1 << 60)
+    lo, hi = s_["off"][j], s_["off"][j + 1]
+    for pi in (0, P - 1):
+        r = O.hmm(s_["median"][lo:hi].cpu().numpy(), s_["mse"][lo:hi].cpu().numpy(), s_["total"][lo:hi].cpu().numpy(), s_["n"][lo:hi].cpu().numpy(), pairs[pi][0], pairs[pi][1], fast=True)
+        assert (state8[S - 1, pi, lo:hi].cpu().numpy() == r["state"]).all(), "cohort / oracle mismatch"
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    fp32_peak = 148 * 128 * 1.965e9                                    # non-FMA FP32 lane-operations per second (SURVEY 8(d))
+    ctx.set_kernel_timing("all")
+    step()
+    kms = ctx.kernel_ms()                                              # the last call's kernels
+    ctx.set_kernel_timing("default")
+    print(json.dumps({
+        "metric": "cohort segmentation-only sweep: bins/s Viterbi-segmented (one unit = one bin under one penalty pair)", "value": units / (ms / 1e3), "unit": "bins/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "wall_ms_per_step": 1e3 * wall, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 Viterbi (the reference's evaluation order)", "data": "synthetic",
+        "config": {"workload": "cohort_sweep", "samples": S, "samples_per_call": SC, "penalty_pairs": P, "problems_per_step": S * P * 24, "coverage": args.coverage, "bin_width": W,
+                   "bins_per_sample": samples[0]["off"][-1], "units_per_step": units, "outputs": "int8 state per bin and pair (%.1f GB resident)" % (state8.numel() / 1e9),
+                   "l2": "inputs (%.0f GB) far larger than the 126 MB L2" % (36 * units / P / 1e9)},
+        "gpu_launches": launches, "clocks": clock_info,
+        "roofline": {"kernel": "viterbi_many", "bound": "fp32 issue (no FMA: the reference's order forbids contraction)", "achieved": 204 * units / (ms / 1e3) / 1e12, "peak": fp32_peak / 1e12,
+                     "unit": "Tops/s", "frac": 204 * units / (ms / 1e3) / fp32_peak, "ops_per_unit": 204, "traffic": None,
+                     "hbm": {"achieved": 36 * units / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": 36 * units / (ms / 1e3) / 1e9 / hbm, "algorithmic_bytes_per_unit": 36}},
+        "kernel_ms_last_call": {k_: round(v, 3) for k_, v in kms.items()},
+        "checks": {"final_loss_sum": chk, "oracle": "sample %d %s under pairs %r and %r: calls bit-exact" % (S - 1, names[j], pairs[0], pairs[-1]), "viterbi": ctx.stats(), "input_generation_s": t_gen},
+    }))
+    sys.stdout.flush()
+    ctx.synchronize()
+    del stream
+    torch.cuda.synchronize()
+    ctx.close()
+
+
 if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "cohort":
+        run_cohort(a)
     else:
         run_b200(a)

@@ -66,7 +66,7 @@ class SegmentProblem(C.Structure):
                 ("scaled", C.c_void_p), ("state", C.c_void_p), ("cn", C.c_void_p),
                 ("mean_coverage", C.c_float), ("sd", C.c_float), ("lambda1_used", C.c_float),
                 ("lambda2_used", C.c_float), ("final_loss", C.c_float), ("last_row", C.c_float * 6),
-                ("status", C.c_int32), ("want_sd", C.c_int32)]
+                ("status", C.c_int32), ("want_sd", C.c_int32), ("state8", C.c_void_p)]
 
 
 class SegmentPart(C.Structure):

@@ -339,17 +339,19 @@ class Context:
         for i, q in enumerate(problems):
             med = q["median"]
             M = _len(med)
+            state8 = q.get("state8", None)
             if _is_torch(med):
                 import torch
                 scaled = q.get("scaled", None)
                 state = q.get("state", None)
                 cn = q.get("cn", None)
-                if scaled is None:
-                    scaled = torch.empty(M, dtype=torch.float32, device=med.device)
-                if state is None:
-                    state = torch.empty(M, dtype=torch.int32, device=med.device)
-                if cn is None:
-                    cn = torch.empty(M, dtype=torch.int32, device=med.device)
+                if state8 is None:                       # (with a state8 array the narrow output is all that is asked for)
+                    if scaled is None:
+                        scaled = torch.empty(M, dtype=torch.float32, device=med.device)
+                    if state is None:
+                        state = torch.empty(M, dtype=torch.int32, device=med.device)
+                    if cn is None:
+                        cn = torch.empty(M, dtype=torch.int32, device=med.device)
                 mse, total, n = q["mse"], q["total"], q["n"]
             else:
                 med = np.ascontiguousarray(med, dtype=np.float32)
@@ -357,12 +359,12 @@ class Context:
                 total = np.ascontiguousarray(q["total"], dtype=np.float32)
                 n = np.ascontiguousarray(q["n"], dtype=np.int32)
                 scaled, state, cn = np.empty(M, np.float32), np.empty(M, np.int32), np.empty(M, np.int32)
-            keep.append((med, mse, total, n, scaled, state, cn))
+            keep.append((med, mse, total, n, scaled, state, cn, state8))
             a = arr[i]
             a.n_markers = M
             a.median, a.mse, a.total, a.n = _ptr(med), _ptr(mse), _ptr(total), _ptr(n)
             a.lambda1, a.lambda2 = float(q["lambda1"]), float(q["lambda2"])
-            a.scaled, a.state, a.cn = _ptr(scaled), _ptr(state), _ptr(cn)
+            a.scaled, a.state, a.cn, a.state8 = _ptr(scaled), _ptr(state), _ptr(cn), _ptr(state8)
             a.want_sd = int(q.get("want_sd", 0))
         return arr, keep
 
@@ -403,7 +405,7 @@ class Context:
         res = []
         for i in range(k):
             a = arr[i]
-            res.append(dict(scaled=keep[i][4], state=keep[i][5], cn=keep[i][6], mean_coverage=np.float32(a.mean_coverage),
+            res.append(dict(scaled=keep[i][4], state=keep[i][5], cn=keep[i][6], state8=keep[i][7], mean_coverage=np.float32(a.mean_coverage),
                             sd=np.float32(a.sd), lambda1=np.float32(a.lambda1_used), lambda2=np.float32(a.lambda2_used),
                             final_loss=np.float32(a.final_loss), last_row=np.array(list(a.last_row), np.float32),
                             status=int(a.status)))

@@ -207,6 +207,8 @@ __global__ void k_text_roundtrip_fix(const double* __restrict__ mse, const doubl
 struct SegDev {
     const float*   median; const float* mse; const float* total; const int32_t* n;
     float*         scaled; int32_t* state; int32_t* cn;
+    int8_t*        state8;         // optional narrow copy of `state`
+    int            scaled_shared;  // scaled_f belongs to an earlier problem with the same inputs (k_scale_depth skips this one)
     uint32_t*      codes;          // per marker: traceback[m][c] for c = 0..5, 3 bits each
     long long      M;
     float          lambda1, lambda2;
@@ -301,6 +303,7 @@ __global__ void k_mean_copy(SegDev* probs, int n_probs) {
 __global__ void __launch_bounds__(256) k_scale_depth(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
     const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
     SegDev& P = probs[pi];
+    if (P.scaled_shared) return;                         // an earlier problem with the same inputs fills the array
     const int M = (int)P.Mf;                             // (markers per chromosome fit an int: checked on entry)
     const int i0 = ((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
     const float mean = P.mean;
@@ -623,7 +626,7 @@ __global__ void __launch_bounds__(256) k_traceback(SegDev* probs, const int* __r
     if (P.par && !P.irregular && !P.skip) return;    // k_vit_p3 already wrote the calls
     const int skip = P.skip, s = P.sstar, many = P.many;
     const uint32_t* __restrict__ codes = P.codes;
-    int32_t* __restrict__ o_state = P.state; int32_t* __restrict__ o_cn = P.cn;
+    int32_t* __restrict__ o_state = P.state; int32_t* __restrict__ o_cn = P.cn; int8_t* __restrict__ o_state8 = P.state8;
     const uint32_t* __restrict__ mine = codes + (size_t)s * (size_t)((M + VM_PACK - 1) / VM_PACK);      // column s* of k_viterbi_many's code words
     #pragma unroll
     for (int k = 0; k < SEG_BLK / 256; ++k) {
@@ -640,6 +643,7 @@ __global__ void __launch_bounds__(256) k_traceback(SegDev* probs, const int* __r
         }
         if (o_state) o_state[i] = st;
         if (o_cn) o_cn[i] = c_cn[st];
+        if (o_state8) o_state8[i] = (int8_t)st;
     }
 }
 
@@ -832,6 +836,7 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
             return hcnv_fail(ctx, HCNV_E_INVALID, "parts must tile the chromosome in order");
         if (pt.n_markers_full >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many markers");
         if (!q.median || !q.mse || !q.total || !q.n) return hcnv_fail(ctx, HCNV_E_INVALID, "null input array");
+        if (q.state8 && hcnv_ptr_kind(q.state8) != 2) return hcnv_fail(ctx, HCNV_E_INVALID, "state8 is a device-buffer output");
         if (pt.n_parts > 1) split = true;
         const void* ptrs[7] = { q.median, q.mse, q.total, q.n, q.scaled, q.state, q.cn };
         // (a pointer query costs about a microsecond: every pointer of the first 64 problems, then one input and one output each)
@@ -905,8 +910,32 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
         return e == cudaErrorMemoryAllocation ? HCNV_E_NOMEM : HCNV_E_CUDA;
     };
     int rc;
-    if ((rc = CU(ctx->buf[H_CODES].reserve(4 * (size_t)totM), "codes"))) return fail(rc);
-    if ((rc = CU(ctx->buf[H_SCALED].reserve(4 * (size_t)totMf), "scaled"))) return fail(rc);
+    // traceback codes: one word per marker for the one-warp kernel (and for the segment-parallel path's fallback to it), 6 x
+    // ceil(M / 10) words for the many-chains kernel; scaled depth in scratch: whole chromosomes that gave no output array (one array per distinct
+    // (median, total, n): a penalty sweep's 16 pairs share it) and every part
+    std::vector<size_t> code_off((size_t)n_problems + 1, 0), sc_off((size_t)n_problems, 0);
+    std::vector<int> sc_src((size_t)n_problems, -1);
+    size_t sc_total = 0;
+    {
+        std::map<std::tuple<const void*, const void*, const void*, long long>, int> first_sc;
+        for (int i = 0; i < n_problems; ++i) {
+            const long long M = parts[i].prob.n_markers;
+            const size_t words = route[i] == 2 ? 6 * (size_t)((M + VM_PACK - 1) / VM_PACK) : (size_t)M;      // (a segment-parallel problem with irregular inputs falls back to the one-warp kernel)
+            code_off[(size_t)i + 1] = code_off[(size_t)i] + words;
+            const hcnv_segment_problem& q = parts[i].prob;
+            const bool own = dev && q.scaled && parts[i].n_parts == 1;
+            if (own) continue;
+            if (dev && !q.scaled && parts[i].n_parts == 1) {
+                auto key = std::make_tuple((const void*)q.median, (const void*)q.total, (const void*)q.n, (long long)parts[i].n_markers_full);
+                auto it = first_sc.find(key);
+                if (it != first_sc.end()) { sc_src[(size_t)i] = it->second; continue; }
+                first_sc.emplace(key, i);
+            }
+            sc_off[(size_t)i] = sc_total; sc_total += (size_t)parts[i].n_markers_full;
+        }
+    }
+    if ((rc = CU(ctx->buf[H_CODES].reserve(4 * code_off[(size_t)n_problems] + 64), "codes"))) return fail(rc);
+    if ((rc = CU(ctx->buf[H_SCALED].reserve(4 * sc_total + 64), "scaled"))) return fail(rc);
     if (!dev) {
         if ((rc = CU(ctx->buf[H_IN_F32].reserve(4 * 8 * (size_t)totM), "inputs"))) return fail(rc);     // median, mse*6, total
         if ((rc = CU(ctx->buf[H_IN_I32].reserve(4 * (size_t)totM), "inputs"))) return fail(rc);
@@ -930,13 +959,16 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
         d.chain_round = pt.n_parts > 1 ? pt.part_index : pt.chain_round;
         if (pt.n_parts == 1) { if (pl->whole_round < 0) pl->whole_round = pt.chain_round; else if (pl->whole_round != pt.chain_round) { hcnv_fail(ctx, HCNV_E_INVALID, "every whole chromosome of a plan walks in the same round"); return fail(HCNV_E_INVALID); } }
         d.prev_call = -1;
-        d.codes = ctx->buf[H_CODES].as<uint32_t>() + off;
+        d.codes = ctx->buf[H_CODES].as<uint32_t>() + code_off[(size_t)i];
         if (dev) {
             d.median = q.median; d.mse = q.mse; d.total = q.total; d.n = q.n;
-            // a whole chromosome scales straight into the caller's array; a part keeps the whole chromosome's scaled depth in scratch
-            d.scaled_f = (q.scaled && pt.n_parts == 1) ? q.scaled : ctx->buf[H_SCALED].as<float>() + foff;
+            // a whole chromosome scales straight into the caller's array; without one, problems with the same inputs share one
+            // scratch array; a part keeps the whole chromosome's scaled depth in scratch
+            if (q.scaled && pt.n_parts == 1) d.scaled_f = q.scaled;
+            else if (sc_src[(size_t)i] >= 0) { d.scaled_f = h[(size_t)sc_src[(size_t)i]].scaled_f; d.scaled_shared = 1; }
+            else d.scaled_f = ctx->buf[H_SCALED].as<float>() + sc_off[(size_t)i];
             d.scaled = d.scaled_f + pt.row0;
-            d.state = q.state; d.cn = q.cn;
+            d.state = q.state; d.cn = q.cn; d.state8 = q.state8;
         } else {
             float* f = ctx->buf[H_IN_F32].as<float>();
             float* dm = f + off; float* dmse = f + totM + 6 * off; float* dt = f + 7 * totM + off;
@@ -946,7 +978,7 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
             if ((rc = CU(cudaMemcpyAsync(dt, q.total, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
             if ((rc = CU(cudaMemcpyAsync(dn, q.n, 4 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
             d.median = dm; d.mse = dmse; d.total = dt; d.n = dn;
-            d.scaled_f = ctx->buf[H_SCALED].as<float>() + foff;
+            d.scaled_f = ctx->buf[H_SCALED].as<float>() + sc_off[(size_t)i];
             d.scaled = d.scaled_f;
             d.state = ctx->buf[H_OUT_I32].as<int32_t>() + off;
             d.cn = ctx->buf[H_OUT_I32].as<int32_t>() + totM + off;

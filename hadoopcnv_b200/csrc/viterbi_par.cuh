@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __rest
         else {
             if (P.state) P.state[m - 1] = arg;                       // best_state[m-1] = traceback[m][s*] (Hmm.java:236)
             if (P.cn) P.cn[m - 1] = c_cn[arg];
+            if (P.state8) P.state8[m - 1] = (int8_t)arg;
         }
         #pragma unroll
         for (int c = 0; c < 6; ++c) { L[c] = Ln[c]; mse[c] = msen[c]; }
@@ -525,5 +526,6 @@ __global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __rest
         int st = c_cn[sstar];
         if (P.state) P.state[M - 1] = st;
         if (P.cn) P.cn[M - 1] = c_cn[st];
+        if (P.state8) P.state8[M - 1] = (int8_t)st;
     }
 }

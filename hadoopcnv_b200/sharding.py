@@ -487,7 +487,7 @@ class ShardedGenome:
                 # parts without rows are dropped from the chain: my part index counts the parts in front of me that have rows
                 idxs = [int(table[self._peer_part(table, me, regions[i], k)[0], self._peer_part(table, me, regions[i], k)[1], _F["rows"]]) > 0 for k in range(regions[i].n_parts)]
                 q.part_index, q.n_parts = int(sum(idxs[: regions[i].part_index])), int(sum(idxs))
-                q.chain_round = q.part_index
+                q.chain_round = q.part_index if q.n_parts > 1 else rounds - 1      # (alone after all: it walks with the whole chromosomes)
             else:
                 q.prob.median, q.prob.total, q.prob.n = _ptr(res.median) + 4 * a, _ptr(t32) + 4 * a, _ptr(res.n) + 4 * a
                 q.n_markers_full, q.row0, q.part_index, q.n_parts = rows[i], 0, 0, 1

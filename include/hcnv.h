@@ -244,6 +244,10 @@ typedef struct {
     float          last_row[HCNV_STATES];
     int32_t        status;          /* HCNV_OK, HCNV_VITERBI_SKIPPED or HCNV_E_NO_MINIMUM */
     int32_t        want_sd;
+    /* optional narrow output (may be NULL): best_state as int8 -- all a penalty sweep needs per bin and pair: the copy number is
+     * cn_arr[state] (Hmm.java:35,484) and the scaled depth does not depend on the penalties (Hmm.java:121-135).  Problems of one
+     * call that share median / total / n and ask for no `scaled` output share one scaled-depth array inside the library. */
+    int8_t*        state8;
 } hcnv_segment_problem;
 
 #define HCNV_SEG_SEQUENTIAL 1       /* flags: force the one-warp-per-chromosome exact kernel */

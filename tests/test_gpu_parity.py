@@ -741,3 +741,31 @@ def test_both_forms_of_the_tile_kernel_agree(ctx, W):
     got1 = ctx.bin_contigs([c], bin_width=W, max_block_len=255, flags=1)
     assert_bins_equal(got2, want)
     assert_bins_equal(got1, want)
+
+
+@pytest.mark.parametrize("flags", [0, L.HCNV_SEG_THROUGHPUT, L.HCNV_SEG_LATENCY, L.HCNV_SEG_SEQUENTIAL])
+def test_penalty_sweep_with_int8_states_and_a_shared_scaled_depth(ctx, flags):
+    """The cohort sweep's narrow form (BASELINE.json configs[4]): problems that share median / total / n and ask only for `state8`
+    share ONE scaled-depth array inside the library and write int8 calls; every Viterbi form must fill them like the full
+    outputs and like the oracle (auto penalties included: their sd comes from the shared array)."""
+    import torch
+    rng = np.random.default_rng(91)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    chroms = []
+    for M in (20000, 6001, 90):
+        b = Hp.random_bins(rng, M)
+        chroms.append((b, dev(b["median"]), dev(O.f64_text_f32(b["mse"])), dev(b["total"].astype(np.float32)), dev(b["n"])))
+    pairs = [(0.01, 1.6), (0.3, 0.4), (-1.0, -1.0), (0.05, 3.2), (0.01, 0.004)]
+    probs, outs, wants = [], [], []
+    for b, med, mse, tt, nn in chroms:
+        for l1, l2 in pairs:
+            s8 = torch.full((len(b["median"]),), -7, dtype=torch.int8, device="cuda")
+            probs.append(dict(median=med, mse=mse, total=tt, n=nn, lambda1=l1, lambda2=l2, state8=s8))
+            outs.append(s8)
+            wants.append(O.hmm(b["median"], O.f64_text_f32(b["mse"]), b["total"].astype(np.float32), b["n"], l1, l2, fast=True))
+    gots = ctx.segment_batch(probs, flags=flags)
+    for got, s8, want in zip(gots, outs, wants):
+        assert got["scaled"] is None and got["state"] is None and got["status"] == want["rc"]
+        np.testing.assert_array_equal(s8.cpu().numpy(), want["state"].astype(np.int8))
+        assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
+        assert f32(got["lambda1"]).view(np.uint32) == f32(want["lambda1"]).view(np.uint32)
