@@ -104,7 +104,7 @@ EXPORTS = [
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
     "hcnv_genome_create", "hcnv_genome_run", "hcnv_genome_kernel_launches", "hcnv_genome_last_error", "hcnv_genome_destroy",
     "hcnv_seg_plan_create", "hcnv_seg_plan_stats", "hcnv_seg_plan_p0", "hcnv_seg_plan_p1", "hcnv_seg_plan_chain", "hcnv_seg_plan_finish", "hcnv_seg_plan_destroy",
-    "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_bam_pack", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
+    "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_bam_pack", "hcnv_bam_pack_mt", "hcnv_pack_stats", "hcnv_bam_write_synthetic", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
 ]
 
 _lib = None
@@ -186,6 +186,11 @@ def lib():
     L.hcnv_snp_table_free.argtypes = [C.c_void_p]
     L.hcnv_snp_table_free.restype = None
     L.hcnv_bam_pack.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.hcnv_bam_pack_mt.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.hcnv_bam_write_synthetic.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int32, C.c_uint64,
+                                           C.c_int32, C.POINTER(C.c_int64)]
+    L.hcnv_pack_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.hcnv_pack_stats.restype = None
     L.hcnv_pack_n_contigs.argtypes = [C.c_void_p]
     L.hcnv_pack_n_records.argtypes = [C.c_void_p]
     L.hcnv_pack_n_records.restype = C.c_int64

@@ -13,9 +13,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 struct hcnv_snp_table {
@@ -36,6 +43,9 @@ struct hcnv_pack {
     };
     std::vector<Contig> contigs;
     int64_t n_records = 0, n_unmapped = 0;
+    int64_t bytes_compressed = 0, bytes_inflated = 0;
+    double seconds = 0.0;
+    int threads = 1;
     std::string err;
 };
 
@@ -67,40 +77,6 @@ bool all_acgt_dot(const std::string& s) {
 bool var_type_is_zero(const std::string& ref, const std::string& alt) {
     bool ref_is_n = ref.size() == 1 && (ref[0] == 'N' || ref[0] == 'n');
     if (!ref_is_n && all_acgt_dot(ref) && all_acgt_dot(alt)) return ref.size() == 1 && alt.size() == 1;
-    return true;
-}
-
-// ---- BGZF: concatenated gzip members -----------------------------------------------------------
-bool inflate_all(const std::vector<unsigned char>& in, std::vector<unsigned char>& out, std::string& err) {
-    size_t pos = 0;
-    out.clear();
-    out.reserve(in.size() * 4);
-    std::vector<unsigned char> buf(1 << 16);
-    while (pos < in.size()) {
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (inflateInit2(&zs, 15 + 16) != Z_OK) { err = "inflateInit2 failed"; return false; }
-        zs.next_in = const_cast<unsigned char*>(in.data() + pos);
-        zs.avail_in = (uInt)std::min<size_t>(in.size() - pos, 1u << 30);
-        int rc;
-        do {
-            zs.next_out = buf.data(); zs.avail_out = (uInt)buf.size();
-            rc = inflate(&zs, Z_NO_FLUSH);
-            if (rc != Z_OK && rc != Z_STREAM_END) { inflateEnd(&zs); err = "corrupt BGZF block"; return false; }
-            out.insert(out.end(), buf.data(), buf.data() + (buf.size() - zs.avail_out));
-        } while (rc != Z_STREAM_END);
-        pos = (size_t)(zs.next_in - in.data());
-        inflateEnd(&zs);
-    }
-    return true;
-}
-
-bool read_file(const char* path, std::vector<unsigned char>& data) {
-    FILE* f = fopen(path, "rb");
-    if (!f) return false;
-    unsigned char b[1 << 16]; size_t n;
-    while ((n = fread(b, 1, sizeof b, f)) > 0) data.insert(data.end(), b, b + n);
-    fclose(f);
     return true;
 }
 
@@ -174,121 +150,472 @@ int hcnv_snp_table_get(const hcnv_snp_table* t, int32_t i, const char** name, co
 
 void hcnv_snp_table_free(hcnv_snp_table* t) { delete t; }
 
-int hcnv_bam_pack(const char* bam_path, const hcnv_snp_table* snps, hcnv_pack** out) {
+// ---- streaming BGZF reader -------------------------------------------------------------------------------------------
+// A 30X BAM is ~50 GB compressed and ~150 GB inflated: the file is never held in memory.  A reader thread cuts the file into
+// batches of whole BGZF blocks (the BC extra field gives every block's size without inflating it), a pool of threads inflates
+// the batches (raw deflate per block, each at its own offset: the blocks' ISIZE trailers give the layout), and the calling
+// thread parses the inflated batches IN ORDER -- BAM records straddle block and batch boundaries freely, so a record that is
+// cut at a batch's end is finished from the head of the next one.  The number of batches in flight is bounded.
+namespace {
+
+struct Batch {
+    std::vector<unsigned char> comp;                      // the compressed blocks, back to back
+    std::vector<uint32_t> cdata_off, cdata_len, isize, out_off;
+    std::vector<unsigned char> out;
+    bool done = false, failed = false;
+};
+
+class BgzfPipeline {
+public:
+    BgzfPipeline(FILE* f, int threads) : f_(f), nthreads_(std::max(1, threads)) {
+        limit_ = (size_t)(2 * nthreads_ + 2);
+        reader_ = std::thread([this] { read_loop(); });
+        for (int i = 0; i < nthreads_; ++i) workers_.emplace_back([this] { inflate_loop(); });
+    }
+    ~BgzfPipeline() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        if (reader_.joinable()) reader_.join();
+        for (auto& t : workers_) if (t.joinable()) t.join();
+    }
+    // next inflated batch in file order; nullptr at the end of the file; *bad on a corrupt or non-BGZF file
+    std::shared_ptr<Batch> next(bool* bad) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return !order_.empty() ? order_.front()->done : eof_; });
+        if (order_.empty()) { *bad = reader_failed_; return nullptr; }
+        std::shared_ptr<Batch> b = order_.front();
+        order_.pop_front();
+        --in_flight_;
+        lk.unlock();
+        cv_.notify_all();
+        if (b->failed) { *bad = true; return nullptr; }
+        return b;
+    }
+    int64_t bytes_compressed() const { return bytes_compressed_; }
+
+private:
+    void read_loop() {
+        std::vector<unsigned char> buf;
+        size_t pos = 0;
+        bool file_end = false;
+        auto fill = [&](size_t need) {                     // make buf[pos .. pos + need) available if the file has it
+            if (buf.size() - pos >= need) return true;
+            if (pos > 0) { buf.erase(buf.begin(), buf.begin() + (long)pos); pos = 0; }
+            while (!file_end && buf.size() < need) {
+                const size_t old = buf.size();
+                buf.resize(old + (1u << 20));
+                const size_t n = fread(buf.data() + old, 1, 1u << 20, f_);
+                buf.resize(old + n);
+                if (n == 0) file_end = true;
+            }
+            return buf.size() - pos >= need;
+        };
+        for (;;) {
+            auto b = std::make_shared<Batch>();
+            size_t payload = 0, inflated = 0;
+            bool bad = false;
+            while (payload < (1u << 20)) {
+                if (!fill(18)) { if (buf.size() - pos != 0) bad = true; break; }
+                const unsigned char* h = buf.data() + pos;
+                if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { bad = true; break; }
+                const unsigned xlen = rdu16(h + 10);
+                if (!fill(12 + (size_t)xlen)) { bad = true; break; }
+                h = buf.data() + pos;
+                long bsize = -1;
+                for (unsigned x = 0; x + 4 <= xlen;) {
+                    const unsigned slen = rdu16(h + 12 + x + 2);
+                    if (h[12 + x] == 'B' && h[12 + x + 1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (long)rdu16(h + 12 + x + 4) + 1;
+                    x += 4 + slen;
+                }
+                if (bsize < (long)(12 + xlen + 8)) { bad = true; break; }
+                if (!fill((size_t)bsize)) { bad = true; break; }
+                h = buf.data() + pos;
+                const size_t o = b->comp.size();
+                b->comp.insert(b->comp.end(), h, h + bsize);
+                b->cdata_off.push_back((uint32_t)(o + 12 + xlen));
+                b->cdata_len.push_back((uint32_t)(bsize - 12 - xlen - 8));
+                const uint32_t isz = rdu32(h + bsize - 4);
+                b->isize.push_back(isz);
+                b->out_off.push_back((uint32_t)inflated);
+                inflated += isz;
+                payload += (size_t)bsize;
+                pos += (size_t)bsize;
+            }
+            if (b->comp.empty() && !bad) break;
+            b->out.resize(inflated);
+            bytes_compressed_ += (int64_t)b->comp.size();
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return in_flight_ < limit_ || stop_; });
+                if (stop_) return;
+                if (bad) { reader_failed_ = true; break; }
+                order_.push_back(b); todo_.push_back(b); ++in_flight_;
+            }
+            cv_.notify_all();
+        }
+        { std::lock_guard<std::mutex> lk(mu_); eof_ = true; }
+        cv_.notify_all();
+    }
+    void inflate_loop() {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        const bool zok = inflateInit2(&zs, -15) == Z_OK;
+        for (;;) {
+            std::shared_ptr<Batch> b;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return !todo_.empty() || eof_ || stop_; });
+                if (stop_ || (todo_.empty() && eof_)) break;
+                b = todo_.front(); todo_.pop_front();
+            }
+            bool ok = zok;
+            for (size_t i = 0; ok && i < b->isize.size(); ++i) {
+                if (b->isize[i] == 0) continue;
+                inflateReset(&zs);
+                zs.next_in = b->comp.data() + b->cdata_off[i]; zs.avail_in = b->cdata_len[i];
+                zs.next_out = b->out.data() + b->out_off[i]; zs.avail_out = b->isize[i];
+                const int rc = inflate(&zs, Z_FINISH);
+                ok = rc == Z_STREAM_END && zs.avail_out == 0;
+            }
+            std::vector<unsigned char>().swap(b->comp);
+            { std::lock_guard<std::mutex> lk(mu_); b->done = true; b->failed = !ok; }
+            cv_.notify_all();
+        }
+        if (zok) inflateEnd(&zs);
+    }
+    FILE* f_;
+    int nthreads_;
+    size_t limit_ = 4, in_flight_ = 0;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::shared_ptr<Batch>> order_, todo_;
+    bool eof_ = false, stop_ = false, reader_failed_ = false;
+    std::thread reader_;
+    std::vector<std::thread> workers_;
+    std::atomic<int64_t> bytes_compressed_{0};
+};
+
+// first SNP site at or after `key`, starting from where the previous block of this contig looked (reads come sorted)
+inline size_t snp_seek(const std::vector<int32_t>& sp, size_t hint, int32_t key) {
+    const size_t n = sp.size();
+    size_t lo = std::min(hint, n);
+    if (lo > 0 && sp[lo - 1] >= key) return (size_t)(std::lower_bound(sp.begin(), sp.begin() + (long)lo, key) - sp.begin());
+    for (int steps = 0; lo < n && sp[lo] < key; ++lo)
+        if (++steps > 8) return (size_t)(std::lower_bound(sp.begin() + (long)lo, sp.end(), key) - sp.begin());
+    return lo;
+}
+
+}  // namespace
+
+int hcnv_bam_pack_mt(const char* bam_path, const hcnv_snp_table* snps, int32_t threads, hcnv_pack** out) {
     if (!bam_path || !out) return HCNV_E_INVALID;
     *out = nullptr;
-    std::vector<unsigned char> comp, raw;
-    if (!read_file(bam_path, comp)) return HCNV_E_IO;
-    std::string err;
-    if (!inflate_all(comp, raw, err)) return HCNV_E_PARSE;
-    comp.clear(); comp.shrink_to_fit();
-    const size_t N = raw.size();
-    if (N < 12 || memcmp(raw.data(), "BAM\1", 4) != 0) return HCNV_E_PARSE;
-    size_t off = 4;
-    int32_t l_text = rd32(&raw[off]); off += 4;
-    if (l_text < 0 || off + (size_t)l_text + 4 > N) return HCNV_E_PARSE;
-    off += (size_t)l_text;
-    int32_t n_ref = rd32(&raw[off]); off += 4;
-    if (n_ref < 0) return HCNV_E_PARSE;
+    FILE* f = fopen(bam_path, "rb");
+    if (!f) return HCNV_E_IO;
+    const auto t_start = std::chrono::steady_clock::now();
+    int nthreads = threads > 0 ? threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
     hcnv_pack* P = new hcnv_pack();
-    P->contigs.resize((size_t)n_ref + 1);                    // + the "chr*" pseudo contig (dropped again if it stays empty)
-    for (int32_t i = 0; i < n_ref; ++i) {
-        if (off + 4 > N) { delete P; return HCNV_E_PARSE; }
-        int32_t l_name = rd32(&raw[off]); off += 4;
-        if (l_name < 1 || off + (size_t)l_name + 4 > N) { delete P; return HCNV_E_PARSE; }
-        hcnv_pack::Contig& c = P->contigs[(size_t)i];
-        c.name = chr_prefix(std::string((const char*)&raw[off], (size_t)l_name - 1)); off += (size_t)l_name;
-        c.length = rd32(&raw[off]); off += 4;
-        if (snps) {
-            auto it = snps->index.find(c.name);
-            if (it != snps->index.end()) { c.snp_pos = &snps->pos[(size_t)it->second]; c.snp_zyg = &snps->zyg[(size_t)it->second]; }
-        }
-    }
-    {   // a record without a reference (refID -1) has htsjdk's reference name "*", so the mapper files its alignment
-        // blocks, if its CIGAR has any, under "chr*" (Mappers.java:176-180); the reference's own example/hg19.extra.bam
-        // holds 241 such records (the unplaced hg19 scaffolds).  Its length is the furthest aligned base.
-        hcnv_pack::Contig& c = P->contigs[(size_t)n_ref];
-        c.name = "chr*";
-        if (snps) {
-            auto it = snps->index.find(c.name);
-            if (it != snps->index.end()) { c.snp_pos = &snps->pos[(size_t)it->second]; c.snp_zyg = &snps->zyg[(size_t)it->second]; }
-        }
-    }
-    const int32_t n_slots = n_ref + 1;
-    // per contig: blocks come out in read order; later blocks of a read (after D/N) are held in a small heap until
-    // the read starts catch up, so the stream is emitted sorted by start0 for coordinate-sorted input
-    std::vector<std::priority_queue<PendingBlock, std::vector<PendingBlock>, ByStart>> heaps((size_t)n_slots);
-    std::vector<char> unsorted((size_t)n_slots, 0);
-    std::vector<int32_t> last_emit((size_t)n_slots, -2147483647 - 1);
-    auto emit = [&](hcnv_pack::Contig& c, int ci, const PendingBlock& b) {
-        if (b.start0 < last_emit[(size_t)ci]) unsorted[(size_t)ci] = 1;
-        last_emit[(size_t)ci] = std::max(last_emit[(size_t)ci], b.start0);
-        c.blocks.push_back(hcnv_block{b.start0, b.len_mapq});
-    };
+    P->threads = nthreads;
     int rc = HCNV_OK;
-    while (off + 4 <= N) {
-        int32_t bs = rd32(&raw[off]);
-        if (bs < 32 || off + 4 + (size_t)bs > N) { rc = HCNV_E_PARSE; break; }
-        const unsigned char* r = &raw[off + 4];
-        off += 4 + (size_t)bs;
-        ++P->n_records;
-        int32_t ref_id = rd32(r); const int32_t pos0 = rd32(r + 4);
-        const uint32_t l_read_name = r[8], mapq = r[9];
-        const uint32_t n_cigar = rdu16(r + 12);
-        const int32_t l_seq = rd32(r + 16);
-        if (ref_id >= n_ref || ref_id < -1) { rc = HCNV_E_PARSE; break; }
-        if (ref_id < 0) { ++P->n_unmapped; ref_id = n_ref; }                      // reference name "*" -> "chr*"
-        if (l_seq < 0 || 32 + (size_t)l_read_name + 4 * (size_t)n_cigar + (size_t)((l_seq + 1) / 2) > (size_t)bs) { rc = HCNV_E_PARSE; break; }
-        const unsigned char* cig = r + 32 + l_read_name;
-        const unsigned char* seq = cig + 4 * (size_t)n_cigar;
-        hcnv_pack::Contig& c = P->contigs[(size_t)ref_id];
-        auto& heap = heaps[(size_t)ref_id];
-        while (!heap.empty() && heap.top().start0 <= pos0) { emit(c, ref_id, heap.top()); heap.pop(); }
-        // htsjdk SAMRecord.getAlignmentBlocks: M/=/X make a block; I,S advance the read; D,N advance the reference; H,P nothing
-        int64_t read_base = 1, ref_base = (int64_t)pos0 + 1;
-        bool first_block = true;
-        for (uint32_t k = 0; k < n_cigar; ++k) {
-            const uint32_t v = rdu32(cig + 4 * (size_t)k), op = v & 15u; const int64_t len = v >> 4;
-            if (op == 0 || op == 7 || op == 8) {
-                // observations at the SNP sites this block covers: base = bases[read_base-1+i] or 'A' (Mappers.java:248-256)
-                if (c.snp_pos && !c.snp_pos->empty()) {
-                    const std::vector<int32_t>& sp = *c.snp_pos;
-                    size_t lo = (size_t)(std::lower_bound(sp.begin(), sp.end(), (int32_t)std::min<int64_t>(ref_base, 2147483647)) - sp.begin());
-                    for (size_t s = lo; s < sp.size() && (int64_t)sp[s] < ref_base + len; ++s) {
-                        const int64_t ridx = read_base - 1 + ((int64_t)sp[s] - ref_base);
-                        uint32_t code = 1;                                         // 'A'
-                        if (ridx < (int64_t)l_seq) { const unsigned char byte = seq[ridx >> 1]; code = (ridx & 1) ? (byte & 15u) : (byte >> 4); }
-                        c.obs.push_back((uint32_t)(s << 4) | code);
+    {
+        BgzfPipeline pipe(f, nthreads);
+        // ---- parser state
+        std::vector<unsigned char> carry;                  // the bytes of a header / record that is cut at a batch's end
+        bool header_done = false;
+        int32_t n_ref = 0, n_slots = 0;
+        std::vector<std::priority_queue<PendingBlock, std::vector<PendingBlock>, ByStart>> heaps;
+        std::vector<char> unsorted;
+        std::vector<int32_t> last_emit;
+        std::vector<size_t> snp_hint;
+        auto emit = [&](hcnv_pack::Contig& c, int ci, const PendingBlock& b) {
+            if (b.start0 < last_emit[(size_t)ci]) unsorted[(size_t)ci] = 1;
+            last_emit[(size_t)ci] = std::max(last_emit[(size_t)ci], b.start0);
+            c.blocks.push_back(hcnv_block{b.start0, b.len_mapq});
+        };
+        // the BAM header, once all of it is in `d`: returns its length, 0 if more bytes are needed, -1 if malformed
+        auto parse_header = [&](const unsigned char* d, size_t N) -> long {
+            if (N < 12) return 0;
+            if (memcmp(d, "BAM\1", 4) != 0) return -1;
+            size_t off = 4;
+            const int32_t l_text = rd32(d + off); off += 4;
+            if (l_text < 0) return -1;
+            if (off + (size_t)l_text + 4 > N) return 0;
+            off += (size_t)l_text;
+            const int32_t nr = rd32(d + off); off += 4;
+            if (nr < 0) return -1;
+            std::vector<std::pair<std::string, int32_t>> refs;
+            for (int32_t i = 0; i < nr; ++i) {
+                if (off + 4 > N) return 0;
+                const int32_t l_name = rd32(d + off); off += 4;
+                if (l_name < 1) return -1;
+                if (off + (size_t)l_name + 4 > N) return 0;
+                refs.emplace_back(chr_prefix(std::string((const char*)d + off, (size_t)l_name - 1)), rd32(d + off + (size_t)l_name));
+                off += (size_t)l_name + 4;
+            }
+            n_ref = nr; n_slots = nr + 1;
+            P->contigs.resize((size_t)n_slots);              // + the "chr*" pseudo contig (dropped again if it stays empty)
+            for (int32_t i = 0; i < n_slots; ++i) {
+                hcnv_pack::Contig& c = P->contigs[(size_t)i];
+                // a record without a reference (refID -1) has htsjdk's reference name "*", so the mapper files its alignment
+                // blocks, if its CIGAR has any, under "chr*" (Mappers.java:176-180); the reference's own example/hg19.extra.bam
+                // holds 241 such records (the unplaced hg19 scaffolds).  Its length is the furthest aligned base.
+                c.name = i < nr ? refs[(size_t)i].first : std::string("chr*");
+                c.length = i < nr ? refs[(size_t)i].second : 0;
+                if (snps) {
+                    auto it = snps->index.find(c.name);
+                    if (it != snps->index.end()) { c.snp_pos = &snps->pos[(size_t)it->second]; c.snp_zyg = &snps->zyg[(size_t)it->second]; }
+                }
+            }
+            heaps.resize((size_t)n_slots); unsorted.assign((size_t)n_slots, 0); last_emit.assign((size_t)n_slots, -2147483647 - 1);
+            snp_hint.assign((size_t)n_slots, 0);
+            return (long)off;
+        };
+        // one alignment record (without its block_size word), Mappers.java:174-212 with htsjdk's getAlignmentBlocks rules
+        auto record = [&](const unsigned char* r, int32_t bs) -> int {
+            ++P->n_records;
+            int32_t ref_id = rd32(r); const int32_t pos0 = rd32(r + 4);
+            const uint32_t l_read_name = r[8], mapq = r[9];
+            const uint32_t n_cigar = rdu16(r + 12);
+            const int32_t l_seq = rd32(r + 16);
+            if (ref_id >= n_ref || ref_id < -1) return HCNV_E_PARSE;
+            if (ref_id < 0) { ++P->n_unmapped; ref_id = n_ref; }                      // reference name "*" -> "chr*"
+            if (l_seq < 0 || 32 + (size_t)l_read_name + 4 * (size_t)n_cigar + (size_t)((l_seq + 1) / 2) > (size_t)bs) return HCNV_E_PARSE;
+            const unsigned char* cig = r + 32 + l_read_name;
+            const unsigned char* seq = cig + 4 * (size_t)n_cigar;
+            hcnv_pack::Contig& c = P->contigs[(size_t)ref_id];
+            auto& heap = heaps[(size_t)ref_id];
+            while (!heap.empty() && heap.top().start0 <= pos0) { emit(c, ref_id, heap.top()); heap.pop(); }
+            // htsjdk SAMRecord.getAlignmentBlocks: M/=/X make a block; I,S advance the read; D,N advance the reference; H,P nothing
+            int64_t read_base = 1, ref_base = (int64_t)pos0 + 1;
+            bool first_block = true;
+            for (uint32_t k = 0; k < n_cigar; ++k) {
+                const uint32_t v = rdu32(cig + 4 * (size_t)k), op = v & 15u; const int64_t len = v >> 4;
+                if (op == 0 || op == 7 || op == 8) {
+                    // observations at the SNP sites this block covers: base = bases[read_base-1+i] or 'A' (Mappers.java:248-256)
+                    if (c.snp_pos && !c.snp_pos->empty()) {
+                        const std::vector<int32_t>& sp = *c.snp_pos;
+                        const size_t lo = snp_seek(sp, snp_hint[(size_t)ref_id], (int32_t)std::min<int64_t>(ref_base, 2147483647));
+                        if (first_block) snp_hint[(size_t)ref_id] = lo;
+                        for (size_t s_ = lo; s_ < sp.size() && (int64_t)sp[s_] < ref_base + len; ++s_) {
+                            const int64_t ridx = read_base - 1 + ((int64_t)sp[s_] - ref_base);
+                            uint32_t code = 1;                                         // 'A'
+                            if (ridx < (int64_t)l_seq) { const unsigned char byte = seq[ridx >> 1]; code = (ridx & 1) ? (byte & 15u) : (byte >> 4); }
+                            c.obs.push_back((uint32_t)(s_ << 4) | code);
+                        }
                     }
+                    // split into pieces the packed formats can hold (splitting is results-neutral)
+                    int64_t s0 = ref_base - 1, left = len;
+                    if (len > HCNV_SHORT_MAX) {
+                        while (left > 0) { int64_t piece = std::min<int64_t>(left, 0x7fffffff); c.longs.push_back(hcnv_long_block{(int32_t)s0, (int32_t)piece, (int32_t)mapq, 0}); s0 += piece; left -= piece; }
+                    } else if (len > 0) {
+                        PendingBlock b{(int32_t)s0, (uint32_t)len | (mapq << 24)};
+                        c.max_len = std::max<int32_t>(c.max_len, (int32_t)len);
+                        if (first_block) emit(c, ref_id, b); else heap.push(b);
+                        first_block = false;
+                    }
+                    read_base += len; ref_base += len;
+                    if (ref_id == n_ref) c.length = (int32_t)std::max<int64_t>(c.length, std::min<int64_t>(ref_base - 1, 2147483647));
+                } else if (op == 1 || op == 4) read_base += len;        // I, S
+                else if (op == 2 || op == 3) ref_base += len;           // D, N
+                // H (5), P (6): nothing
+            }
+            return HCNV_OK;
+        };
+        for (;;) {
+            bool bad = false;
+            std::shared_ptr<Batch> b = pipe.next(&bad);
+            if (!b) { if (bad) rc = HCNV_E_PARSE; break; }
+            P->bytes_inflated += (int64_t)b->out.size();
+            const unsigned char* d = b->out.data();
+            size_t N = b->out.size(), off = 0;
+            if (!header_done) {                              // (headers are small: gather bytes until the whole header is there)
+                carry.insert(carry.end(), d, d + N);
+                const long hl = parse_header(carry.data(), carry.size());
+                if (hl < 0) { rc = HCNV_E_PARSE; break; }
+                if (hl == 0) continue;
+                header_done = true;
+                std::vector<unsigned char> rest(carry.begin() + hl, carry.end());
+                carry.swap(rest);
+                // the rest of the gathered bytes are records: parse them out of `carry`, keep what is cut
+                size_t o = 0;
+                while (o + 4 <= carry.size()) {
+                    const int32_t bs = rd32(carry.data() + o);
+                    if (bs < 32) { rc = HCNV_E_PARSE; break; }
+                    if (o + 4 + (size_t)bs > carry.size()) break;
+                    if ((rc = record(carry.data() + o + 4, bs))) break;
+                    o += 4 + (size_t)bs;
                 }
-                // split into pieces the packed formats can hold (splitting is results-neutral)
-                int64_t s0 = ref_base - 1, left = len;
-                if (len > HCNV_SHORT_MAX) {
-                    while (left > 0) { int64_t piece = std::min<int64_t>(left, 0x7fffffff); c.longs.push_back(hcnv_long_block{(int32_t)s0, (int32_t)piece, (int32_t)mapq, 0}); s0 += piece; left -= piece; }
-                } else if (len > 0) {
-                    PendingBlock b{(int32_t)s0, (uint32_t)len | (mapq << 24)};
-                    c.max_len = std::max<int32_t>(c.max_len, (int32_t)len);
-                    if (first_block) emit(c, ref_id, b); else heap.push(b);
-                    first_block = false;
-                }
-                read_base += len; ref_base += len;
-                if (ref_id == n_ref) c.length = (int32_t)std::max<int64_t>(c.length, std::min<int64_t>(ref_base - 1, 2147483647));
-            } else if (op == 1 || op == 4) read_base += len;        // I, S
-            else if (op == 2 || op == 3) ref_base += len;           // D, N
-            // H (5), P (6): nothing
+                if (rc) break;
+                carry.erase(carry.begin(), carry.begin() + (long)o);
+                continue;
+            }
+            if (!carry.empty()) {                            // finish the record that was cut at the previous batch's end
+                while (carry.size() < 4 && off < N) carry.push_back(d[off++]);
+                if (carry.size() < 4) continue;
+                const int32_t bs = rd32(carry.data());
+                if (bs < 32) { rc = HCNV_E_PARSE; break; }
+                const size_t need = 4 + (size_t)bs - carry.size();
+                const size_t take = std::min(need, N - off);
+                carry.insert(carry.end(), d + off, d + off + take);
+                off += take;
+                if (carry.size() < 4 + (size_t)bs) continue;
+                if ((rc = record(carry.data() + 4, bs))) break;
+                carry.clear();
+            }
+            while (off + 4 <= N) {
+                const int32_t bs = rd32(d + off);
+                if (bs < 32) { rc = HCNV_E_PARSE; break; }
+                if (off + 4 + (size_t)bs > N) break;
+                if ((rc = record(d + off + 4, bs))) break;
+                off += 4 + (size_t)bs;
+            }
+            if (rc) break;
+            carry.assign(d + off, d + N);
+        }
+        if (!rc && (!header_done || !carry.empty())) rc = HCNV_E_PARSE;       // truncated file
+        P->bytes_compressed = pipe.bytes_compressed();
+        if (!rc) {
+            for (int32_t i = 0; i < n_slots; ++i) {
+                hcnv_pack::Contig& c = P->contigs[(size_t)i];
+                auto& heap = heaps[(size_t)i];
+                while (!heap.empty()) { emit(c, i, heap.top()); heap.pop(); }
+                if (unsorted[(size_t)i])                                     // input was not coordinate-sorted: sort now
+                    std::stable_sort(c.blocks.begin(), c.blocks.end(), [](const hcnv_block& a, const hcnv_block& b2) { return a.start0 < b2.start0; });
+            }
+            if (!P->contigs.empty() && P->contigs.back().blocks.empty() && P->contigs.back().longs.empty()) P->contigs.pop_back();
         }
     }
+    fclose(f);
     if (rc) { delete P; return rc; }
-    for (int32_t i = 0; i < n_slots; ++i) {
-        hcnv_pack::Contig& c = P->contigs[(size_t)i];
-        auto& heap = heaps[(size_t)i];
-        while (!heap.empty()) { emit(c, i, heap.top()); heap.pop(); }
-        if (unsorted[(size_t)i])                                     // input was not coordinate-sorted: sort now
-            std::stable_sort(c.blocks.begin(), c.blocks.end(), [](const hcnv_block& a, const hcnv_block& b) { return a.start0 < b.start0; });
-    }
-    if (P->contigs.back().blocks.empty() && P->contigs.back().longs.empty()) P->contigs.pop_back();
+    P->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     *out = P;
     return HCNV_OK;
+}
+
+int hcnv_bam_pack(const char* bam_path, const hcnv_snp_table* snps, hcnv_pack** out) { return hcnv_bam_pack_mt(bam_path, snps, 0, out); }
+
+void hcnv_pack_stats(const hcnv_pack* p, double out[5]) {
+    if (!p || !out) return;
+    out[0] = (double)p->n_records; out[1] = (double)p->bytes_compressed; out[2] = (double)p->bytes_inflated; out[3] = p->seconds; out[4] = (double)p->threads;
+}
+
+// ---- synthetic BAM writer (tests and tools/bench_packer.py: the packer needs inputs of real size and there is no network) ------
+namespace {
+struct Xs { uint64_t s; uint64_t next() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; } double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); } };
+
+int reg2bin(int64_t beg, int64_t end) {                     // SAM specification, section 5.3
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+// BGZF blocks of `data`, compressed by `threads` threads, appended to the file in order
+bool write_bgzf(FILE* f, const std::vector<unsigned char>& data, int threads, int level) {
+    const size_t BLK = 0xff00;
+    const size_t nb = (data.size() + BLK - 1) / BLK;
+    std::vector<std::vector<unsigned char>> outs(nb);
+    std::atomic<size_t> next{0};
+    std::atomic<bool> ok{true};
+    auto work = [&]() {
+        z_stream zs;
+        std::vector<unsigned char> tmp(BLK + 1024);
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= nb) break;
+            const size_t o = i * BLK, n = std::min(BLK, data.size() - o);
+            memset(&zs, 0, sizeof zs);
+            if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; break; }
+            zs.next_in = const_cast<unsigned char*>(data.data() + o); zs.avail_in = (uInt)n;
+            zs.next_out = tmp.data(); zs.avail_out = (uInt)tmp.size();
+            const int rc = deflate(&zs, Z_FINISH);
+            const size_t clen = tmp.size() - zs.avail_out;
+            deflateEnd(&zs);
+            if (rc != Z_STREAM_END || clen + 26 > 65536) { ok = false; break; }
+            std::vector<unsigned char>& b = outs[i];
+            b.resize(18 + clen + 8);
+            const unsigned char hdr[12] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0};
+            memcpy(b.data(), hdr, 12);
+            b[12] = 'B'; b[13] = 'C'; b[14] = 2; b[15] = 0;
+            const uint16_t bsize = (uint16_t)(b.size() - 1);
+            memcpy(b.data() + 16, &bsize, 2);
+            memcpy(b.data() + 18, tmp.data(), clen);
+            const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), data.data() + o, (uInt)n), isz = (uint32_t)n;
+            memcpy(b.data() + 18 + clen, &crc, 4); memcpy(b.data() + 22 + clen, &isz, 4);
+        }
+    };
+    std::vector<std::thread> ts;
+    for (int t = 1; t < std::max(1, threads); ++t) ts.emplace_back(work);
+    work();
+    for (auto& t : ts) t.join();
+    if (!ok) return false;
+    for (auto& b : outs) if (fwrite(b.data(), 1, b.size(), f) != b.size()) return false;
+    return true;
+}
+}  // namespace
+
+// Writes a coordinate-sorted BAM of random reads: per reference n_reads[r] reads of read_len bases with uniform starts, the CIGAR
+// mix of SURVEY.md 8(d) (90 % <len>M, 2.5 % one 1-10 bp insertion, 2.5 % one 1-10 bp deletion, 5 % a 5-30 bp soft clip), random
+// bases, MAPQ 60 for 90 % of the reads.  stats[0..2] = records, alignment blocks, aligned bases.  Returns 0 or a status.
+int hcnv_bam_write_synthetic(const char* path, int32_t n_ref, const char* const* names, const int32_t* lengths, const int64_t* n_reads,
+                             int32_t read_len, uint64_t seed, int32_t threads, int64_t stats[3]) {
+    if (!path || n_ref <= 0 || !names || !lengths || !n_reads || read_len < 40 || read_len > 1000) return HCNV_E_INVALID;
+    FILE* f = fopen(path, "wb");
+    if (!f) return HCNV_E_IO;
+    const int nt = threads > 0 ? threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<unsigned char> buf;
+    auto put32 = [&](int32_t v) { unsigned char b[4]; memcpy(b, &v, 4); buf.insert(buf.end(), b, b + 4); };
+    std::string text = "@HD\tVN:1.4\tSO:coordinate\n";
+    for (int r = 0; r < n_ref; ++r) text += std::string("@SQ\tSN:") + names[r] + "\tLN:" + std::to_string(lengths[r]) + "\n";
+    buf.insert(buf.end(), {'B', 'A', 'M', 1});
+    put32((int32_t)text.size()); buf.insert(buf.end(), text.begin(), text.end());
+    put32(n_ref);
+    for (int r = 0; r < n_ref; ++r) { const size_t l = strlen(names[r]) + 1; put32((int32_t)l); buf.insert(buf.end(), names[r], names[r] + l); put32(lengths[r]); }
+    Xs rng{seed * 0x9E3779B97F4A7C15ull + 0x1234567ull};
+    int64_t n_rec = 0, n_blk = 0, n_bases = 0;
+    bool ok = true;
+    for (int r = 0; r < n_ref && ok; ++r) {
+        const int64_t span = std::max<int64_t>(1, (int64_t)lengths[r] - read_len - 40);
+        std::vector<int32_t> st((size_t)n_reads[r]);
+        for (auto& x : st) x = (int32_t)(rng.next() % (uint64_t)span);
+        std::sort(st.begin(), st.end());
+        for (size_t i = 0; i < st.size() && ok; ++i) {
+            const double u = rng.uni();
+            uint32_t cig[3]; int nc = 0;
+            int64_t ref_span = read_len;
+            if (u < 0.90) { cig[nc++] = (uint32_t)read_len << 4; n_blk += 1; n_bases += read_len; }
+            else if (u < 0.925) { const int k = 1 + (int)(rng.next() % 10), j = 10 + (int)(rng.next() % (uint64_t)(read_len - 30)); cig[nc++] = (uint32_t)j << 4; cig[nc++] = ((uint32_t)k << 4) | 1; cig[nc++] = (uint32_t)(read_len - j - k) << 4; n_blk += 2; n_bases += read_len - k; ref_span = read_len - k; }
+            else if (u < 0.95) { const int k = 1 + (int)(rng.next() % 10), j = 10 + (int)(rng.next() % (uint64_t)(read_len - 30)); cig[nc++] = (uint32_t)j << 4; cig[nc++] = ((uint32_t)k << 4) | 2; cig[nc++] = (uint32_t)(read_len - j) << 4; n_blk += 2; n_bases += read_len; ref_span = read_len + k; }
+            else { const int k = 5 + (int)(rng.next() % 26); cig[nc++] = ((uint32_t)k << 4) | 4; cig[nc++] = (uint32_t)(read_len - k) << 4; n_blk += 1; n_bases += read_len - k; ref_span = read_len - k; }
+            char name[24];
+            const int ln = snprintf(name, sizeof name, "r%lld", (long long)n_rec) + 1;
+            const int mapq = rng.uni() < 0.9 ? 60 : (int)(rng.next() % 60);
+            const int32_t bs = 32 + ln + 4 * nc + (read_len + 1) / 2 + read_len;
+            put32(bs); put32(r); put32(st[i]);
+            const uint32_t bin_mq_nl = ((uint32_t)reg2bin(st[i], st[i] + ref_span) << 16) | ((uint32_t)mapq << 8) | (uint32_t)ln;
+            put32((int32_t)bin_mq_nl);
+            put32((int32_t)(((uint32_t)0 << 16) | (uint32_t)nc));
+            put32(read_len); put32(-1); put32(-1); put32(0);
+            buf.insert(buf.end(), name, name + ln);
+            for (int c = 0; c < nc; ++c) put32((int32_t)cig[c]);
+            const size_t so = buf.size();
+            buf.resize(so + (size_t)(read_len + 1) / 2 + (size_t)read_len);
+            static const unsigned char code[4] = {1, 2, 4, 8};
+            for (int b = 0; b < (read_len + 1) / 2; ++b) { const uint64_t x = rng.next(); buf[so + (size_t)b] = (unsigned char)((code[x & 3] << 4) | code[(x >> 2) & 3]); }
+            memset(buf.data() + so + (size_t)(read_len + 1) / 2, 30, (size_t)read_len);
+            ++n_rec;
+            if (buf.size() >= ((size_t)32 << 20)) { ok = write_bgzf(f, buf, nt, 1); buf.clear(); }
+        }
+    }
+    if (ok && !buf.empty()) ok = write_bgzf(f, buf, nt, 1);
+    static const unsigned char eof_block[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) ok = fwrite(eof_block, 1, 28, f) == 28;
+    ok = (fclose(f) == 0) && ok;
+    if (stats) { stats[0] = n_rec; stats[1] = n_blk; stats[2] = n_bases; }
+    return ok ? HCNV_OK : HCNV_E_IO;
 }
 
 int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, double mapping_quality_threshold,

@@ -53,16 +53,20 @@ class SnpTable:
         return ["%s\t%d\t%d\t0" % (c, int(p), int(z)) for c, (ps, zs) in self.contigs().items() for p, z in zip(ps, zs)]
 
 
-def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = False):
+def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = False, threads: int = 0, stats: Optional[dict] = None):
     """hcnv_bam_pack -> (names, [Contig with numpy arrays], [max_block_len], n_records).  Arrays are copies.
     compact=True: the block stream comes in the 2-byte delta-coded form (Contig.cblocks / anchors) and the observations in
     their 2-byte form (Contig.cobs / cobs_anchors)."""
     lib = L.lib()
     h = C.c_void_p()
-    st = lib.hcnv_bam_pack(bam_path.encode(), snps._h if snps is not None else None, C.byref(h))
+    st = lib.hcnv_bam_pack_mt(bam_path.encode(), snps._h if snps is not None else None, int(threads), C.byref(h))
     if st != 0:
         raise L.HcnvError(st, "hcnv_bam_pack(%s): %s" % (bam_path, lib.hcnv_strerror(st).decode()))
     try:
+        if stats is not None:                                # records, bytes read / inflated, seconds, inflating threads (hcnv_pack_stats)
+            v = (C.c_double * 5)()
+            lib.hcnv_pack_stats(h, v)
+            stats.update(records=int(v[0]), bytes_compressed=int(v[1]), bytes_inflated=int(v[2]), seconds=float(v[3]), threads=int(v[4]))
         names, contigs, maxlens = [], [], []
         for i in range(lib.hcnv_pack_n_contigs(h)):
             name, ci, ml = C.c_char_p(), L.ContigInput(), C.c_int32()
@@ -92,3 +96,18 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
         return names, contigs, maxlens, int(lib.hcnv_pack_n_records(h))
     finally:
         lib.hcnv_pack_free(h)
+
+
+def write_synthetic_bam(path: str, refs, n_reads, read_len: int = 150, seed: int = 1, threads: int = 0) -> dict:
+    """hcnv_bam_write_synthetic: a coordinate-sorted BGZF BAM of random reads (tests, tools/bench_packer.py).  refs: [(name, length)];
+    n_reads: reads per reference.  Returns dict(records, blocks, bases)."""
+    lib = L.lib()
+    k = len(refs)
+    names = (C.c_char_p * k)(*[n.encode() for n, _ in refs])
+    lens = (C.c_int32 * k)(*[int(l) for _, l in refs])
+    nr = (C.c_int64 * k)(*[int(x) for x in n_reads])
+    st = (C.c_int64 * 3)()
+    rc = lib.hcnv_bam_write_synthetic(path.encode(), k, names, lens, nr, int(read_len), int(seed), int(threads), st)
+    if rc != 0:
+        raise L.HcnvError(rc, "hcnv_bam_write_synthetic(%s): %s" % (path, lib.hcnv_strerror(rc).decode()))
+    return dict(records=int(st[0]), blocks=int(st[1]), bases=int(st[2]))

@@ -206,6 +206,17 @@ void    hcnv_snp_table_free(hcnv_snp_table* t);
  * Produces, per @SQ contig, the sorted hcnv_block stream, the long blocks and the observations against `snps`. */
 typedef struct hcnv_pack hcnv_pack;
 int     hcnv_bam_pack(const char* bam_path, const hcnv_snp_table* snps, hcnv_pack** out);
+/* the same with a given number of inflating threads (0: one per core, at most 16).  The file is STREAMED: a reader thread cuts
+ * it into batches of whole BGZF blocks, the pool inflates them, the calling thread parses the records in order; a bounded number
+ * of batches is in flight (a 30X BAM is ~150 GB inflated and is never held in memory; what is held is the packed result). */
+int     hcnv_bam_pack_mt(const char* bam_path, const hcnv_snp_table* snps, int32_t threads, hcnv_pack** out);
+/* out[0..4] = records, compressed bytes read, inflated bytes parsed, seconds, threads */
+void    hcnv_pack_stats(const hcnv_pack* p, double out[5]);
+/* Test / benchmark helper (there is no network for real data): a coordinate-sorted BGZF BAM of random reads -- n_reads[r] reads of
+ * read_len bases per reference with uniform starts, SURVEY.md 8(d)'s CIGAR mix (90 % <len>M, 2.5 % one insertion, 2.5 % one
+ * deletion, 5 % a soft clip), random bases.  stats[0..2] = records, alignment blocks, aligned bases. */
+int     hcnv_bam_write_synthetic(const char* path, int32_t n_ref, const char* const* names, const int32_t* lengths, const int64_t* n_reads,
+                                 int32_t read_len, uint64_t seed, int32_t threads, int64_t stats[3]);
 int32_t hcnv_pack_n_contigs(const hcnv_pack* p);
 int64_t hcnv_pack_n_records(const hcnv_pack* p);
 /* fills `in` with pointers into the pack (valid until hcnv_pack_free); max_block_len for hcnv_bin_params */

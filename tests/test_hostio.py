@@ -171,3 +171,46 @@ def test_compact_block_stream_round_trip():
     assert ei.value.status == L.HCNV_E_UNSORTED
     cb0, an0 = H.compact_blocks(H.pack_blocks([], []))
     assert len(cb0) == 0 and len(an0) == 0
+
+
+def test_streaming_packer_on_a_synthetic_bam(tmp_path):
+    """The BGZF reader streams the file through a pool of inflating threads and parses records that straddle blocks and batches:
+    a synthetic BAM of 300 k reads (about 80 batches) packs to the writer's own counts, identically with 1 and with 6 threads, with
+    observations at SNP sites; a truncated or corrupted file is a parse error, not a crash."""
+    from hadoopcnv_b200 import _lib as L
+    refs = [("1", 3_000_000), ("chr2", 2_000_000), ("X", 150_000)]
+    bam = str(tmp_path / "s.bam")
+    st = hostio.write_synthetic_bam(bam, refs, [170_000, 120_000, 10_000], seed=11, threads=4)
+    assert st["records"] == 300_000 and st["blocks"] > st["records"]
+    rng = np.random.default_rng(2)
+    vcf = tmp_path / "s.vcf"
+    vcf.write_text("\n".join(Hp.vcf_lines_for("chr1", [(int(p), -1) for p in np.unique(rng.integers(1, 3_000_000, 2000))])) + "\n")
+    snps = hostio.SnpTable(str(vcf))
+    packs = []
+    for th in (1, 6):
+        stats = {}
+        names, contigs, maxlens, nrec = hostio.pack_bam(bam, snps, threads=th, stats=stats)
+        assert names == ["chr1", "chr2", "chrX"] and nrec == st["records"] and stats["threads"] == th and stats["bytes_inflated"] > 4 * stats["bytes_compressed"] > 0
+        assert sum(len(c.blocks) for c in contigs) == st["blocks"]
+        assert sum(int((c.blocks["len_mapq"] & 0xFFFFFF).sum()) for c in contigs) == st["bases"]
+        assert all((np.diff(c.blocks["start0"]) >= 0).all() for c in contigs) and max(maxlens) <= 150
+        packs.append(contigs)
+    for a, b in zip(*packs):
+        assert (a.blocks == b.blocks).all()
+        assert (a.obs is None and b.obs is None) or (a.obs == b.obs).all()
+    assert packs[0][0].obs is not None and len(packs[0][0].obs) > 1000
+    # every observation names a site its block covers: coverage at the sites == observations per site
+    c = packs[0][0]
+    depth, tally = O.depth_from_blocks(c.blocks.view(O.BLOCK_DTYPE), c.length, c.obs, len(c.snp_pos1))
+    assert (tally.sum(axis=1) == depth[c.snp_pos1]).all()
+    raw = open(bam, "rb").read()
+    for cut in (len(raw) // 2, len(raw) - 40, 100):
+        bad = str(tmp_path / "cut.bam")
+        open(bad, "wb").write(raw[:cut])
+        with pytest.raises(L.HcnvError) as ei:
+            hostio.pack_bam(bad, None, threads=3)
+        assert ei.value.status == L.HCNV_E_PARSE
+    garbled = bytearray(raw); garbled[len(raw) // 3: len(raw) // 3 + 64] = b"\x55" * 64
+    open(bad, "wb").write(bytes(garbled))
+    with pytest.raises(L.HcnvError):
+        hostio.pack_bam(bad, None, threads=3)

@@ -252,7 +252,9 @@ def test_a_chromosome_cut_across_ranks_equals_the_uncut_one(world, l1, l2):
     assert bool((outs[0].merged_state == want_state.to(torch.int8)).all()) and int(outs[0].merged_rows.sum()) == off[-1]
     # the chromosome's scalars sit with the rank that holds its last part
     for r, o in enumerate(outs):
-        for reg, sc in zip(o.regions, o.scalars):
+        for k_, (reg, sc) in enumerate(zip(o.regions, o.scalars)):
+            if o.row_offset[k_ + 1] == o.row_offset[k_]:
+                continue                                                   # a part without rows (an N gap) has nothing to report
             w_ = want[reg.contig]
             assert sc["status"] == w_["status"]
             assert np.float32(sc["mean_coverage"]).view(np.uint32) == np.float32(w_["mean_coverage"]).view(np.uint32)
