@@ -376,51 +376,77 @@ def run_b200(args):
                                  pin(c.cobs_anchors), c.region_first_bin, c.region_n_bins, c.snp_index_base) for c in contigs]
         torch.cuda.synchronize()
         e2e_state = {}
-        if world == 1:
-            from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
-            pipe = GenomePipeline(local, workers=args.e2e_workers, groups=args.e2e_groups)
-            gout = GenomeOutput([c.length for c in host_contigs], W)
-            prep = pipe.prepare(host_contigs)
-            cnames = [names[r.contig] for r in regions]
-            h2d = sum(int(x.nbytes) for c in host_contigs for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors) if x is not None)
+        # whole chromosomes: hcnv_genome_run, the C-ABI call that owns the pipeline (continuous upload, worker contexts, downloads behind
+        # the uploads).  Parts of chromosomes that are cut across ranks: the sharded step on their records alone (upload, region
+        # binning, boundary exchange over NCCL, download), concurrently on the main thread.  Every rank's rows land in its own pinned
+        # host arrays -- one part file per rank, like the reference's reducers (PennCnvSeq.java:330-350); getmerge is rank order.
+        from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
+        whole_i = [i for i, r in enumerate(regions) if r.n_parts == 1]
+        part_i = [i for i, r in enumerate(regions) if r.n_parts > 1]
+        nbytes = lambda c: sum(int(x.nbytes) for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors) if x is not None)
+        pipe = gout = prep = None
+        if whole_i:
+            pipe = GenomePipeline(local, workers=args.e2e_workers, groups=max(1, min(args.e2e_groups, len(whole_i))))
+            gout = GenomeOutput([host_contigs[i].length for i in whole_i], W)
+            prep = pipe.prepare([host_contigs[i] for i in whole_i])
+        cnames = [names[regions[i].contig] for i in whole_i]
+        sgp = None
+        any_parts = any(r.n_parts > 1 for p_ in ranks for r in p_)
+        if any_parts:                                        # (every rank takes part in the exchanges, with or without parts of its own)
+            ctx_p = H.Context(local)
+            sgp = sharding.ShardedGenome(ctx_p, comm, [regions[i] for i in part_i], [contigs[i] for i in part_i], len(names), W, READ_LEN, LAMBDA1, LAMBDA2, bin_flags=bin_flags)
+            sgp.attach_host([host_contigs[i] for i in part_i])
+        h2d = sum(nbytes(c) for c in host_contigs)
 
-            def step_e2e():
-                e2e_state["rs"] = pipe.run(prep, cnames, gout, bin_width=W, max_block_len=READ_LEN, lambda1=LAMBDA1, lambda2=LAMBDA2, bin_flags=bin_flags)
-            launches_of = lambda: pipe.kernel_launches
-            how = ("pinned host inputs -> hcnv_genome_run (one C-ABI call: continuous upload in 64 MB pieces, %d worker contexts, %d tasks of chromosomes: "
-                   "hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> hcnv_segment_batch -> hcnv_download_results) -> results.txt columns in pinned host "
-                   "arrays (int8 calls, MSE rows listed where non-zero)" % (args.e2e_workers, args.e2e_groups))
-        else:
-            sg.attach_host(host_contigs)
-            h2d = sg.h2d_bytes
-
-            def step_e2e():
-                e2e_state["out"] = sg.run_host(gather_calls=True)
-            launches_of = lambda: ctx.kernel_launches
-            how = ("every rank: pinned host records of its regions -> device (its own PCIe link) -> the region-sharded step (boundary exchange over NCCL, "
-                   "int8 calls gathered to rank 0) -> its rows of the results.txt columns in pinned host arrays")
+        def step_e2e():
+            th = None
+            if pipe is not None:
+                def whole():
+                    e2e_state["rs"] = pipe.run(prep, cnames, gout, bin_width=W, max_block_len=READ_LEN, lambda1=LAMBDA1, lambda2=LAMBDA2, bin_flags=bin_flags)
+                if sgp is not None:
+                    th = threading.Thread(target=whole)
+                    th.start()
+                else:
+                    whole()
+            if sgp is not None:
+                e2e_state["out"] = sgp.run_host(gather_calls=False)
+            if th is not None:
+                th.join()
+        launches_of = lambda: (pipe.kernel_launches if pipe is not None else 0) + (ctx_p.kernel_launches if sgp is not None else 0)
+        how = ("pinned host inputs -> results.txt columns in pinned host arrays (int8 calls, MSE rows listed where non-zero).  Whole chromosomes: hcnv_genome_run "
+               "(one C-ABI call: continuous upload in 64 MB pieces, %d worker contexts, tasks of chromosomes: hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> "
+               "hcnv_segment_batch -> hcnv_download_results)%s" % (args.e2e_workers, "; parts of the chromosomes cut across ranks: upload -> region binning -> boundary "
+               "exchange over NCCL -> download, concurrently; every rank keeps its rows (one part file per rank)" if any_parts else ""))
         for _ in range(2):
             step_e2e()
         l0 = launches_of()
         ms_e2e, ms_e2e_wall = timed(step_e2e, args.steps)
         e2e_launches = (launches_of() - l0) // args.steps
         # the end-to-end leg returns the same calls as the resident leg (same inputs)
-        if world == 1:
-            d2h = gout.d2h_bytes()
-            for i, r_ in enumerate(e2e_state["rs"]):
+        d2h = 0
+        if pipe is not None:
+            d2h += gout.d2h_bytes()
+            for k_, r_ in enumerate(e2e_state["rs"]):
+                i = whole_i[k_]
                 a, b = off[i], off[i + 1]
                 assert r_.n_bins == b - a, "e2e / resident bin count mismatch on %s" % r_.name
                 assert bool((gout.state[r_.offset:r_.offset + r_.n_bins] == out.state[a:b].cpu().to(torch.int8)).all()), "e2e / resident state mismatch on %s" % r_.name
-                assert (gout.dense_mse(i).view(np.uint32) == out.mse32[a:b].cpu().numpy().view(np.uint32)).all(), "e2e / resident MSE mismatch on %s" % r_.name
+                assert (gout.dense_mse(k_).view(np.uint32) == out.mse32[a:b].cpu().numpy().view(np.uint32)).all(), "e2e / resident MSE mismatch on %s" % r_.name
             pipe.close()
-        else:
-            d2h = sg.d2h_bytes
-            assert bool((sg.h_state[:n_bins] == out.state.cpu().to(torch.int8)).all()), "e2e / resident state mismatch"
+        if sgp is not None:
+            d2h += sgp.d2h_bytes
+            po = e2e_state["out"].row_offset
+            for k_, i in enumerate(part_i):
+                a, b = off[i], off[i + 1]
+                assert int(po[k_ + 1] - po[k_]) == b - a and bool((sgp.h_state[int(po[k_]):int(po[k_ + 1])] == out.state[a:b].cpu().to(torch.int8)).all()), "e2e / resident state mismatch on a cut chromosome"
+            ctx_p.synchronize()
+            del sgp
+            ctx_p.close()
         t2 = torch.tensor([h2d, d2h, e2e_launches], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t2)
         e2e = {"value": g_reads / (ms_e2e_wall / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(t2[0]), "d2h_bytes_per_step": int(t2[1]),
-               "ms_per_step": ms_e2e_wall, "workers": args.e2e_workers if world == 1 else 1, "gpu_launches_per_step": int(t2[2]), "note": how}
+               "ms_per_step": ms_e2e_wall, "workers": args.e2e_workers, "gpu_launches_per_step": int(t2[2]), "note": how}
 
     # ---- roofline of the dominant kernel (and of the binning kernel), from live CUDA-event timings
     peaks = {}
@@ -561,7 +587,7 @@ def run_b200(args):
             "roofline": roofline, "roofline_binning": roofline_binning, "roofline_segmentation": roofline_segmentation, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "checks": {"oracle": oracle_checks, "final_loss_sum": float(np.sum([v.get("final_loss", 0.0) for v in summary.values()])),
                        "chromosomes": len({k_.split("#")[0] for k_ in summary}), "merged_calls_on_rank0": int(out.merged_state.shape[0]),
-                       "input_generation_s": t_gen, "viterbi_rank0": ctx.stats()},
+                       "input_generation_s": t_gen, "viterbi_rank0": ctx.stats(), "step_trace_rank0_ms": getattr(sg, "trace", None)},
         }
         print(json.dumps(line))
     sys.stdout.flush()

@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(32) k_viterbi_seq(SegDev* probs, float alpha) 
 #define VM_U 16
 #define VM_PACK 10
 #define VM_MIN_MARKERS 64
+#define VM_WARPS_PER_SM 8           // resident warps per SM of the many-chains kernel (two per scheduler)
 // One marker of one chain on the six lanes that own it.  LITERAL = false is the same function of the six candidates
 // written for latency: a NaN-ignoring min tree (FMNMX) and the first index that attains it, instead of the reference's
 // serial compare-and-keep over ascending p.  The two agree whenever equal candidates are bit-identical, i.e. no
@@ -564,10 +565,25 @@ __device__ __forceinline__ void vm_run(const float* __restrict__ sdp, const floa
     if (sh != 0 && mycodes && M > 1) mycodes[wi] = word;      // a chain that ended with the last whole chunk (the tail loop flushes at m == M - 1)
 }
 
-__global__ void __launch_bounds__(32) k_viterbi_many(SegDev* probs, const int* __restrict__ order, int n_slots, float alpha) {
+// One launch = a fixed number of warps per SM (VM_WARPS_PER_SM) that take groups of five chains from a queue, longest first.  A lone
+// warp needs ~138 cycles per marker and issues ~66 instructions in them, so TWO warps per scheduler already fill the issue slots;
+// every further resident warp only slows the longest chains down (a chr1-long chain that shares its scheduler with three others
+// runs at a quarter of the issue rate and finishes last: 267 ms for 12 288 problems with every warp resident at once).
+__device__ __forceinline__ void vm_group(SegDev* probs, const int* __restrict__ order, int n_slots, float alpha, int group);
+__global__ void __launch_bounds__(32) k_viterbi_many(SegDev* probs, const int* __restrict__ order, int n_slots, float alpha, int* __restrict__ queue) {
+    const int n_groups = (n_slots + VM_CH - 1) / VM_CH;
+    for (;;) {
+        int gidx = 0;
+        if (threadIdx.x == 0) gidx = atomicAdd(queue, 1);
+        gidx = __shfl_sync(0xffffffffu, gidx, 0);
+        if (gidx >= n_groups) return;
+        vm_group(probs, order, n_slots, alpha, gidx);
+    }
+}
+__device__ __forceinline__ void vm_group(SegDev* probs, const int* __restrict__ order, int n_slots, float alpha, int group) {
     const int lane = threadIdx.x;
     const int g = lane / 6, c = lane - 6 * g;              // lanes 30 and 31 (g = 5) idle along
-    const int slot = blockIdx.x * VM_CH + g;
+    const int slot = group * VM_CH + g;
     const int pi = (g < VM_CH && slot < n_slots) ? __ldg(&order[slot]) : -1;
     const int src = min(g, VM_CH - 1) * 6;                 // first lane of the chain this lane reads predecessors from
     int M = 0, irregular = 0;
@@ -582,7 +598,7 @@ __global__ void __launch_bounds__(32) k_viterbi_many(SegDev* probs, const int* _
     if (Mmax == 0) return;
     const int Mmin = __reduce_min_sync(0xffffffffu, M > 0 ? M : 0x7fffffff);
     const float oma = __fsub_rn(1.f, alpha);
-    const float muc = c_mu[c];
+    const float muc = c_mu[c < 6 ? c : 0];
     const float c3 = __fmul_rn(l1, fabsf(muc));
     float c4[6];
     #pragma unroll
@@ -617,34 +633,46 @@ __global__ void __launch_bounds__(32) k_viterbi_many(SegDev* probs, const int* _
     }
 }
 
-// best_state / cn columns (Hmm.java:234-237, 483-484)
+// best_state / cn columns (Hmm.java:234-237, 483-484).  A thread takes FOUR CONSECUTIVE markers: the narrow output (state8, all a
+// penalty sweep asks for) leaves as one 32-bit store when the array allows it, and the code words are read once per thread.
 __global__ void __launch_bounds__(256) k_traceback(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
     const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
     SegDev& P = probs[pi];
     const int M = (int)P.M;                              // (markers per chromosome fit an int: checked on entry)
-    const int i0 = ((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + threadIdx.x;
+    const int i0 = ((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + 4 * (int)threadIdx.x;
     if (P.par && !P.irregular && !P.skip) return;    // k_vit_p3 already wrote the calls
+    if (i0 >= M) return;
     const int skip = P.skip, s = P.sstar, many = P.many;
     const uint32_t* __restrict__ codes = P.codes;
     int32_t* __restrict__ o_state = P.state; int32_t* __restrict__ o_cn = P.cn; int8_t* __restrict__ o_state8 = P.state8;
     const uint32_t* __restrict__ mine = codes + (size_t)s * (size_t)((M + VM_PACK - 1) / VM_PACK);      // column s* of k_viterbi_many's code words
+    int st[4];
     #pragma unroll
-    for (int k = 0; k < SEG_BLK / 256; ++k) {
-        const int i = i0 + k * 256;
-        if (i >= M) break;
-        int st = 0;
-        if (!skip) {
-            if (i == M - 1) st = c_cn[s];                                         // (sic) Hmm.java:234
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        int v = 0;
+        if (!skip && i < M) {
+            if (i == M - 1) v = c_cn[s];                                          // (sic) Hmm.java:234
             else if (many) {
                 const unsigned m = (unsigned)i + 1u;
-                st = (int)((__ldg(&mine[m / VM_PACK]) >> (3u * (m % VM_PACK))) & 7u);
+                v = (int)((__ldg(&mine[m / VM_PACK]) >> (3u * (m % VM_PACK))) & 7u);
             }
-            else st = (int)((__ldg(&codes[i + 1]) >> (3 * s)) & 7u);              // traceback[m+1][s*], Hmm.java:236
+            else v = (int)((__ldg(&codes[i + 1]) >> (3 * s)) & 7u);               // traceback[m+1][s*], Hmm.java:236
         }
-        if (o_state) o_state[i] = st;
-        if (o_cn) o_cn[i] = c_cn[st];
-        if (o_state8) o_state8[i] = (int8_t)st;
+        st[k] = v;
     }
+    const bool full = i0 + 4 <= M;
+    if (o_state8) {
+        if (full && ((reinterpret_cast<unsigned long long>(o_state8) + (unsigned long long)i0) & 3ull) == 0)
+            *reinterpret_cast<uint32_t*>(o_state8 + i0) = (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24);
+        else
+            for (int k = 0; k < 4 && i0 + k < M; ++k) o_state8[i0 + k] = (int8_t)st[k];
+    }
+    if (o_state || o_cn)
+        for (int k = 0; k < 4 && i0 + k < M; ++k) {
+            if (o_state) o_state[i0 + k] = st[k];
+            if (o_cn) o_cn[i0 + k] = c_cn[st[k]];
+        }
 }
 
 #include "viterbi_par.cuh"
@@ -987,7 +1015,7 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
             hcnv_fail(ctx, HCNV_E_INVALID, "too many markers in one call"); return fail(HCNV_E_INVALID);
         }
         pl->blk_base[i + 1] = pl->blk_base[i] + (int)((M + SEG_BLK - 1) / SEG_BLK);
-        pl->fblk_base[i + 1] = pl->fblk_base[i] + (int)((Mf + SEG_BLK - 1) / SEG_BLK);
+        pl->fblk_base[i + 1] = pl->fblk_base[i] + (d.scaled_shared ? 0 : (int)((Mf + SEG_BLK - 1) / SEG_BLK));
         off += M; foff += Mf;
         {
             auto key = std::make_tuple((const void*)q.total, (const void*)q.n, (long long)Mf);
@@ -1134,11 +1162,17 @@ int hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round)
     if (round == std::max(pl->whole_round, 0) && !pl->order.empty() && pl->iter == 0) {
         {
             // large batches: the many-chains kernel (five chromosomes per warp, longest first)
-            HCNV_CUDA(ctx, ctx->buf[H_ORDER].reserve(4 * pl->order.size()));
-            int* d_order = ctx->buf[H_ORDER].as<int>();
+            HCNV_CUDA(ctx, ctx->buf[H_ORDER].reserve(4 * pl->order.size() + 64));
+            int* d_queue = ctx->buf[H_ORDER].as<int>();
+            int* d_order = d_queue + 16;
+            HCNV_CUDA(ctx, cudaMemsetAsync(d_queue, 0, 64, ctx->stream));
             HCNV_CUDA(ctx, cudaMemcpyAsync(d_order, pl->order.data(), 4 * pl->order.size(), cudaMemcpyHostToDevice, ctx->stream));
+            const long long n_groups = ((long long)pl->order.size() + VM_CH - 1) / VM_CH;
+            int wps = VM_WARPS_PER_SM;
+            if (const char* e = getenv("HCNV_VM_WARPS_PER_SM")) wps = std::max(1, std::min(32, atoi(e)));
+            const unsigned grid = (unsigned)std::min<long long>(n_groups, (long long)ctx->sm_count * wps);
             KT_BEGIN(ctx, HCNV_K_VIT_MANY);
-            k_viterbi_many<<<(unsigned)((pl->order.size() + VM_CH - 1) / VM_CH), 32, 0, ctx->stream>>>(pl->dprobs, d_order, (int)pl->order.size(), pl->alpha);
+            k_viterbi_many<<<grid, 32, 0, ctx->stream>>>(pl->dprobs, d_order, (int)pl->order.size(), pl->alpha, d_queue);
             KT_END(ctx, HCNV_K_VIT_MANY);
             HCNV_CUDA(ctx, cudaGetLastError());
             ctx->launches++;

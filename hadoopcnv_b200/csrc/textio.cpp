@@ -68,11 +68,32 @@ void shortest_digits(T v, char* digits, int* nd_out, int* e10_out) {
     digits[0] = '0'; digits[1] = 0; *nd_out = 1; *e10_out = 0;   // not reached for finite v
 }
 
+template <class T> int java_to_string_slow(T v, char* buf);
+
+// Float.toString / Double.toString.  The columns of a bins or results file repeat a few values millions of times (scaled depths
+// are (integer - mean) / mean, MSEs are mostly 0.0, totals are integers), and the digit search below costs microseconds: integers
+// print directly and everything else goes through a small direct-mapped cache of finished strings.
 template <class T>
 int java_to_string(T v, char* buf) {
     if (std::isnan(v)) { strcpy(buf, "NaN"); return 3; }
     if (std::isinf(v)) { strcpy(buf, v < 0 ? "-Infinity" : "Infinity"); return (int)strlen(buf); }
     if (v == 0) { strcpy(buf, std::signbit(v) ? "-0.0" : "0.0"); return (int)strlen(buf); }
+    const double dv = (double)v;
+    if (std::fabs(dv) < 1e7 && dv == (double)(long long)dv) return sprintf(buf, "%lld.0", (long long)dv);       // (1e-3 <= |v| < 1e7: plain decimal notation)
+    struct Entry { unsigned long long bits; int len; char text[28]; };
+    static thread_local Entry cache[4096];
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    bits |= (unsigned long long)sizeof(T) << 60;                      // (float and double share the cache; a double's top bits are its exponent < 0x7ff: no clash with the tag of 8)
+    Entry& e = cache[(bits * 0x9E3779B97F4A7C15ull) >> 52];
+    if (e.bits == bits && e.len > 0) { memcpy(buf, e.text, (size_t)e.len + 1); return e.len; }
+    const int n = java_to_string_slow<T>(v, buf);
+    if (n < (int)sizeof e.text) { e.bits = bits; e.len = n; memcpy(e.text, buf, (size_t)n + 1); }
+    return n;
+}
+
+template <class T>
+int java_to_string_slow(T v, char* buf) {
     char dg[24]; int nd, e10;
     T av = v < 0 ? -v : v;
     shortest_digits<T>(av, dg, &nd, &e10);

@@ -416,15 +416,26 @@ class ShardedGenome:
     def run(self, gather_calls: bool = True) -> ShardResult:
         torch, ctx, comm, W = self.torch, self.ctx, self.comm, self.W
         me = comm.rank
+        import os
+        import time
+        trace = [] if os.environ.get("HCNV_SHARD_TRACE") else None
+        t_start = time.perf_counter()
+
+        def mark(name):
+            if trace is not None:
+                torch.cuda.synchronize()
+                trace.append((name, round(1e3 * (time.perf_counter() - t_start), 3)))
         regions = self.regions
         # ---- binning of my regions + the text round trip of the bins
         if self.contigs:
             res = ctx.bin_contigs(self.prepared, bin_width=W, max_block_len=self.maxlen, out=self.out, capacity=max(self.cap, 1), flags=self.bin_flags)
             self.kernel_ms.update(ctx.kernel_ms())
             off = np.asarray(res.contig_offset, np.int64)
+            mark("bin")
             m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total) if len(res) else (torch.empty((0, 6), dtype=torch.float32, device=self.dev), torch.empty(0, dtype=torch.float32, device=self.dev))
         else:
             res, off, m32, t32 = None, np.zeros(1, np.int64), None, None
+        mark("text")
         rows = [int(off[i + 1] - off[i]) for i in range(len(regions))]
         cut = [i for i, r in enumerate(regions) if r.n_parts > 1]
         # ---- exchange 1: who holds what (rows of the parts of cut chromosomes)
@@ -434,6 +445,7 @@ class ShardedGenome:
             s = self.slot_of[i]
             rec[s, _F["valid"]], rec[s, _F["contig"]], rec[s, _F["part"]], rec[s, _F["rows"]] = 1, regions[i].contig, regions[i].part_index, rows[i]
         table = comm.all_gather_vec(rec.ravel()).reshape(comm.world, 2, REC) if comm.world > 1 else rec[None]
+        mark("allgather1")
         rounds = 1
         for r_ in range(table.shape[0]):
             for s_ in range(2):
@@ -462,6 +474,7 @@ class ShardedGenome:
             pending.append((i, bufs, part_rows))
         if comm.world > 1:
             comm.exchange(sends, recvs)
+        mark("p2p")
         for i, bufs, part_rows in pending:
             med = torch.cat([b_[: nr] for b_, nr in zip(bufs, part_rows)]).view(torch.float32)
             tot = torch.cat([b_[nr: 2 * nr] for b_, nr in zip(bufs, part_rows)]).view(torch.float32)
@@ -497,8 +510,10 @@ class ShardedGenome:
         if live:
             from .api import SegPlan
             plan = SegPlan(ctx, parts, self.alpha, 0, keep=(keep, m32, t32, res))
+            mark("plan_create")
             plan.stats()
             plan.p0()
+            mark("stats+p0")
         live_pos = {i: j for j, i in enumerate(live)}
 
         def my_cut_parts():
@@ -543,8 +558,10 @@ class ShardedGenome:
                         v = _min_plus_apply(v, t3[r_, s_, _F["prod"]: _F["prod"] + 36].reshape(6, 6))
                     for c_ in range(6):
                         parts[j].start_approx[c_] = float(v[c_])
+        mark("allgather3")
         if live:
             plan.p1()
+        mark("p1")
         while True:
             # ---- the chain, round by round; exchange 4: the exact loss vector at every cut
             t4 = None
@@ -566,11 +583,13 @@ class ShardedGenome:
                         rec[s, _F["end"]: _F["end"] + 6] = list(parts[j].end_exact)
                         rec[s, _F["sstar"]], rec[s, _F["status"]] = parts[j].sstar, parts[j].prob.status
                     t4 = comm.all_gather_vec(rec.ravel()).reshape(comm.world, 2, REC)
+                mark("chain%d" % rnd)
             if any_cut and comm.world > 1 and t4 is not None:
                 for i, j in my_cut_parts():                 # s* of the chromosome = the last part's
                     r_, s_ = last_live_part(i)
                     parts[j].sstar = int(t4[r_, s_, _F["sstar"]])
             st = plan.finish() if live else 0
+            mark("finish")
             again = 1.0 if st == L.HCNV_SEG_AGAIN else 0.0
             t5 = None
             if any_cut and comm.world > 1:
@@ -615,6 +634,7 @@ class ShardedGenome:
             self.kernel_ms.update(ctx.kernel_ms())
             plan.close()
         nrows = int(off[-1])
+        mark("patch")
         out = ShardResult(regions, off, res, m32, self.scaled[:nrows], self.state[:nrows], self.cn[:nrows], scal)
         # ---- the merge: int8 calls of every rank to rank 0, in genome order (ranks hold consecutive pieces of the genome)
         if gather_calls:
@@ -623,4 +643,6 @@ class ShardedGenome:
             if blocks is not None:
                 out.merged_state = torch.cat([b_.to(self.dev) for b_ in blocks])
                 out.merged_rows = counts
+        mark("gather")
+        self.trace = trace
         return out
