@@ -633,46 +633,51 @@ __device__ __forceinline__ void vm_group(SegDev* probs, const int* __restrict__ 
     }
 }
 
-// best_state / cn columns (Hmm.java:234-237, 483-484).  A thread takes FOUR CONSECUTIVE markers: the narrow output (state8, all a
-// penalty sweep asks for) leaves as one 32-bit store when the array allows it, and the code words are read once per thread.
+// best_state / cn columns (Hmm.java:234-237, 483-484).  A thread takes FOUR CONSECUTIVE markers at a time: the narrow output
+// (state8, all a penalty sweep asks for) leaves as one 32-bit store when the array allows it, and the code words are read once
+// per thread.  A block covers TB_BLK markers (the look-up of its chromosome is a chain of dependent loads: with 1 024 markers
+// per block it was most of this kernel's time on a 12 288-problem sweep).
+#define TB_BLK 8192
 __global__ void __launch_bounds__(256) k_traceback(SegDev* probs, const int* __restrict__ blk_base, int n_probs) {
     const int pi = blk_find(blk_base, n_probs, (int)blockIdx.x);
     SegDev& P = probs[pi];
     const int M = (int)P.M;                              // (markers per chromosome fit an int: checked on entry)
-    const int i0 = ((int)blockIdx.x - __ldg(&blk_base[pi])) * SEG_BLK + 4 * (int)threadIdx.x;
     if (P.par && !P.irregular && !P.skip) return;    // k_vit_p3 already wrote the calls
-    if (i0 >= M) return;
     const int skip = P.skip, s = P.sstar, many = P.many;
     const uint32_t* __restrict__ codes = P.codes;
     int32_t* __restrict__ o_state = P.state; int32_t* __restrict__ o_cn = P.cn; int8_t* __restrict__ o_state8 = P.state8;
     const uint32_t* __restrict__ mine = codes + (size_t)s * (size_t)((M + VM_PACK - 1) / VM_PACK);      // column s* of k_viterbi_many's code words
-    int st[4];
-    #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k;
-        int v = 0;
-        if (!skip && i < M) {
-            if (i == M - 1) v = c_cn[s];                                          // (sic) Hmm.java:234
-            else if (many) {
-                const unsigned m = (unsigned)i + 1u;
-                v = (int)((__ldg(&mine[m / VM_PACK]) >> (3u * (m % VM_PACK))) & 7u);
+    const int b0 = ((int)blockIdx.x - __ldg(&blk_base[pi])) * TB_BLK;
+    #pragma unroll 2
+    for (int i0 = b0 + 4 * (int)threadIdx.x; i0 < min(M, b0 + TB_BLK); i0 += 1024) {
+        int st[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k;
+            int v = 0;
+            if (!skip && i < M) {
+                if (i == M - 1) v = c_cn[s];                                          // (sic) Hmm.java:234
+                else if (many) {
+                    const unsigned m = (unsigned)i + 1u;
+                    v = (int)((__ldg(&mine[m / VM_PACK]) >> (3u * (m % VM_PACK))) & 7u);
+                }
+                else v = (int)((__ldg(&codes[i + 1]) >> (3 * s)) & 7u);               // traceback[m+1][s*], Hmm.java:236
             }
-            else v = (int)((__ldg(&codes[i + 1]) >> (3 * s)) & 7u);               // traceback[m+1][s*], Hmm.java:236
+            st[k] = v;
         }
-        st[k] = v;
-    }
-    const bool full = i0 + 4 <= M;
-    if (o_state8) {
-        if (full && ((reinterpret_cast<unsigned long long>(o_state8) + (unsigned long long)i0) & 3ull) == 0)
-            *reinterpret_cast<uint32_t*>(o_state8 + i0) = (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24);
-        else
-            for (int k = 0; k < 4 && i0 + k < M; ++k) o_state8[i0 + k] = (int8_t)st[k];
-    }
-    if (o_state || o_cn)
-        for (int k = 0; k < 4 && i0 + k < M; ++k) {
-            if (o_state) o_state[i0 + k] = st[k];
-            if (o_cn) o_cn[i0 + k] = c_cn[st[k]];
+        const bool full = i0 + 4 <= M;
+        if (o_state8) {
+            if (full && ((reinterpret_cast<unsigned long long>(o_state8) + (unsigned long long)i0) & 3ull) == 0)
+                *reinterpret_cast<uint32_t*>(o_state8 + i0) = (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24);
+            else
+                for (int k = 0; k < 4 && i0 + k < M; ++k) o_state8[i0 + k] = (int8_t)st[k];
         }
+        if (o_state || o_cn)
+            for (int k = 0; k < 4 && i0 + k < M; ++k) {
+                if (o_state) o_state[i0 + k] = st[k];
+                if (o_cn) o_cn[i0 + k] = c_cn[st[k]];
+            }
+    }
 }
 
 #include "viterbi_par.cuh"
@@ -1011,10 +1016,10 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
             d.state = ctx->buf[H_OUT_I32].as<int32_t>() + off;
             d.cn = ctx->buf[H_OUT_I32].as<int32_t>() + totM + off;
         }
-        if ((M + SEG_BLK - 1) / SEG_BLK + pl->blk_base[i] > 0x7fffffffLL || (Mf + SEG_BLK - 1) / SEG_BLK + pl->fblk_base[i] > 0x7fffffffLL) {
+        if ((M + TB_BLK - 1) / TB_BLK + pl->blk_base[i] > 0x7fffffffLL || (Mf + SEG_BLK - 1) / SEG_BLK + pl->fblk_base[i] > 0x7fffffffLL) {
             hcnv_fail(ctx, HCNV_E_INVALID, "too many markers in one call"); return fail(HCNV_E_INVALID);
         }
-        pl->blk_base[i + 1] = pl->blk_base[i] + (int)((M + SEG_BLK - 1) / SEG_BLK);
+        pl->blk_base[i + 1] = pl->blk_base[i] + (int)((M + TB_BLK - 1) / TB_BLK);
         pl->fblk_base[i + 1] = pl->fblk_base[i] + (d.scaled_shared ? 0 : (int)((Mf + SEG_BLK - 1) / SEG_BLK));
         off += M; foff += Mf;
         {
