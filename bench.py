@@ -49,6 +49,9 @@ def parse_args():
                     help="genome: BASELINE.json configs[1] / [2] (default); cohort: configs[4], the segmentation-only penalty sweep over precomputed bins")
     ap.add_argument("--samples", type=int, default=64, help="cohort: samples (64 in the config)")
     ap.add_argument("--samples-per-call", type=int, default=32, help="cohort: samples per hcnv_segment_batch call")
+    ap.add_argument("--partition", default="auto", choices=["auto", "regions", "contigs"],
+                    help="N > 1: regions = the genome cut into equal pieces (chromosomes that straddle a cut are binned in parts and segmented with the NCCL "
+                         "boundary exchange); contigs = whole chromosomes by LPT (no exchange); auto = contigs when they balance within 10 %%, else regions")
     ap.add_argument("--bin-kernel", default="v2", choices=["v1", "v2"], help="v2: 64 bins per warp, packed 16-bit pairs (default); v1: the first form")
     ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
     ap.add_argument("--e2e-groups", type=int, default=8, help="tasks (groups of chromosomes) per genome in the end-to-end leg")
@@ -113,7 +116,7 @@ def workload_config(args, world):
             "hg19_%gx_wgs_bin%d%s" % (args.coverage, args.bin_width, "" if args.scale == 1.0 else "_scaled_%g" % args.scale),
             "coverage": args.coverage, "bin_width": args.bin_width, "read_len": READ_LEN, "lambda1": LAMBDA1, "lambda2": LAMBDA2,
             "genome": "hg19 shape: 24 contigs, 3 095 677 412 bp, non-N intervals of example/hg19.extra.bam",
-            "parallelism": "one genome region-sharded over %d GPU(s)" % world,
+            "parallelism": "one genome over %d GPU(s), partition policy %s (sharding.plan_partition)" % (world, args.partition),
             "l2": "inputs (GBs per GPU) far larger than the 126 MB L2; no flush needed"}
 
 
@@ -255,9 +258,8 @@ def run_b200(args):
     names, w = contig_weights(args.scale)
     shape = synth.hg19_shape()
     lengths = [max(1000, int(c["length"] * args.scale)) for c in shape["contigs"]]
-    order = sharding.layout_order(w, world)                       # contigs end to end in this order: cuts fall into small chromosomes
-    names, w, lengths = [names[i] for i in order], [w[i] for i in order], [lengths[i] for i in order]
-    ranks = sharding.partition_regions(lengths, w, world, W)
+    order, ranks = sharding.plan_partition(lengths, w, world, W, args.partition)
+    names, w, lengths = [names[i] for i in order], [w[i] for i in order], [lengths[i] for i in order]     # (layout order: Region.contig indexes it)
     regions = ranks[rank]
     ids = sorted({r.contig for r in regions})
     t_gen = time.perf_counter()

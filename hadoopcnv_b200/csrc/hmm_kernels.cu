@@ -1051,7 +1051,7 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
         size_t o_repl = o_force + 4 * S, o_tf = (o_repl + 4 * (size_t)n_problems + 255) / 256 * 256, o_ti = o_tf + 144 * S;
         size_t o_ls = o_ti + 288 * S, o_tc = (o_ls + 24 * (S + (size_t)n_problems) + 255) / 256 * 256;
         size_t o_cinfo = o_tc + 288 * NC, o_cbase = o_cinfo + 4 * NC, o_tie = o_cbase + 4 * np1;
-        size_t o_scan = (o_tie + 4 * (S + 4) + 255) / 256 * 256, bytes = o_scan + (split ? (size_t)n_problems * P0C_T * 144 : 0);
+        size_t o_scan = (o_tie + 4 * (S + 4) + 255) / 256 * 256, bytes = o_scan + (size_t)n_problems * P0C_K * P0C_T * 144;
         if ((rc = CU(ctx->buf[H_VPAR].reserve(bytes), "segment scratch"))) return fail(rc);
         char* vb = ctx->buf[H_VPAR].as<char>();
         pl->d_tc = (int*)(vb + o_tc); pl->d_cinfo = (int*)(vb + o_cinfo); pl->d_cbase = (int*)(vb + o_cbase);
@@ -1105,11 +1105,11 @@ int hcnv_seg_plan_p0_impl(hcnv_seg_plan* pl)
         k_vit_p0<<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_tf);
         KT_END(ctx, HCNV_K_VIT_P0);
         ctx->launches++;
-        if (pl->split) {
+        {
             const int sm = 2 * P0C_T * 36 * 4;
             HCNV_CUDA(ctx, cudaFuncSetAttribute(k_vit_p0c_par<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
             KT_BEGIN(ctx, HCNV_K_VIT_P0C);
-            k_vit_p0c_par<1><<<pl->n, P0C_T, sm, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
+            k_vit_p0c_par<1><<<pl->n * P0C_K, P0C_T, sm, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
             KT_END(ctx, HCNV_K_VIT_P0C);
             ctx->launches++;
         }
@@ -1123,10 +1123,28 @@ int hcnv_seg_plan_p0_impl(hcnv_seg_plan* pl)
             pt.irregular = pl->h[i].irregular; pt.skipped = pl->h[i].skip ? 1 : 0;
             for (int c = 0; c < 6; ++c) pt.first_vector[c] = pl->h[i].loss0_out[c];
             for (int j = 0; j < 36; ++j) pt.product_approx[j] = (j / 6 == j % 6) ? 0.f : V_INF_F;
-            if (pl->h[i].par && pl->h[i].n_seg > 0 && !pl->h[i].skip)
-                HCNV_CUDA(ctx, cudaMemcpyAsync(pt.product_approx, pl->d_scan + ((size_t)i * P0C_T + (P0C_T - 1)) * 36, 144, cudaMemcpyDeviceToHost, ctx->stream));
         }
+        std::vector<float> sub((size_t)pl->n * P0C_K * 36);
+        for (int i = 0; i < pl->n; ++i)
+            if (pl->h[i].par && pl->h[i].n_seg > 0 && !pl->h[i].skip)
+                for (int q = 0; q < P0C_K; ++q)
+                    HCNV_CUDA(ctx, cudaMemcpyAsync(&sub[((size_t)i * P0C_K + q) * 36], pl->d_scan + (((size_t)i * P0C_K + q) * P0C_T + (P0C_T - 1)) * 36, 144, cudaMemcpyDeviceToHost, ctx->stream));
         HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < pl->n; ++i) {
+            if (!(pl->h[i].par && pl->h[i].n_seg > 0 && !pl->h[i].skip)) continue;
+            float* R = pl->parts[i].product_approx;           // R = R (x) sub-block q, in order
+            for (int q = 0; q < P0C_K; ++q) {
+                const float* B = &sub[((size_t)i * P0C_K + q) * 36];
+                float t[36];
+                for (int a = 0; a < 6; ++a)
+                    for (int c = 0; c < 6; ++c) {
+                        float best = V_INF_F;
+                        for (int m = 0; m < 6; ++m) best = std::min(best, R[a * 6 + m] + B[m * 6 + c]);
+                        t[a * 6 + c] = best;
+                    }
+                memcpy(R, t, sizeof t);
+            }
+        }
     }
     return HCNV_OK;
 }
@@ -1137,17 +1155,12 @@ int hcnv_seg_plan_p1_impl(hcnv_seg_plan* pl)
     hcnv_ctx* ctx = pl->ctx;
     if (pl->total_segs == 0) return HCNV_OK;
     const unsigned gs = (unsigned)(((size_t)pl->total_segs + 127) / 128);
-    const int sm = 2 * P0C_T * 36 * 4;
     KT_BEGIN(ctx, HCNV_K_VIT_P0C);
     if (pl->split) {
         for (int i = 0; i < pl->n; ++i)
             if (!pl->h[i].part_first) { for (int c = 0; c < 6; ++c) pl->h[i].Lf_in[c] = pl->parts[i].start_approx[c]; int rc = push_prob(pl, i); if (rc) return rc; }
-        HCNV_CUDA(ctx, cudaFuncSetAttribute(k_vit_p0c_par<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        k_vit_p0c_par<2><<<pl->n, P0C_T, sm, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
-    } else {
-        HCNV_CUDA(ctx, cudaFuncSetAttribute(k_vit_p0c_par<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        k_vit_p0c_par<0><<<pl->n, P0C_T, sm, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
     }
+    k_vit_p0c_par<2><<<pl->n * P0C_K, P0C_T, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
     KT_END(ctx, HCNV_K_VIT_P0C);
     KT_BEGIN(ctx, HCNV_K_VIT_P1);
     k_vit_p1<false><<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_tielist, pl->d_tiecnt);

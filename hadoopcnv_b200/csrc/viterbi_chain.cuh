@@ -58,24 +58,30 @@ __device__ __forceinline__ void fmat_load(const float* __restrict__ g, float* T)
 }
 
 #define P0C_T 256
-// MODE 0: scan and walk in one launch (whole chromosomes).  A chromosome that is cut across ranks needs the products of the
-// parts in front of it before it can walk: MODE 1 scans and leaves every thread's inclusive prefix in `scan_out` (the last one
-// is the part's product), MODE 2 walks from P.Lf_in with the prefixes of MODE 1.
+// P0c in two launches over (chromosome x P0C_K sub-blocks): one CTA per chromosome was a 0.3 ms latency-bound launch at every GPU
+// count (39 000 segments of chr1 on 256 threads, twice).  Sub-block kb of a chromosome owns the segments [kb, kb + 1) * ceil(n_seg /
+// P0C_K).  MODE 1: every thread's inclusive prefix of its sub-block's products -> `scan_out` (the last thread's is the sub-block's
+// product; a part of a cut chromosome hands the product of its sub-blocks to the later parts).  MODE 2: the walk, from the
+// chromosome's first vector (x) the products of the sub-blocks in front (x) the thread's exclusive prefix.
+#define P0C_K 8
 template <int MODE>
 __global__ void __launch_bounds__(P0C_T) k_vit_p0c_par(SegDev* probs, const int* __restrict__ seg_base, float alpha,
                                                        const float* __restrict__ Tf, int* __restrict__ epred, float* __restrict__ scan_out) {
     extern __shared__ __align__(16) float sm_scan[];           // [2][P0C_T][36]
-    SegDev& P = probs[blockIdx.x];
+    const int pi = blockIdx.x / P0C_K, kb = blockIdx.x % P0C_K;
+    SegDev& P = probs[pi];
     if (P.skip || !P.par) return;
     const int tid = threadIdx.x;
     const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
-    const int nseg = P.n_seg, base = seg_base[blockIdx.x];
-    const int C = (nseg + P0C_T - 1) / P0C_T;
-    const int s0 = min(nseg, tid * C), s1 = min(nseg, s0 + C);
+    const int nseg = P.n_seg, base = seg_base[pi];
+    const int SB = (nseg + P0C_K - 1) / P0C_K;                 // segments per sub-block
+    const int b0 = min(nseg, kb * SB), b1 = min(nseg, b0 + SB);
+    const int C = (b1 - b0 + P0C_T - 1) / P0C_T;
+    const int s0 = min(b1, b0 + tid * C), s1 = min(b1, s0 + C);
     float R[36], T[36];
-    int cur = 0;
     float* gscan = scan_out + (size_t)blockIdx.x * P0C_T * 36;
-    if (MODE != 2) {
+    if (MODE == 1) {
+        int cur = 0;
         fmat_identity(R);
         for (int s = s0; s < s1; ++s) {
             fmat_load(Tf + (size_t)(base + s) * 36, T);
@@ -97,38 +103,29 @@ __global__ void __launch_bounds__(P0C_T) k_vit_p0c_par(SegDev* probs, const int*
             for (int i = 0; i < 36; ++i) sm_scan[(cur * P0C_T + tid) * 36 + i] = R[i];
             __syncthreads();
         }
-        if (MODE == 1) {
-            #pragma unroll
-            for (int i = 0; i < 36; ++i) gscan[(size_t)tid * 36 + i] = R[i];
-            if (tid < 6 && P.part_first) P.loss0_out[tid] = loss0(P, k, tid);
-            return;
-        }
-    } else {
-        if (tid > 0) {
-            #pragma unroll
-            for (int i = 0; i < 36; ++i) sm_scan[(tid - 1) * 36 + i] = gscan[(size_t)(tid - 1) * 36 + i];       // only the own exclusive prefix is read back
-        }
-    }
-    // exclusive prefix applied to the loss vector in front of the first segment, then walk the chunk with the vector
-    double v[6];
-    {
-        double L0[6];
         #pragma unroll
-        for (int c = 0; c < 6; ++c) L0[c] = P.part_first ? (double)loss0(P, k, c) : P.Lf_in[c];
-        if (tid == 0) {
-            #pragma unroll
-            for (int c = 0; c < 6; ++c) v[c] = L0[c];
-        } else {
-            const float* E = &sm_scan[(cur * P0C_T + tid - 1) * 36];
-            #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                double best = 1e300;
-                #pragma unroll
-                for (int i = 0; i < 6; ++i) best = fmin(best, L0[i] + (double)E[i * 6 + j]);
-                v[j] = best;
-            }
-        }
+        for (int i = 0; i < 36; ++i) gscan[(size_t)tid * 36 + i] = R[i];
+        if (kb == 0 && tid < 6 && P.part_first) P.loss0_out[tid] = loss0(P, k, tid);
+        return;
     }
+    // ---- MODE 2: the vector in front of the thread's first segment, then the walk
+    double v[6];
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) v[c] = P.part_first ? (double)loss0(P, k, c) : P.Lf_in[c];
+    auto apply = [&](const float* __restrict__ E) {           // v = v (x) E
+        double nv[6];
+        #pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double best = 1e300;
+            #pragma unroll
+            for (int i = 0; i < 6; ++i) best = fmin(best, v[i] + (double)__ldg(&E[i * 6 + j]));
+            nv[j] = best;
+        }
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) v[c] = nv[c];
+    };
+    for (int q = 0; q < kb; ++q) apply(scan_out + ((size_t)(pi * P0C_K + q) * P0C_T + (P0C_T - 1)) * 36);     // the sub-blocks in front
+    if (tid > 0) apply(gscan + (size_t)(tid - 1) * 36);                                                       // the threads in front
     for (int s = s0; s < s1; ++s) {
         fmat_load(Tf + (size_t)(base + s) * 36, T);
         double lo = v[0], hi = 0.0, nv[6];

@@ -108,6 +108,25 @@ def partition_regions(lengths: Sequence[int], weights: Sequence[float], world: i
     return ranks
 
 
+def plan_partition(lengths: Sequence[int], weights: Sequence[float], world: int, bin_width: int, policy: str = "auto", tolerance: float = 1.10):
+    """(order, ranks): the layout order of the contigs and every rank's regions IN THAT ORDER (Region.contig indexes `order`).
+    policy "contigs": whole chromosomes only, the longest-processing-time groups (no exchange at all);
+           "regions": the genome cut into equal pieces (partition_regions): balanced to a bin, at the price of the boundary
+                      exchange and of a chain that runs rank after rank for every chromosome that is cut;
+           "auto":    whole chromosomes when their heaviest group is within `tolerance` of the mean (24 chromosomes on up to 8
+                      GPUs are: the exchange would cost more than the imbalance), regions otherwise (more GPUs, few big contigs)."""
+    order = layout_order(weights, world)
+    lo, wo = [lengths[i] for i in order], [weights[i] for i in order]
+    groups = partition_contigs(weights, world)
+    loads = [sum(weights[i] for i in g) for g in groups]
+    balanced = max(loads) <= tolerance * (sum(loads) / world) and all(g for g in groups)
+    if policy == "contigs" or (policy == "auto" and balanced):
+        pos = {c: k for k, c in enumerate(order)}
+        groups = sorted(groups, key=lambda g: (sum(weights[i] for i in g), g))            # (the order layout_order laid them out in)
+        return order, [[Region(pos[i], 0, 0, 0, 1) for i in sorted(g, key=lambda i: pos[i])] for g in groups]
+    return order, partition_regions(lo, wo, world, bin_width)
+
+
 def region_contig(c, region: Region, bin_width: int):
     """The inputs of one region as a Contig of views (numpy or torch): the groups of the compact stream that can reach into the
     region, the region's SNP sites, the observation groups that can name them (hcnv_contig_input::region_*)."""
