@@ -12,8 +12,12 @@
 #include "hcnv_internal.h"
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <thread>
+
+struct GenomeTask { std::vector<int> contigs; };
 
 struct hcnv_genome {
     int device = 0;
@@ -24,6 +28,19 @@ struct hcnv_genome {
     size_t piece_bytes = (size_t)64 << 20;
     std::string err;
     std::mutex mu;
+    // ---- the sample in flight (hcnv_genome_begin .. hcnv_genome_end)
+    bool open = false, closed = false;
+    hcnv_bin_params P{};
+    float lambda1 = 0.f, lambda2 = 0.f, alpha = 0.5f;
+    int n_contigs = 0;
+    hcnv_genome_output out{};
+    std::vector<long long> cap;
+    std::vector<hcnv_contig_input> dev_in;
+    long long task_rows_hint = 0;
+    std::deque<GenomeTask> queue;
+    std::condition_variable cv;
+    std::vector<std::thread> workers;
+    std::atomic<int> worst{HCNV_OK};
 };
 
 namespace {
@@ -89,39 +106,204 @@ int64_t hcnv_genome_kernel_launches(const hcnv_genome* g) {
     return n;
 }
 
-int hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
-                    int32_t n_contigs, const hcnv_contig_input* contigs, int32_t n_groups, hcnv_genome_output* out) {
-    if (!g || n_contigs <= 0 || !contigs || !out) return HCNV_E_INVALID;
+// one task = a few chromosomes end to end on worker w
+static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
+    hcnv_ctx* ctx = g->ctx[(size_t)w];
+    hcnv_genome_output* out = &g->out;
+    auto fail = [&](int rc, const char* what) {
+        genome_fail(g, rc, std::string(what) + ": " + hcnv_last_error(ctx));
+        int expect = HCNV_OK; g->worst.compare_exchange_strong(expect, rc);
+    };
+    const std::vector<int>& gr = task.contigs;
+    long long rows_cap = 0;
+    for (int c : gr) rows_cap += g->cap[(size_t)c];
+    const size_t C = (size_t)std::max<long long>(std::max<long long>(rows_cap, g->task_rows_hint), 1);
+    // per-worker device scratch (grows to the largest task): BinReducer's columns, their float32 twins, the calls
+    if (ctx->buf[G_BINS_I32].reserve(4 * 4 * C + 64) != cudaSuccess || ctx->buf[G_BINS_F32].reserve(4 * C + 64) != cudaSuccess ||
+        ctx->buf[G_BINS_F64].reserve(8 * 7 * C + 64) != cudaSuccess || ctx->buf[G_M32].reserve(4 * 7 * C + 64) != cudaSuccess ||
+        ctx->buf[G_SEG_F32].reserve(4 * C + 64) != cudaSuccess || ctx->buf[G_SEG_I32].reserve(4 * 2 * C + 64) != cudaSuccess) {
+        cudaGetLastError(); ctx->err = "out of device memory"; fail(HCNV_E_NOMEM, "worker scratch"); return;
+    }
+    int32_t* bi = ctx->buf[G_BINS_I32].as<int32_t>();
+    hcnv_bins bins{};
+    bins.capacity = (int64_t)C;
+    bins.bin = bi; bins.start = bi + C; bins.end = bi + 2 * C; bins.n = bi + 3 * C;
+    bins.median = ctx->buf[G_BINS_F32].as<float>();
+    bins.mse = ctx->buf[G_BINS_F64].as<double>(); bins.total = bins.mse + 6 * C;
+    float* m32 = ctx->buf[G_M32].as<float>(); float* t32 = m32 + 6 * C;
+    float* scaled = ctx->buf[G_SEG_F32].as<float>();
+    int32_t* state = ctx->buf[G_SEG_I32].as<int32_t>(); int32_t* cn = state + C;
+    // the task's records are on the device once its last chromosome's event has fired (uploads are in order)
+    if (cudaStreamWaitEvent(ctx->stream, g->landed[(size_t)gr.back()], 0) != cudaSuccess) { ctx->err = "cudaStreamWaitEvent"; fail(HCNV_E_CUDA, "wait"); return; }
+    std::vector<hcnv_contig_input> in;
+    for (int c : gr) in.push_back(g->dev_in[(size_t)c]);
+    std::vector<int64_t> off(gr.size() + 1, 0);
+    bins.contig_offset = off.data();
+    int rc = hcnv_bin_contigs_impl(ctx, &g->P, (int32_t)gr.size(), in.data(), &bins);
+    if (rc) { fail(rc, "hcnv_bin_contigs"); return; }
+    const int64_t nrows = off[gr.size()];
+    if (nrows == 0) return;
+    rc = hcnv_bins_to_hmm_input_impl(ctx, nrows, bins.mse, bins.total, m32, t32);
+    if (rc) { fail(rc, "hcnv_bins_to_hmm_input"); return; }
+    std::vector<hcnv_segment_problem> probs;
+    std::vector<int> live;
+    for (size_t j = 0; j < gr.size(); ++j) {
+        const int64_t a = off[j], nb = off[j + 1] - off[j];
+        if (nb <= 0) continue;
+        hcnv_segment_problem q{};
+        q.n_markers = nb; q.median = bins.median + a; q.mse = m32 + 6 * a; q.total = t32 + a; q.n = bins.n + a;
+        q.lambda1 = g->lambda1; q.lambda2 = g->lambda2; q.scaled = scaled + a; q.state = state + a; q.cn = cn + a;
+        probs.push_back(q); live.push_back((int)j);
+    }
+    rc = hcnv_segment_batch_impl(ctx, g->alpha, (int32_t)probs.size(), probs.data(), 0);
+    if (rc < 0 && rc != HCNV_E_NO_MINIMUM) { fail(rc, "hcnv_segment_batch"); return; }
+    for (size_t k = 0; k < live.size(); ++k) {
+        const size_t j = (size_t)live[k];
+        const int c = gr[j];
+        const int64_t a = off[j], nb = off[j + 1] - off[j], o = out->row_offset[c];
+        hcnv_results_download d{};
+        d.n = nb; d.start = bins.start + a; d.end = bins.end + a; d.scaled = scaled + a; d.state = state + a; d.cn = cn + a; d.mse = m32 + 6 * a;
+        d.h_start = out->start + o; d.h_end = out->end + o; d.h_scaled = out->scaled + o; d.h_state = out->state + o;
+        d.h_cn = out->cn ? out->cn + o : nullptr;
+        d.h_mse_rows = out->mse_rows + o; d.h_mse_vals = out->mse_vals + 6 * o; d.mse_capacity = nb;
+        rc = hcnv_download_results_impl(ctx, &d);
+        if (rc) { fail(rc, "hcnv_download_results"); return; }
+        out->n_bins[c] = nb; out->n_mse_rows[c] = d.n_mse_rows;
+        const hcnv_segment_problem& q = probs[k];
+        if (out->status) out->status[c] = q.status;
+        if (out->mean_coverage) out->mean_coverage[c] = q.mean_coverage;
+        if (out->final_loss) out->final_loss[c] = q.final_loss;
+        if (out->lambda1_used) out->lambda1_used[c] = q.lambda1_used;
+        if (out->lambda2_used) out->lambda2_used[c] = q.lambda2_used;
+        if (q.status < 0) { int expect = HCNV_OK; g->worst.compare_exchange_strong(expect, q.status); }
+    }
+}
+
+static void genome_worker(hcnv_genome* g, int w) {
+    cudaSetDevice(g->device);
+    for (;;) {
+        GenomeTask task;
+        {
+            std::unique_lock<std::mutex> lk(g->mu);
+            g->cv.wait(lk, [g] { return !g->queue.empty() || g->closed; });
+            if (g->queue.empty()) return;
+            task = std::move(g->queue.front());
+            g->queue.pop_front();
+        }
+        if (g->worst.load() == HCNV_OK) genome_task(g, w, task);
+    }
+}
+
+// The sample as a stream of chromosomes: begin (the contig lengths fix the layout of the output), push groups of chromosomes as
+// the packer finishes them (each push uploads its records and hands the group to a worker; it returns at once), end (waits).
+// This is the per-key push of the reference's map side (SAMRecordWindowMapper.map emits per record, the shuffle groups by
+// chromosome, Mappers.java:167-272) at the granularity the GPU wants: the host never has to hold more than the chromosomes
+// it is still packing, and the GPU work hides behind the packer.
+int hcnv_genome_begin(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
+                      int32_t n_contigs, const int32_t* lengths, int64_t max_task_rows, hcnv_genome_output* out) {
+    if (!g || n_contigs <= 0 || !lengths || !out) return HCNV_E_INVALID;
+    if (g->open) return genome_fail(g, HCNV_E_INVALID, "hcnv_genome_begin: a sample is already in flight");
     if (!out->start || !out->end || !out->scaled || !out->state || !out->mse_rows || !out->mse_vals || !out->row_offset || !out->n_bins || !out->n_mse_rows)
         return genome_fail(g, HCNV_E_INVALID, "null output array");
     if (cudaSetDevice(g->device) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaSetDevice failed");
     g->err.clear();
-    hcnv_bin_params P;
-    if (params) P = *params; else hcnv_bin_params_default(&P);
-    const int W = P.bin_width;
+    if (params) g->P = *params; else hcnv_bin_params_default(&g->P);
+    const int W = g->P.bin_width;
     if (W < 1) return genome_fail(g, HCNV_E_INVALID, "bin_width");
     // rows of contig c start at the sum of the capacities (length / W + 1: what BinReducer can reach) of the contigs before it
-    std::vector<long long> cap((size_t)n_contigs);
-    long long total_cap = 0, total_len = 0;
+    g->cap.assign((size_t)n_contigs, 0);
+    long long total_cap = 0;
     for (int c = 0; c < n_contigs; ++c) {
-        if (contigs[c].length < 0) return genome_fail(g, HCNV_E_INVALID, "negative contig length");
-        if (contigs[c].region_first_bin || contigs[c].region_n_bins) return genome_fail(g, HCNV_E_INVALID, "hcnv_genome_run takes whole contigs");
-        cap[(size_t)c] = contigs[c].length / W + 1;
+        if (lengths[c] < 0) return genome_fail(g, HCNV_E_INVALID, "negative contig length");
+        g->cap[(size_t)c] = lengths[c] / W + 1;
         out->row_offset[c] = total_cap; out->n_bins[c] = 0; out->n_mse_rows[c] = 0;
         if (out->status) out->status[c] = HCNV_OK;
         if (out->mean_coverage) out->mean_coverage[c] = 0.f;
         if (out->final_loss) out->final_loss[c] = 0.f;
         if (out->lambda1_used) out->lambda1_used[c] = lambda1;
         if (out->lambda2_used) out->lambda2_used[c] = lambda2;
-        total_cap += cap[(size_t)c]; total_len += contigs[c].length;
+        total_cap += g->cap[(size_t)c];
     }
     if (total_cap > out->capacity) return genome_fail(g, HCNV_E_CAPACITY, "output capacity below the sum of length / bin_width + 1");
+    if (g->stage.size() < (size_t)n_contigs * ST_N) g->stage.resize((size_t)n_contigs * ST_N);
+    while (g->landed.size() < (size_t)n_contigs) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventCreate failed");
+        g->landed.push_back(e);
+    }
+    g->dev_in.assign((size_t)n_contigs, hcnv_contig_input{});
+    g->lambda1 = lambda1; g->lambda2 = lambda2; g->alpha = alpha; g->n_contigs = n_contigs; g->out = *out;
+    g->task_rows_hint = max_task_rows;
+    g->worst = HCNV_OK; g->closed = false; g->queue.clear();
+    for (size_t w = 0; w < g->ctx.size(); ++w) g->workers.emplace_back(genome_worker, g, (int)w);
+    g->open = true;
+    return HCNV_OK;
+}
 
+int hcnv_genome_push(hcnv_genome* g, int32_t n, const int32_t* contig_index, const hcnv_contig_input* contigs) {
+    if (!g || !g->open || n <= 0 || !contig_index || !contigs) return HCNV_E_INVALID;
+    if (cudaSetDevice(g->device) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaSetDevice failed");
+    GenomeTask task;
+    for (int k = 0; k < n; ++k) {
+        const int c = contig_index[k];
+        if (c < 0 || c >= g->n_contigs) return genome_fail(g, HCNV_E_INVALID, "contig index");
+        if (contigs[k].region_first_bin || contigs[k].region_n_bins) return genome_fail(g, HCNV_E_INVALID, "hcnv_genome_push takes whole contigs");
+        if ((long long)contigs[k].length / g->P.bin_width + 1 != g->cap[(size_t)c]) return genome_fail(g, HCNV_E_INVALID, "contig length differs from hcnv_genome_begin's");
+        Field f[ST_N];
+        contig_fields(contigs[k], f);
+        void* d[ST_N];
+        for (int q = 0; q < ST_N; ++q) {
+            DevBuf& b = g->stage[(size_t)c * ST_N + q];
+            d[q] = nullptr;
+            if (!f[q].bytes) continue;
+            if (!f[q].src) return genome_fail(g, HCNV_E_INVALID, "null input array with non-zero count");
+            if (b.reserve(f[q].bytes) != cudaSuccess) { cudaGetLastError(); return genome_fail(g, HCNV_E_NOMEM, "staging buffer"); }
+            d[q] = b.p;
+            for (size_t o = 0; o < f[q].bytes; o += g->piece_bytes) {
+                const size_t nb = std::min(g->piece_bytes, f[q].bytes - o);
+                if (cudaMemcpyAsync((char*)b.p + o, (const char*)f[q].src + o, nb, cudaMemcpyHostToDevice, g->copy) != cudaSuccess)
+                    return genome_fail(g, HCNV_E_CUDA, "upload failed");
+            }
+        }
+        if (cudaEventRecord(g->landed[(size_t)c], g->copy) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventRecord failed");
+        hcnv_contig_input& di = g->dev_in[(size_t)c];
+        di = contigs[k];
+        di.blocks = (const hcnv_block*)d[ST_BLOCKS]; di.long_blocks = (const hcnv_long_block*)d[ST_LONG];
+        di.snp_pos1 = (const int32_t*)d[ST_SNPPOS]; di.snp_zyg = (const int8_t*)d[ST_SNPZYG]; di.obs = (const uint32_t*)d[ST_OBS];
+        di.cblocks = (const hcnv_cblock*)d[ST_CBLOCKS]; di.anchors = (const int32_t*)d[ST_ANCHORS];
+        di.cobs = (const hcnv_cobs*)d[ST_COBS]; di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
+        task.contigs.push_back(c);
+    }
+    { std::lock_guard<std::mutex> lk(g->mu); g->queue.push_back(std::move(task)); }
+    g->cv.notify_one();
+    return HCNV_OK;
+}
+
+// Waits for every pushed group; the caller's host buffers of a group must stay valid until then (the uploads are asynchronous).
+int hcnv_genome_end(hcnv_genome* g) {
+    if (!g || !g->open) return HCNV_E_INVALID;
+    { std::lock_guard<std::mutex> lk(g->mu); g->closed = true; }
+    g->cv.notify_all();
+    for (auto& t : g->workers) t.join();
+    g->workers.clear();
+    g->open = false;
+    cudaSetDevice(g->device);
+    if (g->worst.load() != HCNV_OK) cudaStreamSynchronize(g->copy);      // a failed sample still drains the copy stream before the caller reuses its arrays
+    return g->worst.load();
+}
+
+int hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
+                    int32_t n_contigs, const hcnv_contig_input* contigs, int32_t n_groups, hcnv_genome_output* out) {
+    if (!g || n_contigs <= 0 || !contigs || !out) return HCNV_E_INVALID;
     // ---- tasks: the chromosomes longest first, grouped into about n_groups pieces of equal length
+    std::vector<int32_t> lengths((size_t)n_contigs);
+    long long total_len = 0;
+    for (int c = 0; c < n_contigs; ++c) { lengths[(size_t)c] = contigs[c].length; total_len += std::max(0, contigs[c].length); }
     std::vector<int> order((size_t)n_contigs);
     for (int c = 0; c < n_contigs; ++c) order[(size_t)c] = c;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return contigs[a].length > contigs[b].length; });
     const int NG = std::max(1, n_groups > 0 ? n_groups : 8);
+    const int W = params && params->bin_width > 0 ? params->bin_width : 100;
     std::vector<std::vector<int>> groups;
     {
         std::vector<int> cur; long long acc = 0;
@@ -132,130 +314,17 @@ int hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1
         if (!cur.empty()) groups.push_back(cur);
     }
     long long max_group_cap = 1;
-    for (auto& gr : groups) { long long s = 0; for (int c : gr) s += cap[(size_t)c]; max_group_cap = std::max(max_group_cap, s); }
-
-    // ---- upload: every chromosome's arrays on one copy stream, in task order, an event per chromosome
-    if (g->stage.size() < (size_t)n_contigs * ST_N) g->stage.resize((size_t)n_contigs * ST_N);
-    while (g->landed.size() < (size_t)n_contigs) {
-        cudaEvent_t e = nullptr;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventCreate failed");
-        g->landed.push_back(e);
-    }
-    std::vector<hcnv_contig_input> dev_in((size_t)n_contigs);
-    for (int c : order) {
-        Field f[ST_N];
-        contig_fields(contigs[c], f);
-        void* d[ST_N];
-        for (int k = 0; k < ST_N; ++k) {
-            DevBuf& b = g->stage[(size_t)c * ST_N + k];
-            d[k] = nullptr;
-            if (!f[k].bytes) continue;
-            if (!f[k].src) return genome_fail(g, HCNV_E_INVALID, "null input array with non-zero count");
-            if (b.reserve(f[k].bytes) != cudaSuccess) { cudaGetLastError(); return genome_fail(g, HCNV_E_NOMEM, "staging buffer"); }
-            d[k] = b.p;
-            for (size_t o = 0; o < f[k].bytes; o += g->piece_bytes) {
-                const size_t nb = std::min(g->piece_bytes, f[k].bytes - o);
-                if (cudaMemcpyAsync((char*)b.p + o, (const char*)f[k].src + o, nb, cudaMemcpyHostToDevice, g->copy) != cudaSuccess)
-                    return genome_fail(g, HCNV_E_CUDA, "upload failed");
-            }
-        }
-        if (cudaEventRecord(g->landed[(size_t)c], g->copy) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventRecord failed");
-        hcnv_contig_input& di = dev_in[(size_t)c];
-        di = contigs[c];
-        di.blocks = (const hcnv_block*)d[ST_BLOCKS]; di.long_blocks = (const hcnv_long_block*)d[ST_LONG];
-        di.snp_pos1 = (const int32_t*)d[ST_SNPPOS]; di.snp_zyg = (const int8_t*)d[ST_SNPZYG]; di.obs = (const uint32_t*)d[ST_OBS];
-        di.cblocks = (const hcnv_cblock*)d[ST_CBLOCKS]; di.anchors = (const int32_t*)d[ST_ANCHORS];
-        di.cobs = (const hcnv_cobs*)d[ST_COBS]; di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
-    }
-
-    // ---- workers
-    std::atomic<size_t> next{0};
-    std::atomic<int> worst{HCNV_OK};
-    auto work = [&](int w) {
-        hcnv_ctx* ctx = g->ctx[(size_t)w];
-        cudaSetDevice(g->device);
-        auto fail = [&](int rc, const char* what) {
-            genome_fail(g, rc, std::string(what) + ": " + hcnv_last_error(ctx));
-            int expect = HCNV_OK; worst.compare_exchange_strong(expect, rc);
-        };
-        const size_t C = (size_t)max_group_cap;
-        // per-worker device scratch for the largest group: BinReducer's columns, their float32 twins, the calls
-        if (ctx->buf[G_BINS_I32].reserve(4 * 4 * C + 64) != cudaSuccess || ctx->buf[G_BINS_F32].reserve(4 * C + 64) != cudaSuccess ||
-            ctx->buf[G_BINS_F64].reserve(8 * 7 * C + 64) != cudaSuccess || ctx->buf[G_M32].reserve(4 * 7 * C + 64) != cudaSuccess ||
-            ctx->buf[G_SEG_F32].reserve(4 * C + 64) != cudaSuccess || ctx->buf[G_SEG_I32].reserve(4 * 2 * C + 64) != cudaSuccess) {
-            cudaGetLastError(); ctx->err = "out of device memory"; fail(HCNV_E_NOMEM, "worker scratch"); return;
-        }
-        int32_t* bi = ctx->buf[G_BINS_I32].as<int32_t>();
-        hcnv_bins bins{};
-        bins.capacity = (int64_t)C;
-        bins.bin = bi; bins.start = bi + C; bins.end = bi + 2 * C; bins.n = bi + 3 * C;
-        bins.median = ctx->buf[G_BINS_F32].as<float>();
-        bins.mse = ctx->buf[G_BINS_F64].as<double>(); bins.total = bins.mse + 6 * C;
-        float* m32 = ctx->buf[G_M32].as<float>(); float* t32 = m32 + 6 * C;
-        float* scaled = ctx->buf[G_SEG_F32].as<float>();
-        int32_t* state = ctx->buf[G_SEG_I32].as<int32_t>(); int32_t* cn = state + C;
+    for (auto& gr : groups) { long long s = 0; for (int c : gr) s += contigs[c].length / W + 1; max_group_cap = std::max(max_group_cap, s); }
+    int rc = hcnv_genome_begin(g, params, lambda1, lambda2, alpha, n_contigs, lengths.data(), max_group_cap, out);
+    if (rc) return rc;
+    for (auto& gr : groups) {
         std::vector<hcnv_contig_input> in;
-        std::vector<int64_t> off;
-        std::vector<hcnv_segment_problem> probs;
-        std::vector<int> live;
-        for (;;) {
-            const size_t gi = next.fetch_add(1);
-            if (gi >= groups.size() || worst.load() != HCNV_OK) return;
-            const std::vector<int>& gr = groups[gi];
-            // the group's records are on the device once its last chromosome's event has fired (uploads are in order)
-            if (cudaStreamWaitEvent(ctx->stream, g->landed[(size_t)gr.back()], 0) != cudaSuccess) { ctx->err = "cudaStreamWaitEvent"; fail(HCNV_E_CUDA, "wait"); return; }
-            in.clear();
-            for (int c : gr) in.push_back(dev_in[(size_t)c]);
-            off.assign(gr.size() + 1, 0);
-            bins.contig_offset = off.data();
-            int rc = hcnv_bin_contigs_impl(ctx, &P, (int32_t)gr.size(), in.data(), &bins);
-            if (rc) { fail(rc, "hcnv_bin_contigs"); return; }
-            const int64_t nrows = off[gr.size()];
-            if (nrows == 0) continue;
-            rc = hcnv_bins_to_hmm_input_impl(ctx, nrows, bins.mse, bins.total, m32, t32);
-            if (rc) { fail(rc, "hcnv_bins_to_hmm_input"); return; }
-            probs.clear(); live.clear();
-            for (size_t j = 0; j < gr.size(); ++j) {
-                const int64_t a = off[j], nb = off[j + 1] - off[j];
-                if (nb <= 0) continue;
-                hcnv_segment_problem q{};
-                q.n_markers = nb; q.median = bins.median + a; q.mse = m32 + 6 * a; q.total = t32 + a; q.n = bins.n + a;
-                q.lambda1 = lambda1; q.lambda2 = lambda2; q.scaled = scaled + a; q.state = state + a; q.cn = cn + a;
-                probs.push_back(q); live.push_back((int)j);
-            }
-            rc = hcnv_segment_batch_impl(ctx, alpha, (int32_t)probs.size(), probs.data(), 0);
-            if (rc < 0 && rc != HCNV_E_NO_MINIMUM) { fail(rc, "hcnv_segment_batch"); return; }
-            for (size_t k = 0; k < live.size(); ++k) {
-                const size_t j = (size_t)live[k];
-                const int c = gr[j];
-                const int64_t a = off[j], nb = off[j + 1] - off[j], o = out->row_offset[c];
-                hcnv_results_download d{};
-                d.n = nb; d.start = bins.start + a; d.end = bins.end + a; d.scaled = scaled + a; d.state = state + a; d.cn = cn + a; d.mse = m32 + 6 * a;
-                d.h_start = out->start + o; d.h_end = out->end + o; d.h_scaled = out->scaled + o; d.h_state = out->state + o;
-                d.h_cn = out->cn ? out->cn + o : nullptr;
-                d.h_mse_rows = out->mse_rows + o; d.h_mse_vals = out->mse_vals + 6 * o; d.mse_capacity = nb;
-                rc = hcnv_download_results_impl(ctx, &d);
-                if (rc) { fail(rc, "hcnv_download_results"); return; }
-                out->n_bins[c] = nb; out->n_mse_rows[c] = d.n_mse_rows;
-                const hcnv_segment_problem& q = probs[k];
-                if (out->status) out->status[c] = q.status;
-                if (out->mean_coverage) out->mean_coverage[c] = q.mean_coverage;
-                if (out->final_loss) out->final_loss[c] = q.final_loss;
-                if (out->lambda1_used) out->lambda1_used[c] = q.lambda1_used;
-                if (out->lambda2_used) out->lambda2_used[c] = q.lambda2_used;
-                if (q.status < 0) { int expect = HCNV_OK; worst.compare_exchange_strong(expect, q.status); }
-            }
-        }
-    };
-    const int nw = (int)std::min<size_t>(g->ctx.size(), groups.size());
-    std::vector<std::thread> threads;
-    for (int w = 1; w < nw; ++w) threads.emplace_back(work, w);
-    work(0);
-    for (auto& t : threads) t.join();
-    // the staging buffers may be overwritten by the next run only after every copy of this one is done (they are: every task
-    // waited for its chromosomes' events); a failed run still drains the copy stream before the caller reuses its arrays
-    if (worst.load() != HCNV_OK) cudaStreamSynchronize(g->copy);
-    return worst.load();
+        for (int c : gr) in.push_back(contigs[c]);
+        rc = hcnv_genome_push(g, (int32_t)gr.size(), gr.data(), in.data());
+        if (rc) break;
+    }
+    const int rc2 = hcnv_genome_end(g);
+    return rc ? rc : rc2;
 }
 
 }  // extern "C"

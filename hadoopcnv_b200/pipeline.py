@@ -106,6 +106,38 @@ class GenomePipeline:
         """The hcnv_contig_input array of a genome whose host buffers stay where they are (built once, like a compiled host does)."""
         return Context.prepare_contigs(contigs)
 
+    # ---- the sample as a stream of chromosomes (hcnv_genome_begin / push / end)
+    def begin(self, lengths: Sequence[int], out: Optional[GenomeOutput] = None, bin_width: int = 100, max_block_len: int = 0,
+              lambda1: float = 0.01, lambda2: float = 1.6, alpha: float = 0.5, bin_flags: int = 0) -> GenomeOutput:
+        """Start a sample whose chromosomes will be pushed as the packer finishes them; `lengths` fixes the output layout."""
+        if out is None:
+            out = GenomeOutput(lengths, bin_width)
+        self.last_output = out
+        p = L.BinParams()
+        self._lib.hcnv_bin_params_default(C.byref(p))
+        p.bin_width, p.max_block_len, p.flags = bin_width, max_block_len, bin_flags
+        arr = (C.c_int32 * len(lengths))(*[int(x) for x in lengths])
+        self._check(self._lib.hcnv_genome_begin(self._h, C.byref(p), float(lambda1), float(lambda2), float(alpha), len(lengths), arr, 0, C.byref(out.struct)))
+        self._pushed = []
+        return out
+
+    def push(self, indices: Sequence[int], contigs: Sequence[Contig]):
+        """One group of whole chromosomes (host arrays; they must stay alive until `end`): uploaded and handed to a worker at once."""
+        prep = Context.prepare_contigs(contigs)
+        self._pushed.append(prep)
+        idx = (C.c_int32 * len(indices))(*[int(i) for i in indices])
+        self._check(self._lib.hcnv_genome_push(self._h, len(indices), idx, prep.arr))
+
+    def end(self) -> GenomeOutput:
+        st = self._lib.hcnv_genome_end(self._h)
+        self._pushed = []
+        self._check(st)
+        return self.last_output
+
+    def _check(self, st: int):
+        if st < 0:
+            raise L.HcnvError(st, self._lib.hcnv_genome_last_error(self._h).decode() or self._lib.hcnv_strerror(st).decode())
+
     def run(self, contigs, names: Optional[Sequence[str]] = None, out: Optional[GenomeOutput] = None,
             bin_width: int = 100, max_block_len: int = 0, lambda1: float = 0.01, lambda2: float = 1.6, alpha: float = 0.5,
             bin_flags: int = 0) -> List[ChromosomeResult]:

@@ -348,6 +348,17 @@ int         hcnv_genome_create(int device, int32_t workers /* 0: 4 */, hcnv_geno
 int         hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
                             int32_t n_contigs, const hcnv_contig_input* contigs /* host arrays */, int32_t n_groups /* tasks per genome, 0: 8 */,
                             hcnv_genome_output* out);
+/* The same sample as a STREAM of chromosomes -- the push the reference's map side has (SAMRecordWindowMapper.map is called per
+ * record and the shuffle groups its output by chromosome, Mappers.java:167-272), at the granularity the GPU wants: begin (the
+ * contig lengths fix the output layout; max_task_rows = rows of the largest group that will be pushed, 0 = grow on demand),
+ * push a group of whole chromosomes as soon as the packer has finished them (uploads the group's records and hands it to a
+ * worker; returns at once; the group's host buffers must stay valid until hcnv_genome_end), end (waits for every group).  The
+ * host never holds more than the chromosomes it is still packing, and the GPU work hides behind the packer.
+ * hcnv_genome_run is begin + push (about n_groups groups, longest chromosomes first) + end. */
+int         hcnv_genome_begin(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
+                              int32_t n_contigs, const int32_t* lengths, int64_t max_task_rows, hcnv_genome_output* out);
+int         hcnv_genome_push(hcnv_genome* g, int32_t n, const int32_t* contig_index, const hcnv_contig_input* contigs);
+int         hcnv_genome_end(hcnv_genome* g);
 int64_t     hcnv_genome_kernel_launches(const hcnv_genome* g);
 const char* hcnv_genome_last_error(const hcnv_genome* g);
 void        hcnv_genome_destroy(hcnv_genome* g);

@@ -481,6 +481,23 @@ def test_genome_pipeline_equals_the_single_call_path(ctx):
             np.testing.assert_array_equal(out.scaled[sl].numpy().view(np.uint32), calls[i]["scaled"].view(np.uint32))
             np.testing.assert_array_equal(out.dense_mse(i).view(np.uint32), m32[a:b].view(np.uint32))
             assert np.float32(r.final_loss).view(np.uint32) == np.float32(calls[i]["final_loss"]).view(np.uint32)
+        # the same sample as a stream of chromosomes (hcnv_genome_begin / push / end): pushed one by one in file order, then in pairs
+        hc = synth.to_api_contigs(g, host=True, compact=True, compact_observations=True)
+        for step in (1, 2):
+            o2 = pipe.begin([c.length for c in g], max_block_len=150)
+            for a0 in range(0, len(g), step):
+                pipe.push(list(range(a0, min(len(g), a0 + step))), hc[a0:a0 + step])
+            pipe.end()
+            for i in range(len(g)):
+                a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
+                sl = slice(int(o2.row_offset[i]), int(o2.row_offset[i]) + int(o2.n_bins[i]))
+                assert int(o2.n_bins[i]) == b - a
+                np.testing.assert_array_equal(o2.state[sl].numpy(), calls[i]["state"])
+                np.testing.assert_array_equal(o2.scaled[sl].numpy().view(np.uint32), calls[i]["scaled"].view(np.uint32))
+                np.testing.assert_array_equal(o2.dense_mse(i).view(np.uint32), m32[a:b].view(np.uint32))
+                assert np.float32(o2.final_loss[i]).view(np.uint32) == np.float32(calls[i]["final_loss"]).view(np.uint32)
+        with pytest.raises(H.HcnvError):
+            pipe.push([0], hc[:1])                                       # no sample in flight
     finally:
         pipe.close()
 
