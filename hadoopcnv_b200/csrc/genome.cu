@@ -11,6 +11,7 @@
 // scratch, streams, events) is kept from run to run.
 #include "hcnv_internal.h"
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -18,6 +19,7 @@
 #include <thread>
 
 struct GenomeTask { std::vector<int> contigs; };
+struct UploadJob { std::vector<int> contigs; std::vector<hcnv_contig_input> host; };   // one pushed group: its host arrays, to be uploaded in order
 
 struct hcnv_genome {
     int device = 0;
@@ -25,7 +27,20 @@ struct hcnv_genome {
     cudaStream_t copy = nullptr;
     std::vector<DevBuf> stage;                    // 9 per contig: blocks, long, snp_pos, snp_zyg, obs, cblocks, anchors, cobs, cobs_anchors
     std::vector<cudaEvent_t> landed;              // one per contig
+    // The upload is PACED: pieces of piece_bytes, at most `depth` of them queued on the copy stream at any time.  With everything
+    // queued at once (1.4 GB), a copy engine that serves its queue in submission order makes every other copy of the process -- the
+    // workers' descriptor tables going up, the results coming down -- wait for the END of the upload: 31 ms per genome in one run,
+    // 43 - 66 ms in the next (same binary, same box).  Measured with pacing (ms per 30X genome end to end, piece MB x depth):
+    // 64 x 2: 32.3, 32 x 4: 32.6, 16 x 3: 32.6 - 32.7, 8 x 3: 33.6, 4 x 4: 35.4, 16 x 6: 37.4, 8 x 8: 105 (many queued pieces are
+    // as bad as one huge one); HCNV_UPLOAD_PIECE_MB / HCNV_UPLOAD_DEPTH override.
     size_t piece_bytes = (size_t)64 << 20;
+    int depth = 2;
+    std::vector<cudaEvent_t> ring;                // one event per piece in flight
+    size_t ring_pos = 0;
+    std::deque<UploadJob> jobs;
+    std::condition_variable cv_up;
+    std::thread uploader;
+    bool jobs_closed = false;
     std::string err;
     std::mutex mu;
     // ---- the sample in flight (hcnv_genome_begin .. hcnv_genome_end)
@@ -41,6 +56,9 @@ struct hcnv_genome {
     std::condition_variable cv;
     std::vector<std::thread> workers;
     std::atomic<int> worst{HCNV_OK};
+    bool trace = false;                           // HCNV_GENOME_TRACE=1: per-task wall times to stderr at hcnv_genome_end
+    std::chrono::steady_clock::time_point t0;
+    std::vector<std::string> trace_lines;
 };
 
 namespace {
@@ -94,6 +112,7 @@ void hcnv_genome_destroy(hcnv_genome* g) {
     for (hcnv_ctx* c : g->ctx) hcnv_ctx_destroy(c);
     for (auto& b : g->stage) b.release();
     for (cudaEvent_t e : g->landed) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : g->ring) if (e) cudaEventDestroy(e);
     if (g->copy) cudaStreamDestroy(g->copy);
     delete g;
 }
@@ -106,6 +125,8 @@ int64_t hcnv_genome_kernel_launches(const hcnv_genome* g) {
     return n;
 }
 
+static void genome_uploader(hcnv_genome* g);
+
 // one task = a few chromosomes end to end on worker w
 static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
     hcnv_ctx* ctx = g->ctx[(size_t)w];
@@ -115,6 +136,9 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
         int expect = HCNV_OK; g->worst.compare_exchange_strong(expect, rc);
     };
     const std::vector<int>& gr = task.contigs;
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g->t0).count(); };
+    const double t_start = g->trace ? now_ms() : 0.0;
+    double t_wait = 0, t_bin = 0, t_text = 0, t_seg = 0;
     long long rows_cap = 0;
     for (int c : gr) rows_cap += g->cap[(size_t)c];
     const size_t C = (size_t)std::max<long long>(std::max<long long>(rows_cap, g->task_rows_hint), 1);
@@ -135,6 +159,7 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
     int32_t* state = ctx->buf[G_SEG_I32].as<int32_t>(); int32_t* cn = state + C;
     // the task's records are on the device once its last chromosome's event has fired (uploads are in order)
     if (cudaStreamWaitEvent(ctx->stream, g->landed[(size_t)gr.back()], 0) != cudaSuccess) { ctx->err = "cudaStreamWaitEvent"; fail(HCNV_E_CUDA, "wait"); return; }
+    if (g->trace) { cudaStreamSynchronize(ctx->stream); t_wait = now_ms(); }
     std::vector<hcnv_contig_input> in;
     for (int c : gr) in.push_back(g->dev_in[(size_t)c]);
     std::vector<int64_t> off(gr.size() + 1, 0);
@@ -142,9 +167,11 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
     int rc = hcnv_bin_contigs_impl(ctx, &g->P, (int32_t)gr.size(), in.data(), &bins);
     if (rc) { fail(rc, "hcnv_bin_contigs"); return; }
     const int64_t nrows = off[gr.size()];
+    if (g->trace) t_bin = now_ms();
     if (nrows == 0) return;
     rc = hcnv_bins_to_hmm_input_impl(ctx, nrows, bins.mse, bins.total, m32, t32);
     if (rc) { fail(rc, "hcnv_bins_to_hmm_input"); return; }
+    if (g->trace) t_text = now_ms();
     std::vector<hcnv_segment_problem> probs;
     std::vector<int> live;
     for (size_t j = 0; j < gr.size(); ++j) {
@@ -157,6 +184,7 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
     }
     rc = hcnv_segment_batch_impl(ctx, g->alpha, (int32_t)probs.size(), probs.data(), 0);
     if (rc < 0 && rc != HCNV_E_NO_MINIMUM) { fail(rc, "hcnv_segment_batch"); return; }
+    if (g->trace) t_seg = now_ms();
     for (size_t k = 0; k < live.size(); ++k) {
         const size_t j = (size_t)live[k];
         const int c = gr[j];
@@ -176,6 +204,12 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
         if (out->lambda1_used) out->lambda1_used[c] = q.lambda1_used;
         if (out->lambda2_used) out->lambda2_used[c] = q.lambda2_used;
         if (q.status < 0) { int expect = HCNV_OK; g->worst.compare_exchange_strong(expect, q.status); }
+    }
+    if (g->trace) {
+        char line[256];
+        snprintf(line, sizeof line, "task w%d contigs=%zu rows=%lld start=%.2f landed=%.2f bin=%.2f text=%.2f seg=%.2f d2h=%.2f", w, gr.size(), (long long)nrows, t_start, t_wait, t_bin, t_text, t_seg, now_ms());
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->trace_lines.push_back(line);
     }
 }
 
@@ -234,16 +268,86 @@ int hcnv_genome_begin(hcnv_genome* g, const hcnv_bin_params* params, float lambd
     g->dev_in.assign((size_t)n_contigs, hcnv_contig_input{});
     g->lambda1 = lambda1; g->lambda2 = lambda2; g->alpha = alpha; g->n_contigs = n_contigs; g->out = *out;
     g->task_rows_hint = max_task_rows;
-    g->worst = HCNV_OK; g->closed = false; g->queue.clear();
+    while (g->ring.size() < 16) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventCreate failed");
+        g->ring.push_back(e);
+    }
+    g->ring_pos = 0;
+    if (const char* e = getenv("HCNV_UPLOAD_PIECE_MB")) g->piece_bytes = (size_t)std::max(1, atoi(e)) << 20;
+    if (const char* e = getenv("HCNV_UPLOAD_DEPTH")) g->depth = std::max(1, std::min((int)g->ring.size(), atoi(e)));
+    g->worst = HCNV_OK; g->closed = false; g->queue.clear(); g->jobs.clear(); g->jobs_closed = false;
+    g->trace = getenv("HCNV_GENOME_TRACE") != nullptr; g->t0 = std::chrono::steady_clock::now(); g->trace_lines.clear();
+    g->uploader = std::thread(genome_uploader, g);
     for (size_t w = 0; w < g->ctx.size(); ++w) g->workers.emplace_back(genome_worker, g, (int)w);
     g->open = true;
     return HCNV_OK;
 }
 
+// the uploader thread: the pushed groups in order, piece by piece, never more than g->depth pieces queued on the copy stream
+static void genome_uploader(hcnv_genome* g) {
+    cudaSetDevice(g->device);
+    auto fail = [&](int rc, const char* what) {
+        genome_fail(g, rc, what);
+        int expect = HCNV_OK; g->worst.compare_exchange_strong(expect, rc);
+    };
+    size_t in_flight = 0;
+    for (;;) {
+        UploadJob job;
+        {
+            std::unique_lock<std::mutex> lk(g->mu);
+            g->cv_up.wait(lk, [g] { return !g->jobs.empty() || g->jobs_closed; });
+            if (g->jobs.empty()) break;
+            job = std::move(g->jobs.front());
+            g->jobs.pop_front();
+        }
+        if (g->worst.load() != HCNV_OK) continue;
+        GenomeTask task;
+        bool ok = true;
+        for (size_t k = 0; k < job.contigs.size() && ok; ++k) {
+            const int c = job.contigs[k];
+            Field f[ST_N];
+            contig_fields(job.host[k], f);
+            void* d[ST_N];
+            for (int q = 0; q < ST_N && ok; ++q) {
+                DevBuf& b = g->stage[(size_t)c * ST_N + q];
+                d[q] = nullptr;
+                if (!f[q].bytes) continue;
+                if (b.reserve(f[q].bytes) != cudaSuccess) { cudaGetLastError(); fail(HCNV_E_NOMEM, "staging buffer"); ok = false; break; }
+                d[q] = b.p;
+                for (size_t o = 0; o < f[q].bytes && ok; o += g->piece_bytes) {
+                    const size_t nb = std::min(g->piece_bytes, f[q].bytes - o);
+                    cudaEvent_t ev = g->ring[g->ring_pos];
+                    if (in_flight >= (size_t)g->depth) cudaEventSynchronize(ev);        // the oldest piece in flight has landed
+                    if (cudaMemcpyAsync((char*)b.p + o, (const char*)f[q].src + o, nb, cudaMemcpyHostToDevice, g->copy) != cudaSuccess ||
+                        cudaEventRecord(ev, g->copy) != cudaSuccess) { fail(HCNV_E_CUDA, "upload failed"); ok = false; break; }
+                    g->ring_pos = (g->ring_pos + 1) % (size_t)g->depth;        // (the event in this slot is the one recorded `depth` pieces ago)
+                    if (in_flight < (size_t)g->depth) ++in_flight;
+                }
+            }
+            if (!ok) break;
+            if (cudaEventRecord(g->landed[(size_t)c], g->copy) != cudaSuccess) { fail(HCNV_E_CUDA, "cudaEventRecord failed"); break; }
+            hcnv_contig_input& di = g->dev_in[(size_t)c];
+            di = job.host[k];
+            di.blocks = (const hcnv_block*)d[ST_BLOCKS]; di.long_blocks = (const hcnv_long_block*)d[ST_LONG];
+            di.snp_pos1 = (const int32_t*)d[ST_SNPPOS]; di.snp_zyg = (const int8_t*)d[ST_SNPZYG]; di.obs = (const uint32_t*)d[ST_OBS];
+            di.cblocks = (const hcnv_cblock*)d[ST_CBLOCKS]; di.anchors = (const int32_t*)d[ST_ANCHORS];
+            di.cobs = (const hcnv_cobs*)d[ST_COBS]; di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
+            task.contigs.push_back(c);
+        }
+        if (!ok || task.contigs.empty()) continue;
+        { std::lock_guard<std::mutex> lk(g->mu); g->queue.push_back(std::move(task)); }     // (its last chromosome's event is recorded: a worker may wait on it)
+        g->cv.notify_one();
+        if (g->trace) fprintf(stderr, "group of %zu contigs queued on the copy stream at %.2f ms\n", job.contigs.size(),
+                              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g->t0).count());
+    }
+    { std::lock_guard<std::mutex> lk(g->mu); g->closed = true; }
+    g->cv.notify_all();
+}
+
 int hcnv_genome_push(hcnv_genome* g, int32_t n, const int32_t* contig_index, const hcnv_contig_input* contigs) {
     if (!g || !g->open || n <= 0 || !contig_index || !contigs) return HCNV_E_INVALID;
-    if (cudaSetDevice(g->device) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaSetDevice failed");
-    GenomeTask task;
+    UploadJob job;
     for (int k = 0; k < n; ++k) {
         const int c = contig_index[k];
         if (c < 0 || c >= g->n_contigs) return genome_fail(g, HCNV_E_INVALID, "contig index");
@@ -251,42 +355,27 @@ int hcnv_genome_push(hcnv_genome* g, int32_t n, const int32_t* contig_index, con
         if ((long long)contigs[k].length / g->P.bin_width + 1 != g->cap[(size_t)c]) return genome_fail(g, HCNV_E_INVALID, "contig length differs from hcnv_genome_begin's");
         Field f[ST_N];
         contig_fields(contigs[k], f);
-        void* d[ST_N];
-        for (int q = 0; q < ST_N; ++q) {
-            DevBuf& b = g->stage[(size_t)c * ST_N + q];
-            d[q] = nullptr;
-            if (!f[q].bytes) continue;
-            if (!f[q].src) return genome_fail(g, HCNV_E_INVALID, "null input array with non-zero count");
-            if (b.reserve(f[q].bytes) != cudaSuccess) { cudaGetLastError(); return genome_fail(g, HCNV_E_NOMEM, "staging buffer"); }
-            d[q] = b.p;
-            for (size_t o = 0; o < f[q].bytes; o += g->piece_bytes) {
-                const size_t nb = std::min(g->piece_bytes, f[q].bytes - o);
-                if (cudaMemcpyAsync((char*)b.p + o, (const char*)f[q].src + o, nb, cudaMemcpyHostToDevice, g->copy) != cudaSuccess)
-                    return genome_fail(g, HCNV_E_CUDA, "upload failed");
-            }
-        }
-        if (cudaEventRecord(g->landed[(size_t)c], g->copy) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventRecord failed");
-        hcnv_contig_input& di = g->dev_in[(size_t)c];
-        di = contigs[k];
-        di.blocks = (const hcnv_block*)d[ST_BLOCKS]; di.long_blocks = (const hcnv_long_block*)d[ST_LONG];
-        di.snp_pos1 = (const int32_t*)d[ST_SNPPOS]; di.snp_zyg = (const int8_t*)d[ST_SNPZYG]; di.obs = (const uint32_t*)d[ST_OBS];
-        di.cblocks = (const hcnv_cblock*)d[ST_CBLOCKS]; di.anchors = (const int32_t*)d[ST_ANCHORS];
-        di.cobs = (const hcnv_cobs*)d[ST_COBS]; di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
-        task.contigs.push_back(c);
+        for (int q = 0; q < ST_N; ++q) if (f[q].bytes && !f[q].src) return genome_fail(g, HCNV_E_INVALID, "null input array with non-zero count");
+        job.contigs.push_back(c); job.host.push_back(contigs[k]);
     }
-    { std::lock_guard<std::mutex> lk(g->mu); g->queue.push_back(std::move(task)); }
-    g->cv.notify_one();
+    { std::lock_guard<std::mutex> lk(g->mu); g->jobs.push_back(std::move(job)); }
+    g->cv_up.notify_one();
     return HCNV_OK;
 }
 
 // Waits for every pushed group; the caller's host buffers of a group must stay valid until then (the uploads are asynchronous).
 int hcnv_genome_end(hcnv_genome* g) {
     if (!g || !g->open) return HCNV_E_INVALID;
-    { std::lock_guard<std::mutex> lk(g->mu); g->closed = true; }
-    g->cv.notify_all();
+    { std::lock_guard<std::mutex> lk(g->mu); g->jobs_closed = true; }
+    g->cv_up.notify_all();
+    g->uploader.join();                           // (it closes the workers' queue behind the last group)
     for (auto& t : g->workers) t.join();
     g->workers.clear();
     g->open = false;
+    if (g->trace) {
+        fprintf(stderr, "hcnv_genome_end at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g->t0).count());
+        for (auto& l : g->trace_lines) fprintf(stderr, "  %s\n", l.c_str());
+    }
     cudaSetDevice(g->device);
     if (g->worst.load() != HCNV_OK) cudaStreamSynchronize(g->copy);      // a failed sample still drains the copy stream before the caller reuses its arrays
     return g->worst.load();
