@@ -54,6 +54,10 @@ def parse_args():
                          "boundary exchange); contigs = whole chromosomes by LPT (no exchange); auto = contigs when they balance within 10 %%, else regions")
     ap.add_argument("--bin-kernel", default="v2", choices=["v1", "v2"], help="v2: 64 bins per warp, packed 16-bit pairs (default); v1: the first form")
     ap.add_argument("--e2e-workers", type=int, default=4, help="worker contexts of the end-to-end leg")
+    ap.add_argument("--e2e-stream", choices=["wire", "cblocks"], default="wire",
+                    help="block stream the end-to-end leg uploads for whole chromosomes: the ~1.1-byte wire form (expanded on the device) or the 2-byte form")
+    ap.add_argument("--e2e-output", choices=["implicit", "dense"], default="implicit",
+                    help="start/end/cn columns of the end-to-end leg's download: implicit (runs of full bins + the exceptions; cn looked up from the state by the writer) or dense")
     ap.add_argument("--e2e-groups", type=int, default=8, help="tasks (groups of chromosomes) per genome in the end-to-end leg")
     return ap.parse_args()
 
@@ -385,11 +389,21 @@ def run_b200(args):
         from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
         whole_i = [i for i, r in enumerate(regions) if r.n_parts == 1]
         part_i = [i for i, r in enumerate(regions) if r.n_parts > 1]
-        nbytes = lambda c: sum(int(x.nbytes) for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors) if x is not None)
+        nbytes = lambda c: sum(int(x.nbytes) for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors, c.wblocks, c.wlens, c.wlen_offsets) if x is not None)
+        if args.e2e_stream == "wire":                        # what hcnv_pack_contig_wire hands a host: 1 byte per record + 1 per record that is not READ_LEN long
+            import dataclasses
+            def pin_np(a_):
+                h = torch.empty(a_.shape, dtype=torch.uint8 if a_.dtype == np.uint8 else torch.int32, pin_memory=True).numpy()
+                h[...] = a_
+                return h
+            for i in whole_i:
+                wc = H.wire_contig(host_contigs[i])
+                if wc.wblocks is not None:
+                    host_contigs[i] = dataclasses.replace(wc, anchors=pin_np(wc.anchors), wblocks=pin_np(wc.wblocks), wlens=pin_np(wc.wlens), wlen_offsets=pin_np(wc.wlen_offsets))
         pipe = gout = prep = None
         if whole_i:
             pipe = GenomePipeline(local, workers=args.e2e_workers, groups=max(1, min(args.e2e_groups, len(whole_i))))
-            gout = GenomeOutput([host_contigs[i].length for i in whole_i], W)
+            gout = GenomeOutput([host_contigs[i].length for i in whole_i], W, want_cn=args.e2e_output == "dense", implicit_bins=args.e2e_output == "implicit")
             prep = pipe.prepare([host_contigs[i] for i in whole_i])
         cnames = [names[regions[i].contig] for i in whole_i]
         sgp = None
@@ -415,9 +429,9 @@ def run_b200(args):
             if th is not None:
                 th.join()
         launches_of = lambda: (pipe.kernel_launches if pipe is not None else 0) + (ctx_p.kernel_launches if sgp is not None else 0)
-        how = ("pinned host inputs -> results.txt columns in pinned host arrays (int8 calls, MSE rows listed where non-zero).  Whole chromosomes: hcnv_genome_run "
+        how = ("pinned host inputs (block stream: %s) -> results.txt columns in pinned host arrays (int8 calls, MSE rows listed where non-zero).  Whole chromosomes: hcnv_genome_run "
                "(one C-ABI call: continuous upload in 64 MB pieces, %d worker contexts, tasks of chromosomes: hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> "
-               "hcnv_segment_batch -> hcnv_download_results)%s" % (args.e2e_workers, "; parts of the chromosomes cut across ranks: upload -> region binning -> boundary "
+               "hcnv_segment_batch -> hcnv_download_results)%s" % ("hcnv_wblock wire form, ~1.1 B per record, expanded on the device" if args.e2e_stream == "wire" else "hcnv_cblock, 2 B per record", args.e2e_workers, "; parts of the chromosomes cut across ranks: upload -> region binning -> boundary "
                "exchange over NCCL -> download, concurrently; every rank keeps its rows (one part file per rank)" if any_parts else ""))
         for _ in range(2):
             step_e2e()
@@ -433,6 +447,8 @@ def run_b200(args):
                 a, b = off[i], off[i + 1]
                 assert r_.n_bins == b - a, "e2e / resident bin count mismatch on %s" % r_.name
                 assert bool((gout.state[r_.offset:r_.offset + r_.n_bins] == out.state[a:b].cpu().to(torch.int8)).all()), "e2e / resident state mismatch on %s" % r_.name
+                st_, en_ = gout.start_end(k_)
+                assert (st_ == out.bins.start[a:b].cpu().numpy()).all() and (en_ == out.bins.end[a:b].cpu().numpy()).all(), "e2e / resident start/end mismatch on %s" % r_.name
                 assert (gout.dense_mse(k_).view(np.uint32) == out.mse32[a:b].cpu().numpy().view(np.uint32)).all(), "e2e / resident MSE mismatch on %s" % r_.name
             pipe.close()
         if sgp is not None:

@@ -42,7 +42,9 @@ class ContigInput(C.Structure):
                 ("obs", C.c_void_p), ("n_obs", C.c_int64),
                 ("cblocks", C.c_void_p), ("anchors", C.c_void_p), ("n_cblocks", C.c_int64),
                 ("cobs", C.c_void_p), ("cobs_anchors", C.c_void_p), ("n_cobs", C.c_int64),
-                ("region_first_bin", C.c_int32), ("region_n_bins", C.c_int32), ("snp_index_base", C.c_int64)]
+                ("region_first_bin", C.c_int32), ("region_n_bins", C.c_int32), ("snp_index_base", C.c_int64),
+                ("wblocks", C.c_void_p), ("wlens", C.c_void_p), ("wlen_offsets", C.c_void_p), ("n_wlens", C.c_int64),
+                ("wire_default_len", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ResultsDownload(C.Structure):
@@ -51,7 +53,10 @@ class ResultsDownload(C.Structure):
                 ("mse", C.c_void_p),
                 ("h_start", C.c_void_p), ("h_end", C.c_void_p), ("h_scaled", C.c_void_p), ("h_state", C.c_void_p), ("h_cn", C.c_void_p),
                 ("h_mse_rows", C.c_void_p), ("h_mse_vals", C.c_void_p), ("mse_capacity", C.c_int64),
-                ("n_mse_rows", C.c_int64)]
+                ("n_mse_rows", C.c_int64),
+                ("bin_width", C.c_int32), ("reserved", C.c_int32),
+                ("h_run_rows", C.c_void_p), ("h_run_bins", C.c_void_p), ("run_capacity", C.c_int64), ("n_runs", C.c_int64),
+                ("h_se_rows", C.c_void_p), ("h_se_vals", C.c_void_p), ("se_capacity", C.c_int64), ("n_se_rows", C.c_int64)]
 
 
 class Bins(C.Structure):
@@ -83,7 +88,9 @@ HCNV_SEG_AGAIN = 2
 class GenomeOutput(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("start", C.c_void_p), ("end", C.c_void_p), ("scaled", C.c_void_p), ("state", C.c_void_p), ("cn", C.c_void_p),
                 ("mse_rows", C.c_void_p), ("mse_vals", C.c_void_p), ("row_offset", C.c_void_p), ("n_bins", C.c_void_p), ("n_mse_rows", C.c_void_p),
-                ("mean_coverage", C.c_void_p), ("final_loss", C.c_void_p), ("lambda1_used", C.c_void_p), ("lambda2_used", C.c_void_p), ("status", C.c_void_p)]
+                ("mean_coverage", C.c_void_p), ("final_loss", C.c_void_p), ("lambda1_used", C.c_void_p), ("lambda2_used", C.c_void_p), ("status", C.c_void_p),
+                ("run_rows", C.c_void_p), ("run_bins", C.c_void_p), ("se_rows", C.c_void_p), ("se_vals", C.c_void_p),
+                ("n_runs", C.c_void_p), ("n_se_rows", C.c_void_p)]
 
 
 class Config(C.Structure):
@@ -98,13 +105,13 @@ class Config(C.Structure):
 EXPORTS = [
     "hcnv_abi_sizes", "hcnv_ctx_create", "hcnv_ctx_destroy", "hcnv_last_error", "hcnv_strerror", "hcnv_version", "hcnv_ctx_stream",
     "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_ctx_set_kernel_timing", "hcnv_ctx_stat", "hcnv_bin_params_default", "hcnv_bin_contigs",
-    "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_download_results", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
+    "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_download_results", "hcnv_expand_start_end", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
     "hcnv_write_bins_text", "hcnv_write_results_text",
     "hcnv_read_bins_text", "hcnv_bins_text_n_chromosomes", "hcnv_bins_text_get", "hcnv_bins_text_free",
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
     "hcnv_genome_create", "hcnv_genome_run", "hcnv_genome_begin", "hcnv_genome_push", "hcnv_genome_end", "hcnv_genome_kernel_launches", "hcnv_genome_last_error", "hcnv_genome_destroy",
     "hcnv_seg_plan_create", "hcnv_seg_plan_stats", "hcnv_seg_plan_p0", "hcnv_seg_plan_p1", "hcnv_seg_plan_chain", "hcnv_seg_plan_finish", "hcnv_seg_plan_destroy",
-    "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_bam_pack", "hcnv_bam_pack_mt", "hcnv_pack_stats", "hcnv_bam_write_synthetic", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
+    "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_wire_from_cblocks", "hcnv_pack_contig_wire", "hcnv_bam_pack", "hcnv_bam_pack_mt", "hcnv_pack_stats", "hcnv_bam_write_synthetic", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
 ]
 
 _lib = None
@@ -142,6 +149,11 @@ def lib():
     L.hcnv_download_results.argtypes = [C.c_void_p, C.POINTER(ResultsDownload)]
     L.hcnv_compact_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
     L.hcnv_compact_blocks.restype = C.c_int64
+    L.hcnv_wire_from_cblocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    L.hcnv_wire_from_cblocks.restype = C.c_int64
+    L.hcnv_pack_contig_wire.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(ContigInput), C.POINTER(C.c_int32)]
+    L.hcnv_expand_start_end.argtypes = [C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hcnv_compact_obs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
     L.hcnv_compact_obs.restype = C.c_int64
     L.hcnv_ctx_stream.argtypes = [C.c_void_p]

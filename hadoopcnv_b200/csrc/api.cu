@@ -1,6 +1,67 @@
 // api.cu -- the extern "C" surface declared in include/hcnv.h: context management and argument checks.
 #include "hcnv_internal.h"
 
+namespace {
+__global__ void k_move_small(void* dst, const void* src, size_t bytes)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)dst | (uintptr_t)src | bytes) & 15) == 0) {
+        for (size_t i = t; i < bytes / 16; i += nt) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    } else if ((((uintptr_t)dst | (uintptr_t)src | bytes) & 3) == 0) {
+        for (size_t i = t; i < bytes / 4; i += nt) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    } else {
+        for (size_t i = t; i < bytes; i += nt) reinterpret_cast<unsigned char*>(dst)[i] = reinterpret_cast<const unsigned char*>(src)[i];
+    }
+}
+const size_t BOUNCE_BYTES = (size_t)1 << 20;
+// a 64-byte aligned piece of the ring, or null when it is full (or absent)
+void* bounce_take(hcnv_ctx* ctx, size_t bytes) {
+    if (bytes > HCNV_SMALL_MAX) return nullptr;
+    if (!ctx->bounce.p && ctx->bounce.reserve(BOUNCE_BYTES) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    const size_t need = (bytes + 63) & ~(size_t)63;
+    if (ctx->bounce_at + need > BOUNCE_BYTES) return nullptr;
+    void* p = ctx->bounce.as<char>() + ctx->bounce_at;
+    ctx->bounce_at += need;
+    return p;
+}
+int move_small(hcnv_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    const unsigned grid = (unsigned)std::min<size_t>(32, (bytes + 4095) / 4096);
+    k_move_small<<<grid, 256, 0, ctx->stream>>>(dst, src, bytes);
+    HCNV_CUDA(ctx, cudaGetLastError());
+    return HCNV_OK;
+}
+}  // namespace
+
+int hcnv_put_small(hcnv_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (bytes == 0) return HCNV_OK;
+    void* b = bounce_take(ctx, bytes);
+    if (!b) { HCNV_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream)); return HCNV_OK; }
+    memcpy(b, src_host, bytes);
+    return move_small(ctx, dst_dev, b, bytes);
+}
+
+int hcnv_get_small(hcnv_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (bytes == 0) return HCNV_OK;
+    void* b = bounce_take(ctx, bytes);
+    if (!b) { HCNV_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return HCNV_OK; }
+    int rc = move_small(ctx, b, src_dev, bytes);
+    if (rc) return rc;
+    ctx->gets.push_back({dst_host, b, bytes});
+    return HCNV_OK;
+}
+
+void hcnv_flush_gets(hcnv_ctx* ctx) {
+    for (const auto& g : ctx->gets) memcpy(g.dst, g.src, g.bytes);
+    ctx->gets.clear();
+}
+
+int hcnv_sync(hcnv_ctx* ctx) {
+    HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    hcnv_flush_gets(ctx);
+    ctx->bounce_at = 0;                      // every mover kernel has run: the ring is free again
+    return HCNV_OK;
+}
+
 extern "C" {
 
 int hcnv_version(void) { return 100; }
@@ -49,17 +110,20 @@ int hcnv_ctx_create(int device, hcnv_ctx** out) {
     for (int i = 0; i < HCNV_K_COUNT; ++i) {
         if (cudaEventCreate(&c->kt_a[i]) != cudaSuccess || cudaEventCreate(&c->kt_b[i]) != cudaSuccess) { delete c; return HCNV_E_CUDA; }
     }
+    if (cudaEventCreateWithFlags(&c->ev_misc, cudaEventDisableTiming) != cudaSuccess) { delete c; return HCNV_E_CUDA; }
     *out = c;
     return HCNV_OK;
 }
 
 void hcnv_ctx_destroy(hcnv_ctx* c) {
     if (!c) return;
+    c->bounce.release();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& b : c->buf) b.release();
     for (auto& b : c->pin) b.release();
     for (int i = 0; i < HCNV_K_COUNT; ++i) { if (c->kt_a[i]) cudaEventDestroy(c->kt_a[i]); if (c->kt_b[i]) cudaEventDestroy(c->kt_b[i]); }
+    if (c->ev_misc) cudaEventDestroy(c->ev_misc);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;

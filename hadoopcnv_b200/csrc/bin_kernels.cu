@@ -344,6 +344,36 @@ __global__ void k_snp_mse(BinK p) {
 namespace {
 // (scratch slot ids: hcnv_internal.h)
 
+// The wire form (hcnv_wblock, ~1.1 bytes per record) -> hcnv_cblock records, one warp per group of HCNV_CGROUP records: a lane takes
+// four records (one 32-bit load), the lanes' counts of records with their own length byte are scanned across the warp, and
+// each lane writes its four 2-byte records with one 8-byte store.  HBM-bound: 3.2 bytes moved per record.
+struct WireJob { const hcnv_wblock* w; const uint8_t* lens; const int32_t* offs; hcnv_cblock* out; long long n_groups, n_lens; int default_len; };
+
+__global__ void __launch_bounds__(256) k_expand_wire(WireJob j, int32_t* err)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < j.n_groups; g += warps) {
+        const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(j.w) + g * 32 + lane);
+        const int own = 4 - __popc(x & 0x80808080u);                 // records of this lane that take a byte of the side stream
+        int r = own;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, r, d); if (lane >= d) r += t; }
+        const int total = __shfl_sync(0xffffffffu, r, 31);
+        const long long off = j.offs[g];
+        if (off < 0 || off + total > j.n_lens || (long long)j.offs[g + 1] - off != total) { if (lane == 0) atomicOr(&err[ERR_RANGE], 1); continue; }
+        const uint8_t* lp = j.lens + off + (r - own);
+        uint32_t rec[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t byte = (x >> (8 * b)) & 0xFFu;
+            const uint32_t len = (byte & 128u) ? (uint32_t)j.default_len : (uint32_t)__ldg(lp++);
+            rec[b] = (byte & 127u) | (len << 8);
+        }
+        reinterpret_cast<uint2*>(j.out)[g * 32 + lane] = make_uint2(rec[0] | (rec[1] << 16), rec[2] | (rec[3] << 16));
+    }
+}
+
 template <class T>
 int stage_in(hcnv_ctx* ctx, int kind, const T* src, long long n, T* dst) {
     if (n == 0) return HCNV_OK;
@@ -379,8 +409,15 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         if (f >= 0) { if (compact < 0) compact = f; else if (compact != f) return hcnv_fail(ctx, HCNV_E_INVALID, "all contigs of a call must use the same block format"); }
         if (ci.n_cblocks > 0) {
             if (ci.n_cblocks % HCNV_CGROUP) return hcnv_fail(ctx, HCNV_E_INVALID, "n_cblocks must be a multiple of HCNV_CGROUP (pad with fillers)");
+            if (ci.wblocks) {                                  // the wire form: expanded to hcnv_cblock records on the device below
+                if (ci.cblocks) return hcnv_fail(ctx, HCNV_E_INVALID, "give cblocks or wblocks, not both");
+                if (!ci.anchors || !ci.wlen_offsets || ci.n_wlens < 0 || (ci.n_wlens > 0 && !ci.wlens)) return hcnv_fail(ctx, HCNV_E_INVALID, "null wire arrays");
+                if (ci.wire_default_len < 1 || ci.wire_default_len > 255) return hcnv_fail(ctx, HCNV_E_INVALID, "wire_default_len must be in [1, 255]");
+                if (reinterpret_cast<uintptr_t>(ci.wblocks) & 15) return hcnv_fail(ctx, HCNV_E_INVALID, "wblocks must be 16-byte aligned");
+            } else {
             if (!ci.cblocks || !ci.anchors) return hcnv_fail(ctx, HCNV_E_INVALID, "null cblocks / anchors");
             if (reinterpret_cast<uintptr_t>(ci.cblocks) & 15) return hcnv_fail(ctx, HCNV_E_INVALID, "cblocks must be 16-byte aligned");
+            }
             if (ci.n_cblocks >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many records in one contig");
         }
     }
@@ -410,19 +447,23 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     // pointer kinds
     int in_kind = -1;
     long long tot_blocks = 0, tot_cblocks = 0, tot_long = 0, tot_snp = 0, tot_obs = 0, tot_cobs = 0, tot_bins_max = 0;
+    long long tot_wire = 0, tot_wlens = 0, n_wire = 0;
     for (int c = 0; c < n_contigs; ++c) {
         const hcnv_contig_input& ci = contigs[c];
         if (ci.length < 0 || ci.n_blocks < 0 || ci.n_long < 0 || ci.n_snp < 0 || ci.n_obs < 0) return hcnv_fail(ctx, HCNV_E_INVALID, "negative count");
         if (ci.n_blocks >= (1ll << 31) || ci.n_snp >= (1ll << 28)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many records in one contig");
         if (ci.length > 0x7fffffff - 2 * HCNV_SHORT_MAX - 4096 * 128) return hcnv_fail(ctx, HCNV_E_INVALID, "contig too long");
         if (ci.n_blocks && (reinterpret_cast<uintptr_t>(ci.blocks) & 7)) return hcnv_fail(ctx, HCNV_E_INVALID, "blocks must be 8-byte aligned");
-        const void* ptrs[9] = { ci.n_blocks ? (const void*)ci.blocks : nullptr, ci.n_long ? (const void*)ci.long_blocks : nullptr,
-                                ci.n_snp ? (const void*)ci.snp_pos1 : nullptr, ci.n_snp ? (const void*)ci.snp_zyg : nullptr,
-                                ci.n_obs ? (const void*)ci.obs : nullptr, ci.n_cblocks ? (const void*)ci.cblocks : nullptr,
-                                ci.n_cblocks ? (const void*)ci.anchors : nullptr, ci.n_cobs ? (const void*)ci.cobs : nullptr,
-                                ci.n_cobs ? (const void*)ci.cobs_anchors : nullptr };
-        const long long cnts[9] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs, ci.n_cblocks, ci.n_cblocks, ci.n_cobs, ci.n_cobs };
-        for (int j = 0; j < 9; ++j) {
+        const bool wire = ci.n_cblocks > 0 && ci.wblocks;
+        const void* ptrs[11] = { ci.n_blocks ? (const void*)ci.blocks : nullptr, ci.n_long ? (const void*)ci.long_blocks : nullptr,
+                                 ci.n_snp ? (const void*)ci.snp_pos1 : nullptr, ci.n_snp ? (const void*)ci.snp_zyg : nullptr,
+                                 ci.n_obs ? (const void*)ci.obs : nullptr, ci.n_cblocks ? (wire ? (const void*)ci.wblocks : (const void*)ci.cblocks) : nullptr,
+                                 ci.n_cblocks ? (const void*)ci.anchors : nullptr, ci.n_cobs ? (const void*)ci.cobs : nullptr,
+                                 ci.n_cobs ? (const void*)ci.cobs_anchors : nullptr, wire ? (const void*)ci.wlen_offsets : nullptr,
+                                 wire && ci.n_wlens ? (const void*)ci.wlens : nullptr };
+        const long long cnts[11] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs, ci.n_cblocks, ci.n_cblocks, ci.n_cobs, ci.n_cobs, wire ? 1 : 0, wire ? ci.n_wlens : 0 };
+        if (wire) { tot_wire += ci.n_cblocks; tot_wlens += (ci.n_wlens + 15) / 16 * 16; ++n_wire; }
+        for (int j = 0; j < 11; ++j) {
             if (cnts[j] == 0) continue;
             if (!ptrs[j]) return hcnv_fail(ctx, HCNV_E_INVALID, "null input array with non-zero count");
             int kd = hcnv_ptr_kind(ptrs[j]) == 2 ? 2 : 0;
@@ -440,6 +481,10 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
 
     // stage inputs that live on the host
     std::vector<ContigDev> hc(n_contigs);
+    std::vector<WireJob> wire_jobs;
+    if (in_kind == 2 && n_wire) HCNV_CUDA(ctx, ctx->buf[B_IN_BLOCKS].reserve(sizeof(hcnv_cblock) * (size_t)tot_cblocks));   // where device-resident wire streams expand to
+    if (in_kind != 2 && n_wire) HCNV_CUDA(ctx, ctx->buf[B_IN_WIRE].reserve((size_t)tot_wire + (size_t)tot_wlens + 4 * (size_t)(tot_wire / HCNV_CGROUP + n_wire) + 64));
+    long long ow = 0, owl = 0, owo = 0;
     if (in_kind != 2) {
         HCNV_CUDA(ctx, ctx->buf[B_IN_BLOCKS].reserve(sizeof(hcnv_block) * (size_t)tot_blocks + sizeof(hcnv_cblock) * (size_t)tot_cblocks));
         HCNV_CUDA(ctx, ctx->buf[B_IN_ANCHORS].reserve(4 * (size_t)(tot_cblocks / HCNV_CGROUP) + 16));
@@ -459,6 +504,10 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         if (in_kind == 2) {
             d.blocks = ci.blocks; d.longs = ci.long_blocks; d.snp_pos = ci.snp_pos1; d.snp_zyg = ci.snp_zyg; d.obs = ci.obs;
             d.cblocks = ci.cblocks; d.anchors = ci.anchors;
+            if (ci.n_cblocks > 0 && ci.wblocks) {
+                d.cblocks = ctx->buf[B_IN_BLOCKS].as<hcnv_cblock>() + ocb;
+                wire_jobs.push_back(WireJob{ ci.wblocks, ci.wlens, ci.wlen_offsets, const_cast<hcnv_cblock*>(d.cblocks), ci.n_cblocks / HCNV_CGROUP, ci.n_wlens, ci.wire_default_len });
+            }
             d.cobs = ci.n_cobs ? ci.cobs : nullptr; d.cobs_anchors = ci.cobs_anchors;
         } else {
             d.cblocks = ctx->buf[B_IN_BLOCKS].as<hcnv_cblock>() + ocb;            // (a call uses one form, so the buffer is shared)
@@ -470,6 +519,18 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             d.obs = ctx->buf[B_IN_OBS].as<uint32_t>() + oo;
             int rc;
             if ((rc = stage_in(ctx, in_kind, ci.blocks, ci.n_blocks, const_cast<hcnv_block*>(d.blocks)))) return rc;
+            if (ci.n_cblocks > 0 && ci.wblocks) {
+                char* const wb = ctx->buf[B_IN_WIRE].as<char>();                  // wire bytes | length bytes | offsets
+                hcnv_wblock* dw = reinterpret_cast<hcnv_wblock*>(wb) + ow;
+                uint8_t* dl = reinterpret_cast<uint8_t*>(wb + tot_wire) + owl;
+                int32_t* dof = reinterpret_cast<int32_t*>(wb + tot_wire + tot_wlens) + owo;
+                const long long ng = ci.n_cblocks / HCNV_CGROUP;
+                if ((rc = stage_in(ctx, in_kind, ci.wblocks, ci.n_cblocks, dw))) return rc;
+                if ((rc = stage_in(ctx, in_kind, ci.wlens, ci.n_wlens, dl))) return rc;
+                if ((rc = stage_in(ctx, in_kind, ci.wlen_offsets, ng + 1, dof))) return rc;
+                wire_jobs.push_back(WireJob{ dw, dl, dof, const_cast<hcnv_cblock*>(d.cblocks), ng, ci.n_wlens, ci.wire_default_len });
+                ow += ci.n_cblocks; owl += (ci.n_wlens + 15) / 16 * 16; owo += ng + 1;
+            } else
             if ((rc = stage_in(ctx, in_kind, ci.cblocks, ci.n_cblocks, const_cast<hcnv_cblock*>(d.cblocks)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.anchors, ci.n_cblocks / HCNV_CGROUP, const_cast<int32_t*>(d.anchors)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.long_blocks, ci.n_long, const_cast<hcnv_long_block*>(d.longs)))) return rc;
@@ -500,7 +561,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
 
     BinK k{};
     HCNV_CUDA(ctx, ctx->buf[B_CONTIGS].reserve(sizeof(ContigDev) * (size_t)n_contigs));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(ctx->buf[B_CONTIGS].p, hc.data(), sizeof(ContigDev) * (size_t)n_contigs, cudaMemcpyHostToDevice, ctx->stream));
+    { int rc_ = hcnv_put_small(ctx, ctx->buf[B_CONTIGS].p, hc.data(), sizeof(ContigDev) * (size_t)n_contigs); if (rc_) return rc_; }
     HCNV_CUDA(ctx, ctx->buf[B_TILEIDX].reserve(sizeof(TileRec) * (size_t)n_tiles));
     HCNV_CUDA(ctx, ctx->buf[B_SNPDEPTH].reserve(4 * (size_t)(tot_snp + 1)));
     HCNV_CUDA(ctx, ctx->buf[B_TALLY].reserve(64 * (size_t)(tot_snp + 1)));
@@ -545,6 +606,12 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     HCNV_CUDA(ctx, cudaMemsetAsync(k.status, 0, 8 * n_status, ctx->stream));
     if (tot_snp) HCNV_CUDA(ctx, cudaMemsetAsync(k.tally, 0, 64 * (size_t)tot_snp, ctx->stream));
 
+    for (const WireJob& wj : wire_jobs) {
+        const int grid = (int)std::max<long long>(1, std::min<long long>((wj.n_groups + 7) / 8, (long long)ctx->sm_count * 8));
+        k_expand_wire<<<grid, 256, 0, ctx->stream>>>(wj, k.err);
+        HCNV_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     KT_BEGIN(ctx, HCNV_K_TILE_INDEX);
     k_tile_index<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(k);
     KT_END(ctx, HCNV_K_TILE_INDEX);
@@ -592,8 +659,8 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     // results: error flags + contig offsets always come back to the host
     HCNV_CUDA(ctx, ctx->pin[0].reserve(128 + 8 * (size_t)(n_contigs + 1)));
     char* hm = ctx->pin[0].as<char>();
-    HCNV_CUDA(ctx, cudaMemcpyAsync(hm, misc, 128 + 8 * (size_t)(n_contigs + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    { int rc_ = hcnv_get_small(ctx, hm, misc, 128 + 8 * (size_t)(n_contigs + 1)); if (rc_) return rc_; }
+    { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
     const int32_t* herr = (const int32_t*)hm;
     if (herr[ERR_INTERNAL]) return hcnv_fail(ctx, HCNV_E_INTERNAL, herr[ERR_INTERNAL] & 2 ? "a bin with SNP sites has no output row" : "look-back spin limit reached");
     if (herr[ERR_UNSORTED]) return hcnv_fail(ctx, HCNV_E_UNSORTED, "blocks or SNP table not sorted by position");
@@ -614,7 +681,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         HCNV_CUDA(ctx, cudaMemcpyAsync(out->median, k.o_median, 4 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
         HCNV_CUDA(ctx, cudaMemcpyAsync(out->mse, k.o_mse, 48 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
         HCNV_CUDA(ctx, cudaMemcpyAsync(out->total, k.o_total, 8 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
     }
     return HCNV_OK;
 }

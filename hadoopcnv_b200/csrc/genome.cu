@@ -25,7 +25,7 @@ struct hcnv_genome {
     int device = 0;
     std::vector<hcnv_ctx*> ctx;                   // one per worker
     cudaStream_t copy = nullptr;
-    std::vector<DevBuf> stage;                    // 9 per contig: blocks, long, snp_pos, snp_zyg, obs, cblocks, anchors, cobs, cobs_anchors
+    std::vector<DevBuf> stage;                    // ST_N per contig: blocks, long, snp_pos, snp_zyg, obs, cblocks, anchors, cobs, cobs_anchors, wire form (3)
     std::vector<cudaEvent_t> landed;              // one per contig
     // The upload is PACED: pieces of piece_bytes, at most `depth` of them queued on the copy stream at any time.  With everything
     // queued at once (1.4 GB), a copy engine that serves its queue in submission order makes every other copy of the process -- the
@@ -35,6 +35,7 @@ struct hcnv_genome {
     // as bad as one huge one); HCNV_UPLOAD_PIECE_MB / HCNV_UPLOAD_DEPTH override.
     size_t piece_bytes = (size_t)64 << 20;
     int depth = 2;
+    double taper = 0.85;                          // hcnv_genome_run's task sizes: group k ~ taper^k of the genome (HCNV_GENOME_TAPER)
     std::vector<cudaEvent_t> ring;                // one event per piece in flight
     size_t ring_pos = 0;
     std::deque<UploadJob> jobs;
@@ -52,7 +53,9 @@ struct hcnv_genome {
     std::vector<long long> cap;
     std::vector<hcnv_contig_input> dev_in;
     long long task_rows_hint = 0;
-    std::deque<GenomeTask> queue;
+    std::vector<std::deque<GenomeTask>> queue;   // one per worker: task k goes to worker k mod workers, so that from the second
+                                                 // sample on every worker has seen its tasks' sizes (grow-only scratch: no cudaMalloc in the steady state)
+    size_t n_tasks = 0;
     std::condition_variable cv;
     std::vector<std::thread> workers;
     std::atomic<int> worst{HCNV_OK};
@@ -62,7 +65,7 @@ struct hcnv_genome {
 };
 
 namespace {
-enum { ST_BLOCKS = 0, ST_LONG, ST_SNPPOS, ST_SNPZYG, ST_OBS, ST_CBLOCKS, ST_ANCHORS, ST_COBS, ST_COBSANC, ST_N };
+enum { ST_BLOCKS = 0, ST_LONG, ST_SNPPOS, ST_SNPZYG, ST_OBS, ST_CBLOCKS, ST_ANCHORS, ST_COBS, ST_COBSANC, ST_WBLOCKS, ST_WLENS, ST_WOFFS, ST_N };
 
 struct Field { const void* src; size_t bytes; };
 
@@ -72,7 +75,11 @@ void contig_fields(const hcnv_contig_input& c, Field f[ST_N]) {
     f[ST_SNPPOS]  = { c.snp_pos1, 4 * (size_t)c.n_snp };
     f[ST_SNPZYG]  = { c.snp_zyg, (size_t)c.n_snp };
     f[ST_OBS]     = { c.obs, 4 * (size_t)c.n_obs };
-    f[ST_CBLOCKS] = { c.cblocks, sizeof(hcnv_cblock) * (size_t)c.n_cblocks };
+    const bool wire = c.wblocks != nullptr && c.n_cblocks > 0;                   // the block stream in its wire form (hcnv_wblock)
+    f[ST_CBLOCKS] = { c.cblocks, wire ? 0 : sizeof(hcnv_cblock) * (size_t)c.n_cblocks };
+    f[ST_WBLOCKS] = { c.wblocks, wire ? (size_t)c.n_cblocks : 0 };
+    f[ST_WLENS]   = { c.wlens, wire ? (size_t)std::max<int64_t>(c.n_wlens, 0) : 0 };
+    f[ST_WOFFS]   = { c.wlen_offsets, wire ? 4 * (size_t)(c.n_cblocks / HCNV_CGROUP + 1) : 0 };
     f[ST_ANCHORS] = { c.anchors, 4 * (size_t)(c.n_cblocks / HCNV_CGROUP) };
     f[ST_COBS]    = { c.cobs, sizeof(hcnv_cobs) * (size_t)c.n_cobs };
     f[ST_COBSANC] = { c.cobs_anchors, 4 * (size_t)(c.n_cobs / HCNV_OGROUP) };
@@ -160,6 +167,7 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
     // the task's records are on the device once its last chromosome's event has fired (uploads are in order)
     if (cudaStreamWaitEvent(ctx->stream, g->landed[(size_t)gr.back()], 0) != cudaSuccess) { ctx->err = "cudaStreamWaitEvent"; fail(HCNV_E_CUDA, "wait"); return; }
     if (g->trace) { cudaStreamSynchronize(ctx->stream); t_wait = now_ms(); }
+    if (getenv("HCNV_GENOME_UPLOAD_ONLY")) { cudaStreamSynchronize(ctx->stream); return; }      // (diagnostic: the upload's own time)
     std::vector<hcnv_contig_input> in;
     for (int c : gr) in.push_back(g->dev_in[(size_t)c]);
     std::vector<int64_t> off(gr.size() + 1, 0);
@@ -185,18 +193,32 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
     rc = hcnv_segment_batch_impl(ctx, g->alpha, (int32_t)probs.size(), probs.data(), 0);
     if (rc < 0 && rc != HCNV_E_NO_MINIMUM) { fail(rc, "hcnv_segment_batch"); return; }
     if (g->trace) t_seg = now_ms();
+    // every chromosome's rows straight into the caller's arrays; two host round trips for the whole task
+    std::vector<hcnv_results_download> dl(live.size());
     for (size_t k = 0; k < live.size(); ++k) {
         const size_t j = (size_t)live[k];
         const int c = gr[j];
         const int64_t a = off[j], nb = off[j + 1] - off[j], o = out->row_offset[c];
-        hcnv_results_download d{};
+        hcnv_results_download& d = dl[k];
+        d = hcnv_results_download{};
         d.n = nb; d.start = bins.start + a; d.end = bins.end + a; d.scaled = scaled + a; d.state = state + a; d.cn = cn + a; d.mse = m32 + 6 * a;
-        d.h_start = out->start + o; d.h_end = out->end + o; d.h_scaled = out->scaled + o; d.h_state = out->state + o;
+        d.h_scaled = out->scaled + o; d.h_state = out->state + o;
         d.h_cn = out->cn ? out->cn + o : nullptr;
         d.h_mse_rows = out->mse_rows + o; d.h_mse_vals = out->mse_vals + 6 * o; d.mse_capacity = nb;
-        rc = hcnv_download_results_impl(ctx, &d);
-        if (rc) { fail(rc, "hcnv_download_results"); return; }
-        out->n_bins[c] = nb; out->n_mse_rows[c] = d.n_mse_rows;
+        if (out->start) { d.h_start = out->start + o; d.h_end = out->end + o; }
+        else {
+            d.bin_width = g->P.bin_width;
+            d.h_run_rows = out->run_rows + o; d.h_run_bins = out->run_bins + o; d.run_capacity = nb;
+            d.h_se_rows = out->se_rows + o; d.h_se_vals = out->se_vals + 2 * o; d.se_capacity = nb;
+        }
+    }
+    if (getenv("HCNV_GENOME_NO_DOWNLOAD")) { cudaStreamSynchronize(ctx->stream); return; }      // (diagnostic)
+    rc = hcnv_download_results_many_impl(ctx, (int32_t)dl.size(), dl.data());
+    if (rc) { fail(rc, "hcnv_download_results"); return; }
+    for (size_t k = 0; k < live.size(); ++k) {
+        const int c = gr[(size_t)live[k]];
+        out->n_bins[c] = dl[k].n; out->n_mse_rows[c] = dl[k].n_mse_rows;
+        if (!out->start) { out->n_runs[c] = dl[k].n_runs; out->n_se_rows[c] = dl[k].n_se_rows; }
         const hcnv_segment_problem& q = probs[k];
         if (out->status) out->status[c] = q.status;
         if (out->mean_coverage) out->mean_coverage[c] = q.mean_coverage;
@@ -219,10 +241,11 @@ static void genome_worker(hcnv_genome* g, int w) {
         GenomeTask task;
         {
             std::unique_lock<std::mutex> lk(g->mu);
-            g->cv.wait(lk, [g] { return !g->queue.empty() || g->closed; });
-            if (g->queue.empty()) return;
-            task = std::move(g->queue.front());
-            g->queue.pop_front();
+            std::deque<GenomeTask>& q = g->queue[(size_t)w];
+            g->cv.wait(lk, [&] { return !q.empty() || g->closed; });
+            if (q.empty()) return;
+            task = std::move(q.front());
+            q.pop_front();
         }
         if (g->worst.load() == HCNV_OK) genome_task(g, w, task);
     }
@@ -237,8 +260,10 @@ int hcnv_genome_begin(hcnv_genome* g, const hcnv_bin_params* params, float lambd
                       int32_t n_contigs, const int32_t* lengths, int64_t max_task_rows, hcnv_genome_output* out) {
     if (!g || n_contigs <= 0 || !lengths || !out) return HCNV_E_INVALID;
     if (g->open) return genome_fail(g, HCNV_E_INVALID, "hcnv_genome_begin: a sample is already in flight");
-    if (!out->start || !out->end || !out->scaled || !out->state || !out->mse_rows || !out->mse_vals || !out->row_offset || !out->n_bins || !out->n_mse_rows)
+    if (!out->scaled || !out->state || !out->mse_rows || !out->mse_vals || !out->row_offset || !out->n_bins || !out->n_mse_rows)
         return genome_fail(g, HCNV_E_INVALID, "null output array");
+    if (out->start ? !out->end : (!out->run_rows || !out->run_bins || !out->se_rows || !out->se_vals || !out->n_runs || !out->n_se_rows))
+        return genome_fail(g, HCNV_E_INVALID, "null start / end arrays (dense: start, end; implicit: run_rows, run_bins, se_rows, se_vals, n_runs, n_se_rows)");
     if (cudaSetDevice(g->device) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaSetDevice failed");
     g->err.clear();
     if (params) g->P = *params; else hcnv_bin_params_default(&g->P);
@@ -251,6 +276,7 @@ int hcnv_genome_begin(hcnv_genome* g, const hcnv_bin_params* params, float lambd
         if (lengths[c] < 0) return genome_fail(g, HCNV_E_INVALID, "negative contig length");
         g->cap[(size_t)c] = lengths[c] / W + 1;
         out->row_offset[c] = total_cap; out->n_bins[c] = 0; out->n_mse_rows[c] = 0;
+        if (!out->start) { out->n_runs[c] = 0; out->n_se_rows[c] = 0; }
         if (out->status) out->status[c] = HCNV_OK;
         if (out->mean_coverage) out->mean_coverage[c] = 0.f;
         if (out->final_loss) out->final_loss[c] = 0.f;
@@ -268,15 +294,15 @@ int hcnv_genome_begin(hcnv_genome* g, const hcnv_bin_params* params, float lambd
     g->dev_in.assign((size_t)n_contigs, hcnv_contig_input{});
     g->lambda1 = lambda1; g->lambda2 = lambda2; g->alpha = alpha; g->n_contigs = n_contigs; g->out = *out;
     g->task_rows_hint = max_task_rows;
-    while (g->ring.size() < 16) {
+    while (g->ring.size() < 32) {
         cudaEvent_t e = nullptr;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return genome_fail(g, HCNV_E_CUDA, "cudaEventCreate failed");
         g->ring.push_back(e);
     }
     g->ring_pos = 0;
     if (const char* e = getenv("HCNV_UPLOAD_PIECE_MB")) g->piece_bytes = (size_t)std::max(1, atoi(e)) << 20;
-    if (const char* e = getenv("HCNV_UPLOAD_DEPTH")) g->depth = std::max(1, std::min((int)g->ring.size(), atoi(e)));
-    g->worst = HCNV_OK; g->closed = false; g->queue.clear(); g->jobs.clear(); g->jobs_closed = false;
+    if (const char* e = getenv("HCNV_UPLOAD_DEPTH")) g->depth = std::max(1, std::min(16, atoi(e)));
+    g->worst = HCNV_OK; g->closed = false; g->queue.assign(g->ctx.size(), {}); g->n_tasks = 0; g->jobs.clear(); g->jobs_closed = false;
     g->trace = getenv("HCNV_GENOME_TRACE") != nullptr; g->t0 = std::chrono::steady_clock::now(); g->trace_lines.clear();
     g->uploader = std::thread(genome_uploader, g);
     for (size_t w = 0; w < g->ctx.size(); ++w) g->workers.emplace_back(genome_worker, g, (int)w);
@@ -291,7 +317,9 @@ static void genome_uploader(hcnv_genome* g) {
         genome_fail(g, rc, what);
         int expect = HCNV_OK; g->worst.compare_exchange_strong(expect, rc);
     };
-    size_t in_flight = 0;
+    std::deque<std::pair<size_t, size_t>> fly;      // (ring slot, bytes) of the pieces queued on the copy stream, oldest first
+    size_t fly_bytes = 0;
+    const size_t budget = g->piece_bytes * (size_t)g->depth;
     for (;;) {
         UploadJob job;
         {
@@ -317,12 +345,18 @@ static void genome_uploader(hcnv_genome* g) {
                 d[q] = b.p;
                 for (size_t o = 0; o < f[q].bytes && ok; o += g->piece_bytes) {
                     const size_t nb = std::min(g->piece_bytes, f[q].bytes - o);
-                    cudaEvent_t ev = g->ring[g->ring_pos];
-                    if (in_flight >= (size_t)g->depth) cudaEventSynchronize(ev);        // the oldest piece in flight has landed
+                    // wait until the pieces in flight leave room: at most depth x piece_bytes queued (small arrays ride along, up to the ring's size)
+                    while (!fly.empty() && (fly_bytes + nb > budget || fly.size() >= g->ring.size())) {
+                        cudaEventSynchronize(g->ring[fly.front().first]);
+                        fly_bytes -= fly.front().second;
+                        fly.pop_front();
+                    }
+                    const size_t slot = g->ring_pos;
+                    g->ring_pos = (g->ring_pos + 1) % g->ring.size();
                     if (cudaMemcpyAsync((char*)b.p + o, (const char*)f[q].src + o, nb, cudaMemcpyHostToDevice, g->copy) != cudaSuccess ||
-                        cudaEventRecord(ev, g->copy) != cudaSuccess) { fail(HCNV_E_CUDA, "upload failed"); ok = false; break; }
-                    g->ring_pos = (g->ring_pos + 1) % (size_t)g->depth;        // (the event in this slot is the one recorded `depth` pieces ago)
-                    if (in_flight < (size_t)g->depth) ++in_flight;
+                        cudaEventRecord(g->ring[slot], g->copy) != cudaSuccess) { fail(HCNV_E_CUDA, "upload failed"); ok = false; break; }
+                    fly.emplace_back(slot, nb);
+                    fly_bytes += nb;
                 }
             }
             if (!ok) break;
@@ -333,11 +367,12 @@ static void genome_uploader(hcnv_genome* g) {
             di.snp_pos1 = (const int32_t*)d[ST_SNPPOS]; di.snp_zyg = (const int8_t*)d[ST_SNPZYG]; di.obs = (const uint32_t*)d[ST_OBS];
             di.cblocks = (const hcnv_cblock*)d[ST_CBLOCKS]; di.anchors = (const int32_t*)d[ST_ANCHORS];
             di.cobs = (const hcnv_cobs*)d[ST_COBS]; di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
+            di.wblocks = (const hcnv_wblock*)d[ST_WBLOCKS]; di.wlens = (const uint8_t*)d[ST_WLENS]; di.wlen_offsets = (const int32_t*)d[ST_WOFFS];
             task.contigs.push_back(c);
         }
         if (!ok || task.contigs.empty()) continue;
-        { std::lock_guard<std::mutex> lk(g->mu); g->queue.push_back(std::move(task)); }     // (its last chromosome's event is recorded: a worker may wait on it)
-        g->cv.notify_one();
+        { std::lock_guard<std::mutex> lk(g->mu); g->queue[g->n_tasks++ % g->queue.size()].push_back(std::move(task)); }     // (its last chromosome's event is recorded: a worker may wait on it)
+        g->cv.notify_all();
         if (g->trace) fprintf(stderr, "group of %zu contigs queued on the copy stream at %.2f ms\n", job.contigs.size(),
                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g->t0).count());
     }
@@ -395,10 +430,16 @@ int hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1
     const int W = params && params->bin_width > 0 ? params->bin_width : 100;
     std::vector<std::vector<int>> groups;
     {
+        // group k's share of the genome ~ taper^k: later groups smaller (taper < 1), so that what is left to do when the upload ends
+        // is little, while the early groups stay large (a task's chain kernels cost their longest chromosome whatever else rides along)
+        double taper = g->taper;
+        if (const char* e = getenv("HCNV_GENOME_TAPER")) taper = std::max(0.3, std::min(1.0, atof(e)));
+        std::vector<double> upto((size_t)NG);
+        { double s = 0, w = 1; for (int k = 0; k < NG; ++k) { s += w; upto[(size_t)k] = s; w *= taper; } for (double& u : upto) u /= s; }
         std::vector<int> cur; long long acc = 0;
         for (int c : order) {
             cur.push_back(c); acc += contigs[c].length;
-            if (acc * NG >= std::max<long long>(total_len, 1) * (long long)(groups.size() + 1)) { groups.push_back(cur); cur.clear(); }
+            if ((double)acc >= (double)std::max<long long>(total_len, 1) * upto[std::min(groups.size(), (size_t)NG - 1)] - 0.5) { groups.push_back(cur); cur.clear(); }
         }
         if (!cur.empty()) groups.push_back(cur);
         // The LAST task is the only one nothing hides (it starts when the upload ends).  Halving the last group to make it small

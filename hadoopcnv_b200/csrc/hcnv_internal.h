@@ -44,7 +44,7 @@ struct PinBuf {
 enum {
     // binning (bin_kernels.cu)
     B_CONTIGS = 0, B_TILEIDX, B_TALLY, B_STATUS, B_MISC, B_IN_BLOCKS, B_IN_LONG, B_IN_SNPPOS, B_IN_SNPZYG, B_IN_OBS,
-    B_OUT_I32, B_OUT_F32, B_OUT_F64, B_SNPDEPTH, B_IN_ANCHORS,
+    B_OUT_I32, B_OUT_F32, B_OUT_F64, B_SNPDEPTH, B_IN_ANCHORS, B_IN_WIRE,
     // segmentation (hmm_kernels.cu)
     H_PROBS, H_BLKMAP, H_CODES, H_SCALED, H_IN_F32, H_IN_I32, H_OUT_I32, H_RT_IN, H_RT_OUT, H_VPAR, H_RT_WORK, H_ORDER, H_DOWNLOAD,
     // genome pipeline (genome.cu)
@@ -68,6 +68,12 @@ struct hcnv_ctx {
     cudaEvent_t  kt_a[HCNV_K_COUNT] = {};  // per-kernel start/stop events on `stream`
     cudaEvent_t  kt_b[HCNV_K_COUNT] = {};
     bool         kt_valid[HCNV_K_COUNT] = {};
+    // small transfers that bypass the copy engines (hcnv_put_small / hcnv_get_small below)
+    PinBuf       bounce;                   // mapped pinned ring
+    size_t       bounce_at = 0;
+    struct PendingGet { void* dst; const void* src; size_t bytes; };
+    std::vector<PendingGet> gets;          // host destinations to fill from the ring at the next hcnv_sync
+    cudaEvent_t  ev_misc = nullptr;        // a host wait on a point of `stream` that is not its end (hcnv_download_results_many_impl)
     uint32_t     kt_mask = 1u << HCNV_K_BIN_TILES;   // which kernels get timing events (default: the dominant one only)
 };
 // per-kernel timing events are recorded only for the kernels selected in kt_mask (hcnv_ctx_set_kernel_timing): an event
@@ -109,7 +115,19 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
                           const hcnv_contig_input* contigs, hcnv_bins* out);
 int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, const double* total,
                                 float* mse_f32, float* total_f32);
+// Small host<->device transfers WITHOUT the copy engines.  In hcnv_genome_run the engines' queues hold the bulk uploads and the
+// other workers' downloads (tens of MB each, FIFO per engine), and a 200-byte descriptor table or an 8-byte count queued behind
+// them waits a millisecond -- several times per task.  Instead a few-thread kernel moves the bytes between device memory and a
+// mapped pinned ring (the device reads / writes host memory directly over PCIe).  hcnv_put_small: the bytes are captured at the
+// call (src may be reused at once).  hcnv_get_small: dst is filled by the next hcnv_sync / hcnv_flush_gets.  Transfers above
+// HCNV_SMALL_MAX bytes, or when the ring is full, fall back to cudaMemcpyAsync on the stream (dst then needs the same sync).
+#define HCNV_SMALL_MAX ((size_t)96 << 10)
+int hcnv_put_small(hcnv_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int hcnv_get_small(hcnv_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+void hcnv_flush_gets(hcnv_ctx* ctx);                 // after the caller has waited for the transfers (event or stream)
+int hcnv_sync(hcnv_ctx* ctx);                        // cudaStreamSynchronize(ctx->stream) + hcnv_flush_gets + ring reset
 int hcnv_download_results_impl(hcnv_ctx* ctx, hcnv_results_download* d);
+int hcnv_download_results_many_impl(hcnv_ctx* ctx, int32_t count, hcnv_results_download* ds);
 int hcnv_segment_batch_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_problem* problems,
                             int32_t flags);
 int  hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hcnv_segment_part* parts, int32_t flags, hcnv_seg_plan** out);

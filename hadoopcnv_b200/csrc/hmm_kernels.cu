@@ -683,32 +683,52 @@ __global__ void __launch_bounds__(256) k_traceback(SegDev* probs, const int* __r
 #include "viterbi_par.cuh"
 #include "viterbi_chain.cuh"
 
-// results download: int8 calls and the non-zero MSE rows (row, six values), compacted per warp with one atomic
+// results download: int8 calls, the non-zero MSE rows (row, six values) and -- in the implicit form of start / end (W > 0) -- the
+// rows that begin a run of consecutive bins and the rows that are not full; every list compacted per warp with one atomic
+struct PackLists { int32_t* mse_rows; float* mse_vals; int32_t* run_rows; int32_t* run_bins; int32_t* se_rows; int32_t* se_vals;
+                   long long mse_cap, run_cap, se_cap; unsigned long long* count; };   // count[0..2] = MSE rows, runs, start/end rows
+
+__device__ __forceinline__ long long pack_slot(bool mine, unsigned long long* counter, int lane) {
+    const unsigned ball = __ballot_sync(0xffffffffu, mine);
+    if (!ball) return -1;
+    unsigned long long base = 0;
+    const int leader = __ffs((int)ball) - 1;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(ball));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return mine ? (long long)base + __popc(ball & ((1u << lane) - 1u)) : -1;
+}
+
 __global__ void k_pack_results(long long n, const int32_t* __restrict__ state, const int32_t* __restrict__ cn, const float* __restrict__ mse,
-                               int8_t* __restrict__ state8, int8_t* __restrict__ cn8, int32_t* __restrict__ rows, float* __restrict__ vals,
-                               unsigned long long* __restrict__ count, long long capacity) {
+                               const int32_t* __restrict__ start, const int32_t* __restrict__ end, int W,
+                               int8_t* __restrict__ state8, int8_t* __restrict__ cn8, PackLists L) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool nz = false;
+    bool nz = false, run = false, part = false;
     float m[6] = {0, 0, 0, 0, 0, 0};
+    int s0 = 0, e0 = 0, id = 0;
     if (i < n) {
         state8[i] = (int8_t)state[i];
         cn8[i] = (int8_t)cn[i];
         #pragma unroll
         for (int c = 0; c < 6; ++c) { m[c] = __ldg(&mse[i * 6 + c]); nz |= __float_as_uint(m[c]) != 0u; }   // (-0.0 and NaN are listed too)
-    }
-    const unsigned ball = __ballot_sync(0xffffffffu, nz);
-    if (!ball) return;
-    unsigned long long base = 0;
-    if (lane == __ffs((int)ball) - 1) base = atomicAdd(count, (unsigned long long)__popc(ball));
-    base = __shfl_sync(0xffffffffu, base, __ffs((int)ball) - 1);
-    if (nz) {
-        const long long k = (long long)base + __popc(ball & ((1u << lane) - 1u));
-        if (k < capacity) {
-            rows[k] = (int32_t)i;
-            #pragma unroll
-            for (int c = 0; c < 6; ++c) vals[k * 6 + c] = m[c];
+        if (W > 0) {
+            s0 = start[i]; e0 = end[i];
+            id = s0 / W * W;
+            run = i == 0 || id != start[i - 1] / W * W + W;
+            part = s0 != (id > 1 ? id : 1) || e0 != id + W - 1;
         }
+    }
+    long long k = pack_slot(nz, L.count + 0, lane);
+    if (k >= 0 && k < L.mse_cap) {
+        L.mse_rows[k] = (int32_t)i;
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) L.mse_vals[k * 6 + c] = m[c];
+    }
+    if (W > 0) {
+        k = pack_slot(run, L.count + 1, lane);
+        if (k >= 0 && k < L.run_cap) { L.run_rows[k] = (int32_t)i; L.run_bins[k] = id; }
+        k = pack_slot(part, L.count + 2, lane);
+        if (k >= 0 && k < L.se_cap) { L.se_rows[k] = (int32_t)i; L.se_vals[2 * k] = s0; L.se_vals[2 * k + 1] = e0; }
     }
 }
 
@@ -751,13 +771,13 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
     // overflowed (more than one value in seven exactly half way between two floats) is everything redone the slow way
     HCNV_CUDA(ctx, ctx->pin[1].reserve(64));
     unsigned long long* h_wn = ctx->pin[1].as<unsigned long long>();
-    HCNV_CUDA(ctx, cudaMemcpyAsync(h_wn, d_wn, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    { int rc_ = hcnv_get_small(ctx, h_wn, d_wn, 8); if (rc_) return rc_; }
     auto download = [&]() -> int {
         if (!dev) {
             HCNV_CUDA(ctx, cudaMemcpyAsync(mse_f32, d_m32, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
             if (total) HCNV_CUDA(ctx, cudaMemcpyAsync(total_f32, d_t32, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         }
-        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
         return HCNV_OK;
     };
     int rc = download();
@@ -771,44 +791,107 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
     return HCNV_OK;
 }
 
+// several chromosomes' results with two host round trips in all (one for the lengths of the lists, one at the end)
+int hcnv_download_results_many_impl(hcnv_ctx* ctx, int32_t count, hcnv_results_download* ds)
+{
+    if (!ctx || count < 0 || (count > 0 && !ds)) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    // device staging per chromosome: [MSE values | MSE rows | run rows | run bins | se rows | se vals | state8 | cn8]
+    auto caps = [](const hcnv_results_download& d, size_t& mc, size_t& rc, size_t& sc) {
+        mc = (size_t)std::min<long long>(std::max<long long>(d.mse_capacity, 0), d.n);
+        rc = d.bin_width > 0 ? (size_t)std::min<long long>(std::max<long long>(d.run_capacity, 0), d.n) : 0;
+        sc = d.bin_width > 0 ? (size_t)std::min<long long>(std::max<long long>(d.se_capacity, 0), d.n) : 0;
+    };
+    size_t need = 64 + 32 * (size_t)count;
+    for (int i = 0; i < count; ++i) {
+        hcnv_results_download* d = &ds[i];
+        d->n_mse_rows = 0; d->n_runs = 0; d->n_se_rows = 0;
+        if (d->n < 0 || d->n >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "row count");
+        if (d->n == 0) continue;
+        const bool implicit = d->bin_width > 0;
+        if (!d->start || !d->end || !d->scaled || !d->state || !d->cn || !d->mse || !d->h_scaled || !d->h_state || !d->h_mse_rows || !d->h_mse_vals)
+            return hcnv_fail(ctx, HCNV_E_INVALID, "null array");                                    // (h_cn may be null: cn is a table look-up of state)
+        if (implicit ? (!d->h_run_rows || !d->h_run_bins || !d->h_se_rows || !d->h_se_vals) : (!d->h_start || !d->h_end))
+            return hcnv_fail(ctx, HCNV_E_INVALID, "null start / end arrays (dense: h_start, h_end; implicit: the run and start/end lists)");
+        size_t mc, rc, sc;
+        caps(*d, mc, rc, sc);
+        need += ((size_t)d->n * 2 + mc * 28 + rc * 8 + sc * 12 + 63) / 64 * 64;
+    }
+    HCNV_CUDA(ctx, ctx->buf[H_DOWNLOAD].reserve(need + 256));
+    HCNV_CUDA(ctx, ctx->pin[2].reserve(64 + 32 * (size_t)count));
+    char* b = ctx->buf[H_DOWNLOAD].as<char>();
+    unsigned long long* d_count = (unsigned long long*)b;                  // 4 per chromosome (3 used)
+    unsigned long long* h_count = ctx->pin[2].as<unsigned long long>();
+    HCNV_CUDA(ctx, cudaMemsetAsync(d_count, 0, 32 * (size_t)std::max(count, 1), ctx->stream));
+    std::vector<PackLists> where((size_t)count);
+    size_t at = (64 + 32 * (size_t)count + 63) / 64 * 64;
+    for (int i = 0; i < count; ++i) {
+        hcnv_results_download* d = &ds[i];
+        const long long n = d->n;
+        if (n == 0) continue;
+        size_t mc, rc, sc;
+        caps(*d, mc, rc, sc);
+        PackLists L{};
+        char* p = b + at;
+        L.mse_vals = (float*)p; p += mc * 24;
+        L.mse_rows = (int32_t*)p; p += mc * 4;
+        L.run_rows = (int32_t*)p; p += rc * 4;
+        L.run_bins = (int32_t*)p; p += rc * 4;
+        L.se_rows = (int32_t*)p; p += sc * 4;
+        L.se_vals = (int32_t*)p; p += sc * 8;
+        int8_t* d_state8 = (int8_t*)p; int8_t* d_cn8 = d_state8 + n;
+        L.mse_cap = (long long)mc; L.run_cap = (long long)rc; L.se_cap = (long long)sc; L.count = d_count + 4 * (size_t)i;
+        at += ((size_t)n * 2 + mc * 28 + rc * 8 + sc * 12 + 63) / 64 * 64;
+        where[(size_t)i] = L;
+        k_pack_results<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, d->state, d->cn, d->mse, d->start, d->end, d->bin_width > 0 ? d->bin_width : 0, d_state8, d_cn8, L);
+        HCNV_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_state, d_state8, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (d->h_cn) HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_cn, d_cn8, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    // the lengths of the lists reach the host behind the packing kernels; the dense columns follow while the host reads them
+    { int rc_ = hcnv_get_small(ctx, h_count, d_count, 32 * (size_t)std::max(count, 1)); if (rc_) return rc_; }
+    HCNV_CUDA(ctx, cudaEventRecord(ctx->ev_misc, ctx->stream));
+    for (int i = 0; i < count; ++i) {
+        hcnv_results_download* d = &ds[i];
+        const size_t n = (size_t)d->n;
+        if (n == 0) continue;
+        if (d->bin_width <= 0) {
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_start, d->start, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_end, d->end, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_scaled, d->scaled, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    HCNV_CUDA(ctx, cudaEventSynchronize(ctx->ev_misc));
+    hcnv_flush_gets(ctx);
+    for (int i = 0; i < count; ++i) {
+        hcnv_results_download* d = &ds[i];
+        if (d->n == 0) continue;
+        const PackLists& L = where[(size_t)i];
+        const long long k = (long long)h_count[4 * i], kr = (long long)h_count[4 * i + 1], ks = (long long)h_count[4 * i + 2];
+        if (k > L.mse_cap) return hcnv_fail(ctx, HCNV_E_CAPACITY, "mse_capacity too small for the non-zero MSE rows");
+        if (kr > L.run_cap || ks > L.se_cap) return hcnv_fail(ctx, HCNV_E_CAPACITY, "run_capacity / se_capacity too small");
+        if (k > 0) {
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_mse_rows, L.mse_rows, 4 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_mse_vals, L.mse_vals, 24 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (kr > 0) {
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_run_rows, L.run_rows, 4 * (size_t)kr, cudaMemcpyDeviceToHost, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_run_bins, L.run_bins, 4 * (size_t)kr, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (ks > 0) {
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_se_rows, L.se_rows, 4 * (size_t)ks, cudaMemcpyDeviceToHost, ctx->stream));
+            HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_se_vals, L.se_vals, 8 * (size_t)ks, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        d->n_mse_rows = k; d->n_runs = kr; d->n_se_rows = ks;
+    }
+    { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
+    return HCNV_OK;
+}
+
 int hcnv_download_results_impl(hcnv_ctx* ctx, hcnv_results_download* d)
 {
-    if (!ctx || !d || d->n < 0) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
-    d->n_mse_rows = 0;
-    const long long n = d->n;
-    if (n == 0) return HCNV_OK;
-    if (n >= (1ll << 31)) return hcnv_fail(ctx, HCNV_E_INVALID, "too many rows");
-    if (!d->start || !d->end || !d->scaled || !d->state || !d->cn || !d->mse || !d->h_start || !d->h_end || !d->h_scaled || !d->h_state ||
-        !d->h_cn || !d->h_mse_rows || !d->h_mse_vals) return hcnv_fail(ctx, HCNV_E_INVALID, "null array");
-    const long long cap = std::min<long long>(d->mse_capacity, n);
-    HCNV_CUDA(ctx, ctx->buf[H_DOWNLOAD].reserve((size_t)n * 2 + (size_t)cap * 28 + 256));
-    char* b = ctx->buf[H_DOWNLOAD].as<char>();
-    unsigned long long* d_count = (unsigned long long*)b;
-    float* d_vals = (float*)(b + 64); int32_t* d_rows = (int32_t*)(b + 64 + (size_t)cap * 24);
-    int8_t* d_state8 = (int8_t*)(b + 64 + (size_t)cap * 28); int8_t* d_cn8 = d_state8 + n;
-    HCNV_CUDA(ctx, cudaMemsetAsync(d_count, 0, 8, ctx->stream));
-    k_pack_results<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, d->state, d->cn, d->mse, d_state8, d_cn8, d_rows, d_vals, d_count, cap);
-    HCNV_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
-    HCNV_CUDA(ctx, ctx->pin[2].reserve(64));
-    unsigned long long* h_count = ctx->pin[2].as<unsigned long long>();
-    HCNV_CUDA(ctx, cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_start, d->start, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_end, d->end, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_scaled, d->scaled, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_state, d_state8, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_cn, d_cn8, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    // the row count is on the host after the first of these copies; the listed rows follow in a second, short round
-    HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const long long k = (long long)*h_count;
-    if (k > cap) return hcnv_fail(ctx, HCNV_E_CAPACITY, "mse_capacity too small for the non-zero MSE rows");
-    if (k > 0) {
-        HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_mse_rows, d_rows, 4 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaMemcpyAsync(d->h_mse_vals, d_vals, 24 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    d->n_mse_rows = k;
-    return HCNV_OK;
+    if (!ctx || !d) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    return hcnv_download_results_many_impl(ctx, 1, d);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -841,12 +924,11 @@ struct hcnv_seg_plan {
 namespace {
 // the fields of SegDev the host sets between phases (boundary vectors, final state) go up one problem at a time
 int push_prob(hcnv_seg_plan* pl, int i) {
-    HCNV_CUDA(pl->ctx, cudaMemcpyAsync(pl->dprobs + i, &pl->h[i], sizeof(SegDev), cudaMemcpyHostToDevice, pl->ctx->stream));
-    return HCNV_OK;
+    return hcnv_put_small(pl->ctx, pl->dprobs + i, &pl->h[i], sizeof(SegDev));
 }
 int pull_probs(hcnv_seg_plan* pl) {
-    HCNV_CUDA(pl->ctx, cudaMemcpyAsync(pl->h.data(), pl->dprobs, sizeof(SegDev) * (size_t)pl->n, cudaMemcpyDeviceToHost, pl->ctx->stream));
-    HCNV_CUDA(pl->ctx, cudaStreamSynchronize(pl->ctx->stream));
+    { int rc_ = hcnv_get_small(pl->ctx, pl->h.data(), pl->dprobs, sizeof(SegDev) * (size_t)pl->n); if (rc_) return rc_; }
+    { int rc_ = hcnv_sync(pl->ctx); if (rc_) return rc_; }
     return HCNV_OK;
 }
 }  // namespace
@@ -1039,9 +1121,9 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
     pl->dprobs = ctx->buf[H_PROBS].as<SegDev>();
     pl->d_blkbase = ctx->buf[H_BLKMAP].as<int>();
     pl->d_fblkbase = pl->d_blkbase + (n_problems + 1);
-    if ((rc = CU(cudaMemcpyAsync(pl->dprobs, h.data(), sizeof(SegDev) * (size_t)n_problems, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
-    if ((rc = CU(cudaMemcpyAsync(pl->d_blkbase, pl->blk_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
-    if ((rc = CU(cudaMemcpyAsync(pl->d_fblkbase, pl->fblk_base.data(), 4 * (size_t)(n_problems + 1), cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+    if ((rc = hcnv_put_small(ctx, pl->dprobs, h.data(), sizeof(SegDev) * (size_t)n_problems))) return fail(rc);
+    if ((rc = hcnv_put_small(ctx, pl->d_blkbase, pl->blk_base.data(), 4 * (size_t)(n_problems + 1)))) return fail(rc);
+    if ((rc = hcnv_put_small(ctx, pl->d_fblkbase, pl->fblk_base.data(), 4 * (size_t)(n_problems + 1)))) return fail(rc);
     if (pl->total_segs > 0) {
         const size_t S = (size_t)pl->total_segs, np1 = (size_t)(n_problems + 1);
         pl->chunk_base.assign(n_problems + 1, 0);
@@ -1060,11 +1142,11 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
         pl->d_tf = (float*)(vb + o_tf); pl->d_ti = (int*)(vb + o_ti); pl->d_ls = (float*)(vb + o_ls);
         pl->d_tiecnt = (int*)(vb + o_tie); pl->d_tielist = pl->d_tiecnt + 4;      // segments that met a rounding tie (P1's second pass)
         pl->d_scan = (float*)(vb + o_scan);
-        if ((rc = CU(cudaMemcpyAsync(pl->d_cbase, pl->chunk_base.data(), 4 * np1, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
-        if ((rc = CU(cudaMemcpyAsync(pl->d_segbase, pl->seg_base.data(), 4 * np1, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc);
+        if ((rc = hcnv_put_small(ctx, pl->d_cbase, pl->chunk_base.data(), 4 * np1))) return fail(rc);
+        if ((rc = hcnv_put_small(ctx, pl->d_segbase, pl->seg_base.data(), 4 * np1))) return fail(rc);
         if ((rc = CU(cudaMemsetAsync(pl->d_tiecnt, 0, 16, ctx->stream), "memset"))) return fail(rc);
         if ((rc = CU(cudaMemsetAsync(pl->d_force, 0, 4 * S, ctx->stream), "memset"))) return fail(rc);
-        { int z[16] = {0}; if ((rc = CU(cudaMemcpyToSymbolAsync(g_vdbg, z, sizeof z, 0, cudaMemcpyHostToDevice, ctx->stream), "H2D"))) return fail(rc); }
+        { void* dbg = nullptr; if ((rc = CU(cudaGetSymbolAddress(&dbg, g_vdbg), "symbol")) || (rc = CU(cudaMemsetAsync(dbg, 0, 64, ctx->stream), "memset"))) return fail(rc); }
     }
     pl->repl.assign(n_problems, 0);
     *out = pl;
@@ -1129,7 +1211,7 @@ int hcnv_seg_plan_p0_impl(hcnv_seg_plan* pl)
             if (pl->h[i].par && pl->h[i].n_seg > 0 && !pl->h[i].skip)
                 for (int q = 0; q < P0C_K; ++q)
                     HCNV_CUDA(ctx, cudaMemcpyAsync(&sub[((size_t)i * P0C_K + q) * 36], pl->d_scan + (((size_t)i * P0C_K + q) * P0C_T + (P0C_T - 1)) * 36, 144, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
         for (int i = 0; i < pl->n; ++i) {
             if (!(pl->h[i].par && pl->h[i].n_seg > 0 && !pl->h[i].skip)) continue;
             float* R = pl->parts[i].product_approx;           // R = R (x) sub-block q, in order
@@ -1184,7 +1266,7 @@ int hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round)
             int* d_queue = ctx->buf[H_ORDER].as<int>();
             int* d_order = d_queue + 16;
             HCNV_CUDA(ctx, cudaMemsetAsync(d_queue, 0, 64, ctx->stream));
-            HCNV_CUDA(ctx, cudaMemcpyAsync(d_order, pl->order.data(), 4 * pl->order.size(), cudaMemcpyHostToDevice, ctx->stream));
+            { int rc_ = hcnv_put_small(ctx, d_order, pl->order.data(), 4 * pl->order.size()); if (rc_) return rc_; }
             const long long n_groups = ((long long)pl->order.size() + VM_CH - 1) / VM_CH;
             int wps = VM_WARPS_PER_SM;
             if (const char* e = getenv("HCNV_VM_WARPS_PER_SM")) wps = std::max(1, std::min(32, atoi(e)));
@@ -1218,8 +1300,8 @@ int hcnv_seg_plan_chain_impl(hcnv_seg_plan* pl, int32_t round)
     if (pl->split) {
         // boundary vectors of this round's parts go back to the host (the caller hands them to the next rank)
         std::vector<SegDev> tmp(n);
-        HCNV_CUDA(ctx, cudaMemcpyAsync(tmp.data(), pl->dprobs, sizeof(SegDev) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        { int rc_ = hcnv_get_small(ctx, tmp.data(), pl->dprobs, sizeof(SegDev) * (size_t)n); if (rc_) return rc_; }
+        { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
         for (int i = 0; i < n; ++i) {
             if (pl->h[i].chain_round != round) continue;
             hcnv_segment_part& pt = pl->parts[i];
@@ -1254,10 +1336,10 @@ int hcnv_seg_plan_finish_impl(hcnv_seg_plan* pl)
         ctx->launches += 2;
         HCNV_CUDA(ctx, cudaGetLastError());
         // one host round trip per pass: the verification verdicts, the replay counters and the diagnostics together
-        HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), pl->dprobs, sizeof(SegDev) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaMemcpyAsync(pl->repl.data(), pl->d_repl, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaMemcpyFromSymbolAsync(ctx->vdbg, g_vdbg, sizeof ctx->vdbg, 0, cudaMemcpyDeviceToHost, ctx->stream));
-        HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        { int rc_ = hcnv_get_small(ctx, h.data(), pl->dprobs, sizeof(SegDev) * (size_t)n); if (rc_) return rc_; }
+        { int rc_ = hcnv_get_small(ctx, pl->repl.data(), pl->d_repl, 4 * (size_t)n); if (rc_) return rc_; }
+        { void* dbg = nullptr; HCNV_CUDA(ctx, cudaGetSymbolAddress(&dbg, g_vdbg)); int rc_ = hcnv_get_small(ctx, ctx->vdbg, dbg, sizeof ctx->vdbg); if (rc_) return rc_; }
+        { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
         bool again = false;
         for (int i = 0; i < n; ++i)
             if (h[i].par && !h[i].irregular && !h[i].skip && h[i].first_bad != 0x7fffffff) again = true;
@@ -1278,7 +1360,7 @@ int hcnv_seg_plan_finish_impl(hcnv_seg_plan* pl)
     KT_END(ctx, HCNV_K_TRACEBACK);
     ctx->launches += 2;
     HCNV_CUDA(ctx, cudaGetLastError());
-    HCNV_CUDA(ctx, cudaMemcpyAsync(h.data(), pl->dprobs, sizeof(SegDev) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    { int rc_ = hcnv_get_small(ctx, h.data(), pl->dprobs, sizeof(SegDev) * (size_t)n); if (rc_) return rc_; }
     for (int i = 0; i < n; ++i) {
         hcnv_segment_problem& q = parts[i].prob;
         const size_t M = (size_t)q.n_markers;
@@ -1289,7 +1371,7 @@ int hcnv_seg_plan_finish_impl(hcnv_seg_plan* pl)
         } else if (q.scaled && parts[i].n_parts > 1)
             HCNV_CUDA(ctx, cudaMemcpyAsync(q.scaled, h[i].scaled, 4 * M, cudaMemcpyDeviceToDevice, ctx->stream));     // the part's rows of the whole chromosome's scaled depth
     }
-    HCNV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
     int worst = HCNV_OK;
     for (int i = 0; i < n; ++i) {
         hcnv_segment_problem& q = parts[i].prob;

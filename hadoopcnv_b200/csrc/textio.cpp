@@ -269,7 +269,8 @@ int hcnv_write_results_text(const char* path, int append, const char* chr, int64
     char b[64];
     for (int64_t i = 0; i < n; ++i) {
         java_to_string<float>(scaled[i], b);
-        fprintf(f, "%s\t%d\t%d\t%s\t%d\t%d", chr, start[i], end[i], b, state[i], cn[i]);
+        static const int cn_of[6] = {0, 1, 2, 2, 3, 4};                      // Hmm.java:35; cn == NULL: the copy number is this look-up of the state
+        fprintf(f, "%s\t%d\t%d\t%s\t%d\t%d", chr, start[i], end[i], b, state[i], cn ? cn[i] : cn_of[state[i] >= 0 && state[i] < 6 ? state[i] : 0]);
         for (int s = 0; s < 6; ++s) { java_to_string<float>(mse[i * 6 + s], b); fputc('\t', f); fputs(b, f); }
         fputc('\n', f);
     }
@@ -369,3 +370,28 @@ int hcnv_bins_text_get(const hcnv_bins_text* t, int32_t i, const char** chrom, i
 void hcnv_bins_text_free(hcnv_bins_text* t) { delete t; }
 
 }  // extern "C"
+
+// the start / end columns from their implicit form (hcnv_results_download): runs of consecutive full bins + the rows that are not full
+extern "C" int hcnv_expand_start_end(int64_t n, int32_t W, int64_t n_runs, const int32_t* run_rows, const int32_t* run_bins,
+                                     int64_t n_se, const int32_t* se_rows, const int32_t* se_vals, int32_t* start, int32_t* end) {
+    if (n < 0 || W < 1 || n_runs < 0 || n_se < 0 || (n > 0 && (!start || !end)) || (n_runs > 0 && (!run_rows || !run_bins)) || (n_se > 0 && (!se_rows || !se_vals)))
+        return HCNV_E_INVALID;
+    if (n == 0) return HCNV_OK;
+    std::vector<std::pair<int32_t, int32_t>> runs((size_t)n_runs);
+    for (int64_t k = 0; k < n_runs; ++k) {
+        if (run_rows[k] < 0 || run_rows[k] >= n) return HCNV_E_RANGE;
+        runs[(size_t)k] = { run_rows[k], run_bins[k] };
+    }
+    std::sort(runs.begin(), runs.end());
+    if (runs.empty() || runs[0].first != 0) return HCNV_E_RANGE;
+    for (size_t k = 0; k < runs.size(); ++k) {
+        const int64_t r0 = runs[k].first, r1 = k + 1 < runs.size() ? runs[k + 1].first : n;
+        int64_t id = runs[k].second;
+        for (int64_t r = r0; r < r1; ++r, id += W) { start[r] = (int32_t)(id > 1 ? id : 1); end[r] = (int32_t)(id + W - 1); }
+    }
+    for (int64_t k = 0; k < n_se; ++k) {
+        if (se_rows[k] < 0 || se_rows[k] >= n) return HCNV_E_RANGE;
+        start[se_rows[k]] = se_vals[2 * k]; end[se_rows[k]] = se_vals[2 * k + 1];
+    }
+    return HCNV_OK;
+}

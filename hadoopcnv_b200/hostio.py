@@ -53,11 +53,13 @@ class SnpTable:
         return ["%s\t%d\t%d\t0" % (c, int(p), int(z)) for c, (ps, zs) in self.contigs().items() for p, z in zip(ps, zs)]
 
 
-def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = False, threads: int = 0, stats: Optional[dict] = None):
+def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = False, threads: int = 0, stats: Optional[dict] = None, wire: bool = False):
     """hcnv_bam_pack -> (names, [Contig with numpy arrays], [max_block_len], n_records).  Arrays are copies.
     compact=True: the block stream comes in the 2-byte delta-coded form (Contig.cblocks / anchors) and the observations in
-    their 2-byte form (Contig.cobs / cobs_anchors)."""
+    their 2-byte form (Contig.cobs / cobs_anchors).  wire=True: the block stream in its ~1.1-byte wire form instead
+    (Contig.wblocks / wlens / wlen_offsets / anchors, hcnv_pack_contig_wire)."""
     lib = L.lib()
+    compact = compact or wire
     h = C.c_void_p()
     st = lib.hcnv_bam_pack_mt(bam_path.encode(), snps._h if snps is not None else None, int(threads), C.byref(h))
     if st != 0:
@@ -70,7 +72,7 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
         names, contigs, maxlens = [], [], []
         for i in range(lib.hcnv_pack_n_contigs(h)):
             name, ci, ml = C.c_char_p(), L.ContigInput(), C.c_int32()
-            rc = (lib.hcnv_pack_contig_compact if compact else lib.hcnv_pack_contig)(h, i, C.byref(name), C.byref(ci), C.byref(ml))
+            rc = (lib.hcnv_pack_contig_wire if wire else lib.hcnv_pack_contig_compact if compact else lib.hcnv_pack_contig)(h, i, C.byref(name), C.byref(ci), C.byref(ml))
             if rc != 0:
                 raise L.HcnvError(rc, "hcnv_pack_contig%s(%s, contig %d): %s" % ("_compact" if compact else "", bam_path, i, lib.hcnv_strerror(rc).decode()))
 
@@ -90,9 +92,16 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
                 return raw[sh:sh + n]
             contigs.append(Contig(ci.length, arr(ci.blocks, ci.n_blocks, BLOCK_DTYPE), arr(ci.long_blocks, ci.n_long, LONG_BLOCK_DTYPE),
                                   arr(ci.snp_pos1, ci.n_snp, np.int32), arr(ci.snp_zyg, ci.n_snp, np.int8),
-                                  arr(ci.obs, ci.n_obs, np.uint32), arr16(ci.cblocks, ci.n_cblocks),
+                                  arr(ci.obs, ci.n_obs, np.uint32), arr16(ci.cblocks, ci.n_cblocks if ci.cblocks else 0),
                                   arr(ci.anchors, ci.n_cblocks // L.HCNV_CGROUP, np.int32),
                                   arr(ci.cobs, ci.n_cobs, np.uint16), arr(ci.cobs_anchors, ci.n_cobs // L.HCNV_OGROUP, np.int32)))
+            if wire and ci.n_cblocks:
+                raw = np.empty(ci.n_cblocks + 16, np.uint8)
+                sh = (-raw.ctypes.data) % 16
+                raw[sh:sh + ci.n_cblocks] = np.frombuffer((C.c_char * ci.n_cblocks).from_address(ci.wblocks), dtype=np.uint8)
+                k = contigs[-1]
+                k.wblocks, k.wlens = raw[sh:sh + ci.n_cblocks], (arr(ci.wlens, ci.n_wlens, np.uint8) if ci.n_wlens else np.zeros(0, np.uint8))
+                k.wlen_offsets, k.wire_default_len = arr(ci.wlen_offsets, ci.n_cblocks // L.HCNV_CGROUP + 1, np.int32), int(ci.wire_default_len)
         return names, contigs, maxlens, int(lib.hcnv_pack_n_records(h))
     finally:
         lib.hcnv_pack_free(h)

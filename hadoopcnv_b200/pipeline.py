@@ -34,15 +34,26 @@ class GenomeOutput:
 
     The download shares the PCIe budget with the upload, so the columns travel in their narrowest lossless form: state and
     copy number as int8, and the MSE columns -- all six are 0.0 for every bin without a SNP site, about 92 % of them -- as
-    (row, six floats) pairs for the rows that hold a non-zero value; `dense_mse` rebuilds the (n_bins, 6) block."""
+    (row, six floats) pairs for the rows that hold a non-zero value; `dense_mse` rebuilds the (n_bins, 6) block.
+    implicit_bins=True: start / end travel in their implicit form as well (hcnv_results_download: the rows that begin a run of
+    consecutive bins and the rows that are not full bins; `start_end(i)` rebuilds the two columns) -- 6 bytes per row instead of 14."""
 
-    def __init__(self, lengths: Sequence[int], bin_width: int, want_cn: bool = True):
+    def __init__(self, lengths: Sequence[int], bin_width: int, want_cn: bool = True, implicit_bins: bool = False):
         import torch
         cap = [int(l) // bin_width + 1 for l in lengths]
         self.offset = np.concatenate([[0], np.cumsum(cap)]).astype(np.int64)
         n, k = int(self.offset[-1]), len(cap)
-        self.start = torch.empty(n, dtype=torch.int32, pin_memory=True)
-        self.end = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        self.bin_width, self.implicit_bins = int(bin_width), bool(implicit_bins)
+        if implicit_bins:
+            self.start = self.end = None
+            self.run_rows = torch.empty(n, dtype=torch.int32, pin_memory=True)
+            self.run_bins = torch.empty(n, dtype=torch.int32, pin_memory=True)
+            self.se_rows = torch.empty(n, dtype=torch.int32, pin_memory=True)
+            self.se_vals = torch.empty((n, 2), dtype=torch.int32, pin_memory=True)
+            self.run_count, self.se_count = np.zeros(k, np.int64), np.zeros(k, np.int64)
+        else:
+            self.start = torch.empty(n, dtype=torch.int32, pin_memory=True)
+            self.end = torch.empty(n, dtype=torch.int32, pin_memory=True)
         self.state = torch.empty(n, dtype=torch.int8, pin_memory=True)
         self.cn = torch.empty(n, dtype=torch.int8, pin_memory=True) if want_cn else None
         self.scaled = torch.empty(n, dtype=torch.float32, pin_memory=True)
@@ -53,11 +64,17 @@ class GenomeOutput:
         self.n_bins = np.zeros(k, np.int64)
         self.mean_coverage, self.final_loss = np.zeros(k, np.float32), np.zeros(k, np.float32)
         self.lambda1, self.lambda2, self.status = np.zeros(k, np.float32), np.zeros(k, np.float32), np.zeros(k, np.int32)
-        self.bytes_per_bin = 4 + 4 + 1 + (1 if want_cn else 0) + 4
+        self.bytes_per_bin = (0 if implicit_bins else 8) + 1 + (1 if want_cn else 0) + 4
         self.bytes_per_mse_row = 4 + 24
         s = self.struct = L.GenomeOutput()
         s.capacity = n
-        s.start, s.end, s.scaled, s.state = self.start.data_ptr(), self.end.data_ptr(), self.scaled.data_ptr(), self.state.data_ptr()
+        s.scaled, s.state = self.scaled.data_ptr(), self.state.data_ptr()
+        if implicit_bins:
+            s.start = s.end = None
+            s.run_rows, s.run_bins, s.se_rows, s.se_vals = self.run_rows.data_ptr(), self.run_bins.data_ptr(), self.se_rows.data_ptr(), self.se_vals.data_ptr()
+            s.n_runs, s.n_se_rows = self.run_count.ctypes.data, self.se_count.ctypes.data
+        else:
+            s.start, s.end = self.start.data_ptr(), self.end.data_ptr()
         s.cn = self.cn.data_ptr() if want_cn else None
         s.mse_rows, s.mse_vals = self.mse_rows.data_ptr(), self.mse_vals.data_ptr()
         s.row_offset, s.n_bins, s.n_mse_rows = self.row_offset.ctypes.data, self.n_bins.ctypes.data, self.mse_count.ctypes.data
@@ -71,8 +88,22 @@ class GenomeOutput:
         m[self.mse_rows[o:o + k].numpy()] = self.mse_vals[o:o + k].numpy()
         return m
 
+    def start_end(self, i: int):
+        """The start / end columns (int32) of chromosome i, whichever form they were downloaded in."""
+        o, nb = int(self.offset[i]), int(self.n_bins[i])
+        if not self.implicit_bins:
+            return self.start[o:o + nb].numpy(), self.end[o:o + nb].numpy()
+        st, en = np.empty(nb, np.int32), np.empty(nb, np.int32)
+        kr, ks = int(self.run_count[i]), int(self.se_count[i])
+        rr, rb, sr, sv = self.run_rows[o:o + kr].numpy(), self.run_bins[o:o + kr].numpy(), self.se_rows[o:o + ks].numpy(), self.se_vals[o:o + ks].numpy()
+        rc = L.lib().hcnv_expand_start_end(nb, self.bin_width, kr, rr.ctypes.data, rb.ctypes.data, ks, sr.ctypes.data, sv.ctypes.data, st.ctypes.data, en.ctypes.data)
+        if rc != 0:
+            raise L.HcnvError(rc, "hcnv_expand_start_end: %s" % L.lib().hcnv_strerror(rc).decode())
+        return st, en
+
     def d2h_bytes(self) -> int:
-        return int(self.n_bins.sum()) * self.bytes_per_bin + int(self.mse_count.sum()) * self.bytes_per_mse_row
+        lists = (int(self.run_count.sum()) * 8 + int(self.se_count.sum()) * 12) if self.implicit_bins else 0
+        return int(self.n_bins.sum()) * self.bytes_per_bin + int(self.mse_count.sum()) * self.bytes_per_mse_row + lists
 
 
 class GenomePipeline:
@@ -112,6 +143,7 @@ class GenomePipeline:
         """Start a sample whose chromosomes will be pushed as the packer finishes them; `lengths` fixes the output layout."""
         if out is None:
             out = GenomeOutput(lengths, bin_width)
+        assert out.bin_width == bin_width
         self.last_output = out
         p = L.BinParams()
         self._lib.hcnv_bin_params_default(C.byref(p))

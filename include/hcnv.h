@@ -110,6 +110,18 @@ typedef struct { int32_t start0; uint32_t len_mapq; } hcnv_block;
 typedef uint16_t hcnv_cblock;
 #define HCNV_CGROUP 128
 
+/* The same records at about 1.1 bytes each -- the WIRE form, for a host whose upload bounds the path (one 30X genome: 0.7 GB
+ * instead of 1.2 GB; the library expands it to hcnv_cblock records on the device, 0.3 ms per genome, before binning):
+ *   wblocks[i]   bits 0-6  start0 - start0 of the previous record (0..127)
+ *                bit 7     1: the block has the contig's default length (wire_default_len, 1..255 -- the read length, nine
+ *                          records in ten); 0: its length (0..255, 0 = filler) is the next byte of the side stream wlens
+ *   anchors[g]   as above: start0 of record HCNV_CGROUP * g (that record's delta field is ignored)
+ *   wlen_offsets[g] = index in wlens of the first length byte of group g; n_cblocks / HCNV_CGROUP + 1 entries, the last = n_wlens
+ * Record i of the wire form IS record i of the hcnv_cblock stream it expands to (same count n_cblocks, same anchors); a gap
+ * above 127 is bridged by fillers or, where that is shorter, by closing the group with fillers so that the next anchor makes
+ * the jump.  wblocks must be 16-byte aligned.  hcnv_wire_from_cblocks builds it. */
+typedef uint8_t hcnv_wblock;
+
 /* The observations at SNP sites at 2 bytes each (at 4 bytes they are a fifth of what a 30X genome uploads):
  *   bits 0-3  BAM 4-bit base code      bits 4-15  snp index - cobs_anchors[k / HCNV_OGROUP]   (0..4094; 4095 = filler, no observation)
  * Observations arrive in block order, so the indices of HCNV_OGROUP consecutive ones lie close together; where they do not
@@ -157,6 +169,9 @@ typedef struct {
      * sites are ignored. */
     int32_t                region_first_bin, region_n_bins;
     int64_t                snp_index_base;
+    /* alternative to `cblocks` (cblocks null, n_cblocks and anchors as for cblocks): the wire form, see hcnv_wblock */
+    const hcnv_wblock*     wblocks;     const uint8_t* wlens; const int32_t* wlen_offsets; int64_t n_wlens;
+    int32_t                wire_default_len; int32_t reserved;
 } hcnv_contig_input;
 
 /* Host helper (no GPU): sorted hcnv_block records -> compact stream; blocks whose MAPQ fails mapping_quality_threshold
@@ -166,6 +181,15 @@ typedef struct {
  * start0 or len > HCNV_SHORT_MAX, HCNV_E_CAPACITY if `capacity` (in records) is too small. */
 int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, double mapping_quality_threshold,
                             hcnv_cblock* out, int32_t* anchors, int64_t capacity);
+
+/* Host helper (no GPU): a compact stream -> its wire form (hcnv_wblock).  default_len 0 picks the most frequent length.
+ * Returns the number of wire records (a multiple of HCNV_CGROUP; it differs from n_cblocks where gaps of 128 - 255 bases
+ * needed a filler) or a negative status; *n_wlens = bytes of the side stream.  With out == NULL only counts.  anchors
+ * needs result / HCNV_CGROUP entries, wlen_offsets one more.  HCNV_E_CAPACITY if `capacity` (records) or `wlens_capacity`
+ * (bytes) is too small. */
+int64_t hcnv_wire_from_cblocks(const hcnv_cblock* cblocks, const int32_t* cblock_anchors, int64_t n_cblocks, int32_t default_len,
+                               hcnv_wblock* out, uint8_t* wlens, int32_t* anchors, int32_t* wlen_offsets,
+                               int64_t capacity, int64_t wlens_capacity, int32_t* default_len_used, int64_t* n_wlens);
 
 /* Host helper (no GPU): obs (snp index << 4 | base4, any order) -> the 2-byte stream.  Returns the number of entries
  * (fillers and padding included, a multiple of HCNV_OGROUP) or a negative status; with out == NULL only counts.  anchors
@@ -224,6 +248,8 @@ int     hcnv_pack_contig(const hcnv_pack* p, int32_t i, const char** name, hcnv_
 /* the same with both streams in their 2-byte forms (built on the first request): in->cblocks / anchors / n_cblocks and
  * in->cobs / cobs_anchors / n_cobs; in->blocks and in->obs are null */
 int     hcnv_pack_contig_compact(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
+/* the same with the block stream in its wire form (in->wblocks / wlens / wlen_offsets / anchors; in->cblocks null) */
+int     hcnv_pack_contig_wire(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
 void    hcnv_pack_free(hcnv_pack* p);
 
 /* ---- between B1 and B2: what Hmm.init's text parsing does to a bins record ---------------------- */
@@ -322,8 +348,21 @@ typedef struct {
     int32_t* h_start; int32_t* h_end; float* h_scaled; int8_t* h_state; int8_t* h_cn;                        /* host, n */
     int32_t* h_mse_rows; float* h_mse_vals; int64_t mse_capacity;                                            /* host */
     int64_t n_mse_rows;                                                                                      /* out */
+    /* start / end in their IMPLICIT form, instead of h_start / h_end (which are then NULL; bin_width > 0 selects it).  In a
+     * covered genome almost every bin is full -- it starts at its first position (its id, or 1 for bin 0) and ends at its last
+     * (id + bin_width - 1) -- and follows the bin before it, so 8 of the 14 bytes per row say nothing.  Listed instead, in no
+     * particular order: the rows whose bin id is not the previous row's + bin_width (row 0 always), h_run_rows[k] with the id
+     * h_run_bins[k]; and the rows that are not full, h_se_rows[k] with h_se_vals[2k] = start, [2k + 1] = end.  Capacities in
+     * rows (n always suffices); hcnv_expand_start_end rebuilds the columns on the host. */
+    int32_t  bin_width; int32_t reserved;
+    int32_t* h_run_rows; int32_t* h_run_bins; int64_t run_capacity; int64_t n_runs;                          /* host; out */
+    int32_t* h_se_rows;  int32_t* h_se_vals;  int64_t se_capacity;  int64_t n_se_rows;                       /* host; out */
 } hcnv_results_download;
 int hcnv_download_results(hcnv_ctx* ctx, hcnv_results_download* d);
+/* Host helper (no GPU): the start / end columns of n rows from their implicit form (see hcnv_results_download).
+ * HCNV_E_RANGE for a listed row outside [0, n) or when row 0 is not listed among the runs (n > 0). */
+int hcnv_expand_start_end(int64_t n, int32_t bin_width, int64_t n_runs, const int32_t* run_rows, const int32_t* run_bins,
+                          int64_t n_se_rows, const int32_t* se_rows, const int32_t* se_vals, int32_t* start, int32_t* end);
 
 /* ---- one sample end to end ---------------------------------------------------------------------------------------- */
 /* What PennCnvSeq.run's jobs do for one BAM's packed records (PennCnvSeq.java:285-350: depth caller -> binner -> one
@@ -335,7 +374,10 @@ int hcnv_download_results(hcnv_ctx* ctx, hcnv_results_download* d);
  * Output rows of contig c start at row_offset[c] = sum over the contigs before it of (length / bin_width + 1); n_bins[c] of them
  * are written.  state / cn are int8; the six MSE columns are listed only for the rows that hold a non-zero value (all six are
  * 0.0 for every bin without a SNP site): mse_rows[row_offset[c] + k] = row inside the contig, mse_vals[6 * (row_offset[c] + k) ..]
- * = its six values, k < n_mse_rows[c].  cn and the per-contig scalar arrays may be NULL. */
+ * = its six values, k < n_mse_rows[c].  cn and the per-contig scalar arrays may be NULL.
+ * start == NULL selects the implicit form of start / end (see hcnv_results_download; it halves the download): run_rows / run_bins /
+ * se_rows (capacity entries each) and se_vals (2 * capacity) are laid out like mse_rows -- contig c's lists begin at row_offset[c],
+ * n_runs[c] and n_se_rows[c] entries long, rows counted inside the contig. */
 typedef struct hcnv_genome hcnv_genome;
 typedef struct {
     int64_t  capacity;                                   /* rows of the arrays below: >= sum of (length / bin_width + 1) */
@@ -343,6 +385,8 @@ typedef struct {
     int32_t* mse_rows; float* mse_vals;                  /* capacity and 6 * capacity entries */
     int64_t* row_offset; int64_t* n_bins; int64_t* n_mse_rows;                       /* n_contigs entries each (out) */
     float* mean_coverage; float* final_loss; float* lambda1_used; float* lambda2_used; int32_t* status;   /* n_contigs entries each (out) */
+    int32_t* run_rows; int32_t* run_bins; int32_t* se_rows; int32_t* se_vals;        /* implicit start / end (used when start == NULL) */
+    int64_t* n_runs; int64_t* n_se_rows;                                             /* n_contigs entries each (out) */
 } hcnv_genome_output;
 int         hcnv_genome_create(int device, int32_t workers /* 0: 4 */, hcnv_genome** out);
 int         hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
@@ -394,7 +438,8 @@ int     hcnv_bins_text_get(const hcnv_bins_text* t, int32_t i, const char** chro
                            const int32_t** start, const int32_t** end, const float** median, const float** mse,
                            const float** total, const int32_t** cnt);
 void    hcnv_bins_text_free(hcnv_bins_text* t);
-/* results.txt lines "chr\tstart\tend\tscaled\tstate\tcn\tmse0..5" (Hmm.java:479-490, Reducers.java:238-241) */
+/* results.txt lines "chr\tstart\tend\tscaled\tstate\tcn\tmse0..5" (Hmm.java:479-490, Reducers.java:238-241); cn == NULL: the copy
+ * number is looked up from the state (Hmm.java:35), which is all the device does to produce it */
 int hcnv_write_results_text(const char* path, int append, const char* chr, int64_t n,
                             const int32_t* start, const int32_t* end, const float* scaled,
                             const int32_t* state, const int32_t* cn, const float* mse);

@@ -453,6 +453,41 @@ def test_end_to_end_bins_to_calls(ctx):
         assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
 
 
+@pytest.mark.parametrize("W,cov", [(100, 30), (50, 100), (1000, 30)])
+def test_binning_wire_stream_matches_compact_stream(ctx, W, cov):
+    """The block stream in its ~1.1-byte wire form (hcnv_wblock), expanded on the device, gives the bins of the 2-byte stream it
+    was made from and of the oracle -- from host and from device buffers; a damaged side stream is refused."""
+    import dataclasses
+    g = synth.make_genome(coverage=cov, scale=0.0015, device="cpu", contigs=["chr10", "chr11", "chr21", "chrY"], seed=99 + W)
+    base = synth.to_api_contigs(g, host=True, compact=True, compact_observations=True)
+    wire = [H.wire_contig(c) for c in base]
+    assert all(c.cblocks is None and c.wblocks is not None and c.wire_default_len == synth.READ_LEN for c in wire)
+    sent = sum(c.wblocks.nbytes + c.wlens.nbytes + c.wlen_offsets.nbytes for c in wire)
+    assert sent < 0.62 * sum(np.asarray(c.cblocks).nbytes for c in base)                 # ~1.15 bytes per record instead of 2
+    want = ctx.bin_contigs(base, bin_width=W, max_block_len=synth.READ_LEN)
+    import torch
+    def dev(c):
+        t = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x).view(np.int8 if x.dtype.itemsize == 1 else np.int16 if x.dtype.itemsize == 2 else np.int32)).cuda()
+        return dataclasses.replace(c, long_blocks=t(c.long_blocks), snp_pos1=t(c.snp_pos1), snp_zyg=t(c.snp_zyg), cobs=t(c.cobs), cobs_anchors=t(c.cobs_anchors),
+                                   anchors=t(c.anchors), wblocks=t(c.wblocks), wlens=t(c.wlens), wlen_offsets=t(c.wlen_offsets))
+    for host in (True, False):
+        res = ctx.bin_contigs(wire if host else [dev(c) for c in wire], bin_width=W, max_block_len=synth.READ_LEN)
+        for i, c in enumerate(g):
+            r = res.contig(i)
+            got = r if host else H.BinsResult(*[x.cpu().numpy() for x in (r.bin, r.start, r.end, r.median, r.mse, r.total, r.n)], r.contig_offset)
+            w_ = want.contig(i)
+            assert_bins_equal(got, {k: np.asarray(getattr(w_, k)) for k in ("bin", "start", "end", "n", "median", "total", "mse")})
+            assert_bins_equal(got, oracle_bins(c, W))
+    bad = dataclasses.replace(wire[0], wlen_offsets=wire[0].wlen_offsets.copy())
+    bad.wlen_offsets[3] += 1
+    with pytest.raises(H.HcnvError) as ei:
+        ctx.bin_contigs([bad], bin_width=W, max_block_len=synth.READ_LEN)
+    assert ei.value.status == L.HCNV_E_RANGE
+    with pytest.raises(H.HcnvError) as ei:
+        ctx.bin_contigs([dataclasses.replace(wire[0], wire_default_len=0)], bin_width=W)
+    assert ei.value.status == L.HCNV_E_INVALID
+
+
 def test_genome_pipeline_equals_the_single_call_path(ctx):
     """GenomePipeline (one chromosome = one end-to-end task on a worker context, compact stream from pinned-like host
     buffers) returns the same results.txt columns as binning all contigs in one call and segmenting them as a batch."""
@@ -496,6 +531,23 @@ def test_genome_pipeline_equals_the_single_call_path(ctx):
                 np.testing.assert_array_equal(o2.scaled[sl].numpy().view(np.uint32), calls[i]["scaled"].view(np.uint32))
                 np.testing.assert_array_equal(o2.dense_mse(i).view(np.uint32), m32[a:b].view(np.uint32))
                 assert np.float32(o2.final_loss[i]).view(np.uint32) == np.float32(calls[i]["final_loss"]).view(np.uint32)
+        # ... and with the block stream in its wire form and start / end in their implicit form, without the cn column
+        # (what bench.py's end-to-end leg uploads and downloads)
+        from hadoopcnv_b200.pipeline import GenomeOutput
+        o3 = GenomeOutput([c.length for c in g], 100, want_cn=False, implicit_bins=True)
+        rs = pipe.run([H.wire_contig(c) for c in hc], [c.name for c in g], o3, max_block_len=150)
+        assert o3.d2h_bytes() < 0.55 * out.d2h_bytes()
+        for i, r in enumerate(rs):
+            a, b = int(res.contig_offset[i]), int(res.contig_offset[i + 1])
+            sl = slice(r.offset, r.offset + r.n_bins)
+            assert r.n_bins == b - a
+            st_, en_ = o3.start_end(i)
+            np.testing.assert_array_equal(st_, res.start[a:b])
+            np.testing.assert_array_equal(en_, res.end[a:b])
+            assert int(o3.run_count[i]) >= 1 and int(o3.se_count[i]) < 0.2 * r.n_bins
+            np.testing.assert_array_equal(o3.state[sl].numpy(), calls[i]["state"])
+            np.testing.assert_array_equal(o3.scaled[sl].numpy().view(np.uint32), calls[i]["scaled"].view(np.uint32))
+            np.testing.assert_array_equal(o3.dense_mse(i).view(np.uint32), m32[a:b].view(np.uint32))
         with pytest.raises(H.HcnvError):
             pipe.push([0], hc[:1])                                       # no sample in flight
     finally:
