@@ -389,8 +389,8 @@ def run_b200(args):
         from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
         whole_i = [i for i, r in enumerate(regions) if r.n_parts == 1]
         part_i = [i for i, r in enumerate(regions) if r.n_parts > 1]
-        nbytes = lambda c: sum(int(x.nbytes) for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors, c.wblocks, c.wlens, c.wlen_offsets) if x is not None)
-        if args.e2e_stream == "wire":                        # what hcnv_pack_contig_wire hands a host: 1 byte per record + 1 per record that is not READ_LEN long
+        nbytes = lambda c: sum(int(x.nbytes) for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors, c.wblocks, c.wside, c.wside_offsets) if x is not None)
+        if args.e2e_stream == "wire":                        # what hcnv_pack_contig_wire hands a host: 4 bits per record + 1 for its length flag + a byte per delta above 14 and per length that is not READ_LEN
             import dataclasses
             def pin_np(a_):
                 h = torch.empty(a_.shape, dtype=torch.uint8 if a_.dtype == np.uint8 else torch.int32, pin_memory=True).numpy()
@@ -399,7 +399,7 @@ def run_b200(args):
             for i in whole_i:
                 wc = H.wire_contig(host_contigs[i])
                 if wc.wblocks is not None:
-                    host_contigs[i] = dataclasses.replace(wc, anchors=pin_np(wc.anchors), wblocks=pin_np(wc.wblocks), wlens=pin_np(wc.wlens), wlen_offsets=pin_np(wc.wlen_offsets))
+                    host_contigs[i] = dataclasses.replace(wc, wblocks=pin_np(wc.wblocks), wside=pin_np(wc.wside), wside_offsets=pin_np(wc.wside_offsets))
         pipe = gout = prep = None
         if whole_i:
             pipe = GenomePipeline(local, workers=args.e2e_workers, groups=max(1, min(args.e2e_groups, len(whole_i))))
@@ -431,7 +431,7 @@ def run_b200(args):
         launches_of = lambda: (pipe.kernel_launches if pipe is not None else 0) + (ctx_p.kernel_launches if sgp is not None else 0)
         how = ("pinned host inputs (block stream: %s) -> results.txt columns in pinned host arrays (int8 calls, MSE rows listed where non-zero).  Whole chromosomes: hcnv_genome_run "
                "(one C-ABI call: continuous upload in 64 MB pieces, %d worker contexts, tasks of chromosomes: hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> "
-               "hcnv_segment_batch -> hcnv_download_results)%s" % ("hcnv_wblock wire form, ~1.1 B per record, expanded on the device" if args.e2e_stream == "wire" else "hcnv_cblock, 2 B per record", args.e2e_workers, "; parts of the chromosomes cut across ranks: upload -> region binning -> boundary "
+               "hcnv_segment_batch -> hcnv_download_results)%s" % ("hcnv_wblock wire form, ~0.85 B per record, expanded on the device" if args.e2e_stream == "wire" else "hcnv_cblock, 2 B per record", args.e2e_workers, "; parts of the chromosomes cut across ranks: upload -> region binning -> boundary "
                "exchange over NCCL -> download, concurrently; every rank keeps its rows (one part file per rank)" if any_parts else ""))
         for _ in range(2):
             step_e2e()

@@ -19,6 +19,7 @@ HCNV_SEG_SEQUENTIAL = 1
 HCNV_SEG_THROUGHPUT = 2
 HCNV_SEG_LATENCY = 4
 HCNV_CGROUP = 128
+HCNV_WGROUP_BYTES = 80
 KERNELS = dict(tile_index=0, tally=1, bin_tiles=2, text_roundtrip=3, mean_coverage=4, scale_depth=5, sd=6, viterbi=7, traceback=8,
                vit_p0=9, vit_p0c=10, vit_p1=11, vit_p2=12, vit_p3=13, vit_p1b=14, vit_p2b=15, snp_mse=16, vit_many=17)
 
@@ -43,7 +44,7 @@ class ContigInput(C.Structure):
                 ("cblocks", C.c_void_p), ("anchors", C.c_void_p), ("n_cblocks", C.c_int64),
                 ("cobs", C.c_void_p), ("cobs_anchors", C.c_void_p), ("n_cobs", C.c_int64),
                 ("region_first_bin", C.c_int32), ("region_n_bins", C.c_int32), ("snp_index_base", C.c_int64),
-                ("wblocks", C.c_void_p), ("wlens", C.c_void_p), ("wlen_offsets", C.c_void_p), ("n_wlens", C.c_int64),
+                ("wblocks", C.c_void_p), ("wside", C.c_void_p), ("wside_offsets", C.c_void_p), ("n_wside", C.c_int64),
                 ("wire_default_len", C.c_int32), ("reserved", C.c_int32)]
 
 
@@ -149,8 +150,7 @@ def lib():
     L.hcnv_download_results.argtypes = [C.c_void_p, C.POINTER(ResultsDownload)]
     L.hcnv_compact_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
     L.hcnv_compact_blocks.restype = C.c_int64
-    L.hcnv_wire_from_cblocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
-                                         C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    L.hcnv_wire_from_cblocks.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
     L.hcnv_wire_from_cblocks.restype = C.c_int64
     L.hcnv_pack_contig_wire.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(ContigInput), C.POINTER(C.c_int32)]
     L.hcnv_expand_start_end.argtypes = [C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -85,37 +85,45 @@ def compact_obs(obs: np.ndarray):
     return co, anchors[: n // L.HCNV_OGROUP]
 
 
-def wire_blocks(cblocks, anchors, default_len: int = 0):
-    """hcnv_wire_from_cblocks: a compact stream -> its wire form, ~1.1 bytes per record (what a host whose upload bounds the path
-    sends; the library expands it on the device).  Returns (wblocks uint8 16-byte aligned, wlens uint8, anchors int32, wlen_offsets
-    int32, default_len)."""
+def wire_blocks(cblocks, default_len: int = 0):
+    """hcnv_wire_from_cblocks: a compact stream -> its wire form, ~0.85 bytes per record (what a host whose upload bounds the path
+    sends; the library expands it on the device; the anchors stay as they are).  Returns (wblocks uint8 -- HCNV_WGROUP_BYTES per
+    group of HCNV_CGROUP records, 16-byte aligned --, wside uint8, wside_offsets int32, default_len)."""
     lib = L.lib()
     cb = np.ascontiguousarray(np.asarray(cblocks).view(np.uint16))
-    an = np.ascontiguousarray(anchors, dtype=np.int32)
-    nl, dl = C.c_int64(0), C.c_int32(0)
-    n = lib.hcnv_wire_from_cblocks(cb.ctypes.data, an.ctypes.data, len(cb), int(default_len), None, None, None, None, 0, 0, C.byref(dl), C.byref(nl))
-    if n < 0:
-        raise L.HcnvError(int(n), "hcnv_wire_from_cblocks: %s" % lib.hcnv_strerror(int(n)).decode())
-    raw = np.empty(n + 16, np.uint8)
+    dl = C.c_int32(0)
+    ns = lib.hcnv_wire_from_cblocks(cb.ctypes.data, len(cb), int(default_len), None, None, None, 0, C.byref(dl))
+    if ns < 0:
+        raise L.HcnvError(int(ns), "hcnv_wire_from_cblocks: %s" % lib.hcnv_strerror(int(ns)).decode())
+    groups = len(cb) // L.HCNV_CGROUP
+    raw = np.empty(groups * L.HCNV_WGROUP_BYTES + 16, np.uint8)
     sh = (-raw.ctypes.data) % 16
-    w = raw[sh:sh + n]
-    lens = np.empty(max(1, nl.value), np.uint8)
-    wan = np.empty(n // L.HCNV_CGROUP + 1, np.int32)
-    off = np.empty(n // L.HCNV_CGROUP + 1, np.int32)
-    m = lib.hcnv_wire_from_cblocks(cb.ctypes.data, an.ctypes.data, len(cb), int(dl.value), w.ctypes.data, lens.ctypes.data, wan.ctypes.data, off.ctypes.data,
-                                   n, nl.value, C.byref(dl), C.byref(nl))
-    if m != n:
+    w = raw[sh:sh + groups * L.HCNV_WGROUP_BYTES]
+    side = np.empty(max(1, ns), np.uint8)
+    off = np.empty(groups + 1, np.int32)
+    m = lib.hcnv_wire_from_cblocks(cb.ctypes.data, len(cb), int(dl.value), w.ctypes.data, side.ctypes.data, off.ctypes.data, ns, C.byref(dl))
+    if m != ns:
         raise L.HcnvError(int(m), "hcnv_wire_from_cblocks: %s" % lib.hcnv_strerror(int(m)).decode())
-    return w, lens[: nl.value], wan[: n // L.HCNV_CGROUP], off, int(dl.value)
+    return w, side[:ns], off, int(dl.value)
 
 
-def expand_wire(wblocks, wlens, anchors, wlen_offsets, default_len) -> np.ndarray:
-    """The hcnv_cblock stream a wire stream stands for (numpy; test helper -- the library does this on the device)."""
-    w = np.asarray(wblocks, dtype=np.uint8)
-    own = (w & 128) == 0
-    ln = np.full(len(w), int(default_len), np.uint16)
-    ln[own] = np.asarray(wlens, dtype=np.uint8)[: int(own.sum())]
-    return (w & 127).astype(np.uint16) | (ln << 8)
+def expand_wire(wblocks, wside, default_len) -> np.ndarray:
+    """The hcnv_cblock stream a wire stream stands for (numpy; test helper -- the library does this on the device).  The delta of
+    every group's first record comes out 0 (it is ignored: the anchor says where the group starts)."""
+    w = np.asarray(wblocks, dtype=np.uint8).reshape(-1, L.HCNV_WGROUP_BYTES)
+    nib = np.empty((w.shape[0], L.HCNV_CGROUP), np.uint16)
+    nib[:, 0::2] = w[:, :64] & 15
+    nib[:, 1::2] = w[:, :64] >> 4
+    dfl = np.unpackbits(w[:, 64:80], axis=1, bitorder="little").astype(bool)
+    nib, dfl = nib.reshape(-1), dfl.reshape(-1)
+    esc = nib == 15
+    take = esc.astype(np.int64) + (~dfl).astype(np.int64)
+    at = np.cumsum(take) - take                                  # index of the record's first side byte
+    side = np.asarray(wside, dtype=np.uint8).astype(np.uint16)
+    side = np.concatenate([side, np.zeros(2, np.uint16)])
+    delta = np.where(esc, side[at], nib)
+    ln = np.where(dfl, np.uint16(default_len), side[at + esc])
+    return (delta | (ln << 8)).astype(np.uint16)
 
 
 def wire_contig(c: "Contig") -> "Contig":
@@ -124,9 +132,8 @@ def wire_contig(c: "Contig") -> "Contig":
     if c.cblocks is None or len(c.cblocks) == 0:
         return c
     cb = c.cblocks.numpy() if _is_torch(c.cblocks) else c.cblocks
-    an = c.anchors.numpy() if _is_torch(c.anchors) else c.anchors
-    w, lens, wan, off, dl = wire_blocks(cb, an)
-    return dataclasses.replace(c, cblocks=None, anchors=wan, wblocks=w, wlens=lens, wlen_offsets=off, wire_default_len=dl)
+    w, side, off, dl = wire_blocks(cb)
+    return dataclasses.replace(c, cblocks=None, wblocks=w, wside=side, wside_offsets=off, wire_default_len=dl)
 
 
 def expand_cobs(cobs, cobs_anchors) -> np.ndarray:
@@ -180,9 +187,9 @@ class Contig:
     region_first_bin: int = 0      # a REGION of the contig (hcnv_contig_input): first bin (a multiple of 64), bin count (0: to the end) ...
     region_n_bins: int = 0
     snp_index_base: int = 0        # ... and the index of snp_pos1[0] in the contig's whole SNP table (observations keep whole-table indices)
-    wblocks: object = None         # alternative to cblocks: the wire form (hcnv_wblock, uint8, 16-byte aligned) with `anchors`, ...
-    wlens: object = None           # ... its side stream of lengths (uint8), ...
-    wlen_offsets: object = None    # ... the side stream's offset per group (int32, groups + 1) ...
+    wblocks: object = None         # alternative to cblocks: the wire form (hcnv_wblock, uint8, HCNV_WGROUP_BYTES per group, 16-byte aligned) with `anchors`, ...
+    wside: object = None           # ... its side stream (uint8: the deltas above 14 and the lengths that are not the default), ...
+    wside_offsets: object = None   # ... the side stream's offset per group (int32, groups + 1) ...
     wire_default_len: int = 0      # ... and the length of the records that carry none
 
 
@@ -326,8 +333,8 @@ class Context:
             arr[i].obs, arr[i].n_obs = _ptr(c.obs), _len(c.obs)
             arr[i].cblocks, arr[i].anchors, arr[i].n_cblocks = _ptr(c.cblocks), _ptr(c.anchors), _len(c.cblocks)
             if c.wblocks is not None:
-                arr[i].wblocks, arr[i].wlens, arr[i].wlen_offsets = _ptr(c.wblocks), _ptr(c.wlens), _ptr(c.wlen_offsets)
-                arr[i].n_cblocks, arr[i].n_wlens, arr[i].wire_default_len = _len(c.wblocks), _len(c.wlens), int(c.wire_default_len)
+                arr[i].wblocks, arr[i].wside, arr[i].wside_offsets = _ptr(c.wblocks), _ptr(c.wside), _ptr(c.wside_offsets)
+                arr[i].n_cblocks, arr[i].n_wside, arr[i].wire_default_len = _len(c.wblocks) // L.HCNV_WGROUP_BYTES * L.HCNV_CGROUP, _len(c.wside), int(c.wire_default_len)
             arr[i].cobs, arr[i].cobs_anchors, arr[i].n_cobs = _ptr(c.cobs), _ptr(c.cobs_anchors), _len(c.cobs)
             arr[i].region_first_bin, arr[i].region_n_bins, arr[i].snp_index_base = int(c.region_first_bin), int(c.region_n_bins), int(c.snp_index_base)
             for x in (c.blocks, c.cblocks, c.wblocks, c.long_blocks, c.snp_pos1, c.obs, c.cobs):

@@ -344,31 +344,36 @@ __global__ void k_snp_mse(BinK p) {
 namespace {
 // (scratch slot ids: hcnv_internal.h)
 
-// The wire form (hcnv_wblock, ~1.1 bytes per record) -> hcnv_cblock records, one warp per group of HCNV_CGROUP records: a lane takes
-// four records (one 32-bit load), the lanes' counts of records with their own length byte are scanned across the warp, and
-// each lane writes its four 2-byte records with one 8-byte store.  HBM-bound: 3.2 bytes moved per record.
-struct WireJob { const hcnv_wblock* w; const uint8_t* lens; const int32_t* offs; hcnv_cblock* out; long long n_groups, n_lens; int default_len; };
+// The wire form (hcnv_wblock, ~0.85 bytes per record) -> hcnv_cblock records, one warp per group of HCNV_CGROUP records: a lane takes
+// four records (their nibbles: one 16-bit load; their default-length bits: 4 bits of a 32-bit word), the lanes' counts of
+// side-stream bytes are scanned across the warp, and each lane writes its four 2-byte records with one 8-byte store.
+// HBM-bound: 2.9 bytes moved per record.
+struct WireJob { const hcnv_wblock* w; const uint8_t* side; const int32_t* offs; hcnv_cblock* out; long long n_groups, n_side; int default_len; };
 
 __global__ void __launch_bounds__(256) k_expand_wire(WireJob j, int32_t* err)
 {
     const int lane = threadIdx.x & 31;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < j.n_groups; g += warps) {
-        const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(j.w) + g * 32 + lane);
-        const int own = 4 - __popc(x & 0x80808080u);                 // records of this lane that take a byte of the side stream
+        const hcnv_wblock* grp = j.w + g * HCNV_WGROUP_BYTES;
+        const uint32_t nib = __ldg(reinterpret_cast<const uint16_t*>(grp) + lane);
+        const uint32_t dfl = (__ldg(reinterpret_cast<const uint32_t*>(grp + 64) + (lane >> 3)) >> ((lane & 7) * 4)) & 15u;
+        const uint32_t esc = ((nib & 0xFu) == 0xFu ? 1u : 0u) | ((nib & 0xF0u) == 0xF0u ? 2u : 0u) | ((nib & 0xF00u) == 0xF00u ? 4u : 0u) | ((nib & 0xF000u) == 0xF000u ? 8u : 0u);
+        const int own = __popc(esc) + 4 - __popc(dfl);                // bytes of the side stream this lane's records take
         int r = own;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, r, d); if (lane >= d) r += t; }
         const int total = __shfl_sync(0xffffffffu, r, 31);
         const long long off = j.offs[g];
-        if (off < 0 || off + total > j.n_lens || (long long)j.offs[g + 1] - off != total) { if (lane == 0) atomicOr(&err[ERR_RANGE], 1); continue; }
-        const uint8_t* lp = j.lens + off + (r - own);
+        if (off < 0 || off + total > j.n_side || (long long)j.offs[g + 1] - off != total) { if (lane == 0) atomicOr(&err[ERR_RANGE], 1); continue; }
+        const uint8_t* sp = j.side + off + (r - own);
         uint32_t rec[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const uint32_t byte = (x >> (8 * b)) & 0xFFu;
-            const uint32_t len = (byte & 128u) ? (uint32_t)j.default_len : (uint32_t)__ldg(lp++);
-            rec[b] = (byte & 127u) | (len << 8);
+            uint32_t delta = (nib >> (4 * b)) & 15u;
+            if ((esc >> b) & 1u) delta = __ldg(sp++);
+            const uint32_t len = ((dfl >> b) & 1u) ? (uint32_t)j.default_len : (uint32_t)__ldg(sp++);
+            rec[b] = delta | (len << 8);
         }
         reinterpret_cast<uint2*>(j.out)[g * 32 + lane] = make_uint2(rec[0] | (rec[1] << 16), rec[2] | (rec[3] << 16));
     }
@@ -411,7 +416,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             if (ci.n_cblocks % HCNV_CGROUP) return hcnv_fail(ctx, HCNV_E_INVALID, "n_cblocks must be a multiple of HCNV_CGROUP (pad with fillers)");
             if (ci.wblocks) {                                  // the wire form: expanded to hcnv_cblock records on the device below
                 if (ci.cblocks) return hcnv_fail(ctx, HCNV_E_INVALID, "give cblocks or wblocks, not both");
-                if (!ci.anchors || !ci.wlen_offsets || ci.n_wlens < 0 || (ci.n_wlens > 0 && !ci.wlens)) return hcnv_fail(ctx, HCNV_E_INVALID, "null wire arrays");
+                if (!ci.anchors || !ci.wside_offsets || ci.n_wside < 0 || (ci.n_wside > 0 && !ci.wside)) return hcnv_fail(ctx, HCNV_E_INVALID, "null wire arrays");
                 if (ci.wire_default_len < 1 || ci.wire_default_len > 255) return hcnv_fail(ctx, HCNV_E_INVALID, "wire_default_len must be in [1, 255]");
                 if (reinterpret_cast<uintptr_t>(ci.wblocks) & 15) return hcnv_fail(ctx, HCNV_E_INVALID, "wblocks must be 16-byte aligned");
             } else {
@@ -447,7 +452,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     // pointer kinds
     int in_kind = -1;
     long long tot_blocks = 0, tot_cblocks = 0, tot_long = 0, tot_snp = 0, tot_obs = 0, tot_cobs = 0, tot_bins_max = 0;
-    long long tot_wire = 0, tot_wlens = 0, n_wire = 0;
+    long long tot_wire = 0, tot_wlens = 0, tot_wgroups = 0, n_wire = 0;     // wire form: bytes of wblocks, of wside (padded), groups, contigs
     for (int c = 0; c < n_contigs; ++c) {
         const hcnv_contig_input& ci = contigs[c];
         if (ci.length < 0 || ci.n_blocks < 0 || ci.n_long < 0 || ci.n_snp < 0 || ci.n_obs < 0) return hcnv_fail(ctx, HCNV_E_INVALID, "negative count");
@@ -459,10 +464,10 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
                                  ci.n_snp ? (const void*)ci.snp_pos1 : nullptr, ci.n_snp ? (const void*)ci.snp_zyg : nullptr,
                                  ci.n_obs ? (const void*)ci.obs : nullptr, ci.n_cblocks ? (wire ? (const void*)ci.wblocks : (const void*)ci.cblocks) : nullptr,
                                  ci.n_cblocks ? (const void*)ci.anchors : nullptr, ci.n_cobs ? (const void*)ci.cobs : nullptr,
-                                 ci.n_cobs ? (const void*)ci.cobs_anchors : nullptr, wire ? (const void*)ci.wlen_offsets : nullptr,
-                                 wire && ci.n_wlens ? (const void*)ci.wlens : nullptr };
-        const long long cnts[11] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs, ci.n_cblocks, ci.n_cblocks, ci.n_cobs, ci.n_cobs, wire ? 1 : 0, wire ? ci.n_wlens : 0 };
-        if (wire) { tot_wire += ci.n_cblocks; tot_wlens += (ci.n_wlens + 15) / 16 * 16; ++n_wire; }
+                                 ci.n_cobs ? (const void*)ci.cobs_anchors : nullptr, wire ? (const void*)ci.wside_offsets : nullptr,
+                                 wire && ci.n_wside ? (const void*)ci.wside : nullptr };
+        const long long cnts[11] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs, ci.n_cblocks, ci.n_cblocks, ci.n_cobs, ci.n_cobs, wire ? 1 : 0, wire ? ci.n_wside : 0 };
+        if (wire) { tot_wire += ci.n_cblocks / HCNV_CGROUP * HCNV_WGROUP_BYTES; tot_wlens += (ci.n_wside + 15) / 16 * 16; tot_wgroups += ci.n_cblocks / HCNV_CGROUP; ++n_wire; }
         for (int j = 0; j < 11; ++j) {
             if (cnts[j] == 0) continue;
             if (!ptrs[j]) return hcnv_fail(ctx, HCNV_E_INVALID, "null input array with non-zero count");
@@ -483,7 +488,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     std::vector<ContigDev> hc(n_contigs);
     std::vector<WireJob> wire_jobs;
     if (in_kind == 2 && n_wire) HCNV_CUDA(ctx, ctx->buf[B_IN_BLOCKS].reserve(sizeof(hcnv_cblock) * (size_t)tot_cblocks));   // where device-resident wire streams expand to
-    if (in_kind != 2 && n_wire) HCNV_CUDA(ctx, ctx->buf[B_IN_WIRE].reserve((size_t)tot_wire + (size_t)tot_wlens + 4 * (size_t)(tot_wire / HCNV_CGROUP + n_wire) + 64));
+    if (in_kind != 2 && n_wire) HCNV_CUDA(ctx, ctx->buf[B_IN_WIRE].reserve((size_t)tot_wire + (size_t)tot_wlens + 4 * (size_t)(tot_wgroups + n_wire) + 64));
     long long ow = 0, owl = 0, owo = 0;
     if (in_kind != 2) {
         HCNV_CUDA(ctx, ctx->buf[B_IN_BLOCKS].reserve(sizeof(hcnv_block) * (size_t)tot_blocks + sizeof(hcnv_cblock) * (size_t)tot_cblocks));
@@ -506,7 +511,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             d.cblocks = ci.cblocks; d.anchors = ci.anchors;
             if (ci.n_cblocks > 0 && ci.wblocks) {
                 d.cblocks = ctx->buf[B_IN_BLOCKS].as<hcnv_cblock>() + ocb;
-                wire_jobs.push_back(WireJob{ ci.wblocks, ci.wlens, ci.wlen_offsets, const_cast<hcnv_cblock*>(d.cblocks), ci.n_cblocks / HCNV_CGROUP, ci.n_wlens, ci.wire_default_len });
+                wire_jobs.push_back(WireJob{ ci.wblocks, ci.wside, ci.wside_offsets, const_cast<hcnv_cblock*>(d.cblocks), ci.n_cblocks / HCNV_CGROUP, ci.n_wside, ci.wire_default_len });
             }
             d.cobs = ci.n_cobs ? ci.cobs : nullptr; d.cobs_anchors = ci.cobs_anchors;
         } else {
@@ -525,11 +530,11 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
                 uint8_t* dl = reinterpret_cast<uint8_t*>(wb + tot_wire) + owl;
                 int32_t* dof = reinterpret_cast<int32_t*>(wb + tot_wire + tot_wlens) + owo;
                 const long long ng = ci.n_cblocks / HCNV_CGROUP;
-                if ((rc = stage_in(ctx, in_kind, ci.wblocks, ci.n_cblocks, dw))) return rc;
-                if ((rc = stage_in(ctx, in_kind, ci.wlens, ci.n_wlens, dl))) return rc;
-                if ((rc = stage_in(ctx, in_kind, ci.wlen_offsets, ng + 1, dof))) return rc;
-                wire_jobs.push_back(WireJob{ dw, dl, dof, const_cast<hcnv_cblock*>(d.cblocks), ng, ci.n_wlens, ci.wire_default_len });
-                ow += ci.n_cblocks; owl += (ci.n_wlens + 15) / 16 * 16; owo += ng + 1;
+                if ((rc = stage_in(ctx, in_kind, ci.wblocks, ng * HCNV_WGROUP_BYTES, dw))) return rc;
+                if ((rc = stage_in(ctx, in_kind, ci.wside, ci.n_wside, dl))) return rc;
+                if ((rc = stage_in(ctx, in_kind, ci.wside_offsets, ng + 1, dof))) return rc;
+                wire_jobs.push_back(WireJob{ dw, dl, dof, const_cast<hcnv_cblock*>(d.cblocks), ng, ci.n_wside, ci.wire_default_len });
+                ow += ng * HCNV_WGROUP_BYTES; owl += (ci.n_wside + 15) / 16 * 16; owo += ng + 1;
             } else
             if ((rc = stage_in(ctx, in_kind, ci.cblocks, ci.n_cblocks, const_cast<hcnv_cblock*>(d.cblocks)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.anchors, ci.n_cblocks / HCNV_CGROUP, const_cast<int32_t*>(d.anchors)))) return rc;

@@ -77,9 +77,9 @@ void contig_fields(const hcnv_contig_input& c, Field f[ST_N]) {
     f[ST_OBS]     = { c.obs, 4 * (size_t)c.n_obs };
     const bool wire = c.wblocks != nullptr && c.n_cblocks > 0;                   // the block stream in its wire form (hcnv_wblock)
     f[ST_CBLOCKS] = { c.cblocks, wire ? 0 : sizeof(hcnv_cblock) * (size_t)c.n_cblocks };
-    f[ST_WBLOCKS] = { c.wblocks, wire ? (size_t)c.n_cblocks : 0 };
-    f[ST_WLENS]   = { c.wlens, wire ? (size_t)std::max<int64_t>(c.n_wlens, 0) : 0 };
-    f[ST_WOFFS]   = { c.wlen_offsets, wire ? 4 * (size_t)(c.n_cblocks / HCNV_CGROUP + 1) : 0 };
+    f[ST_WBLOCKS] = { c.wblocks, wire ? (size_t)(c.n_cblocks / HCNV_CGROUP) * HCNV_WGROUP_BYTES : 0 };
+    f[ST_WLENS]   = { c.wside, wire ? (size_t)std::max<int64_t>(c.n_wside, 0) : 0 };
+    f[ST_WOFFS]   = { c.wside_offsets, wire ? 4 * (size_t)(c.n_cblocks / HCNV_CGROUP + 1) : 0 };
     f[ST_ANCHORS] = { c.anchors, 4 * (size_t)(c.n_cblocks / HCNV_CGROUP) };
     f[ST_COBS]    = { c.cobs, sizeof(hcnv_cobs) * (size_t)c.n_cobs };
     f[ST_COBSANC] = { c.cobs_anchors, 4 * (size_t)(c.n_cobs / HCNV_OGROUP) };
@@ -367,7 +367,7 @@ static void genome_uploader(hcnv_genome* g) {
             di.snp_pos1 = (const int32_t*)d[ST_SNPPOS]; di.snp_zyg = (const int8_t*)d[ST_SNPZYG]; di.obs = (const uint32_t*)d[ST_OBS];
             di.cblocks = (const hcnv_cblock*)d[ST_CBLOCKS]; di.anchors = (const int32_t*)d[ST_ANCHORS];
             di.cobs = (const hcnv_cobs*)d[ST_COBS]; di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
-            di.wblocks = (const hcnv_wblock*)d[ST_WBLOCKS]; di.wlens = (const uint8_t*)d[ST_WLENS]; di.wlen_offsets = (const int32_t*)d[ST_WOFFS];
+            di.wblocks = (const hcnv_wblock*)d[ST_WBLOCKS]; di.wside = (const uint8_t*)d[ST_WLENS]; di.wside_offsets = (const int32_t*)d[ST_WOFFS];
             task.contigs.push_back(c);
         }
         if (!ok || task.contigs.empty()) continue;

@@ -38,7 +38,7 @@ struct hcnv_pack {
         std::string name; int32_t length = 0; int32_t max_len = 0;
         std::vector<hcnv_block> blocks; std::vector<hcnv_long_block> longs; std::vector<uint32_t> obs;
         std::vector<hcnv_cblock> cstore; std::vector<int32_t> anchors; hcnv_cblock* cblocks = nullptr; int64_t n_cblocks = -1;   // built on demand
-        std::vector<uint8_t> wstore, wlens; std::vector<int32_t> wanchors, wlen_offsets; hcnv_wblock* wblocks = nullptr; int64_t n_wblocks = -1; int32_t wdefault = 0;   // built on demand
+        std::vector<uint8_t> wstore, wside; std::vector<int32_t> wside_offsets; hcnv_wblock* wblocks = nullptr; int64_t n_wside = -1; int32_t wdefault = 0;   // built on demand
         std::vector<hcnv_cobs> cobs; std::vector<int32_t> cobs_anchors; int64_t n_cobs = -1;                                        // built on demand
         const std::vector<int32_t>* snp_pos = nullptr; const std::vector<int8_t>* snp_zyg = nullptr;
     };
@@ -666,10 +666,9 @@ int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, double mapping_
     return k;
 }
 
-int64_t hcnv_wire_from_cblocks(const hcnv_cblock* cb, const int32_t* cb_anchors, int64_t n, int32_t default_len,
-                               hcnv_wblock* out, uint8_t* wlens, int32_t* anchors, int32_t* wlen_offsets,
-                               int64_t capacity, int64_t wlens_capacity, int32_t* default_len_used, int64_t* n_wlens) {
-    if (n < 0 || n % HCNV_CGROUP || (n > 0 && (!cb || !cb_anchors)) || (out && (!wlens || !anchors || !wlen_offsets)) || default_len < 0 || default_len > 255)
+int64_t hcnv_wire_from_cblocks(const hcnv_cblock* cb, int64_t n, int32_t default_len,
+                               hcnv_wblock* out, uint8_t* wside, int32_t* wside_offsets, int64_t wside_capacity, int32_t* default_len_used) {
+    if (n < 0 || n % HCNV_CGROUP || (n > 0 && !cb) || (out && (!wside_offsets || (wside_capacity > 0 && !wside))) || default_len < 0 || default_len > 255)
         return HCNV_E_INVALID;
     if (default_len == 0) {                                 // the most frequent length (the read length)
         std::vector<int64_t> hist(256, 0);
@@ -678,46 +677,28 @@ int64_t hcnv_wire_from_cblocks(const hcnv_cblock* cb, const int32_t* cb_anchors,
         for (int l = 1; l < 256; ++l) if (hist[(size_t)l] > hist[(size_t)best]) best = l;
         default_len = best;
     }
-    int64_t k = 0, nl = 0;                                  // wire records / side-stream bytes written (or counted) so far
-    int64_t prev = 0;                                       // start0 of the last record written
-    auto put = [&](int64_t start0, uint32_t delta, uint32_t len) -> bool {
-        const bool dflt = len == (uint32_t)default_len;
-        if (out) {
-            if (k >= capacity || (!dflt && nl >= wlens_capacity)) return false;
-            if (k % HCNV_CGROUP == 0) { anchors[k / HCNV_CGROUP] = (int32_t)start0; wlen_offsets[k / HCNV_CGROUP] = (int32_t)nl; delta = 0; }
-            out[k] = (hcnv_wblock)(delta | (dflt ? 128u : 0u));
-            if (!dflt) wlens[nl] = (uint8_t)len;
-        }
-        ++k;
-        if (!dflt) ++nl;
-        return true;
-    };
-    int64_t pos = 0;
-    bool first = true;
-    for (int64_t i = 0; i < n; ++i) {
-        pos = (i % HCNV_CGROUP == 0) ? (int64_t)cb_anchors[i / HCNV_CGROUP] : pos + (cb[i] & 0xFF);
-        const uint32_t len = cb[i] >> 8;
-        if (len == 0) continue;                             // the 2-byte stream's fillers: the gaps are bridged anew below
-        if (pos < prev && !first) return HCNV_E_UNSORTED;
-        int64_t gap = first ? 0 : pos - prev;
-        if (gap > 127 && k % HCNV_CGROUP) {
-            const int64_t fillers = (gap - 1) / 127, to_end = HCNV_CGROUP - k % HCNV_CGROUP;
-            if (to_end <= fillers) { while (k % HCNV_CGROUP) if (!put(prev, 0u, 0u)) return HCNV_E_CAPACITY; }   // the next anchor makes the jump
-            else while (gap > 127) {
-                if (k % HCNV_CGROUP == 0) break;            // (the fillers reached a group boundary: its anchor makes the rest of the jump)
-                prev += 127; gap -= 127;
-                if (!put(prev, 127u, 0u)) return HCNV_E_CAPACITY;
-            }
-        }
-        if (!put(pos, k % HCNV_CGROUP ? (uint32_t)gap : 0u, len)) return HCNV_E_CAPACITY;
-        prev = pos; first = false;
-    }
-    while (k % HCNV_CGROUP) if (!put(prev, 0u, 0u)) return HCNV_E_CAPACITY;
-    if (nl >= (1ll << 31)) return HCNV_E_RANGE;
-    if (out) wlen_offsets[k / HCNV_CGROUP] = (int32_t)nl;
     if (default_len_used) *default_len_used = default_len;
-    if (n_wlens) *n_wlens = nl;
-    return k;
+    int64_t ns = 0;                                         // side-stream bytes written (or counted) so far
+    for (int64_t g = 0; g < n / HCNV_CGROUP; ++g) {
+        const hcnv_cblock* rec = cb + g * HCNV_CGROUP;
+        if (out) { wside_offsets[g] = (int32_t)ns; memset(out + g * HCNV_WGROUP_BYTES, 0, HCNV_WGROUP_BYTES); }
+        hcnv_wblock* w = out ? out + g * HCNV_WGROUP_BYTES : nullptr;
+        for (int i = 0; i < HCNV_CGROUP; ++i) {
+            const uint32_t delta = i ? (rec[i] & 0xFFu) : 0u, len = rec[i] >> 8;       // (the group's first delta is ignored: the anchor says where it starts)
+            const bool esc = delta >= 15u, own = len != (uint32_t)default_len;
+            if (out) {
+                if (ns + (esc ? 1 : 0) + (own ? 1 : 0) > wside_capacity) return HCNV_E_CAPACITY;
+                w[i >> 1] |= (hcnv_wblock)((esc ? 15u : delta) << (4 * (i & 1)));
+                if (!own) w[64 + (i >> 3)] |= (hcnv_wblock)(1u << (i & 7));
+                if (esc) wside[ns] = (uint8_t)delta;
+                if (own) wside[ns + (esc ? 1 : 0)] = (uint8_t)len;
+            }
+            ns += (esc ? 1 : 0) + (own ? 1 : 0);
+        }
+        if (ns >= (1ll << 31)) return HCNV_E_RANGE;
+    }
+    if (out) wside_offsets[n / HCNV_CGROUP] = (int32_t)ns;
+    return ns;
 }
 
 int64_t hcnv_compact_obs(const uint32_t* obs, int64_t n, hcnv_cobs* out, int32_t* anchors, int64_t capacity) {
@@ -799,27 +780,25 @@ int hcnv_pack_contig_wire(hcnv_pack* p, int32_t i, const char** name, hcnv_conti
     int rc = hcnv_pack_contig_compact(p, i, name, in, max_block_len);
     if (rc) return rc;
     hcnv_pack::Contig& c = p->contigs[(size_t)i];
-    if (c.n_wblocks < 0) {                                  // first request: the wire form of the 2-byte stream, 16-byte aligned
-        int64_t nl = 0; int32_t dl = 0;
-        const int64_t n = hcnv_wire_from_cblocks(c.cblocks, c.anchors.data(), c.n_cblocks, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, &dl, &nl);
-        if (n < 0) return (int)n;
-        c.wstore.resize((size_t)n + 16);
+    if (c.n_wside < 0) {                                    // first request: the wire form of the 2-byte stream, 16-byte aligned
+        int32_t dl = 0;
+        const int64_t ns = hcnv_wire_from_cblocks(c.cblocks, c.n_cblocks, 0, nullptr, nullptr, nullptr, 0, &dl);
+        if (ns < 0) return (int)ns;
+        const size_t groups = (size_t)(c.n_cblocks / HCNV_CGROUP);
+        c.wstore.resize(groups * HCNV_WGROUP_BYTES + 16);
         const uintptr_t a = reinterpret_cast<uintptr_t>(c.wstore.data());
         c.wblocks = c.wstore.data() + ((16 - (a & 15)) & 15);
-        c.wlens.resize((size_t)nl + 1);
-        c.wanchors.resize((size_t)(n / HCNV_CGROUP) + 1);
-        c.wlen_offsets.resize((size_t)(n / HCNV_CGROUP) + 1);
-        const int64_t m = hcnv_wire_from_cblocks(c.cblocks, c.anchors.data(), c.n_cblocks, dl, c.wblocks, c.wlens.data(), c.wanchors.data(), c.wlen_offsets.data(),
-                                                 n, nl, &c.wdefault, &nl);
-        if (m != n) return HCNV_E_INTERNAL;
-        c.n_wblocks = n;
+        c.wside.resize((size_t)ns + 1);
+        c.wside_offsets.resize(groups + 1);
+        const int64_t m = hcnv_wire_from_cblocks(c.cblocks, c.n_cblocks, dl, c.wblocks, c.wside.data(), c.wside_offsets.data(), ns, &c.wdefault);
+        if (m != ns) return HCNV_E_INTERNAL;
+        c.n_wside = ns;
     }
-    in->cblocks = nullptr;
-    in->n_cblocks = c.n_wblocks;
-    in->anchors = c.n_wblocks ? c.wanchors.data() : nullptr;
-    in->wblocks = c.n_wblocks ? c.wblocks : nullptr; in->wlens = c.wlens.data(); in->wlen_offsets = c.wlen_offsets.data();
-    in->n_wlens = c.n_wblocks ? (int64_t)c.wlen_offsets[(size_t)(c.n_wblocks / HCNV_CGROUP)] : 0;
-    in->wire_default_len = c.wdefault;
+    if (c.n_cblocks > 0) {
+        in->cblocks = nullptr;
+        in->wblocks = c.wblocks; in->wside = c.wside.data(); in->wside_offsets = c.wside_offsets.data();
+        in->n_wside = c.n_wside; in->wire_default_len = c.wdefault;
+    }
     return HCNV_OK;
 }
 

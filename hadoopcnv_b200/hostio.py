@@ -57,7 +57,7 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
     """hcnv_bam_pack -> (names, [Contig with numpy arrays], [max_block_len], n_records).  Arrays are copies.
     compact=True: the block stream comes in the 2-byte delta-coded form (Contig.cblocks / anchors) and the observations in
     their 2-byte form (Contig.cobs / cobs_anchors).  wire=True: the block stream in its ~1.1-byte wire form instead
-    (Contig.wblocks / wlens / wlen_offsets / anchors, hcnv_pack_contig_wire)."""
+    (Contig.wblocks / wside / wside_offsets, anchors as before; hcnv_pack_contig_wire)."""
     lib = L.lib()
     compact = compact or wire
     h = C.c_void_p()
@@ -96,12 +96,13 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
                                   arr(ci.anchors, ci.n_cblocks // L.HCNV_CGROUP, np.int32),
                                   arr(ci.cobs, ci.n_cobs, np.uint16), arr(ci.cobs_anchors, ci.n_cobs // L.HCNV_OGROUP, np.int32)))
             if wire and ci.n_cblocks:
-                raw = np.empty(ci.n_cblocks + 16, np.uint8)
+                nw = ci.n_cblocks // L.HCNV_CGROUP * L.HCNV_WGROUP_BYTES
+                raw = np.empty(nw + 16, np.uint8)
                 sh = (-raw.ctypes.data) % 16
-                raw[sh:sh + ci.n_cblocks] = np.frombuffer((C.c_char * ci.n_cblocks).from_address(ci.wblocks), dtype=np.uint8)
+                raw[sh:sh + nw] = np.frombuffer((C.c_char * nw).from_address(ci.wblocks), dtype=np.uint8)
                 k = contigs[-1]
-                k.wblocks, k.wlens = raw[sh:sh + ci.n_cblocks], (arr(ci.wlens, ci.n_wlens, np.uint8) if ci.n_wlens else np.zeros(0, np.uint8))
-                k.wlen_offsets, k.wire_default_len = arr(ci.wlen_offsets, ci.n_cblocks // L.HCNV_CGROUP + 1, np.int32), int(ci.wire_default_len)
+                k.wblocks, k.wside = raw[sh:sh + nw], (arr(ci.wside, ci.n_wside, np.uint8) if ci.n_wside else np.zeros(0, np.uint8))
+                k.wside_offsets, k.wire_default_len = arr(ci.wside_offsets, ci.n_cblocks // L.HCNV_CGROUP + 1, np.int32), int(ci.wire_default_len)
         return names, contigs, maxlens, int(lib.hcnv_pack_n_records(h))
     finally:
         lib.hcnv_pack_free(h)

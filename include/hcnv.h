@@ -110,17 +110,20 @@ typedef struct { int32_t start0; uint32_t len_mapq; } hcnv_block;
 typedef uint16_t hcnv_cblock;
 #define HCNV_CGROUP 128
 
-/* The same records at about 1.1 bytes each -- the WIRE form, for a host whose upload bounds the path (one 30X genome: 0.7 GB
- * instead of 1.2 GB; the library expands it to hcnv_cblock records on the device, 0.3 ms per genome, before binning):
- *   wblocks[i]   bits 0-6  start0 - start0 of the previous record (0..127)
- *                bit 7     1: the block has the contig's default length (wire_default_len, 1..255 -- the read length, nine
- *                          records in ten); 0: its length (0..255, 0 = filler) is the next byte of the side stream wlens
- *   anchors[g]   as above: start0 of record HCNV_CGROUP * g (that record's delta field is ignored)
- *   wlen_offsets[g] = index in wlens of the first length byte of group g; n_cblocks / HCNV_CGROUP + 1 entries, the last = n_wlens
- * Record i of the wire form IS record i of the hcnv_cblock stream it expands to (same count n_cblocks, same anchors); a gap
- * above 127 is bridged by fillers or, where that is shorter, by closing the group with fillers so that the next anchor makes
- * the jump.  wblocks must be 16-byte aligned.  hcnv_wire_from_cblocks builds it. */
+/* The same records at about 0.85 bytes each -- the WIRE form, for a host whose upload bounds the path (one 30X genome: 0.5 GB
+ * instead of 1.2 GB; the library expands it to hcnv_cblock records on the device, 0.3 ms per genome, before binning).  It is a
+ * re-encoding of the hcnv_cblock stream record for record (same count n_cblocks, same anchors).  Every group of HCNV_CGROUP
+ * records is HCNV_WGROUP_BYTES bytes of wblocks:
+ *   bytes 0-63   one nibble per record, record i of the group in bits 4 * (i & 1) .. of byte i / 2: its delta (0..14), or 15 =
+ *                the delta (0..255) is a byte of the side stream
+ *   bytes 64-79  one bit per record (bit i & 7 of byte 64 + i / 8): 1 = the block has the contig's default length
+ *                (wire_default_len, 1..255 -- the read length, nine records in ten), 0 = its length (0..255) is a byte of the
+ *                side stream
+ * wside holds those bytes in record order (a record's delta byte before its length byte); wside_offsets[g] = index in wside of
+ * group g's first byte, n_cblocks / HCNV_CGROUP + 1 entries, the last = n_wside.  wblocks must be 16-byte aligned.
+ * hcnv_wire_from_cblocks builds it. */
 typedef uint8_t hcnv_wblock;
+#define HCNV_WGROUP_BYTES 80
 
 /* The observations at SNP sites at 2 bytes each (at 4 bytes they are a fifth of what a 30X genome uploads):
  *   bits 0-3  BAM 4-bit base code      bits 4-15  snp index - cobs_anchors[k / HCNV_OGROUP]   (0..4094; 4095 = filler, no observation)
@@ -170,7 +173,7 @@ typedef struct {
     int32_t                region_first_bin, region_n_bins;
     int64_t                snp_index_base;
     /* alternative to `cblocks` (cblocks null, n_cblocks and anchors as for cblocks): the wire form, see hcnv_wblock */
-    const hcnv_wblock*     wblocks;     const uint8_t* wlens; const int32_t* wlen_offsets; int64_t n_wlens;
+    const hcnv_wblock*     wblocks;     const uint8_t* wside; const int32_t* wside_offsets; int64_t n_wside;
     int32_t                wire_default_len; int32_t reserved;
 } hcnv_contig_input;
 
@@ -182,14 +185,13 @@ typedef struct {
 int64_t hcnv_compact_blocks(const hcnv_block* blocks, int64_t n, double mapping_quality_threshold,
                             hcnv_cblock* out, int32_t* anchors, int64_t capacity);
 
-/* Host helper (no GPU): a compact stream -> its wire form (hcnv_wblock).  default_len 0 picks the most frequent length.
- * Returns the number of wire records (a multiple of HCNV_CGROUP; it differs from n_cblocks where gaps of 128 - 255 bases
- * needed a filler) or a negative status; *n_wlens = bytes of the side stream.  With out == NULL only counts.  anchors
- * needs result / HCNV_CGROUP entries, wlen_offsets one more.  HCNV_E_CAPACITY if `capacity` (records) or `wlens_capacity`
- * (bytes) is too small. */
-int64_t hcnv_wire_from_cblocks(const hcnv_cblock* cblocks, const int32_t* cblock_anchors, int64_t n_cblocks, int32_t default_len,
-                               hcnv_wblock* out, uint8_t* wlens, int32_t* anchors, int32_t* wlen_offsets,
-                               int64_t capacity, int64_t wlens_capacity, int32_t* default_len_used, int64_t* n_wlens);
+/* Host helper (no GPU): a compact stream -> its wire form (hcnv_wblock; the anchors stay as they are).  default_len 0 picks
+ * the most frequent length.  Returns the bytes of the side stream or a negative status; with wblocks == NULL only counts.
+ * wblocks needs n_cblocks / HCNV_CGROUP * HCNV_WGROUP_BYTES bytes, wside_offsets n_cblocks / HCNV_CGROUP + 1 entries.
+ * HCNV_E_CAPACITY if wside_capacity (bytes) is too small, HCNV_E_RANGE for a side stream of 2^31 bytes or more. */
+int64_t hcnv_wire_from_cblocks(const hcnv_cblock* cblocks, int64_t n_cblocks, int32_t default_len,
+                               hcnv_wblock* wblocks, uint8_t* wside, int32_t* wside_offsets, int64_t wside_capacity,
+                               int32_t* default_len_used);
 
 /* Host helper (no GPU): obs (snp index << 4 | base4, any order) -> the 2-byte stream.  Returns the number of entries
  * (fillers and padding included, a multiple of HCNV_OGROUP) or a negative status; with out == NULL only counts.  anchors
@@ -248,7 +250,7 @@ int     hcnv_pack_contig(const hcnv_pack* p, int32_t i, const char** name, hcnv_
 /* the same with both streams in their 2-byte forms (built on the first request): in->cblocks / anchors / n_cblocks and
  * in->cobs / cobs_anchors / n_cobs; in->blocks and in->obs are null */
 int     hcnv_pack_contig_compact(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
-/* the same with the block stream in its wire form (in->wblocks / wlens / wlen_offsets / anchors; in->cblocks null) */
+/* the same with the block stream in its wire form (in->wblocks / wside / wside_offsets; anchors as before; in->cblocks null) */
 int     hcnv_pack_contig_wire(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
 void    hcnv_pack_free(hcnv_pack* p);
 

@@ -455,21 +455,21 @@ def test_end_to_end_bins_to_calls(ctx):
 
 @pytest.mark.parametrize("W,cov", [(100, 30), (50, 100), (1000, 30)])
 def test_binning_wire_stream_matches_compact_stream(ctx, W, cov):
-    """The block stream in its ~1.1-byte wire form (hcnv_wblock), expanded on the device, gives the bins of the 2-byte stream it
+    """The block stream in its ~0.85-byte wire form (hcnv_wblock), expanded on the device, gives the bins of the 2-byte stream it
     was made from and of the oracle -- from host and from device buffers; a damaged side stream is refused."""
     import dataclasses
     g = synth.make_genome(coverage=cov, scale=0.0015, device="cpu", contigs=["chr10", "chr11", "chr21", "chrY"], seed=99 + W)
     base = synth.to_api_contigs(g, host=True, compact=True, compact_observations=True)
     wire = [H.wire_contig(c) for c in base]
     assert all(c.cblocks is None and c.wblocks is not None and c.wire_default_len == synth.READ_LEN for c in wire)
-    sent = sum(c.wblocks.nbytes + c.wlens.nbytes + c.wlen_offsets.nbytes for c in wire)
-    assert sent < 0.62 * sum(np.asarray(c.cblocks).nbytes for c in base)                 # ~1.15 bytes per record instead of 2
+    sent = sum(c.wblocks.nbytes + c.wside.nbytes + c.wside_offsets.nbytes for c in wire)
+    assert sent < 0.5 * sum(np.asarray(c.cblocks).nbytes for c in base)                  # ~0.85 bytes per record instead of 2
     want = ctx.bin_contigs(base, bin_width=W, max_block_len=synth.READ_LEN)
     import torch
     def dev(c):
         t = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x).view(np.int8 if x.dtype.itemsize == 1 else np.int16 if x.dtype.itemsize == 2 else np.int32)).cuda()
         return dataclasses.replace(c, long_blocks=t(c.long_blocks), snp_pos1=t(c.snp_pos1), snp_zyg=t(c.snp_zyg), cobs=t(c.cobs), cobs_anchors=t(c.cobs_anchors),
-                                   anchors=t(c.anchors), wblocks=t(c.wblocks), wlens=t(c.wlens), wlen_offsets=t(c.wlen_offsets))
+                                   anchors=t(c.anchors), wblocks=t(c.wblocks), wside=t(c.wside), wside_offsets=t(c.wside_offsets))
     for host in (True, False):
         res = ctx.bin_contigs(wire if host else [dev(c) for c in wire], bin_width=W, max_block_len=synth.READ_LEN)
         for i, c in enumerate(g):
@@ -478,8 +478,8 @@ def test_binning_wire_stream_matches_compact_stream(ctx, W, cov):
             w_ = want.contig(i)
             assert_bins_equal(got, {k: np.asarray(getattr(w_, k)) for k in ("bin", "start", "end", "n", "median", "total", "mse")})
             assert_bins_equal(got, oracle_bins(c, W))
-    bad = dataclasses.replace(wire[0], wlen_offsets=wire[0].wlen_offsets.copy())
-    bad.wlen_offsets[3] += 1
+    bad = dataclasses.replace(wire[0], wside_offsets=wire[0].wside_offsets.copy())
+    bad.wside_offsets[3] += 1
     with pytest.raises(H.HcnvError) as ei:
         ctx.bin_contigs([bad], bin_width=W, max_block_len=synth.READ_LEN)
     assert ei.value.status == L.HCNV_E_RANGE

@@ -174,43 +174,46 @@ def test_compact_block_stream_round_trip():
 
 
 def test_wire_block_stream_round_trip():
-    """hcnv_wire_from_cblocks (host, no GPU): the ~1.1-byte wire form names exactly the compact stream's blocks -- 7-bit deltas, the
-    default length without a length byte, gaps above 127 bridged by fillers or by closing the group, side-stream offsets per group."""
+    """hcnv_wire_from_cblocks (host, no GPU): the ~0.85-byte wire form is the compact stream record for record -- a nibble per delta
+    (15 = a byte of the side stream), a bit per record for the default length, side-stream offsets per group."""
     rng = np.random.default_rng(5)
     n = 20000
     gaps = rng.integers(0, 12, n)
-    gaps[rng.random(n) < 0.01] = rng.integers(128, 256, int((gaps[rng.random(n) < 0.01]).shape[0]) or 1)[0]
-    gaps[rng.random(n) < 0.003] = 60000                                    # N gaps
-    gaps[rng.random(n) < 0.003] = 700                                      # a few fillers are shorter than closing the group
+    gaps[rng.random(n) < 0.05] = 14
+    gaps[rng.random(n) < 0.05] = 15
+    gaps[rng.random(n) < 0.02] = 255
+    gaps[rng.random(n) < 0.003] = 60000                                    # N gaps (fillers of the compact stream)
     start = np.cumsum(gaps)
     ln = np.where(rng.random(n) < 0.9, 150, rng.integers(1, 256, n))
     b = H.pack_blocks(start, ln, np.zeros(n, np.int64))
     cb, an = H.compact_blocks(b)
-    w, lens, wan, off, dl = H.wire_blocks(cb, an)
-    assert dl == 150 and w.dtype == np.uint8 and w.ctypes.data % 16 == 0 and len(w) % L.HCNV_CGROUP == 0
-    assert len(wan) == len(w) // L.HCNV_CGROUP and len(off) == len(wan) + 1 and off[0] == 0 and off[-1] == len(lens)
-    own = (w & 128) == 0
-    np.testing.assert_array_equal(np.add.reduceat(own.astype(np.int64), np.arange(0, len(w), L.HCNV_CGROUP)), np.diff(off))
-    e = H.expand_cblocks(H.expand_wire(w, lens, wan, off, dl), wan)
+    w, side, off, dl = H.wire_blocks(cb)
+    groups = len(cb) // L.HCNV_CGROUP
+    assert dl == 150 and w.dtype == np.uint8 and w.ctypes.data % 16 == 0 and len(w) == groups * L.HCNV_WGROUP_BYTES
+    assert len(off) == groups + 1 and off[0] == 0 and off[-1] == len(side) and (np.diff(off) >= 0).all()
+    x = H.expand_wire(w, side, dl)
+    want = cb.copy()
+    want[::L.HCNV_CGROUP] &= np.uint16(0xFF00)                              # (a group's first delta is ignored; the wire form carries 0)
+    np.testing.assert_array_equal(x, want)
+    e = H.expand_cblocks(x, an)
     assert (e["start0"] == b["start0"]).all() and ((e["len_mapq"] & 0xFFFFFF) == ln).all()
-    assert (np.diff(wan) >= 0).all()
-    # size: one byte per record, one more for the records that are not 150 long, fillers only where a gap needs them
-    n_fill = int(own.sum()) - int((ln != 150).sum())
-    g = np.diff(start)
-    assert len(w) == n + n_fill and n_fill <= int(np.minimum((g[g > 127] - 1) // 127, L.HCNV_CGROUP - 1).sum()) + L.HCNV_CGROUP   # a 60 kb gap: < one group of fillers, not 470
-    assert len(lens) == int((ln != 150).sum()) + n_fill
+    # the side stream holds exactly the deltas above 14 and the lengths that are not the default, group by group
+    d = (want & 0xFF).astype(np.int64); l_ = (want >> 8).astype(np.int64)
+    per_rec = (d >= 15).astype(np.int64) + (l_ != 150).astype(np.int64)
+    np.testing.assert_array_equal(np.add.reduceat(per_rec, np.arange(0, len(cb), L.HCNV_CGROUP)), np.diff(off))
+    assert len(w) + len(side) + 4 * len(off) < 0.85 * cb.nbytes           # (many long deltas and fillers here; 0.43 of the 2-byte stream on 30X data)
     # a chosen default length, a stream without any default-length record, the empty stream
-    w2, lens2, wan2, off2, dl2 = H.wire_blocks(cb, an, default_len=7)
-    e2 = H.expand_cblocks(H.expand_wire(w2, lens2, wan2, off2, dl2), wan2)
-    assert dl2 == 7 and (e2["start0"] == b["start0"]).all() and ((e2["len_mapq"] & 0xFFFFFF) == ln).all()
-    w0, lens0, wan0, off0, _ = H.wire_blocks(*H.compact_blocks(H.pack_blocks([], [])))
-    assert len(w0) == 0 and len(lens0) == 0 and len(wan0) == 0 and off0.tolist() == [0]
+    w2, side2, off2, dl2 = H.wire_blocks(cb, default_len=7)
+    assert dl2 == 7
+    np.testing.assert_array_equal(H.expand_wire(w2, side2, dl2), want)
+    w0, side0, off0, _ = H.wire_blocks(H.compact_blocks(H.pack_blocks([], []))[0])
+    assert len(w0) == 0 and len(side0) == 0 and off0.tolist() == [0]
     # blocks above 255 bases arrive as pieces of the compact stream and stay pieces
     b3 = H.pack_blocks([10, 20, 300, 301, 4000], [1000, 5, 700, 30, 4095], [60] * 5)
     cb3, an3 = H.compact_blocks(b3)
-    w3, lens3, wan3, off3, dl3 = H.wire_blocks(cb3, an3)
+    w3, side3, off3, dl3 = H.wire_blocks(cb3)
     d_want, _ = O.depth_from_blocks(b3, 9000)
-    d_got, _ = O.depth_from_blocks(H.expand_cblocks(H.expand_wire(w3, lens3, wan3, off3, dl3), wan3), 9000)
+    d_got, _ = O.depth_from_blocks(H.expand_cblocks(H.expand_wire(w3, side3, dl3), an3), 9000)
     assert (d_want == d_got).all()
 
 

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--coverage", type=float, default=30.0)
     ap.add_argument("--reps", type=int, default=8)
     ap.add_argument("--stream", choices=["wire", "cblocks"], default="wire")
+    ap.add_argument("--output", choices=["implicit", "dense"], default="implicit")
     ap.add_argument("--grid", default="groups=6,8,10;workers=3,4;taper=1,0.8")
     a = ap.parse_args()
     import torch
@@ -50,12 +51,12 @@ def main():
         if a.stream == "wire":
             wc = H.wire_contig(hc)
             if wc.wblocks is not None:
-                hc = dataclasses.replace(wc, anchors=pin(wc.anchors), wblocks=pin(wc.wblocks), wlens=pin(wc.wlens), wlen_offsets=pin(wc.wlen_offsets))
+                hc = dataclasses.replace(wc, wblocks=pin(wc.wblocks), wside=pin(wc.wside), wside_offsets=pin(wc.wside_offsets))
         host.append(hc)
     del api, made
     torch.cuda.empty_cache()
     names = ["c%d" % i for i in range(len(host))]
-    gout = GenomeOutput([c.length for c in host], 100)
+    gout = GenomeOutput([c.length for c in host], 100, want_cn=a.output == "dense", implicit_bins=a.output == "implicit")
     grid = {}
     for part in a.grid.split(";"):
         k, v = part.split("=")
