@@ -389,7 +389,7 @@ def run_b200(args):
         from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
         whole_i = [i for i, r in enumerate(regions) if r.n_parts == 1]
         part_i = [i for i, r in enumerate(regions) if r.n_parts > 1]
-        nbytes = lambda c: sum(int(x.nbytes) for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors, c.wblocks, c.wside, c.wside_offsets) if x is not None)
+        nbytes = lambda c: sum(int(x.nbytes) for x in (c.long_blocks, c.snp_pos1, c.snp_zyg, c.cblocks, c.anchors, c.cobs, c.cobs_anchors, c.wblocks, c.wside, c.wside_offsets, c.wobs) if x is not None)
         if args.e2e_stream == "wire":                        # what hcnv_pack_contig_wire hands a host: 4 bits per record + 1 for its length flag + a byte per delta above 14 and per length that is not READ_LEN
             import dataclasses
             def pin_np(a_):
@@ -399,7 +399,8 @@ def run_b200(args):
             for i in whole_i:
                 wc = H.wire_contig(host_contigs[i])
                 if wc.wblocks is not None:
-                    host_contigs[i] = dataclasses.replace(wc, wblocks=pin_np(wc.wblocks), wside=pin_np(wc.wside), wside_offsets=pin_np(wc.wside_offsets))
+                    host_contigs[i] = dataclasses.replace(wc, wblocks=pin_np(wc.wblocks), wside=pin_np(wc.wside), wside_offsets=pin_np(wc.wside_offsets),
+                                                          wobs=None if wc.wobs is None else pin_np(wc.wobs), cobs_anchors=wc.cobs_anchors if wc.wobs is None else pin_np(wc.cobs_anchors))
         pipe = gout = prep = None
         if whole_i:
             pipe = GenomePipeline(local, workers=args.e2e_workers, groups=max(1, min(args.e2e_groups, len(whole_i))))

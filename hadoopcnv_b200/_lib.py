@@ -20,6 +20,7 @@ HCNV_SEG_THROUGHPUT = 2
 HCNV_SEG_LATENCY = 4
 HCNV_CGROUP = 128
 HCNV_WGROUP_BYTES = 80
+HCNV_WOGROUP = 64
 KERNELS = dict(tile_index=0, tally=1, bin_tiles=2, text_roundtrip=3, mean_coverage=4, scale_depth=5, sd=6, viterbi=7, traceback=8,
                vit_p0=9, vit_p0c=10, vit_p1=11, vit_p2=12, vit_p3=13, vit_p1b=14, vit_p2b=15, snp_mse=16, vit_many=17)
 
@@ -45,7 +46,7 @@ class ContigInput(C.Structure):
                 ("cobs", C.c_void_p), ("cobs_anchors", C.c_void_p), ("n_cobs", C.c_int64),
                 ("region_first_bin", C.c_int32), ("region_n_bins", C.c_int32), ("snp_index_base", C.c_int64),
                 ("wblocks", C.c_void_p), ("wside", C.c_void_p), ("wside_offsets", C.c_void_p), ("n_wside", C.c_int64),
-                ("wire_default_len", C.c_int32), ("reserved", C.c_int32)]
+                ("wire_default_len", C.c_int32), ("reserved", C.c_int32), ("wobs", C.c_void_p)]
 
 
 class ResultsDownload(C.Structure):
@@ -112,7 +113,7 @@ EXPORTS = [
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
     "hcnv_genome_create", "hcnv_genome_run", "hcnv_genome_begin", "hcnv_genome_push", "hcnv_genome_end", "hcnv_genome_kernel_launches", "hcnv_genome_last_error", "hcnv_genome_destroy",
     "hcnv_seg_plan_create", "hcnv_seg_plan_stats", "hcnv_seg_plan_p0", "hcnv_seg_plan_p1", "hcnv_seg_plan_chain", "hcnv_seg_plan_finish", "hcnv_seg_plan_destroy",
-    "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_wire_from_cblocks", "hcnv_pack_contig_wire", "hcnv_bam_pack", "hcnv_bam_pack_mt", "hcnv_pack_stats", "hcnv_bam_write_synthetic", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
+    "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_wire_from_cblocks", "hcnv_wire_obs", "hcnv_pack_contig_wire", "hcnv_bam_pack", "hcnv_bam_pack_mt", "hcnv_pack_stats", "hcnv_bam_write_synthetic", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
 ]
 
 _lib = None
@@ -156,6 +157,8 @@ def lib():
     L.hcnv_expand_start_end.argtypes = [C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hcnv_compact_obs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
     L.hcnv_compact_obs.restype = C.c_int64
+    L.hcnv_wire_obs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+    L.hcnv_wire_obs.restype = C.c_int64
     L.hcnv_ctx_stream.argtypes = [C.c_void_p]
     L.hcnv_ctx_stream.restype = C.c_void_p
     L.hcnv_ctx_kernel_launches.argtypes = [C.c_void_p]

@@ -133,7 +133,35 @@ def wire_contig(c: "Contig") -> "Contig":
         return c
     cb = c.cblocks.numpy() if _is_torch(c.cblocks) else c.cblocks
     w, side, off, dl = wire_blocks(cb)
-    return dataclasses.replace(c, cblocks=None, wblocks=w, wside=side, wside_offsets=off, wire_default_len=dl)
+    c = dataclasses.replace(c, cblocks=None, wblocks=w, wside=side, wside_offsets=off, wire_default_len=dl)
+    if c.cobs is not None and len(c.cobs):                     # and the observations at 1 byte each
+        to_np = lambda x: x.numpy() if _is_torch(x) else x
+        wo, wan = wire_obs(expand_cobs(to_np(c.cobs).view(np.uint16), to_np(c.cobs_anchors)))
+        c = dataclasses.replace(c, cobs=None, wobs=wo, cobs_anchors=wan)
+    return c
+
+
+def wire_obs(obs):
+    """hcnv_wire_obs: observations (snp index << 4 | base4) -> (wobs uint8, anchors int32): 1 byte each (4-bit index relative to
+    the anchor of the group of HCNV_WOGROUP entries, 15 = filler)."""
+    lib = L.lib()
+    obs = np.ascontiguousarray(obs, dtype=np.uint32)
+    n = lib.hcnv_wire_obs(obs.ctypes.data, len(obs), None, None, 0)
+    if n < 0:
+        raise L.HcnvError(int(n), "hcnv_wire_obs: %s" % lib.hcnv_strerror(int(n)).decode())
+    wo = np.empty(n, np.uint8)
+    anchors = np.empty(max(1, n // L.HCNV_WOGROUP), np.int32)
+    m = lib.hcnv_wire_obs(obs.ctypes.data, len(obs), wo.ctypes.data, anchors.ctypes.data, n)
+    assert m == n
+    return wo, anchors[: n // L.HCNV_WOGROUP]
+
+
+def expand_wobs(wobs, anchors) -> np.ndarray:
+    """Inverse of wire_obs (numpy; test helper): the observations in stream order, fillers dropped."""
+    wo = np.asarray(wobs, dtype=np.uint8).astype(np.uint32)
+    idx = np.repeat(np.asarray(anchors, dtype=np.int64), L.HCNV_WOGROUP)[: len(wo)] + (wo >> 4)
+    keep = (wo >> 4) != 15
+    return ((idx[keep] << 4) | (wo[keep] & 15)).astype(np.uint32)
 
 
 def expand_cobs(cobs, cobs_anchors) -> np.ndarray:
@@ -191,6 +219,7 @@ class Contig:
     wside: object = None           # ... its side stream (uint8: the deltas above 14 and the lengths that are not the default), ...
     wside_offsets: object = None   # ... the side stream's offset per group (int32, groups + 1) ...
     wire_default_len: int = 0      # ... and the length of the records that carry none
+    wobs: object = None            # alternative to cobs: hcnv_wobs stream (uint8) with cobs_anchors
 
 
 @dataclass
@@ -336,8 +365,10 @@ class Context:
                 arr[i].wblocks, arr[i].wside, arr[i].wside_offsets = _ptr(c.wblocks), _ptr(c.wside), _ptr(c.wside_offsets)
                 arr[i].n_cblocks, arr[i].n_wside, arr[i].wire_default_len = _len(c.wblocks) // L.HCNV_WGROUP_BYTES * L.HCNV_CGROUP, _len(c.wside), int(c.wire_default_len)
             arr[i].cobs, arr[i].cobs_anchors, arr[i].n_cobs = _ptr(c.cobs), _ptr(c.cobs_anchors), _len(c.cobs)
+            if c.wobs is not None:
+                arr[i].wobs, arr[i].n_cobs = _ptr(c.wobs), _len(c.wobs)
             arr[i].region_first_bin, arr[i].region_n_bins, arr[i].snp_index_base = int(c.region_first_bin), int(c.region_n_bins), int(c.snp_index_base)
-            for x in (c.blocks, c.cblocks, c.wblocks, c.long_blocks, c.snp_pos1, c.obs, c.cobs):
+            for x in (c.blocks, c.cblocks, c.wblocks, c.long_blocks, c.snp_pos1, c.obs, c.cobs, c.wobs):
                 if x is not None and _is_torch(x):
                     on_device = True
         return PreparedContigs(list(contigs), arr, on_device)

@@ -30,6 +30,7 @@ struct ContigDev {
     const uint32_t*        obs;       // observations at 4 bytes, or ...
     const hcnv_cobs*       cobs;      // ... at 2 bytes (n_obs entries, a multiple of HCNV_OGROUP) with their anchors
     const int32_t*         cobs_anchors;
+    const hcnv_wobs*       wobs;      // ... or at 1 byte (same count and anchors)
     long long n_blocks, n_long, n_snp, n_obs;
     long long snp_base;     // row offset of this contig in the tally table
     long long obs_base32;   // start of this contig's observations in the launch-wide index space (each contig rounded up to 256)
@@ -227,7 +228,17 @@ __global__ void __launch_bounds__(256) k_tally(BinK p, long long n_obs_total) {
         const hcnv_cobs* __restrict__ cobs = c.cobs;
         uint32_t* tally = p.tally + 16 * (size_t)c.snp_base;
         uint32_t ov[8];
-        if (cobs) {
+        const hcnv_wobs* __restrict__ wobs = c.wobs;
+        if (wobs) {
+            // 1-byte observations: groups of HCNV_WOGROUP = 64 entries (four anchors per span) with a 4-bit index
+            const int32_t* __restrict__ anc = c.cobs_anchors + (g0 - c.obs_base32) / HCNV_WOGROUP;
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t anchor = (uint32_t)__ldg(&anc[u >> 1]);
+                const uint32_t v = (i0 + 32 * u < n_obs) ? (uint32_t)__ldg(&wobs[i0 + 32 * u]) : HCNV_WOBS_FILLER;
+                ov[u] = (v >> 4) == 15u ? 0xFFFFFFFFu : (((anchor + (v >> 4)) << 4) | (v & 15u));
+            }
+        } else if (cobs) {
             // 2-byte observations: a span is one group (HCNV_OGROUP = 256 entries) with one anchor; a filler names no site
             const uint32_t anchor = (uint32_t)__ldg(&c.cobs_anchors[(g0 - c.obs_base32) / HCNV_OGROUP]);
             #pragma unroll
@@ -242,7 +253,7 @@ __global__ void __launch_bounds__(256) k_tally(BinK p, long long n_obs_total) {
         #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const uint32_t o = ov[u];
-            const bool valid = cobs ? (o != 0xFFFFFFFFu) : (i0 + 32 * u < n_obs);
+            const bool valid = (cobs || wobs) ? (o != 0xFFFFFFFFu) : (i0 + 32 * u < n_obs);
             const unsigned act = __ballot_sync(0xffffffffu, valid);
             if (!valid) continue;
             const unsigned same = __match_any_sync(act, o);         // lanes that saw the same (site, base)
@@ -431,8 +442,9 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         const hcnv_contig_input& ci = contigs[c];
         if (ci.n_cobs < 0 || (ci.n_cobs > 0 && ci.n_obs > 0)) return hcnv_fail(ctx, HCNV_E_INVALID, "give obs or cobs, not both");
         if (ci.n_cobs % HCNV_OGROUP) return hcnv_fail(ctx, HCNV_E_INVALID, "n_cobs must be a multiple of HCNV_OGROUP (pad with fillers)");
-        if (ci.n_cobs > 0 && (!ci.cobs || !ci.cobs_anchors)) return hcnv_fail(ctx, HCNV_E_INVALID, "null cobs / cobs_anchors");
-        if (ci.n_cobs > 0 && (reinterpret_cast<uintptr_t>(ci.cobs) & 1)) return hcnv_fail(ctx, HCNV_E_INVALID, "cobs must be 2-byte aligned");
+        if (ci.n_cobs > 0 && ((!ci.cobs && !ci.wobs) || !ci.cobs_anchors)) return hcnv_fail(ctx, HCNV_E_INVALID, "null cobs / cobs_anchors");
+        if (ci.n_cobs > 0 && ci.cobs && ci.wobs) return hcnv_fail(ctx, HCNV_E_INVALID, "give cobs or wobs, not both");
+        if (ci.n_cobs > 0 && ci.cobs && (reinterpret_cast<uintptr_t>(ci.cobs) & 1)) return hcnv_fail(ctx, HCNV_E_INVALID, "cobs must be 2-byte aligned");
     }
 
     // tile geometry: one warp = one tile of 32 bins; a warp's shared-memory slice = tile records + two record chunks +
@@ -463,7 +475,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         const void* ptrs[11] = { ci.n_blocks ? (const void*)ci.blocks : nullptr, ci.n_long ? (const void*)ci.long_blocks : nullptr,
                                  ci.n_snp ? (const void*)ci.snp_pos1 : nullptr, ci.n_snp ? (const void*)ci.snp_zyg : nullptr,
                                  ci.n_obs ? (const void*)ci.obs : nullptr, ci.n_cblocks ? (wire ? (const void*)ci.wblocks : (const void*)ci.cblocks) : nullptr,
-                                 ci.n_cblocks ? (const void*)ci.anchors : nullptr, ci.n_cobs ? (const void*)ci.cobs : nullptr,
+                                 ci.n_cblocks ? (const void*)ci.anchors : nullptr, ci.n_cobs ? (ci.wobs ? (const void*)ci.wobs : (const void*)ci.cobs) : nullptr,
                                  ci.n_cobs ? (const void*)ci.cobs_anchors : nullptr, wire ? (const void*)ci.wside_offsets : nullptr,
                                  wire && ci.n_wside ? (const void*)ci.wside : nullptr };
         const long long cnts[11] = { ci.n_blocks, ci.n_long, ci.n_snp, ci.n_snp, ci.n_obs, ci.n_cblocks, ci.n_cblocks, ci.n_cobs, ci.n_cobs, wire ? 1 : 0, wire ? ci.n_wside : 0 };
@@ -496,7 +508,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
         HCNV_CUDA(ctx, ctx->buf[B_IN_LONG].reserve(sizeof(hcnv_long_block) * (size_t)tot_long));
         HCNV_CUDA(ctx, ctx->buf[B_IN_SNPPOS].reserve(4 * (size_t)tot_snp));
         HCNV_CUDA(ctx, ctx->buf[B_IN_SNPZYG].reserve((size_t)tot_snp + 16 * n_contigs));
-        HCNV_CUDA(ctx, ctx->buf[B_IN_OBS].reserve(4 * (size_t)tot_obs + 2 * (size_t)tot_cobs + 4 * (size_t)(tot_cobs / HCNV_OGROUP) + 128));
+        HCNV_CUDA(ctx, ctx->buf[B_IN_OBS].reserve(4 * (size_t)tot_obs + 2 * (size_t)tot_cobs + 4 * (size_t)(tot_cobs / HCNV_WOGROUP) + 128));
     }
     long long ob = 0, ocb = 0, ol = 0, os = 0, oo = 0, oco = 0, obs32_total = 0;
     // (host inputs) B_IN_OBS holds the 4-byte observations, then the 2-byte ones, then their anchors
@@ -513,7 +525,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
                 d.cblocks = ctx->buf[B_IN_BLOCKS].as<hcnv_cblock>() + ocb;
                 wire_jobs.push_back(WireJob{ ci.wblocks, ci.wside, ci.wside_offsets, const_cast<hcnv_cblock*>(d.cblocks), ci.n_cblocks / HCNV_CGROUP, ci.n_wside, ci.wire_default_len });
             }
-            d.cobs = ci.n_cobs ? ci.cobs : nullptr; d.cobs_anchors = ci.cobs_anchors;
+            d.cobs = ci.n_cobs ? ci.cobs : nullptr; d.cobs_anchors = ci.cobs_anchors; d.wobs = ci.n_cobs ? ci.wobs : nullptr;
         } else {
             d.cblocks = ctx->buf[B_IN_BLOCKS].as<hcnv_cblock>() + ocb;            // (a call uses one form, so the buffer is shared)
             d.anchors = ctx->buf[B_IN_ANCHORS].as<int32_t>() + ocb / HCNV_CGROUP;
@@ -542,10 +554,13 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
             if ((rc = stage_in(ctx, in_kind, ci.snp_pos1, ci.n_snp, const_cast<int32_t*>(d.snp_pos)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.snp_zyg, ci.n_snp, const_cast<int8_t*>(d.snp_zyg)))) return rc;
             if ((rc = stage_in(ctx, in_kind, ci.obs, ci.n_obs, const_cast<uint32_t*>(d.obs)))) return rc;
-            d.cobs = ci.n_cobs ? reinterpret_cast<const hcnv_cobs*>(obs_stage + cobs_at) + oco : nullptr;
-            d.cobs_anchors = reinterpret_cast<const int32_t*>(obs_stage + canc_at) + oco / HCNV_OGROUP;
+            d.cobs = ci.n_cobs && !ci.wobs ? reinterpret_cast<const hcnv_cobs*>(obs_stage + cobs_at) + oco : nullptr;
+            d.wobs = ci.n_cobs && ci.wobs ? reinterpret_cast<const hcnv_wobs*>(obs_stage + cobs_at + 2 * (size_t)oco) : nullptr;       // (a 1-byte stream takes the first half of its 2-byte slot)
+            d.cobs_anchors = reinterpret_cast<const int32_t*>(obs_stage + canc_at) + oco / HCNV_WOGROUP;      // (room for the finer groups of a 1-byte stream)
+            if (ci.wobs) { if ((rc = stage_in(ctx, in_kind, ci.wobs, ci.n_cobs, const_cast<hcnv_wobs*>(d.wobs)))) return rc; }
+            else
             if ((rc = stage_in(ctx, in_kind, ci.cobs, ci.n_cobs, const_cast<hcnv_cobs*>(reinterpret_cast<const hcnv_cobs*>(obs_stage + cobs_at) + oco)))) return rc;
-            if ((rc = stage_in(ctx, in_kind, ci.cobs_anchors, ci.n_cobs / HCNV_OGROUP, const_cast<int32_t*>(d.cobs_anchors)))) return rc;
+            if ((rc = stage_in(ctx, in_kind, ci.cobs_anchors, ci.n_cobs / (ci.wobs ? HCNV_WOGROUP : HCNV_OGROUP), const_cast<int32_t*>(d.cobs_anchors)))) return rc;
         }
         d.n_blocks = ci.n_blocks; d.n_cblocks = ci.n_cblocks; d.n_long = ci.n_long; d.n_snp = ci.n_snp; d.n_obs = ci.n_cobs ? ci.n_cobs : ci.n_obs;
         d.obs_base32 = obs32_total; obs32_total += (d.n_obs + 255) / 256 * 256;

@@ -81,8 +81,8 @@ void contig_fields(const hcnv_contig_input& c, Field f[ST_N]) {
     f[ST_WLENS]   = { c.wside, wire ? (size_t)std::max<int64_t>(c.n_wside, 0) : 0 };
     f[ST_WOFFS]   = { c.wside_offsets, wire ? 4 * (size_t)(c.n_cblocks / HCNV_CGROUP + 1) : 0 };
     f[ST_ANCHORS] = { c.anchors, 4 * (size_t)(c.n_cblocks / HCNV_CGROUP) };
-    f[ST_COBS]    = { c.cobs, sizeof(hcnv_cobs) * (size_t)c.n_cobs };
-    f[ST_COBSANC] = { c.cobs_anchors, 4 * (size_t)(c.n_cobs / HCNV_OGROUP) };
+    f[ST_COBS]    = { c.wobs ? (const void*)c.wobs : (const void*)c.cobs, (c.wobs ? sizeof(hcnv_wobs) : sizeof(hcnv_cobs)) * (size_t)c.n_cobs };
+    f[ST_COBSANC] = { c.cobs_anchors, 4 * (size_t)(c.n_cobs / (c.wobs ? HCNV_WOGROUP : HCNV_OGROUP)) };
 }
 
 int genome_fail(hcnv_genome* g, int code, const std::string& msg) {
@@ -366,7 +366,8 @@ static void genome_uploader(hcnv_genome* g) {
             di.blocks = (const hcnv_block*)d[ST_BLOCKS]; di.long_blocks = (const hcnv_long_block*)d[ST_LONG];
             di.snp_pos1 = (const int32_t*)d[ST_SNPPOS]; di.snp_zyg = (const int8_t*)d[ST_SNPZYG]; di.obs = (const uint32_t*)d[ST_OBS];
             di.cblocks = (const hcnv_cblock*)d[ST_CBLOCKS]; di.anchors = (const int32_t*)d[ST_ANCHORS];
-            di.cobs = (const hcnv_cobs*)d[ST_COBS]; di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
+            di.cobs = job.host[k].wobs ? nullptr : (const hcnv_cobs*)d[ST_COBS]; di.wobs = job.host[k].wobs ? (const hcnv_wobs*)d[ST_COBS] : nullptr;
+            di.cobs_anchors = (const int32_t*)d[ST_COBSANC];
             di.wblocks = (const hcnv_wblock*)d[ST_WBLOCKS]; di.wside = (const uint8_t*)d[ST_WLENS]; di.wside_offsets = (const int32_t*)d[ST_WOFFS];
             task.contigs.push_back(c);
         }

@@ -39,6 +39,7 @@ struct hcnv_pack {
         std::vector<hcnv_block> blocks; std::vector<hcnv_long_block> longs; std::vector<uint32_t> obs;
         std::vector<hcnv_cblock> cstore; std::vector<int32_t> anchors; hcnv_cblock* cblocks = nullptr; int64_t n_cblocks = -1;   // built on demand
         std::vector<uint8_t> wstore, wside; std::vector<int32_t> wside_offsets; hcnv_wblock* wblocks = nullptr; int64_t n_wside = -1; int32_t wdefault = 0;   // built on demand
+        std::vector<hcnv_wobs> wobs; std::vector<int32_t> wobs_anchors; int64_t n_wobs = -1;                                        // built on demand
         std::vector<hcnv_cobs> cobs; std::vector<int32_t> cobs_anchors; int64_t n_cobs = -1;                                        // built on demand
         const std::vector<int32_t>* snp_pos = nullptr; const std::vector<int8_t>* snp_zyg = nullptr;
     };
@@ -701,31 +702,55 @@ int64_t hcnv_wire_from_cblocks(const hcnv_cblock* cb, int64_t n, int32_t default
     return ns;
 }
 
-int64_t hcnv_compact_obs(const uint32_t* obs, int64_t n, hcnv_cobs* out, int32_t* anchors, int64_t capacity) {
+}  // extern "C"
+
+namespace {
+// observations -> groups of HCNV_OGROUP entries whose indices lie within `span` of the group's smallest (its anchor)
+template <class T, int GROUP>
+int64_t group_obs(const uint32_t* obs, int64_t n, T* out, int32_t* anchors, int64_t capacity, uint32_t span, T filler) {
     if (n < 0 || (n > 0 && !obs) || (out && !anchors)) return HCNV_E_INVALID;
     int64_t k = 0;                                          // entries written (or counted) so far
     int64_t i = 0;
     while (i < n) {
-        // one group: as many of the next observations as keep max - min of the indices within 4094, at most HCNV_OGROUP
+        // one group: as many of the next observations as keep max - min of the indices within the span, at most GROUP
         uint32_t lo = obs[i] >> 4, hi = lo;
         if (lo >= (1u << 28) - 1) return HCNV_E_RANGE;
         int64_t j = i + 1;
-        for (; j < n && j - i < HCNV_OGROUP; ++j) {
+        for (; j < n && j - i < GROUP; ++j) {
             const uint32_t x = obs[j] >> 4;
             const uint32_t nlo = x < lo ? x : lo, nhi = x > hi ? x : hi;
-            if (nhi - nlo > 4094u) break;
+            if (nhi - nlo > span) break;
             lo = nlo; hi = nhi;
         }
         if (out) {
-            if (k + HCNV_OGROUP > capacity) return HCNV_E_CAPACITY;
-            anchors[k / HCNV_OGROUP] = (int32_t)lo;
-            for (int64_t t = i; t < j; ++t) out[k + (t - i)] = (hcnv_cobs)((((obs[t] >> 4) - lo) << 4) | (obs[t] & 15u));
-            for (int64_t t = j - i; t < HCNV_OGROUP; ++t) out[k + t] = (hcnv_cobs)HCNV_COBS_FILLER;
+            if (k + GROUP > capacity) return HCNV_E_CAPACITY;
+            anchors[k / GROUP] = (int32_t)lo;
+            for (int64_t t = i; t < j; ++t) out[k + (t - i)] = (T)((((obs[t] >> 4) - lo) << 4) | (obs[t] & 15u));
+            for (int64_t t = j - i; t < GROUP; ++t) out[k + t] = filler;
         }
-        k += HCNV_OGROUP;
+        k += GROUP;
         i = j;
     }
+    while (k % HCNV_OGROUP) {                               // (groups smaller than a tally span: whole groups of fillers up to one)
+        if (out) {
+            if (k + GROUP > capacity) return HCNV_E_CAPACITY;
+            anchors[k / GROUP] = 0;
+            for (int t = 0; t < GROUP; ++t) out[k + t] = filler;
+        }
+        k += GROUP;
+    }
     return k;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t hcnv_compact_obs(const uint32_t* obs, int64_t n, hcnv_cobs* out, int32_t* anchors, int64_t capacity) {
+    return group_obs<hcnv_cobs, HCNV_OGROUP>(obs, n, out, anchors, capacity, 4094u, (hcnv_cobs)HCNV_COBS_FILLER);
+}
+
+int64_t hcnv_wire_obs(const uint32_t* obs, int64_t n, hcnv_wobs* out, int32_t* anchors, int64_t capacity) {
+    return group_obs<hcnv_wobs, HCNV_WOGROUP>(obs, n, out, anchors, capacity, 14u, (hcnv_wobs)HCNV_WOBS_FILLER);
 }
 
 int32_t hcnv_pack_n_contigs(const hcnv_pack* p) { return p ? (int32_t)p->contigs.size() : 0; }
@@ -799,6 +824,17 @@ int hcnv_pack_contig_wire(hcnv_pack* p, int32_t i, const char** name, hcnv_conti
         in->wblocks = c.wblocks; in->wside = c.wside.data(); in->wside_offsets = c.wside_offsets.data();
         in->n_wside = c.n_wside; in->wire_default_len = c.wdefault;
     }
+    if (c.n_wobs < 0) {                                     // and the 1-byte observations
+        const int64_t n = hcnv_wire_obs(c.obs.data(), (int64_t)c.obs.size(), nullptr, nullptr, 0);
+        if (n < 0) return (int)n;
+        c.wobs.resize((size_t)n);
+        c.wobs_anchors.resize((size_t)(n / HCNV_WOGROUP) + 1);
+        const int64_t m = hcnv_wire_obs(c.obs.data(), (int64_t)c.obs.size(), c.wobs.data(), c.wobs_anchors.data(), n);
+        if (m != n) return HCNV_E_INTERNAL;
+        c.n_wobs = n;
+    }
+    in->cobs = nullptr;
+    in->wobs = c.n_wobs ? c.wobs.data() : nullptr; in->cobs_anchors = c.n_wobs ? c.wobs_anchors.data() : nullptr; in->n_cobs = c.n_wobs;
     return HCNV_OK;
 }
 

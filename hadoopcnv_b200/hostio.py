@@ -94,7 +94,7 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
                                   arr(ci.snp_pos1, ci.n_snp, np.int32), arr(ci.snp_zyg, ci.n_snp, np.int8),
                                   arr(ci.obs, ci.n_obs, np.uint32), arr16(ci.cblocks, ci.n_cblocks if ci.cblocks else 0),
                                   arr(ci.anchors, ci.n_cblocks // L.HCNV_CGROUP, np.int32),
-                                  arr(ci.cobs, ci.n_cobs, np.uint16), arr(ci.cobs_anchors, ci.n_cobs // L.HCNV_OGROUP, np.int32)))
+                                  arr(ci.cobs, ci.n_cobs if ci.cobs else 0, np.uint16), arr(ci.cobs_anchors, ci.n_cobs // (L.HCNV_WOGROUP if ci.wobs else L.HCNV_OGROUP), np.int32)))
             if wire and ci.n_cblocks:
                 nw = ci.n_cblocks // L.HCNV_CGROUP * L.HCNV_WGROUP_BYTES
                 raw = np.empty(nw + 16, np.uint8)
@@ -103,6 +103,8 @@ def pack_bam(bam_path: str, snps: Optional[SnpTable] = None, compact: bool = Fal
                 k = contigs[-1]
                 k.wblocks, k.wside = raw[sh:sh + nw], (arr(ci.wside, ci.n_wside, np.uint8) if ci.n_wside else np.zeros(0, np.uint8))
                 k.wside_offsets, k.wire_default_len = arr(ci.wside_offsets, ci.n_cblocks // L.HCNV_CGROUP + 1, np.int32), int(ci.wire_default_len)
+            if wire and ci.n_cobs:
+                contigs[-1].wobs = arr(ci.wobs, ci.n_cobs, np.uint8)
         return names, contigs, maxlens, int(lib.hcnv_pack_n_records(h))
     finally:
         lib.hcnv_pack_free(h)

@@ -133,6 +133,14 @@ typedef uint8_t hcnv_wblock;
 typedef uint16_t hcnv_cobs;
 #define HCNV_OGROUP 256
 #define HCNV_COBS_FILLER 0xFFF0u
+/* ... and at 1 byte each, the observations' wire form (64 consecutive observations of a 30X sample name two or three sites):
+ *   bits 0-3  BAM 4-bit base code      bits 4-7  snp index - cobs_anchors[k / HCNV_WOGROUP]   (0..14; 15 = filler)
+ * Same rules with groups of HCNV_WOGROUP entries and 14 in place of 4094; the stream is padded to a multiple of HCNV_OGROUP
+ * entries (whole groups of fillers with anchor 0), n_cobs counts them all, cobs_anchors holds n_cobs / HCNV_WOGROUP anchors.
+ * hcnv_wire_obs builds it. */
+typedef uint8_t hcnv_wobs;
+#define HCNV_WOGROUP 64
+#define HCNV_WOBS_FILLER 0xF0u
 
 /* A block of any length (e.g. the baseline BAM's artificial whole-interval reads, example/preprocessBAM.py).
  * Not required to be sorted.  Splitting a block is results-neutral: only per-position counts matter. */
@@ -175,6 +183,8 @@ typedef struct {
     /* alternative to `cblocks` (cblocks null, n_cblocks and anchors as for cblocks): the wire form, see hcnv_wblock */
     const hcnv_wblock*     wblocks;     const uint8_t* wside; const int32_t* wside_offsets; int64_t n_wside;
     int32_t                wire_default_len; int32_t reserved;
+    /* alternative to `cobs` (cobs null; cobs_anchors and n_cobs as for cobs): the observations at 1 byte each, see hcnv_wobs */
+    const hcnv_wobs*       wobs;
 } hcnv_contig_input;
 
 /* Host helper (no GPU): sorted hcnv_block records -> compact stream; blocks whose MAPQ fails mapping_quality_threshold
@@ -197,6 +207,8 @@ int64_t hcnv_wire_from_cblocks(const hcnv_cblock* cblocks, int64_t n_cblocks, in
  * (fillers and padding included, a multiple of HCNV_OGROUP) or a negative status; with out == NULL only counts.  anchors
  * needs result / HCNV_OGROUP entries.  HCNV_E_RANGE for an index of 2^28 or more, HCNV_E_CAPACITY if `capacity` is too small. */
 int64_t hcnv_compact_obs(const uint32_t* obs, int64_t n, hcnv_cobs* out, int32_t* anchors, int64_t capacity);
+/* the same for the 1-byte form (hcnv_wobs) */
+int64_t hcnv_wire_obs(const uint32_t* obs, int64_t n, hcnv_wobs* out, int32_t* anchors, int64_t capacity);
 
 /* Outputs: one record per non-empty bin, all contigs concatenated in input order, bins ascending within a
  * contig (the (chr,bin) secondary sort, PennCnvSeq.java:382-414).  Field meaning = the columns BinReducer
@@ -250,7 +262,8 @@ int     hcnv_pack_contig(const hcnv_pack* p, int32_t i, const char** name, hcnv_
 /* the same with both streams in their 2-byte forms (built on the first request): in->cblocks / anchors / n_cblocks and
  * in->cobs / cobs_anchors / n_cobs; in->blocks and in->obs are null */
 int     hcnv_pack_contig_compact(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
-/* the same with the block stream in its wire form (in->wblocks / wside / wside_offsets; anchors as before; in->cblocks null) */
+/* the same with the block stream and the observations in their wire forms (in->wblocks / wside / wside_offsets, anchors as before,
+ * in->cblocks null; in->wobs / cobs_anchors / n_cobs, in->cobs null) */
 int     hcnv_pack_contig_wire(hcnv_pack* p, int32_t i, const char** name, hcnv_contig_input* in, int32_t* max_block_len);
 void    hcnv_pack_free(hcnv_pack* p);
 

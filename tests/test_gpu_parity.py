@@ -461,7 +461,8 @@ def test_binning_wire_stream_matches_compact_stream(ctx, W, cov):
     g = synth.make_genome(coverage=cov, scale=0.0015, device="cpu", contigs=["chr10", "chr11", "chr21", "chrY"], seed=99 + W)
     base = synth.to_api_contigs(g, host=True, compact=True, compact_observations=True)
     wire = [H.wire_contig(c) for c in base]
-    assert all(c.cblocks is None and c.wblocks is not None and c.wire_default_len == synth.READ_LEN for c in wire)
+    assert all(c.cblocks is None and c.wblocks is not None and c.wire_default_len == synth.READ_LEN and c.cobs is None and c.wobs is not None for c in wire)
+    assert sum(c.wobs.nbytes for c in wire) < 0.7 * sum(np.asarray(c.cobs).nbytes for c in base)           # 1 byte per observation, a few more fillers
     sent = sum(c.wblocks.nbytes + c.wside.nbytes + c.wside_offsets.nbytes for c in wire)
     assert sent < 0.5 * sum(np.asarray(c.cblocks).nbytes for c in base)                  # ~0.85 bytes per record instead of 2
     want = ctx.bin_contigs(base, bin_width=W, max_block_len=synth.READ_LEN)
@@ -469,7 +470,7 @@ def test_binning_wire_stream_matches_compact_stream(ctx, W, cov):
     def dev(c):
         t = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x).view(np.int8 if x.dtype.itemsize == 1 else np.int16 if x.dtype.itemsize == 2 else np.int32)).cuda()
         return dataclasses.replace(c, long_blocks=t(c.long_blocks), snp_pos1=t(c.snp_pos1), snp_zyg=t(c.snp_zyg), cobs=t(c.cobs), cobs_anchors=t(c.cobs_anchors),
-                                   anchors=t(c.anchors), wblocks=t(c.wblocks), wside=t(c.wside), wside_offsets=t(c.wside_offsets))
+                                   anchors=t(c.anchors), wblocks=t(c.wblocks), wside=t(c.wside), wside_offsets=t(c.wside_offsets), wobs=t(c.wobs))
     for host in (True, False):
         res = ctx.bin_contigs(wire if host else [dev(c) for c in wire], bin_width=W, max_block_len=synth.READ_LEN)
         for i, c in enumerate(g):

@@ -173,6 +173,26 @@ def test_compact_block_stream_round_trip():
     assert len(cb0) == 0 and len(an0) == 0
 
 
+def test_wire_observation_stream_round_trip():
+    """hcnv_wire_obs (host, no GPU): 1 byte per observation, a 4-bit index relative to the group's anchor, groups closed early
+    where 256 consecutive observations span more than 15 sites."""
+    rng = np.random.default_rng(8)
+    idx = np.sort(rng.integers(0, 3000, 60000)) + rng.integers(-2, 3, 60000)         # block order: locally unsorted
+    idx = np.clip(idx, 0, None).astype(np.uint32)
+    obs = (idx << 4) | rng.integers(0, 16, len(idx)).astype(np.uint32)
+    wo, an = H.wire_obs(obs)
+    assert wo.dtype == np.uint8 and len(wo) % L.HCNV_OGROUP == 0 and len(an) == len(wo) // L.HCNV_WOGROUP
+    np.testing.assert_array_equal(H.expand_wobs(wo, an), obs)
+    assert len(wo) < 1.25 * len(obs)                                                 # few fillers at ~20 observations per site
+    sparse = (np.arange(0, 4000, 40, dtype=np.uint32) << 4) | 1                      # every observation far from the last: one per group
+    wo2, an2 = H.wire_obs(sparse)
+    assert len(an2) >= len(sparse) and (H.expand_wobs(wo2, an2) == sparse).all()
+    assert len(H.wire_obs(np.zeros(0, np.uint32))[0]) == 0
+    with pytest.raises(H.HcnvError) as e:
+        H.wire_obs(np.array([((1 << 28) - 1) << 4], np.uint32))
+    assert e.value.status == L.HCNV_E_RANGE
+
+
 def test_wire_block_stream_round_trip():
     """hcnv_wire_from_cblocks (host, no GPU): the ~0.85-byte wire form is the compact stream record for record -- a nibble per delta
     (15 = a byte of the side stream), a bit per record for the default length, side-stream offsets per group."""

@@ -51,7 +51,8 @@ def main():
         if a.stream == "wire":
             wc = H.wire_contig(hc)
             if wc.wblocks is not None:
-                hc = dataclasses.replace(wc, wblocks=pin(wc.wblocks), wside=pin(wc.wside), wside_offsets=pin(wc.wside_offsets))
+                hc = dataclasses.replace(wc, wblocks=pin(wc.wblocks), wside=pin(wc.wside), wside_offsets=pin(wc.wside_offsets),
+                                         wobs=None if wc.wobs is None else pin(wc.wobs), cobs_anchors=wc.cobs_anchors if wc.wobs is None else pin(wc.cobs_anchors))
         host.append(hc)
     del api, made
     torch.cuda.empty_cache()
