@@ -226,28 +226,39 @@ __device__ __forceinline__ bool vit_apply(const int* sT, float L, int e, int lan
     return ok;
 }
 
-// exact float replay of markers [a, b) by lanes 0..5 (regular inputs)
+// exact float replay of markers [a, b) by lanes 0..5 (regular inputs).  The chain L -> L' is all that has to be sequential: the
+// emission terms of 32 markers at a time are computed by the 32 lanes side by side (lane j: marker m0 + j, all six states) into
+// shared memory, so that the sequential loop is one 8-byte shared load (independent of L: issued ahead) and the step itself.
 __device__ __forceinline__ float vit_replay(const SegDev& P, const VitConsts& k, float L, long long a, long long b,
-                                            int lane, int c, float c3, const float* c4, int& bad1e10) {
+                                            int lane, int c, float c3, const float* c4, int& bad1e10, float2* sAB) {
     for (long long m0 = a; m0 < b; m0 += 32) {
         const long long m = m0 + lane;
-        const float sdv = (m < b) ? __ldg(&P.scaled[m]) : 0.f;
-        float mv[6];
-        #pragma unroll
-        for (int i = 0; i < 6; ++i) { long long idx = m0 * 6 + i * 32 + lane; mv[i] = (idx < b * 6) ? __ldg(&P.mse[idx]) : 0.f; }
+        if (m < b) {
+            const float sdv = __ldg(&P.scaled[m]);
+            float mv[6];
+            if ((reinterpret_cast<unsigned long long>(P.mse) & 7ull) == 0) {          // (a marker's six values are 24 bytes: 8-byte aligned with the array)
+                const float2* mp = reinterpret_cast<const float2*>(P.mse + m * 6);
+                const float2 m01 = __ldg(mp), m23 = __ldg(mp + 1), m45 = __ldg(mp + 2);
+                mv[0] = m01.x; mv[1] = m01.y; mv[2] = m23.x; mv[3] = m23.y; mv[4] = m45.x; mv[5] = m45.y;
+            } else {
+                #pragma unroll
+                for (int i = 0; i < 6; ++i) mv[i] = __ldg(&P.mse[m * 6 + i]);
+            }
+            #pragma unroll
+            for (int cc = 0; cc < 6; ++cc) {
+                const float dev = __fsub_rn(sdv, c_mu[cc]);
+                sAB[lane * 6 + cc] = make_float2(__fmul_rn(k.oma, __fmul_rn(dev, dev)), __fmul_rn(k.alpha, mv[cc]));
+            }
+        }
+        __syncwarp();
         const int cnt = (int)min((long long)32, b - m0);
         #pragma unroll 4
         for (int jj = 0; jj < cnt; ++jj) {
-            const float sdj = __shfl_sync(0xffffffffu, sdv, jj);
-            const int el = jj * 6 + c;
-            float msel = 0.f;
-            #pragma unroll
-            for (int i = 0; i < 6; ++i) { float x = __shfl_sync(0xffffffffu, mv[i], el & 31); if ((el >> 5) == i) msel = x; }
-            const float dev = __fsub_rn(sdj, c_mu[c]);
-            const float A = __fmul_rn(k.oma, __fmul_rn(dev, dev)), B = __fmul_rn(k.alpha, msel);
-            L = lanes_step(L, A, B, c3, c4);
+            const float2 ab = sAB[jj * 6 + c];
+            L = lanes_step(L, ab.x, ab.y, c3, c4);
             if (L == 1e10f) bad1e10 = 1;           // (1e10 is a float: 9765625 * 2^10)
         }
+        __syncwarp();
     }
     return L;
 }
@@ -259,6 +270,7 @@ __global__ void __launch_bounds__(32) k_vit_p2c(SegDev* probs, const int* __rest
                                                 float* __restrict__ Lstart, int* __restrict__ replayed, int round) {
     __shared__ __align__(16) int sC[2][VB * 72];          // staged chunk matrices
     __shared__ __align__(16) int sS[VCH * 72];            // staged segment matrices of one chunk (fallback walk)
+    __shared__ __align__(8) float2 sAB[32 * 6];           // emission terms of 32 markers (float replay)
     SegDev& P = probs[blockIdx.x];
     if (P.skip || !P.par || P.irregular) return;
     if (P.chain_round != round) return;                   // a later part of a cut chromosome waits for its predecessor's end vector
@@ -316,7 +328,7 @@ __global__ void __launch_bounds__(32) k_vit_p2c(SegDev* probs, const int* __rest
                 if (!oks) {
                     ++n_replayed;
                     const long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
-                    Lnew = vit_replay(P, k, L, a, b, lane, c, c3, c4, bad1e10);
+                    Lnew = vit_replay(P, k, L, a, b, lane, c, c3, c4, bad1e10, sAB);
                 }
                 L = Lnew;
                 if (lane < 6) ls[(size_t)(s + 1) * 6 + lane] = L;

@@ -347,112 +347,15 @@ __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __rest
 // lanes 0..5 hold L[c]; regular inputs (finite, non-negative): the min over ascending p with strict '<' from
 // Float.MAX_VALUE equals the plain minimum when it is below Float.MAX_VALUE, else "no candidate" -> 0 (Java default)
 __device__ __forceinline__ float lanes_step(float L, float A, float B, float c3, const float* c4) {
-    float best = 3.402823466e+38f;
+    float x[6];
     #pragma unroll
     for (int p = 0; p < 6; ++p) {
         float Lp = __shfl_sync(0xffffffffu, L, p);
-        best = fminf(best, __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(Lp, A), B), c3), c4[p]));
+        x[p] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(Lp, A), B), c3), c4[p]);
     }
+    // (the minimum as a tree: this step is the chain's critical path, and min is exact in any order)
+    const float best = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(x[4], x[5]));
     return best < 3.402823466e+38f ? best : 0.f;
-}
-
-// ---------------------------------------------------------------------------------------------- P2
-__global__ void __launch_bounds__(32) k_vit_p2(SegDev* probs, const int* __restrict__ seg_base, int VSEG, float alpha,
-                                               const int* __restrict__ epred, const int* __restrict__ Ti,
-                                               const int* __restrict__ flags, const int* __restrict__ force,
-                                               float* __restrict__ Lstart, int* __restrict__ replayed) {
-    SegDev& P = probs[blockIdx.x];
-    if (P.skip || !P.par || P.irregular) return;
-    const int lane = threadIdx.x, c = lane < 6 ? lane : 0;
-    const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
-    const float c3 = k.c3[c];
-    float c4[6];
-    #pragma unroll
-    for (int p = 0; p < 6; ++p) { int d = vpt(c) - vpt(p); c4[p] = k.dq[d < 0 ? -d : d]; }
-    const int nseg = P.n_seg, base = seg_base[blockIdx.x];
-    const long long M = P.M;
-    float* ls = Lstart + ((size_t)base + blockIdx.x) * 6;     // n_seg + 1 vectors per chromosome
-    float L = loss0(P, k, c);
-    if (lane < 6) ls[lane] = L;
-    int bad1e10 = 0, n_replayed = 0;
-    __shared__ __align__(16) int sT[2][VB * 72];
-    if (nseg > 0) stage_mats(sT[0], Ti + (size_t)base * 72, min(VB, nseg), lane, 72);
-    int buf = 0;
-    // per-batch control words: lane l holds (usable, binade) of segment s0 + l
-    int f_nx = 0, e_nx = -1;
-    if (lane < nseg) { f_nx = __ldg(&flags[base + lane]) && !__ldg(&force[base + lane]); e_nx = __ldg(&epred[base + lane]); }
-    for (int s0 = 0; s0 < nseg; s0 += VB, buf ^= 1) {
-      const bool more = s0 + VB < nseg;
-      const int f_cur = f_nx, e_cur = e_nx;
-      if (more) {
-          stage_mats(sT[buf ^ 1], Ti + (size_t)(base + s0 + VB) * 72, min(VB, nseg - s0 - VB), lane, 72);
-          int sn = s0 + VB + lane;
-          f_nx = 0; e_nx = -1;
-          if (sn < nseg) { f_nx = __ldg(&flags[base + sn]) && !__ldg(&force[base + sn]); e_nx = __ldg(&epred[base + sn]); }
-          __pipeline_wait_prior(1);
-      } else __pipeline_wait_prior(0);
-      __syncwarp();
-      const int cnt = min(VB, nseg - s0);
-      for (int ss = 0; ss < cnt; ++ss) {
-        const int s = s0 + ss;
-        int ok = __shfl_sync(0xffffffffu, f_cur, ss), e = __shfl_sync(0xffffffffu, e_cur, ss);
-        if (lane == 0 && !ok) atomicAdd(&g_vdbg[e < 0 ? 4 : 5], 1);
-        { int ok0 = ok; ok = ok && __all_sync(0xffffffffu, lane >= 6 || (L > 0.f && fexp(L) == e)); if (lane == 0 && ok0 && !ok) atomicAdd(&g_vdbg[6], 1); }
-        float Lnew = L;
-        if (ok) {
-            const float scale = __int_as_float((127 + 23 - e) << 23), inv = __int_as_float((127 - 23 + e) << 23);
-            int Li = __float2int_rn(__fmul_rn(L, scale));            // exact: L is a multiple of u
-            int best = 0x7fffffff;
-            #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                int Lsrc = __shfl_sync(0xffffffffu, Li, i);                  // row (i, parity of the start value)
-                best = min(best, Lsrc + sT[buf][ss * 72 + ((Lsrc & 1) * 6 + i) * 6 + c]);
-            }
-            ok = __all_sync(0xffffffffu, lane >= 6 || best < (1 << 24));
-            if (lane == 0 && !ok) atomicAdd(&g_vdbg[7], 1);
-            Lnew = __fmul_rn((float)best, inv);
-        }
-        if (!ok) {                                                    // exact replay of this segment
-            ++n_replayed;
-            const long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
-            Lnew = L;
-            for (long long m0 = a; m0 < b; m0 += 32) {
-                long long m = m0 + lane;
-                float sdv = (m < b) ? __ldg(&P.scaled[m]) : 0.f;
-                float mv[6];
-                #pragma unroll
-                for (int i = 0; i < 6; ++i) { long long idx = m0 * 6 + i * 32 + lane; mv[i] = (idx < b * 6) ? __ldg(&P.mse[idx]) : 0.f; }
-                int cnt = (int)min((long long)32, b - m0);
-                for (int jj = 0; jj < cnt; ++jj) {
-                    float sdj = __shfl_sync(0xffffffffu, sdv, jj);
-                    int el = jj * 6 + c;                              // element of the 192-float chunk
-                    float msel = 0.f;
-                    #pragma unroll
-                    for (int i = 0; i < 6; ++i) { float x = __shfl_sync(0xffffffffu, mv[i], el & 31); if ((el >> 5) == i) msel = x; }
-                    float dev = __fsub_rn(sdj, c_mu[c]);
-                    float A = __fmul_rn(k.oma, __fmul_rn(dev, dev)), B = __fmul_rn(k.alpha, msel);
-                    Lnew = lanes_step(Lnew, A, B, c3, c4);
-                    if ((double)Lnew == 1e10) bad1e10 = 1;
-                }
-            }
-        }
-        L = Lnew;
-        if (lane < 6) ls[(size_t)(s + 1) * 6 + lane] = L;
-      }
-      __syncwarp();
-    }
-    int min_index = 1; float mn = 3.402823466e+38f, row[6];
-    #pragma unroll
-    for (int s6 = 0; s6 < 6; ++s6) { row[s6] = __shfl_sync(0xffffffffu, L, s6); if (row[s6] < mn) { mn = row[s6]; min_index = s6; } }
-    bad1e10 = __any_sync(0xffffffffu, bad1e10 && lane < 6);
-    if (lane == 0) {
-        for (int s6 = 0; s6 < 6; ++s6) P.last_row[s6] = row[s6];
-        P.sstar = min_index; P.final_loss = mn;
-        P.status = HCNV_OK;
-        if (bad1e10 || mn == 3.402823466e+38f) { P.status = HCNV_E_NO_MINIMUM; P.skip = 2; }
-        P.first_bad = 0x7fffffff;
-        replayed[blockIdx.x] = n_replayed;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------- P3
