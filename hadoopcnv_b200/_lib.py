@@ -111,7 +111,7 @@ EXPORTS = [
     "hcnv_write_bins_text", "hcnv_write_results_text",
     "hcnv_read_bins_text", "hcnv_bins_text_n_chromosomes", "hcnv_bins_text_get", "hcnv_bins_text_free",
     "hcnv_vcf_load", "hcnv_snp_table_n_contigs", "hcnv_snp_table_get", "hcnv_snp_table_free",
-    "hcnv_genome_create", "hcnv_genome_run", "hcnv_genome_begin", "hcnv_genome_push", "hcnv_genome_end", "hcnv_genome_kernel_launches", "hcnv_genome_last_error", "hcnv_genome_destroy",
+    "hcnv_sample_run_device", "hcnv_genome_create", "hcnv_genome_run", "hcnv_genome_begin", "hcnv_genome_push", "hcnv_genome_end", "hcnv_genome_kernel_launches", "hcnv_genome_last_error", "hcnv_genome_destroy",
     "hcnv_seg_plan_create", "hcnv_seg_plan_stats", "hcnv_seg_plan_p0", "hcnv_seg_plan_p1", "hcnv_seg_plan_chain", "hcnv_seg_plan_finish", "hcnv_seg_plan_destroy",
     "hcnv_compact_blocks", "hcnv_compact_obs", "hcnv_wire_from_cblocks", "hcnv_wire_obs", "hcnv_pack_contig_wire", "hcnv_bam_pack", "hcnv_bam_pack_mt", "hcnv_pack_stats", "hcnv_bam_write_synthetic", "hcnv_pack_n_contigs", "hcnv_pack_n_records", "hcnv_pack_contig", "hcnv_pack_contig_compact", "hcnv_pack_free",
 ]
@@ -176,6 +176,8 @@ def lib():
     L.hcnv_bins_to_hmm_input.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hcnv_segment_batch.argtypes = [C.c_void_p, C.c_float, C.c_int32, C.POINTER(SegmentProblem), C.c_int32]
     L.hcnv_genome_create.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_void_p)]
+    L.hcnv_sample_run_device.argtypes = [C.c_void_p, C.POINTER(BinParams), C.c_float, C.c_float, C.c_float, C.c_int32, C.POINTER(ContigInput), C.POINTER(Bins),
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SegmentProblem)]
     L.hcnv_genome_run.argtypes = [C.c_void_p, C.POINTER(BinParams), C.c_float, C.c_float, C.c_float, C.c_int32, C.POINTER(ContigInput), C.c_int32, C.POINTER(GenomeOutput)]
     L.hcnv_genome_begin.argtypes = [C.c_void_p, C.POINTER(BinParams), C.c_float, C.c_float, C.c_float, C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.POINTER(GenomeOutput)]
     L.hcnv_genome_push.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(ContigInput)]

@@ -28,6 +28,7 @@ int move_small(hcnv_ctx* ctx, void* dst, const void* src, size_t bytes) {
     const unsigned grid = (unsigned)std::min<size_t>(32, (bytes + 4095) / 4096);
     k_move_small<<<grid, 256, 0, ctx->stream>>>(dst, src, bytes);
     HCNV_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
     return HCNV_OK;
 }
 }  // namespace

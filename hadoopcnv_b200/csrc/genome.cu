@@ -417,6 +417,38 @@ int hcnv_genome_end(hcnv_genome* g) {
     return g->worst.load();
 }
 
+// The same chain for records that are already on the device, on the caller's context: what a task does between its upload and
+// its download, as one call (no interpreter between the three stages: on a 3 ms step the gaps are a tenth of it).
+int hcnv_sample_run_device(hcnv_ctx* ctx, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
+                           int32_t n_contigs, const hcnv_contig_input* contigs, hcnv_bins* bins,
+                           float* mse32, float* total32, float* scaled, int32_t* state, int32_t* cn, hcnv_segment_problem* probs) {
+    if (!ctx) return HCNV_E_INVALID;
+    if (n_contigs <= 0 || !contigs || !bins || !mse32 || !total32 || !scaled || !state || !cn || !probs || !bins->contig_offset)
+        return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return hcnv_fail(ctx, HCNV_E_CUDA, "cudaSetDevice failed");
+    int rc = hcnv_bin_contigs_impl(ctx, params, n_contigs, contigs, bins);
+    if (rc) return rc;
+    const int64_t* off = bins->contig_offset;
+    const int64_t nrows = off[n_contigs];
+    for (int c = 0; c < n_contigs; ++c) {
+        hcnv_segment_problem q{};
+        const int64_t a = off[c];
+        q.n_markers = off[c + 1] - a; q.median = bins->median + a; q.mse = mse32 + 6 * a; q.total = total32 + a; q.n = bins->n + a;
+        q.lambda1 = lambda1; q.lambda2 = lambda2; q.lambda1_used = lambda1; q.lambda2_used = lambda2;
+        q.scaled = scaled + a; q.state = state + a; q.cn = cn + a;
+        probs[c] = q;
+    }
+    if (nrows == 0) return HCNV_OK;
+    rc = hcnv_bins_to_hmm_input_impl(ctx, nrows, bins->mse, bins->total, mse32, total32);
+    if (rc) return rc;
+    std::vector<hcnv_segment_problem> live;
+    std::vector<int> which;
+    for (int c = 0; c < n_contigs; ++c) if (probs[c].n_markers > 0) { live.push_back(probs[c]); which.push_back(c); }
+    rc = hcnv_segment_batch_impl(ctx, alpha, (int32_t)live.size(), live.data(), 0);
+    for (size_t k = 0; k < live.size(); ++k) probs[which[k]] = live[k];
+    return rc;
+}
+
 int hcnv_genome_run(hcnv_genome* g, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
                     int32_t n_contigs, const hcnv_contig_input* contigs, int32_t n_groups, hcnv_genome_output* out) {
     if (!g || n_contigs <= 0 || !contigs || !out) return HCNV_E_INVALID;

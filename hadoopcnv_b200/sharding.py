@@ -443,6 +443,70 @@ class ShardedGenome:
             int(table[r, s, _F["part"]]) == part_index, "the ranks disagree about the partition"
         return r, s
 
+    def _merge(self, out: "ShardResult", nrows: int, table=None):
+        """The merge: int8 calls of every rank to rank 0, in genome order (ranks hold consecutive pieces of the genome)."""
+        torch, comm = self.torch, self.comm
+        if comm.world == 1:
+            out.merged_state, out.merged_rows = self.state[:nrows].to(torch.int8), np.array([nrows])
+        elif self.gather_cap is not None:
+            # fixed-size blocks (the most rows a rank can hold) with the row count in front: no exchange of counts
+            if getattr(self, "_gbuf", None) is None:
+                self._gbuf = torch.zeros(self.gather_cap + 8, dtype=torch.int8, device=self.dev)
+                self._ghead = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self._ghead[0] = nrows
+            self._gbuf[:8].view(torch.int64).copy_(self._ghead, non_blocking=True)
+            self._gbuf[8:8 + nrows] = self.state[:nrows]
+            blocks = comm.gather_rows(self._gbuf, [self.gather_cap + 8] * comm.world)
+            if blocks is not None:
+                counts = torch.stack([b_[:8].view(torch.int64)[0] for b_ in blocks]).cpu().numpy().astype(np.int64)     # (one read for all the counts)
+                out.merged_state = torch.cat([b_[8:8 + int(n_)].to(self.dev) for b_, n_ in zip(blocks, counts)])
+                out.merged_rows = counts
+        else:
+            counts = table[:, 0, _F["nrows"]].astype(np.int64)
+            blocks = comm.gather_rows(self.state[:nrows].to(torch.int8), [int(x) for x in counts])
+            if blocks is not None:
+                out.merged_state = torch.cat([b_.to(self.dev) for b_ in blocks])
+                out.merged_rows = counts
+
+    def _run_whole(self, gather_calls: bool) -> "ShardResult":
+        """A rank that holds whole chromosomes only, in a plan that cuts none: hcnv_sample_run_device -- binning, text round trip and
+        segmentation back to back inside the library -- then the merge.  No exchange with anybody before the merge."""
+        import ctypes as C
+        from .api import _ptr, BinsResult
+        torch, ctx = self.torch, self.ctx
+        n = len(self.contigs)
+        if getattr(self, "_fast", None) is None:
+            cap = max(self.cap, 1)
+            b = L.Bins()
+            o = self.out
+            b.capacity = cap
+            b.bin, b.start, b.end, b.median, b.mse, b.total, b.n = _ptr(o.bin), _ptr(o.start), _ptr(o.end), _ptr(o.median), _ptr(o.mse), _ptr(o.total), _ptr(o.n)
+            off = np.zeros(n + 1, np.int64)
+            b.contig_offset = off.ctypes.data
+            p = L.BinParams()
+            L.lib().hcnv_bin_params_default(C.byref(p))
+            p.bin_width, p.max_block_len, p.flags = self.W, self.maxlen, self.bin_flags
+            m32 = torch.empty((cap, 6), dtype=torch.float32, device=self.dev)
+            t32 = torch.empty(cap, dtype=torch.float32, device=self.dev)
+            self._fast = (b, off, p, m32, t32, (L.SegmentProblem * n)())
+        b, off, p, m32, t32, probs = self._fast
+        st = L.lib().hcnv_sample_run_device(ctx._h, C.byref(p), float(self.l1), float(self.l2), float(self.alpha), n, self.prepared.arr, C.byref(b),
+                                           _ptr(m32), _ptr(t32), _ptr(self.scaled), _ptr(self.state), _ptr(self.cn), probs)
+        if st == L.HCNV_E_NO_MINIMUM:
+            raise L.HcnvError(st, "Hmm: failed to find minimum (the reference exits here, Hmm.java:205-215,229-232)")
+        ctx._check(st)
+        self.kernel_ms.update(ctx.kernel_ms())
+        nrows = int(off[-1])
+        o = self.out
+        res = BinsResult(o.bin[:nrows], o.start[:nrows], o.end[:nrows], o.median[:nrows], o.mse[:nrows], o.total[:nrows], o.n[:nrows], off.copy())
+        scal = [dict(mean_coverage=np.float32(q.mean_coverage), final_loss=np.float32(q.final_loss), lambda1=np.float32(q.lambda1_used),
+                     lambda2=np.float32(q.lambda2_used), status=int(q.status)) for q in probs]
+        out = ShardResult(self.regions, off.copy(), res, m32[:nrows], self.scaled[:nrows], self.state[:nrows], self.cn[:nrows], scal)
+        if gather_calls:
+            self._merge(out, nrows)
+        self.trace = None
+        return out
+
     def run(self, gather_calls: bool = True) -> ShardResult:
         torch, ctx, comm, W = self.torch, self.ctx, self.comm, self.W
         me = comm.rank
@@ -456,6 +520,8 @@ class ShardedGenome:
                 torch.cuda.synchronize()
                 trace.append((name, round(1e3 * (time.perf_counter() - t_start), 3)))
         regions = self.regions
+        if trace is None and self.static_no_cut and self.contigs and all(r.n_parts == 1 for r in regions):
+            return self._run_whole(gather_calls)
         # ---- binning of my regions + the text round trip of the bins
         if self.contigs:
             res = ctx.bin_contigs(self.prepared, bin_width=W, max_block_len=self.maxlen, out=self.out, capacity=max(self.cap, 1), flags=self.bin_flags)
@@ -672,27 +738,8 @@ class ShardedGenome:
         nrows = int(off[-1])
         mark("patch")
         out = ShardResult(regions, off, res, m32, self.scaled[:nrows], self.state[:nrows], self.cn[:nrows], scal)
-        # ---- the merge: int8 calls of every rank to rank 0, in genome order (ranks hold consecutive pieces of the genome)
         if gather_calls:
-            if comm.world == 1:
-                out.merged_state, out.merged_rows = self.state[:nrows].to(torch.int8), np.array([nrows])
-            elif self.gather_cap is not None:
-                # fixed-size blocks (the most rows a rank can hold) with the row count in front: no exchange of counts
-                if getattr(self, "_gbuf", None) is None:
-                    self._gbuf = torch.zeros(self.gather_cap + 8, dtype=torch.int8, device=self.dev)
-                self._gbuf[:8].view(torch.int64)[0] = nrows
-                self._gbuf[8:8 + nrows] = self.state[:nrows]
-                blocks = comm.gather_rows(self._gbuf, [self.gather_cap + 8] * comm.world)
-                if blocks is not None:
-                    counts = np.array([int(b_[:8].view(torch.int64)[0]) for b_ in blocks], np.int64)
-                    out.merged_state = torch.cat([b_[8:8 + int(n_)].to(self.dev) for b_, n_ in zip(blocks, counts)])
-                    out.merged_rows = counts
-            else:
-                counts = table[:, 0, _F["nrows"]].astype(np.int64)
-                blocks = comm.gather_rows(self.state[:nrows].to(torch.int8), [int(x) for x in counts])
-                if blocks is not None:
-                    out.merged_state = torch.cat([b_.to(self.dev) for b_ in blocks])
-                    out.merged_rows = counts
+            self._merge(out, nrows, table)
         mark("gather")
         self.trace = trace
         return out

@@ -393,6 +393,15 @@ int hcnv_expand_start_end(int64_t n, int32_t bin_width, int64_t n_runs, const in
  * start == NULL selects the implicit form of start / end (see hcnv_results_download; it halves the download): run_rows / run_bins /
  * se_rows (capacity entries each) and se_vals (2 * capacity) are laid out like mse_rows -- contig c's lists begin at row_offset[c],
  * n_runs[c] and n_se_rows[c] entries long, rows counted inside the contig. */
+/* The chain for records that are ALREADY on the device (a resident step; region sharding's whole chromosomes): hcnv_bin_contigs ->
+ * hcnv_bins_to_hmm_input -> hcnv_segment_batch back to back on the context's stream.  contigs and every array of `bins` are device
+ * pointers (bins->contig_offset: host, n_contigs + 1); mse32 (6 per row), total32, scaled, state, cn: device arrays of
+ * bins->capacity rows.  probs (host, n_contigs entries) is filled in: n_markers, pointers to the contig's rows, and the outputs of
+ * hcnv_segment_batch (status, mean_coverage, final_loss, lambda1_used, lambda2_used).  Returns what hcnv_segment_batch returns. */
+int hcnv_sample_run_device(hcnv_ctx* ctx, const hcnv_bin_params* params, float lambda1, float lambda2, float alpha,
+                           int32_t n_contigs, const hcnv_contig_input* contigs, hcnv_bins* bins,
+                           float* mse32, float* total32, float* scaled, int32_t* state, int32_t* cn, hcnv_segment_problem* probs);
+
 typedef struct hcnv_genome hcnv_genome;
 typedef struct {
     int64_t  capacity;                                   /* rows of the arrays below: >= sum of (length / bin_width + 1) */
