@@ -413,6 +413,43 @@ class Context:
         self._check(self._lib.hcnv_download_results(self._h, C.byref(d)))
         return int(d.n_mse_rows)
 
+    # ------------------------------------------------------------------ B1 -> text -> B2 in one call (device-resident records)
+    def sample_run_device(self, contigs, bin_width: int = 100, max_block_len: int = 0, lambda1: float = 0.01, lambda2: float = 1.6,
+                          alpha: float = 0.5, flags: int = 0):
+        """hcnv_sample_run_device: binning, the text round trip and the segmentation of device-resident contigs back to back inside
+        the library.  Returns (BinsResult, mse32, total32, scaled, state, cn, [per-contig dict of scalars]) -- all device tensors."""
+        import torch
+        prep = contigs if isinstance(contigs, PreparedContigs) else self.prepare_contigs(contigs)
+        if not prep.on_device:
+            raise ValueError("hcnv_sample_run_device takes device-resident contigs (host buffers: GenomePipeline / hcnv_genome_run)")
+        n = len(prep.contigs)
+        cap = max(1, sum(int(c.length) // bin_width + 1 for c in prep.contigs))
+        dev = torch.device("cuda", self.device)
+        out = self.alloc_bins(cap, True, n)
+        b = L.Bins()
+        b.capacity = cap
+        b.bin, b.start, b.end, b.median, b.mse, b.total, b.n = _ptr(out.bin), _ptr(out.start), _ptr(out.end), _ptr(out.median), _ptr(out.mse), _ptr(out.total), _ptr(out.n)
+        off = np.zeros(n + 1, np.int64)
+        b.contig_offset = off.ctypes.data
+        p = L.BinParams()
+        self._lib.hcnv_bin_params_default(C.byref(p))
+        p.bin_width, p.max_block_len, p.flags = bin_width, max_block_len, flags
+        m32 = torch.empty((cap, 6), dtype=torch.float32, device=dev)
+        t32 = torch.empty(cap, dtype=torch.float32, device=dev)
+        scaled = torch.empty(cap, dtype=torch.float32, device=dev)
+        state = torch.empty(cap, dtype=torch.int32, device=dev)
+        cn = torch.empty(cap, dtype=torch.int32, device=dev)
+        probs = (L.SegmentProblem * n)()
+        st = self._lib.hcnv_sample_run_device(self._h, C.byref(p), float(lambda1), float(lambda2), float(alpha), n, prep.arr, C.byref(b),
+                                              _ptr(m32), _ptr(t32), _ptr(scaled), _ptr(state), _ptr(cn), probs)
+        if st != L.HCNV_E_NO_MINIMUM:
+            self._check(st)
+        nb = int(off[-1])
+        res = BinsResult(out.bin[:nb], out.start[:nb], out.end[:nb], out.median[:nb], out.mse[:nb], out.total[:nb], out.n[:nb], off)
+        scal = [dict(n_markers=int(q.n_markers), mean_coverage=np.float32(q.mean_coverage), final_loss=np.float32(q.final_loss),
+                     lambda1=np.float32(q.lambda1_used), lambda2=np.float32(q.lambda2_used), status=int(q.status)) for q in probs]
+        return res, m32[:nb], t32[:nb], scaled[:nb], state[:nb], cn[:nb], scal
+
     # ------------------------------------------------------------------ B2
     def segment_batch(self, problems: List[dict], alpha: float = 0.5, flags: int = 0, raise_on_exit: bool = True) -> List[dict]:
         """hcnv_segment_batch.  Each problem: dict(median, mse, total, n, lambda1, lambda2[, want_sd][, scaled/state/cn

@@ -453,6 +453,46 @@ def test_end_to_end_bins_to_calls(ctx):
         assert f32(got["final_loss"]).view(np.uint32) == f32(want["final_loss"]).view(np.uint32)
 
 
+def test_one_call_for_device_resident_records(ctx):
+    """hcnv_sample_run_device (binning -> text round trip -> segmentation inside the library) returns what the three calls return,
+    for the 2-byte streams and for the wire forms, including a contig without reads."""
+    import torch
+    import dataclasses
+    g = synth.make_genome(coverage=30, scale=0.003, device="cuda", contigs=["chr17", "chr18", "chrY"], seed=5)
+    api_c = synth.to_api_contigs(g, compact=True, compact_observations=True)
+    empty = H.Contig(50_000, None, None, None, None, None)
+    api_c = [api_c[0], empty, api_c[1], api_c[2]]
+    res = ctx.bin_contigs(api_c, max_block_len=150)
+    m32, t32 = ctx.bins_to_hmm_input(res.mse, res.total)
+    off = [int(x) for x in res.contig_offset]
+    assert off[2] == off[1]
+    live = [i for i in range(4) if off[i + 1] > off[i]]
+    want = ctx.segment_batch([dict(median=res.median[off[i]:off[i + 1]], mse=m32[off[i]:off[i + 1]], total=t32[off[i]:off[i + 1]], n=res.n[off[i]:off[i + 1]],
+                                   lambda1=0.01, lambda2=1.6) for i in live])
+    def to_dev_wire(c):
+        if c.cblocks is None:
+            return c
+        h = dataclasses.replace(c, **{k: (None if getattr(c, k) is None else getattr(c, k).cpu().numpy()) for k in ("long_blocks", "snp_pos1", "snp_zyg", "cblocks", "anchors", "cobs", "cobs_anchors")})
+        h = dataclasses.replace(h, cblocks=h.cblocks.view(np.uint16), cobs=None if h.cobs is None else h.cobs.view(np.uint16))
+        w = H.wire_contig(h)
+        t = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x).view(np.int8 if x.dtype.itemsize == 1 else np.int16 if x.dtype.itemsize == 2 else np.int32)).cuda()
+        return dataclasses.replace(w, **{k: t(getattr(w, k)) for k in ("long_blocks", "snp_pos1", "snp_zyg", "anchors", "cobs_anchors", "wblocks", "wside", "wside_offsets", "wobs")})
+    for contigs in (api_c, [to_dev_wire(c) for c in api_c]):
+        r2, m2, t2, scaled, state, cn, scal = ctx.sample_run_device(contigs, max_block_len=150)
+        assert [int(x) for x in r2.contig_offset] == off
+        for k in ("bin", "start", "end", "n", "median", "total", "mse"):
+            assert bool((getattr(r2, k).view(torch.uint8) == getattr(res, k).view(torch.uint8)).all()), k
+        assert bool((m2.view(torch.int32) == m32.view(torch.int32)).all())
+        for w_, i in zip(want, live):
+            a, b = off[i], off[i + 1]
+            assert bool((state[a:b] == w_["state"]).all()) and bool((cn[a:b] == w_["cn"]).all())
+            assert bool((scaled[a:b].view(torch.int32) == w_["scaled"].view(torch.int32)).all())
+            assert scal[i]["n_markers"] == b - a and scal[i]["status"] == w_["status"]
+            assert np.float32(scal[i]["final_loss"]).view(np.uint32) == np.float32(w_["final_loss"]).view(np.uint32)
+            assert np.float32(scal[i]["mean_coverage"]).view(np.uint32) == np.float32(w_["mean_coverage"]).view(np.uint32)
+        assert scal[1]["n_markers"] == 0
+
+
 @pytest.mark.parametrize("W,cov", [(100, 30), (50, 100), (1000, 30)])
 def test_binning_wire_stream_matches_compact_stream(ctx, W, cov):
     """The block stream in its ~0.85-byte wire form (hcnv_wblock), expanded on the device, gives the bins of the 2-byte stream it
