@@ -122,6 +122,14 @@ __global__ void __cluster_dims__(MCC_CS, 1, 1) __launch_bounds__(MCC_T) k_mean_c
         }
         long long sv = s_start + ((s_start & 1) ? ex.a1 : ex.a0);
         int mycross = 0x7fffffff; long long mybefore = 0;
+        // only the CTA in whose window the sum reaches 2^(e+1) looks for the element (the running value is monotone: the CTAs in
+        // front end below the threshold, the ones behind start above it); the search was 27 % of the kernel's instructions when
+        // every CTA ran it
+        const long long v_before = s_start + ((s_start & 1) ? pre.a1 : pre.a0);
+        const PMap mine = s_w[MCC_T / 32 - 1];
+        const long long v_after = v_before + ((v_before & 1) ? mine.a1 : mine.a0);
+        const bool search = v_before < thr && v_after >= thr;
+        if (search)
         for (int k2 = 0; k2 < cnt; ++k2) {
             long long ti = (long long)s_el[tid * (MCC_K + 1) + k2];
             long long q = ti >> sh, r = ti & msk;
