@@ -381,10 +381,14 @@ __global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __rest
     const float c3s = k.c3[sstar];
     int bad = 0;
     float sd, mse[6];
-    load_marker(P.scaled, P.mse, a, sd, mse);
+    // (the problem's pointers in registers: read through P inside the loop they are re-loaded from global memory in front of every
+    // store -- the stores may alias the struct -- and each such load is a scoreboard stall in front of a store address)
+    const float* __restrict__ sdp = P.scaled; const float* __restrict__ msep = P.mse;
+    int32_t* __restrict__ o_state = P.state; int32_t* __restrict__ o_cn = P.cn; int8_t* __restrict__ o_state8 = P.state8;
+    load_marker(sdp, msep, a, sd, mse);
     for (long long m = a; m < b; ++m) {
         float sdn = 0.f, msen[6] = {0, 0, 0, 0, 0, 0};
-        if (m + 1 < b) load_marker(P.scaled, P.mse, m + 1, sdn, msen);
+        if (m + 1 < b) load_marker(sdp, msep, m + 1, sdn, msen);
         float A[6], B[6], Ln[6];
         emis(k, sd, mse, A, B);
         #pragma unroll
@@ -410,9 +414,9 @@ __global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __rest
         }
         if (m == 0) P.prev_call = arg;                               // (a later part's marker 0 decides the call of the previous part's last row)
         else {
-            if (P.state) P.state[m - 1] = arg;                       // best_state[m-1] = traceback[m][s*] (Hmm.java:236)
-            if (P.cn) P.cn[m - 1] = c_cn[arg];
-            if (P.state8) P.state8[m - 1] = (int8_t)arg;
+            if (o_state) o_state[m - 1] = arg;                       // best_state[m-1] = traceback[m][s*] (Hmm.java:236)
+            if (o_cn) o_cn[m - 1] = c_cn[arg];
+            if (o_state8) o_state8[m - 1] = (int8_t)arg;
         }
         #pragma unroll
         for (int c = 0; c < 6; ++c) { L[c] = Ln[c]; mse[c] = msen[c]; }
@@ -427,8 +431,8 @@ __global__ void __launch_bounds__(128) k_vit_p3(SegDev* probs, const int* __rest
     if (bad) P.status = HCNV_E_NO_MINIMUM;                          // Hmm.java:205-215 would exit
     if (b == M && P.part_last) {                                     // last marker (Hmm.java:234, sic)
         int st = c_cn[sstar];
-        if (P.state) P.state[M - 1] = st;
-        if (P.cn) P.cn[M - 1] = c_cn[st];
-        if (P.state8) P.state8[M - 1] = (int8_t)st;
+        if (o_state) o_state[M - 1] = st;
+        if (o_cn) o_cn[M - 1] = c_cn[st];
+        if (o_state8) o_state8[M - 1] = (int8_t)st;
     }
 }
