@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(128) k_vit_p0(SegDev* probs, const int* __rest
         #pragma unroll
         for (int c = 0; c < 6; ++c) bad |= __float_as_uint(mse[c]) >= 0x7f800000u;
     }
+    const float* __restrict__ sdp = P.scaled; const float* __restrict__ msep = P.mse;
     for (long long m = a; m < b; ++m) {
-        load_marker(P.scaled, P.mse, m, sd, mse);
+        load_marker(sdp, msep, m, sd, mse);
         bad |= !(fabsf(sd) <= 2.0f);                  // NaN scaled depth (mean coverage 0/NaN) is not regular
         float A[6], B[6], e[6];
         emis(k, sd, mse, A, B);
@@ -255,9 +256,10 @@ __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __rest
         #pragma unroll
         for (int c = 0; c < 6; ++c) { v0[i][c] = (i == c) ? 0 : V_INF_I; if (FULL) v1[i][c] = v0[i][c]; }
     bool split = false;                             // v1 differs from v0 only after the first tie
+    const float* __restrict__ sdp = P.scaled; const float* __restrict__ msep = P.mse;      // (in registers: see k_vit_p3)
     for (long long m = a; m < b; ++m) {
         float sd, mse[6], A[6], B[6];
-        load_marker(P.scaled, P.mse, m, sd, mse);
+        load_marker(sdp, msep, m, sd, mse);
         emis(k, sd, mse, A, B);
         int qa[6], qb[6]; bool ta[6], tb[6], mt = const_tie;
         #pragma unroll
