@@ -409,6 +409,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     hcnv_bin_params P;
     if (params) P = *params; else hcnv_bin_params_default(&P);
     if (!ctx || n_contigs <= 0 || !contigs || !out) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    ctx->gets.clear();                               // (reads a failed call left pending must never land: their destinations are gone)
     const int W = P.bin_width;
     if (W < 1 || W > 4096) return hcnv_fail(ctx, HCNV_E_INVALID, "bin_width must be in [1, 4096]");
     int maxlen = P.max_block_len > 0 ? P.max_block_len : HCNV_SHORT_MAX;

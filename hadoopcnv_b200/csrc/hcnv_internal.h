@@ -121,6 +121,8 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
 // mapped pinned ring (the device reads / writes host memory directly over PCIe).  hcnv_put_small: the bytes are captured at the
 // call (src may be reused at once).  hcnv_get_small: dst is filled by the next hcnv_sync / hcnv_flush_gets.  Transfers above
 // HCNV_SMALL_MAX bytes, or when the ring is full, fall back to cudaMemcpyAsync on the stream (dst then needs the same sync).
+// Every function that asks for a read waits for it before it returns successfully; a function that FAILS in between leaves its
+// reads pending, so the entry points drop pending reads first (ctx->gets.clear()): they must never land in memory that is gone.
 #define HCNV_SMALL_MAX ((size_t)96 << 10)
 int hcnv_put_small(hcnv_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int hcnv_get_small(hcnv_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);

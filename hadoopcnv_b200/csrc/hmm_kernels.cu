@@ -743,6 +743,7 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
     if (!ctx || n < 0 || (n > 0 && (!mse || !mse_f32))) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
     if ((total == nullptr) != (total_f32 == nullptr)) return hcnv_fail(ctx, HCNV_E_INVALID, "total and total_f32 must both be given or both be null");
     if (n == 0) return HCNV_OK;
+    ctx->gets.clear();                               // (see hcnv_bin_contigs_impl)
     const bool dev = hcnv_ptr_kind(mse) == 2;
     if ((hcnv_ptr_kind(mse_f32) == 2) != dev || (total && ((hcnv_ptr_kind(total) == 2) != dev || (hcnv_ptr_kind(total_f32) == 2) != dev)))
         return hcnv_fail(ctx, HCNV_E_INVALID, "mixed host/device pointers");
@@ -795,6 +796,7 @@ int hcnv_bins_to_hmm_input_impl(hcnv_ctx* ctx, int64_t n, const double* mse, con
 int hcnv_download_results_many_impl(hcnv_ctx* ctx, int32_t count, hcnv_results_download* ds)
 {
     if (!ctx || count < 0 || (count > 0 && !ds)) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
+    ctx->gets.clear();                               // (see hcnv_bin_contigs_impl)
     // device staging per chromosome: [MSE values | MSE rows | run rows | run bins | se rows | se vals | state8 | cn8]
     auto caps = [](const hcnv_results_download& d, size_t& mc, size_t& rc, size_t& sc) {
         mc = (size_t)std::min<long long>(std::max<long long>(d.mse_capacity, 0), d.n);
@@ -937,6 +939,7 @@ int hcnv_seg_plan_create_impl(hcnv_ctx* ctx, float alpha, int32_t n_problems, hc
 {
     if (!ctx || n_problems <= 0 || !parts || !out) return hcnv_fail(ctx, HCNV_E_INVALID, "null argument");
     *out = nullptr;
+    ctx->gets.clear();                               // (see hcnv_bin_contigs_impl)
     long long totM = 0, totMf = 0;
     int kind = -1;
     bool split = false;
