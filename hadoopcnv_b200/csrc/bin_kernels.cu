@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(256) k_expand_wire(WireJob j, int32_t* err)
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, r, d); if (lane >= d) r += t; }
         const int total = __shfl_sync(0xffffffffu, r, 31);
         const long long off = j.offs[g];
-        if (off < 0 || off + total > j.n_side || (long long)j.offs[g + 1] - off != total) { if (lane == 0) atomicOr(&err[ERR_RANGE], 1); continue; }
+        if (off < 0 || off + total > j.n_side || (long long)j.offs[g + 1] - off != total) { if (lane == 0) atomicOr(&err[ERR_RANGE], 2); continue; }
         const uint8_t* sp = j.side + off + (r - own);
         uint32_t rec[4];
 #pragma unroll
@@ -683,6 +683,7 @@ int hcnv_bin_contigs_impl(hcnv_ctx* ctx, const hcnv_bin_params* params, int32_t 
     { int rc_ = hcnv_get_small(ctx, hm, misc, 128 + 8 * (size_t)(n_contigs + 1)); if (rc_) return rc_; }
     { int rc_ = hcnv_sync(ctx); if (rc_) return rc_; }
     const int32_t* herr = (const int32_t*)hm;
+    if (herr[ERR_RANGE] & 2) return hcnv_fail(ctx, HCNV_E_RANGE, "wire form: the side-stream offsets of a group do not match its records");   // (what follows saw an incomplete stream)
     if (herr[ERR_INTERNAL]) return hcnv_fail(ctx, HCNV_E_INTERNAL, herr[ERR_INTERNAL] & 2 ? "a bin with SNP sites has no output row" : "look-back spin limit reached");
     if (herr[ERR_UNSORTED]) return hcnv_fail(ctx, HCNV_E_UNSORTED, "blocks or SNP table not sorted by position");
     if (herr[ERR_RANGE]) return hcnv_fail(ctx, HCNV_E_RANGE, "record outside the contig, longer than max_block_len, or SNP index out of range");

@@ -595,6 +595,46 @@ def test_genome_pipeline_equals_the_single_call_path(ctx):
         pipe.close()
 
 
+def test_genome_pipeline_refuses_bad_calls(ctx):
+    """hcnv_genome_run's argument checks: output arrays that are too small or missing, a contig whose length differs from the
+    layout, regions (they belong to the sharded step), and a failed sample leaves the pipeline usable."""
+    from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
+    import dataclasses
+    g = synth.make_genome(coverage=30, scale=0.002, device="cpu", contigs=["chr21", "chrY"], seed=9)
+    hc = synth.to_api_contigs(g, host=True, compact=True, compact_observations=True)
+    pipe = GenomePipeline(0, workers=2, groups=2)
+    try:
+        small = GenomeOutput([c.length // 2 for c in g], 100)
+        with pytest.raises(H.HcnvError) as ei:
+            pipe.run(hc, out=small, max_block_len=150)
+        assert ei.value.status == L.HCNV_E_CAPACITY
+        bad = GenomeOutput([c.length for c in g], 100, implicit_bins=True)
+        bad.struct.run_rows = None
+        with pytest.raises(H.HcnvError) as ei:
+            pipe.run(hc, out=bad, max_block_len=150)
+        assert ei.value.status == L.HCNV_E_INVALID
+        with pytest.raises(H.HcnvError) as ei:
+            pipe.run([dataclasses.replace(hc[0], region_first_bin=64), hc[1]], max_block_len=150)
+        assert ei.value.status == L.HCNV_E_INVALID
+        o = pipe.begin([c.length for c in g], max_block_len=150)
+        with pytest.raises(H.HcnvError):
+            pipe.push([0], [hc[1]])                                      # chrY's records under chr21's index: the lengths differ
+        pipe.push([0], [hc[0]])
+        pipe.end()
+        assert int(o.n_bins[0]) > 0 and int(o.n_bins[1]) == 0            # the sample goes on without the refused group
+        # a damaged wire stream fails the sample with the kernel's verdict, and the next sample runs
+        w = H.wire_contig(hc[0])
+        dmg = dataclasses.replace(w, wside_offsets=w.wside_offsets.copy())
+        dmg.wside_offsets[1] += 3
+        with pytest.raises(H.HcnvError) as ei:
+            pipe.run([dmg, hc[1]], max_block_len=150)
+        assert ei.value.status == L.HCNV_E_RANGE
+        rs = pipe.run([w, hc[1]], max_block_len=150)
+        assert rs[0].n_bins == int(o.n_bins[0]) and rs[0].status >= 0
+    finally:
+        pipe.close()
+
+
 def _random_contig(rng, length, n_reads, read_len, n_snp, pile=None):
     """blocks (sorted), snp table and consistent observations for one contig; optional pile-up (pos, count)."""
     starts = rng.integers(0, max(1, length - read_len), n_reads)
