@@ -1248,10 +1248,28 @@ int hcnv_seg_plan_p1_impl(hcnv_seg_plan* pl)
     k_vit_p0c_par<2><<<pl->n * P0C_K, P0C_T, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->alpha, pl->d_tf, pl->d_epred, pl->d_scan);
     KT_END(ctx, HCNV_K_VIT_P0C);
     KT_BEGIN(ctx, HCNV_K_VIT_P1);
-    k_vit_p1<false><<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_tielist, pl->d_tiecnt);
-    k_vit_p1<true><<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_tielist, pl->d_tiecnt);
+    k_vit_p1<false><<<gs, 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags, pl->d_tielist, pl->d_tiecnt,
+                                                 0, 0, 1, nullptr, nullptr);
+    // the segments that met a tie, in quarters: their matrices go where the float matrices of P0 were (144 B per segment, dead after
+    // P0c: room for the quarters of one segment in eight); a list longer than that finishes in the whole-segment form
+    const int NQ = 4;
+    const int S = pl->total_segs;
+    const int cap = (int)std::min<size_t>((size_t)S, (size_t)144 * (size_t)S / ((size_t)NQ * (72 * 4 + 4)));
+    int* Tq = reinterpret_cast<int*>(pl->d_tf);
+    int* Tqf = Tq + (size_t)cap * NQ * 72;
+    if (cap > 0) {
+        k_vit_p1<true><<<(unsigned)(((size_t)cap * NQ + 127) / 128), 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags,
+                                                                                              pl->d_tielist, pl->d_tiecnt, 0, cap, NQ, Tq, Tqf);
+        k_vit_p1_join<<<(unsigned)((cap + 63) / 64), 64, 0, ctx->stream>>>(pl->d_tielist, pl->d_tiecnt, cap, NQ, Tq, Tqf, pl->d_ti, pl->d_flags);
+        ctx->launches += 2;
+    }
+    if (S > cap) {
+        k_vit_p1<true><<<(unsigned)(((size_t)(S - cap) + 127) / 128), 128, 0, ctx->stream>>>(pl->dprobs, pl->d_segbase, pl->n, pl->total_segs, pl->VSEG, pl->alpha, pl->d_epred, pl->d_ti, pl->d_flags,
+                                                                                             pl->d_tielist, pl->d_tiecnt, cap, S, 1, nullptr, nullptr);
+        ctx->launches++;
+    }
     KT_END(ctx, HCNV_K_VIT_P1);
-    ctx->launches += 3;
+    ctx->launches += 2;
     HCNV_CUDA(ctx, cudaGetLastError());
     return HCNV_OK;
 }

@@ -176,6 +176,28 @@ __device__ __forceinline__ void imat_load(const int* __restrict__ g, int* T) {
     for (int i = 0; i < 18; ++i) { int4 v = __ldg(q + i); T[4 * i] = v.x; T[4 * i + 1] = v.y; T[4 * i + 2] = v.z; T[4 * i + 3] = v.w; }
 }
 
+// P1, second pass in quarters (k_vit_p1<true> with nq = 4): one thread per listed segment composes its quarters' matrices, in order
+__global__ void __launch_bounds__(64) k_vit_p1_join(const int* __restrict__ tie_list, const int* __restrict__ tie_count, int cap, int nq,
+                                                    const int* __restrict__ Tq, const int* __restrict__ Tqf, int* __restrict__ Ti, int* __restrict__ flags) {
+    const int entry = blockIdx.x * blockDim.x + threadIdx.x;
+    if (entry >= min(*tie_count, cap)) return;
+    const int g = tie_list[entry];
+    int R[72], T[72];
+    imat_load(Tq + (size_t)entry * nq * 72, R);
+    int st = Tqf[(size_t)entry * nq];
+    for (int q = 1; q < nq; ++q) {
+        imat_load(Tq + ((size_t)entry * nq + q) * 72, T);
+        imat_mul_right(R, T);
+        st |= Tqf[(size_t)entry * nq + q];
+    }
+    bool bad = (st & 1) != 0;
+    int* out = Ti + (size_t)g * 72;
+    #pragma unroll
+    for (int i = 0; i < 72; ++i) { out[i] = R[i]; bad |= R[i] >= (V_INF_I >> 1); }
+    flags[g] = bad ? 0 : 1;
+    atomicAdd(&g_vdbg[0], 1); if (st & 1) atomicAdd(&g_vdbg[1], 1); if (bad && !(st & 1)) atomicAdd(&g_vdbg[2], 1); if (st & 2) atomicAdd(&g_vdbg[3], 1);
+}
+
 __global__ void __launch_bounds__(64) k_vit_p1b(SegDev* probs, const int* __restrict__ seg_base, const int* __restrict__ chunk_base,
                                                 int n_probs, int total_chunks, const int* __restrict__ epred,
                                                 const int* __restrict__ Ti, const int* __restrict__ flags, const int* __restrict__ force,

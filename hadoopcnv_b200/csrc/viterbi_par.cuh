@@ -226,13 +226,24 @@ __device__ __forceinline__ void vadd(int q, bool tie, int& inc, int& par) {
 // Two instantiations: FULL = false runs every segment with the one matrix that is enough as long as no addend is an exact
 // half-unit tie (92 % of the segments; half the registers, so more resident warps) and hands a segment that meets a tie
 // over to a work list; FULL = true redoes the listed segments with both parity variants.
+// The second pass has few threads (8 % of the segments) that each walk a whole segment with twice the state: two thread lifetimes
+// per batch whatever its size.  So a listed segment may be walked by `nq` threads, a QUARTER of its markers each (nq = 4; the
+// matrices of consecutive markers compose associatively, parity rows included): list entries [tie_lo, tie_hi) of this launch, thread
+// t -> entry tie_lo + t / nq, quarter t % nq, its 72-word matrix and a status word to Tq / Tqf; k_vit_p1_join (viterbi_chain.cuh)
+// composes the quarters into Ti.  nq = 1 is the whole-segment form (entries that do not fit the quarter scratch).
 template <bool FULL>
 __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __restrict__ seg_base, int n_probs, int total_segs,
                                                 int VSEG, float alpha, const int* __restrict__ epred,
                                                 int* __restrict__ Ti, int* __restrict__ flags,
-                                                int* __restrict__ tie_list, int* __restrict__ tie_count) {
+                                                int* __restrict__ tie_list, int* __restrict__ tie_count,
+                                                int tie_lo, int tie_hi, int nq, int* __restrict__ Tq, int* __restrict__ Tqf) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (FULL) { if (g >= *tie_count) return; g = tie_list[g]; }
+    int quarter = 0, entry = 0;
+    if (FULL) {
+        entry = tie_lo + g / nq; quarter = g % nq;
+        if (entry >= min(*tie_count, tie_hi)) return;
+        g = tie_list[entry];
+    }
     if (g >= total_segs) return;
     int pi = find_prob(seg_base, n_probs, g);
     SegDev& P = probs[pi];
@@ -241,7 +252,8 @@ __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __rest
     if (e < 0 || P.irregular) { flags[g] = 0; return; }
     const int s = g - seg_base[pi];
     const long long M = P.M;
-    const long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
+    long long a = P.m0 + (long long)s * VSEG, b = min(M, a + VSEG);
+    if (FULL && nq > 1) { const int ql = (VSEG + nq - 1) / nq; a = min(b, a + (long long)quarter * ql); b = min(b, a + ql); }   // (an empty quarter leaves the identity)
     const VitConsts k = make_consts(alpha, P.l1u, P.l2u);
     const float scale = __int_as_float((127 + 23 - e) << 23);
     bool ovf = false, const_tie = false;
@@ -330,6 +342,15 @@ __global__ void __launch_bounds__(128) k_vit_p1(SegDev* probs, const int* __rest
             tied(v0, 0);
             tied(v1, 1);
         }
+    }
+    if (FULL && nq > 1) {
+        int* out = Tq + ((size_t)(entry - tie_lo) * nq + quarter) * VT_WORDS;
+        #pragma unroll
+        for (int i = 0; i < 6; ++i)
+            #pragma unroll
+            for (int c = 0; c < 6; ++c) { out[i * 6 + c] = v0[i][c]; out[36 + i * 6 + c] = split ? v1[i][c] : v0[i][c]; }
+        Tqf[(size_t)(entry - tie_lo) * nq + quarter] = (ovf ? 1 : 0) | (split ? 2 : 0);
+        return;
     }
     int* out = Ti + (size_t)g * VT_WORDS;
     bool bad = ovf;
