@@ -173,6 +173,32 @@ def test_compact_block_stream_round_trip():
     assert len(cb0) == 0 and len(an0) == 0
 
 
+def test_implicit_start_end_columns_expand_on_the_host():
+    """hcnv_expand_start_end (host, no GPU): runs of consecutive full bins + the rows that are not full -> the start / end columns
+    of results.txt (hcnv_results_download's implicit form); rows may be listed in any order; bad lists are refused."""
+    import ctypes as C
+    lib = L.lib()
+    W, n = 100, 12
+    # bins 0, 100, 200 | 1000 .. 1400 | 5000, 5100, 5200, 5300; bin 0 starts at 1; row 4 is cut short, row 11 is the contig's last
+    bins = np.array([0, 100, 200, 1000, 1100, 1200, 1300, 1400, 5000, 5100, 5200, 5300], np.int32)
+    start = np.maximum(bins, 1).astype(np.int32); end = (bins + W - 1).astype(np.int32)
+    start[4], end[4] = 1117, 1180
+    end[11] = 5342
+    run_rows = np.array([8, 0, 3], np.int32); run_bins = np.array([5000, 0, 1000], np.int32)       # any order
+    se_rows = np.array([11, 4], np.int32); se_vals = np.array([[5300, 5342], [1117, 1180]], np.int32)
+    st, en = np.empty(n, np.int32), np.empty(n, np.int32)
+    rc = lib.hcnv_expand_start_end(n, W, 3, run_rows.ctypes.data, run_bins.ctypes.data, 2, se_rows.ctypes.data, se_vals.ctypes.data, st.ctypes.data, en.ctypes.data)
+    assert rc == 0 and (st == start).all() and (en == end).all()
+    # row 0 must begin a run; listed rows must exist
+    rc = lib.hcnv_expand_start_end(n, W, 2, run_rows[[0, 2]].copy().ctypes.data, run_bins[[0, 2]].copy().ctypes.data, 0, None, None, st.ctypes.data, en.ctypes.data)
+    assert rc == L.HCNV_E_RANGE
+    bad = np.array([12, 4], np.int32)
+    rc = lib.hcnv_expand_start_end(n, W, 3, run_rows.ctypes.data, run_bins.ctypes.data, 2, bad.ctypes.data, se_vals.ctypes.data, st.ctypes.data, en.ctypes.data)
+    assert rc == L.HCNV_E_RANGE
+    assert lib.hcnv_expand_start_end(0, W, 0, None, None, 0, None, None, None, None) == 0
+    assert lib.hcnv_expand_start_end(n, 0, 3, run_rows.ctypes.data, run_bins.ctypes.data, 0, None, None, st.ctypes.data, en.ctypes.data) == L.HCNV_E_INVALID
+
+
 def test_wire_observation_stream_round_trip():
     """hcnv_wire_obs (host, no GPU): 1 byte per observation, a 4-bit index relative to the group's anchor, groups closed early
     where 256 consecutive observations span more than 15 sites."""
