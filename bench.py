@@ -432,7 +432,8 @@ def run_b200(args):
         launches_of = lambda: (pipe.kernel_launches if pipe is not None else 0) + (ctx_p.kernel_launches if sgp is not None else 0)
         how = ("pinned host inputs (block stream: %s) -> results.txt columns in pinned host arrays (int8 calls, MSE rows listed where non-zero).  Whole chromosomes: hcnv_genome_run "
                "(one C-ABI call: continuous upload in 64 MB pieces, %d worker contexts, tasks of chromosomes: hcnv_bin_contigs -> hcnv_bins_to_hmm_input -> "
-               "hcnv_segment_batch -> hcnv_download_results)%s" % ("hcnv_wblock wire form, ~0.85 B per record, expanded on the device" if args.e2e_stream == "wire" else "hcnv_cblock, 2 B per record", args.e2e_workers, "; parts of the chromosomes cut across ranks: upload -> region binning -> boundary "
+               "hcnv_segment_batch -> hcnv_download_results)%s" % (("hcnv_wblock wire form, ~0.85 B per record, expanded on the device; observations hcnv_wobs, 1 B each" if args.e2e_stream == "wire" else "hcnv_cblock, 2 B per record; observations hcnv_cobs, 2 B each")
+                  + ("; output: start / end in their implicit form (runs of full bins + exceptions), no cn column (a look-up of state)" if args.e2e_output == "implicit" else "; output: dense start / end / cn columns"), args.e2e_workers, "; parts of the chromosomes cut across ranks: upload -> region binning -> boundary "
                "exchange over NCCL -> download, concurrently; every rank keeps its rows (one part file per rank)" if any_parts else ""))
         for _ in range(2):
             step_e2e()
