@@ -105,7 +105,7 @@ class Config(C.Structure):
 
 # every symbol include/hcnv.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "hcnv_abi_sizes", "hcnv_ctx_create", "hcnv_ctx_destroy", "hcnv_last_error", "hcnv_strerror", "hcnv_version", "hcnv_ctx_stream",
+    "hcnv_abi_sizes", "hcnv_abi_sizes2", "hcnv_ctx_create", "hcnv_ctx_destroy", "hcnv_last_error", "hcnv_strerror", "hcnv_version", "hcnv_ctx_stream",
     "hcnv_ctx_kernel_launches", "hcnv_ctx_synchronize", "hcnv_ctx_kernel_ms", "hcnv_ctx_set_kernel_timing", "hcnv_ctx_stat", "hcnv_bin_params_default", "hcnv_bin_contigs",
     "hcnv_bins_to_hmm_input", "hcnv_segment_batch", "hcnv_download_results", "hcnv_expand_start_end", "hcnv_config_load", "hcnv_format_float", "hcnv_format_double",
     "hcnv_write_bins_text", "hcnv_write_results_text",

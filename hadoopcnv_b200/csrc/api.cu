@@ -72,6 +72,10 @@ void hcnv_abi_sizes(int32_t out[7]) {
     out[3] = sizeof(hcnv_contig_input); out[4] = sizeof(hcnv_bins); out[5] = sizeof(hcnv_segment_problem); out[6] = sizeof(hcnv_config);
 }
 
+void hcnv_abi_sizes2(int32_t out[4]) {
+    out[0] = sizeof(hcnv_results_download); out[1] = sizeof(hcnv_genome_output); out[2] = sizeof(hcnv_segment_part); out[3] = sizeof(hcnv_bins);
+}
+
 const char* hcnv_strerror(int s) {
     switch (s) {
         case HCNV_OK: return "ok";

@@ -58,6 +58,8 @@ int         hcnv_version(void);
 /* sizeof of hcnv_block, hcnv_long_block, hcnv_bin_params, hcnv_contig_input, hcnv_bins, hcnv_segment_problem, hcnv_config
  * (so that a binding can verify its struct layouts) */
 void        hcnv_abi_sizes(int32_t out[7]);
+/* ... and, four entries, of hcnv_results_download, hcnv_genome_output, hcnv_segment_part and hcnv_bins once more */
+void        hcnv_abi_sizes2(int32_t out[4]);
 /* cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the caller) */
 void*       hcnv_ctx_stream(hcnv_ctx* ctx);
 /* number of kernels this context has launched so far */

@@ -40,6 +40,12 @@ def test_struct_layouts_match_header(lib):
                            C.sizeof(L.ContigInput), C.sizeof(L.Bins), C.sizeof(L.SegmentProblem), C.sizeof(L.Config)]
 
 
+def test_struct_layouts_of_the_pipeline_structs_match_header(lib):
+    sizes = (C.c_int32 * 4)()
+    lib.hcnv_abi_sizes2(sizes)
+    assert list(sizes) == [C.sizeof(L.ResultsDownload), C.sizeof(L.GenomeOutput), C.sizeof(L.SegmentPart), C.sizeof(L.Bins)]
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
