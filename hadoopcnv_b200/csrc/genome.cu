@@ -167,7 +167,6 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
     // the task's records are on the device once its last chromosome's event has fired (uploads are in order)
     if (cudaStreamWaitEvent(ctx->stream, g->landed[(size_t)gr.back()], 0) != cudaSuccess) { ctx->err = "cudaStreamWaitEvent"; fail(HCNV_E_CUDA, "wait"); return; }
     if (g->trace) { cudaStreamSynchronize(ctx->stream); t_wait = now_ms(); }
-    if (getenv("HCNV_GENOME_UPLOAD_ONLY")) { cudaStreamSynchronize(ctx->stream); return; }      // (diagnostic: the upload's own time)
     std::vector<hcnv_contig_input> in;
     for (int c : gr) in.push_back(g->dev_in[(size_t)c]);
     std::vector<int64_t> off(gr.size() + 1, 0);
@@ -212,7 +211,6 @@ static void genome_task(hcnv_genome* g, int w, const GenomeTask& task) {
             d.h_se_rows = out->se_rows + o; d.h_se_vals = out->se_vals + 2 * o; d.se_capacity = nb;
         }
     }
-    if (getenv("HCNV_GENOME_NO_DOWNLOAD")) { cudaStreamSynchronize(ctx->stream); return; }      // (diagnostic)
     rc = hcnv_download_results_many_impl(ctx, (int32_t)dl.size(), dl.data());
     if (rc) { fail(rc, "hcnv_download_results"); return; }
     for (size_t k = 0; k < live.size(); ++k) {
