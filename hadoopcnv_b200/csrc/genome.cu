@@ -2,9 +2,9 @@
 // (PennCnvSeq.java:285-350: depth caller -> binner -> one CnvReducer call per chromosome, Reducers.java:225-243), from HOST
 // buffers to the results.txt columns (Hmm.java:479-490) in HOST buffers.
 //
-// The upload bounds this path (1.4 GB per 30X genome over PCIe), so it never pauses: one copy stream sends every chromosome's
-// packed records, longest chromosome first, into device staging buffers back to back in pieces of 64 MB; the chromosomes are
-// grouped into a few tasks of about equal size, and a worker thread (one hcnv_ctx = one stream + its scratch each, like the task
+// The upload bounds this path (0.63 GB per 30X genome in the wire forms, 1.4 GB in the 2-byte forms), so it never pauses: one copy
+// stream sends every chromosome's packed records, longest chromosome first, into device staging buffers back to back in pieces of
+// at most 64 MB; the chromosomes are grouped into a few tasks of tapering size, and a worker thread (one hcnv_ctx = one stream + its scratch each, like the task
 // slots of a Hadoop node) takes a task as soon as its records have landed: hcnv_bin_contigs -> hcnv_bins_to_hmm_input ->
 // hcnv_segment_batch on device buffers, then hcnv_download_results per chromosome straight into the caller's arrays -- kernels
 // and downloads run behind the uploads of the tasks after it.  Everything the steady state needs (staging buffers, worker
@@ -27,10 +27,11 @@ struct hcnv_genome {
     cudaStream_t copy = nullptr;
     std::vector<DevBuf> stage;                    // ST_N per contig: blocks, long, snp_pos, snp_zyg, obs, cblocks, anchors, cobs, cobs_anchors, wire form (3)
     std::vector<cudaEvent_t> landed;              // one per contig
-    // The upload is PACED: pieces of piece_bytes, at most `depth` of them queued on the copy stream at any time.  With everything
-    // queued at once (1.4 GB), a copy engine that serves its queue in submission order makes every other copy of the process -- the
+    // The upload is PACED: pieces of at most piece_bytes, at most depth x piece_bytes queued on the copy stream at any time (small
+    // arrays ride along, up to the ring's size).  With everything queued at once (1.4 GB), a copy engine that serves its queue in submission order makes every other copy of the process -- the
     // workers' descriptor tables going up, the results coming down -- wait for the END of the upload: 31 ms per genome in one run,
-    // 43 - 66 ms in the next (same binary, same box).  Measured with pacing (ms per 30X genome end to end, piece MB x depth):
+    // 43 - 66 ms in the next (same binary, same box).  Measured with pacing in round 2's first form (2-byte streams; ms per 30X genome
+    // end to end, piece MB x pieces in flight):
     // 64 x 2: 32.3, 32 x 4: 32.6, 16 x 3: 32.6 - 32.7, 8 x 3: 33.6, 4 x 4: 35.4, 16 x 6: 37.4, 8 x 8: 105 (many queued pieces are
     // as bad as one huge one); HCNV_UPLOAD_PIECE_MB / HCNV_UPLOAD_DEPTH override.
     size_t piece_bytes = (size_t)64 << 20;
