@@ -199,6 +199,26 @@ def test_implicit_start_end_columns_expand_on_the_host():
     assert lib.hcnv_expand_start_end(n, 0, 3, run_rows.ctypes.data, run_bins.ctypes.data, 0, None, None, st.ctypes.data, en.ctypes.data) == L.HCNV_E_INVALID
 
 
+def test_wire_forms_known_answer_bytes():
+    """The wire formats are part of the ABI (include/hcnv.h: hcnv_wblock, hcnv_wobs): a hand-made stream against its bytes."""
+    # four records: start 10 len 150 | +3 len 150 | +14 len 7 | +15 (escape) len 150; then fillers to the end of the group
+    b = H.pack_blocks([10, 13, 27, 42], [150, 150, 7, 150], [0, 0, 0, 0])
+    cb, an = H.compact_blocks(b)
+    assert len(cb) == 128 and an.tolist() == [10]
+    w, side, off, dl = H.wire_blocks(cb)
+    assert dl == 150 and len(w) == L.HCNV_WGROUP_BYTES and off.tolist() == [0, len(side)]
+    # nibbles: record 0 carries 0 (the anchor says where the group starts), then 3, 14, 15 = escape; fillers 0
+    assert w[0] == (0 | (3 << 4)) and w[1] == (14 | (15 << 4)) and (w[2:64] == 0).all()
+    # default-length bits: records 0, 1 and 3 (bits 0, 1, 3 of byte 64); record 2 and the 124 fillers (length 0) carry their own length
+    assert w[64] == 0b00001011 and (w[65:80] == 0).all()
+    # side stream in record order: record 2's length 7, record 3's delta 15, then the fillers' lengths 0
+    assert side[:2].tolist() == [7, 15] and len(side) == 2 + 124 and (side[2:] == 0).all()
+    # observations: sites 5, 5, 6, 20 (far: closes the group of 64), bases 1, 2, 4, 8
+    wo, wan = H.wire_obs(np.array([(5 << 4) | 1, (5 << 4) | 2, (6 << 4) | 4, (20 << 4) | 8], np.uint32))
+    assert len(wo) == L.HCNV_OGROUP and wan.tolist() == [5, 20, 0, 0]
+    assert wo[:3].tolist() == [0x01, 0x02, 0x14] and (wo[3:64] == 0xF0).all() and wo[64] == 0x08 and (wo[65:] == 0xF0).all()
+
+
 def test_wire_observation_stream_round_trip():
     """hcnv_wire_obs (host, no GPU): 1 byte per observation, a 4-bit index relative to the group's anchor, groups closed early
     where 256 consecutive observations span more than 15 sites."""
