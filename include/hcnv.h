@@ -113,7 +113,7 @@ typedef uint16_t hcnv_cblock;
 #define HCNV_CGROUP 128
 
 /* The same records at about 0.85 bytes each -- the WIRE form, for a host whose upload bounds the path (one 30X genome: 0.5 GB
- * instead of 1.2 GB; the library expands it to hcnv_cblock records on the device, 0.3 ms per genome, before binning).  It is a
+ * instead of 1.2 GB; the library expands it to hcnv_cblock records on the device, ~1 ms of GPU time per genome, before binning).  It is a
  * re-encoding of the hcnv_cblock stream record for record (same count n_cblocks, same anchors).  Every group of HCNV_CGROUP
  * records is HCNV_WGROUP_BYTES bytes of wblocks:
  *   bytes 0-63   one nibble per record, record i of the group in bits 4 * (i & 1) .. of byte i / 2: its delta (0..14), or 15 =
