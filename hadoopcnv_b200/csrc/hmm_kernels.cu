@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(32) k_viterbi_seq(SegDev* probs, float alpha) 
 // Traceback codes: every lane packs its own 3-bit arg-min of VM_PACK consecutive markers into one word (no cross-lane
 // assembly): codes[c * ceil(M / VM_PACK) + m / VM_PACK], read back by k_traceback for the column s*.
 #define VM_CH 5
-#define VM_U 16
+#define VM_U 20                     // markers per register-prefetched chunk: a multiple of VM_PACK, so that the code words' bit positions are static
 #define VM_PACK 10
 #define VM_MIN_MARKERS 64
 #define VM_WARPS_PER_SM 8           // resident warps per SM of the many-chains kernel (two per scheduler)
@@ -528,7 +528,9 @@ __device__ __forceinline__ void vm_run(const float* __restrict__ sdp, const floa
     };
     fetch(1);
     int m0 = 1;
-    // whole chunks while every chain of the warp is alive: no per-marker tests
+    // whole chunks while every chain of the warp is alive: no per-marker tests.  A chunk starts at a marker = 1 (mod VM_PACK), so
+    // marker m0 + j sits at the compile-time position (1 + j) % VM_PACK of its code word: static shifts, a store where a word fills
+    static_assert(VM_U % VM_PACK == 0, "VM_U must be a multiple of VM_PACK");
     for (; m0 + VM_U <= Mmin; m0 += VM_U) {
         float csd[VM_U], cm[VM_U];
         #pragma unroll
@@ -538,11 +540,12 @@ __device__ __forceinline__ void vm_run(const float* __restrict__ sdp, const floa
         for (int j = 0; j < VM_U; ++j) {
             int arg;
             vm_step<LITERAL>(L, bad, arg, csd[j], cm[j], muc, oma, alpha, c3, c4, src);
-            word |= (uint32_t)arg << sh;
-            sh += 3;
-            if (sh == 3 * VM_PACK) { if (mycodes) mycodes[wi] = word; ++wi; word = 0; sh = 0; }
+            const int pos = (1 + j) % VM_PACK;
+            word |= (uint32_t)arg << (3 * pos);
+            if (pos == VM_PACK - 1) { if (mycodes) mycodes[wi] = word; ++wi; word = 0; }
         }
     }
+    // (sh is still 3 here: the next marker is again = 1 (mod VM_PACK), and `word` holds position 0 of its word)
     // the rest: chains end at different markers
     for (; m0 < Mmax; m0 += VM_U) {
         float csd[VM_U], cm[VM_U];
