@@ -49,24 +49,26 @@ def main():
     for label, th in (("1_thread", 1), ("all_threads", a.threads)):
         stats = {}
         t0 = time.perf_counter()
-        names, contigs, maxlens, nrec = hostio.pack_bam(bam, snps, compact=True, threads=th, stats=stats)
+        names, contigs, maxlens, nrec = hostio.pack_bam(bam, snps, wire=True, threads=th, stats=stats)        # (wire forms: what hcnv_genome_run uploads)
         dt = time.perf_counter() - t0
         assert nrec == st["records"]
         out["pack_" + label] = {"threads": stats["threads"], "seconds": round(dt, 3), "reads_per_s": nrec / dt, "inflated_GB_per_s": stats["bytes_inflated"] / dt / 1e9,
                                 "seconds_in_hcnv_bam_pack": round(stats["seconds"], 3)}
     out["inflated_bytes"] = stats["bytes_inflated"]
-    out["packed_bytes"] = int(sum((0 if c.cblocks is None else c.cblocks.nbytes + c.anchors.nbytes) + (0 if c.cobs is None else c.cobs.nbytes + c.cobs_anchors.nbytes) for c in contigs))
+    nb_ = lambda *xs: sum(0 if x is None else int(x.nbytes) for x in xs)
+    out["packed_bytes"] = int(sum(nb_(c.wblocks, c.wside, c.wside_offsets, c.anchors, c.wobs, c.cobs_anchors, c.cblocks, c.cobs) for c in contigs))
     try:
         import torch
         gpu = torch.cuda.is_available()
     except Exception:
         gpu = False
     if gpu:
-        from hadoopcnv_b200.pipeline import GenomePipeline
+        from hadoopcnv_b200.pipeline import GenomePipeline, GenomeOutput
         pipe = GenomePipeline(0, workers=3, groups=3)
+        gout = GenomeOutput([c.length for c in contigs], 100, want_cn=False, implicit_bins=True)
         for rep in range(2):                                               # (the first run allocates the staging buffers)
             t0 = time.perf_counter()
-            rs = pipe.run(contigs, names, max_block_len=max(maxlens + [1]))
+            rs = pipe.run(contigs, names, gout, max_block_len=max(maxlens + [1]))
             t_gpu = time.perf_counter() - t0
         o = pipe.last_output
         t0 = time.perf_counter()
@@ -75,8 +77,9 @@ def main():
         rows = 0
         for i, r in enumerate(rs):
             sl = slice(r.offset, r.offset + r.n_bins)
-            H.write_results_text(res_path, r.name, o.start[sl].numpy(), o.end[sl].numpy(), o.scaled[sl].numpy(), o.state[sl].numpy().astype(np.int32),
-                                 o.cn[sl].numpy().astype(np.int32), o.dense_mse(i), append=True)
+            st_, en_ = o.start_end(i)                                         # (implicit start / end: expanded by hcnv_expand_start_end)
+            H.write_results_text(res_path, r.name, st_, en_, o.scaled[sl].numpy(), o.state[sl].numpy().astype(np.int32),
+                                 None, o.dense_mse(i), append=True)        # (cn: looked up from the state by the writer)
             rows += r.n_bins
         t_text = time.perf_counter() - t0
         out["gpu"] = {"hcnv_genome_run_s": round(t_gpu, 4), "results_txt_rows": rows, "results_txt_write_s": round(t_text, 2),
